@@ -1,0 +1,106 @@
+"""ctypes binding of libacx.so (the C ABI in include/acx.h).
+
+The library is the product: if it is missing or does not load, importing anything that computes
+raises - there is no CPU or PyTorch fallback.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libacx.so")
+
+MAX_PLANES = 3
+
+
+class AcxError(RuntimeError):
+    pass
+
+
+class Planes(ctypes.Structure):
+    _fields_ = [("planes", ctypes.c_void_p * MAX_PLANES), ("num_planes", ctypes.c_int),
+                ("rows", ctypes.c_int), ("cols", ctypes.c_int), ("ld", ctypes.c_int)]
+
+
+class Gemm(ctypes.Structure):
+    _fields_ = [("a", Planes), ("b", Planes), ("trans_a", ctypes.c_int), ("trans_b", ctypes.c_int),
+                ("m", ctypes.c_int), ("n", ctypes.c_int), ("k", ctypes.c_int),
+                ("num_pairs", ctypes.c_int), ("pair_a", ctypes.c_int * 6), ("pair_b", ctypes.c_int * 6),
+                ("alpha", ctypes.c_float), ("bias", ctypes.c_void_p), ("relu", ctypes.c_int),
+                ("symmetric", ctypes.c_int),
+                ("c", ctypes.c_void_p), ("ldc", ctypes.c_int),
+                ("c_planes", ctypes.c_void_p * MAX_PLANES), ("c_num_planes", ctypes.c_int), ("ldc_planes", ctypes.c_int),
+                ("mask_plane", ctypes.c_void_p), ("mask_ld", ctypes.c_int), ("mask_rows", ctypes.c_int),
+                ("splits", ctypes.c_int), ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t)]
+
+
+class LearnerConfig(ctypes.Structure):
+    _fields_ = [("num_envs", ctypes.c_int), ("num_steps", ctypes.c_int), ("num_actions", ctypes.c_int),
+                ("conv3_filters", ctypes.c_int), ("acktr", ctypes.c_int),
+                ("gamma", ctypes.c_float), ("entropy_beta", ctypes.c_float), ("value_loss_weight", ctypes.c_float),
+                ("lr_start", ctypes.c_float), ("lr_end", ctypes.c_float), ("lr_decay_steps", ctypes.c_double),
+                ("cov_ema_decay", ctypes.c_float), ("damping", ctypes.c_float), ("momentum", ctypes.c_float),
+                ("norm_constraint", ctypes.c_float),
+                ("invert_every", ctypes.c_int), ("num_cold_updates", ctypes.c_int),
+                ("cold_lr", ctypes.c_float), ("cold_momentum", ctypes.c_float), ("clip_norm", ctypes.c_float),
+                ("rms_decay", ctypes.c_float), ("rms_epsilon", ctypes.c_float),
+                ("num_locations_mode", ctypes.c_int), ("world_size", ctypes.c_int), ("gemm_impl", ctypes.c_int),
+                ("seed", ctypes.c_uint64)]
+
+
+# every symbol include/acx.h declares: name -> (restype, argtypes)
+_P = ctypes.c_void_p
+SIGNATURES = {
+    "acx_last_error": (ctypes.c_char_p, []),
+    "acx_version": (ctypes.c_int, []),
+    "acx_launch_count": (ctypes.c_uint64, []),
+    "acx_reset_launch_count": (None, []),
+    "acx_preprocess_stack_u8": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, ctypes.c_int, _P]),
+    "acx_preprocess_reset_u8": (ctypes.c_int, [_P, _P, ctypes.c_size_t, ctypes.c_int, _P]),
+    "acx_returns_adv": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_float, ctypes.c_int, ctypes.c_int, _P, _P, _P]),
+    "acx_gemm": (ctypes.c_int, [ctypes.POINTER(Gemm), ctypes.c_int, _P]),
+    "acx_gemm_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(Gemm)]),
+    "acx_split_planes": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                        ctypes.POINTER(_P), ctypes.c_int, ctypes.c_int, _P]),
+    "acx_debug_set_mn_desc": (None, [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]),
+    "acx_learner_arena_bytes": (ctypes.c_size_t, [ctypes.POINTER(LearnerConfig)]),
+    "acx_learner_create": (_P, [ctypes.POINTER(LearnerConfig), _P, ctypes.c_size_t]),
+    "acx_learner_destroy": (None, [_P]),
+    "acx_learner_num_params": (ctypes.c_size_t, [_P]),
+    "acx_learner_set_params": (ctypes.c_int, [_P, _P, _P]),
+    "acx_learner_get_params": (ctypes.c_int, [_P, _P, _P]),
+    "acx_learner_buffer": (_P, [_P, ctypes.c_char_p, ctypes.POINTER(ctypes.c_size_t)]),
+    "acx_learner_obs_buffer": (_P, [_P, ctypes.POINTER(ctypes.c_size_t)]),
+    "acx_learner_phase1": (ctypes.c_int, [_P, _P, _P, _P]),
+    "acx_learner_phase2": (ctypes.c_int, [_P, _P]),
+    "acx_learner_global_step": (ctypes.c_int64, [_P]),
+    "acx_learner_set_global_step": (None, [_P, ctypes.c_int64]),
+    "acx_learner_act": (ctypes.c_int, [_P, _P, ctypes.c_int, _P, ctypes.c_int, _P, _P, _P, _P]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libacx.so (building nothing: run `python __graft_entry__.py` / csrc/build.py first)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AcxError("libacx.so not found at %s - build it with actorcritic_b200/csrc/build.py "
+                       "(there is no CPU fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is missing
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status != 0:
+        raise AcxError(load().acx_last_error().decode("utf-8", "replace"))
+
+
+def launch_count():
+    return int(load().acx_launch_count())

@@ -1,0 +1,712 @@
+// gemm.cu - GEMM on bf16 planes for sm_100a: TMA -> shared memory (128B swizzle) -> tcgen05.mma with
+// the fp32 accumulator in TMEM -> tcgen05.ld epilogue.  One kernel serves every matrix product of the
+// learner (conv/fc forward as im2col GEMMs, dgrad, wgrad, K-FAC factor SYRKs, preconditioning); the
+// precision is chosen per call by how many bf16 plane pairs are accumulated (1 = bf16, 3 ~ 2^-17,
+// 6 = fp32-class) - see DESIGN.md "precision by plane pairs".
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..5 = epilogue (one TMEM lane quarter each).
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+
+namespace acx {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int A_TILE_BYTES = BM * BK * 2;
+
+struct OutParams {
+  int m, n;
+  float alpha;
+  const float* bias;
+  int relu;
+  float* c;
+  int ldc;
+  bf16* cp[ACX_MAX_PLANES];
+  int c_num_planes;
+  int ldcp;
+  const bf16* mask;
+  int mask_ld, mask_rows;
+};
+
+struct TcParams {
+  OutParams out;
+  int k;
+  int kb_total, kb_per_split;
+  int num_pairs;
+  int pair_a[6], pair_b[6];
+  int symmetric;
+  int to_workspace;
+  float* ws;
+  int ws_ld;
+  long long ws_split_stride;  // floats
+  uint32_t mn_lbo, mn_sbo, mn_kstep;
+};
+
+__device__ int g_tc_error = 0;
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a wrong barrier protocol must not hang the GPU box (records an error and moves on)
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) {  // ~2 s
+      atomicExch(&g_tc_error, code);
+      return;
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor (SWIZZLE_128B, sm_100 "version 1")
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;
+  d |= 2ull << 61;
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared epilogue: one result element (or a run of them) -> fp32 C and/or bf16 planes
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float finish_value(const OutParams& o, int m, int n, float acc) {
+  float v = o.alpha * acc;
+  if (o.bias) v += __ldg(o.bias + n);
+  if (o.relu) v = fmaxf(v, 0.0f);
+  if (o.mask) {
+    float mk = __bfloat162float(o.mask[(size_t)(m % o.mask_rows) * o.mask_ld + n]);
+    if (!(mk > 0.0f)) v = 0.0f;
+  }
+  return v;
+}
+__device__ __forceinline__ void store_value(const OutParams& o, int m, int n, float v) {
+  if (o.c) o.c[(size_t)m * o.ldc + n] = v;
+  if (o.c_num_planes > 0) {
+    bf16 p0, p1, p2;
+    split3(v, p0, p1, p2);
+    size_t idx = (size_t)m * o.ldcp + n;
+    o.cp[0][idx] = p0;
+    if (o.c_num_planes > 1) o.cp[1][idx] = p1;
+    if (o.c_num_planes > 2) o.cp[2][idx] = p2;
+  }
+}
+
+// a thread owns 32 consecutive columns [n_base, n_base+32) of row m
+__device__ __forceinline__ void store_run32(const OutParams& o, int m, int n_base, const float* v) {
+  if (m >= o.m) return;
+  const bool full = (n_base + 32 <= o.n);
+  if (o.c) {
+    float* dst = o.c + (size_t)m * o.ldc + n_base;
+    if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+      for (int j = 0; j < 32; ++j)
+        if (n_base + j < o.n) dst[j] = v[j];
+    }
+  }
+  if (o.c_num_planes > 0) {
+    size_t idx = (size_t)m * o.ldcp + n_base;
+    const bool vec = full && ((o.ldcp & 7) == 0) && ((n_base & 7) == 0);
+#pragma unroll
+    for (int pl = 0; pl < ACX_MAX_PLANES; ++pl) {
+      if (pl >= o.c_num_planes) break;
+      bf16* dst = o.cp[pl] + idx;
+      if (vec && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          __align__(16) bf16 t[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            bf16 p0, p1, p2;
+            split3(v[j + q], p0, p1, p2);
+            t[q] = pl == 0 ? p0 : (pl == 1 ? p1 : p2);
+          }
+          *reinterpret_cast<uint4*>(dst + j) = *reinterpret_cast<uint4*>(t);
+        }
+      } else {
+        for (int j = 0; j < 32; ++j)
+          if (n_base + j < o.n) {
+            bf16 p0, p1, p2;
+            split3(v[j], p0, p1, p2);
+            dst[j] = pl == 0 ? p0 : (pl == 1 ? p1 : p2);
+          }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the tcgen05 kernel.  MAJOR 0: A stored [M,K], B stored [N,K] (both K-major).
+//                      MAJOR 1: A stored [K,M], B stored [K,N] (both MN-major).
+// ------------------------------------------------------------------------------------------------
+template <int BN, int MAJOR, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ CUtensorMap ta1,
+               const __grid_constant__ CUtensorMap ta2, const __grid_constant__ CUtensorMap tb0,
+               const __grid_constant__ CUtensorMap tb1, const __grid_constant__ CUtensorMap tb2, const TcParams p) {
+  constexpr int B_TILE_BYTES = BN * BK * 2;
+  constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  static_assert(MAJOR == 0 || BN % 64 == 0, "MN-major tiles are built from 64-column swizzle atoms");
+
+  const int tile_n = blockIdx.x, tile_m = blockIdx.y, split = blockIdx.z;
+  if (p.symmetric && tile_m > tile_n) return;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = tile_m * BM, n0 = tile_n * BN;
+  const int kb0 = split * p.kb_per_split;
+  const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+  const int nkb = kb1 - kb0;
+  const int iters = nkb * p.num_pairs;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u, 1);
+        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+        const int pr = it / nkb, kb = kb0 + it % nkb;
+        const int pa = p.pair_a[pr], pb = p.pair_b[pr];
+        const CUtensorMap* ma = pa == 0 ? &ta0 : (pa == 1 ? &ta1 : &ta2);
+        const CUtensorMap* mb = pb == 0 ? &tb0 : (pb == 1 ? &tb1 : &tb2);
+        uint8_t* a_s = smem + s * STAGE_BYTES;
+        uint8_t* b_s = a_s + A_TILE_BYTES;
+        if (MAJOR == 0) {
+          tma_load_2d(a_s, ma, &full_bar[s], kb * BK, m0);
+          tma_load_2d(b_s, mb, &full_bar[s], kb * BK, n0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BM / 64; ++j) tma_load_2d(a_s + j * (BK * 128), ma, &full_bar[s], m0 + 64 * j, kb * BK);
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_s + j * (BK * 128), mb, &full_bar[s], n0 + 64 * j, kb * BK);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one elected lane) =====
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)MAJOR << 15) | ((uint32_t)MAJOR << 16) |
+                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const uint32_t lbo = MAJOR == 0 ? 16u : p.mn_lbo;
+    const uint32_t sbo = MAJOR == 0 ? 1024u : p.mn_sbo;
+    const uint32_t kstep = MAJOR == 0 ? 32u : p.mn_kstep;
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      mbar_wait(&full_bar[s], ph, 2);
+      tc_fence_after();
+      if (lane == 0) {
+        const int kb = kb0 + it % nkb;
+        const int kvalid = min(BK, p.k - kb * BK);
+        const int ksteps = (kvalid + 15) >> 4;
+        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t b_addr = a_addr + A_TILE_BYTES;
+        for (int kk = 0; kk < ksteps; ++kk) {
+          const uint64_t ad = make_smem_desc(a_addr + kk * kstep, lbo, sbo);
+          const uint64_t bd = make_smem_desc(b_addr + kk * kstep, lbo, sbo);
+          umma_bf16(tmem_base, ad, bd, idesc, (it | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
+      }
+      __syncwarp();
+    }
+    if (lane == 0) umma_commit(tmem_full_bar);
+    __syncwarp();
+  } else {
+    // ===== epilogue: TMEM -> registers -> global =====
+    mbar_wait(tmem_full_bar, 0, 3);
+    tc_fence_after();
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int m = m0 + row;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t raw[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, raw);
+      float v[32];
+      if (p.to_workspace) {
+        float* dst = p.ws + (size_t)split * p.ws_split_stride + (size_t)m * p.ws_ld + n0 + c0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]),
+                                                            __uint_as_float(raw[j + 2]), __uint_as_float(raw[j + 3]));
+      } else {
+        if (m < p.out.m) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = n0 + c0 + j;
+            v[j] = n < p.out.n ? finish_value(p.out, m, n, __uint_as_float(raw[j])) : 0.0f;
+          }
+          store_run32(p.out, m, n0 + c0, v);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// reduce split-K partials (and mirror symmetric results), then the shared epilogue
+__global__ void gemm_finalize_kernel(OutParams o, const float* ws, int ws_ld, long long ws_split_stride, int splits,
+                                     int symmetric, int bm, int bn) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (n >= o.n || m >= o.m) return;
+  int mm = m, nn = n;
+  if (symmetric && (m / bm) > (n / bn)) {
+    mm = n;
+    nn = m;
+  }
+  const float* src = ws + (size_t)mm * ws_ld + nn;
+  float acc = 0.0f;
+  for (int s = 0; s < splits; ++s) acc += src[(size_t)s * ws_split_stride];
+  store_value(o, m, n, finish_value(o, m, n, acc));
+}
+
+// ------------------------------------------------------------------------------------------------
+// SIMT fp32 reference on the same planes (validation / debug only)
+// ------------------------------------------------------------------------------------------------
+struct SimtParams {
+  OutParams out;
+  const bf16* a[ACX_MAX_PLANES];
+  const bf16* b[ACX_MAX_PLANES];
+  int lda, ldb, trans_a, trans_b, k;
+  int num_pairs;
+  int pair_a[6], pair_b[6];
+};
+
+__global__ void __launch_bounds__(256) gemm_simt_kernel(SimtParams p) {
+  __shared__ float as[16][65];
+  __shared__ float bs[16][65];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4] = {};
+  for (int pr = 0; pr < p.num_pairs; ++pr) {
+    const bf16* A = p.a[p.pair_a[pr]];
+    const bf16* B = p.b[p.pair_b[pr]];
+    for (int k0 = 0; k0 < p.k; k0 += 16) {
+      for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+        const int kk = i / 64, r = i % 64;  // generic gather; speed is irrelevant here
+        const int k = k0 + kk;
+        float av = 0.f, bv = 0.f;
+        if (k < p.k) {
+          const int m = m0 + r, n = n0 + r;
+          if (m < p.out.m) av = __bfloat162float(p.trans_a ? A[(size_t)k * p.lda + m] : A[(size_t)m * p.lda + k]);
+          if (n < p.out.n) bv = __bfloat162float(p.trans_b ? B[(size_t)k * p.ldb + n] : B[(size_t)n * p.ldb + k]);
+        }
+        as[kk][r] = av;
+        bs[kk][r] = bv;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < 16; ++kk) {
+        float a4[4], b4[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          a4[i] = as[kk][ty + 16 * i];
+          b4[i] = bs[kk][tx + 16 * i];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      const int m = m0 + ty + 16 * i, n = n0 + tx + 16 * j;
+      if (m < p.out.m && n < p.out.n) store_value(p.out, m, n, finish_value(p.out, m, n, acc[i][j]));
+    }
+}
+
+__global__ void split_planes_kernel(const float* __restrict__ in, int ld_in, int rows, int cols, float scale, bf16* p0,
+                                    bf16* p1, bf16* p2, int num_planes, int ld_out) {
+  const size_t total = (size_t)rows * ld_out;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / ld_out), c = (int)(i % ld_out);
+    float x = c < cols ? in[(size_t)r * ld_in + c] * scale : 0.0f;
+    bf16 a, b, d;
+    split3(x, a, b, d);
+    p0[i] = a;
+    if (num_planes > 1) p1[i] = b;
+    if (num_planes > 2) p2[i] = d;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  int rows, cols, ld, box0, box1;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box0 == o.box0 && box1 == o.box1;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    h = h * 1000003u ^ (size_t)k.rows;
+    h = h * 1000003u ^ (size_t)k.cols;
+    h = h * 1000003u ^ (size_t)k.ld;
+    h = h * 1000003u ^ (size_t)(k.box0 * 4096 + k.box1);
+    return h;
+  }
+};
+static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+static std::mutex g_maps_mu;
+
+// row-major bf16 [rows, cols] with leading dimension ld; box = box0 columns x box1 rows, 128B swizzle
+static int get_tensor_map(const void* ptr, int rows, int cols, int ld, int box0, int box1, CUtensorMap* out) {
+  MapKey key{ptr, rows, cols, ld, box0, box1};
+  std::lock_guard<std::mutex> lock(g_maps_mu);
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) {
+    *out = it->second;
+    return 0;
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  ACX_CHECK(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  ACX_CHECK((ld % 8) == 0, "plane leading dimension must be a multiple of 8 bf16 elements");
+  ACX_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "plane pointer must be 16-byte aligned");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box0, (cuuint32_t)box1};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ACX_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  if (g_maps.size() > 4096) g_maps.clear();
+  g_maps[key] = m;
+  *out = m;
+  return 0;
+}
+
+static uint32_t g_mn_lbo = 0, g_mn_sbo = 0, g_mn_kstep = 0;
+
+static void fill_out(const acx_gemm_t* g, OutParams* o) {
+  o->m = g->m;
+  o->n = g->n;
+  o->alpha = g->alpha;
+  o->bias = g->bias;
+  o->relu = g->relu;
+  o->c = g->c;
+  o->ldc = g->ldc;
+  for (int i = 0; i < ACX_MAX_PLANES; ++i) o->cp[i] = reinterpret_cast<bf16*>(g->c_planes[i]);
+  o->c_num_planes = g->c_num_planes;
+  o->ldcp = g->ldc_planes;
+  o->mask = reinterpret_cast<const bf16*>(g->mask_plane);
+  o->mask_ld = g->mask_ld;
+  o->mask_rows = g->mask_rows > 0 ? g->mask_rows : (g->m > 0 ? g->m : 1);
+}
+
+struct TcPlan {
+  int bn, tiles_m, tiles_n, splits, kb_total, kb_per_split, to_ws;
+  size_t ws_bytes;
+};
+
+static int pick_bn(const acx_gemm_t* g) {
+  if (g->symmetric) return 128;
+  if (g->trans_a) return g->n <= 64 ? 64 : 128;
+  if (g->n <= 32) return 32;
+  if (g->n <= 64) return 64;
+  return 128;
+}
+
+static void plan_tc(const acx_gemm_t* g, TcPlan* pl) {
+  pl->bn = pick_bn(g);
+  pl->tiles_m = ceil_div(g->m, BM);
+  pl->tiles_n = ceil_div(g->n, pl->bn);
+  pl->kb_total = ceil_div(g->k, BK);
+  int tiles = pl->tiles_m * pl->tiles_n;
+  if (g->symmetric) tiles = pl->tiles_n * (pl->tiles_n + 1) / 2;
+  int splits = g->splits;
+  if (splits <= 0) {  // auto: about one CTA per SM, at least 4 k-blocks per split
+    splits = 148 / (tiles > 0 ? tiles : 1);
+    int cap = pl->kb_total / 4;
+    if (splits > cap) splits = cap;
+    if (splits < 1) splits = 1;
+  }
+  if (splits > pl->kb_total) splits = pl->kb_total;
+  pl->kb_per_split = ceil_div(pl->kb_total, splits);
+  pl->splits = ceil_div(pl->kb_total, pl->kb_per_split);
+  pl->to_ws = (pl->splits > 1 || g->symmetric) ? 1 : 0;
+  pl->ws_bytes = pl->to_ws ? (size_t)pl->splits * pl->tiles_m * BM * pl->tiles_n * pl->bn * sizeof(float) : 0;
+}
+
+template <int BN, int MAJOR, int STAGES>
+static int launch_tc(const CUtensorMap* ta, const CUtensorMap* tb, const TcParams& p, dim3 grid, cudaStream_t st) {
+  constexpr int smem = STAGES * (A_TILE_BYTES + BN * BK * 2) + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    ACX_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, MAJOR, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  gemm_tc_kernel<BN, MAJOR, STAGES><<<grid, 192, smem, st>>>(ta[0], ta[1], ta[2], tb[0], tb[1], tb[2], p);
+  ACX_LAUNCH_CHECK();
+  return 0;
+}
+
+static int validate(const acx_gemm_t* g) {
+  ACX_CHECK(g != nullptr, "null gemm");
+  ACX_CHECK(g->m > 0 && g->n > 0 && g->k > 0, "empty problem");
+  ACX_CHECK(g->num_pairs >= 1 && g->num_pairs <= 6, "num_pairs out of range");
+  ACX_CHECK(g->a.num_planes >= 1 && g->a.num_planes <= ACX_MAX_PLANES, "a.num_planes");
+  ACX_CHECK(g->b.num_planes >= 1 && g->b.num_planes <= ACX_MAX_PLANES, "b.num_planes");
+  for (int i = 0; i < g->num_pairs; ++i) {
+    ACX_CHECK(g->pair_a[i] >= 0 && g->pair_a[i] < g->a.num_planes, "pair_a index");
+    ACX_CHECK(g->pair_b[i] >= 0 && g->pair_b[i] < g->b.num_planes, "pair_b index");
+  }
+  ACX_CHECK(g->trans_a == g->trans_b, "only (K-major,K-major) and (MN-major,MN-major) operand pairs are supported");
+  ACX_CHECK(g->c != nullptr || g->c_num_planes > 0, "no output requested");
+  ACX_CHECK(g->c_num_planes >= 0 && g->c_num_planes <= ACX_MAX_PLANES, "c_num_planes");
+  if (g->symmetric) ACX_CHECK(g->m == g->n, "symmetric needs m == n");
+  return 0;
+}
+
+static int gemm_tc(const acx_gemm_t* g, cudaStream_t st) {
+  TcPlan pl;
+  plan_tc(g, &pl);
+  if (pl.to_ws) {
+    ACX_CHECK(g->workspace != nullptr && g->workspace_bytes >= pl.ws_bytes, "split-K / symmetric GEMM needs workspace");
+  }
+  CUtensorMap ta[3], tb[3];
+  const int major = g->trans_a ? 1 : 0;
+  for (int i = 0; i < 3; ++i) {
+    const int ia = i < g->a.num_planes ? i : 0, ib = i < g->b.num_planes ? i : 0;
+    int r;
+    if (major == 0) {
+      r = get_tensor_map(g->a.planes[ia], g->m, g->k, g->a.ld, BK, BM, &ta[i]);
+      if (r) return r;
+      r = get_tensor_map(g->b.planes[ib], g->n, g->k, g->b.ld, BK, pl.bn, &tb[i]);
+      if (r) return r;
+    } else {
+      r = get_tensor_map(g->a.planes[ia], g->k, g->m, g->a.ld, 64, BK, &ta[i]);
+      if (r) return r;
+      r = get_tensor_map(g->b.planes[ib], g->k, g->n, g->b.ld, 64, BK, &tb[i]);
+      if (r) return r;
+    }
+  }
+  TcParams p;
+  fill_out(g, &p.out);
+  p.k = g->k;
+  p.kb_total = pl.kb_total;
+  p.kb_per_split = pl.kb_per_split;
+  p.num_pairs = g->num_pairs;
+  for (int i = 0; i < 6; ++i) {
+    p.pair_a[i] = g->pair_a[i];
+    p.pair_b[i] = g->pair_b[i];
+  }
+  p.symmetric = g->symmetric;
+  p.to_workspace = pl.to_ws;
+  p.ws = g->workspace;
+  p.ws_ld = pl.tiles_n * pl.bn;
+  p.ws_split_stride = (long long)pl.tiles_m * BM * p.ws_ld;
+  p.mn_lbo = g_mn_lbo ? g_mn_lbo : (uint32_t)(BK * 128);
+  p.mn_sbo = g_mn_sbo ? g_mn_sbo : 1024u;
+  p.mn_kstep = g_mn_kstep ? g_mn_kstep : 2048u;
+  dim3 grid(pl.tiles_n, pl.tiles_m, pl.splits);
+  int r = 0;
+  if (major == 0) {
+    if (pl.bn == 32) r = launch_tc<32, 0, 6>(ta, tb, p, grid, st);
+    else if (pl.bn == 64) r = launch_tc<64, 0, 6>(ta, tb, p, grid, st);
+    else r = launch_tc<128, 0, 6>(ta, tb, p, grid, st);
+  } else {
+    if (pl.bn == 64) r = launch_tc<64, 1, 6>(ta, tb, p, grid, st);
+    else r = launch_tc<128, 1, 6>(ta, tb, p, grid, st);
+  }
+  if (r) return r;
+  if (pl.to_ws) {
+    dim3 fg(ceil_div(g->n, 256), g->m);
+    gemm_finalize_kernel<<<fg, 256, 0, st>>>(p.out, g->workspace, p.ws_ld, p.ws_split_stride, pl.splits, g->symmetric, BM,
+                                            pl.bn);
+    ACX_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+static int gemm_simt(const acx_gemm_t* g, cudaStream_t st) {
+  SimtParams p;
+  fill_out(g, &p.out);
+  for (int i = 0; i < ACX_MAX_PLANES; ++i) {
+    p.a[i] = reinterpret_cast<const bf16*>(g->a.planes[i < g->a.num_planes ? i : 0]);
+    p.b[i] = reinterpret_cast<const bf16*>(g->b.planes[i < g->b.num_planes ? i : 0]);
+  }
+  p.lda = g->a.ld;
+  p.ldb = g->b.ld;
+  p.trans_a = g->trans_a;
+  p.trans_b = g->trans_b;
+  p.k = g->k;
+  p.num_pairs = g->num_pairs;
+  for (int i = 0; i < 6; ++i) {
+    p.pair_a[i] = g->pair_a[i];
+    p.pair_b[i] = g->pair_b[i];
+  }
+  dim3 grid(ceil_div(g->n, 64), ceil_div(g->m, 64));
+  gemm_simt_kernel<<<grid, 256, 0, st>>>(p);
+  ACX_LAUNCH_CHECK();
+  return 0;
+}
+
+int gemm_dispatch(const acx_gemm_t* g, int impl, cudaStream_t st) {
+  int r = validate(g);
+  if (r) return r;
+  return impl == 1 ? gemm_simt(g, st) : gemm_tc(g, st);
+}
+
+int tc_error_flag() {
+  int v = 0;
+  cudaMemcpyFromSymbol(&v, g_tc_error, sizeof(int));
+  return v;
+}
+
+}  // namespace acx
+
+extern "C" {
+
+int acx_gemm(const acx_gemm_t* g, int impl, void* stream) {
+  return acx::gemm_dispatch(g, impl, reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t acx_gemm_workspace_bytes(const acx_gemm_t* g) {
+  acx::TcPlan pl;
+  acx::plan_tc(g, &pl);
+  return pl.ws_bytes;
+}
+
+int acx_split_planes(const float* d_in, int ld_in, int rows, int cols, float scale, void* const* d_planes, int num_planes,
+                     int ld_out, void* stream) {
+  ACX_CHECK(num_planes >= 1 && num_planes <= ACX_MAX_PLANES, "num_planes");
+  ACX_CHECK(rows > 0 && cols > 0 && ld_out >= cols, "shape");
+  const size_t total = (size_t)rows * ld_out;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  acx::split_planes_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      d_in, ld_in, rows, cols, scale, reinterpret_cast<acx::bf16*>(d_planes[0]),
+      reinterpret_cast<acx::bf16*>(num_planes > 1 ? d_planes[1] : nullptr),
+      reinterpret_cast<acx::bf16*>(num_planes > 2 ? d_planes[2] : nullptr), num_planes, ld_out);
+  ACX_LAUNCH_CHECK();
+  return 0;
+}
+
+void acx_debug_set_mn_desc(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t kstep_bytes) {
+  acx::g_mn_lbo = lbo_bytes;
+  acx::g_mn_sbo = sbo_bytes;
+  acx::g_mn_kstep = kstep_bytes;
+}
+
+int acx_debug_tc_error(void) { return acx::tc_error_flag(); }
+
+}  // extern "C"

@@ -1,0 +1,142 @@
+"""Thin torch-tensor wrappers over the C ABI (device memory and streams come from torch; every
+computation is a libacx kernel).  Used by the API layer and by the parity tests."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.AcxError("libacx operates on CUDA tensors only (no CPU fallback)")
+
+
+def preprocess_stack(raw_a, raw_b, stack_in, terminal=None, reset_mask=None, reset_raw=None, out=None,
+                     out_env_stride=None):
+    """K-PRE (include/acx.h acx_preprocess_stack_u8).  raw_*: uint8 [E,210,160,3]; stack_in uint8 [E,84,84,4].
+    `out` may be a slice of a batch-major rollout buffer; out_env_stride is then its env stride in bytes."""
+    _need_cuda(raw_a, raw_b, stack_in)
+    e = raw_a.shape[0]
+    assert raw_a.dtype == torch.uint8 and tuple(raw_a.shape[1:]) == (210, 160, 3) and raw_a.is_contiguous()
+    assert raw_b.shape == raw_a.shape and raw_b.is_contiguous() and stack_in.is_contiguous()
+    if out is None:
+        out = torch.empty((e, 84, 84, 4), dtype=torch.uint8, device=raw_a.device)
+        out_env_stride = 28224
+    elif out_env_stride is None:
+        out_env_stride = out.stride(0)
+    for t in (terminal, reset_mask):
+        assert t is None or (t.dtype == torch.uint8 and t.is_contiguous())
+    _lib.check(_lib.load().acx_preprocess_stack_u8(_ptr(raw_a), _ptr(raw_b), _ptr(terminal), _ptr(reset_mask),
+                                                   _ptr(reset_raw), _ptr(stack_in), _ptr(out),
+                                                   ctypes.c_size_t(out_env_stride), e, _stream()))
+    return out
+
+
+def preprocess_reset(raw, out=None, out_env_stride=None):
+    _need_cuda(raw)
+    e = raw.shape[0]
+    if out is None:
+        out = torch.empty((e, 84, 84, 4), dtype=torch.uint8, device=raw.device)
+        out_env_stride = 28224
+    elif out_env_stride is None:
+        out_env_stride = out.stride(0)
+    _lib.check(_lib.load().acx_preprocess_reset_u8(_ptr(raw), _ptr(out), ctypes.c_size_t(out_env_stride), e, _stream()))
+    return out
+
+
+def returns_adv(rewards, terminals, values, bootstrap_values, gamma):
+    """K-RET.  rewards f32 [E,T], terminals uint8/bool [E,T], values f32 [E,T], bootstrap f32 [E]."""
+    _need_cuda(rewards, terminals, values, bootstrap_values)
+    e, t = rewards.shape
+    term = terminals.to(torch.uint8).contiguous()
+    targets = torch.empty((e, t), dtype=torch.float32, device=rewards.device)
+    adv = torch.empty_like(targets)
+    _lib.check(_lib.load().acx_returns_adv(_ptr(rewards.contiguous()), _ptr(term), _ptr(values.contiguous()),
+                                           _ptr(bootstrap_values.contiguous()), float(gamma), e, t,
+                                           _ptr(targets), _ptr(adv), _stream()))
+    return targets, adv
+
+
+def pad8(n):
+    return (n + 7) // 8 * 8
+
+
+def split_planes(x, num_planes, scale=1.0):
+    """fp32 [rows, cols] -> list of bf16 planes [rows, pad8(cols)] with x*scale ~= sum(planes)."""
+    _need_cuda(x)
+    x = x.contiguous().float()
+    rows, cols = x.shape
+    ld = pad8(cols)
+    planes = [torch.empty((rows, ld), dtype=torch.bfloat16, device=x.device) for _ in range(num_planes)]
+    arr = (ctypes.c_void_p * num_planes)(*[p.data_ptr() for p in planes])
+    _lib.check(_lib.load().acx_split_planes(_ptr(x), x.stride(0), rows, cols, float(scale), arr, num_planes, ld, _stream()))
+    return planes
+
+
+def _planes_struct(planes, rows, cols):
+    s = _lib.Planes()
+    for i, p in enumerate(planes):
+        s.planes[i] = p.data_ptr()
+    s.num_planes = len(planes)
+    s.rows, s.cols, s.ld = rows, cols, planes[0].stride(0)
+    return s
+
+
+PAIRS = {1: [(0, 0)], 3: [(0, 0), (0, 1), (1, 0)], 6: [(0, 0), (0, 1), (1, 0), (0, 2), (2, 0), (1, 1)]}
+
+
+def gemm(a_planes, b_planes, m, n, k, trans=False, pairs=None, alpha=1.0, bias=None, relu=False, symmetric=False,
+         out_planes=0, want_f32=True, mask=None, mask_rows=0, splits=0, impl=0):
+    """C[m,n] = alpha * sum_pairs op(A_i) op(B_j) (+bias) via acx_gemm.
+    trans=False: A planes stored [m,k], B planes stored [n,k];  trans=True: A stored [k,m], B stored [k,n]."""
+    lib = _lib.load()
+    dev = a_planes[0].device
+    if pairs is None:
+        pairs = PAIRS[{1: 1, 2: 3, 3: 6}[min(len(a_planes), len(b_planes))]]
+    g = _lib.Gemm()
+    if trans:
+        g.a = _planes_struct(a_planes, k, m)
+        g.b = _planes_struct(b_planes, k, n)
+    else:
+        g.a = _planes_struct(a_planes, m, k)
+        g.b = _planes_struct(b_planes, n, k)
+    g.trans_a = g.trans_b = 1 if trans else 0
+    g.m, g.n, g.k = m, n, k
+    g.num_pairs = len(pairs)
+    for i, (pa, pb) in enumerate(pairs):
+        g.pair_a[i], g.pair_b[i] = pa, pb
+    g.alpha = alpha
+    g.bias = bias.data_ptr() if bias is not None else None
+    g.relu = int(relu)
+    g.symmetric = int(symmetric)
+    c = None
+    if want_f32:
+        c = torch.empty((m, n), dtype=torch.float32, device=dev)
+        g.c, g.ldc = c.data_ptr(), n
+    cps = []
+    if out_planes:
+        ld = pad8(n)
+        cps = [torch.zeros((m, ld), dtype=torch.bfloat16, device=dev) for _ in range(out_planes)]
+        for i, p in enumerate(cps):
+            g.c_planes[i] = p.data_ptr()
+        g.c_num_planes, g.ldc_planes = out_planes, ld
+    if mask is not None:
+        g.mask_plane, g.mask_ld, g.mask_rows = mask.data_ptr(), mask.stride(0), mask_rows or mask.shape[0]
+    g.splits = splits
+    ws_bytes = lib.acx_gemm_workspace_bytes(ctypes.byref(g))
+    ws = None
+    if ws_bytes:
+        ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)
+        g.workspace, g.workspace_bytes = ws.data_ptr(), ws_bytes
+    _lib.check(lib.acx_gemm(ctypes.byref(g), impl, _stream()))
+    return c, cps

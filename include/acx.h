@@ -1,0 +1,167 @@
+/* acx.h - C ABI of libacx.so, the B200 (sm_100a) implementation of the ACKTR learner hot path
+ * of jrobine/actor-critic.
+ *
+ * The reference has no FFI layer: its boundary is the Python API.  These entry points
+ * are what a ctypes binding inside the reference's Python modules would call; each one cites the
+ * reference code whose work it replaces.  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every pointer named d_* is a DEVICE pointer owned by the caller; h_* is a HOST pointer.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - no hidden device allocation, no host synchronisation unless the function says so.
+ *   - return value: 0 on success, non-zero on error; acx_last_error() gives the message
+ *     (thread-local).  Nothing here falls back to the CPU.
+ *   - "planes": a real matrix held as 1..3 bf16 matrices hi, mid, lo with x ~= hi + mid + lo
+ *     (bf16 split of fp32; 1 plane = bf16, 2 planes ~ 2^-17, 3 planes = fp32-exact).
+ */
+#ifndef ACX_H_
+#define ACX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACX_MAX_PLANES 3
+
+/* ---- library ------------------------------------------------------------------------------ */
+const char* acx_last_error(void);
+int acx_version(void);
+/* number of kernels this library has launched in this process since load / last reset
+ * (bench.py's "gpu_launches"). */
+uint64_t acx_launch_count(void);
+void acx_reset_launch_count(void);
+
+/* ---- K-PRE: batched Atari preprocessing + frame stack (uint8, bit-exact) ------------------- */
+/* Replaces, for E environments at once:
+ *   AtariFrameskipWrapper.step max        wrappers.py:64-65
+ *   AtariPreprocessFrameWrapper.observation wrappers.py:30-33  (cv2 RGB2GRAY + INTER_AREA 84x84)
+ *   FrameStackWrapper.step / reset        wrappers.py:224-235
+ *   _AutoResetWrapper.step ordering       multi_env.py:127-132
+ * d_raw_a, d_raw_b : uint8 [E,210,160,3] the last two raw frames of the frameskip window
+ *                    (pass the same pointer twice for a single-frame window, wrappers.py:66-67)
+ * d_terminal       : uint8 [E] terminal flag of THIS step (may be NULL = all zero)
+ * d_reset_mask     : uint8 [E] 1 if the previous step was terminal, i.e. the env is reset first
+ *                    (may be NULL); d_reset_raw: uint8 [E,210,160,3] first frame after that reset
+ * d_stack_in       : uint8 [E,84,84,4] previous stacks;  d_stack_out: uint8 [E, out_env_stride]
+ *                    new stacks (out_env_stride in bytes, >= 28224; lets the caller write straight
+ *                    into step t of a batch-major rollout buffer [E,T,84,84,4]).
+ *                    d_stack_in == d_stack_out (in place) is allowed when out_env_stride == 28224. */
+int acx_preprocess_stack_u8(const uint8_t* d_raw_a, const uint8_t* d_raw_b, const uint8_t* d_terminal,
+                            const uint8_t* d_reset_mask, const uint8_t* d_reset_raw,
+                            const uint8_t* d_stack_in, uint8_t* d_stack_out, size_t out_env_stride,
+                            int num_envs, void* stream);
+/* MultiEnv.reset (multi_env.py:49-57) + FrameStackWrapper.reset (wrappers.py:232-235):
+ * stack = 4 copies of preprocess(raw). */
+int acx_preprocess_reset_u8(const uint8_t* d_raw, uint8_t* d_stack_out, size_t out_env_stride,
+                            int num_envs, void* stream);
+
+/* ---- K-RET: n-step returns and advantages --------------------------------------------------- */
+/* Replaces objectives._discount/_discount_bootstrap + targets/advantage (objectives.py:123-130,
+ * 178-214).  rewards f32 [E,T], terminals u8 [E,T], values f32 [E,T], bootstrap f32 [E]
+ * -> targets f32 [E,T], advantages f32 [E,T] (either output may be NULL). */
+int acx_returns_adv(const float* d_rewards, const uint8_t* d_terminals, const float* d_values,
+                    const float* d_bootstrap_values, float gamma, int num_envs, int num_steps,
+                    float* d_targets, float* d_advantages, void* stream);
+
+/* ---- GEMM on bf16 planes (tcgen05 / TMEM / TMA) --------------------------------------------- */
+typedef struct {
+  const void* planes[ACX_MAX_PLANES]; /* bf16 matrices, row-major, same shape/ld */
+  int num_planes;
+  int rows, cols;                      /* as stored */
+  int ld;                              /* elements; multiple of 8 */
+} acx_planes_t;
+
+typedef struct {
+  /* C[M,N] = alpha * sum_{(i,j) in pairs} opA(A_i) * opB(B_j)  (+ bias[n]) ; fp32 accumulate.
+   * trans_a == 0: A stored [M,K] (K-major);  trans_a == 1: A stored [K,M] (MN-major).
+   * trans_b == 0: B stored [N,K] (K-major);  trans_b == 1: B stored [K,N] (MN-major).
+   * Only (0,0) and (1,1) are implemented on the tensor-core path. */
+  acx_planes_t a, b;
+  int trans_a, trans_b;
+  int m, n, k;
+  int num_pairs;                       /* 1..6 */
+  int pair_a[6], pair_b[6];            /* plane indices */
+  float alpha;
+  const float* bias;                   /* [n] or NULL */
+  int relu;                            /* max(0, .) after bias */
+  int symmetric;                       /* C = C^T known (SYRK): only tiles with tile_n >= tile_m are
+                                          computed; the finalize step mirrors them */
+  /* outputs (any subset): */
+  float* c; int ldc;                   /* fp32 */
+  void* c_planes[ACX_MAX_PLANES]; int c_num_planes; int ldc_planes; /* bf16 split of the result */
+  const void* mask_plane; int mask_ld; int mask_rows; /* optional: result *= (mask[m % mask_rows][n] > 0) (bf16) */
+  /* split-K: splits > 1 writes partial sums to workspace [splits][m_pad][n_pad] fp32 and the
+   * outputs above are produced by the finalize kernel. */
+  int splits;
+  float* workspace; size_t workspace_bytes;
+} acx_gemm_t;
+
+/* impl: 0 = tcgen05 tensor-core kernel (the product path), 1 = SIMT fp32 reference kernel on the
+ * same planes (debug/validation only, never selected automatically). */
+int acx_gemm(const acx_gemm_t* g, int impl, void* stream);
+size_t acx_gemm_workspace_bytes(const acx_gemm_t* g);
+/* fp32 [rows, cols] (ld_in) -> num_planes bf16 planes (ld_out multiple of 8); scale applied first. */
+int acx_split_planes(const float* d_in, int ld_in, int rows, int cols, float scale,
+                     void* const* d_planes, int num_planes, int ld_out, void* stream);
+/* debug hook: override the UMMA shared-memory descriptor strides (bytes) used for MN-major operands;
+ * 0 restores the built-in values. */
+void acx_debug_set_mn_desc(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t kstep_bytes);
+
+/* ---- learner (one process per GPU) ----------------------------------------------------------- */
+typedef struct {
+  int num_envs, num_steps, num_actions, conv3_filters;
+  int acktr;                   /* 1 = K-FAC (ColdStartPeriodicInvUpdateKfacOpt), 0 = A2C RMSProp */
+  float gamma, entropy_beta, value_loss_weight;
+  /* schedule / optimiser (a2c_acktr.py:64-71,240-251) */
+  float lr_start, lr_end; double lr_decay_steps;
+  float cov_ema_decay, damping, momentum, norm_constraint;
+  int invert_every, num_cold_updates;
+  float cold_lr, cold_momentum, clip_norm;
+  float rms_decay, rms_epsilon;
+  int num_locations_mode;      /* 0 = true VALID output count, 1 = kfac-0.1 input//stride */
+  int world_size;              /* data-parallel ranks (factor/gradient means are divided by it) */
+  int gemm_impl;               /* 0 tensor core, 1 SIMT (debug) */
+  uint64_t seed;               /* Philox seed for on-device Fisher sampling */
+} acx_learner_config_t;
+
+typedef struct acx_learner acx_learner_t;
+
+size_t acx_learner_arena_bytes(const acx_learner_config_t* cfg);
+/* d_arena: caller-allocated device memory of at least acx_learner_arena_bytes (256-byte aligned). */
+acx_learner_t* acx_learner_create(const acx_learner_config_t* cfg, void* d_arena, size_t arena_bytes);
+void acx_learner_destroy(acx_learner_t* l);
+
+/* flat fp32 parameter vector, per layer [K_l+1, C_l] (weights rows in (kh,kw,cin) order = the
+ * reference's HWIO variable flattened, nn.py:81-83 / 31-32; then the bias row), layers in the order
+ * conv1, conv2, conv3, fc4, fc_policy, fc_baseline. */
+size_t acx_learner_num_params(const acx_learner_t* l);
+int acx_learner_set_params(acx_learner_t* l, const float* h_params, void* stream);
+int acx_learner_get_params(acx_learner_t* l, float* h_params, void* stream);
+/* device views (offsets in floats into the arena's fp32 region), for torch views / all-reduce */
+float* acx_learner_buffer(acx_learner_t* l, const char* name, size_t* num_floats);
+uint8_t* acx_learner_obs_buffer(acx_learner_t* l, size_t* num_bytes); /* [N+E,84,84,4] train then bootstrap rows */
+
+/* One learner update = the reference's session.run(optimize_op, feed_dict) (a2c_acktr.py:117-126).
+ * phase 1: forward (train + bootstrap rows), returns, loss, backward, Fisher backward, batch factor
+ *          statistics -> everything that must be all-reduced lands in buffer "reduce_bucket".
+ * phase 2: (after the caller's all-reduce, if world_size > 1) EMA, scheduled inverse refresh,
+ *          precondition, KL clip, momentum, apply (or cold / RMSProp step); global_step advances.
+ * Inputs are read from the arena's input buffers (obs buffer + "actions","rewards","terminals");
+ * d_fisher_labels (int32 [N]) / d_fisher_eps (f32 [N]) inject the Fisher samples (NULL = Philox). */
+int acx_learner_phase1(acx_learner_t* l, const int32_t* d_fisher_labels, const float* d_fisher_eps, void* stream);
+int acx_learner_phase2(acx_learner_t* l, void* stream);
+int64_t acx_learner_global_step(const acx_learner_t* l);
+void acx_learner_set_global_step(acx_learner_t* l, int64_t gs);
+/* forward only on `rows` observations already in d_obs (uint8 [rows,84,84,4]) -> logits [rows,A],
+ * values [rows]; then categorical sample (u in [0,1) given, or Philox) / argmax.  Replaces
+ * ActorCriticModel.sample_actions / select_max_actions (model.py:135-169). */
+int acx_learner_act(acx_learner_t* l, const uint8_t* d_obs, int rows, const float* d_uniform,
+                    int greedy, int32_t* d_actions, float* d_logits, float* d_values, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACX_H_ */

@@ -1,0 +1,119 @@
+"""GPU bring-up of the tcgen05 GEMM: checks K-major and MN-major operand paths against fp64 and, if
+the MN-major descriptor is wrong, sweeps candidate (LBO, SBO, k-step) encodings.  Writes a report to
+gpurun_out/gemm_bringup.json."""
+import ctypes
+import itertools
+import json
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from actorcritic_b200 import _lib, ops  # noqa: E402
+
+lib = _lib.load()
+lib.acx_debug_tc_error.restype = ctypes.c_int
+report = {"cases": []}
+
+
+def ref64(planes, pairs, a_pl, b_pl, trans):
+    acc = None
+    for pa, pb in pairs:
+        a = a_pl[pa].double()
+        b = b_pl[pb].double()
+        t = (a.t() @ b) if trans else (a @ b.t())
+        acc = t if acc is None else acc + t
+    return acc
+
+
+def run_case(name, m, n, k, trans, nplanes=1, impl=0, splits=0, symmetric=False, **kw):
+    torch.manual_seed(hash(name) % 1000)
+    dev = "cuda"
+    if symmetric:
+        x = torch.randn((k, m) if trans else (m, k), device=dev)
+        a_pl = ops.split_planes(x, nplanes)
+        b_pl = a_pl
+    else:
+        xa = torch.randn((k, m) if trans else (m, k), device=dev)
+        xb = torch.randn((k, n) if trans else (n, k), device=dev)
+        a_pl = ops.split_planes(xa, nplanes)
+        b_pl = ops.split_planes(xb, nplanes)
+    pairs = ops.PAIRS[{1: 1, 2: 3, 3: 6}[nplanes]]
+    a_v = [p[:, :(m if trans else k)] for p in a_pl]
+    b_v = [p[:, :(n if trans else k)] for p in b_pl]
+    want = ref64(None, pairs, a_v, b_v, trans)
+    t0 = time.time()
+    c, _ = ops.gemm(a_pl, b_pl, m, n, k, trans=trans, pairs=pairs, impl=impl, splits=splits, symmetric=symmetric, **kw)
+    torch.cuda.synchronize()
+    err_flag = lib.acx_debug_tc_error()
+    err = float((c.double() - want).abs().max())
+    scale = float(want.abs().max())
+    rec = dict(name=name, m=m, n=n, k=k, trans=trans, planes=nplanes, impl=impl, splits=splits, sym=symmetric,
+               max_abs_err=err, ref_max=scale, rel=err / max(scale, 1e-30), tc_error=err_flag, sec=time.time() - t0)
+    report["cases"].append(rec)
+    print(json.dumps(rec), flush=True)
+    return rec
+
+
+def main():
+    os.makedirs("gpurun_out", exist_ok=True)
+    print(torch.cuda.get_device_name(0))
+    run_case("simt_k", 200, 100, 300, False, impl=1)
+    run_case("simt_mn", 200, 100, 300, True, impl=1)
+    r = run_case("tc_k_basic", 256, 128, 256, False)
+    run_case("tc_k_small", 128, 32, 64, False)
+    run_case("tc_k_n64", 300, 64, 512, False)
+    run_case("tc_k_odd", 333, 200, 577, False)
+    run_case("tc_k_split", 256, 128, 4096, False, splits=8)
+    run_case("tc_k_x3", 256, 128, 512, False, nplanes=2)
+    run_case("tc_k_x6", 256, 128, 512, False, nplanes=3)
+    r = run_case("tc_mn_basic", 256, 128, 256, True)
+    if r["rel"] > 1e-3:
+        best = None
+        for lbo, sbo, kstep in itertools.product([8192, 1024, 128, 16384, 2048], [1024, 8192, 128, 2048], [2048, 32, 256, 1024]):
+            lib.acx_debug_set_mn_desc(lbo, sbo, kstep)
+            rr = run_case("sweep_%d_%d_%d" % (lbo, sbo, kstep), 256, 128, 256, True)
+            if best is None or rr["rel"] < best[0]:
+                best = (rr["rel"], lbo, sbo, kstep)
+        report["mn_sweep_best"] = best
+        print("BEST", best)
+        if best and best[0] < 1e-3:
+            lib.acx_debug_set_mn_desc(best[1], best[2], best[3])
+        else:
+            lib.acx_debug_set_mn_desc(0, 0, 0)
+    run_case("tc_mn_n64", 256, 64, 640, True)
+    run_case("tc_mn_odd", 257, 100, 1000, True)
+    run_case("tc_mn_split", 256, 32, 64000, True, splits=0)
+    run_case("tc_mn_sym", 576, 576, 31360, True, symmetric=True)
+    run_case("tc_mn_sym_small", 256, 256, 2560, True, symmetric=True, splits=3)
+    run_case("tc_mn_x3", 512, 512, 640, True, nplanes=2)
+    run_case("tc_k_bias_relu", 256, 128, 256, False, bias=torch.randn(128, device="cuda"), relu=True)
+    # timing of the big SYRK shape (conv1 A factor) and a conv1-forward-like GEMM
+    for name, m, n, k, trans, sym in [("time_syrk_conv1", 256, 256, 256000, True, True),
+                                      ("time_syrk_conv2", 512, 512, 51840, True, True),
+                                      ("time_fwd_conv1", 256000, 32, 256, False, False),
+                                      ("time_fc4", 672, 512, 1568, False, False)]:
+        x = torch.randn((k, m) if trans else (m, k), device="cuda")
+        a_pl = ops.split_planes(x, 1)
+        b_pl = a_pl if sym else ops.split_planes(torch.randn((k, n) if trans else (n, k), device="cuda"), 1)
+        for _ in range(3):
+            ops.gemm(a_pl, b_pl, m, n, k, trans=trans, symmetric=sym)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            ops.gemm(a_pl, b_pl, m, n, k, trans=trans, symmetric=sym)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        flops = 2.0 * m * n * k
+        rec = dict(name=name, ms=ms, tflops_full=flops / ms / 1e9)
+        report["cases"].append(rec)
+        print(json.dumps(rec), flush=True)
+    json.dump(report, open("gpurun_out/gemm_bringup.json", "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
