@@ -89,10 +89,17 @@ def load():
         raise AcxError("libacx.so not found at %s - build it with actorcritic_b200/csrc/build.py "
                        "(there is no CPU fallback)" % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
+    missing = []
     for name, (restype, argtypes) in SIGNATURES.items():
-        fn = getattr(lib, name)          # AttributeError if the symbol is missing
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            missing.append(name)
+            continue
         fn.restype = restype
         fn.argtypes = argtypes
+    if missing:
+        raise AcxError("libacx.so is stale or incomplete, missing symbols: %s" % ", ".join(missing))
     _lib = lib
     return lib
 

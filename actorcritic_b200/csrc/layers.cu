@@ -1,0 +1,506 @@
+// layers.cu - the non-GEMM kernels of the Nature-CNN forward/backward and the A2C objective:
+// im2col (uint8 -> bf16 and bf16 -> bf16), col2im + ReLU mask + bf16 split, policy/value heads
+// forward, categorical log-prob / entropy / value loss + output gradients (true loss and Fisher sample),
+// heads backward, column sums, weight preparation.  Reference semantics: envs/atari/model.py:92-127,
+// 173-217, nn.py:37-52,88-110, policies.py:86-89,144, objectives.py:128-154,78.
+#include "layers.cuh"
+
+namespace acx {
+
+// ------------------------------------------------------------------------------------------------
+// im2col for conv1: obs uint8 [R,84,84,4] -> P1 bf16 [R*400, 256] holding the RAW byte values
+// (exact in bf16; the 1/255 of envs/atari/model.py:93 is folded into the GEMM alpha).
+// One thread per (patch row, ky): 32 contiguous input bytes -> 32 bf16.
+// ------------------------------------------------------------------------------------------------
+__global__ void im2col_conv1_kernel(const uint8_t* __restrict__ obs, bf16* __restrict__ out, int rows_total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)rows_total * 8) return;
+  const int ky = (int)(i & 7);
+  const int row = (int)(i >> 3);
+  const int n = row / 400, loc = row % 400, oy = loc / 20, ox = loc % 20;
+  const uint8_t* src = obs + ((size_t)(n * 84 + oy * 4 + ky) * 84 + ox * 4) * 4;
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(src));
+  const uint4 b = __ldg(reinterpret_cast<const uint4*>(src) + 1);
+  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  __align__(16) bf16 t[32];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) t[j * 4 + q] = __float2bfloat16_rn((float)((w[j] >> (8 * q)) & 0xffu));
+  uint4* dst = reinterpret_cast<uint4*>(out + (size_t)row * 256 + ky * 32);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) dst[j] = reinterpret_cast<const uint4*>(t)[j];
+}
+
+// generic NHWC bf16 im2col, patch order (ky, kx, c): each (row, ky) segment is k*C contiguous elements.
+// grid.y = plane.
+__global__ void im2col_bf16_kernel(const bf16* __restrict__ in0, const bf16* __restrict__ in1, bf16* __restrict__ out0,
+                                   bf16* __restrict__ out1, int rows_total, int hw_in, int c, int k, int s, int hw_out) {
+  const bf16* in = blockIdx.y == 0 ? in0 : in1;
+  bf16* out = blockIdx.y == 0 ? out0 : out1;
+  const int seg_vec = k * c / 8;               // uint4 per (row, ky) segment
+  const long long total = (long long)rows_total * k * seg_vec;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int v = (int)(i % seg_vec);
+  const long long t = i / seg_vec;
+  const int ky = (int)(t % k);
+  const int row = (int)(t / k);
+  const int per = hw_out * hw_out;
+  const int n = row / per, loc = row % per, oy = loc / hw_out, ox = loc % hw_out;
+  const uint4* src = reinterpret_cast<const uint4*>(in + ((size_t)(n * hw_in + oy * s + ky) * hw_in + ox * s) * c) + v;
+  uint4* dst = reinterpret_cast<uint4*>(out + (size_t)row * (k * k * c) + ky * (k * c)) + v;
+  *dst = __ldg(src);
+}
+
+// col2im (adjoint of im2col) as a gather + ReLU mask + bf16 split:
+//   dX[n,y,x,c] = sum_{ky,kx : (y-ky)%s==0, (x-kx)%s==0, in range} dP[(n,oy,ox), (ky,kx,c)]
+//   dPre[n,y,x,c] = dX * 1[act(n % mask_n, y, x, c) > 0]       (true rows and Fisher rows share the mask)
+// One thread per (n, y, x, 4 channels).
+__global__ void col2im_mask_split_kernel(const float* __restrict__ dp, const bf16* __restrict__ act_hi, bf16* __restrict__ out_hi,
+                                         bf16* __restrict__ out_lo, int n_total, int mask_n, int hw_in, int c, int k, int s,
+                                         int hw_out) {
+  const int cv = c / 4;
+  const long long total = (long long)n_total * hw_in * hw_in * cv;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c4 = (int)(i % cv) * 4;
+  long long t = i / cv;
+  const int x = (int)(t % hw_in);
+  t /= hw_in;
+  const int y = (int)(t % hw_in);
+  const int n = (int)(t / hw_in);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int kkc = k * k * c;
+  for (int ky = y % s; ky < k; ky += s) {
+    const int oy = (y - ky) / s;
+    if (y - ky < 0) break;
+    if (oy >= hw_out) continue;
+    for (int kx = x % s; kx < k; kx += s) {
+      const int ox = (x - kx) / s;
+      if (x - kx < 0) break;
+      if (ox >= hw_out) continue;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(
+          dp + ((size_t)(n * hw_out + oy) * hw_out + ox) * kkc + (ky * k + kx) * c + c4));
+      acc.x += v.x;
+      acc.y += v.y;
+      acc.z += v.z;
+      acc.w += v.w;
+    }
+  }
+  const size_t pix = ((size_t)((n % mask_n) * hw_in + y) * hw_in + x) * c + c4;
+  const size_t opix = ((size_t)(n * hw_in + y) * hw_in + x) * c + c4;
+  const float vals[4] = {acc.x, acc.y, acc.z, acc.w};
+  __align__(8) bf16 hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float m = __bfloat162float(act_hi[pix + j]);
+    const float v = m > 0.0f ? vals[j] : 0.0f;
+    bf16 p2;
+    split3(v, hi[j], lo[j], p2);
+  }
+  *reinterpret_cast<uint2*>(out_hi + opix) = *reinterpret_cast<const uint2*>(hi);
+  *reinterpret_cast<uint2*>(out_lo + opix) = *reinterpret_cast<const uint2*>(lo);
+}
+
+// ------------------------------------------------------------------------------------------------
+// heads forward: act4 planes [R,512] x W_pol [512,A], W_val [512,1] (+ biases) -> logits [R,A], values [R]
+// (envs/atari/model.py:207-216).  One warp per row.
+// ------------------------------------------------------------------------------------------------
+__global__ void heads_fwd_kernel(const bf16* __restrict__ a_hi, const bf16* __restrict__ a_lo, const float* __restrict__ vpol,
+                                 const float* __restrict__ vval, int rows, int num_actions, float* __restrict__ logits,
+                                 float* __restrict__ values) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float x[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const size_t idx = (size_t)row * 512 + lane + 32 * j;
+    x[j] = __bfloat162float(a_hi[idx]) + __bfloat162float(a_lo[idx]);
+  }
+  for (int a = 0; a <= num_actions; ++a) {
+    const float* w = a < num_actions ? vpol + a : vval;
+    const int ld = a < num_actions ? num_actions : 1;
+    float acc = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc = fmaf(x[j], __ldg(w + (size_t)(lane + 32 * j) * ld), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      if (a < num_actions)
+        logits[(size_t)row * num_actions + a] = acc + vpol[(size_t)512 * num_actions + a];
+      else
+        values[row] = acc + vval[512];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (counter-based RNG) for on-device Fisher sampling / action sampling
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+
+// ------------------------------------------------------------------------------------------------
+// A2C objective + output gradients (objectives.py:128-154,78; closed forms of SURVEY A.4) and the
+// Fisher-sample output gradients.  dheads is [2N, A+1]: rows [0,N) = d(shared loss)/d(logits|value),
+// rows [N,2N) = d(L_sample)/d(logits|value).  One CTA; each thread strides over rows; deterministic
+// block reduction for the three scalars.  inv_count = 1/N_global_rows_per_rank (the means are per rank;
+// data-parallel ranks average them afterwards).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) loss_grad_kernel(const float* __restrict__ logits, const float* __restrict__ values,
+                                                        const uint8_t* __restrict__ actions, const float* __restrict__ targets,
+                                                        const int32_t* __restrict__ fisher_labels,
+                                                        const float* __restrict__ fisher_eps, uint64_t seed, uint64_t step,
+                                                        int n_rows, int num_actions, float beta, float value_weight,
+                                                        float* __restrict__ dheads, float* __restrict__ scalars,
+                                                        int want_fisher) {
+  __shared__ float red[3][8];
+  float s_obj = 0.f, s_ent = 0.f, s_val = 0.f;
+  const float inv_n = 1.0f / (float)n_rows;
+  const int ld = num_actions + 1;
+  for (int r = threadIdx.x; r < n_rows; r += blockDim.x) {
+    const float* z = logits + (size_t)r * num_actions;
+    float mx = z[0];
+    for (int a = 1; a < num_actions; ++a) mx = fmaxf(mx, z[a]);
+    float se = 0.f;
+    for (int a = 0; a < num_actions; ++a) se += expf(z[a] - mx);
+    const float lse = logf(se) + mx;
+    float ent = 0.f;
+    for (int a = 0; a < num_actions; ++a) {
+      const float lp = z[a] - lse;
+      ent -= expf(lp) * lp;
+    }
+    const int act = actions[r];
+    const float v = values[r], tg = targets[r];
+    const float adv = tg - v;
+    const float logp_a = z[act] - lse;
+    s_obj += adv * logp_a;
+    s_ent += ent;
+    s_val += 0.5f * (tg - v) * (tg - v);
+    // Fisher sample
+    int yhat = 0;
+    float eps = 0.f;
+    if (want_fisher) {
+      if (fisher_labels) {
+        yhat = fisher_labels[r];
+        eps = fisher_eps[r];
+      } else {
+        const uint4 rnd = philox4x32(make_uint4((uint32_t)r, (uint32_t)step, (uint32_t)(step >> 32), 0x46495348u),
+                                     make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+        const float u = u01(rnd.x);
+        float cum = 0.f;
+        yhat = num_actions - 1;
+        for (int a = 0; a < num_actions; ++a) {
+          cum += expf(z[a] - lse);
+          if (u < cum) {
+            yhat = a;
+            break;
+          }
+        }
+        eps = sqrtf(-2.0f * logf(u01(rnd.y))) * cospif(2.0f * u01(rnd.z));
+      }
+    }
+    float* d_true = dheads + (size_t)r * ld;
+    float* d_fish = dheads + (size_t)(n_rows + r) * ld;
+    for (int a = 0; a < num_actions; ++a) {
+      const float lp = z[a] - lse;
+      const float p = expf(lp);
+      d_true[a] = -(adv * inv_n) * ((a == act ? 1.0f : 0.0f) - p) + (beta * inv_n) * p * (lp + ent);
+      if (want_fisher) d_fish[a] = p - (a == yhat ? 1.0f : 0.0f);
+    }
+    d_true[num_actions] = -value_weight * (tg - v) * inv_n;
+    if (want_fisher) d_fish[num_actions] = -eps;
+  }
+  s_obj = warp_sum(s_obj);
+  s_ent = warp_sum(s_ent);
+  s_val = warp_sum(s_val);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    red[0][warp] = s_obj;
+    red[1][warp] = s_ent;
+    red[2][warp] = s_val;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float o = 0.f, e = 0.f, vl = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      o += red[0][w];
+      e += red[1][w];
+      vl += red[2][w];
+    }
+    const float mean_ent = e * inv_n;
+    scalars[0] = -(o * inv_n + beta * mean_ent);  // policy_loss   objectives.py:145-149
+    scalars[1] = vl * inv_n;                       // baseline_loss objectives.py:154
+    scalars[2] = mean_ent;                         // mean_entropy  objectives.py:138-139
+    scalars[3] = scalars[0] + value_weight * scalars[1];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// heads backward.  (a) dPre4[r, j] = (sum_a dH[r,a] W_pol[j,a] + dH[r,A] W_val[j]) * 1[act4[r % N, j] > 0] -> planes
+// ------------------------------------------------------------------------------------------------
+__global__ void heads_bwd_data_kernel(const float* __restrict__ dheads, const float* __restrict__ vpol,
+                                      const float* __restrict__ vval, const bf16* __restrict__ act4_hi, int rows, int mask_rows,
+                                      int num_actions, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)rows * 512) return;
+  const int j = (int)(i & 511), r = (int)(i >> 9);
+  const float* d = dheads + (size_t)r * (num_actions + 1);
+  float acc = d[num_actions] * __ldg(vval + j);
+  for (int a = 0; a < num_actions; ++a) acc = fmaf(d[a], __ldg(vpol + (size_t)j * num_actions + a), acc);
+  const float m = __bfloat162float(act4_hi[(size_t)(r % mask_rows) * 512 + j]);
+  if (!(m > 0.0f)) acc = 0.0f;
+  bf16 hi, lo, p2;
+  split3(acc, hi, lo, p2);
+  out_hi[i] = hi;
+  out_lo[i] = lo;
+}
+
+// (b) weight gradients of the two heads from the TRUE-loss rows: g_pol[j,a] = sum_n act4[n,j] dH[n,a]
+// (j = 512 is the bias row: sum_n dH[n,a]); same for the value head.  One CTA per j, 128 threads over n.
+__global__ void __launch_bounds__(128) heads_wgrad_kernel(const float* __restrict__ dheads, const bf16* __restrict__ act4_hi,
+                                                          const bf16* __restrict__ act4_lo, int n_rows, int num_actions,
+                                                          float* __restrict__ gpol, float* __restrict__ gval) {
+  __shared__ float red[4][32];
+  const int j = blockIdx.x;  // 0..512
+  const int ld = num_actions + 1;
+  float acc[32];
+#pragma unroll
+  for (int a = 0; a < 32; ++a) acc[a] = 0.f;
+  for (int n = threadIdx.x; n < n_rows; n += blockDim.x) {
+    float x = 1.0f;
+    if (j < 512) {
+      const size_t idx = (size_t)n * 512 + j;
+      x = __bfloat162float(act4_hi[idx]) + __bfloat162float(act4_lo[idx]);
+    }
+    const float* d = dheads + (size_t)n * ld;
+#pragma unroll
+    for (int a = 0; a < 32; ++a)
+      if (a < ld) acc[a] = fmaf(x, d[a], acc[a]);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int a = 0; a < 32; ++a) {
+    if (a < ld) {
+      const float v = warp_sum(acc[a]);
+      if (lane == 0) red[warp][a] = v;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < ld) {
+    const int a = threadIdx.x;
+    const float v = red[0][a] + red[1][a] + red[2][a] + red[3][a];
+    if (a < num_actions)
+      gpol[(size_t)j * num_actions + a] = v;
+    else
+      gval[j] = v;
+  }
+}
+
+// (c) output factors of the heads from the FISHER rows: G_pol = dz^T dz / N [A,A], G_val = dv^T dv / N [1,1]
+__global__ void __launch_bounds__(256) heads_gfactor_kernel(const float* __restrict__ dheads_fisher, int n_rows, int num_actions,
+                                                            float* __restrict__ g_pol, float* __restrict__ g_val) {
+  __shared__ float red[8];
+  const int ld = num_actions + 1;
+  const int pair = blockIdx.x;  // 0 .. A*A (last = value)
+  const int a = pair < num_actions * num_actions ? pair / num_actions : num_actions;
+  const int b = pair < num_actions * num_actions ? pair % num_actions : num_actions;
+  float acc = 0.f;
+  for (int n = threadIdx.x; n < n_rows; n += blockDim.x) acc = fmaf(dheads_fisher[(size_t)n * ld + a], dheads_fisher[(size_t)n * ld + b], acc);
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += red[w];
+    v /= (float)n_rows;
+    if (pair < num_actions * num_actions)
+      g_pol[pair] = v;
+    else
+      g_val[0] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// column sums of a planes matrix over rows [0, rows): two deterministic stages.
+// stage 1: grid (ceil(cols/128), chunks) ; stage 2: sums the chunks and scales.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) colsum_stage1_kernel(const bf16* __restrict__ hi, const bf16* __restrict__ lo, int rows,
+                                                            int cols, int ld, int rows_per_chunk, float* __restrict__ partial) {
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  if (c >= cols) return;
+  const int r0 = blockIdx.y * rows_per_chunk;
+  const int r1 = min(rows, r0 + rows_per_chunk);
+  float acc = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    const size_t idx = (size_t)r * ld + c;
+    float v = __bfloat162float(hi[idx]);
+    if (lo) v += __bfloat162float(lo[idx]);
+    acc += v;
+  }
+  partial[(size_t)blockIdx.y * cols + c] = acc;
+}
+__global__ void colsum_stage2_kernel(const float* __restrict__ partial, int chunks, int cols, float scale, float* __restrict__ out,
+                                     int out_stride) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float acc = 0.f;
+  for (int k = 0; k < chunks; ++k) acc += partial[(size_t)k * cols + c];
+  out[(size_t)c * out_stride] = acc * scale;
+}
+
+// fp32 [K, C] (row-major, the V-layout weight rows) -> transposed bf16 planes [C, ld_out]
+__global__ void transpose_split_kernel(const float* __restrict__ in, int k_rows, int c_cols, bf16* __restrict__ p0,
+                                       bf16* __restrict__ p1, bf16* __restrict__ p2, int num_planes, int ld_out) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int k = k0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (k < k_rows && c < c_cols) ? in[(size_t)k * c_cols + c] : 0.0f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, k = k0 + threadIdx.x;
+    if (c < c_cols && k < ld_out) {
+      bf16 a, b, d;
+      split3(k < k_rows ? tile[threadIdx.x][i] : 0.0f, a, b, d);
+      const size_t idx = (size_t)c * ld_out + k;
+      p0[idx] = a;
+      if (num_planes > 1) p1[idx] = b;
+      if (num_planes > 2) p2[idx] = d;
+    }
+  }
+}
+
+// categorical sample (inverse CDF on softmax(logits)) or argmax  (policies.py:86-87)
+__global__ void sample_actions_kernel(const float* __restrict__ logits, const float* __restrict__ uniform, uint64_t seed,
+                                      uint64_t step, int rows, int num_actions, int greedy, int32_t* __restrict__ actions) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const float* z = logits + (size_t)r * num_actions;
+  float mx = z[0];
+  int arg = 0;
+  for (int a = 1; a < num_actions; ++a)
+    if (z[a] > mx) {
+      mx = z[a];
+      arg = a;
+    }
+  if (greedy) {
+    actions[r] = arg;
+    return;
+  }
+  float se = 0.f;
+  for (int a = 0; a < num_actions; ++a) se += expf(z[a] - mx);
+  float u;
+  if (uniform)
+    u = uniform[r];
+  else
+    u = u01(philox4x32(make_uint4((uint32_t)r, (uint32_t)step, (uint32_t)(step >> 32), 0x41435421u),
+                       make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)))
+                .x);
+  float cum = 0.f;
+  int pick = num_actions - 1;
+  for (int a = 0; a < num_actions; ++a) {
+    cum += expf(z[a] - mx) / se;
+    if (u < cum) {
+      pick = a;
+      break;
+    }
+  }
+  actions[r] = pick;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+int im2col_conv1(const uint8_t* obs, bf16* out, int rows_total, cudaStream_t st) {
+  const long long total = (long long)rows_total * 8;
+  im2col_conv1_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(obs, out, rows_total);
+  ACX_LAUNCH_CHECK();
+  return 0;
+}
+int im2col_bf16(const bf16* in0, const bf16* in1, bf16* out0, bf16* out1, int rows_total, int hw_in, int c, int k, int s,
+                int hw_out, cudaStream_t st) {
+  const long long total = (long long)rows_total * k * (k * c / 8);
+  dim3 grid((unsigned)((total + 255) / 256), 2);
+  im2col_bf16_kernel<<<grid, 256, 0, st>>>(in0, in1, out0, out1, rows_total, hw_in, c, k, s, hw_out);
+  ACX_LAUNCH_CHECK();
+  return 0;
+}
+int col2im_mask_split(const float* dp, const bf16* act_hi, bf16* out_hi, bf16* out_lo, int n_total, int mask_n, int hw_in, int c,
+                      int k, int s, int hw_out, cudaStream_t st) {
+  const long long total = (long long)n_total * hw_in * hw_in * (c / 4);
+  col2im_mask_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dp, act_hi, out_hi, out_lo, n_total, mask_n, hw_in,
+                                                                           c, k, s, hw_out);
+  ACX_LAUNCH_CHECK();
+  return 0;
+}
+int heads_fwd(const bf16* a_hi, const bf16* a_lo, const float* vpol, const float* vval, int rows, int num_actions, float* logits,
+              float* values, cudaStream_t st) {
+  heads_fwd_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(a_hi, a_lo, vpol, vval, rows, num_actions, logits, values);
+  ACX_LAUNCH_CHECK();
+  return 0;
+}
+int loss_grad(const float* logits, const float* values, const uint8_t* actions, const float* targets, const int32_t* fl,
+              const float* fe, uint64_t seed, uint64_t step, int n_rows, int num_actions, float beta, float vw, float* dheads,
+              float* scalars, int want_fisher, cudaStream_t st) {
+  loss_grad_kernel<<<1, 256, 0, st>>>(logits, values, actions, targets, fl, fe, seed, step, n_rows, num_actions, beta, vw, dheads,
+                                      scalars, want_fisher);
+  ACX_LAUNCH_CHECK();
+  return 0;
+}
+int heads_bwd(const float* dheads, const float* vpol, const float* vval, const bf16* act4_hi, const bf16* act4_lo, int n_rows,
+              int rows_bwd, int num_actions, bf16* dpre4_hi, bf16* dpre4_lo, float* gpol, float* gval, cudaStream_t st) {
+  const long long total = (long long)rows_bwd * 512;
+  heads_bwd_data_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dheads, vpol, vval, act4_hi, rows_bwd, n_rows, num_actions,
+                                                                        dpre4_hi, dpre4_lo);
+  ACX_LAUNCH_CHECK();
+  heads_wgrad_kernel<<<513, 128, 0, st>>>(dheads, act4_hi, act4_lo, n_rows, num_actions, gpol, gval);
+  ACX_LAUNCH_CHECK();
+  return 0;
+}
+int heads_gfactor(const float* dheads_fisher, int n_rows, int num_actions, float* g_pol, float* g_val, cudaStream_t st) {
+  heads_gfactor_kernel<<<num_actions * num_actions + 1, 256, 0, st>>>(dheads_fisher, n_rows, num_actions, g_pol, g_val);
+  ACX_LAUNCH_CHECK();
+  return 0;
+}
+int colsum(const bf16* hi, const bf16* lo, int rows, int cols, int ld, float scale, float* partial, int max_chunks, float* out,
+           int out_stride, cudaStream_t st) {
+  int chunks = ceil_div(rows, 256);
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  const int rpc = ceil_div(rows, chunks);
+  chunks = ceil_div(rows, rpc);
+  dim3 grid(ceil_div(cols, 128), chunks);
+  colsum_stage1_kernel<<<grid, 128, 0, st>>>(hi, lo, rows, cols, ld, rpc, partial);
+  ACX_LAUNCH_CHECK();
+  colsum_stage2_kernel<<<ceil_div(cols, 128), 128, 0, st>>>(partial, chunks, cols, scale, out, out_stride);
+  ACX_LAUNCH_CHECK();
+  return 0;
+}
+int transpose_split(const float* in, int k_rows, int c_cols, bf16* p0, bf16* p1, bf16* p2, int num_planes, int ld_out,
+                    cudaStream_t st) {
+  dim3 grid(ceil_div(ld_out, 32), ceil_div(c_cols, 32));
+  transpose_split_kernel<<<grid, dim3(32, 8), 0, st>>>(in, k_rows, c_cols, p0, p1, p2, num_planes, ld_out);
+  ACX_LAUNCH_CHECK();
+  return 0;
+}
+int sample_actions(const float* logits, const float* uniform, uint64_t seed, uint64_t step, int rows, int num_actions, int greedy,
+                   int32_t* actions, cudaStream_t st) {
+  sample_actions_kernel<<<ceil_div(rows, 128), 128, 0, st>>>(logits, uniform, seed, step, rows, num_actions, greedy, actions);
+  ACX_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace acx
