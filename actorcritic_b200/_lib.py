@@ -44,7 +44,7 @@ class LearnerConfig(ctypes.Structure):
                 ("cold_lr", ctypes.c_float), ("cold_momentum", ctypes.c_float), ("clip_norm", ctypes.c_float),
                 ("rms_decay", ctypes.c_float), ("rms_epsilon", ctypes.c_float),
                 ("num_locations_mode", ctypes.c_int), ("world_size", ctypes.c_int), ("gemm_impl", ctypes.c_int),
-                ("seed", ctypes.c_uint64)]
+                ("precision", ctypes.c_int), ("seed", ctypes.c_uint64)]
 
 
 # every symbol include/acx.h declares: name -> (restype, argtypes)
@@ -68,12 +68,14 @@ SIGNATURES = {
     "acx_learner_num_params": (ctypes.c_size_t, [_P]),
     "acx_learner_set_params": (ctypes.c_int, [_P, _P, _P]),
     "acx_learner_get_params": (ctypes.c_int, [_P, _P, _P]),
+    "acx_learner_refresh_weights": (ctypes.c_int, [_P, _P]),
     "acx_learner_buffer": (_P, [_P, ctypes.c_char_p, ctypes.POINTER(ctypes.c_size_t)]),
-    "acx_learner_obs_buffer": (_P, [_P, ctypes.POINTER(ctypes.c_size_t)]),
     "acx_learner_phase1": (ctypes.c_int, [_P, _P, _P, _P]),
     "acx_learner_phase2": (ctypes.c_int, [_P, _P]),
     "acx_learner_global_step": (ctypes.c_int64, [_P]),
-    "acx_learner_set_global_step": (None, [_P, ctypes.c_int64]),
+    "acx_learner_set_state": (ctypes.c_int, [_P, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, _P]),
+    "acx_learner_get_state": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64),
+                                             ctypes.POINTER(ctypes.c_int)]),
     "acx_learner_act": (ctypes.c_int, [_P, _P, ctypes.c_int, _P, ctypes.c_int, _P, _P, _P, _P]),
 }
 

@@ -9,7 +9,7 @@
 #include <mutex>
 #include <unordered_map>
 
-#include "common.cuh"
+#include "layers.cuh"
 
 namespace acx {
 
@@ -255,7 +255,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
         const int s = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
         mbar_wait(&empty_bar[s], ph ^ 1u, 1);
-        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+        // MN-major tiles are loaded as 64-column chunks; chunks that start beyond the matrix are skipped (their
+        // shared memory only feeds accumulator rows/columns that are never stored)
+        const int na = MAJOR == 0 ? 0 : min(BM / 64, (p.out.m - m0 + 63) / 64);
+        const int nb = MAJOR == 0 ? 0 : min(BN / 64, (p.out.n - n0 + 63) / 64);
+        mbar_expect_tx(&full_bar[s], MAJOR == 0 ? (uint32_t)STAGE_BYTES : (uint32_t)((na + nb) * BK * 128));
         const int pr = it / nkb, kb = kb0 + it % nkb;
         const int pa = p.pair_a[pr], pb = p.pair_b[pr];
         const CUtensorMap* ma = pa == 0 ? &ta0 : (pa == 1 ? &ta1 : &ta2);
@@ -267,9 +271,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
           tma_load_2d(b_s, mb, &full_bar[s], kb * BK, n0);
         } else {
 #pragma unroll
-          for (int j = 0; j < BM / 64; ++j) tma_load_2d(a_s + j * (BK * 128), ma, &full_bar[s], m0 + 64 * j, kb * BK);
+          for (int j = 0; j < BM / 64; ++j)
+            if (j < na) tma_load_2d(a_s + j * (BK * 128), ma, &full_bar[s], m0 + 64 * j, kb * BK);
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_s + j * (BK * 128), mb, &full_bar[s], n0 + 64 * j, kb * BK);
+          for (int j = 0; j < BN / 64; ++j)
+            if (j < nb) tma_load_2d(b_s + j * (BK * 128), mb, &full_bar[s], n0 + 64 * j, kb * BK);
         }
       }
     }
@@ -666,6 +672,18 @@ int gemm_dispatch(const acx_gemm_t* g, int impl, cudaStream_t st) {
   return impl == 1 ? gemm_simt(g, st) : gemm_tc(g, st);
 }
 
+int split_planes(const float* in, int ld_in, int rows, int cols, float scale, bf16* p0, bf16* p1, bf16* p2, int num_planes,
+                 int ld_out, cudaStream_t st) {
+  ACX_CHECK(num_planes >= 1 && num_planes <= ACX_MAX_PLANES, "num_planes");
+  ACX_CHECK(rows > 0 && cols > 0 && ld_out >= cols, "shape");
+  const size_t total = (size_t)rows * ld_out;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  split_planes_kernel<<<blocks, 256, 0, st>>>(in, ld_in, rows, cols, scale, p0, p1, p2, num_planes, ld_out);
+  ACX_LAUNCH_CHECK();
+  return 0;
+}
+
 int tc_error_flag() {
   int v = 0;
   cudaMemcpyFromSymbol(&v, g_tc_error, sizeof(int));
@@ -688,17 +706,11 @@ size_t acx_gemm_workspace_bytes(const acx_gemm_t* g) {
 
 int acx_split_planes(const float* d_in, int ld_in, int rows, int cols, float scale, void* const* d_planes, int num_planes,
                      int ld_out, void* stream) {
-  ACX_CHECK(num_planes >= 1 && num_planes <= ACX_MAX_PLANES, "num_planes");
-  ACX_CHECK(rows > 0 && cols > 0 && ld_out >= cols, "shape");
-  const size_t total = (size_t)rows * ld_out;
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  acx::split_planes_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      d_in, ld_in, rows, cols, scale, reinterpret_cast<acx::bf16*>(d_planes[0]),
-      reinterpret_cast<acx::bf16*>(num_planes > 1 ? d_planes[1] : nullptr),
-      reinterpret_cast<acx::bf16*>(num_planes > 2 ? d_planes[2] : nullptr), num_planes, ld_out);
-  ACX_LAUNCH_CHECK();
-  return 0;
+  ACX_CHECK(num_planes >= 1 && num_planes <= ACX_MAX_PLANES && d_planes != nullptr, "num_planes");
+  return acx::split_planes(d_in, ld_in, rows, cols, scale, reinterpret_cast<acx::bf16*>(d_planes[0]),
+                           reinterpret_cast<acx::bf16*>(num_planes > 1 ? d_planes[1] : nullptr),
+                           reinterpret_cast<acx::bf16*>(num_planes > 2 ? d_planes[2] : nullptr), num_planes, ld_out,
+                           reinterpret_cast<cudaStream_t>(stream));
 }
 
 void acx_debug_set_mn_desc(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t kstep_bytes) {

@@ -1,0 +1,514 @@
+// kfac.cu - the K-FAC side of the ACKTR update that is not a GEMM: homogeneous border of the input
+// factors, the moving average of the factor statistics, pi-adjusted damping from traces, the damped SPD
+// inverses, the <V,U> reduction for the KL clip and the fused clip + momentum + apply steps (K-FAC,
+// cold momentum-SGD, RMSProp).  Semantics: SURVEY A.5 (tensorflow/kfac 0.1.x as driven by
+// kfac_utils.py:38-53 with the hyper-parameters of a2c_acktr.py:240-251) and nn.py:185-189.
+#include "layers.cuh"
+
+namespace acx {
+
+// ------------------------------------------------------------------------------------------------
+// A = [[P^T P, P^T 1], [1^T P, rows]] / rows : the tensor-core SYRK fills the K x K block, this writes
+// the border (column / row d-1) from the scaled column sums and the corner 1.
+// ------------------------------------------------------------------------------------------------
+__global__ void homog_border_kernel(float* __restrict__ a, int d, const float* __restrict__ cs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d) return;
+  const float v = i < d - 1 ? cs[i] : 1.0f;
+  a[(size_t)i * d + (d - 1)] = v;
+  a[(size_t)(d - 1) * d + i] = v;
+}
+
+// S <- decay * S + (1 - decay) * scale_c * C      (kfac MovingAverageVariable, cov_ema_decay)
+__global__ void ema_kernel(float* __restrict__ s, const float* __restrict__ c, size_t count, float decay, float wc) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t n4 = count / 4;
+  float4* s4 = reinterpret_cast<float4*>(s);
+  const float4* c4 = reinterpret_cast<const float4*>(c);
+  for (size_t j = i; j < n4; j += stride) {
+    float4 a = s4[j];
+    const float4 b = c4[j];
+    a.x = decay * a.x + wc * b.x;
+    a.y = decay * a.y + wc * b.y;
+    a.z = decay * a.z + wc * b.z;
+    a.w = decay * a.w + wc * b.w;
+    s4[j] = a;
+  }
+  for (size_t j = n4 * 4 + i; j < count; j += stride) s[j] = decay * s[j] + wc * c[j];
+}
+
+__global__ void fill_kernel(float* __restrict__ p, size_t count, float v) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) p[i] = v;
+}
+__global__ void scale_kernel(float* __restrict__ p, size_t count, float v) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) p[i] *= v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pi-adjusted damping (SURVEY A.5 "Damping"): per block, from the traces of the running sums (the
+// zero-debias factor is common to A and G and cancels in pi):
+//   pi = sqrt((tr A / dim A) / (tr G / dim G)),  damp_A = pi * sqrt(lambda_l),  damp_G = sqrt(lambda_l) / pi
+// One warp per block (layer); out[2*l] = damp_A, out[2*l+1] = damp_G.
+// ------------------------------------------------------------------------------------------------
+__global__ void dampings_kernel(const float* const* __restrict__ a_ptrs, const float* const* __restrict__ g_ptrs,
+                                const int* __restrict__ a_dims, const int* __restrict__ g_dims,
+                                const float* __restrict__ lambdas, int num_layers, float* __restrict__ out) {
+  const int l = blockIdx.x;
+  if (l >= num_layers) return;
+  const int lane = threadIdx.x;
+  const float* a = a_ptrs[l];
+  const float* g = g_ptrs[l];
+  const int da = a_dims[l], dg = g_dims[l];
+  double ta = 0.0, tg = 0.0;
+  for (int i = lane; i < da; i += 32) ta += (double)a[(size_t)i * da + i];
+  for (int i = lane; i < dg; i += 32) tg += (double)g[(size_t)i * dg + i];
+  ta = warp_sum_d(ta);
+  tg = warp_sum_d(tg);
+  if (lane == 0) {
+    ta /= (double)da;
+    tg /= (double)dg;
+    const double pi = (ta > 0.0 && tg > 0.0) ? sqrt(ta / tg) : 1.0;
+    const double root = sqrt((double)lambdas[l]);
+    out[2 * l] = (float)(pi * root);
+    out[2 * l + 1] = (float)(root / pi);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Damped SPD inverse, batched over jobs (grid.z = job), fp64, blocked in-place Gauss-Jordan without
+// pivoting (safe for SPD): for each 32-wide pivot block p
+//   D^-1 = inv(M_pp);  R_j = D^-1 M_pj (j != p);  M_ij -= M_ip R_j (i, j != p);
+//   M_ip = -M_ip D^-1 (i != p);  M_pj = R_j;  M_pp = D^-1.
+// After the last block M holds the inverse.  2 n^3 flops; runs only every `invert_every` updates.
+// ------------------------------------------------------------------------------------------------
+constexpr int IB = 32;  // pivot block
+
+struct InvDev {
+  const float* s;
+  int n;
+  int damp_index;
+  double* m;     // [n, n]
+  double* rbuf;  // [IB, n] row panel R, then [IB, IB] D^-1 at rbuf + IB * n
+  float* inv;
+  bf16* planes[3];
+  int ld_planes;
+};
+
+__global__ void inv_prepare_kernel(const InvDev* __restrict__ jobs, const Sched* __restrict__ sched,
+                                   const float* __restrict__ damp) {
+  const InvDev jb = jobs[blockIdx.z];
+  const float debias = sched->debias;
+  const size_t total = (size_t)jb.n * jb.n;
+  const double dv = (double)damp[jb.damp_index];
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int r = (int)(i / jb.n), c = (int)(i % jb.n);
+    // symmetrise while loading: the statistics are symmetric up to the rounding of the border writes
+    const double v = 0.5 * ((double)jb.s[i] + (double)jb.s[(size_t)c * jb.n + r]) * (double)debias;
+    jb.m[i] = r == c ? v + dv : v;
+  }
+}
+
+// invert the IB x IB diagonal block in shared memory (unblocked Gauss-Jordan, 32x32 threads... here 1024 threads)
+__device__ void invert_block_smem(double (*d)[IB + 1], int nb) {
+  // d holds an nb x nb SPD-derived block (rows/cols >= nb are identity padding)
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 32 threads
+  for (int k = 0; k < IB; ++k) {
+    __syncthreads();
+    const double pivot = d[k][k];
+    const double inv_p = 1.0 / pivot;
+    const double row_k = d[k][tx];
+    const double col_k = d[ty][k];
+    __syncthreads();
+    double v;
+    if (ty == k && tx == k)
+      v = inv_p;
+    else if (ty == k)
+      v = row_k * inv_p;
+    else if (tx == k)
+      v = -col_k * inv_p;
+    else
+      v = d[ty][tx] - col_k * row_k * inv_p;
+    d[ty][tx] = v;
+  }
+  __syncthreads();
+}
+
+// step kernel A: grid.x = column blocks (ceil(n / IB)), grid.z = job.  Every CTA inverts the pivot block
+// (redundantly - it is 32 steps) and computes its R_j = D^-1 M_pj into rbuf; CTA j == p stores D^-1.
+__global__ void __launch_bounds__(1024) inv_rowpanel_kernel(const InvDev* __restrict__ jobs, int p) {
+  const InvDev jb = jobs[blockIdx.z];
+  const int n = jb.n;
+  const int p0 = p * IB;
+  if (p0 >= n) return;
+  const int j0 = blockIdx.x * IB;
+  if (j0 >= n) return;
+  __shared__ double d[IB][IB + 1];
+  __shared__ double mp[IB][IB + 1];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int nb = min(IB, n - p0);
+  {
+    const int r = p0 + ty, c = p0 + tx;
+    d[ty][tx] = (ty < nb && tx < nb) ? jb.m[(size_t)r * n + c] : (ty == tx ? 1.0 : 0.0);
+    const int cj = j0 + tx;
+    mp[ty][tx] = (ty < nb && cj < n) ? jb.m[(size_t)r * n + cj] : 0.0;
+  }
+  invert_block_smem(d, nb);
+  double* dinv = jb.rbuf + (size_t)IB * n;
+  if (blockIdx.x == p) {
+    dinv[ty * IB + tx] = d[ty][tx];
+  } else {
+    double acc = 0.0;
+#pragma unroll 8
+    for (int k = 0; k < IB; ++k) acc += d[ty][k] * mp[k][tx];
+    const int cj = j0 + tx;
+    if (cj < n) jb.rbuf[(size_t)ty * n + cj] = acc;
+  }
+}
+
+// step kernel B: M_ij -= M_ip R_j for i, j != p.  CTA tile 64 x 64, 256 threads, 4 x 4 per thread.
+__global__ void __launch_bounds__(256) inv_update_kernel(const InvDev* __restrict__ jobs, int p) {
+  const InvDev jb = jobs[blockIdx.z];
+  const int n = jb.n;
+  const int p0 = p * IB;
+  if (p0 >= n) return;
+  const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  if (i0 >= n || j0 >= n) return;
+  __shared__ double cs[64][IB + 1];  // M_ip tile  [64 rows][32]
+  __shared__ double rs[IB][64 + 1];  // R tile     [32][64 cols]
+  const int nb = min(IB, n - p0);
+  for (int idx = threadIdx.x; idx < 64 * IB; idx += 256) {
+    const int r = idx / IB, k = idx % IB;
+    const int gi = i0 + r;
+    cs[r][k] = (gi < n && k < nb) ? jb.m[(size_t)gi * n + p0 + k] : 0.0;
+  }
+  for (int idx = threadIdx.x; idx < IB * 64; idx += 256) {
+    const int k = idx / 64, c = idx % 64;
+    const int gj = j0 + c;
+    rs[k][c] = (gj < n && k < nb) ? jb.rbuf[(size_t)k * n + gj] : 0.0;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  double acc[4][4] = {};
+#pragma unroll 4
+  for (int k = 0; k < IB; ++k) {
+    double a[4], b[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      a[q] = cs[ty + 16 * q][k];
+      b[q] = rs[k][tx + 16 * q];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[q][r] += a[q] * b[r];
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int gi = i0 + ty + 16 * q;
+    if (gi >= n || (gi >= p0 && gi < p0 + IB)) continue;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int gj = j0 + tx + 16 * r;
+      if (gj >= n || (gj >= p0 && gj < p0 + IB)) continue;
+      jb.m[(size_t)gi * n + gj] -= acc[q][r];
+    }
+  }
+}
+
+// step kernel C: column panel M_ip = -M_ip D^-1 (i != p), row panel M_pj = R_j (j != p), M_pp = D^-1.
+// grid.x = row blocks of 32; 1024 threads.
+__global__ void __launch_bounds__(1024) inv_colpanel_kernel(const InvDev* __restrict__ jobs, int p) {
+  const InvDev jb = jobs[blockIdx.z];
+  const int n = jb.n;
+  const int p0 = p * IB;
+  if (p0 >= n) return;
+  const int i0 = blockIdx.x * IB;
+  if (i0 >= n) return;
+  __shared__ double d[IB][IB + 1];
+  __shared__ double c[IB][IB + 1];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int nb = min(IB, n - p0);
+  const double* dinv = jb.rbuf + (size_t)IB * n;
+  d[ty][tx] = dinv[ty * IB + tx];
+  const int gi = i0 + ty;
+  if (blockIdx.x == p) {
+    // this block holds the pivot rows: write D^-1 and the row panel
+    __syncthreads();
+    if (ty < nb && tx < nb) jb.m[(size_t)(p0 + ty) * n + p0 + tx] = d[ty][tx];
+    for (int j = threadIdx.x; j < nb * n; j += 1024) {
+      const int r = j / n, col = j % n;
+      if (col >= p0 && col < p0 + IB) continue;
+      jb.m[(size_t)(p0 + r) * n + col] = jb.rbuf[(size_t)r * n + col];
+    }
+    return;
+  }
+  c[ty][tx] = (gi < n && tx < nb) ? jb.m[(size_t)gi * n + p0 + tx] : 0.0;
+  __syncthreads();
+  double acc = 0.0;
+#pragma unroll 8
+  for (int k = 0; k < IB; ++k) acc += c[ty][k] * d[k][tx];
+  if (gi < n && tx < nb) jb.m[(size_t)gi * n + p0 + tx] = -acc;
+}
+
+__global__ void inv_finish_kernel(const InvDev* __restrict__ jobs) {
+  const InvDev jb = jobs[blockIdx.z];
+  const int n = jb.n;
+  const size_t total = (size_t)n * jb.ld_planes;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int r = (int)(i / jb.ld_planes), c = (int)(i % jb.ld_planes);
+    float v = 0.0f;
+    if (c < n) {
+      v = (float)(0.5 * (jb.m[(size_t)r * n + c] + jb.m[(size_t)c * n + r]));
+      jb.inv[(size_t)r * n + c] = v;
+    }
+    bf16 p0, p1, p2;
+    split3(v, p0, p1, p2);
+    jb.planes[0][i] = p0;
+    jb.planes[1][i] = p1;
+    jb.planes[2][i] = p2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// reductions and the fused optimiser steps
+// ------------------------------------------------------------------------------------------------
+// partial[b] = sum over the b-th contiguous chunk of a[i] * b[i]   (deterministic two-stage reduction)
+__global__ void __launch_bounds__(256) dot_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t count,
+                                                          float* __restrict__ partial) {
+  __shared__ double red[8];
+  const size_t per = (count + gridDim.x - 1) / gridDim.x;
+  const size_t i0 = (size_t)blockIdx.x * per;
+  const size_t i1 = i0 + per < count ? i0 + per : count;
+  double acc = 0.0;
+  for (size_t i = i0 + threadIdx.x; i < i1; i += 256) acc += (double)a[i] * (double)b[i];
+  acc = warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double v = 0.0;
+    for (int w = 0; w < 8; ++w) v += red[w];
+    partial[blockIdx.x] = (float)v;
+  }
+}
+
+__device__ __forceinline__ float sum_partials(const float* partial, int num) {
+  // every thread of the block needs the same scalar: warp 0 reduces in a fixed order, broadcast via smem
+  __shared__ float total;
+  if (threadIdx.x < 32) {
+    double v = 0.0;
+    for (int i = threadIdx.x; i < num; i += 32) v += (double)partial[i];
+    v = warp_sum_d(v);
+    if (threadIdx.x == 0) total = (float)v;
+  }
+  __syncthreads();
+  return total;
+}
+
+// K-FAC: s = sum <V, U>; c = min(1, sqrt(kappa / (lr^2 s))); v <- mu v + c U; theta <- theta - lr v
+// (kfac _clip_updates / _update_velocities / GradientDescentOptimizer; a2c_acktr.py:245-246)
+__global__ void __launch_bounds__(256) kfac_step_kernel(float* __restrict__ params, float* __restrict__ vel,
+                                                        const float* __restrict__ precon, size_t count,
+                                                        const float* __restrict__ partial, int num_partials,
+                                                        const Sched* __restrict__ sched, float mu, float kappa,
+                                                        float* __restrict__ out_scalars) {
+  const float lr = sched->lr;
+  const float s = sum_partials(partial, num_partials);
+  float c = 1.0f;
+  if (s > 0.0f) c = fminf(1.0f, sqrtf(kappa / (lr * lr * s)));
+  if (blockIdx.x == 0 && threadIdx.x == 0 && out_scalars) {
+    out_scalars[0] = c;
+    out_scalars[1] = s;
+    out_scalars[3] = lr;
+  }
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    const float v = mu * vel[i] + c * precon[i];
+    vel[i] = v;
+    params[i] -= lr * v;
+  }
+}
+
+// ClipGlobalNormOptimizer(MomentumOptimizer): g <- g * clip / max(||g||, clip); acc <- mu acc + g; theta -= lr acc
+// (nn.py:185-189, a2c_acktr.py:240-241)
+__global__ void __launch_bounds__(256) momentum_clip_kernel(float* __restrict__ params, float* __restrict__ accum,
+                                                            const float* __restrict__ grads, size_t count,
+                                                            const float* __restrict__ partial, int num_partials, float lr,
+                                                            float mu, float clip, float* __restrict__ out_scalars) {
+  const float sq = sum_partials(partial, num_partials);
+  const float norm = sqrtf(sq);
+  const float scale = clip / fmaxf(norm, clip);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && out_scalars) out_scalars[0] = norm;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    const float a = mu * accum[i] + grads[i] * scale;
+    accum[i] = a;
+    params[i] -= lr * a;
+  }
+}
+
+// ClipGlobalNormOptimizer(RMSPropOptimizer) with the TF-1 defaults (decay 0.9, momentum 0, eps 1e-10, ms = 1 at start):
+// ms <- d ms + (1-d) g^2; theta -= lr g / sqrt(ms + eps)     (a2c_acktr.py:250-251)
+__global__ void __launch_bounds__(256) rmsprop_clip_kernel(float* __restrict__ params, float* __restrict__ ms,
+                                                           const float* __restrict__ grads, size_t count,
+                                                           const float* __restrict__ partial, int num_partials,
+                                                           const Sched* __restrict__ sched, float decay, float eps, float clip,
+                                                           float* __restrict__ out_scalars) {
+  const float lr = sched->lr;
+  const float sq = sum_partials(partial, num_partials);
+  const float norm = sqrtf(sq);
+  const float scale = clip / fmaxf(norm, clip);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && out_scalars) {
+    out_scalars[0] = norm;
+    out_scalars[1] = lr;
+  }
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    const float g = grads[i] * scale;
+    const float m = decay * ms[i] + (1.0f - decay) * g * g;
+    ms[i] = m;
+    params[i] -= lr * g / sqrtf(m + eps);
+  }
+}
+
+// schedule state (one thread)
+__global__ void sched_begin_kernel(Sched* s, float lr_start, float lr_end, double decay_steps, float* out_lr) {
+  // nn.py:154-156 linear_decay = polynomial_decay(power 1, cycle False), evaluated at the step the update starts with
+  double g = (double)s->gs;
+  if (g > decay_steps) g = decay_steps;
+  s->lr = (float)(((double)lr_start - (double)lr_end) * (1.0 - g / decay_steps) + (double)lr_end);
+  if (out_lr) *out_lr = s->lr;
+}
+__global__ void sched_advance_kernel(Sched* s, int gs_inc, int ncov_inc, float ema_decay, int zero_debias) {
+  s->gs += (unsigned long long)gs_inc;
+  s->ncov += (unsigned long long)ncov_inc;
+  if (ncov_inc) {
+    double d = 1.0;
+    if (zero_debias && s->ncov > 0) d = 1.0 / (1.0 - pow((double)ema_decay, (double)s->ncov));
+    s->debias = (float)d;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+int sched_begin(Sched* s, float lr_start, float lr_end, double decay_steps, float* out_lr, cudaStream_t st) {
+  sched_begin_kernel<<<1, 1, 0, st>>>(s, lr_start, lr_end, decay_steps, out_lr);
+  ACX_LAUNCH_CHECK();
+  return 0;
+}
+int sched_advance(Sched* s, int gs_inc, int ncov_inc, float ema_decay, int zero_debias, cudaStream_t st) {
+  sched_advance_kernel<<<1, 1, 0, st>>>(s, gs_inc, ncov_inc, ema_decay, zero_debias);
+  ACX_LAUNCH_CHECK();
+  return 0;
+}
+
+static int grid_for(size_t count, int threads, int max_blocks) {
+  size_t b = (count + threads - 1) / threads;
+  if (b > (size_t)max_blocks) b = max_blocks;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+int homog_border(float* a, int d, const float* colsum_scaled, cudaStream_t st) {
+  homog_border_kernel<<<ceil_div(d, 128), 128, 0, st>>>(a, d, colsum_scaled);
+  ACX_LAUNCH_CHECK();
+  return 0;
+}
+int ema_update(float* s, const float* c, size_t count, float decay, float scale_c, cudaStream_t st) {
+  ACX_CHECK(((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(c)) & 15) == 0, "unaligned factor region");
+  ema_kernel<<<grid_for(count / 4 + 1, 256, 148 * 8), 256, 0, st>>>(s, c, count, decay, (1.0f - decay) * scale_c);
+  ACX_LAUNCH_CHECK();
+  return 0;
+}
+int fill_f32(float* p, size_t count, float v, cudaStream_t st) {
+  if (count == 0) return 0;
+  fill_kernel<<<grid_for(count, 256, 148 * 8), 256, 0, st>>>(p, count, v);
+  ACX_LAUNCH_CHECK();
+  return 0;
+}
+int scale_f32(float* p, size_t count, float v, cudaStream_t st) {
+  if (count == 0) return 0;
+  scale_kernel<<<grid_for(count, 256, 148 * 8), 256, 0, st>>>(p, count, v);
+  ACX_LAUNCH_CHECK();
+  return 0;
+}
+int compute_dampings(const float* const* d_a_ptrs, const float* const* d_g_ptrs, const int* d_a_dims, const int* d_g_dims,
+                     const float* d_lambda, int num_layers, float* d_damp, cudaStream_t st) {
+  dampings_kernel<<<num_layers, 32, 0, st>>>(d_a_ptrs, d_g_ptrs, d_a_dims, d_g_dims, d_lambda, num_layers, d_damp);
+  ACX_LAUNCH_CHECK();
+  return 0;
+}
+
+int spd_inverse_batched(const InvJob* h_jobs, const InvJob* d_jobs, int num_jobs, const Sched* sched, const float* d_damp,
+                        cudaStream_t st) {
+  static_assert(sizeof(InvJob) == sizeof(InvDev), "InvJob and InvDev must have the same layout");
+  const InvDev* dj = reinterpret_cast<const InvDev*>(d_jobs);
+  int nmax = 0;
+  for (int i = 0; i < num_jobs; ++i) nmax = h_jobs[i].n > nmax ? h_jobs[i].n : nmax;
+  ACX_CHECK(nmax > 0, "no inverse jobs");
+  {
+    dim3 grid(grid_for((size_t)nmax * nmax, 256, 148 * 4), 1, num_jobs);
+    inv_prepare_kernel<<<grid, 256, 0, st>>>(dj, sched, d_damp);
+    ACX_LAUNCH_CHECK();
+  }
+  const int steps = ceil_div(nmax, IB);
+  for (int p = 0; p < steps; ++p) {
+    // jobs are sorted by decreasing n by the caller, so the jobs still active at step p are a prefix
+    int active = 0;
+    int nact = 0;
+    for (int i = 0; i < num_jobs; ++i)
+      if (h_jobs[i].n > p * IB) {
+        active = i + 1;
+        nact = h_jobs[i].n > nact ? h_jobs[i].n : nact;
+      }
+    if (active == 0) break;
+    inv_rowpanel_kernel<<<dim3(ceil_div(nact, IB), 1, active), 1024, 0, st>>>(dj, p);
+    ACX_LAUNCH_CHECK();
+    if (nact > IB) {
+      inv_update_kernel<<<dim3(ceil_div(nact, 64), ceil_div(nact, 64), active), 256, 0, st>>>(dj, p);
+      ACX_LAUNCH_CHECK();
+    }
+    inv_colpanel_kernel<<<dim3(ceil_div(nact, IB), 1, active), 1024, 0, st>>>(dj, p);
+    ACX_LAUNCH_CHECK();
+  }
+  {
+    dim3 grid(grid_for((size_t)nmax * (nmax + 8), 256, 148 * 4), 1, num_jobs);
+    inv_finish_kernel<<<grid, 256, 0, st>>>(dj);
+    ACX_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+int dot_partial(const float* a, const float* b, size_t count, float* partial, int num_partials, cudaStream_t st) {
+  dot_partial_kernel<<<num_partials, 256, 0, st>>>(a, b, count, partial);
+  ACX_LAUNCH_CHECK();
+  return 0;
+}
+int kfac_step(float* params, float* velocity, const float* precon, size_t count, const float* dot_partials, int num_partials,
+              const Sched* sched, float momentum, float norm_constraint, float* out_scalars, cudaStream_t st) {
+  kfac_step_kernel<<<grid_for(count, 256, 148 * 4), 256, 0, st>>>(params, velocity, precon, count, dot_partials, num_partials,
+                                                                 sched, momentum, norm_constraint, out_scalars);
+  ACX_LAUNCH_CHECK();
+  return 0;
+}
+int momentum_clip_step(float* params, float* accum, const float* grads, size_t count, const float* sq_partials, int num_partials,
+                       float lr, float momentum, float clip_norm, float* out_scalars, cudaStream_t st) {
+  momentum_clip_kernel<<<grid_for(count, 256, 148 * 4), 256, 0, st>>>(params, accum, grads, count, sq_partials, num_partials, lr,
+                                                                     momentum, clip_norm, out_scalars);
+  ACX_LAUNCH_CHECK();
+  return 0;
+}
+int rmsprop_clip_step(float* params, float* ms, const float* grads, size_t count, const float* sq_partials, int num_partials,
+                      const Sched* sched, float decay, float epsilon, float clip_norm, float* out_scalars, cudaStream_t st) {
+  rmsprop_clip_kernel<<<grid_for(count, 256, 148 * 4), 256, 0, st>>>(params, ms, grads, count, sq_partials, num_partials, sched,
+                                                                    decay, epsilon, clip_norm, out_scalars);
+  ACX_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace acx

@@ -34,10 +34,10 @@ __global__ void im2col_conv1_kernel(const uint8_t* __restrict__ obs, bf16* __res
 
 // generic NHWC bf16 im2col, patch order (ky, kx, c): each (row, ky) segment is k*C contiguous elements.
 // grid.y = plane.
-__global__ void im2col_bf16_kernel(const bf16* __restrict__ in0, const bf16* __restrict__ in1, bf16* __restrict__ out0,
-                                   bf16* __restrict__ out1, int rows_total, int hw_in, int c, int k, int s, int hw_out) {
-  const bf16* in = blockIdx.y == 0 ? in0 : in1;
-  bf16* out = blockIdx.y == 0 ? out0 : out1;
+__global__ void im2col_bf16_kernel(const Planes pin, const Planes pout, int rows_total, int hw_in, int c, int k, int s,
+                                   int hw_out) {
+  const bf16* __restrict__ in = pin.p[blockIdx.y];
+  bf16* __restrict__ out = pout.p[blockIdx.y];
   const int seg_vec = k * c / 8;               // uint4 per (row, ky) segment
   const long long total = (long long)rows_total * k * seg_vec;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -57,9 +57,8 @@ __global__ void im2col_bf16_kernel(const bf16* __restrict__ in0, const bf16* __r
 //   dX[n,y,x,c] = sum_{ky,kx : (y-ky)%s==0, (x-kx)%s==0, in range} dP[(n,oy,ox), (ky,kx,c)]
 //   dPre[n,y,x,c] = dX * 1[act(n % mask_n, y, x, c) > 0]       (true rows and Fisher rows share the mask)
 // One thread per (n, y, x, 4 channels).
-__global__ void col2im_mask_split_kernel(const float* __restrict__ dp, const bf16* __restrict__ act_hi, bf16* __restrict__ out_hi,
-                                         bf16* __restrict__ out_lo, int n_total, int mask_n, int hw_in, int c, int k, int s,
-                                         int hw_out) {
+__global__ void col2im_mask_split_kernel(const float* __restrict__ dp, const bf16* __restrict__ act_hi, const Planes out,
+                                         int n_total, int mask_n, int hw_in, int c, int k, int s, int hw_out) {
   const int cv = c / 4;
   const long long total = (long long)n_total * hw_in * hw_in * cv;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -91,25 +90,24 @@ __global__ void col2im_mask_split_kernel(const float* __restrict__ dp, const bf1
   const size_t pix = ((size_t)((n % mask_n) * hw_in + y) * hw_in + x) * c + c4;
   const size_t opix = ((size_t)(n * hw_in + y) * hw_in + x) * c + c4;
   const float vals[4] = {acc.x, acc.y, acc.z, acc.w};
-  __align__(8) bf16 hi[4], lo[4];
+  __align__(8) bf16 hi[4], mid[4], lo[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const float m = __bfloat162float(act_hi[pix + j]);
     const float v = m > 0.0f ? vals[j] : 0.0f;
-    bf16 p2;
-    split3(v, hi[j], lo[j], p2);
+    split3(v, hi[j], mid[j], lo[j]);
   }
-  *reinterpret_cast<uint2*>(out_hi + opix) = *reinterpret_cast<const uint2*>(hi);
-  *reinterpret_cast<uint2*>(out_lo + opix) = *reinterpret_cast<const uint2*>(lo);
+  *reinterpret_cast<uint2*>(out.p[0] + opix) = *reinterpret_cast<const uint2*>(hi);
+  if (out.n > 1) *reinterpret_cast<uint2*>(out.p[1] + opix) = *reinterpret_cast<const uint2*>(mid);
+  if (out.n > 2) *reinterpret_cast<uint2*>(out.p[2] + opix) = *reinterpret_cast<const uint2*>(lo);
 }
 
 // ------------------------------------------------------------------------------------------------
 // heads forward: act4 planes [R,512] x W_pol [512,A], W_val [512,1] (+ biases) -> logits [R,A], values [R]
 // (envs/atari/model.py:207-216).  One warp per row.
 // ------------------------------------------------------------------------------------------------
-__global__ void heads_fwd_kernel(const bf16* __restrict__ a_hi, const bf16* __restrict__ a_lo, const float* __restrict__ vpol,
-                                 const float* __restrict__ vval, int rows, int num_actions, float* __restrict__ logits,
-                                 float* __restrict__ values) {
+__global__ void heads_fwd_kernel(const Planes act4, const float* __restrict__ vpol, const float* __restrict__ vval, int rows,
+                                 int num_actions, float* __restrict__ logits, float* __restrict__ values) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -117,7 +115,10 @@ __global__ void heads_fwd_kernel(const bf16* __restrict__ a_hi, const bf16* __re
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     const size_t idx = (size_t)row * 512 + lane + 32 * j;
-    x[j] = __bfloat162float(a_hi[idx]) + __bfloat162float(a_lo[idx]);
+    float v = __bfloat162float(act4.p[0][idx]);
+    if (act4.n > 1) v += __bfloat162float(act4.p[1][idx]);
+    if (act4.n > 2) v += __bfloat162float(act4.p[2][idx]);
+    x[j] = v;
   }
   for (int a = 0; a <= num_actions; ++a) {
     const float* w = a < num_actions ? vpol + a : vval;
@@ -161,11 +162,12 @@ __device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5
 __global__ void __launch_bounds__(256) loss_grad_kernel(const float* __restrict__ logits, const float* __restrict__ values,
                                                         const uint8_t* __restrict__ actions, const float* __restrict__ targets,
                                                         const int32_t* __restrict__ fisher_labels,
-                                                        const float* __restrict__ fisher_eps, uint64_t seed, uint64_t step,
-                                                        int n_rows, int num_actions, float beta, float value_weight,
+                                                        const float* __restrict__ fisher_eps, uint64_t seed,
+                                                        const Sched* __restrict__ sched, int n_rows, int num_actions, float beta, float value_weight,
                                                         float* __restrict__ dheads, float* __restrict__ scalars,
                                                         int want_fisher) {
   __shared__ float red[3][8];
+  const uint64_t step = sched ? sched->gs : 0ull;
   float s_obj = 0.f, s_ent = 0.f, s_val = 0.f;
   const float inv_n = 1.0f / (float)n_rows;
   const int ld = num_actions + 1;
@@ -252,7 +254,7 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(const float* __restrict_
 // ------------------------------------------------------------------------------------------------
 __global__ void heads_bwd_data_kernel(const float* __restrict__ dheads, const float* __restrict__ vpol,
                                       const float* __restrict__ vval, const bf16* __restrict__ act4_hi, int rows, int mask_rows,
-                                      int num_actions, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo) {
+                                      int num_actions, const Planes out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)rows * 512) return;
   const int j = (int)(i & 511), r = (int)(i >> 9);
@@ -261,17 +263,17 @@ __global__ void heads_bwd_data_kernel(const float* __restrict__ dheads, const fl
   for (int a = 0; a < num_actions; ++a) acc = fmaf(d[a], __ldg(vpol + (size_t)j * num_actions + a), acc);
   const float m = __bfloat162float(act4_hi[(size_t)(r % mask_rows) * 512 + j]);
   if (!(m > 0.0f)) acc = 0.0f;
-  bf16 hi, lo, p2;
-  split3(acc, hi, lo, p2);
-  out_hi[i] = hi;
-  out_lo[i] = lo;
+  bf16 hi, mid, lo;
+  split3(acc, hi, mid, lo);
+  out.p[0][i] = hi;
+  if (out.n > 1) out.p[1][i] = mid;
+  if (out.n > 2) out.p[2][i] = lo;
 }
 
 // (b) weight gradients of the two heads from the TRUE-loss rows: g_pol[j,a] = sum_n act4[n,j] dH[n,a]
 // (j = 512 is the bias row: sum_n dH[n,a]); same for the value head.  One CTA per j, 128 threads over n.
-__global__ void __launch_bounds__(128) heads_wgrad_kernel(const float* __restrict__ dheads, const bf16* __restrict__ act4_hi,
-                                                          const bf16* __restrict__ act4_lo, int n_rows, int num_actions,
-                                                          float* __restrict__ gpol, float* __restrict__ gval) {
+__global__ void __launch_bounds__(128) heads_wgrad_kernel(const float* __restrict__ dheads, const Planes act4, int n_rows,
+                                                          int num_actions, float* __restrict__ gpol, float* __restrict__ gval) {
   __shared__ float red[4][32];
   const int j = blockIdx.x;  // 0..512
   const int ld = num_actions + 1;
@@ -282,7 +284,9 @@ __global__ void __launch_bounds__(128) heads_wgrad_kernel(const float* __restric
     float x = 1.0f;
     if (j < 512) {
       const size_t idx = (size_t)n * 512 + j;
-      x = __bfloat162float(act4_hi[idx]) + __bfloat162float(act4_lo[idx]);
+      x = __bfloat162float(act4.p[0][idx]);
+      if (act4.n > 1) x += __bfloat162float(act4.p[1][idx]);
+      if (act4.n > 2) x += __bfloat162float(act4.p[2][idx]);
     }
     const float* d = dheads + (size_t)n * ld;
 #pragma unroll
@@ -336,17 +340,18 @@ __global__ void __launch_bounds__(256) heads_gfactor_kernel(const float* __restr
 // column sums of a planes matrix over rows [0, rows): two deterministic stages.
 // stage 1: grid (ceil(cols/128), chunks) ; stage 2: sums the chunks and scales.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) colsum_stage1_kernel(const bf16* __restrict__ hi, const bf16* __restrict__ lo, int rows,
-                                                            int cols, int ld, int rows_per_chunk, float* __restrict__ partial) {
+__global__ void __launch_bounds__(128) colsum_stage1_kernel(const Planes x, int rows, int cols, int rows_per_chunk,
+                                                            float* __restrict__ partial) {
   const int c = blockIdx.x * 128 + threadIdx.x;
   if (c >= cols) return;
   const int r0 = blockIdx.y * rows_per_chunk;
   const int r1 = min(rows, r0 + rows_per_chunk);
   float acc = 0.f;
   for (int r = r0; r < r1; ++r) {
-    const size_t idx = (size_t)r * ld + c;
-    float v = __bfloat162float(hi[idx]);
-    if (lo) v += __bfloat162float(lo[idx]);
+    const size_t idx = (size_t)r * x.ld + c;
+    float v = __bfloat162float(x.p[0][idx]);
+    if (x.n > 1) v += __bfloat162float(x.p[1][idx]);
+    if (x.n > 2) v += __bfloat162float(x.p[2][idx]);
     acc += v;
   }
   partial[(size_t)blockIdx.y * cols + c] = acc;
@@ -430,43 +435,43 @@ int im2col_conv1(const uint8_t* obs, bf16* out, int rows_total, cudaStream_t st)
   ACX_LAUNCH_CHECK();
   return 0;
 }
-int im2col_bf16(const bf16* in0, const bf16* in1, bf16* out0, bf16* out1, int rows_total, int hw_in, int c, int k, int s,
-                int hw_out, cudaStream_t st) {
+int im2col_bf16(const Planes& in, const Planes& out, int rows_total, int hw_in, int c, int k, int s, int hw_out, cudaStream_t st) {
   const long long total = (long long)rows_total * k * (k * c / 8);
-  dim3 grid((unsigned)((total + 255) / 256), 2);
-  im2col_bf16_kernel<<<grid, 256, 0, st>>>(in0, in1, out0, out1, rows_total, hw_in, c, k, s, hw_out);
+  const int np = in.n < out.n ? in.n : out.n;
+  dim3 grid((unsigned)((total + 255) / 256), np);
+  im2col_bf16_kernel<<<grid, 256, 0, st>>>(in, out, rows_total, hw_in, c, k, s, hw_out);
   ACX_LAUNCH_CHECK();
   return 0;
 }
-int col2im_mask_split(const float* dp, const bf16* act_hi, bf16* out_hi, bf16* out_lo, int n_total, int mask_n, int hw_in, int c,
-                      int k, int s, int hw_out, cudaStream_t st) {
+int col2im_mask_split(const float* dp, const bf16* act_hi, const Planes& out, int n_total, int mask_n, int hw_in, int c, int k, int s,
+                      int hw_out, cudaStream_t st) {
   const long long total = (long long)n_total * hw_in * hw_in * (c / 4);
-  col2im_mask_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dp, act_hi, out_hi, out_lo, n_total, mask_n, hw_in,
-                                                                           c, k, s, hw_out);
+  col2im_mask_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dp, act_hi, out, n_total, mask_n, hw_in, c, k, s,
+                                                                           hw_out);
   ACX_LAUNCH_CHECK();
   return 0;
 }
-int heads_fwd(const bf16* a_hi, const bf16* a_lo, const float* vpol, const float* vval, int rows, int num_actions, float* logits,
-              float* values, cudaStream_t st) {
-  heads_fwd_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(a_hi, a_lo, vpol, vval, rows, num_actions, logits, values);
+int heads_fwd(const Planes& act4, const float* vpol, const float* vval, int rows, int num_actions, float* logits, float* values,
+              cudaStream_t st) {
+  heads_fwd_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(act4, vpol, vval, rows, num_actions, logits, values);
   ACX_LAUNCH_CHECK();
   return 0;
 }
 int loss_grad(const float* logits, const float* values, const uint8_t* actions, const float* targets, const int32_t* fl,
-              const float* fe, uint64_t seed, uint64_t step, int n_rows, int num_actions, float beta, float vw, float* dheads,
+              const float* fe, uint64_t seed, const Sched* sched, int n_rows, int num_actions, float beta, float vw, float* dheads,
               float* scalars, int want_fisher, cudaStream_t st) {
-  loss_grad_kernel<<<1, 256, 0, st>>>(logits, values, actions, targets, fl, fe, seed, step, n_rows, num_actions, beta, vw, dheads,
+  loss_grad_kernel<<<1, 256, 0, st>>>(logits, values, actions, targets, fl, fe, seed, sched, n_rows, num_actions, beta, vw, dheads,
                                       scalars, want_fisher);
   ACX_LAUNCH_CHECK();
   return 0;
 }
-int heads_bwd(const float* dheads, const float* vpol, const float* vval, const bf16* act4_hi, const bf16* act4_lo, int n_rows,
-              int rows_bwd, int num_actions, bf16* dpre4_hi, bf16* dpre4_lo, float* gpol, float* gval, cudaStream_t st) {
+int heads_bwd(const float* dheads, const float* vpol, const float* vval, const Planes& act4, int n_rows, int rows_bwd,
+              int num_actions, const Planes& dpre4, float* gpol, float* gval, cudaStream_t st) {
   const long long total = (long long)rows_bwd * 512;
-  heads_bwd_data_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dheads, vpol, vval, act4_hi, rows_bwd, n_rows, num_actions,
-                                                                        dpre4_hi, dpre4_lo);
+  heads_bwd_data_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dheads, vpol, vval, act4.p[0], rows_bwd, n_rows,
+                                                                        num_actions, dpre4);
   ACX_LAUNCH_CHECK();
-  heads_wgrad_kernel<<<513, 128, 0, st>>>(dheads, act4_hi, act4_lo, n_rows, num_actions, gpol, gval);
+  heads_wgrad_kernel<<<513, 128, 0, st>>>(dheads, act4, n_rows, num_actions, gpol, gval);
   ACX_LAUNCH_CHECK();
   return 0;
 }
@@ -475,15 +480,15 @@ int heads_gfactor(const float* dheads_fisher, int n_rows, int num_actions, float
   ACX_LAUNCH_CHECK();
   return 0;
 }
-int colsum(const bf16* hi, const bf16* lo, int rows, int cols, int ld, float scale, float* partial, int max_chunks, float* out,
-           int out_stride, cudaStream_t st) {
+int colsum(const Planes& x, int rows, int cols, float scale, float* partial, int max_chunks, float* out, int out_stride,
+           cudaStream_t st) {
   int chunks = ceil_div(rows, 256);
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
   const int rpc = ceil_div(rows, chunks);
   chunks = ceil_div(rows, rpc);
   dim3 grid(ceil_div(cols, 128), chunks);
-  colsum_stage1_kernel<<<grid, 128, 0, st>>>(hi, lo, rows, cols, ld, rpc, partial);
+  colsum_stage1_kernel<<<grid, 128, 0, st>>>(x, rows, cols, rpc, partial);
   ACX_LAUNCH_CHECK();
   colsum_stage2_kernel<<<ceil_div(cols, 128), 128, 0, st>>>(partial, chunks, cols, scale, out, out_stride);
   ACX_LAUNCH_CHECK();

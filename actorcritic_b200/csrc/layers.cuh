@@ -4,25 +4,40 @@
 
 namespace acx {
 
+// device-resident schedule state: every kernel that needs the learning rate, the zero-debias factor or the
+// RNG step reads it from here, so a captured CUDA graph of an update stays valid from step to step.
+struct Sched {
+  unsigned long long gs;    // global_step (kfac_utils.py:38-53 semantics: cold step and K-FAC apply both count)
+  unsigned long long ncov;  // number of covariance (EMA) updates so far
+  float lr;                 // linear_decay(gs at the start of the update)  nn.py:154-156
+  float debias;             // 1 / (1 - decay^ncov)   (1 when ncov == 0)
+};
+
+// a real matrix held as n bf16 planes p[0] + p[1] + p[2] (hi, mid, lo), row-major with leading dimension ld
+struct Planes {
+  bf16* p[3] = {nullptr, nullptr, nullptr};
+  int n = 0;
+  int ld = 0;
+};
+
 int gemm_dispatch(const acx_gemm_t* g, int impl, cudaStream_t st);
 int returns_launch(const float* rewards, const uint8_t* terminals, const float* values, const float* bootstrap, float gamma,
                    int num_envs, int num_steps, float* targets, float* adv, cudaStream_t st);
 
 int im2col_conv1(const uint8_t* obs, bf16* out, int rows_total, cudaStream_t st);
-int im2col_bf16(const bf16* in0, const bf16* in1, bf16* out0, bf16* out1, int rows_total, int hw_in, int c, int k, int s,
-                int hw_out, cudaStream_t st);
-int col2im_mask_split(const float* dp, const bf16* act_hi, bf16* out_hi, bf16* out_lo, int n_total, int mask_n, int hw_in, int c,
-                      int k, int s, int hw_out, cudaStream_t st);
-int heads_fwd(const bf16* a_hi, const bf16* a_lo, const float* vpol, const float* vval, int rows, int num_actions, float* logits,
-              float* values, cudaStream_t st);
+int im2col_bf16(const Planes& in, const Planes& out, int rows_total, int hw_in, int c, int k, int s, int hw_out, cudaStream_t st);
+int col2im_mask_split(const float* dp, const bf16* act_hi, const Planes& out, int n_total, int mask_n, int hw_in, int c, int k, int s,
+                      int hw_out, cudaStream_t st);
+int heads_fwd(const Planes& act4, const float* vpol, const float* vval, int rows, int num_actions, float* logits, float* values,
+              cudaStream_t st);
 int loss_grad(const float* logits, const float* values, const uint8_t* actions, const float* targets, const int32_t* fl,
-              const float* fe, uint64_t seed, uint64_t step, int n_rows, int num_actions, float beta, float vw, float* dheads,
+              const float* fe, uint64_t seed, const Sched* sched, int n_rows, int num_actions, float beta, float vw, float* dheads,
               float* scalars, int want_fisher, cudaStream_t st);
-int heads_bwd(const float* dheads, const float* vpol, const float* vval, const bf16* act4_hi, const bf16* act4_lo, int n_rows,
-              int rows_bwd, int num_actions, bf16* dpre4_hi, bf16* dpre4_lo, float* gpol, float* gval, cudaStream_t st);
+int heads_bwd(const float* dheads, const float* vpol, const float* vval, const Planes& act4, int n_rows, int rows_bwd,
+              int num_actions, const Planes& dpre4, float* gpol, float* gval, cudaStream_t st);
 int heads_gfactor(const float* dheads_fisher, int n_rows, int num_actions, float* g_pol, float* g_val, cudaStream_t st);
-int colsum(const bf16* hi, const bf16* lo, int rows, int cols, int ld, float scale, float* partial, int max_chunks, float* out,
-           int out_stride, cudaStream_t st);
+int colsum(const Planes& x, int rows, int cols, float scale, float* partial, int max_chunks, float* out, int out_stride,
+           cudaStream_t st);
 int transpose_split(const float* in, int k_rows, int c_cols, bf16* p0, bf16* p1, bf16* p2, int num_planes, int ld_out,
                     cudaStream_t st);
 int sample_actions(const float* logits, const float* uniform, uint64_t seed, uint64_t step, int rows, int num_actions, int greedy,
@@ -35,8 +50,8 @@ struct InvJob {          // one SPD inverse: M = debias * S + damp * I  (fp64) -
   const float* s;        // [n, n] running covariance sum
   int n;
   int damp_index;        // index into the device damping array
-  double* work_m;        // [n, n] fp64 scratch (Cholesky in place)
-  double* work_x;        // [n, n] fp64 scratch (L^-1)
+  double* work_m;        // [n, n] fp64 scratch (inverted in place)
+  double* work_x;        // [32, n] row panel + [32, 32] pivot-block inverse
   float* inv;            // [n, n] fp32 result
   bf16* planes[3];       // [n, ld_planes]
   int ld_planes;
@@ -45,15 +60,17 @@ int homog_border(float* a, int d, const float* colsum_scaled, cudaStream_t st);
 int ema_update(float* s, const float* c, size_t count, float decay, float scale_c, cudaStream_t st);
 int compute_dampings(const float* const* d_a_ptrs, const float* const* d_g_ptrs, const int* d_a_dims, const int* d_g_dims,
                      const float* d_lambda, int num_layers, float* d_damp, cudaStream_t st);
-int spd_inverse_batched(const InvJob* h_jobs, const InvJob* d_jobs, int num_jobs, float debias, const float* d_damp,
+int spd_inverse_batched(const InvJob* h_jobs, const InvJob* d_jobs, int num_jobs, const Sched* sched, const float* d_damp,
                         cudaStream_t st);
+int sched_begin(Sched* s, float lr_start, float lr_end, double decay_steps, float* out_lr, cudaStream_t st);
+int sched_advance(Sched* s, int gs_inc, int ncov_inc, float ema_decay, int zero_debias, cudaStream_t st);
 int dot_partial(const float* a, const float* b, size_t count, float* partial, int num_partials, cudaStream_t st);
 int kfac_step(float* params, float* velocity, const float* precon, size_t count, const float* dot_partials, int num_partials,
-              float lr, float momentum, float norm_constraint, float* out_scalars, cudaStream_t st);
+              const Sched* sched, float momentum, float norm_constraint, float* out_scalars, cudaStream_t st);
 int momentum_clip_step(float* params, float* accum, const float* grads, size_t count, const float* sq_partials, int num_partials,
                        float lr, float momentum, float clip_norm, float* out_scalars, cudaStream_t st);
 int rmsprop_clip_step(float* params, float* ms, const float* grads, size_t count, const float* sq_partials, int num_partials,
-                      float lr, float decay, float epsilon, float clip_norm, float* out_scalars, cudaStream_t st);
+                      const Sched* sched, float decay, float epsilon, float clip_norm, float* out_scalars, cudaStream_t st);
 int fill_f32(float* p, size_t count, float v, cudaStream_t st);
 int scale_f32(float* p, size_t count, float v, cudaStream_t st);
 

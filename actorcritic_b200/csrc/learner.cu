@@ -1,17 +1,784 @@
-// learner.cu - placeholder until the learner engine lands (keeps the C ABI complete for the first GPU bring-up)
-#include "common.cuh"
-extern "C" {
-size_t acx_learner_arena_bytes(const acx_learner_config_t*) { return 0; }
-acx_learner_t* acx_learner_create(const acx_learner_config_t*, void*, size_t) { acx::set_error("learner not built yet"); return nullptr; }
-void acx_learner_destroy(acx_learner_t*) {}
-size_t acx_learner_num_params(const acx_learner_t*) { return 0; }
-int acx_learner_set_params(acx_learner_t*, const float*, void*) { return 1; }
-int acx_learner_get_params(acx_learner_t*, float*, void*) { return 1; }
-float* acx_learner_buffer(acx_learner_t*, const char*, size_t*) { return nullptr; }
-uint8_t* acx_learner_obs_buffer(acx_learner_t*, size_t*) { return nullptr; }
-int acx_learner_phase1(acx_learner_t*, const int32_t*, const float*, void*) { return 1; }
-int acx_learner_phase2(acx_learner_t*, void*) { return 1; }
-int64_t acx_learner_global_step(const acx_learner_t*) { return 0; }
-void acx_learner_set_global_step(acx_learner_t*, int64_t) {}
-int acx_learner_act(acx_learner_t*, const uint8_t*, int, const float*, int, int32_t*, float*, float*, void*) { return 1; }
+// learner.cu - the ACKTR / A2C learner engine: one device arena, every matrix product on the tcgen05 GEMM
+// (gemm.cu), everything else on the streaming / reduction kernels of layers.cu and kfac.cu.
+//
+// One update = the reference's session.run(optimize_op, feed_dict) (a2c_acktr.py:117-126):
+//   phase 1  forward of the N train rows and the E bootstrap rows in one batch (envs/atari/model.py:113,116),
+//            returns/advantages (objectives.py:123-130), A2C loss and output gradients (objectives.py:132-154,78),
+//            backward for the true loss and - stacked as a second batch sharing weights and ReLU masks - for
+//            the Fisher-sample loss, weight gradients, and the 11 batch factor statistics.
+//            Everything a data-parallel job must sum lands in one flat fp32 bucket [grads | A | G | scalars].
+//   phase 2  schedule of ColdStartPeriodicInvUpdateKfacOpt.apply_gradients as coded (kfac_utils.py:38-53):
+//            cold momentum-SGD step or factor EMA, scheduled inverse refresh, precondition, KL clip, momentum,
+//            apply; or the A2C RMSProp step (a2c_acktr.py:250-251).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "layers.cuh"
+
+namespace acx {
+
+struct Layer {
+  const char* name;
+  int K, C;         // V_l = [K+1, C]
+  int T;            // output locations (1 for fc)
+  int Tnorm;        // T~_l used for lambda/T~ and the 1/T~ rescale
+  int conv, k, s, cin, hw_in, hw_out;
+  size_t off;       // offset of V_l in the flat parameter vector
+  int afac;         // index of its input factor (the two heads share one)
+};
+
+struct Buf {
+  void* ptr;
+  size_t bytes;
+};
+
+struct Arena {
+  uint8_t* base = nullptr;
+  size_t used = 0;
+  void* take(size_t bytes) {
+    used = align_up(used, 256);
+    void* p = base ? base + used : nullptr;
+    used += bytes;
+    return p;
+  }
+};
+
+}  // namespace acx
+
+using namespace acx;
+
+struct acx_learner {
+  acx_learner_config_t cfg;
+  int E, T, N, R, A, c3;
+  Layer L[6];
+  size_t num_params, params_pad;
+  int adim[5];
+  size_t aoff[5], goff[6], factor_floats;
+  // fp32 state
+  float *params, *precon, *velocity, *accum;
+  float *bucket, *grads, *stats, *bscalars;
+  size_t bucket_floats;
+  float *sums;            // running factor sums, same layout as stats
+  float *inv;             // fp32 inverses: A^-1 per layer (6) then G^-1 per layer (6)
+  size_t ainv_off[6], ginv_off[6], inv_floats;
+  Planes ainv_pl[6], ginv_pl[6];
+  float *damp, *lambdas, *scalars;
+  Sched* sched;
+  const float** d_a_ptrs;
+  const float** d_g_ptrs;
+  int *d_a_dims, *d_g_dims;
+  InvJob h_jobs[12];
+  InvJob* d_jobs;
+  // inputs
+  uint8_t *obs, *actions, *terminals;
+  float* rewards;
+  // activations
+  Planes P1, act1, P2, act2, P3, act3, act4;
+  Planes dpre4, dpre3, dpre2, dpre1;
+  float *dP, *logits, *values, *targets, *adv, *dheads;
+  Planes wT[4], wN[4];
+  Planes Vp, Wt;
+  float *colsum_partial, *colsum_tmp, *dot_partials;
+  float* ws;
+  size_t ws_bytes;
+  // host mirror of the schedule
+  int64_t gs, ncov;
+  bool inverses_valid;
+  uint64_t act_calls;
+  int lvl_fwd, lvl_bwd, lvl_factor, lvl_precon, act_planes;
+  std::map<std::string, Buf> named;
+};
+
+namespace acx {
+
+static const int kColsumChunks = 256;
+static const int kDotPartials = 64;
+
+static int pad8(int x) { return (x + 7) / 8 * 8; }
+
+static Planes take_planes(Arena& ar, int nplanes, size_t rows, int ld) {
+  Planes pl;
+  pl.n = nplanes;
+  pl.ld = ld;
+  for (int i = 0; i < nplanes; ++i) pl.p[i] = reinterpret_cast<bf16*>(ar.take(rows * (size_t)ld * sizeof(bf16)));
+  return pl;
 }
+
+static Planes offset_rows(const Planes& p, size_t rows) {
+  Planes q = p;
+  for (int i = 0; i < p.n; ++i) q.p[i] = p.p[i] + rows * (size_t)p.ld;
+  return q;
+}
+static Planes with_ld(const Planes& p, int ld) {
+  Planes q = p;
+  q.ld = ld;
+  return q;
+}
+static Planes first_planes(const Planes& p, int n) {
+  Planes q = p;
+  q.n = n < p.n ? n : p.n;
+  return q;
+}
+
+static void setup_layers(acx_learner* l) {
+  const int c3 = l->c3, A = l->A;
+  const int mode = l->cfg.num_locations_mode;
+  Layer defs[6] = {
+      {"conv1", 256, 32, 400, mode ? 84 * 84 / 16 : 400, 1, 8, 4, 4, 84, 20, 0, 0},
+      {"conv2", 512, 64, 81, mode ? 20 * 20 / 4 : 81, 1, 4, 2, 32, 20, 9, 0, 1},
+      {"conv3", 576, c3, 49, mode ? 81 : 49, 1, 3, 1, 64, 9, 7, 0, 2},
+      {"fc4", 49 * c3, 512, 1, 1, 0, 0, 0, 0, 0, 0, 0, 3},
+      {"fc_policy", 512, A, 1, 1, 0, 0, 0, 0, 0, 0, 0, 4},
+      {"fc_baseline", 512, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 4},
+  };
+  size_t off = 0;
+  for (int i = 0; i < 6; ++i) {
+    l->L[i] = defs[i];
+    l->L[i].off = off;
+    off += (size_t)(defs[i].K + 1) * defs[i].C;
+  }
+  l->num_params = off;
+  l->params_pad = align_up(off, 4);
+  const int adims[5] = {257, 513, 577, 49 * c3 + 1, 513};
+  size_t f = 0;
+  for (int i = 0; i < 5; ++i) {
+    l->adim[i] = adims[i];
+    l->aoff[i] = f;
+    f += align_up((size_t)adims[i] * adims[i], 4);
+  }
+  for (int i = 0; i < 6; ++i) {
+    l->goff[i] = f;
+    f += align_up((size_t)l->L[i].C * l->L[i].C, 4);
+  }
+  l->factor_floats = f;
+  size_t v = 0;
+  for (int i = 0; i < 6; ++i) {
+    const int d = l->L[i].K + 1;
+    l->ainv_off[i] = v;
+    v += align_up((size_t)d * d, 4);
+  }
+  for (int i = 0; i < 6; ++i) {
+    l->ginv_off[i] = v;
+    v += align_up((size_t)l->L[i].C * l->L[i].C, 4);
+  }
+  l->inv_floats = v;
+}
+
+static void reg(acx_learner* l, const char* name, void* p, size_t bytes) { l->named[name] = Buf{p, bytes}; }
+
+// lay the arena out (base == nullptr: size pass only)
+static size_t layout(acx_learner* l, uint8_t* base) {
+  Arena ar;
+  ar.base = base;
+  const int N = l->N, R = l->R, A = l->A, c3 = l->c3;
+  const size_t B2 = 2 * (size_t)N;
+  const size_t P = l->params_pad, F = l->factor_floats;
+  auto f32 = [&](size_t n) { return reinterpret_cast<float*>(ar.take(n * sizeof(float))); };
+  // ---- persistent fp32 state (one contiguous block so that it can be zeroed / checkpointed as a whole)
+  l->params = f32(P);
+  l->velocity = f32(P);
+  l->accum = f32(P);
+  l->precon = f32(P);
+  l->bucket_floats = P + F + 4;
+  l->bucket = f32(l->bucket_floats);
+  l->grads = l->bucket;
+  l->stats = l->bucket + P;
+  l->bscalars = l->bucket + P + F;
+  l->sums = f32(F);
+  l->inv = f32(l->inv_floats);
+  l->damp = f32(16);
+  l->lambdas = f32(8);
+  l->scalars = f32(16);
+  l->sched = reinterpret_cast<Sched*>(ar.take(sizeof(Sched)));
+  l->d_a_ptrs = reinterpret_cast<const float**>(ar.take(6 * sizeof(float*)));
+  l->d_g_ptrs = reinterpret_cast<const float**>(ar.take(6 * sizeof(float*)));
+  l->d_a_dims = reinterpret_cast<int*>(ar.take(6 * sizeof(int)));
+  l->d_g_dims = reinterpret_cast<int*>(ar.take(6 * sizeof(int)));
+  l->d_jobs = reinterpret_cast<InvJob*>(ar.take(12 * sizeof(InvJob)));
+  for (int i = 0; i < 6; ++i) {
+    const int d = l->L[i].K + 1, c = l->L[i].C;
+    l->ainv_pl[i] = take_planes(ar, 3, d, pad8(d));
+    l->ginv_pl[i] = take_planes(ar, 3, c, pad8(c));
+  }
+  // inverse jobs (sorted by decreasing n later)
+  for (int i = 0; i < 6; ++i) {
+    const int d = l->L[i].K + 1, c = l->L[i].C;
+    InvJob& ja = l->h_jobs[i];
+    ja.s = l->sums + l->aoff[l->L[i].afac];
+    ja.n = d;
+    ja.damp_index = 2 * i;
+    ja.work_m = reinterpret_cast<double*>(ar.take((size_t)d * d * sizeof(double)));
+    ja.work_x = reinterpret_cast<double*>(ar.take(((size_t)32 * d + 32 * 32) * sizeof(double)));
+    ja.inv = l->inv + l->ainv_off[i];
+    for (int q = 0; q < 3; ++q) ja.planes[q] = l->ainv_pl[i].p[q];
+    ja.ld_planes = l->ainv_pl[i].ld;
+    InvJob& jg = l->h_jobs[6 + i];
+    jg.s = l->sums + l->goff[i];
+    jg.n = c;
+    jg.damp_index = 2 * i + 1;
+    jg.work_m = reinterpret_cast<double*>(ar.take((size_t)c * c * sizeof(double)));
+    jg.work_x = reinterpret_cast<double*>(ar.take(((size_t)32 * c + 32 * 32) * sizeof(double)));
+    jg.inv = l->inv + l->ginv_off[i];
+    for (int q = 0; q < 3; ++q) jg.planes[q] = l->ginv_pl[i].p[q];
+    jg.ld_planes = l->ginv_pl[i].ld;
+  }
+  // ---- inputs
+  l->obs = reinterpret_cast<uint8_t*>(ar.take((size_t)R * 28224));
+  l->actions = reinterpret_cast<uint8_t*>(ar.take(N));
+  l->terminals = reinterpret_cast<uint8_t*>(ar.take(N));
+  l->rewards = f32(N);
+  // ---- weights as GEMM operands
+  for (int i = 0; i < 4; ++i) {
+    l->wT[i] = take_planes(ar, 3, l->L[i].C, pad8(l->L[i].K));   // W^T [C, K]   (forward: B operand, K-major)
+    l->wN[i] = take_planes(ar, 3, l->L[i].K, pad8(l->L[i].C));   // W   [K, C]   (dgrad:   B operand, K-major)
+  }
+  // ---- activations (forward rows R = N + E; backward rows 2N = true-loss rows then Fisher-sample rows)
+  const int np = l->act_planes;
+  l->P1 = take_planes(ar, 1, (size_t)R * 400, 256);
+  l->act1 = take_planes(ar, np, (size_t)R * 400, 32);
+  l->P2 = take_planes(ar, np, (size_t)R * 81, 512);
+  l->act2 = take_planes(ar, np, (size_t)R * 81, 64);
+  l->P3 = take_planes(ar, np, (size_t)R * 49, 576);
+  l->act3 = take_planes(ar, np, (size_t)R * 49, c3);
+  l->act4 = take_planes(ar, np, (size_t)R, 512);
+  l->logits = f32((size_t)R * A);
+  l->values = f32(R);
+  l->targets = f32(N);
+  l->adv = f32(N);
+  l->dheads = f32(B2 * (A + 1));
+  l->dpre4 = take_planes(ar, np, B2, 512);
+  l->dpre3 = take_planes(ar, np, B2 * 49, c3);
+  l->dpre2 = take_planes(ar, np, B2 * 81, 64);
+  l->dpre1 = take_planes(ar, np, B2 * 400, 32);
+  l->dP = f32(std::max(B2 * 49 * 576, B2 * 81 * 512));
+  // ---- preconditioning scratch
+  int dmax = 0, cmax = 0;
+  for (int i = 0; i < 6; ++i) {
+    dmax = std::max(dmax, l->L[i].K + 1);
+    cmax = std::max(cmax, l->L[i].C);
+  }
+  l->Vp = take_planes(ar, 3, dmax, pad8(cmax));
+  l->Wt = take_planes(ar, 3, cmax, pad8(dmax));
+  l->colsum_partial = f32((size_t)kColsumChunks * (size_t)std::max(49 * c3, 576));
+  l->colsum_tmp = f32(std::max(49 * c3, 576) + 8);
+  l->dot_partials = f32(kDotPartials);
+  const size_t kpad = align_up((size_t)49 * c3, 128);
+  l->ws_bytes = std::max<size_t>((size_t)48 << 20, kpad * kpad * sizeof(float) + (1 << 20));
+  l->ws = reinterpret_cast<float*>(ar.take(l->ws_bytes));
+  return align_up(ar.used, 256);
+}
+
+static void register_buffers(acx_learner* l) {
+  const size_t P = l->num_params;
+  reg(l, "params", l->params, P * 4);
+  reg(l, "velocity", l->velocity, P * 4);
+  reg(l, "accum", l->accum, P * 4);
+  reg(l, "precon", l->precon, P * 4);
+  reg(l, "grads", l->grads, P * 4);
+  reg(l, "reduce_bucket", l->bucket, l->bucket_floats * 4);
+  reg(l, "factor_stats", l->stats, l->factor_floats * 4);
+  reg(l, "factor_sums", l->sums, l->factor_floats * 4);
+  reg(l, "inverses", l->inv, l->inv_floats * 4);
+  reg(l, "dampings", l->damp, 12 * 4);
+  reg(l, "scalars", l->scalars, 16 * 4);
+  reg(l, "sched", l->sched, sizeof(Sched));
+  reg(l, "observations", l->obs, (size_t)l->R * 28224);
+  reg(l, "actions", l->actions, l->N);
+  reg(l, "terminals", l->terminals, l->N);
+  reg(l, "rewards", l->rewards, (size_t)l->N * 4);
+  reg(l, "logits", l->logits, (size_t)l->R * l->A * 4);
+  reg(l, "values", l->values, (size_t)l->R * 4);
+  reg(l, "targets", l->targets, (size_t)l->N * 4);
+  reg(l, "advantages", l->adv, (size_t)l->N * 4);
+  reg(l, "dheads", l->dheads, (size_t)2 * l->N * (l->A + 1) * 4);
+  static const char* an[5] = {"conv1", "conv2", "conv3", "fc4", "heads"};
+  for (int i = 0; i < 5; ++i) {
+    const size_t b = (size_t)l->adim[i] * l->adim[i] * 4;
+    reg(l, (std::string("stats/A/") + an[i]).c_str(), l->stats + l->aoff[i], b);
+    reg(l, (std::string("sums/A/") + an[i]).c_str(), l->sums + l->aoff[i], b);
+  }
+  for (int i = 0; i < 6; ++i) {
+    const size_t b = (size_t)l->L[i].C * l->L[i].C * 4;
+    reg(l, (std::string("stats/G/") + l->L[i].name).c_str(), l->stats + l->goff[i], b);
+    reg(l, (std::string("sums/G/") + l->L[i].name).c_str(), l->sums + l->goff[i], b);
+    const int d = l->L[i].K + 1;
+    reg(l, (std::string("inv/A/") + l->L[i].name).c_str(), l->inv + l->ainv_off[i], (size_t)d * d * 4);
+    reg(l, (std::string("inv/G/") + l->L[i].name).c_str(), l->inv + l->ginv_off[i], b);
+    const size_t vb = (size_t)d * l->L[i].C * 4;
+    reg(l, (std::string("params/") + l->L[i].name).c_str(), l->params + l->L[i].off, vb);
+    reg(l, (std::string("grads/") + l->L[i].name).c_str(), l->grads + l->L[i].off, vb);
+    reg(l, (std::string("precon/") + l->L[i].name).c_str(), l->precon + l->L[i].off, vb);
+    reg(l, (std::string("velocity/") + l->L[i].name).c_str(), l->velocity + l->L[i].off, vb);
+    reg(l, (std::string("accum/") + l->L[i].name).c_str(), l->accum + l->L[i].off, vb);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEMM helper: picks the plane pairs from the precision level (pairs (i,j) with i + j <= level)
+// ------------------------------------------------------------------------------------------------
+struct GemmOut {
+  float* c = nullptr;
+  int ldc = 0;
+  const Planes* planes = nullptr;
+  const float* bias = nullptr;
+  int relu = 0;
+  const bf16* mask = nullptr;
+  int mask_ld = 0, mask_rows = 0;
+};
+
+static int run_gemm(acx_learner* l, const Planes& a, const Planes& b, int trans, int m, int n, int k, int level, float alpha,
+                    int symmetric, const GemmOut& o, cudaStream_t st) {
+  acx_gemm_t g;
+  memset(&g, 0, sizeof(g));
+  for (int i = 0; i < a.n; ++i) g.a.planes[i] = a.p[i];
+  for (int i = 0; i < b.n; ++i) g.b.planes[i] = b.p[i];
+  g.a.num_planes = a.n;
+  g.b.num_planes = b.n;
+  g.a.ld = a.ld;
+  g.b.ld = b.ld;
+  if (trans) {
+    g.a.rows = k; g.a.cols = m; g.b.rows = k; g.b.cols = n;
+  } else {
+    g.a.rows = m; g.a.cols = k; g.b.rows = n; g.b.cols = k;
+  }
+  g.trans_a = g.trans_b = trans;
+  g.m = m; g.n = n; g.k = k;
+  int np = 0;
+  for (int s = 0; s <= level && np < 6; ++s)
+    for (int i = 0; i <= s && np < 6; ++i) {
+      const int j = s - i;
+      if (i < a.n && j < b.n) {
+        g.pair_a[np] = i;
+        g.pair_b[np] = j;
+        ++np;
+      }
+    }
+  g.num_pairs = np;
+  g.alpha = alpha;
+  g.bias = o.bias;
+  g.relu = o.relu;
+  g.symmetric = symmetric;
+  g.c = o.c;
+  g.ldc = o.ldc;
+  if (o.planes) {
+    for (int i = 0; i < o.planes->n; ++i) g.c_planes[i] = o.planes->p[i];
+    g.c_num_planes = o.planes->n;
+    g.ldc_planes = o.planes->ld;
+  }
+  g.mask_plane = o.mask;
+  g.mask_ld = o.mask_ld;
+  g.mask_rows = o.mask_rows;
+  g.splits = 0;
+  g.workspace = l->ws;
+  g.workspace_bytes = l->ws_bytes;
+  return gemm_dispatch(&g, l->cfg.gemm_impl, st);
+}
+
+#define ACX_TRY(expr)        \
+  do {                       \
+    int _r = (expr);         \
+    if (_r) return _r;       \
+  } while (0)
+
+static int refresh_weight_planes(acx_learner* l, cudaStream_t st) {
+  for (int i = 0; i < 4; ++i) {
+    const Layer& L = l->L[i];
+    ACX_TRY(transpose_split(l->params + L.off, L.K, L.C, l->wT[i].p[0], l->wT[i].p[1], l->wT[i].p[2], 3, l->wT[i].ld, st));
+    if (i > 0)
+      ACX_TRY(split_planes(l->params + L.off, L.C, L.K, L.C, 1.0f, l->wN[i].p[0], l->wN[i].p[1], l->wN[i].p[2], 3, l->wN[i].ld, st));
+  }
+  return 0;
+}
+
+// Nature-CNN forward on `rows` observations (envs/atari/model.py:173-217): im2col + GEMM with bias/ReLU epilogues
+static int forward(acx_learner* l, const uint8_t* obs, int rows, cudaStream_t st) {
+  const int c3 = l->c3;
+  GemmOut o;
+  o.relu = 1;
+  // conv1: raw bytes are exact in bf16; the /255 of envs/atari/model.py:93 is the GEMM alpha
+  ACX_TRY(im2col_conv1(obs, l->P1.p[0], rows * 400, st));
+  o.bias = l->params + l->L[0].off + (size_t)l->L[0].K * l->L[0].C;
+  o.planes = &l->act1;
+  ACX_TRY(run_gemm(l, l->P1, l->wT[0], 0, rows * 400, 32, 256, l->lvl_fwd, 1.0f / 255.0f, 0, o, st));
+  ACX_TRY(im2col_bf16(l->act1, l->P2, rows * 81, 20, 32, 4, 2, 9, st));
+  o.bias = l->params + l->L[1].off + (size_t)l->L[1].K * l->L[1].C;
+  o.planes = &l->act2;
+  ACX_TRY(run_gemm(l, l->P2, l->wT[1], 0, rows * 81, 64, 512, l->lvl_fwd, 1.0f, 0, o, st));
+  ACX_TRY(im2col_bf16(l->act2, l->P3, rows * 49, 9, 64, 3, 1, 7, st));
+  o.bias = l->params + l->L[2].off + (size_t)l->L[2].K * l->L[2].C;
+  o.planes = &l->act3;
+  ACX_TRY(run_gemm(l, l->P3, l->wT[2], 0, rows * 49, c3, 576, l->lvl_fwd, 1.0f, 0, o, st));
+  // fc4 on the (h, w, c)-flattened conv3 output (nn.py:125-126)
+  o.bias = l->params + l->L[3].off + (size_t)l->L[3].K * l->L[3].C;
+  o.planes = &l->act4;
+  ACX_TRY(run_gemm(l, with_ld(l->act3, 49 * c3), l->wT[3], 0, rows, 512, 49 * c3, l->lvl_fwd, 1.0f, 0, o, st));
+  ACX_TRY(heads_fwd(l->act4, l->params + l->L[4].off, l->params + l->L[5].off, rows, l->A, l->logits, l->values, st));
+  return 0;
+}
+
+// input factor of layer `li` from the patch/input planes `x` (first `rows` rows, K columns): SYRK + homogeneous border
+static int input_factor(acx_learner* l, int fac, const Planes& x, int rows, int K, float scale_sq, float scale_lin,
+                        cudaStream_t st) {
+  const int d = K + 1;
+  float* dst = l->stats + l->aoff[fac];
+  GemmOut o;
+  o.c = dst;
+  o.ldc = d;
+  ACX_TRY(run_gemm(l, x, x, 1, K, K, rows, l->lvl_factor, scale_sq, 1, o, st));
+  ACX_TRY(colsum(x, rows, K, scale_lin, l->colsum_partial, kColsumChunks, l->colsum_tmp, 1, st));
+  ACX_TRY(homog_border(dst, d, l->colsum_tmp, st));
+  return 0;
+}
+
+// weight gradient V_l[:K] = X^T g over the true-loss rows, bias row = column sums of g
+static int weight_grad(acx_learner* l, int li, const Planes& x, const Planes& g, int rows, float alpha, cudaStream_t st) {
+  const Layer& L = l->L[li];
+  GemmOut o;
+  o.c = l->grads + L.off;
+  o.ldc = L.C;
+  ACX_TRY(run_gemm(l, x, g, 1, L.K, L.C, rows, l->lvl_bwd, alpha, 0, o, st));
+  ACX_TRY(colsum(g, rows, L.C, 1.0f, l->colsum_partial, kColsumChunks, l->grads + L.off + (size_t)L.K * L.C, 1, st));
+  return 0;
+}
+
+// output factor G_l = g^T g / rows over the Fisher-sample rows
+static int output_factor(acx_learner* l, int li, const Planes& g_fisher, int rows, cudaStream_t st) {
+  const Layer& L = l->L[li];
+  GemmOut o;
+  o.c = l->stats + l->goff[li];
+  o.ldc = L.C;
+  return run_gemm(l, g_fisher, g_fisher, 1, L.C, L.C, rows, l->lvl_factor, 1.0f / (float)rows, 1, o, st);
+}
+
+static int phase1(acx_learner* l, const int32_t* fisher_labels, const float* fisher_eps, cudaStream_t st) {
+  const int N = l->N, E = l->E, T = l->T, A = l->A, c3 = l->c3;
+  const bool acktr = l->cfg.acktr != 0;
+  const bool fisher = acktr && l->gs >= l->cfg.num_cold_updates;   // kfac_utils.py:42-44: covariances only after the cold phase
+  const int RB = fisher ? 2 * N : N;
+  ACX_TRY(forward(l, l->obs, l->R, st));
+  // targets use the bootstrap tower's values = rows [N, N+E) (envs/atari/model.py:116,126-127)
+  ACX_TRY(returns_launch(l->rewards, l->terminals, l->values, l->values + N, l->cfg.gamma, E, T, l->targets, l->adv, st));
+  ACX_TRY(loss_grad(l->logits, l->values, l->actions, l->targets, fisher_labels, fisher_eps, l->cfg.seed, l->sched, N, A,
+                    l->cfg.entropy_beta, l->cfg.value_loss_weight, l->dheads, l->bscalars, fisher ? 1 : 0, st));
+  ACX_TRY(heads_bwd(l->dheads, l->params + l->L[4].off, l->params + l->L[5].off, l->act4, N, RB, A, l->dpre4,
+                    l->grads + l->L[4].off, l->grads + l->L[5].off, st));
+  const Planes flat3 = with_ld(l->act3, 49 * c3);
+  // ---- fc4
+  ACX_TRY(weight_grad(l, 3, flat3, l->dpre4, N, 1.0f, st));
+  {
+    GemmOut o;   // d(act3) = dpre4 W4^T, masked by ReLU(conv3) -> dpre3  (rows of the Fisher half reuse the mask)
+    const Planes out = with_ld(l->dpre3, 49 * c3);
+    o.planes = &out;
+    o.mask = l->act3.p[0];
+    o.mask_ld = 49 * c3;
+    o.mask_rows = N;
+    ACX_TRY(run_gemm(l, l->dpre4, l->wN[3], 0, RB, 49 * c3, 512, l->lvl_bwd, 1.0f, 0, o, st));
+  }
+  // ---- conv3
+  ACX_TRY(weight_grad(l, 2, l->P3, l->dpre3, N * 49, 1.0f, st));
+  {
+    GemmOut o;
+    o.c = l->dP;
+    o.ldc = 576;
+    ACX_TRY(run_gemm(l, l->dpre3, l->wN[2], 0, RB * 49, 576, c3, l->lvl_bwd, 1.0f, 0, o, st));
+    ACX_TRY(col2im_mask_split(l->dP, l->act2.p[0], l->dpre2, RB, N, 9, 64, 3, 1, 7, st));
+  }
+  // ---- conv2
+  ACX_TRY(weight_grad(l, 1, l->P2, l->dpre2, N * 81, 1.0f, st));
+  {
+    GemmOut o;
+    o.c = l->dP;
+    o.ldc = 512;
+    ACX_TRY(run_gemm(l, l->dpre2, l->wN[1], 0, RB * 81, 512, 64, l->lvl_bwd, 1.0f, 0, o, st));
+    ACX_TRY(col2im_mask_split(l->dP, l->act1.p[0], l->dpre1, RB, N, 20, 32, 4, 2, 9, st));
+  }
+  // ---- conv1 (no input gradient: observations are constants, envs/atari/model.py:101-104)
+  ACX_TRY(weight_grad(l, 0, l->P1, l->dpre1, N * 400, 1.0f / 255.0f, st));
+  if (fisher) {
+    // ---- the 11 batch factor statistics
+    ACX_TRY(heads_gfactor(l->dheads + (size_t)N * (A + 1), N, A, l->stats + l->goff[4], l->stats + l->goff[5], st));
+    ACX_TRY(output_factor(l, 3, offset_rows(l->dpre4, N), N, st));
+    ACX_TRY(output_factor(l, 2, offset_rows(l->dpre3, (size_t)N * 49), N * 49, st));
+    ACX_TRY(output_factor(l, 1, offset_rows(l->dpre2, (size_t)N * 81), N * 81, st));
+    ACX_TRY(output_factor(l, 0, offset_rows(l->dpre1, (size_t)N * 400), N * 400, st));
+    const float r1 = 1.0f / (float)(N * 400), r2 = 1.0f / (float)(N * 81), r3 = 1.0f / (float)(N * 49), r4 = 1.0f / (float)N;
+    ACX_TRY(input_factor(l, 0, l->P1, N * 400, 256, r1 / (255.0f * 255.0f), r1 / 255.0f, st));
+    ACX_TRY(input_factor(l, 1, l->P2, N * 81, 512, r2, r2, st));
+    ACX_TRY(input_factor(l, 2, l->P3, N * 49, 576, r3, r3, st));
+    ACX_TRY(input_factor(l, 3, flat3, N, 49 * c3, r4, r4, st));
+    ACX_TRY(input_factor(l, 4, l->act4, N, 512, r4, r4, st));
+  }
+  return 0;
+}
+
+static int precondition(acx_learner* l, cudaStream_t st) {
+  for (int i = 0; i < 6; ++i) {
+    const Layer& L = l->L[i];
+    const int d = L.K + 1, C = L.C;
+    Planes vp = l->Vp;
+    vp.ld = pad8(C);
+    Planes wt = l->Wt;
+    wt.ld = pad8(d);
+    ACX_TRY(split_planes(l->grads + L.off, C, d, C, 1.0f, vp.p[0], vp.p[1], vp.p[2], 3, vp.ld, st));
+    GemmOut o1;   // Wt [C, d] = G^-1 V^T
+    o1.planes = &wt;
+    ACX_TRY(run_gemm(l, l->ginv_pl[i], vp, 0, C, d, C, l->lvl_precon, 1.0f, 0, o1, st));
+    GemmOut o2;   // U [d, C] = A^-1 W / T~
+    o2.c = l->precon + L.off;
+    o2.ldc = C;
+    ACX_TRY(run_gemm(l, l->ainv_pl[i], wt, 0, d, C, d, l->lvl_precon, 1.0f / (float)L.Tnorm, 0, o2, st));
+  }
+  return 0;
+}
+
+static int phase2(acx_learner* l, cudaStream_t st) {
+  const acx_learner_config_t& c = l->cfg;
+  const size_t P = l->num_params;
+  if (c.world_size > 1) ACX_TRY(scale_f32(l->bucket, l->bucket_floats, 1.0f / (float)c.world_size, st));
+  ACX_CUDA(cudaMemcpyAsync(l->scalars, l->bscalars, 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  ACX_TRY(sched_begin(l->sched, c.lr_start, c.lr_end, c.lr_decay_steps, l->scalars + 7, st));
+  if (!c.acktr) {   // ClipGlobalNorm(RMSProp)   a2c_acktr.py:250-251
+    ACX_TRY(dot_partial(l->grads, l->grads, P, l->dot_partials, kDotPartials, st));
+    ACX_TRY(rmsprop_clip_step(l->params, l->accum, l->grads, P, l->dot_partials, kDotPartials, l->sched, c.rms_decay,
+                              c.rms_epsilon, c.clip_norm, l->scalars + 6, st));
+    ACX_TRY(sched_advance(l->sched, 1, 0, c.cov_ema_decay, 1, st));
+    l->gs += 1;
+    return refresh_weight_planes(l, st);
+  }
+  const bool cold = l->gs < c.num_cold_updates;
+  if (cold) {       // kfac_utils.py:42-43: ClipGlobalNorm(Momentum(3e-4, 0.9)) - this also increments global_step
+    ACX_TRY(dot_partial(l->grads, l->grads, P, l->dot_partials, kDotPartials, st));
+    ACX_TRY(momentum_clip_step(l->params, l->accum, l->grads, P, l->dot_partials, kDotPartials, c.cold_lr, c.cold_momentum,
+                               c.clip_norm, l->scalars + 6, st));
+    ACX_TRY(sched_advance(l->sched, 1, 0, c.cov_ema_decay, 1, st));
+    l->gs += 1;
+  } else {          // kfac_utils.py:44: all covariance updates
+    ACX_TRY(ema_update(l->sums, l->stats, l->factor_floats, c.cov_ema_decay, 1.0f, st));
+    ACX_TRY(sched_advance(l->sched, 0, 1, c.cov_ema_decay, 1, st));
+    l->ncov += 1;
+  }
+  if (l->gs > c.num_cold_updates && (l->gs - c.num_cold_updates) % c.invert_every == 0) {   // kfac_utils.py:47-50
+    ACX_TRY(compute_dampings(l->d_a_ptrs, l->d_g_ptrs, l->d_a_dims, l->d_g_dims, l->lambdas, 6, l->damp, st));
+    ACX_TRY(spd_inverse_batched(l->h_jobs, l->d_jobs, 12, l->sched, l->damp, st));
+    l->inverses_valid = true;
+  }
+  // kfac_utils.py:52-53 - always.  With the zero-initialised inverses of kfac the step is exactly a no-op
+  // (U = 0, v stays 0) until the first refresh, so only the step counter moves.
+  if (l->inverses_valid) {
+    ACX_TRY(precondition(l, st));
+    ACX_TRY(dot_partial(l->grads, l->precon, P, l->dot_partials, kDotPartials, st));
+    ACX_TRY(kfac_step(l->params, l->velocity, l->precon, P, l->dot_partials, kDotPartials, l->sched, c.momentum,
+                      c.norm_constraint, l->scalars + 4, st));
+  }
+  ACX_TRY(sched_advance(l->sched, 1, 0, c.cov_ema_decay, 1, st));
+  l->gs += 1;
+  if (cold || l->inverses_valid) ACX_TRY(refresh_weight_planes(l, st));
+  return 0;
+}
+
+}  // namespace acx
+
+extern "C" {
+
+static int check_cfg(const acx_learner_config_t* c) {
+  ACX_CHECK(c != nullptr, "null config");
+  ACX_CHECK(c->num_envs > 0 && c->num_steps > 0, "num_envs and num_steps must be positive");
+  ACX_CHECK(c->num_actions >= 1 && c->num_actions <= 31, "num_actions must be in [1, 31]");
+  ACX_CHECK(c->conv3_filters >= 8 && c->conv3_filters <= 256 && c->conv3_filters % 8 == 0,
+            "conv3_filters must be a multiple of 8 in [8, 256]");
+  ACX_CHECK(c->world_size >= 1, "world_size");
+  ACX_CHECK((long long)(c->num_envs) * c->num_steps <= (1 << 20), "rollout too large");
+  if (c->acktr) ACX_CHECK(c->invert_every >= 1, "invert_every");
+  return 0;
+}
+
+static void init_dims(acx_learner* l, const acx_learner_config_t* cfg) {
+  l->cfg = *cfg;
+  // precision: activations / gradients are kept as act_planes bf16 planes; a GEMM of level L accumulates the plane
+  // pairs (i, j) with i + j <= L  (1 pair = bf16 inputs, 3 pairs ~ 2^-17, 6 pairs = fp32 class)
+  switch (cfg->precision) {
+    case 1: l->act_planes = 2; l->lvl_fwd = 1; l->lvl_bwd = 1; l->lvl_factor = 1; l->lvl_precon = 2; break;
+    case 2: l->act_planes = 2; l->lvl_fwd = 1; l->lvl_bwd = 1; l->lvl_factor = 0; l->lvl_precon = 2; break;
+    case 3: l->act_planes = 1; l->lvl_fwd = 0; l->lvl_bwd = 0; l->lvl_factor = 0; l->lvl_precon = 1; break;
+    default: l->act_planes = 3; l->lvl_fwd = 2; l->lvl_bwd = 2; l->lvl_factor = 1; l->lvl_precon = 2; break;
+  }
+  l->E = cfg->num_envs;
+  l->T = cfg->num_steps;
+  l->N = l->E * l->T;
+  l->R = l->N + l->E;
+  l->A = cfg->num_actions;
+  l->c3 = cfg->conv3_filters;
+  setup_layers(l);
+}
+
+size_t acx_learner_arena_bytes(const acx_learner_config_t* cfg) {
+  if (check_cfg(cfg)) return 0;
+  acx_learner tmp;
+  init_dims(&tmp, cfg);
+  return layout(&tmp, nullptr);
+}
+
+acx_learner_t* acx_learner_create(const acx_learner_config_t* cfg, void* d_arena, size_t arena_bytes) {
+  if (check_cfg(cfg)) return nullptr;
+  acx_learner* l = new acx_learner();
+  init_dims(l, cfg);
+  const size_t need = layout(l, nullptr);
+  if (d_arena == nullptr || arena_bytes < need || (reinterpret_cast<uintptr_t>(d_arena) & 255) != 0) {
+    acx::set_error("acx_learner_create: arena must be a 256-byte aligned device buffer of at least acx_learner_arena_bytes()");
+    delete l;
+    return nullptr;
+  }
+  layout(l, reinterpret_cast<uint8_t*>(d_arena));
+  register_buffers(l);
+  l->gs = 0;
+  l->ncov = 0;
+  l->inverses_valid = false;
+  l->act_calls = 0;
+  // zero everything persistent; RMSProp's ms starts at one (TF-1 default)
+  cudaError_t e = cudaMemset(d_arena, 0, need);
+  if (e != cudaSuccess) {
+    acx::set_error(std::string("acx_learner_create: cudaMemset: ") + cudaGetErrorString(e));
+    delete l;
+    return nullptr;
+  }
+  std::vector<float> ones;
+  if (!cfg->acktr) {
+    ones.assign(l->params_pad, 1.0f);
+    cudaMemcpy(l->accum, ones.data(), l->params_pad * 4, cudaMemcpyHostToDevice);
+  }
+  Sched s0 = {0ull, 0ull, cfg->lr_start, 1.0f};
+  cudaMemcpy(l->sched, &s0, sizeof(s0), cudaMemcpyHostToDevice);
+  const float* ap[6];
+  const float* gp[6];
+  int ad[6], gd[6];
+  float lam[8] = {0};
+  for (int i = 0; i < 6; ++i) {
+    ap[i] = l->sums + l->aoff[l->L[i].afac];
+    gp[i] = l->sums + l->goff[i];
+    ad[i] = l->adim[l->L[i].afac];
+    gd[i] = l->L[i].C;
+    lam[i] = cfg->damping / (float)l->L[i].Tnorm;
+  }
+  cudaMemcpy(l->d_a_ptrs, ap, sizeof(ap), cudaMemcpyHostToDevice);
+  cudaMemcpy(l->d_g_ptrs, gp, sizeof(gp), cudaMemcpyHostToDevice);
+  cudaMemcpy(l->d_a_dims, ad, sizeof(ad), cudaMemcpyHostToDevice);
+  cudaMemcpy(l->d_g_dims, gd, sizeof(gd), cudaMemcpyHostToDevice);
+  cudaMemcpy(l->lambdas, lam, sizeof(lam), cudaMemcpyHostToDevice);
+  std::stable_sort(l->h_jobs, l->h_jobs + 12, [](const InvJob& a, const InvJob& b) { return a.n > b.n; });
+  e = cudaMemcpy(l->d_jobs, l->h_jobs, sizeof(l->h_jobs), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    acx::set_error(std::string("acx_learner_create: cudaMemcpy: ") + cudaGetErrorString(e));
+    delete l;
+    return nullptr;
+  }
+  return l;
+}
+
+void acx_learner_destroy(acx_learner_t* l) { delete l; }
+
+size_t acx_learner_num_params(const acx_learner_t* l) { return l ? l->num_params : 0; }
+
+int acx_learner_set_params(acx_learner_t* l, const float* h_params, void* stream) {
+  ACX_CHECK(l && h_params, "null argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  ACX_CUDA(cudaMemcpyAsync(l->params, h_params, l->num_params * sizeof(float), cudaMemcpyHostToDevice, st));
+  int r = refresh_weight_planes(l, st);
+  if (r) return r;
+  ACX_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int acx_learner_get_params(acx_learner_t* l, float* h_params, void* stream) {
+  ACX_CHECK(l && h_params, "null argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  ACX_CUDA(cudaMemcpyAsync(h_params, l->params, l->num_params * sizeof(float), cudaMemcpyDeviceToHost, st));
+  ACX_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int acx_learner_refresh_weights(acx_learner_t* l, void* stream) {
+  ACX_CHECK(l, "null learner");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int r = refresh_weight_planes(l, st);
+  if (r) return r;
+  for (int i = 0; i < 6; ++i) {   // the bf16 planes of the stored inverses are derived state too
+    const int d = l->L[i].K + 1, c = l->L[i].C;
+    r = split_planes(l->inv + l->ainv_off[i], d, d, d, 1.0f, l->ainv_pl[i].p[0], l->ainv_pl[i].p[1], l->ainv_pl[i].p[2], 3,
+                     l->ainv_pl[i].ld, st);
+    if (r) return r;
+    r = split_planes(l->inv + l->ginv_off[i], c, c, c, 1.0f, l->ginv_pl[i].p[0], l->ginv_pl[i].p[1], l->ginv_pl[i].p[2], 3,
+                     l->ginv_pl[i].ld, st);
+    if (r) return r;
+  }
+  return 0;
+}
+
+void* acx_learner_buffer(acx_learner_t* l, const char* name, size_t* num_bytes) {
+  if (!l || !name) return nullptr;
+  auto it = l->named.find(name);
+  if (it == l->named.end()) {
+    acx::set_error(std::string("acx_learner_buffer: unknown buffer '") + name + "'");
+    return nullptr;
+  }
+  if (num_bytes) *num_bytes = it->second.bytes;
+  return it->second.ptr;
+}
+
+int acx_learner_phase1(acx_learner_t* l, const int32_t* d_fisher_labels, const float* d_fisher_eps, void* stream) {
+  ACX_CHECK(l, "null learner");
+  ACX_CHECK((d_fisher_labels == nullptr) == (d_fisher_eps == nullptr), "inject both Fisher labels and eps, or neither");
+  return phase1(l, d_fisher_labels, d_fisher_eps, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int acx_learner_phase2(acx_learner_t* l, void* stream) {
+  ACX_CHECK(l, "null learner");
+  return phase2(l, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int64_t acx_learner_global_step(const acx_learner_t* l) { return l ? l->gs : -1; }
+
+int acx_learner_set_state(acx_learner_t* l, int64_t global_step, int64_t num_cov_updates, int inverses_valid, void* stream) {
+  ACX_CHECK(l, "null learner");
+  ACX_CHECK(global_step >= 0 && num_cov_updates >= 0, "negative counters");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  l->gs = global_step;
+  l->ncov = num_cov_updates;
+  l->inverses_valid = inverses_valid != 0;
+  Sched s;
+  s.gs = (unsigned long long)global_step;
+  s.ncov = (unsigned long long)num_cov_updates;
+  s.lr = l->cfg.lr_start;
+  s.debias = num_cov_updates > 0 ? (float)(1.0 / (1.0 - pow((double)l->cfg.cov_ema_decay, (double)num_cov_updates))) : 1.0f;
+  ACX_CUDA(cudaMemcpyAsync(l->sched, &s, sizeof(s), cudaMemcpyHostToDevice, st));
+  ACX_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int acx_learner_get_state(const acx_learner_t* l, int64_t* global_step, int64_t* num_cov_updates, int* inverses_valid) {
+  ACX_CHECK(l, "null learner");
+  if (global_step) *global_step = l->gs;
+  if (num_cov_updates) *num_cov_updates = l->ncov;
+  if (inverses_valid) *inverses_valid = l->inverses_valid ? 1 : 0;
+  return 0;
+}
+
+int acx_learner_act(acx_learner_t* l, const uint8_t* d_obs, int rows, const float* d_uniform, int greedy, int32_t* d_actions,
+                    float* d_logits, float* d_values, void* stream) {
+  ACX_CHECK(l && d_obs && d_actions, "null argument");
+  ACX_CHECK(rows > 0 && rows <= l->R, "rows must be in [1, num_envs * num_steps + num_envs]");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int r = forward(l, d_obs, rows, st);
+  if (r) return r;
+  r = sample_actions(l->logits, d_uniform, l->cfg.seed, l->act_calls++, rows, l->A, greedy, d_actions, st);
+  if (r) return r;
+  if (d_logits)
+    ACX_CUDA(cudaMemcpyAsync(d_logits, l->logits, (size_t)rows * l->A * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (d_values) ACX_CUDA(cudaMemcpyAsync(d_values, l->values, (size_t)rows * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,348 @@
+"""Host-side handle of the native learner engine (include/acx.h `acx_learner_*`).
+
+torch is used for device memory (the arena is one uint8 CUDA tensor, every buffer a view into it),
+the current CUDA stream and `torch.distributed`; all arithmetic runs in libacx.so.  There is no CPU
+path: constructing an `Engine` without a CUDA device raises.
+
+The hyper-parameters default to the literals of the reference's example
+(actorcritic/examples/atari/a2c_acktr.py:52,57,64-71,76,240-251).
+"""
+import ctypes
+import dataclasses
+
+import numpy as np
+import torch
+
+from . import _lib
+
+LAYERS = ("conv1", "conv2", "conv3", "fc4", "fc_policy", "fc_baseline")
+A_FACTORS = ("conv1", "conv2", "conv3", "fc4", "heads")
+OBS_SHAPE = (84, 84, 4)
+OBS_BYTES = 84 * 84 * 4
+
+SCALAR_NAMES = ("policy_loss", "baseline_loss", "mean_entropy", "loss", "clip_coeff", "fisher_norm", "grad_norm",
+                "learning_rate")
+
+
+@dataclasses.dataclass
+class EngineConfig:
+    num_envs: int = 32
+    num_steps: int = 20
+    num_actions: int = 4
+    conv3_filters: int = 32                 # a2c_acktr.py:52 (32 for ACKTR, 64 for A2C)
+    acktr: bool = True
+    gamma: float = 0.99                     # :57
+    entropy_beta: float = 0.01              # :57
+    value_loss_weight: float = 0.5          # :76
+    lr_start: float = 0.25                  # :68  (A2C: 0.0007, :71)
+    lr_end: float = 0.025
+    lr_decay_steps: float = None            # :64  1e7 / (num_envs * num_steps)
+    cov_ema_decay: float = 0.99             # :245
+    damping: float = 0.01
+    momentum: float = 0.9
+    norm_constraint: float = 0.0001
+    invert_every: int = 10
+    num_cold_updates: int = 30              # :244
+    cold_lr: float = 0.0003                 # :240
+    cold_momentum: float = 0.9
+    clip_norm: float = 0.5                  # :241 / :251
+    rms_decay: float = 0.9                  # TF-1 RMSPropOptimizer defaults (:250)
+    rms_epsilon: float = 1e-10
+    num_locations_mode: str = "true"        # or "input_div_stride" 
+    world_size: int = 1
+    gemm_impl: int = 0
+    precision: int = 0
+    seed: int = 0
+
+    @staticmethod
+    def a2c(num_envs=16, num_steps=5, num_actions=4, **kw):
+        """The reference's A2C configuration (a2c_acktr.py:52,71,250-251,309-310)."""
+        base = dict(num_envs=num_envs, num_steps=num_steps, num_actions=num_actions, conv3_filters=64, acktr=False,
+                    lr_start=0.0007, lr_end=0.00007)
+        base.update(kw)
+        return EngineConfig(**base)
+
+    def to_c(self):
+        c = _lib.LearnerConfig()
+        c.num_envs, c.num_steps, c.num_actions = self.num_envs, self.num_steps, self.num_actions
+        c.conv3_filters, c.acktr = self.conv3_filters, int(self.acktr)
+        c.gamma, c.entropy_beta, c.value_loss_weight = self.gamma, self.entropy_beta, self.value_loss_weight
+        c.lr_start, c.lr_end = self.lr_start, self.lr_end
+        steps = self.lr_decay_steps
+        c.lr_decay_steps = float(steps) if steps is not None else 1e7 / (self.num_envs * self.num_steps * self.world_size)
+        c.cov_ema_decay, c.damping, c.momentum = self.cov_ema_decay, self.damping, self.momentum
+        c.norm_constraint = self.norm_constraint
+        c.invert_every, c.num_cold_updates = self.invert_every, self.num_cold_updates
+        c.cold_lr, c.cold_momentum, c.clip_norm = self.cold_lr, self.cold_momentum, self.clip_norm
+        c.rms_decay, c.rms_epsilon = self.rms_decay, self.rms_epsilon
+        if self.num_locations_mode not in ("true", "input_div_stride"):
+            raise ValueError("num_locations_mode must be 'true' or 'input_div_stride'")
+        c.num_locations_mode = 0 if self.num_locations_mode == "true" else 1
+        c.world_size, c.gemm_impl, c.precision, c.seed = self.world_size, self.gemm_impl, self.precision, self.seed
+        return c
+
+
+def param_shapes(num_actions, c3):
+    """Variable shapes of AtariModel (envs/atari/model.py:137-170; HWIO conv kernels, [in, out] fc weights)."""
+    return {
+        "conv1/weights": (8, 8, 4, 32), "conv1/bias": (32,),
+        "conv2/weights": (4, 4, 32, 64), "conv2/bias": (64,),
+        "conv3/weights": (3, 3, 64, c3), "conv3/bias": (c3,),
+        "fc4/weights": (49 * c3, 512), "fc4/bias": (512,),
+        "fc_policy/weights": (512, num_actions), "fc_policy/bias": (num_actions,),
+        "fc_baseline/weights": (512, 1), "fc_baseline/bias": (1,),
+    }
+
+
+def flatten_params(params, num_actions, c3):
+    """dict of reference-named variables -> the engine's flat vector: per layer [K+1, C] (weight rows in
+    (kh, kw, cin) order = the HWIO variable reshaped, then the bias row)."""
+    shapes = param_shapes(num_actions, c3)
+    parts = []
+    for layer in LAYERS:
+        w = np.asarray(params[layer + "/weights"], np.float32)
+        b = np.asarray(params[layer + "/bias"], np.float32)
+        if tuple(w.shape) != shapes[layer + "/weights"] or tuple(b.shape) != shapes[layer + "/bias"]:
+            raise ValueError("bad shape for layer %s: %s / %s" % (layer, w.shape, b.shape))
+        parts.append(w.reshape(-1, w.shape[-1]).ravel())
+        parts.append(b.ravel())
+    return np.concatenate(parts)
+
+
+def unflatten_params(flat, num_actions, c3):
+    shapes = param_shapes(num_actions, c3)
+    out, off = {}, 0
+    flat = np.asarray(flat)
+    for layer in LAYERS:
+        for kind in ("weights", "bias"):
+            shape = shapes[layer + "/" + kind]
+            n = int(np.prod(shape))
+            out[layer + "/" + kind] = flat[off:off + n].reshape(shape).copy()
+            off += n
+    return out
+
+
+def orthogonal_init(num_actions=4, c3=32, seed=None):
+    """envs/atari/model.py:132-135: orthogonal kernels with gains sqrt(2) (trunk), 0.01 (policy), 1.0 (value);
+    zero biases.  QR-based like tf.orthogonal_initializer; the random stream is numpy's, not TensorFlow's."""
+    rng = np.random.default_rng(seed)
+    gains = {"conv1": 2.0 ** 0.5, "conv2": 2.0 ** 0.5, "conv3": 2.0 ** 0.5, "fc4": 2.0 ** 0.5, "fc_policy": 0.01,
+             "fc_baseline": 1.0}
+    params = {}
+    for key, shape in param_shapes(num_actions, c3).items():
+        layer, kind = key.split("/")
+        if kind == "bias":
+            params[key] = np.zeros(shape, np.float32)
+            continue
+        rows, cols = int(np.prod(shape[:-1])), int(shape[-1])
+        a = rng.standard_normal((max(rows, cols), min(rows, cols)))
+        q, r = np.linalg.qr(a)
+        q = q * np.sign(np.diag(r))
+        if rows < cols:
+            q = q.T
+        params[key] = (gains[layer] * q).reshape(shape).astype(np.float32)
+    return params
+
+
+class Engine:
+    """One learner per process / GPU."""
+
+    def __init__(self, config, device=None):
+        if not torch.cuda.is_available():
+            raise _lib.AcxError("actorcritic_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.config = config
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._c = config.to_c()
+        with torch.cuda.device(self.device):
+            nbytes = self.lib.acx_learner_arena_bytes(ctypes.byref(self._c))
+            if nbytes == 0:
+                raise _lib.AcxError(self.lib.acx_last_error().decode())
+            self.arena = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
+            self._arena_off = (-self.arena.data_ptr()) % 256
+            base = self.arena.data_ptr() + self._arena_off
+            self._h = self.lib.acx_learner_create(ctypes.byref(self._c), ctypes.c_void_p(base), ctypes.c_size_t(nbytes))
+            if not self._h:
+                raise _lib.AcxError(self.lib.acx_last_error().decode())
+        self.num_params = int(self.lib.acx_learner_num_params(self._h))
+        self.num_envs, self.num_steps = config.num_envs, config.num_steps
+        self.rows = config.num_envs * config.num_steps
+        self._views = {}
+        n, e, a = self.rows, config.num_envs, config.num_actions
+        self.observations = self.buffer("observations", torch.uint8, (n + e,) + OBS_SHAPE)
+        self.actions = self.buffer("actions", torch.uint8, (e, config.num_steps))
+        self.rewards = self.buffer("rewards", torch.float32, (e, config.num_steps))
+        self.terminals = self.buffer("terminals", torch.uint8, (e, config.num_steps))
+        self.bucket = self.buffer("reduce_bucket", torch.float32)
+        self.scalars = self.buffer("scalars", torch.float32)
+        self.logits = self.buffer("logits", torch.float32, (n + e, a))
+        self.values = self.buffer("values", torch.float32, (n + e,))
+        self._pinned_scalars = torch.empty(16, dtype=torch.float32).pin_memory()
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self.lib.acx_learner_destroy(h)
+
+    # ------------------------------------------------------------------ buffers
+    def buffer(self, name, dtype=torch.float32, shape=None):
+        key = (name, dtype, shape)
+        if key in self._views:
+            return self._views[key]
+        nbytes = ctypes.c_size_t(0)
+        ptr = self.lib.acx_learner_buffer(self._h, name.encode(), ctypes.byref(nbytes))
+        if not ptr:
+            raise KeyError(self.lib.acx_last_error().decode())
+        off = ptr - self.arena.data_ptr()
+        view = self.arena[off:off + nbytes.value].view(dtype)
+        if shape is not None:
+            view = view.view(shape)
+        self._views[key] = view
+        return view
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ parameters / state
+    def set_params(self, params):
+        flat = params if isinstance(params, np.ndarray) and params.ndim == 1 else flatten_params(
+            params, self.config.num_actions, self.config.conv3_filters)
+        flat = np.ascontiguousarray(flat, np.float32)
+        if flat.size != self.num_params:
+            raise ValueError("expected %d parameters, got %d" % (self.num_params, flat.size))
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.acx_learner_set_params(self._h, flat.ctypes.data_as(ctypes.c_void_p), self._stream()))
+
+    def get_params_flat(self):
+        out = np.empty(self.num_params, np.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.acx_learner_get_params(self._h, out.ctypes.data_as(ctypes.c_void_p), self._stream()))
+        return out
+
+    def get_params(self):
+        return unflatten_params(self.get_params_flat(), self.config.num_actions, self.config.conv3_filters)
+
+    def layer_matrix(self, kind, layer):
+        """[K+1, C] device view of "params" / "grads" / "precon" for one layer."""
+        c = self.config
+        cols = {"conv1": 32, "conv2": 64, "conv3": c.conv3_filters, "fc4": 512, "fc_policy": c.num_actions,
+                "fc_baseline": 1}[layer]
+        return self.buffer("%s/%s" % (kind, layer), torch.float32).view(-1, cols)
+
+    def factor(self, kind, which, name):
+        """Square device view: kind in {"stats","sums","inv"}, which in {"A","G"}."""
+        v = self.buffer("%s/%s/%s" % (kind, which, name), torch.float32)
+        d = int(round(v.numel() ** 0.5))
+        return v.view(d, d)
+
+    @property
+    def global_step(self):
+        return int(self.lib.acx_learner_global_step(self._h))
+
+    def get_state(self):
+        gs, nc, iv = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int(0)
+        _lib.check(self.lib.acx_learner_get_state(self._h, ctypes.byref(gs), ctypes.byref(nc), ctypes.byref(iv)))
+        return dict(global_step=gs.value, num_cov_updates=nc.value, inverses_valid=bool(iv.value))
+
+    def set_state(self, global_step, num_cov_updates=0, inverses_valid=False):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.acx_learner_set_state(self._h, int(global_step), int(num_cov_updates),
+                                                      int(bool(inverses_valid)), self._stream()))
+
+    def refresh_derived(self):
+        """Re-derive the bf16 operand planes after writing "params" / "inverses" on the device."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.acx_learner_refresh_weights(self._h, self._stream()))
+
+    def state_dict(self):
+        """Everything `tf.train.Saver` would save for this path (a2c_acktr.py:101): parameters, optimiser slots,
+        K-FAC running sums, stored inverses and the schedule counters - as host tensors."""
+        torch.cuda.synchronize(self.device)
+        sd = {k: self.buffer(k, torch.float32).cpu().clone() for k in ("params", "velocity", "accum", "factor_sums",
+                                                                       "inverses")}
+        sd.update(self.get_state())
+        sd["config"] = dataclasses.asdict(self.config)
+        return sd
+
+    def load_state_dict(self, sd):
+        for k in ("params", "velocity", "accum", "factor_sums", "inverses"):
+            self.buffer(k, torch.float32).copy_(sd[k].to(self.device))
+        self.refresh_derived()
+        self.set_state(sd["global_step"], sd["num_cov_updates"], sd["inverses_valid"])
+
+    # ------------------------------------------------------------------ one update
+    def load_batch(self, observations, bootstrap_observations, actions, rewards, terminals, non_blocking=True):
+        """Copy the five train-step inputs (ActorCriticModel placeholders, model.py:97-105) into the arena.
+        Accepts host (numpy / pinned torch) or device tensors; layouts [E,T,84,84,4] u8, [E,84,84,4] u8,
+        [E,T] u8, [E,T] f32, [E,T] bool/u8."""
+        n = self.rows
+
+        def as_t(x, dtype):
+            t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+            if t.dtype == torch.bool:
+                t = t.to(torch.uint8)
+            if t.dtype != dtype:
+                t = t.to(dtype)
+            return t
+
+        self.observations[:n].view(self.num_envs, self.num_steps, *OBS_SHAPE).copy_(as_t(observations, torch.uint8),
+                                                                                  non_blocking=non_blocking)
+        self.observations[n:].copy_(as_t(bootstrap_observations, torch.uint8), non_blocking=non_blocking)
+        self.actions.copy_(as_t(actions, torch.uint8), non_blocking=non_blocking)
+        self.rewards.copy_(as_t(rewards, torch.float32), non_blocking=non_blocking)
+        self.terminals.copy_(as_t(terminals, torch.uint8), non_blocking=non_blocking)
+
+    def phase1(self, fisher_labels=None, fisher_eps=None):
+        fl = ctypes.c_void_p(fisher_labels.data_ptr()) if fisher_labels is not None else None
+        fe = ctypes.c_void_p(fisher_eps.data_ptr()) if fisher_eps is not None else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.acx_learner_phase1(self._h, fl, fe, self._stream()))
+
+    def allreduce(self, group=None):
+        """The one collective of the data-parallel path: sum of [grads | A | G | scalars]."""
+        if self.config.world_size > 1:
+            torch.distributed.all_reduce(self.bucket, op=torch.distributed.ReduceOp.SUM, group=group)
+
+    def phase2(self):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.acx_learner_phase2(self._h, self._stream()))
+
+    def update(self, batch=None, fisher_labels=None, fisher_eps=None, fetch=True, group=None):
+        """The reference's `session.run([..., optimize_op], feed_dict)` (a2c_acktr.py:117-126)."""
+        if batch is not None:
+            self.load_batch(batch["observations"], batch["bootstrap_observations"], batch["actions"], batch["rewards"],
+                            batch["terminals"])
+        self.phase1(fisher_labels, fisher_eps)
+        self.allreduce(group)
+        self.phase2()
+        if not fetch:
+            return None
+        return self.fetch_scalars()
+
+    def fetch_scalars(self):
+        self._pinned_scalars.copy_(self.scalars, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        vals = self._pinned_scalars.tolist()
+        return dict(zip(SCALAR_NAMES, vals))
+
+    # ------------------------------------------------------------------ acting
+    def act(self, observations, uniform=None, greedy=False, want_logits=False):
+        """Forward + categorical sample / argmax on [rows,84,84,4] uint8 device observations
+        (ActorCriticModel.sample_actions / select_max_actions, model.py:135-169)."""
+        if not observations.is_cuda:
+            observations = observations.to(self.device, non_blocking=True)
+        observations = observations.contiguous()
+        rows = observations.shape[0]
+        actions = torch.empty(rows, dtype=torch.int32, device=self.device)
+        logits = torch.empty((rows, self.config.num_actions), dtype=torch.float32, device=self.device) if want_logits else None
+        values = torch.empty(rows, dtype=torch.float32, device=self.device) if want_logits else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.acx_learner_act(
+                self._h, ctypes.c_void_p(observations.data_ptr()), rows,
+                ctypes.c_void_p(uniform.data_ptr()) if uniform is not None else None, int(bool(greedy)),
+                ctypes.c_void_p(actions.data_ptr()),
+                ctypes.c_void_p(logits.data_ptr()) if want_logits else None,
+                ctypes.c_void_p(values.data_ptr()) if want_logits else None, self._stream()))
+        if want_logits:
+            return actions, logits, values
+        return actions

@@ -124,6 +124,12 @@ typedef struct {
   int num_locations_mode;      /* 0 = true VALID output count, 1 = kfac-0.1 input//stride */
   int world_size;              /* data-parallel ranks (factor/gradient means are divided by it) */
   int gemm_impl;               /* 0 tensor core, 1 SIMT (debug) */
+  int precision;               /* activations / gradients are held as bf16 planes (x = hi + mid + lo); a GEMM of level L
+                                  accumulates the plane pairs (i,j) with i+j <= L (1 pair, 3 pairs ~2^-17, 6 pairs fp32 class):
+                                  0 = parity grade: 3 planes, forward/backward 6 pairs, factor SYRKs 3 pairs, preconditioning 6
+                                  1 = 2 planes, forward/backward/factors 3 pairs, preconditioning 6
+                                  2 = as 1 with the factor SYRKs on the hi plane only (bf16 inputs)
+                                  3 = single-plane bf16 everywhere (fastest; not parity grade) */
   uint64_t seed;               /* Philox seed for on-device Fisher sampling */
 } acx_learner_config_t;
 
@@ -140,9 +146,21 @@ void acx_learner_destroy(acx_learner_t* l);
 size_t acx_learner_num_params(const acx_learner_t* l);
 int acx_learner_set_params(acx_learner_t* l, const float* h_params, void* stream);
 int acx_learner_get_params(acx_learner_t* l, float* h_params, void* stream);
-/* device views (offsets in floats into the arena's fp32 region), for torch views / all-reduce */
-float* acx_learner_buffer(acx_learner_t* l, const char* name, size_t* num_floats);
-uint8_t* acx_learner_obs_buffer(acx_learner_t* l, size_t* num_bytes); /* [N+E,84,84,4] train then bootstrap rows */
+/* call after writing the "params" / "inverses" buffers directly on the device (checkpoint restore):
+ * re-derives the bf16 operand planes of the weights and of the stored inverses */
+int acx_learner_refresh_weights(acx_learner_t* l, void* stream);
+/* named device views into the arena (for torch views, the all-reduce and checkpoints); NULL + error if unknown.
+ * inputs:  "observations" u8 [N+E,84,84,4] (train rows batch-major [E,T], then the E bootstrap rows),
+ *          "actions" u8 [N], "rewards" f32 [N], "terminals" u8 [N]
+ * state:   "params" "velocity" "accum" (cold momentum / RMSProp ms) "factor_sums" "inverses" "sched"
+ * per update: "grads" "precon" "factor_stats" "reduce_bucket" (= grads | factor_stats | 4 scalars)
+ *          "logits" f32 [N+E,A] "values" f32 [N+E] "targets" "advantages" f32 [N] "dampings" f32 [12]
+ *          "scalars" f32 [16]: 0 policy_loss 1 baseline_loss 2 mean_entropy 3 loss 4 KL-clip coeff 5 <V,U>
+ *                              6 gradient global norm (cold / A2C step) 7 learning rate used
+ * per block views: "params/<layer>" "grads/<layer>" "precon/<layer>" "velocity/<layer>" "accum/<layer>" ([K+1, C]), "stats/A/<factor>"
+ *          "sums/A/<factor>" (conv1 conv2 conv3 fc4 heads), "stats/G/<layer>" "sums/G/<layer>",
+ *          "inv/A/<layer>" "inv/G/<layer>" */
+void* acx_learner_buffer(acx_learner_t* l, const char* name, size_t* num_bytes);
 
 /* One learner update = the reference's session.run(optimize_op, feed_dict) (a2c_acktr.py:117-126).
  * phase 1: forward (train + bootstrap rows), returns, loss, backward, Fisher backward, batch factor
@@ -154,7 +172,10 @@ uint8_t* acx_learner_obs_buffer(acx_learner_t* l, size_t* num_bytes); /* [N+E,84
 int acx_learner_phase1(acx_learner_t* l, const int32_t* d_fisher_labels, const float* d_fisher_eps, void* stream);
 int acx_learner_phase2(acx_learner_t* l, void* stream);
 int64_t acx_learner_global_step(const acx_learner_t* l);
-void acx_learner_set_global_step(acx_learner_t* l, int64_t gs);
+/* schedule counters (checkpoint / resume): global_step, number of covariance updates, whether the stored
+ * inverses have been computed at least once (kfac initialises them to zero). */
+int acx_learner_set_state(acx_learner_t* l, int64_t global_step, int64_t num_cov_updates, int inverses_valid, void* stream);
+int acx_learner_get_state(const acx_learner_t* l, int64_t* global_step, int64_t* num_cov_updates, int* inverses_valid);
 /* forward only on `rows` observations already in d_obs (uint8 [rows,84,84,4]) -> logits [rows,A],
  * values [rows]; then categorical sample (u in [0,1) given, or Philox) / argmax.  Replaces
  * ActorCriticModel.sample_actions / select_max_actions (model.py:135-169). */
