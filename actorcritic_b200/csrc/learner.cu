@@ -90,6 +90,10 @@ struct acx_learner {
   bool inverses_valid;
   uint64_t act_calls;
   int lvl_fwd, lvl_bwd, lvl_factor, lvl_precon, act_planes;
+  // optional stage timing (CUDA events on the launching stream)
+  bool profiling = false;
+  cudaEvent_t ev[ACX_NUM_STAGES + 2];
+  bool ev_set[ACX_NUM_STAGES + 2];
   std::map<std::string, Buf> named;
 };
 
@@ -378,6 +382,13 @@ static int run_gemm(acx_learner* l, const Planes& a, const Planes& b, int trans,
   return gemm_dispatch(&g, l->cfg.gemm_impl, st);
 }
 
+// stage boundaries: mark k closes stage k-1 (phase 1: marks 0..4, phase 2: marks 5..9)
+static void mark(acx_learner* l, int k, cudaStream_t st) {
+  if (!l->profiling) return;
+  cudaEventRecord(l->ev[k], st);
+  l->ev_set[k] = true;
+}
+
 #define ACX_TRY(expr)        \
   do {                       \
     int _r = (expr);         \
@@ -459,7 +470,9 @@ static int phase1(acx_learner* l, const int32_t* fisher_labels, const float* fis
   const bool acktr = l->cfg.acktr != 0;
   const bool fisher = acktr && l->gs >= l->cfg.num_cold_updates;   // kfac_utils.py:42-44: covariances only after the cold phase
   const int RB = fisher ? 2 * N : N;
+  mark(l, 0, st);
   ACX_TRY(forward(l, l->obs, l->R, st));
+  mark(l, 1, st);
   // targets use the bootstrap tower's values = rows [N, N+E) (envs/atari/model.py:116,126-127)
   ACX_TRY(returns_launch(l->rewards, l->terminals, l->values, l->values + N, l->cfg.gamma, E, T, l->targets, l->adv, st));
   ACX_TRY(loss_grad(l->logits, l->values, l->actions, l->targets, fisher_labels, fisher_eps, l->cfg.seed, l->sched, N, A,
@@ -467,6 +480,7 @@ static int phase1(acx_learner* l, const int32_t* fisher_labels, const float* fis
   ACX_TRY(heads_bwd(l->dheads, l->params + l->L[4].off, l->params + l->L[5].off, l->act4, N, RB, A, l->dpre4,
                     l->grads + l->L[4].off, l->grads + l->L[5].off, st));
   const Planes flat3 = with_ld(l->act3, 49 * c3);
+  mark(l, 2, st);
   // ---- fc4
   ACX_TRY(weight_grad(l, 3, flat3, l->dpre4, N, 1.0f, st));
   {
@@ -498,6 +512,7 @@ static int phase1(acx_learner* l, const int32_t* fisher_labels, const float* fis
   }
   // ---- conv1 (no input gradient: observations are constants, envs/atari/model.py:101-104)
   ACX_TRY(weight_grad(l, 0, l->P1, l->dpre1, N * 400, 1.0f / 255.0f, st));
+  mark(l, 3, st);
   if (fisher) {
     // ---- the 11 batch factor statistics
     ACX_TRY(heads_gfactor(l->dheads + (size_t)N * (A + 1), N, A, l->stats + l->goff[4], l->stats + l->goff[5], st));
@@ -512,6 +527,7 @@ static int phase1(acx_learner* l, const int32_t* fisher_labels, const float* fis
     ACX_TRY(input_factor(l, 3, flat3, N, 49 * c3, r4, r4, st));
     ACX_TRY(input_factor(l, 4, l->act4, N, 512, r4, r4, st));
   }
+  mark(l, 4, st);
   return 0;
 }
 
@@ -538,6 +554,7 @@ static int precondition(acx_learner* l, cudaStream_t st) {
 static int phase2(acx_learner* l, cudaStream_t st) {
   const acx_learner_config_t& c = l->cfg;
   const size_t P = l->num_params;
+  mark(l, 5, st);
   if (c.world_size > 1) ACX_TRY(scale_f32(l->bucket, l->bucket_floats, 1.0f / (float)c.world_size, st));
   ACX_CUDA(cudaMemcpyAsync(l->scalars, l->bscalars, 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   ACX_TRY(sched_begin(l->sched, c.lr_start, c.lr_end, c.lr_decay_steps, l->scalars + 7, st));
@@ -547,7 +564,9 @@ static int phase2(acx_learner* l, cudaStream_t st) {
                               c.rms_epsilon, c.clip_norm, l->scalars + 6, st));
     ACX_TRY(sched_advance(l->sched, 1, 0, c.cov_ema_decay, 1, st));
     l->gs += 1;
-    return refresh_weight_planes(l, st);
+    ACX_TRY(refresh_weight_planes(l, st));
+    for (int k = 6; k <= 9; ++k) mark(l, k, st);
+    return 0;
   }
   const bool cold = l->gs < c.num_cold_updates;
   if (cold) {       // kfac_utils.py:42-43: ClipGlobalNorm(Momentum(3e-4, 0.9)) - this also increments global_step
@@ -561,6 +580,7 @@ static int phase2(acx_learner* l, cudaStream_t st) {
     ACX_TRY(sched_advance(l->sched, 0, 1, c.cov_ema_decay, 1, st));
     l->ncov += 1;
   }
+  mark(l, 6, st);
   if (l->gs > c.num_cold_updates && (l->gs - c.num_cold_updates) % c.invert_every == 0) {   // kfac_utils.py:47-50
     ACX_TRY(compute_dampings(l->d_a_ptrs, l->d_g_ptrs, l->d_a_dims, l->d_g_dims, l->lambdas, 6, l->damp, st));
     ACX_TRY(spd_inverse_batched(l->h_jobs, l->d_jobs, 12, l->sched, l->damp, st));
@@ -568,8 +588,10 @@ static int phase2(acx_learner* l, cudaStream_t st) {
   }
   // kfac_utils.py:52-53 - always.  With the zero-initialised inverses of kfac the step is exactly a no-op
   // (U = 0, v stays 0) until the first refresh, so only the step counter moves.
+  mark(l, 7, st);
   if (l->inverses_valid) {
     ACX_TRY(precondition(l, st));
+    mark(l, 8, st);
     ACX_TRY(dot_partial(l->grads, l->precon, P, l->dot_partials, kDotPartials, st));
     ACX_TRY(kfac_step(l->params, l->velocity, l->precon, P, l->dot_partials, kDotPartials, l->sched, c.momentum,
                       c.norm_constraint, l->scalars + 4, st));
@@ -577,6 +599,8 @@ static int phase2(acx_learner* l, cudaStream_t st) {
   ACX_TRY(sched_advance(l->sched, 1, 0, c.cov_ema_decay, 1, st));
   l->gs += 1;
   if (cold || l->inverses_valid) ACX_TRY(refresh_weight_planes(l, st));
+  if (!l->inverses_valid) mark(l, 8, st);
+  mark(l, 9, st);
   return 0;
 }
 
@@ -678,7 +702,43 @@ acx_learner_t* acx_learner_create(const acx_learner_config_t* cfg, void* d_arena
   return l;
 }
 
-void acx_learner_destroy(acx_learner_t* l) { delete l; }
+void acx_learner_destroy(acx_learner_t* l) {
+  if (l && l->profiling)
+    for (int k = 0; k < ACX_NUM_STAGES + 2; ++k) cudaEventDestroy(l->ev[k]);
+  delete l;
+}
+
+int acx_learner_set_profiling(acx_learner_t* l, int enable) {
+  ACX_CHECK(l, "null learner");
+  if (enable && !l->profiling) {
+    for (int k = 0; k < ACX_NUM_STAGES + 2; ++k) {
+      ACX_CUDA(cudaEventCreate(&l->ev[k]));
+      l->ev_set[k] = false;
+    }
+    l->profiling = true;
+  } else if (!enable && l->profiling) {
+    for (int k = 0; k < ACX_NUM_STAGES + 2; ++k) cudaEventDestroy(l->ev[k]);
+    l->profiling = false;
+  }
+  return 0;
+}
+
+int acx_learner_stage_ms(acx_learner_t* l, float* h_ms) {
+  ACX_CHECK(l && h_ms, "null argument");
+  ACX_CHECK(l->profiling, "profiling is off (acx_learner_set_profiling)");
+  // stages 0..3 = marks 0..4 (phase 1), stages 4..7 = marks 5..9 (phase 2)
+  for (int s = 0; s < ACX_NUM_STAGES; ++s) {
+    const int a = s < 4 ? s : s + 1, b = a + 1;
+    h_ms[s] = 0.0f;
+    if (l->ev_set[a] && l->ev_set[b]) {
+      ACX_CUDA(cudaEventSynchronize(l->ev[b]));
+      float ms = 0.0f;
+      ACX_CUDA(cudaEventElapsedTime(&ms, l->ev[a], l->ev[b]));
+      h_ms[s] = ms;
+    }
+  }
+  return 0;
+}
 
 size_t acx_learner_num_params(const acx_learner_t* l) { return l ? l->num_params : 0; }
 

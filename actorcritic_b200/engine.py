@@ -325,6 +325,17 @@ class Engine:
         vals = self._pinned_scalars.tolist()
         return dict(zip(SCALAR_NAMES, vals))
 
+    # ------------------------------------------------------------------ stage timing
+    STAGES = ("forward", "loss_heads", "backward", "factors", "ema_or_cold", "inverse", "precondition", "apply")
+
+    def set_profiling(self, enable=True):
+        _lib.check(self.lib.acx_learner_set_profiling(self._h, int(bool(enable))))
+
+    def stage_ms(self):
+        arr = (ctypes.c_float * 8)()
+        _lib.check(self.lib.acx_learner_stage_ms(self._h, arr))
+        return dict(zip(self.STAGES, [float(x) for x in arr]))
+
     # ------------------------------------------------------------------ acting
     def act(self, observations, uniform=None, greedy=False, want_logits=False):
         """Forward + categorical sample / argmax on [rows,84,84,4] uint8 device observations

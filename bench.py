@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py - the ACKTR learner update of jrobine/actor-critic on B200 (one process per GPU).
+
+A step = one learner update = the reference's `session.run([..., optimize_op], feed_dict)`
+(actorcritic/examples/atari/a2c_acktr.py:117-126) in its steady state: forward of the 32x20 train rows and
+the 32 bootstrap rows, returns/advantages, A2C loss, backward, Fisher-sample backward, the 11 K-FAC factor
+statistics, their EMA, the inverse refresh every 10th update, preconditioning, KL clip, momentum, apply.
+Weak scaling: 32 environments x 20 steps PER GPU (8 GPUs = BASELINE.json's 256 x 20 configuration), one NCCL
+all-reduce of [gradients | factor statistics | loss scalars] per update.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Prints ONE JSON line (rank 0).  `value` = env-steps/s (updates/s x envs x steps, whole job) with the inputs
+resident in HBM; `e2e` = the same with the five train-step inputs coming from pinned host memory every step and
+the loss scalars read back; `roofline` = the factor-statistics GEMM stage timed live with CUDA events;
+`cpu_baseline` = the CPU restatement of the reference's update (oracle/, fp32 torch-CPU, all host threads)
+timed on this box.  `--impl reference` times that CPU restatement alone (TensorFlow-1.x + tensorflow/kfac, the
+reference's real dependencies, are not installable offline - see DESIGN.md).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+
+METRIC = "acktr_learner_env_steps_per_sec"
+UNIT = "env-steps/s"
+FRAMESKIP = 4   # a2c_acktr.py:195 - emulator frames per env-step
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=32)
+    ap.add_argument("--num-steps", type=int, default=20)
+    ap.add_argument("--conv3", type=int, default=32)
+    ap.add_argument("--precision", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=15.0)
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tensor_burst=p["bf16_tflops"], tensor_sustained=p["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+def workload_name(args, world):
+    return "ACKTR Nature-CNN, %d envs x %d steps per GPU (%d x %d total), conv3=%d, 4 actions, factor EMA every update, " \
+           "inverse refresh every 10 updates" % (args.envs_per_gpu, args.num_steps, args.envs_per_gpu * world,
+                                                 args.num_steps, args.conv3)
+
+
+def algorithmic_flops(n_rows, e_rows, c3, num_actions=4):
+    """Per-update algorithmic FLOPs (MAC = 2) of each stage, SURVEY 8(d)."""
+    mac = 3276800 + 2654208 + 903168 * c3 // 32 + 49 * c3 * 512 + 512 * (num_actions + 1)
+    dgrad_mac = 2654208 + 903168 * c3 // 32 + 49 * c3 * 512 + 512 * (num_actions + 1)      # no conv1 input gradient
+    dims = [(n_rows * 400, 257), (n_rows * 81, 513), (n_rows * 49, 577), (n_rows, 49 * c3 + 1), (n_rows, 513)]
+    a_half = sum(r * d * (d + 1) for r, d in dims)
+    gdims = [(n_rows * 400, 32), (n_rows * 81, 64), (n_rows * 49, c3), (n_rows, 512), (n_rows, num_actions), (n_rows, 1)]
+    g_half = sum(r * d * (d + 1) for r, d in gdims)
+    layers = [(257, 32), (513, 64), (577, c3), (49 * c3 + 1, 512), (513, num_actions), (513, 1)]
+    precon = sum(2 * d * d * c + 2 * d * c * c for d, c in layers)
+    inverse = sum(2 * d ** 3 + 2 * c ** 3 for d, c in layers)     # Gauss-Jordan: 2 n^3
+    return dict(forward=2.0 * mac * (n_rows + e_rows), backward=2.0 * mac * n_rows + 2.0 * dgrad_mac * 2 * n_rows,
+                factors=float(a_half + g_half), precondition=float(precon), inverse=float(inverse))
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), power_w_max=float(max(power)),
+                    samples=len(sm), reasons=sorted(reasons))
+
+
+def make_batches(count, envs, steps, seed):
+    import synth
+    return [synth.rollout(seed + i, envs, steps, 4, terminal_prob=0.05, obs_kind="uniform") for i in range(count)]
+
+
+def cpu_reference_rate(args, budget_s, warmup=1, steps=None):
+    """The CPU restatement of the reference's update (oracle/learner.py, fp32, reference_cost=True: materialised
+    patch matrices, [E,T,T] discount matrices, two towers, separate Fisher backward, dense inverses) on a bounded
+    sample: whole 32x20 updates in the steady state (covariances every update, inverses every 10th)."""
+    import torch
+    import synth
+    from oracle import kfac as K
+    from oracle import learner as OL
+    from oracle import network as onet
+    torch.set_num_threads(os.cpu_count() or 1)
+    envs, t_count = args.envs_per_gpu, args.num_steps
+    params = onet.init_params(4, args.conv3, 0)
+    o = OL.OracleLearner(params, 4, args.conv3, acktr=True, cfg=K.KfacConfig(decay_steps=1e7 / (envs * t_count)),
+                         dtype=torch.float32, reference_cost=True)
+    o.global_step = 30
+    batch = synth.rollout(1, envs, t_count, 4)
+    n = envs * t_count
+    y_hat, eps = synth.fisher_samples(2, n)
+    # reach the first inverse refresh outside the timed sample (9 cheap "updates" would be the honest way, but each
+    # costs ~1 s; instead run the covariance + inverse update once directly)
+    info = o.compute(batch, y_hat, eps, need_fisher=True)
+    o.kfac.update_covs(info["new_a"], info["new_g"])
+    o.kfac.update_inverses()
+    o.global_step = 40
+    for _ in range(warmup):
+        o.update(batch, y_hat, eps)
+    times = []
+    t_begin = time.perf_counter()
+    while True:
+        t0 = time.perf_counter()
+        o.update(batch, y_hat, eps)
+        times.append(time.perf_counter() - t0)
+        if steps is not None and len(times) >= steps:
+            break
+        if steps is None and (time.perf_counter() - t_begin > budget_s or len(times) >= 50):
+            break
+    sec = float(np.mean(times))
+    return dict(sec_per_update=sec, updates=len(times), env_steps_per_sec=n / sec, cores=torch.get_num_threads(),
+                gs_end=o.global_step)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    budget_steps = max(1, args.steps)
+    r = cpu_reference_rate(args, budget_s=1e9, warmup=max(1, min(args.warmup, 3)), steps=min(budget_steps, 60))
+    n = args.envs_per_gpu * args.num_steps
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["env_steps_per_sec"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": r["updates"], "warmup": max(1, min(args.warmup, 3)), "ms_per_step": r["sec_per_update"] * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "updates_per_sec": 1.0 / r["sec_per_update"], "env_frames_per_sec": r["env_steps_per_sec"] * FRAMESKIP,
+        "config": {"workload": workload_name(args, args.gpus),
+                   "note": "CPU restatement of the reference's TF+kfac update (oracle/learner.py, fp32 torch-CPU); the "
+                           "reference itself needs TensorFlow 1.x + tensorflow/kfac, not installable offline"},
+        "cpu_baseline": {"value": r["env_steps_per_sec"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                         "sample": "%d whole %dx%d ACKTR updates (%d rows each), steady state incl. inverse refresh every 10"
+                                   % (r["updates"], args.envs_per_gpu, args.num_steps, n)},
+        "e2e": {"value": r["env_steps_per_sec"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_native(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from actorcritic_b200 import engine as eng
+    from actorcritic_b200 import _lib
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    envs, t_count, c3 = args.envs_per_gpu, args.num_steps, args.conv3
+    n = envs * t_count
+    cfg = eng.EngineConfig(num_envs=envs, num_steps=t_count, conv3_filters=c3, precision=args.precision,
+                           world_size=world, seed=1234 + rank)
+    e = eng.Engine(cfg, dev)
+    e.set_params(eng.orthogonal_init(4, c3, seed=0))
+    # synthetic inputs: 8 resident batches (8 x 19 MB > L2) + the same in pinned host memory for the e2e leg
+    batches = make_batches(8, envs, t_count, seed=1000 * (rank + 1))
+    keys = ("observations", "bootstrap_observations", "actions", "rewards", "terminals")
+    host = [{k: torch.from_numpy(np.ascontiguousarray(b[k] if b[k].dtype != bool else b[k].astype(np.uint8))).pin_memory()
+             for k in keys} for b in batches]
+    resident = [{k: v.to(dev) for k, v in hb.items()} for hb in host]
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
+    torch.cuda.synchronize()
+
+    def step(i, src, fetch):
+        b = src[i % len(src)]
+        e.load_batch(b["observations"], b["bootstrap_observations"], b["actions"], b["rewards"], b["terminals"])
+        e.phase1()
+        e.allreduce()
+        e.phase2()
+        return e.fetch_scalars() if fetch else None
+
+    # prime: post-cold state, then enough updates to pass the first inverse refresh (not part of warm-up or timing)
+    e.set_state(30, 0, False)
+    for i in range(11):
+        step(i, resident, False)
+    torch.cuda.synchronize()
+    assert e.get_state()["inverses_valid"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(src, fetch, steps, warmup):
+        for i in range(warmup):
+            step(i, src, fetch)
+        barrier()
+        launches0 = _lib.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        last = None
+        for i in range(steps):
+            last = step(i, src, fetch)
+        ev1.record()
+        barrier()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), _lib.launch_count() - launches0, last
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_dev, launches, _ = timed(resident, False, args.steps, max(3, args.warmup))
+    ms_e2e, _, scal = timed(host, True, args.steps, 3)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # stage timing (CUDA events inside the engine, one host sync per step)
+    e.set_profiling(True)
+    stage_sum = {}
+    prof_steps = min(args.steps, 20)
+    for i in range(prof_steps):
+        step(i, resident, False)
+        torch.cuda.synchronize()
+        for k, v in e.stage_ms().items():
+            stage_sum.setdefault(k, []).append(v)
+    e.set_profiling(False)
+    stage_ms = {k: float(np.mean(v)) for k, v in stage_sum.items()}
+    stage_ms["inverse"] = float(np.sum(stage_sum["inverse"]) / max(1, sum(1 for x in stage_sum["inverse"] if x > 0.01)))
+    flops = algorithmic_flops(n, envs, c3)
+    total_envs = envs * world
+    ms_step = ms_dev / args.steps
+    value = total_envs * t_count / (ms_step * 1e-3)
+    e2e_value = total_envs * t_count / (ms_e2e / args.steps * 1e-3)
+    fac_tflops = flops["factors"] / (stage_ms["factors"] * 1e-3) / 1e12 if stage_ms["factors"] > 0 else 0.0
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16x3 planes, fp32 accumulate (fp32-class)" if args.precision == 0 else "bf16 planes, precision preset %d" % args.precision,
+        "data": "synthetic",
+        "updates_per_sec": 1e3 / ms_step, "env_frames_per_sec": value * FRAMESKIP,
+        "config": {"workload": workload_name(args, world), "precision": args.precision,
+                   "l2": "8 resident input batches rotated (152 MB > 126 MB L2); per-step intermediates ~0.9 GB, self-flushing",
+                   "parallelism": "dp%d (envs sharded, one NCCL all-reduce of grads+factor statistics per update)" % world},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 64,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel, factor-statistics stage (11 SYRKs A=[P 1]^T[P 1], G=g^T g)",
+                     "achieved": fac_tflops, "peak": peaks["tensor_sustained"], "unit": "TFLOP/s",
+                     "frac": fac_tflops / peaks["tensor_sustained"], "traffic": None,
+                     "algorithmic_gflop_per_launch_group": flops["factors"] / 1e9, "peak_source": peaks["source"] + ", sustained bf16",
+                     "stage_ms": stage_ms,
+                     "stage_tflops": {k: flops[k] / (stage_ms[k] * 1e-3) / 1e12 for k in ("forward", "backward", "factors", "precondition", "inverse")
+                                      if stage_ms.get(k, 0) > 0}},
+        "losses": scal,
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_reference_rate(args, args.cpu_budget_s)
+            line["cpu_baseline"] = {"value": r["env_steps_per_sec"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                                    "sample": "%d whole %dx%d ACKTR updates of the CPU restatement (oracle/learner.py, fp32), "
+                                              "%.2f s each" % (r["updates"], envs, t_count, r["sec_per_update"])}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-launch ourselves under torch.distributed.run
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_native(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -171,6 +171,13 @@ void* acx_learner_buffer(acx_learner_t* l, const char* name, size_t* num_bytes);
  * d_fisher_labels (int32 [N]) / d_fisher_eps (f32 [N]) inject the Fisher samples (NULL = Philox). */
 int acx_learner_phase1(acx_learner_t* l, const int32_t* d_fisher_labels, const float* d_fisher_eps, void* stream);
 int acx_learner_phase2(acx_learner_t* l, void* stream);
+/* optional stage timing with CUDA events on the launching stream (bench.py's live roofline numbers).
+ * stages: 0 forward, 1 returns+loss+heads backward, 2 backward (dgrad+wgrad), 3 factor statistics,
+ *         4 cold step / factor EMA, 5 inverse refresh, 6 preconditioning, 7 KL clip+momentum+apply+operand refresh.
+ * acx_learner_stage_ms synchronises on the recorded events and writes ACX_NUM_STAGES floats (last update). */
+#define ACX_NUM_STAGES 8
+int acx_learner_set_profiling(acx_learner_t* l, int enable);
+int acx_learner_stage_ms(acx_learner_t* l, float* h_ms);
 int64_t acx_learner_global_step(const acx_learner_t* l);
 /* schedule counters (checkpoint / resume): global_step, number of covariance updates, whether the stored
  * inverses have been computed at least once (kfac initialises them to zero). */
