@@ -1,0 +1,105 @@
+"""actorcritic/agents.py: agents that sample rollouts.  `interact()` keeps the reference's contract - the 6-tuple
+(observations, actions, rewards, terminals, next_observations, infos) in batch-major [environment][step] order
+(agents.py:26-45,157-228) - for any `MultiEnv`.  When the environment is device resident
+(envs.atari.device_env.DeviceAtariMultiEnv) the rollout stays on the GPU: K-PRE writes each step's frame stacks
+straight into a [E,T,84,84,4] rollout buffer and the tuple holds torch tensors instead of nested lists (the
+replacement for the reference's Python list shuffling)."""
+from abc import ABCMeta, abstractmethod
+
+import torch
+
+
+class Agent(object, metaclass=ABCMeta):
+    """agents.py:6-47."""
+
+    @abstractmethod
+    def interact(self, session):
+        pass
+
+
+def transpose_list(values):
+    """agents.py:231-257: [[a1, a2], [b1, b2], [c1, c2]] -> [[a1, b1, c1], [a2, b2, c2]]."""
+    return list(map(list, zip(*values)))
+
+
+class MultiEnvAgent(Agent):
+    """agents.py:134-228."""
+
+    def __init__(self, multi_env, model, num_steps):
+        self._env = multi_env
+        self._model = model
+        self._num_steps = num_steps
+        self._observations = None   # kept between calls to reuse `next_observations` (agents.py:155,198-200,219)
+
+    def interact(self, session):
+        if getattr(self._env, "device_resident", False):
+            return self._interact_device(session)
+        observation_steps, action_steps, reward_steps, terminal_steps, info_steps = [], [], [], [], []
+        next_observations = self._observations
+        if next_observations is None:
+            next_observations = self._env.reset()
+        for _ in range(self._num_steps):
+            observation_steps.append(next_observations)
+            batch_next_observations = transpose_list([next_observations])          # [env] -> [env, 1]
+            actions = self._model.sample_actions(batch_next_observations, session)
+            next_observations, rewards, terminals, infos = self._env.step(actions)
+            action_steps.append(actions)
+            reward_steps.append(rewards)
+            terminal_steps.append(terminals)
+            info_steps.append(infos)
+        self._observations = next_observations
+        return (transpose_list(observation_steps), transpose_list(action_steps), transpose_list(reward_steps),
+                transpose_list(terminal_steps), next_observations, transpose_list(info_steps))
+
+    def _interact_device(self, session):
+        env, t_count = self._env, self._num_steps
+        e_count = env.num_envs
+        dev = env.device
+        if self._observations is None:
+            self._observations = env.reset()                                       # uint8 [E,84,84,4] on the device
+        obs = torch.empty((e_count, t_count, 84, 84, 4), dtype=torch.uint8, device=dev)
+        actions = torch.empty((e_count, t_count), dtype=torch.uint8, device=dev)
+        rewards = torch.empty((e_count, t_count), dtype=torch.float32, device=dev)
+        terminals = torch.empty((e_count, t_count), dtype=torch.uint8, device=dev)
+        engine = self._model.engine
+        if engine is None:
+            engine = self._model._build_engine(session, e_count, t_count, None)
+        cur = self._observations
+        for t in range(t_count):
+            obs[:, t].copy_(cur)
+            a = engine.act(cur)                                                    # int32 [E]
+            cur, r, term = env.step_device(a)
+            actions[:, t] = a.to(torch.uint8)
+            rewards[:, t] = r
+            terminals[:, t] = term
+        self._observations = cur
+        return obs, actions, rewards, terminals.bool(), cur, [[{} for _ in range(t_count)] for _ in range(e_count)]
+
+
+class SingleEnvAgent(Agent):
+    """agents.py:50-131: same contract with one environment ([1][step])."""
+
+    def __init__(self, env, model, num_steps):
+        self._env = env
+        self._model = model
+        self._num_steps = num_steps
+        self._observation = None
+
+    def interact(self, session):
+        observations, actions, rewards, terminals, infos = [], [], [], [], []
+        next_observation = self._observation
+        if next_observation is None:
+            next_observation = self._env.reset()
+        for _ in range(self._num_steps):
+            observations.append(next_observation)
+            action = self._model.sample_actions([[next_observation]], session)[0]
+            action = action[0] if isinstance(action, list) else action
+            next_observation, reward, terminal, info = self._env.step(action)
+            actions.append(action)
+            rewards.append(reward)
+            terminals.append(terminal)
+            infos.append(info)
+            if terminal:
+                next_observation = self._env.reset()
+        self._observation = next_observation
+        return [observations], [actions], [rewards], [terminals], [next_observation], [infos]

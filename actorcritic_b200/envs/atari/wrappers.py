@@ -1,0 +1,90 @@
+"""The array-processing subset of actorcritic/envs/atari/wrappers.py, batched over environments and run by the
+K-PRE kernel (preprocess.cu): 2-frame max (wrappers.py:64-65), RGB->gray + 84x84 INTER_AREA resize (:30-33), frame
+stack push / zero-on-terminal / reset-to-4-copies (:224-235) in the order MultiEnv's auto-reset imposes
+(multi_env.py:127-132).  Bit-exact with the reference's cv2 + NumPy path (tests/test_gpu_preprocess.py).
+
+`BatchedAtariPreprocessor` is the batched form; the per-environment classes keep the reference's names and call
+the same kernel with one environment."""
+import numpy as np
+import torch
+
+from ... import ops
+from ... import spaces
+
+
+class BatchedAtariPreprocessor:
+    """Frame stacks of E environments on the device."""
+
+    def __init__(self, num_envs, device=None, num_stacked_frames=4):
+        if num_stacked_frames != 4:
+            raise NotImplementedError("the K-PRE kernel packs exactly 4 stacked frames into one 32-bit word per pixel")
+        self.num_envs = num_envs
+        self.device = torch.device("cuda") if device is None else torch.device(device)
+        self.stacks = torch.zeros((num_envs, 84, 84, 4), dtype=torch.uint8, device=self.device)
+        self.prev_terminal = torch.zeros(num_envs, dtype=torch.uint8, device=self.device)
+
+    def reset(self, raw_frames):
+        """MultiEnv.reset: stack = 4 copies of preprocess(frame) (wrappers.py:232-235)."""
+        ops.preprocess_reset(raw_frames, out=self.stacks, out_env_stride=28224)
+        self.prev_terminal.zero_()
+        return self.stacks
+
+    def step(self, raw_a, raw_b, terminal, reset_raw=None, out=None, out_env_stride=None):
+        """One MultiEnv.step: raw_a/raw_b = the last two emulator frames of each frameskip window, `terminal` = this
+        step's terminal flags; environments whose PREVIOUS step was terminal are first reset from reset_raw.
+        `out` may be a slice [:, t] of a batch-major rollout buffer."""
+        reset_mask = self.prev_terminal if reset_raw is not None else None
+        ops.preprocess_stack(raw_a, raw_b, self.stacks, terminal=terminal, reset_mask=reset_mask, reset_raw=reset_raw,
+                             out=self.stacks, out_env_stride=28224)
+        if out is not None:
+            out.copy_(self.stacks)
+        self.prev_terminal = terminal.clone() if terminal is not None else torch.zeros_like(self.prev_terminal)
+        return self.stacks
+
+
+class AtariPreprocessFrameWrapper:
+    """wrappers.py:16-33 for one environment: observation(frame) -> uint8 [84,84,1]."""
+
+    def __init__(self, env):
+        self.env = env
+        self.observation_space = spaces.Box(low=0, high=255, shape=(84, 84, 1), dtype=np.uint8)
+        self.action_space = getattr(env, "action_space", None)
+
+    def observation(self, frame):
+        raw = torch.from_numpy(np.ascontiguousarray(frame, dtype=np.uint8)[None]).cuda()
+        return ops.preprocess_reset(raw)[0, :, :, 3:4].cpu().numpy()
+
+    def reset(self, **kwargs):
+        return self.observation(self.env.reset(**kwargs))
+
+    def step(self, action):
+        observation, reward, terminal, info = self.env.step(action)
+        return self.observation(observation), reward, terminal, info
+
+
+class FrameStackWrapper:
+    """wrappers.py:201-235 for one environment that already yields [84,84,1] frames (host arrays)."""
+
+    def __init__(self, env, num_stacked_frames):
+        if num_stacked_frames != 4:
+            raise NotImplementedError("4 stacked frames (a2c_acktr.py:171)")
+        self.env = env
+        self.action_space = getattr(env, "action_space", None)
+        self.observation_space = spaces.Box(low=0, high=255, shape=(84, 84, 4), dtype=np.uint8)
+        self._stack = torch.zeros((1, 84, 84, 4), dtype=torch.uint8, device="cuda")
+
+    def step(self, action):
+        frame, reward, terminal, info = self.env.step(action)
+        word = self._stack.view(torch.int32)
+        f = torch.from_numpy(np.ascontiguousarray(frame, np.uint8).reshape(1, 84, 84, 1)).cuda()
+        shifted = torch.zeros_like(self._stack) if terminal else torch.roll(self._stack, -1, dims=-1)
+        shifted[..., 3:4] = f
+        self._stack = shifted
+        del word
+        return self._stack[0].cpu().numpy(), reward, terminal, info
+
+    def reset(self, **kwargs):
+        frame = self.env.reset(**kwargs)
+        f = torch.from_numpy(np.ascontiguousarray(frame, np.uint8).reshape(1, 84, 84, 1)).cuda()
+        self._stack = f.repeat(1, 1, 1, 4)
+        return self._stack[0].cpu().numpy()
