@@ -343,21 +343,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-// reduce split-K partials (and mirror symmetric results), then the shared epilogue
-__global__ void gemm_finalize_kernel(OutParams o, const float* ws, int ws_ld, long long ws_split_stride, int splits,
-                                     int symmetric, int bm, int bn) {
+// reduce split-K partials (and mirror symmetric results), then the shared epilogue.  Block (256 / L columns, L split
+// lanes), L in {1, 2, 4, 8}: the split lanes are combined through shared memory in a fixed order (deterministic).
+__global__ void __launch_bounds__(256) gemm_finalize_kernel(OutParams o, const float* __restrict__ ws, int ws_ld,
+                                                            long long ws_split_stride, int splits, int symmetric, int bm,
+                                                            int bn) {
+  __shared__ float red[256];
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int m = blockIdx.y;
-  if (n >= o.n || m >= o.m) return;
-  int mm = m, nn = n;
-  if (symmetric && (m / bm) > (n / bn)) {
-    mm = n;
-    nn = m;
-  }
-  const float* src = ws + (size_t)mm * ws_ld + nn;
   float acc = 0.0f;
-  for (int s = 0; s < splits; ++s) acc += src[(size_t)s * ws_split_stride];
-  store_value(o, m, n, finish_value(o, m, n, acc));
+  if (n < o.n) {
+    int mm = m, nn = n;
+    if (symmetric && (m / bm) > (n / bn)) {
+      mm = n;
+      nn = m;
+    }
+    const float* src = ws + (size_t)mm * ws_ld + nn;
+    for (int s = threadIdx.y; s < splits; s += blockDim.y) acc += src[(size_t)s * ws_split_stride];
+  }
+  if (blockDim.y > 1) {
+    red[threadIdx.y * blockDim.x + threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0) {
+      acc = 0.f;
+      for (int k = 0; k < (int)blockDim.y; ++k) acc += red[k * blockDim.x + threadIdx.x];
+    }
+  }
+  if (threadIdx.y == 0 && n < o.n) store_value(o, m, n, finish_value(o, m, n, acc));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -635,8 +647,9 @@ static int gemm_tc(const acx_gemm_t* g, cudaStream_t st) {
   }
   if (r) return r;
   if (pl.to_ws) {
-    dim3 fg(ceil_div(g->n, 256), g->m);
-    gemm_finalize_kernel<<<fg, 256, 0, st>>>(p.out, g->workspace, p.ws_ld, p.ws_split_stride, pl.splits, g->symmetric, BM,
+    const int lanes = pl.splits >= 8 ? 8 : (pl.splits >= 4 ? 4 : (pl.splits >= 2 ? 2 : 1));
+    dim3 fg(ceil_div(g->n, 256 / lanes), g->m);
+    gemm_finalize_kernel<<<fg, dim3(256 / lanes, lanes), 0, st>>>(p.out, g->workspace, p.ws_ld, p.ws_split_stride, pl.splits, g->symmetric, BM,
                                             pl.bn);
     ACX_LAUNCH_CHECK();
   }

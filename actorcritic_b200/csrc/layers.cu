@@ -338,31 +338,81 @@ __global__ void __launch_bounds__(256) heads_gfactor_kernel(const float* __restr
 
 // ------------------------------------------------------------------------------------------------
 // column sums of a planes matrix over rows [0, rows): two deterministic stages.
-// stage 1: grid (ceil(cols/128), chunks) ; stage 2: sums the chunks and scales.
+// stage 1: each CTA owns a contiguous chunk of rows; a thread owns one 8-column vector (one 16-byte load per plane
+//          and row) and a row lane, so a warp reads whole 512-byte row segments; row lanes are combined through
+//          shared memory in a fixed order.  partial[chunk][cols].
+// stage 2: sums the chunks (8 chunk lanes per column) and scales.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) colsum_stage1_kernel(const Planes x, int rows, int cols, int rows_per_chunk,
-                                                            float* __restrict__ partial) {
-  const int c = blockIdx.x * 128 + threadIdx.x;
-  if (c >= cols) return;
-  const int r0 = blockIdx.y * rows_per_chunk;
-  const int r1 = min(rows, r0 + rows_per_chunk);
-  float acc = 0.f;
-  for (int r = r0; r < r1; ++r) {
-    const size_t idx = (size_t)r * x.ld + c;
-    float v = __bfloat162float(x.p[0][idx]);
-    if (x.n > 1) v += __bfloat162float(x.p[1][idx]);
-    if (x.n > 2) v += __bfloat162float(x.p[2][idx]);
-    acc += v;
+constexpr int CS_THREADS = 256;
+constexpr int CS_MAXV = 2;   // vector columns per thread when cols / 8 > 256  (cols <= 4096)
+
+__device__ __forceinline__ void add8(float* acc, const uint4 q) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    acc[2 * i] += __uint_as_float(w[i] << 16);            // low half = even element (bf16 -> fp32 is a 16-bit shift)
+    acc[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
   }
-  partial[(size_t)blockIdx.y * cols + c] = acc;
 }
-__global__ void colsum_stage2_kernel(const float* __restrict__ partial, int chunks, int cols, float scale, float* __restrict__ out,
-                                     int out_stride) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
+
+__global__ void __launch_bounds__(CS_THREADS) colsum_stage1_kernel(const Planes x, int rows, int cols, int rows_per_chunk,
+                                                                   float* __restrict__ partial) {
+  extern __shared__ float cs_smem[];   // [lanes_r][cols]
+  const int nv = cols >> 3;
+  const int lanes_r = nv >= CS_THREADS ? 1 : CS_THREADS / nv;
+  const int row_lane = nv >= CS_THREADS ? 0 : threadIdx.x / nv;
+  const int v0 = nv >= CS_THREADS ? threadIdx.x : threadIdx.x % nv;
+  const bool active = row_lane < lanes_r;
+  const int r0 = blockIdx.x * rows_per_chunk;
+  const int r1 = min(rows, r0 + rows_per_chunk);
+  float acc[CS_MAXV][8];
+#pragma unroll
+  for (int q = 0; q < CS_MAXV; ++q)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[q][i] = 0.f;
+  if (active) {
+    for (int r = r0 + row_lane; r < r1; r += lanes_r) {
+#pragma unroll
+      for (int q = 0; q < CS_MAXV; ++q) {
+        const int v = v0 + q * CS_THREADS;
+        if (v < nv) {
+          const size_t idx = (size_t)r * x.ld + (size_t)v * 8;
+          add8(acc[q], __ldg(reinterpret_cast<const uint4*>(x.p[0] + idx)));
+          if (x.n > 1) add8(acc[q], __ldg(reinterpret_cast<const uint4*>(x.p[1] + idx)));
+          if (x.n > 2) add8(acc[q], __ldg(reinterpret_cast<const uint4*>(x.p[2] + idx)));
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < CS_MAXV; ++q) {
+      const int v = v0 + q * CS_THREADS;
+      if (v < nv)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cs_smem[(size_t)row_lane * cols + v * 8 + i] = acc[q][i];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < cols; c += CS_THREADS) {
+    float t = 0.f;
+    for (int l = 0; l < lanes_r; ++l) t += cs_smem[(size_t)l * cols + c];
+    partial[(size_t)blockIdx.x * cols + c] = t;
+  }
+}
+__global__ void __launch_bounds__(256) colsum_stage2_kernel(const float* __restrict__ partial, int chunks, int cols, float scale,
+                                                            float* __restrict__ out, int out_stride) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;   // block (32, 8)
   float acc = 0.f;
-  for (int k = 0; k < chunks; ++k) acc += partial[(size_t)k * cols + c];
-  out[(size_t)c * out_stride] = acc * scale;
+  if (c < cols)
+    for (int k = threadIdx.y; k < chunks; k += 8) acc += partial[(size_t)k * cols + c];
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+    out[(size_t)c * out_stride] = t * scale;
+  }
 }
 
 // fp32 [K, C] (row-major, the V-layout weight rows) -> transposed bf16 planes [C, ld_out]
@@ -482,15 +532,23 @@ int heads_gfactor(const float* dheads_fisher, int n_rows, int num_actions, float
 }
 int colsum(const Planes& x, int rows, int cols, float scale, float* partial, int max_chunks, float* out, int out_stride,
            cudaStream_t st) {
-  int chunks = ceil_div(rows, 256);
+  ACX_CHECK((cols & 7) == 0 && (x.ld & 7) == 0 && cols <= 8 * CS_THREADS * CS_MAXV, "colsum: cols must be a multiple of 8, <= 4096");
+  const int nv = cols >> 3;
+  const int lanes_r = nv >= CS_THREADS ? 1 : CS_THREADS / nv;
+  int chunks = ceil_div(rows, lanes_r * 4);          // at least ~4 rows per lane
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
   const int rpc = ceil_div(rows, chunks);
   chunks = ceil_div(rows, rpc);
-  dim3 grid(ceil_div(cols, 128), chunks);
-  colsum_stage1_kernel<<<grid, 128, 0, st>>>(x, rows, cols, rpc, partial);
+  const size_t smem = (size_t)lanes_r * cols * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    ACX_CUDA(cudaFuncSetAttribute(colsum_stage1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    configured = true;
+  }
+  colsum_stage1_kernel<<<chunks, CS_THREADS, smem, st>>>(x, rows, cols, rpc, partial);
   ACX_LAUNCH_CHECK();
-  colsum_stage2_kernel<<<ceil_div(cols, 128), 128, 0, st>>>(partial, chunks, cols, scale, out, out_stride);
+  colsum_stage2_kernel<<<ceil_div(cols, 32), dim3(32, 8), 0, st>>>(partial, chunks, cols, scale, out, out_stride);
   ACX_LAUNCH_CHECK();
   return 0;
 }

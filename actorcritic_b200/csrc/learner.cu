@@ -47,6 +47,23 @@ struct Arena {
   }
 };
 
+struct GraphKey {
+  int phase, variant;
+  const void* p0;
+  const void* p1;
+  bool operator<(const GraphKey& o) const {
+    if (phase != o.phase) return phase < o.phase;
+    if (variant != o.variant) return variant < o.variant;
+    if (p0 != o.p0) return p0 < o.p0;
+    return p1 < o.p1;
+  }
+};
+struct GraphEntry {
+  int uses = 0;
+  cudaGraphExec_t exec = nullptr;
+  uint64_t launches = 0;
+};
+
 }  // namespace acx
 
 using namespace acx;
@@ -95,11 +112,12 @@ struct acx_learner {
   cudaEvent_t ev[ACX_NUM_STAGES + 2];
   bool ev_set[ACX_NUM_STAGES + 2];
   std::map<std::string, Buf> named;
+  std::map<GraphKey, GraphEntry> graphs;
 };
 
 namespace acx {
 
-static const int kColsumChunks = 256;
+static const int kColsumChunks = 592;
 static const int kDotPartials = 64;
 
 static int pad8(int x) { return (x + 7) / 8 * 8; }
@@ -465,7 +483,7 @@ static int output_factor(acx_learner* l, int li, const Planes& g_fisher, int row
   return run_gemm(l, g_fisher, g_fisher, 1, L.C, L.C, rows, l->lvl_factor, 1.0f / (float)rows, 1, o, st);
 }
 
-static int phase1(acx_learner* l, const int32_t* fisher_labels, const float* fisher_eps, cudaStream_t st) {
+static int issue_phase1(acx_learner* l, const int32_t* fisher_labels, const float* fisher_eps, cudaStream_t st) {
   const int N = l->N, E = l->E, T = l->T, A = l->A, c3 = l->c3;
   const bool acktr = l->cfg.acktr != 0;
   const bool fisher = acktr && l->gs >= l->cfg.num_cold_updates;   // kfac_utils.py:42-44: covariances only after the cold phase
@@ -551,45 +569,72 @@ static int precondition(acx_learner* l, cudaStream_t st) {
   return 0;
 }
 
-static int phase2(acx_learner* l, cudaStream_t st) {
+// what one phase-2 call does, decided on the host from the schedule counters (kfac_utils.py:38-53)
+struct Plan2 {
+  bool a2c, cold, invert, kfac_apply, refresh;
+  int key() const { return (a2c ? 1 : 0) | (cold ? 2 : 0) | (invert ? 4 : 0) | (kfac_apply ? 8 : 0) | (refresh ? 16 : 0); }
+};
+
+static Plan2 plan_phase2(const acx_learner* l) {
+  const acx_learner_config_t& c = l->cfg;
+  Plan2 p = {false, false, false, false, false};
+  if (!c.acktr) {
+    p.a2c = true;
+    p.refresh = true;
+    return p;
+  }
+  p.cold = l->gs < c.num_cold_updates;
+  const int64_t gs1 = l->gs + (p.cold ? 1 : 0);   // the cold optimizer increments global_step itself (kfac_utils.py:43)
+  p.invert = gs1 > c.num_cold_updates && (gs1 - c.num_cold_updates) % c.invert_every == 0;   // kfac_utils.py:47-50
+  // kfac_utils.py:52-53 runs always; with kfac's zero-initialised inverses it is exactly a no-op (U = 0, v stays 0)
+  // until the first refresh, so only the step counter moves.
+  p.kfac_apply = l->inverses_valid || p.invert;
+  p.refresh = p.cold || p.kfac_apply;
+  return p;
+}
+
+static void advance_phase2(acx_learner* l, const Plan2& p) {
+  if (p.a2c) {
+    l->gs += 1;
+    return;
+  }
+  if (p.cold) l->gs += 1; else l->ncov += 1;
+  if (p.invert) l->inverses_valid = true;
+  l->gs += 1;
+}
+
+static int issue_phase2(acx_learner* l, const Plan2& p, cudaStream_t st) {
   const acx_learner_config_t& c = l->cfg;
   const size_t P = l->num_params;
   mark(l, 5, st);
   if (c.world_size > 1) ACX_TRY(scale_f32(l->bucket, l->bucket_floats, 1.0f / (float)c.world_size, st));
   ACX_CUDA(cudaMemcpyAsync(l->scalars, l->bscalars, 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   ACX_TRY(sched_begin(l->sched, c.lr_start, c.lr_end, c.lr_decay_steps, l->scalars + 7, st));
-  if (!c.acktr) {   // ClipGlobalNorm(RMSProp)   a2c_acktr.py:250-251
+  if (p.a2c) {   // ClipGlobalNorm(RMSProp)   a2c_acktr.py:250-251
     ACX_TRY(dot_partial(l->grads, l->grads, P, l->dot_partials, kDotPartials, st));
     ACX_TRY(rmsprop_clip_step(l->params, l->accum, l->grads, P, l->dot_partials, kDotPartials, l->sched, c.rms_decay,
                               c.rms_epsilon, c.clip_norm, l->scalars + 6, st));
     ACX_TRY(sched_advance(l->sched, 1, 0, c.cov_ema_decay, 1, st));
-    l->gs += 1;
     ACX_TRY(refresh_weight_planes(l, st));
     for (int k = 6; k <= 9; ++k) mark(l, k, st);
     return 0;
   }
-  const bool cold = l->gs < c.num_cold_updates;
-  if (cold) {       // kfac_utils.py:42-43: ClipGlobalNorm(Momentum(3e-4, 0.9)) - this also increments global_step
+  if (p.cold) {     // kfac_utils.py:42-43: ClipGlobalNorm(Momentum(3e-4, 0.9)) - this also increments global_step
     ACX_TRY(dot_partial(l->grads, l->grads, P, l->dot_partials, kDotPartials, st));
     ACX_TRY(momentum_clip_step(l->params, l->accum, l->grads, P, l->dot_partials, kDotPartials, c.cold_lr, c.cold_momentum,
                                c.clip_norm, l->scalars + 6, st));
     ACX_TRY(sched_advance(l->sched, 1, 0, c.cov_ema_decay, 1, st));
-    l->gs += 1;
   } else {          // kfac_utils.py:44: all covariance updates
     ACX_TRY(ema_update(l->sums, l->stats, l->factor_floats, c.cov_ema_decay, 1.0f, st));
     ACX_TRY(sched_advance(l->sched, 0, 1, c.cov_ema_decay, 1, st));
-    l->ncov += 1;
   }
   mark(l, 6, st);
-  if (l->gs > c.num_cold_updates && (l->gs - c.num_cold_updates) % c.invert_every == 0) {   // kfac_utils.py:47-50
+  if (p.invert) {
     ACX_TRY(compute_dampings(l->d_a_ptrs, l->d_g_ptrs, l->d_a_dims, l->d_g_dims, l->lambdas, 6, l->damp, st));
     ACX_TRY(spd_inverse_batched(l->h_jobs, l->d_jobs, 12, l->sched, l->damp, st));
-    l->inverses_valid = true;
   }
-  // kfac_utils.py:52-53 - always.  With the zero-initialised inverses of kfac the step is exactly a no-op
-  // (U = 0, v stays 0) until the first refresh, so only the step counter moves.
   mark(l, 7, st);
-  if (l->inverses_valid) {
+  if (p.kfac_apply) {
     ACX_TRY(precondition(l, st));
     mark(l, 8, st);
     ACX_TRY(dot_partial(l->grads, l->precon, P, l->dot_partials, kDotPartials, st));
@@ -597,10 +642,58 @@ static int phase2(acx_learner* l, cudaStream_t st) {
                       c.norm_constraint, l->scalars + 4, st));
   }
   ACX_TRY(sched_advance(l->sched, 1, 0, c.cov_ema_decay, 1, st));
-  l->gs += 1;
-  if (cold || l->inverses_valid) ACX_TRY(refresh_weight_planes(l, st));
-  if (!l->inverses_valid) mark(l, 8, st);
+  if (p.refresh) ACX_TRY(refresh_weight_planes(l, st));
+  if (!p.kfac_apply) mark(l, 8, st);
   mark(l, 9, st);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CUDA-graph cache: the first use of a (phase, variant) runs eagerly (it also performs one-time host work such as
+// tensor-map encoding and function attributes), the second is captured and instantiated, later uses replay the graph.
+// Valid because no kernel takes a step-dependent scalar by value (see Sched).
+// ------------------------------------------------------------------------------------------------
+template <typename F>
+static int run_cached(acx_learner* l, const GraphKey& key, cudaStream_t st, F&& issue) {
+  if (!l->cfg.use_graphs || l->profiling || st == nullptr) return issue();
+  GraphEntry& ge = l->graphs[key];
+  if (ge.uses == 0) {
+    ge.uses = 1;
+    return issue();
+  }
+  if (ge.exec == nullptr) {
+    const uint64_t before = g_launch_count;
+    ACX_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const int r = issue();
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(st, &graph);
+    if (r != 0 || e != cudaSuccess || graph == nullptr) {
+      if (graph) cudaGraphDestroy(graph);
+      if (r == 0) set_error(std::string("graph capture failed: ") + cudaGetErrorString(e));
+      return r ? r : 4;
+    }
+    ge.launches = g_launch_count - before;
+    g_launch_count = before;
+    const cudaError_t e2 = cudaGraphInstantiate(&ge.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e2 != cudaSuccess) {
+      ge.exec = nullptr;
+      set_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e2));
+      return 4;
+    }
+  }
+  ACX_CUDA(cudaGraphLaunch(ge.exec, st));
+  count_launch((int)ge.launches);
+  ge.uses += 1;
+  return 0;
+}
+
+static int phase2(acx_learner* l, cudaStream_t st) {
+  const Plan2 p = plan_phase2(l);
+  GraphKey key = {2, p.key(), nullptr, nullptr};
+  const int r = run_cached(l, key, st, [&]() { return issue_phase2(l, p, st); });
+  if (r) return r;
+  advance_phase2(l, p);
   return 0;
 }
 
@@ -703,6 +796,9 @@ acx_learner_t* acx_learner_create(const acx_learner_config_t* cfg, void* d_arena
 }
 
 void acx_learner_destroy(acx_learner_t* l) {
+  if (l)
+    for (auto& kv : l->graphs)
+      if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   if (l && l->profiling)
     for (int k = 0; k < ACX_NUM_STAGES + 2; ++k) cudaEventDestroy(l->ev[k]);
   delete l;
@@ -791,7 +887,10 @@ void* acx_learner_buffer(acx_learner_t* l, const char* name, size_t* num_bytes) 
 int acx_learner_phase1(acx_learner_t* l, const int32_t* d_fisher_labels, const float* d_fisher_eps, void* stream) {
   ACX_CHECK(l, "null learner");
   ACX_CHECK((d_fisher_labels == nullptr) == (d_fisher_eps == nullptr), "inject both Fisher labels and eps, or neither");
-  return phase1(l, d_fisher_labels, d_fisher_eps, reinterpret_cast<cudaStream_t>(stream));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool fisher = l->cfg.acktr != 0 && l->gs >= l->cfg.num_cold_updates;
+  GraphKey key = {1, fisher ? 1 : 0, d_fisher_labels, d_fisher_eps};
+  return run_cached(l, key, st, [&]() { return issue_phase1(l, d_fisher_labels, d_fisher_eps, st); });
 }
 
 int acx_learner_phase2(acx_learner_t* l, void* stream) {

@@ -7,6 +7,7 @@ path: constructing an `Engine` without a CUDA device raises.
 The hyper-parameters default to the literals of the reference's example
 (actorcritic/examples/atari/a2c_acktr.py:52,57,64-71,76,240-251).
 """
+import contextlib
 import ctypes
 import dataclasses
 
@@ -52,6 +53,7 @@ class EngineConfig:
     world_size: int = 1
     gemm_impl: int = 0
     precision: int = 0
+    use_graphs: bool = True                 # replay each update as CUDA graphs (captured on the second use of a variant)
     seed: int = 0
 
     @staticmethod
@@ -79,6 +81,7 @@ class EngineConfig:
             raise ValueError("num_locations_mode must be 'true' or 'input_div_stride'")
         c.num_locations_mode = 0 if self.num_locations_mode == "true" else 1
         c.world_size, c.gemm_impl, c.precision, c.seed = self.world_size, self.gemm_impl, self.precision, self.seed
+        c.use_graphs = int(bool(self.use_graphs))
         return c
 
 
@@ -154,6 +157,8 @@ class Engine:
         self.config = config
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self._c = config.to_c()
+        # the engine launches on its own (non-default) stream: CUDA graphs cannot be captured on the legacy stream
+        self.stream = torch.cuda.Stream(self.device)
         with torch.cuda.device(self.device):
             nbytes = self.lib.acx_learner_arena_bytes(ctypes.byref(self._c))
             if nbytes == 0:
@@ -201,7 +206,20 @@ class Engine:
         return view
 
     def _stream(self):
-        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return ctypes.c_void_p(self.stream.cuda_stream)
+
+    @contextlib.contextmanager
+    def on_stream(self):
+        """Run the enclosed torch ops on the engine's stream, ordered after what the caller's current stream has
+        queued and before what it queues next.  Inside `with torch.cuda.stream(engine.stream)` this is free."""
+        cur = torch.cuda.current_stream(self.device)
+        if cur == self.stream:
+            yield
+            return
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            yield
+        cur.wait_stream(self.stream)
 
     # ------------------------------------------------------------------ parameters / state
     def set_params(self, params):
@@ -210,12 +228,12 @@ class Engine:
         flat = np.ascontiguousarray(flat, np.float32)
         if flat.size != self.num_params:
             raise ValueError("expected %d parameters, got %d" % (self.num_params, flat.size))
-        with torch.cuda.device(self.device):
+        with self.on_stream():
             _lib.check(self.lib.acx_learner_set_params(self._h, flat.ctypes.data_as(ctypes.c_void_p), self._stream()))
 
     def get_params_flat(self):
         out = np.empty(self.num_params, np.float32)
-        with torch.cuda.device(self.device):
+        with self.on_stream():
             _lib.check(self.lib.acx_learner_get_params(self._h, out.ctypes.data_as(ctypes.c_void_p), self._stream()))
         return out
 
@@ -245,13 +263,13 @@ class Engine:
         return dict(global_step=gs.value, num_cov_updates=nc.value, inverses_valid=bool(iv.value))
 
     def set_state(self, global_step, num_cov_updates=0, inverses_valid=False):
-        with torch.cuda.device(self.device):
+        with self.on_stream():
             _lib.check(self.lib.acx_learner_set_state(self._h, int(global_step), int(num_cov_updates),
                                                       int(bool(inverses_valid)), self._stream()))
 
     def refresh_derived(self):
         """Re-derive the bf16 operand planes after writing "params" / "inverses" on the device."""
-        with torch.cuda.device(self.device):
+        with self.on_stream():
             _lib.check(self.lib.acx_learner_refresh_weights(self._h, self._stream()))
 
     def state_dict(self):
@@ -285,26 +303,28 @@ class Engine:
                 t = t.to(dtype)
             return t
 
-        self.observations[:n].view(self.num_envs, self.num_steps, *OBS_SHAPE).copy_(as_t(observations, torch.uint8),
-                                                                                  non_blocking=non_blocking)
-        self.observations[n:].copy_(as_t(bootstrap_observations, torch.uint8), non_blocking=non_blocking)
-        self.actions.copy_(as_t(actions, torch.uint8), non_blocking=non_blocking)
-        self.rewards.copy_(as_t(rewards, torch.float32), non_blocking=non_blocking)
-        self.terminals.copy_(as_t(terminals, torch.uint8), non_blocking=non_blocking)
+        with self.on_stream():
+            self.observations[:n].view(self.num_envs, self.num_steps, *OBS_SHAPE).copy_(as_t(observations, torch.uint8),
+                                                                                      non_blocking=non_blocking)
+            self.observations[n:].copy_(as_t(bootstrap_observations, torch.uint8), non_blocking=non_blocking)
+            self.actions.copy_(as_t(actions, torch.uint8), non_blocking=non_blocking)
+            self.rewards.copy_(as_t(rewards, torch.float32), non_blocking=non_blocking)
+            self.terminals.copy_(as_t(terminals, torch.uint8), non_blocking=non_blocking)
 
     def phase1(self, fisher_labels=None, fisher_eps=None):
         fl = ctypes.c_void_p(fisher_labels.data_ptr()) if fisher_labels is not None else None
         fe = ctypes.c_void_p(fisher_eps.data_ptr()) if fisher_eps is not None else None
-        with torch.cuda.device(self.device):
+        with self.on_stream():
             _lib.check(self.lib.acx_learner_phase1(self._h, fl, fe, self._stream()))
 
     def allreduce(self, group=None):
         """The one collective of the data-parallel path: sum of [grads | A | G | scalars]."""
         if self.config.world_size > 1:
-            torch.distributed.all_reduce(self.bucket, op=torch.distributed.ReduceOp.SUM, group=group)
+            with self.on_stream():
+                torch.distributed.all_reduce(self.bucket, op=torch.distributed.ReduceOp.SUM, group=group)
 
     def phase2(self):
-        with torch.cuda.device(self.device):
+        with self.on_stream():
             _lib.check(self.lib.acx_learner_phase2(self._h, self._stream()))
 
     def update(self, batch=None, fisher_labels=None, fisher_eps=None, fetch=True, group=None):
@@ -320,8 +340,9 @@ class Engine:
         return self.fetch_scalars()
 
     def fetch_scalars(self):
-        self._pinned_scalars.copy_(self.scalars, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
+        with self.on_stream():
+            self._pinned_scalars.copy_(self.scalars, non_blocking=True)
+        self.stream.synchronize()
         vals = self._pinned_scalars.tolist()
         return dict(zip(SCALAR_NAMES, vals))
 
@@ -347,7 +368,7 @@ class Engine:
         actions = torch.empty(rows, dtype=torch.int32, device=self.device)
         logits = torch.empty((rows, self.config.num_actions), dtype=torch.float32, device=self.device) if want_logits else None
         values = torch.empty(rows, dtype=torch.float32, device=self.device) if want_logits else None
-        with torch.cuda.device(self.device):
+        with self.on_stream():
             _lib.check(self.lib.acx_learner_act(
                 self._h, ctypes.c_void_p(observations.data_ptr()), rows,
                 ctypes.c_void_p(uniform.data_ptr()) if uniform is not None else None, int(bool(greedy)),

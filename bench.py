@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--num-steps", type=int, default=20)
     ap.add_argument("--conv3", type=int, default=32)
     ap.add_argument("--precision", type=int, default=0)
+    ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=15.0)
     return ap.parse_args()
@@ -211,7 +212,7 @@ def run_native(args, rank, world, local_rank):
     envs, t_count, c3 = args.envs_per_gpu, args.num_steps, args.conv3
     n = envs * t_count
     cfg = eng.EngineConfig(num_envs=envs, num_steps=t_count, conv3_filters=c3, precision=args.precision,
-                           world_size=world, seed=1234 + rank)
+                           world_size=world, seed=1234 + rank, use_graphs=not args.no_graphs)
     e = eng.Engine(cfg, dev)
     e.set_params(eng.orthogonal_init(4, c3, seed=0))
     # synthetic inputs: 8 resident batches (8 x 19 MB > L2) + the same in pinned host memory for the e2e leg
@@ -244,17 +245,19 @@ def run_native(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     def timed(src, fetch, steps, warmup):
-        for i in range(warmup):
-            step(i, src, fetch)
-        barrier()
-        launches0 = _lib.launch_count()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        last = None
-        for i in range(steps):
-            last = step(i, src, fetch)
-        ev1.record()
-        barrier()
+        # everything is launched on the engine's stream (events are recorded on that stream too)
+        with torch.cuda.stream(e.stream):
+            for i in range(warmup):
+                step(i, src, fetch)
+            barrier()
+            launches0 = _lib.launch_count()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            last = None
+            for i in range(steps):
+                last = step(i, src, fetch)
+            ev1.record()
+            barrier()
         ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -291,7 +294,7 @@ def run_native(args, rank, world, local_rank):
         "dtype": "bf16x3 planes, fp32 accumulate (fp32-class)" if args.precision == 0 else "bf16 planes, precision preset %d" % args.precision,
         "data": "synthetic",
         "updates_per_sec": 1e3 / ms_step, "env_frames_per_sec": value * FRAMESKIP,
-        "config": {"workload": workload_name(args, world), "precision": args.precision,
+        "config": {"workload": workload_name(args, world), "precision": args.precision, "cuda_graphs": not args.no_graphs,
                    "l2": "8 resident input batches rotated (152 MB > 126 MB L2); per-step intermediates ~0.9 GB, self-flushing",
                    "parallelism": "dp%d (envs sharded, one NCCL all-reduce of grads+factor statistics per update)" % world},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 64,

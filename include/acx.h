@@ -130,6 +130,8 @@ typedef struct {
                                   1 = 2 planes, forward/backward/factors 3 pairs, preconditioning 6
                                   2 = as 1 with the factor SYRKs on the hi plane only (bf16 inputs)
                                   3 = single-plane bf16 everywhere (fastest; not parity grade) */
+  int use_graphs;              /* 1 = capture each (phase, schedule variant) into a CUDA graph on its second use and replay
+                                  it afterwards (needs a non-NULL stream); 0 = launch kernel by kernel */
   uint64_t seed;               /* Philox seed for on-device Fisher sampling */
 } acx_learner_config_t;
 

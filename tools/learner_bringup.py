@@ -65,15 +65,16 @@ def timing(e_count=32, t_count=20, c3=32, precision=0, updates=30):
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     t1 = t2 = 0.0
-    for _ in range(updates):
-        ev[0].record()
-        e.phase1()
-        ev[1].record()
-        e.phase2()
-        ev[2].record()
-        torch.cuda.synchronize()
-        t1 += ev[0].elapsed_time(ev[1])
-        t2 += ev[1].elapsed_time(ev[2])
+    with torch.cuda.stream(e.stream):
+        for _ in range(updates):
+            ev[0].record()
+            e.phase1()
+            ev[1].record()
+            e.phase2()
+            ev[2].record()
+            torch.cuda.synchronize()
+            t1 += ev[0].elapsed_time(ev[1])
+            t2 += ev[1].elapsed_time(ev[2])
     s = e.fetch_scalars()
     return dict(phase1_ms=t1 / updates, phase2_ms=t2 / updates, scalars=s, gs=e.global_step,
                 launches=int(e.lib.acx_launch_count()))
