@@ -204,16 +204,16 @@ want = np.concatenate([full.mean(0), (full.T @ full / full.shape[0]).ravel(), [f
 assert np.allclose(bucket.numpy(), want, atol=1e-12), (bucket.numpy(), want)
 dist.barrier()
 dist.destroy_process_group()
-print("rank", rank, "ok")
+open(os.path.join(%(out)r, "rank%%d.ok" %% rank), "w").write("ok")
 """
 
 
 def test_bucket_allreduce_equals_full_batch_statistics_gloo_world2(tmp_path):
     script = tmp_path / "worker.py"
-    script.write_text(_WORKER % {"root": ROOT})
+    script.write_text(_WORKER % {"root": ROOT, "out": str(tmp_path)})
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29533", str(script)]
     env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
     assert res.returncode == 0, res.stdout + res.stderr
-    assert "rank 0 ok" in res.stdout and "rank 1 ok" in res.stdout
+    assert (tmp_path / "rank0.ok").exists() and (tmp_path / "rank1.ok").exists()
