@@ -37,6 +37,10 @@ struct TcParams {
   int kb_total, kb_per_split;
   int num_pairs;
   int pair_a[6], pair_b[6];
+  int npa, npb;          // planes of A / B that the pairs reference (each is loaded once per k-block)
+  int bn;                // tile width (32, 64, 128)
+  int stages;            // shared-memory ring depth
+  int tiles_m, tiles_n, num_tiles, splits, total_work;
   int symmetric;
   int to_workspace;
   float* ws;
@@ -134,7 +138,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 }
 
 // ------------------------------------------------------------------------------------------------
-// shared epilogue: one result element (or a run of them) -> fp32 C and/or bf16 planes
+// shared epilogue math: one result element -> alpha, bias, ReLU, mask
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float finish_value(const OutParams& o, int m, int n, float acc) {
   float v = o.alpha * acc;
@@ -158,189 +162,322 @@ __device__ __forceinline__ void store_value(const OutParams& o, int m, int n, fl
   }
 }
 
-// a thread owns 32 consecutive columns [n_base, n_base+32) of row m
-__device__ __forceinline__ void store_run32(const OutParams& o, int m, int n_base, const float* v) {
-  if (m >= o.m) return;
-  const bool full = (n_base + 32 <= o.n);
+// a lane owns columns (n, n+1) of row m (n even): 8-byte fp32 and 4-byte bf16x2 stores, so a warp writes 256 / 128
+// contiguous bytes of one row per instruction
+__device__ __forceinline__ void store_pair(const OutParams& o, int m, int n, float v0, float v1, bool c_vec_ok) {
+  const bool two = n + 1 < o.n;
   if (o.c) {
-    float* dst = o.c + (size_t)m * o.ldc + n_base;
-    if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    float* dst = o.c + (size_t)m * o.ldc + n;
+    if (two && c_vec_ok) {
+      *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);
     } else {
-      for (int j = 0; j < 32; ++j)
-        if (n_base + j < o.n) dst[j] = v[j];
+      dst[0] = v0;
+      if (two) dst[1] = v1;
     }
   }
   if (o.c_num_planes > 0) {
-    size_t idx = (size_t)m * o.ldcp + n_base;
-    const bool vec = full && ((o.ldcp & 7) == 0) && ((n_base & 7) == 0);
-#pragma unroll
-    for (int pl = 0; pl < ACX_MAX_PLANES; ++pl) {
-      if (pl >= o.c_num_planes) break;
-      bf16* dst = o.cp[pl] + idx;
-      if (vec && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          __align__(16) bf16 t[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            bf16 p0, p1, p2;
-            split3(v[j + q], p0, p1, p2);
-            t[q] = pl == 0 ? p0 : (pl == 1 ? p1 : p2);
-          }
-          *reinterpret_cast<uint4*>(dst + j) = *reinterpret_cast<uint4*>(t);
-        }
-      } else {
-        for (int j = 0; j < 32; ++j)
-          if (n_base + j < o.n) {
-            bf16 p0, p1, p2;
-            split3(v[j], p0, p1, p2);
-            dst[j] = pl == 0 ? p0 : (pl == 1 ? p1 : p2);
-          }
-      }
+    bf16 a0, a1, a2, b0, b1, b2;
+    split3(v0, a0, a1, a2);
+    split3(v1, b0, b1, b2);
+    const size_t idx = (size_t)m * o.ldcp + n;   // ldcp % 8 == 0 and n even: 4-byte aligned
+    if (two) {
+      *reinterpret_cast<__nv_bfloat162*>(o.cp[0] + idx) = __halves2bfloat162(a0, b0);
+      if (o.c_num_planes > 1) *reinterpret_cast<__nv_bfloat162*>(o.cp[1] + idx) = __halves2bfloat162(a1, b1);
+      if (o.c_num_planes > 2) *reinterpret_cast<__nv_bfloat162*>(o.cp[2] + idx) = __halves2bfloat162(a2, b2);
+    } else {
+      o.cp[0][idx] = a0;
+      if (o.c_num_planes > 1) o.cp[1][idx] = a1;
+      if (o.c_num_planes > 2) o.cp[2][idx] = a2;
     }
   }
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int MAX_STAGES = 8;
+constexpr int EPI_LD = 68;                              // padded row of the per-warp 32 x 64 fp32 staging tile (16-byte multiple)
+constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;          // four epilogue warps
+
 // ------------------------------------------------------------------------------------------------
-// the tcgen05 kernel.  MAJOR 0: A stored [M,K], B stored [N,K] (both K-major).
-//                      MAJOR 1: A stored [K,M], B stored [K,N] (both MN-major).
+// the tcgen05 kernel: persistent, warp specialised.
+//   warp 0      TMA producer: per k-block loads every referenced A plane and B plane ONCE into one ring stage
+//   warp 1      TMEM allocator + MMA issuer (one elected lane): all plane pairs of the stage accumulate into one
+//               fp32 accumulator; two accumulators in TMEM so that the epilogue of tile t overlaps the MMAs of t+1
+//   warps 2..5  epilogue: tcgen05.ld -> per-warp shared-memory transpose -> row-contiguous global stores
+// MAJOR 0: A stored [M,K], B stored [N,K] (both K-major).  MAJOR 1: A stored [K,M], B stored [K,N] (both MN-major).
+// Work items (tile, split) are taken round-robin: w = blockIdx.x, + gridDim.x, ...
 // ------------------------------------------------------------------------------------------------
-template <int BN, int MAJOR, int STAGES>
+template <int MAJOR>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ CUtensorMap ta1,
                const __grid_constant__ CUtensorMap ta2, const __grid_constant__ CUtensorMap tb0,
                const __grid_constant__ CUtensorMap tb1, const __grid_constant__ CUtensorMap tb2, const TcParams p) {
-  constexpr int B_TILE_BYTES = BN * BK * 2;
-  constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
-  static_assert(MAJOR == 0 || BN % 64 == 0, "MN-major tiles are built from 64-column swizzle atoms");
-
-  const int tile_n = blockIdx.x, tile_m = blockIdx.y, split = blockIdx.z;
-  if (p.symmetric && tile_m > tile_n) return;
-
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];   // 128B-swizzled TMA tiles need 1024-byte alignment
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem_raw) & 1023u) != 0) {                 // never expected; fail loudly instead of corrupting tiles
+    if (threadIdx.x == 0) atomicExch(&g_tc_error, 9);
+    return;
+  }
+  const int BN = p.bn;
+  const int b_tile_bytes = BN * BK * 2;
+  const int stage_bytes = p.npa * A_TILE_BYTES + p.npb * b_tile_bytes;
+  float* epi = reinterpret_cast<float*>(smem + p.stages * stage_bytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(epi) + EPI_BYTES);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* acc_full = empty_bar + MAX_STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = tile_m * BM, n0 = tile_n * BN;
-  const int kb0 = split * p.kb_per_split;
-  const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-  const int nkb = kb1 - kb0;
-  const int iters = nkb * p.num_pairs;
+  const uint32_t tmem_cols = (uint32_t)(2 * BN);   // 64, 128 or 256: a power of two >= 32
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 4);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // work item -> (tile_m, tile_n, split)
+  auto decode = [&](int w, int& tm, int& tn, int& split) {
+    split = w / p.num_tiles;
+    int t = w - split * p.num_tiles;
+    if (p.symmetric) {
+      tm = 0;
+      int cnt = p.tiles_n;
+      while (t >= cnt) {
+        t -= cnt;
+        ++tm;
+        --cnt;
+      }
+      tn = tm + t;
+    } else {
+      tm = t / p.tiles_n;
+      tn = t - tm * p.tiles_n;
+    }
+  };
+
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        mbar_wait(&empty_bar[s], ph ^ 1u, 1);
+      int it = 0;
+      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+        int tm, tn, split;
+        decode(w, tm, tn, split);
+        const int m0 = tm * BM, n0 = tn * BN;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         // MN-major tiles are loaded as 64-column chunks; chunks that start beyond the matrix are skipped (their
         // shared memory only feeds accumulator rows/columns that are never stored)
         const int na = MAJOR == 0 ? 0 : min(BM / 64, (p.out.m - m0 + 63) / 64);
         const int nb = MAJOR == 0 ? 0 : min(BN / 64, (p.out.n - n0 + 63) / 64);
-        mbar_expect_tx(&full_bar[s], MAJOR == 0 ? (uint32_t)STAGE_BYTES : (uint32_t)((na + nb) * BK * 128));
-        const int pr = it / nkb, kb = kb0 + it % nkb;
-        const int pa = p.pair_a[pr], pb = p.pair_b[pr];
-        const CUtensorMap* ma = pa == 0 ? &ta0 : (pa == 1 ? &ta1 : &ta2);
-        const CUtensorMap* mb = pb == 0 ? &tb0 : (pb == 1 ? &tb1 : &tb2);
-        uint8_t* a_s = smem + s * STAGE_BYTES;
-        uint8_t* b_s = a_s + A_TILE_BYTES;
-        if (MAJOR == 0) {
-          tma_load_2d(a_s, ma, &full_bar[s], kb * BK, m0);
-          tma_load_2d(b_s, mb, &full_bar[s], kb * BK, n0);
-        } else {
-#pragma unroll
-          for (int j = 0; j < BM / 64; ++j)
-            if (j < na) tma_load_2d(a_s + j * (BK * 128), ma, &full_bar[s], m0 + 64 * j, kb * BK);
-#pragma unroll
-          for (int j = 0; j < BN / 64; ++j)
-            if (j < nb) tma_load_2d(b_s + j * (BK * 128), mb, &full_bar[s], n0 + 64 * j, kb * BK);
+        const uint32_t tx = MAJOR == 0 ? (uint32_t)stage_bytes : (uint32_t)((p.npa * na + p.npb * nb) * BK * 128);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u, 1);
+          mbar_expect_tx(&full_bar[s], tx);
+          uint8_t* a_s = smem + s * stage_bytes;
+          uint8_t* b_s = a_s + p.npa * A_TILE_BYTES;
+          for (int i = 0; i < p.npa; ++i) {
+            const CUtensorMap* ma = i == 0 ? &ta0 : (i == 1 ? &ta1 : &ta2);
+            uint8_t* dst = a_s + i * A_TILE_BYTES;
+            if (MAJOR == 0) {
+              tma_load_2d(dst, ma, &full_bar[s], kb * BK, m0);
+            } else {
+              for (int j = 0; j < na; ++j) tma_load_2d(dst + j * (BK * 128), ma, &full_bar[s], m0 + 64 * j, kb * BK);
+            }
+          }
+          for (int i = 0; i < p.npb; ++i) {
+            const CUtensorMap* mb = i == 0 ? &tb0 : (i == 1 ? &tb1 : &tb2);
+            uint8_t* dst = b_s + i * b_tile_bytes;
+            if (MAJOR == 0) {
+              tma_load_2d(dst, mb, &full_bar[s], kb * BK, n0);
+            } else {
+              for (int j = 0; j < nb; ++j) tma_load_2d(dst + j * (BK * 128), mb, &full_bar[s], n0 + 64 * j, kb * BK);
+            }
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one elected lane) =====
-    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)MAJOR << 15) | ((uint32_t)MAJOR << 16) |
-                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)MAJOR << 15) | ((uint32_t)MAJOR << 16) |
+                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     const uint32_t lbo = MAJOR == 0 ? 16u : p.mn_lbo;
     const uint32_t sbo = MAJOR == 0 ? 1024u : p.mn_sbo;
     const uint32_t kstep = MAJOR == 0 ? 32u : p.mn_kstep;
-    for (int it = 0; it < iters; ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-      mbar_wait(&full_bar[s], ph, 2);
+    int it = 0, lt = 0;
+    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++lt) {
+      int tm, tn, split;
+      decode(w, tm, tn, split);
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      const int buf = lt & 1;
+      const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
+      mbar_wait(&acc_empty[buf], aph ^ 1u, 4);
       tc_fence_after();
-      if (lane == 0) {
-        const int kb = kb0 + it % nkb;
-        const int kvalid = min(BK, p.k - kb * BK);
-        const int ksteps = (kvalid + 15) >> 4;
-        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t b_addr = a_addr + A_TILE_BYTES;
-        for (int kk = 0; kk < ksteps; ++kk) {
-          const uint64_t ad = make_smem_desc(a_addr + kk * kstep, lbo, sbo);
-          const uint64_t bd = make_smem_desc(b_addr + kk * kstep, lbo, sbo);
-          umma_bf16(tmem_base, ad, bd, idesc, (it | kk) != 0 ? 1u : 0u);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        mbar_wait(&full_bar[s], ph, 2);
+        tc_fence_after();
+        if (lane == 0) {
+          const int kvalid = min(BK, p.k - kb * BK);
+          const int ksteps = (kvalid + 15) >> 4;
+          const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+          const uint32_t b_addr = a_addr + (uint32_t)(p.npa * A_TILE_BYTES);
+          for (int pr = 0; pr < p.num_pairs; ++pr) {
+            const uint32_t aa = a_addr + (uint32_t)(p.pair_a[pr] * A_TILE_BYTES);
+            const uint32_t bb = b_addr + (uint32_t)(p.pair_b[pr] * b_tile_bytes);
+            for (int kk = 0; kk < ksteps; ++kk) {
+              const uint64_t ad = make_smem_desc(aa + kk * kstep, lbo, sbo);
+              const uint64_t bd = make_smem_desc(bb + kk * kstep, lbo, sbo);
+              umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || pr > 0 || kk > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
         }
-        umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
+        __syncwarp();
       }
+      if (lane == 0) umma_commit(&acc_full[buf]);
       __syncwarp();
     }
-    if (lane == 0) umma_commit(tmem_full_bar);
-    __syncwarp();
   } else {
-    // ===== epilogue: TMEM -> registers -> global =====
-    mbar_wait(tmem_full_bar, 0, 3);
-    tc_fence_after();
+    // ===== epilogue: TMEM -> registers -> shared-memory transpose -> global =====
+    // A lane owns 4 consecutive columns; CH / 4 lanes cover one row of the chunk, so every global store instruction
+    // writes whole contiguous row segments (fp32: 16 B per lane, bf16 planes: 8 B per lane).  Shared-memory rows are
+    // padded to 68 floats: the 128-bit row writes and the 128-bit transposed reads are both conflict free.
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;
-    const int m = m0 + row;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t raw[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, raw);
-      float v[32];
-      if (p.to_workspace) {
-        float* dst = p.ws + (size_t)split * p.ws_split_stride + (size_t)m * p.ws_ld + n0 + c0;
+    float* st = epi + (size_t)q * 32 * EPI_LD;
+    const int CH = BN >= 64 ? 64 : 32;
+    const int lpr = CH >> 2;              // lanes per row
+    const int rpi = 32 / lpr;             // rows per iteration
+    const int rsub = lane / lpr;
+    const int cl = (lane - rsub * lpr) * 4;
+    const OutParams& o = p.out;
+    float* const oc = o.c;
+    bf16* const cp0 = o.cp[0];
+    bf16* const cp1 = o.cp[1];
+    bf16* const cp2 = o.cp[2];
+    const int npl = o.c_num_planes;
+    const bool c_vec = oc != nullptr && (o.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(oc) & 15) == 0;
+    const float alpha = o.alpha;
+    int lt = 0;
+    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++lt) {
+      int tm, tn, split;
+      decode(w, tm, tn, split);
+      const int m0 = tm * BM + q * 32, n0 = tn * BN;
+      const int buf = lt & 1;
+      const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
+      mbar_wait(&acc_full[buf], aph, 3);
+      tc_fence_after();
+      for (int c0 = 0; c0 < BN; c0 += CH) {
+        uint32_t raw[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0);
+        tmem_ld32(taddr, raw);
+        float4* strow = reinterpret_cast<float4*>(st + lane * EPI_LD);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]),
-                                                            __uint_as_float(raw[j + 2]), __uint_as_float(raw[j + 3]));
-      } else {
-        if (m < p.out.m) {
+        for (int j = 0; j < 8; ++j)
+          strow[j] = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]), __uint_as_float(raw[4 * j + 2]),
+                                 __uint_as_float(raw[4 * j + 3]));
+        if (CH == 64) {
+          tmem_ld32(taddr + 32u, raw);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0 + c0 + j;
-            v[j] = n < p.out.n ? finish_value(p.out, m, n, __uint_as_float(raw[j])) : 0.0f;
-          }
-          store_run32(p.out, m, n0 + c0, v);
+          for (int j = 0; j < 8; ++j)
+            strow[8 + j] = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
+                                       __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3]));
         }
+        if (c0 + CH >= BN) {   // the accumulator has been drained: hand the TMEM buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+        __syncwarp();
+        const int n = n0 + c0 + cl;
+        if (p.to_workspace) {
+          float* dst = p.ws + (size_t)split * p.ws_split_stride + (size_t)(m0 + rsub) * p.ws_ld + n;
+          for (int r = rsub; r < 32; r += rpi, dst += (size_t)rpi * p.ws_ld)
+            *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(st + r * EPI_LD + cl);
+        } else if (n < o.n) {
+          const bool full4 = n + 3 < o.n;
+          float b[4] = {0.f, 0.f, 0.f, 0.f};
+          if (o.bias) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (n + j < o.n) b[j] = __ldg(o.bias + n + j);
+          }
+          for (int r = rsub; r < 32; r += rpi) {
+            const int m = m0 + r;
+            if (m >= o.m) break;
+            const float4 a4 = *reinterpret_cast<const float4*>(st + r * EPI_LD + cl);
+            float v[4] = {fmaf(alpha, a4.x, b[0]), fmaf(alpha, a4.y, b[1]), fmaf(alpha, a4.z, b[2]), fmaf(alpha, a4.w, b[3])};
+            if (o.relu) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.0f);
+            }
+            if (o.mask) {
+              const bf16* mk = o.mask + (size_t)(m % o.mask_rows) * o.mask_ld + n;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (n + j < o.n && !(__bfloat162float(mk[j]) > 0.0f)) v[j] = 0.0f;
+            }
+            if (full4) {
+              if (oc) {
+                float* dst = oc + (size_t)m * o.ldc + n;
+                if (c_vec) {
+                  *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) dst[j] = v[j];
+                }
+              }
+              if (npl > 0) {
+                bf16 h[4], md[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) split3(v[j], h[j], md[j], lo[j]);
+                const size_t idx = (size_t)m * o.ldcp + n;   // ldcp % 8 == 0 and n % 4 == 0: 8-byte aligned
+                uint2 pk;
+                pk.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
+                pk.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+                *reinterpret_cast<uint2*>(cp0 + idx) = pk;
+                if (npl > 1) {
+                  pk.x = (uint32_t)__bfloat16_as_ushort(md[0]) | ((uint32_t)__bfloat16_as_ushort(md[1]) << 16);
+                  pk.y = (uint32_t)__bfloat16_as_ushort(md[2]) | ((uint32_t)__bfloat16_as_ushort(md[3]) << 16);
+                  *reinterpret_cast<uint2*>(cp1 + idx) = pk;
+                }
+                if (npl > 2) {
+                  pk.x = (uint32_t)__bfloat16_as_ushort(lo[0]) | ((uint32_t)__bfloat16_as_ushort(lo[1]) << 16);
+                  pk.y = (uint32_t)__bfloat16_as_ushort(lo[2]) | ((uint32_t)__bfloat16_as_ushort(lo[3]) << 16);
+                  *reinterpret_cast<uint2*>(cp2 + idx) = pk;
+                }
+              }
+            } else {
+              for (int j = 0; j < 4; ++j)
+                if (n + j < o.n) store_value(o, m, n + j, v[j]);
+            }
+          }
+        }
+        __syncwarp();
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 // reduce split-K partials (and mirror symmetric results), then the shared epilogue.  Block (256 / L columns, L split
@@ -551,7 +688,7 @@ static void plan_tc(const acx_gemm_t* g, TcPlan* pl) {
   int tiles = pl->tiles_m * pl->tiles_n;
   if (g->symmetric) tiles = pl->tiles_n * (pl->tiles_n + 1) / 2;
   int splits = g->splits;
-  if (splits <= 0) {  // auto: about one CTA per SM, at least 4 k-blocks per split
+  if (splits <= 0) {  // auto: about one work item per SM, at least 4 k-blocks per split
     splits = 148 / (tiles > 0 ? tiles : 1);
     int cap = pl->kb_total / 4;
     if (splits > cap) splits = cap;
@@ -564,17 +701,29 @@ static void plan_tc(const acx_gemm_t* g, TcPlan* pl) {
   pl->ws_bytes = pl->to_ws ? (size_t)pl->splits * pl->tiles_m * BM * pl->tiles_n * pl->bn * sizeof(float) : 0;
 }
 
-template <int BN, int MAJOR, int STAGES>
-static int launch_tc(const CUtensorMap* ta, const CUtensorMap* tb, const TcParams& p, dim3 grid, cudaStream_t st) {
-  constexpr int smem = STAGES * (A_TILE_BYTES + BN * BK * 2) + 1024 + 256;
+constexpr int SMEM_LIMIT = 232448;                       // 227 KB per CTA on sm_100
+constexpr int SMEM_FIXED = EPI_BYTES + 256;              // epilogue staging + barriers (the base is 1024-aligned)
+
+template <int MAJOR>
+static int launch_tc(const CUtensorMap* ta, const CUtensorMap* tb, const TcParams& p, int grid, int smem, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    ACX_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, MAJOR, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ACX_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MAJOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     configured = true;
   }
-  gemm_tc_kernel<BN, MAJOR, STAGES><<<grid, 192, smem, st>>>(ta[0], ta[1], ta[2], tb[0], tb[1], tb[2], p);
+  gemm_tc_kernel<MAJOR><<<grid, 192, smem, st>>>(ta[0], ta[1], ta[2], tb[0], tb[1], tb[2], p);
   ACX_LAUNCH_CHECK();
   return 0;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
 }
 
 static int validate(const acx_gemm_t* g) {
@@ -623,10 +772,25 @@ static int gemm_tc(const acx_gemm_t* g, cudaStream_t st) {
   p.kb_total = pl.kb_total;
   p.kb_per_split = pl.kb_per_split;
   p.num_pairs = g->num_pairs;
+  p.npa = p.npb = 1;
   for (int i = 0; i < 6; ++i) {
     p.pair_a[i] = g->pair_a[i];
     p.pair_b[i] = g->pair_b[i];
+    if (i < g->num_pairs) {
+      if (g->pair_a[i] + 1 > p.npa) p.npa = g->pair_a[i] + 1;
+      if (g->pair_b[i] + 1 > p.npb) p.npb = g->pair_b[i] + 1;
+    }
   }
+  p.bn = pl.bn;
+  const int stage_bytes = p.npa * A_TILE_BYTES + p.npb * pl.bn * BK * 2;
+  p.stages = (SMEM_LIMIT - SMEM_FIXED) / stage_bytes;
+  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  ACX_CHECK(p.stages >= 2, "tile does not fit the shared-memory ring");
+  p.tiles_m = pl.tiles_m;
+  p.tiles_n = pl.tiles_n;
+  p.num_tiles = g->symmetric ? pl.tiles_n * (pl.tiles_n + 1) / 2 : pl.tiles_m * pl.tiles_n;
+  p.splits = pl.splits;
+  p.total_work = p.num_tiles * pl.splits;
   p.symmetric = g->symmetric;
   p.to_workspace = pl.to_ws;
   p.ws = g->workspace;
@@ -635,16 +799,9 @@ static int gemm_tc(const acx_gemm_t* g, cudaStream_t st) {
   p.mn_lbo = g_mn_lbo ? g_mn_lbo : (uint32_t)(BK * 128);
   p.mn_sbo = g_mn_sbo ? g_mn_sbo : 1024u;
   p.mn_kstep = g_mn_kstep ? g_mn_kstep : 2048u;
-  dim3 grid(pl.tiles_n, pl.tiles_m, pl.splits);
-  int r = 0;
-  if (major == 0) {
-    if (pl.bn == 32) r = launch_tc<32, 0, 6>(ta, tb, p, grid, st);
-    else if (pl.bn == 64) r = launch_tc<64, 0, 6>(ta, tb, p, grid, st);
-    else r = launch_tc<128, 0, 6>(ta, tb, p, grid, st);
-  } else {
-    if (pl.bn == 64) r = launch_tc<64, 1, 6>(ta, tb, p, grid, st);
-    else r = launch_tc<128, 1, 6>(ta, tb, p, grid, st);
-  }
+  const int grid = p.total_work < num_sms() ? p.total_work : num_sms();
+  const int smem = SMEM_FIXED + p.stages * stage_bytes;
+  int r = major == 0 ? launch_tc<0>(ta, tb, p, grid, smem, st) : launch_tc<1>(ta, tb, p, grid, smem, st);
   if (r) return r;
   if (pl.to_ws) {
     const int lanes = pl.splits >= 8 ? 8 : (pl.splits >= 4 ? 4 : (pl.splits >= 2 ? 2 : 1));

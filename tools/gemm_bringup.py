@@ -44,6 +44,10 @@ def run_case(name, m, n, k, trans, nplanes=1, impl=0, splits=0, symmetric=False,
     a_v = [p[:, :(m if trans else k)] for p in a_pl]
     b_v = [p[:, :(n if trans else k)] for p in b_pl]
     want = ref64(None, pairs, a_v, b_v, trans)
+    if kw.get("bias") is not None:
+        want = want + kw["bias"].double()[None, :]
+    if kw.get("relu"):
+        want = want.clamp_min(0)
     t0 = time.time()
     c, _ = ops.gemm(a_pl, b_pl, m, n, k, trans=trans, pairs=pairs, impl=impl, splits=splits, symmetric=symmetric, **kw)
     torch.cuda.synchronize()
@@ -90,21 +94,33 @@ def main():
     run_case("tc_mn_sym_small", 256, 256, 2560, True, symmetric=True, splits=3)
     run_case("tc_mn_x3", 512, 512, 640, True, nplanes=2)
     run_case("tc_k_bias_relu", 256, 128, 256, False, bias=torch.randn(128, device="cuda"), relu=True)
+    run_case("tc_k_bias_relu_n32", 1000, 32, 256, False, nplanes=3, bias=torch.randn(32, device="cuda"), relu=True)
+    run_case("tc_k_tiny_1x513x1", 1, 513, 1, False, nplanes=3)
+    run_case("tc_k_tiny_513x1x513", 513, 1, 513, False, nplanes=3)
+    run_case("tc_k_tiny_4x513x4", 4, 513, 4, False, nplanes=3)
+    run_case("tc_k_k32", 5000, 576, 32, False, nplanes=3)
+    run_case("tc_k_many_tiles", 20000, 512, 64, False, nplanes=3)
+    run_case("tc_mn_sym_32", 32, 32, 25600, True, symmetric=True, nplanes=2)
+    run_case("tc_mn_sym_1568", 1568, 1568, 640, True, symmetric=True, nplanes=2)
+    run_case("tc_mn_wgrad", 576, 32, 31360, True, nplanes=3)
     # timing of the big SYRK shape (conv1 A factor) and a conv1-forward-like GEMM
-    for name, m, n, k, trans, sym in [("time_syrk_conv1", 256, 256, 256000, True, True),
-                                      ("time_syrk_conv2", 512, 512, 51840, True, True),
-                                      ("time_fwd_conv1", 256000, 32, 256, False, False),
-                                      ("time_fc4", 672, 512, 1568, False, False)]:
+    for name, m, n, k, trans, sym, npl, outp in [("time_syrk_conv1", 256, 256, 256000, True, True, 1, 0),
+                                                 ("time_syrk_conv2_x3", 512, 512, 51840, True, True, 2, 0),
+                                                 ("time_fwd_conv1_x3", 268800, 32, 256, False, False, 3, 3),
+                                                 ("time_fwd_conv2_x6", 54432, 64, 512, False, False, 3, 3),
+                                                 ("time_dgrad_conv2_x6", 103680, 512, 64, False, False, 3, 0),
+                                                 ("time_wgrad_conv1_x6", 256, 32, 256000, True, False, 3, 0),
+                                                 ("time_fc4_x6", 672, 512, 1568, False, False, 3, 3)]:
         x = torch.randn((k, m) if trans else (m, k), device="cuda")
-        a_pl = ops.split_planes(x, 1)
-        b_pl = a_pl if sym else ops.split_planes(torch.randn((k, n) if trans else (n, k), device="cuda"), 1)
+        a_pl = ops.split_planes(x, npl)
+        b_pl = a_pl if sym else ops.split_planes(torch.randn((k, n) if trans else (n, k), device="cuda"), npl)
         for _ in range(3):
-            ops.gemm(a_pl, b_pl, m, n, k, trans=trans, symmetric=sym)
+            ops.gemm(a_pl, b_pl, m, n, k, trans=trans, symmetric=sym, out_planes=outp, want_f32=outp == 0)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(10):
-            ops.gemm(a_pl, b_pl, m, n, k, trans=trans, symmetric=sym)
+            ops.gemm(a_pl, b_pl, m, n, k, trans=trans, symmetric=sym, out_planes=outp, want_f32=outp == 0)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10

@@ -1,0 +1,35 @@
+"""Run one GEMM shape a few times (for ncu --set full).  usage: gemm_one.py name  (see SHAPES)."""
+import sys, os
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from actorcritic_b200 import ops
+
+SHAPES = {  # name: (m, n, k, trans, sym, planes, out_planes)
+    "fwd_conv1": (268800, 32, 256, False, False, 3, 3),
+    "fwd_conv2": (54432, 64, 512, False, False, 3, 3),
+    "dgrad_conv2": (103680, 512, 64, False, False, 3, 0),
+    "wgrad_conv1": (256, 32, 256000, True, False, 3, 0),
+    "syrk_conv1": (256, 256, 256000, True, True, 1, 0),
+    "syrk_conv2": (512, 512, 51840, True, True, 2, 0),
+    "fc4": (672, 512, 1568, False, False, 3, 3),
+}
+name = sys.argv[1]
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+m, n, k, trans, sym, npl, outp = SHAPES[name]
+x = torch.randn((k, m) if trans else (m, k), device="cuda")
+a_pl = ops.split_planes(x, npl if name != "fwd_conv1" else 1)
+b_pl = a_pl if sym else ops.split_planes(torch.randn((k, n) if trans else (n, k), device="cuda"), npl)
+pairs = None
+if name == "fwd_conv1":
+    pairs = [(0, 0), (0, 1), (0, 2)]
+bias = torch.randn(n, device="cuda") if outp else None
+for _ in range(iters):
+    ops.gemm(a_pl, b_pl, m, n, k, trans=trans, symmetric=sym, out_planes=outp, want_f32=outp == 0, pairs=pairs, bias=bias, relu=bool(outp))
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(iters):
+    ops.gemm(a_pl, b_pl, m, n, k, trans=trans, symmetric=sym, out_planes=outp, want_f32=outp == 0, pairs=pairs, bias=bias, relu=bool(outp))
+e1.record()
+torch.cuda.synchronize()
+print(name, "ms", e0.elapsed_time(e1) / iters)
