@@ -192,6 +192,13 @@ __device__ __forceinline__ void store_pair(const OutParams& o, int m, int n, flo
   }
 }
 
+__device__ __forceinline__ uint2 pack4(bf16 a, bf16 b, bf16 c, bf16 d) {
+  uint2 r;
+  r.x = (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+  r.y = (uint32_t)__bfloat16_as_ushort(c) | ((uint32_t)__bfloat16_as_ushort(d) << 16);
+  return r;
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -376,6 +383,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
     const int npl = o.c_num_planes;
     const bool c_vec = oc != nullptr && (o.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(oc) & 15) == 0;
     const float alpha = o.alpha;
+    const float* const bias = o.bias;
+    const bf16* const mask = o.mask;
+    const int mask_ld = o.mask_ld, mask_rows = o.mask_rows;
+    const bool relu = o.relu != 0;
+    const int om = o.m, on = o.n, ldc = o.ldc, ldcp = o.ldcp;
+    const bool to_ws = p.to_workspace != 0;
+    float* const ws = p.ws;
+    const int ws_ld = p.ws_ld;
+    const long long ws_split_stride = p.ws_split_stride;
     int lt = 0;
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++lt) {
       int tm, tn, split;
@@ -408,66 +424,108 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
         }
         __syncwarp();
         const int n = n0 + c0 + cl;
-        if (p.to_workspace) {
-          float* dst = p.ws + (size_t)split * p.ws_split_stride + (size_t)(m0 + rsub) * p.ws_ld + n;
-          for (int r = rsub; r < 32; r += rpi, dst += (size_t)rpi * p.ws_ld)
-            *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(st + r * EPI_LD + cl);
-        } else if (n < o.n) {
-          const bool full4 = n + 3 < o.n;
-          float b[4] = {0.f, 0.f, 0.f, 0.f};
-          if (o.bias) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (n + j < o.n) b[j] = __ldg(o.bias + n + j);
+        const float* src = st + rsub * EPI_LD + cl;
+        if (to_ws) {
+          float* dst = ws + (size_t)split * ws_split_stride + (size_t)(m0 + rsub) * ws_ld + n;
+#pragma unroll 4
+          for (int r = rsub; r < 32; r += rpi, dst += (size_t)rpi * ws_ld, src += rpi * EPI_LD)
+            *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(src);
+        } else if (n < on) {
+          const int rows_valid = min(32, om - m0);
+          float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+          if (bias) {
+            b0 = __ldg(bias + n);
+            if (n + 1 < on) b1 = __ldg(bias + n + 1);
+            if (n + 2 < on) b2 = __ldg(bias + n + 2);
+            if (n + 3 < on) b3 = __ldg(bias + n + 3);
           }
-          for (int r = rsub; r < 32; r += rpi) {
-            const int m = m0 + r;
-            if (m >= o.m) break;
-            const float4 a4 = *reinterpret_cast<const float4*>(st + r * EPI_LD + cl);
-            float v[4] = {fmaf(alpha, a4.x, b[0]), fmaf(alpha, a4.y, b[1]), fmaf(alpha, a4.z, b[2]), fmaf(alpha, a4.w, b[3])};
-            if (o.relu) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.0f);
-            }
-            if (o.mask) {
-              const bf16* mk = o.mask + (size_t)(m % o.mask_rows) * o.mask_ld + n;
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (n + j < o.n && !(__bfloat162float(mk[j]) > 0.0f)) v[j] = 0.0f;
-            }
-            if (full4) {
-              if (oc) {
-                float* dst = oc + (size_t)m * o.ldc + n;
+          if (n + 3 < on && mask == nullptr) {
+            // fast path: whole 4-column groups, no mask
+            float* dc = oc ? oc + (size_t)(m0 + rsub) * ldc + n : nullptr;
+            size_t idx = (size_t)(m0 + rsub) * ldcp + n;   // ldcp % 8 == 0 and n % 4 == 0: 8-byte aligned plane stores
+#pragma unroll 4
+            for (int r = rsub; r < rows_valid; r += rpi, src += rpi * EPI_LD, idx += (size_t)rpi * ldcp) {
+              const float4 a4 = *reinterpret_cast<const float4*>(src);
+              float v0 = fmaf(alpha, a4.x, b0), v1 = fmaf(alpha, a4.y, b1), v2 = fmaf(alpha, a4.z, b2), v3 = fmaf(alpha, a4.w, b3);
+              if (relu) {
+                v0 = fmaxf(v0, 0.0f);
+                v1 = fmaxf(v1, 0.0f);
+                v2 = fmaxf(v2, 0.0f);
+                v3 = fmaxf(v3, 0.0f);
+              }
+              if (dc) {
                 if (c_vec) {
-                  *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                  *reinterpret_cast<float4*>(dc) = make_float4(v0, v1, v2, v3);
                 } else {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) dst[j] = v[j];
+                  dc[0] = v0;
+                  dc[1] = v1;
+                  dc[2] = v2;
+                  dc[3] = v3;
                 }
+                dc += (size_t)rpi * ldc;
               }
               if (npl > 0) {
-                bf16 h[4], md[4], lo[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) split3(v[j], h[j], md[j], lo[j]);
-                const size_t idx = (size_t)m * o.ldcp + n;   // ldcp % 8 == 0 and n % 4 == 0: 8-byte aligned
-                uint2 pk;
-                pk.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
-                pk.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
-                *reinterpret_cast<uint2*>(cp0 + idx) = pk;
-                if (npl > 1) {
-                  pk.x = (uint32_t)__bfloat16_as_ushort(md[0]) | ((uint32_t)__bfloat16_as_ushort(md[1]) << 16);
-                  pk.y = (uint32_t)__bfloat16_as_ushort(md[2]) | ((uint32_t)__bfloat16_as_ushort(md[3]) << 16);
-                  *reinterpret_cast<uint2*>(cp1 + idx) = pk;
-                }
-                if (npl > 2) {
-                  pk.x = (uint32_t)__bfloat16_as_ushort(lo[0]) | ((uint32_t)__bfloat16_as_ushort(lo[1]) << 16);
-                  pk.y = (uint32_t)__bfloat16_as_ushort(lo[2]) | ((uint32_t)__bfloat16_as_ushort(lo[3]) << 16);
-                  *reinterpret_cast<uint2*>(cp2 + idx) = pk;
-                }
+                bf16 h0, h1, h2, h3, m0_, m1_, m2_, m3_, l0, l1, l2, l3;
+                split3(v0, h0, m0_, l0);
+                split3(v1, h1, m1_, l1);
+                split3(v2, h2, m2_, l2);
+                split3(v3, h3, m3_, l3);
+                *reinterpret_cast<uint2*>(cp0 + idx) = pack4(h0, h1, h2, h3);
+                if (npl > 1) *reinterpret_cast<uint2*>(cp1 + idx) = pack4(m0_, m1_, m2_, m3_);
+                if (npl > 2) *reinterpret_cast<uint2*>(cp2 + idx) = pack4(l0, l1, l2, l3);
               }
-            } else {
-              for (int j = 0; j < 4; ++j)
-                if (n + j < o.n) store_value(o, m, n + j, v[j]);
+            }
+          } else {
+            // general path: ragged right edge and / or ReLU mask of the forward activation
+            int mrow = mask ? (m0 + rsub) % mask_rows : 0;
+            const int mstep = mask ? rpi % mask_rows : 0;
+            for (int r = rsub; r < rows_valid; r += rpi, src += rpi * EPI_LD) {
+              const int m = m0 + r;
+              const float4 a4 = *reinterpret_cast<const float4*>(src);
+              float v[4] = {fmaf(alpha, a4.x, b0), fmaf(alpha, a4.y, b1), fmaf(alpha, a4.z, b2), fmaf(alpha, a4.w, b3)};
+              if (relu) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.0f);
+              }
+              if (mask) {
+                const bf16* mk = mask + (size_t)mrow * mask_ld + n;
+                if (n + 3 < on) {
+                  const uint2 mw = *reinterpret_cast<const uint2*>(mk);   // mask_ld % 8 == 0, n % 4 == 0
+                  if (!(__uint_as_float(mw.x << 16) > 0.0f)) v[0] = 0.0f;
+                  if (!(__uint_as_float(mw.x & 0xffff0000u) > 0.0f)) v[1] = 0.0f;
+                  if (!(__uint_as_float(mw.y << 16) > 0.0f)) v[2] = 0.0f;
+                  if (!(__uint_as_float(mw.y & 0xffff0000u) > 0.0f)) v[3] = 0.0f;
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    if (n + j < on && !(__bfloat162float(mk[j]) > 0.0f)) v[j] = 0.0f;
+                }
+                mrow += mstep;
+                if (mrow >= mask_rows) mrow -= mask_rows;
+              }
+              if (n + 3 < on) {
+                if (oc) {
+                  float* dc = oc + (size_t)m * ldc + n;
+                  if (c_vec) {
+                    *reinterpret_cast<float4*>(dc) = make_float4(v[0], v[1], v[2], v[3]);
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dc[j] = v[j];
+                  }
+                }
+                if (npl > 0) {
+                  bf16 h[4], md[4], lo[4];
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) split3(v[j], h[j], md[j], lo[j]);
+                  const size_t idx = (size_t)m * ldcp + n;
+                  *reinterpret_cast<uint2*>(cp0 + idx) = pack4(h[0], h[1], h[2], h[3]);
+                  if (npl > 1) *reinterpret_cast<uint2*>(cp1 + idx) = pack4(md[0], md[1], md[2], md[3]);
+                  if (npl > 2) *reinterpret_cast<uint2*>(cp2 + idx) = pack4(lo[0], lo[1], lo[2], lo[3]);
+                }
+              } else {
+                for (int j = 0; j < 4; ++j)
+                  if (n + j < on) store_value(o, m, n + j, v[j]);
+              }
             }
           }
         }
