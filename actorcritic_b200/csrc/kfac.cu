@@ -112,64 +112,98 @@ __global__ void inv_prepare_kernel(const InvDev* __restrict__ jobs, const Sched*
   }
 }
 
-// invert the IB x IB diagonal block in shared memory (unblocked Gauss-Jordan, 32x32 threads... here 1024 threads)
-__device__ void invert_block_smem(double (*d)[IB + 1], int nb) {
-  // d holds an nb x nb SPD-derived block (rows/cols >= nb are identity padding)
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 32 threads
+// invert an IB x IB block held in shared memory, in place (unblocked Gauss-Jordan without pivoting; rows/columns >= nb
+// are identity padding).  Works for any block size that is a multiple of 32 threads; every thread must call it.
+__device__ void invert_block_smem(double (*d)[IB + 1]) {
+  const int nthreads = blockDim.x;
   for (int k = 0; k < IB; ++k) {
     __syncthreads();
-    const double pivot = d[k][k];
-    const double inv_p = 1.0 / pivot;
-    const double row_k = d[k][tx];
-    const double col_k = d[ty][k];
+    const double inv_p = 1.0 / d[k][k];
+    double v[4];
+    int cnt = 0;
+    for (int e = threadIdx.x; e < IB * IB; e += nthreads, ++cnt) {
+      const int ty = e >> 5, tx = e & 31;
+      const double row_k = d[k][tx], col_k = d[ty][k];
+      if (ty == k && tx == k)
+        v[cnt] = inv_p;
+      else if (ty == k)
+        v[cnt] = row_k * inv_p;
+      else if (tx == k)
+        v[cnt] = -col_k * inv_p;
+      else
+        v[cnt] = d[ty][tx] - col_k * row_k * inv_p;
+    }
     __syncthreads();
-    double v;
-    if (ty == k && tx == k)
-      v = inv_p;
-    else if (ty == k)
-      v = row_k * inv_p;
-    else if (tx == k)
-      v = -col_k * inv_p;
-    else
-      v = d[ty][tx] - col_k * row_k * inv_p;
-    d[ty][tx] = v;
+    cnt = 0;
+    for (int e = threadIdx.x; e < IB * IB; e += nthreads, ++cnt) d[e >> 5][e & 31] = v[cnt];
   }
   __syncthreads();
 }
 
-// step kernel A: grid.x = column blocks (ceil(n / IB)), grid.z = job.  Every CTA inverts the pivot block
-// (redundantly - it is 32 steps) and computes its R_j = D^-1 M_pj into rbuf; CTA j == p stores D^-1.
-__global__ void __launch_bounds__(1024) inv_rowpanel_kernel(const InvDev* __restrict__ jobs, int p) {
+// per-job scratch inside InvDev::rbuf:  R [IB][n] | Cold [n][IB] | Cnew [n][IB] | Dinv [2][IB][IB] (by pivot parity: the
+// update kernel of step p reads D_p^-1 while one of its CTAs already writes D_{p+1}^-1)
+__device__ __forceinline__ double* scratch_r(const InvDev& jb) { return jb.rbuf; }
+__device__ __forceinline__ double* scratch_cold(const InvDev& jb) { return jb.rbuf + (size_t)IB * jb.n; }
+__device__ __forceinline__ double* scratch_cnew(const InvDev& jb) { return jb.rbuf + (size_t)2 * IB * jb.n; }
+__device__ __forceinline__ double* scratch_dinv(const InvDev& jb, int p) {
+  return jb.rbuf + (size_t)3 * IB * jb.n + (size_t)(p & 1) * IB * IB;
+}
+
+// D_0^-1 of every job (one CTA of 256 threads per job) - later pivot inverses come out of the update kernel
+__global__ void __launch_bounds__(256) inv_diag0_kernel(const InvDev* __restrict__ jobs) {
+  const InvDev jb = jobs[blockIdx.z];
+  const int n = jb.n;
+  __shared__ double d[IB][IB + 1];
+  const int nb = min(IB, n);
+  for (int e = threadIdx.x; e < IB * IB; e += 256) {
+    const int ty = e >> 5, tx = e & 31;
+    d[ty][tx] = (ty < nb && tx < nb) ? jb.m[(size_t)ty * n + tx] : (ty == tx ? 1.0 : 0.0);
+  }
+  invert_block_smem(d);
+  double* dinv = scratch_dinv(jb, 0);
+  for (int e = threadIdx.x; e < IB * IB; e += 256) dinv[e] = d[e >> 5][e & 31];
+}
+
+// step kernel A (panels): grid.x = 2 * nblk.  CTAs [0, nblk): R_j = D^-1 M_pj.  CTAs [nblk, 2 nblk): copy of the old
+// column panel M_ip and Cnew_i = -M_ip D^-1.  1024 threads = one 32 x 32 block.
+__global__ void __launch_bounds__(1024) inv_panels_kernel(const InvDev* __restrict__ jobs, int p, int nblk) {
   const InvDev jb = jobs[blockIdx.z];
   const int n = jb.n;
   const int p0 = p * IB;
   if (p0 >= n) return;
-  const int j0 = blockIdx.x * IB;
-  if (j0 >= n) return;
+  const bool is_col_cta = (int)blockIdx.x >= nblk;
+  const int blk = is_col_cta ? blockIdx.x - nblk : blockIdx.x;
+  const int b0 = blk * IB;
+  if (b0 >= n || blk == p) return;
   __shared__ double d[IB][IB + 1];
-  __shared__ double mp[IB][IB + 1];
+  __shared__ double t[IB][IB + 1];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int nb = min(IB, n - p0);
-  {
-    const int r = p0 + ty, c = p0 + tx;
-    d[ty][tx] = (ty < nb && tx < nb) ? jb.m[(size_t)r * n + c] : (ty == tx ? 1.0 : 0.0);
-    const int cj = j0 + tx;
-    mp[ty][tx] = (ty < nb && cj < n) ? jb.m[(size_t)r * n + cj] : 0.0;
-  }
-  invert_block_smem(d, nb);
-  double* dinv = jb.rbuf + (size_t)IB * n;
-  if (blockIdx.x == p) {
-    dinv[ty * IB + tx] = d[ty][tx];
-  } else {
+  d[ty][tx] = scratch_dinv(jb, p)[ty * IB + tx];
+  if (!is_col_cta) {
+    const int cj = b0 + tx;
+    t[ty][tx] = (ty < nb && cj < n) ? jb.m[(size_t)(p0 + ty) * n + cj] : 0.0;
+    __syncthreads();
     double acc = 0.0;
 #pragma unroll 8
-    for (int k = 0; k < IB; ++k) acc += d[ty][k] * mp[k][tx];
-    const int cj = j0 + tx;
-    if (cj < n) jb.rbuf[(size_t)ty * n + cj] = acc;
+    for (int k = 0; k < IB; ++k) acc += d[ty][k] * t[k][tx];
+    if (cj < n) scratch_r(jb)[(size_t)ty * n + cj] = acc;
+  } else {
+    const int gi = b0 + ty;
+    const double c = (gi < n && tx < nb) ? jb.m[(size_t)gi * n + p0 + tx] : 0.0;
+    t[ty][tx] = c;
+    if (gi < n) scratch_cold(jb)[(size_t)gi * IB + tx] = c;
+    __syncthreads();
+    double acc = 0.0;
+#pragma unroll 8
+    for (int k = 0; k < IB; ++k) acc += t[ty][k] * d[k][tx];
+    if (gi < n) scratch_cnew(jb)[(size_t)gi * IB + tx] = -acc;
   }
 }
 
-// step kernel B: M_ij -= M_ip R_j for i, j != p.  CTA tile 64 x 64, 256 threads, 4 x 4 per thread.
+// step kernel B (update), CTA tile 64 x 64, 256 threads, 4 x 4 per thread:
+//   M_ij -= Cold_i R_j (i, j != p);  M_ip = Cnew_i;  M_pj = R_j;  M_pp = D^-1;
+// the CTA that owns pivot block p+1 then inverts it (it is final after this update) for the next step.
 __global__ void __launch_bounds__(256) inv_update_kernel(const InvDev* __restrict__ jobs, int p) {
   const InvDev jb = jobs[blockIdx.z];
   const int n = jb.n;
@@ -177,18 +211,20 @@ __global__ void __launch_bounds__(256) inv_update_kernel(const InvDev* __restric
   if (p0 >= n) return;
   const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
   if (i0 >= n || j0 >= n) return;
-  __shared__ double cs[64][IB + 1];  // M_ip tile  [64 rows][32]
-  __shared__ double rs[IB][64 + 1];  // R tile     [32][64 cols]
+  __shared__ double cs[64][IB + 1];  // Cold tile [64 rows][32]
+  __shared__ double rs[IB][64 + 1];  // R tile    [32][64 cols]
   const int nb = min(IB, n - p0);
+  const double* cold = scratch_cold(jb);
+  const double* rb = scratch_r(jb);
   for (int idx = threadIdx.x; idx < 64 * IB; idx += 256) {
     const int r = idx / IB, k = idx % IB;
     const int gi = i0 + r;
-    cs[r][k] = (gi < n && k < nb) ? jb.m[(size_t)gi * n + p0 + k] : 0.0;
+    cs[r][k] = (gi < n && k < nb && !(gi >= p0 && gi < p0 + IB)) ? cold[(size_t)gi * IB + k] : 0.0;
   }
   for (int idx = threadIdx.x; idx < IB * 64; idx += 256) {
     const int k = idx / 64, c = idx % 64;
     const int gj = j0 + c;
-    rs[k][c] = (gj < n && k < nb) ? jb.rbuf[(size_t)k * n + gj] : 0.0;
+    rs[k][c] = (gj < n && k < nb && !(gj >= p0 && gj < p0 + IB)) ? rb[(size_t)k * n + gj] : 0.0;
   }
   __syncthreads();
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -206,52 +242,43 @@ __global__ void __launch_bounds__(256) inv_update_kernel(const InvDev* __restric
 #pragma unroll
       for (int r = 0; r < 4; ++r) acc[q][r] += a[q] * b[r];
   }
+  const double* cnew = scratch_cnew(jb);
+  const double* dinv = scratch_dinv(jb, p);
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int gi = i0 + ty + 16 * q;
-    if (gi >= n || (gi >= p0 && gi < p0 + IB)) continue;
+    if (gi >= n) continue;
+    const bool ip = gi >= p0 && gi < p0 + IB;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int gj = j0 + tx + 16 * r;
-      if (gj >= n || (gj >= p0 && gj < p0 + IB)) continue;
-      jb.m[(size_t)gi * n + gj] -= acc[q][r];
+      if (gj >= n) continue;
+      const bool jp = gj >= p0 && gj < p0 + IB;
+      double* dst = jb.m + (size_t)gi * n + gj;
+      if (ip && jp)
+        *dst = dinv[(gi - p0) * IB + (gj - p0)];
+      else if (ip)
+        *dst = rb[(size_t)(gi - p0) * n + gj];
+      else if (jp)
+        *dst = cnew[(size_t)gi * IB + (gj - p0)];
+      else
+        *dst -= acc[q][r];
     }
   }
-}
-
-// step kernel C: column panel M_ip = -M_ip D^-1 (i != p), row panel M_pj = R_j (j != p), M_pp = D^-1.
-// grid.x = row blocks of 32; 1024 threads.
-__global__ void __launch_bounds__(1024) inv_colpanel_kernel(const InvDev* __restrict__ jobs, int p) {
-  const InvDev jb = jobs[blockIdx.z];
-  const int n = jb.n;
-  const int p0 = p * IB;
-  if (p0 >= n) return;
-  const int i0 = blockIdx.x * IB;
-  if (i0 >= n) return;
-  __shared__ double d[IB][IB + 1];
-  __shared__ double c[IB][IB + 1];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int nb = min(IB, n - p0);
-  const double* dinv = jb.rbuf + (size_t)IB * n;
-  d[ty][tx] = dinv[ty * IB + tx];
-  const int gi = i0 + ty;
-  if (blockIdx.x == p) {
-    // this block holds the pivot rows: write D^-1 and the row panel
-    __syncthreads();
-    if (ty < nb && tx < nb) jb.m[(size_t)(p0 + ty) * n + p0 + tx] = d[ty][tx];
-    for (int j = threadIdx.x; j < nb * n; j += 1024) {
-      const int r = j / n, col = j % n;
-      if (col >= p0 && col < p0 + IB) continue;
-      jb.m[(size_t)(p0 + r) * n + col] = jb.rbuf[(size_t)r * n + col];
+  // next pivot block (p+1) lies inside exactly one 64 x 64 tile; that CTA inverts it now
+  const int q0 = p0 + IB;
+  if (q0 < n && q0 >= i0 && q0 < i0 + 64 && q0 >= j0 && q0 < j0 + 64) {
+    __syncthreads();   // this CTA's global writes above are visible to its own threads after the barrier
+    double (*d)[IB + 1] = reinterpret_cast<double (*)[IB + 1]>(&cs[0][0]);   // 64*33 doubles >= 32*33
+    const int nbq = min(IB, n - q0);
+    for (int e = threadIdx.x; e < IB * IB; e += 256) {
+      const int yy = e >> 5, xx = e & 31;
+      d[yy][xx] = (yy < nbq && xx < nbq) ? jb.m[(size_t)(q0 + yy) * n + q0 + xx] : (yy == xx ? 1.0 : 0.0);
     }
-    return;
+    invert_block_smem(d);
+    double* out = scratch_dinv(jb, p + 1);
+    for (int e = threadIdx.x; e < IB * IB; e += 256) out[e] = d[e >> 5][e & 31];
   }
-  c[ty][tx] = (gi < n && tx < nb) ? jb.m[(size_t)gi * n + p0 + tx] : 0.0;
-  __syncthreads();
-  double acc = 0.0;
-#pragma unroll 8
-  for (int k = 0; k < IB; ++k) acc += c[ty][k] * d[k][tx];
-  if (gi < n && tx < nb) jb.m[(size_t)gi * n + p0 + tx] = -acc;
 }
 
 __global__ void inv_finish_kernel(const InvDev* __restrict__ jobs) {
@@ -375,6 +402,98 @@ __global__ void __launch_bounds__(256) rmsprop_clip_kernel(float* __restrict__ p
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Preconditioning of the small blocks (C <= 64 output channels: conv1..3 and the two heads) in fp32 SIMT, batched over
+// blocks: U = A^-1 (V G^-1) / T~.  Two launches for all of them; only fc4 (1569 x 512) is worth the tensor cores.
+// ------------------------------------------------------------------------------------------------
+// W[r, c] = sum_k V[r, k] Ginv[k, c];  grid (ceil(d / 64), 1, jobs), 256 threads
+__global__ void __launch_bounds__(256) precon_vg_kernel(const PreconJob* __restrict__ jobs) {
+  const PreconJob jb = jobs[blockIdx.z];
+  const int d = jb.d, c = jb.c;
+  const int r0 = blockIdx.x * 64;
+  if (r0 >= d) return;
+  __shared__ float gs[64][65];
+  __shared__ float vs[64][65];
+  for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+    const int k = i >> 6, j = i & 63;
+    gs[k][j] = (k < c && j < c) ? jb.ginv[(size_t)k * c + j] : 0.0f;
+    const int r = r0 + k;
+    vs[k][j] = (r < d && j < c) ? jb.v[(size_t)r * c + j] : 0.0f;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4] = {};
+  for (int k = 0; k < c; ++k) {
+    float a[4], b[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      a[q] = vs[ty + 16 * q][k];
+      b[q] = gs[k][tx + 16 * q];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[q][r] = fmaf(a[q], b[r], acc[q][r]);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int r = r0 + ty + 16 * q;
+    if (r >= d) continue;
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const int col = tx + 16 * rr;
+      if (col < c) jb.w[(size_t)r * c + col] = acc[q][rr];
+    }
+  }
+}
+
+// U[r, c] = scale * sum_k Ainv[r, k] W[k, c];  grid (ceil(d / 64), 1, jobs), 256 threads, k in chunks of 32
+__global__ void __launch_bounds__(256) precon_aw_kernel(const PreconJob* __restrict__ jobs) {
+  const PreconJob jb = jobs[blockIdx.z];
+  const int d = jb.d, c = jb.c;
+  const int r0 = blockIdx.x * 64;
+  if (r0 >= d) return;
+  __shared__ float as[64][33];
+  __shared__ float ws[32][65];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < d; k0 += 32) {
+    for (int i = threadIdx.x; i < 64 * 32; i += 256) {
+      const int r = i >> 5, k = i & 31;
+      as[r][k] = (r0 + r < d && k0 + k < d) ? jb.ainv[(size_t)(r0 + r) * d + k0 + k] : 0.0f;
+    }
+    for (int i = threadIdx.x; i < 32 * 64; i += 256) {
+      const int k = i >> 6, j = i & 63;
+      ws[k][j] = (k0 + k < d && j < c) ? jb.w[(size_t)(k0 + k) * c + j] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        a[q] = as[ty + 16 * q][k];
+        b[q] = ws[k][tx + 16 * q];
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[q][r] = fmaf(a[q], b[r], acc[q][r]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int r = r0 + ty + 16 * q;
+    if (r >= d) continue;
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const int col = tx + 16 * rr;
+      if (col < c) jb.u[(size_t)r * c + col] = acc[q][rr] * jb.scale;
+    }
+  }
+}
+
 // schedule state (one thread)
 __global__ void sched_begin_kernel(Sched* s, float lr_start, float lr_end, double decay_steps, float* out_lr) {
   // nn.py:154-156 linear_decay = polynomial_decay(power 1, cycle False), evaluated at the step the update starts with
@@ -456,6 +575,8 @@ int spd_inverse_batched(const InvJob* h_jobs, const InvJob* d_jobs, int num_jobs
     inv_prepare_kernel<<<grid, 256, 0, st>>>(dj, sched, d_damp);
     ACX_LAUNCH_CHECK();
   }
+  inv_diag0_kernel<<<dim3(1, 1, num_jobs), 256, 0, st>>>(dj);
+  ACX_LAUNCH_CHECK();
   const int steps = ceil_div(nmax, IB);
   for (int p = 0; p < steps; ++p) {
     // jobs are sorted by decreasing n by the caller, so the jobs still active at step p are a prefix
@@ -467,13 +588,12 @@ int spd_inverse_batched(const InvJob* h_jobs, const InvJob* d_jobs, int num_jobs
         nact = h_jobs[i].n > nact ? h_jobs[i].n : nact;
       }
     if (active == 0) break;
-    inv_rowpanel_kernel<<<dim3(ceil_div(nact, IB), 1, active), 1024, 0, st>>>(dj, p);
-    ACX_LAUNCH_CHECK();
-    if (nact > IB) {
-      inv_update_kernel<<<dim3(ceil_div(nact, 64), ceil_div(nact, 64), active), 256, 0, st>>>(dj, p);
+    const int nblk = ceil_div(nact, IB);
+    if (nblk > 1) {
+      inv_panels_kernel<<<dim3(2 * nblk, 1, active), 1024, 0, st>>>(dj, p, nblk);
       ACX_LAUNCH_CHECK();
     }
-    inv_colpanel_kernel<<<dim3(ceil_div(nact, IB), 1, active), 1024, 0, st>>>(dj, p);
+    inv_update_kernel<<<dim3(ceil_div(nact, 64), ceil_div(nact, 64), active), 256, 0, st>>>(dj, p);
     ACX_LAUNCH_CHECK();
   }
   {
@@ -481,6 +601,16 @@ int spd_inverse_batched(const InvJob* h_jobs, const InvJob* d_jobs, int num_jobs
     inv_finish_kernel<<<grid, 256, 0, st>>>(dj);
     ACX_LAUNCH_CHECK();
   }
+  return 0;
+}
+
+int precondition_small(const PreconJob* d_jobs, int num_jobs, int max_d, cudaStream_t st) {
+  if (num_jobs == 0) return 0;
+  dim3 grid(ceil_div(max_d, 64), 1, num_jobs);
+  precon_vg_kernel<<<grid, 256, 0, st>>>(d_jobs);
+  ACX_LAUNCH_CHECK();
+  precon_aw_kernel<<<grid, 256, 0, st>>>(d_jobs);
+  ACX_LAUNCH_CHECK();
   return 0;
 }
 

@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(256) heads_gfactor_kernel(const float* __restr
 // stage 2: sums the chunks (8 chunk lanes per column) and scales.
 // ------------------------------------------------------------------------------------------------
 constexpr int CS_THREADS = 256;
-constexpr int CS_MAXV = 2;   // vector columns per thread when cols / 8 > 256  (cols <= 4096)
+constexpr int CS_COLBLOCK = CS_THREADS * 8;   // columns per CTA (one 8-column vector per thread)
 
 __device__ __forceinline__ void add8(float* acc, const uint4 q) {
   const uint32_t w[4] = {q.x, q.y, q.z, q.w};
@@ -355,49 +355,77 @@ __device__ __forceinline__ void add8(float* acc, const uint4 q) {
   }
 }
 
+// grid (row chunks, column blocks of 2048)
 __global__ void __launch_bounds__(CS_THREADS) colsum_stage1_kernel(const Planes x, int rows, int cols, int rows_per_chunk,
                                                                    float* __restrict__ partial) {
-  extern __shared__ float cs_smem[];   // [lanes_r][cols]
-  const int nv = cols >> 3;
+  extern __shared__ float cs_smem[];   // [lanes_r][cb]
+  const int col0 = blockIdx.y * CS_COLBLOCK;
+  const int cb = min(CS_COLBLOCK, cols - col0);
+  const int nv = cb >> 3;
   const int lanes_r = nv >= CS_THREADS ? 1 : CS_THREADS / nv;
   const int row_lane = nv >= CS_THREADS ? 0 : threadIdx.x / nv;
-  const int v0 = nv >= CS_THREADS ? threadIdx.x : threadIdx.x % nv;
-  const bool active = row_lane < lanes_r;
+  const int v = nv >= CS_THREADS ? threadIdx.x : threadIdx.x % nv;
+  const bool active = row_lane < lanes_r && v < nv;
   const int r0 = blockIdx.x * rows_per_chunk;
   const int r1 = min(rows, r0 + rows_per_chunk);
-  float acc[CS_MAXV][8];
+  float acc[8];
 #pragma unroll
-  for (int q = 0; q < CS_MAXV; ++q)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[q][i] = 0.f;
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   if (active) {
     for (int r = r0 + row_lane; r < r1; r += lanes_r) {
-#pragma unroll
-      for (int q = 0; q < CS_MAXV; ++q) {
-        const int v = v0 + q * CS_THREADS;
-        if (v < nv) {
-          const size_t idx = (size_t)r * x.ld + (size_t)v * 8;
-          add8(acc[q], __ldg(reinterpret_cast<const uint4*>(x.p[0] + idx)));
-          if (x.n > 1) add8(acc[q], __ldg(reinterpret_cast<const uint4*>(x.p[1] + idx)));
-          if (x.n > 2) add8(acc[q], __ldg(reinterpret_cast<const uint4*>(x.p[2] + idx)));
-        }
-      }
+      const size_t idx = (size_t)r * x.ld + col0 + (size_t)v * 8;
+      add8(acc, __ldg(reinterpret_cast<const uint4*>(x.p[0] + idx)));
+      if (x.n > 1) add8(acc, __ldg(reinterpret_cast<const uint4*>(x.p[1] + idx)));
+      if (x.n > 2) add8(acc, __ldg(reinterpret_cast<const uint4*>(x.p[2] + idx)));
     }
 #pragma unroll
-    for (int q = 0; q < CS_MAXV; ++q) {
-      const int v = v0 + q * CS_THREADS;
-      if (v < nv)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) cs_smem[(size_t)row_lane * cols + v * 8 + i] = acc[q][i];
-    }
+    for (int i = 0; i < 8; ++i) cs_smem[(size_t)row_lane * cb + v * 8 + i] = acc[i];
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < cols; c += CS_THREADS) {
+  for (int c = threadIdx.x; c < cb; c += CS_THREADS) {
     float t = 0.f;
-    for (int l = 0; l < lanes_r; ++l) t += cs_smem[(size_t)l * cols + c];
-    partial[(size_t)blockIdx.x * cols + c] = t;
+    for (int l = 0; l < lanes_r; ++l) t += cs_smem[(size_t)l * cb + c];
+    partial[(size_t)blockIdx.x * cols + col0 + c] = t;
   }
 }
+
+// uint8 [rows, cols] -> per-chunk column sums (exact in uint32, stored as fp32: sums stay below 2^24 for <= 65793 rows
+// per chunk); one 16-byte vector per thread.  grid (row chunks, ceil(cols / 4096))
+__global__ void __launch_bounds__(256) colsum_u8_kernel(const uint8_t* __restrict__ x, int rows, int cols, int rows_per_chunk,
+                                                        float* __restrict__ partial) {
+  const int c0 = (blockIdx.y * 256 + threadIdx.x) * 16;
+  if (c0 >= cols) return;
+  const int r0 = blockIdx.x * rows_per_chunk;
+  const int r1 = min(rows, r0 + rows_per_chunk);
+  uint32_t acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0u;
+  for (int r = r0; r < r1; ++r) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(x + (size_t)r * cols + c0));
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[4 * i + b] += (w[i] >> (8 * b)) & 0xffu;
+  }
+  float* dst = partial + (size_t)blockIdx.x * cols + c0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) dst[i] = (float)acc[i];
+}
+
+// border of a conv input factor from the batch-summed input S [hw_in, hw_in, c]:
+//   out[(ky*k + kx)*c + ch] = scale * sum_{oy,ox} S[(oy*s + ky), (ox*s + kx), ch]      (= P^T 1 without touching P)
+__global__ void window_sum_kernel(const float* __restrict__ sum_in, int hw_in, int c, int k, int s, int hw_out, float scale,
+                                  float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= k * k * c) return;
+  const int ch = i % c, kx = (i / c) % k, ky = i / (c * k);
+  float acc = 0.f;
+  for (int oy = 0; oy < hw_out; ++oy)
+    for (int ox = 0; ox < hw_out; ++ox) acc += sum_in[((size_t)(oy * s + ky) * hw_in + ox * s + kx) * c + ch];
+  out[i] = acc * scale;
+}
+
 __global__ void __launch_bounds__(256) colsum_stage2_kernel(const float* __restrict__ partial, int chunks, int cols, float scale,
                                                             float* __restrict__ out, int out_stride) {
   __shared__ float red[8][33];
@@ -532,26 +560,53 @@ int heads_gfactor(const float* dheads_fisher, int n_rows, int num_actions, float
 }
 int colsum(const Planes& x, int rows, int cols, float scale, float* partial, int max_chunks, float* out, int out_stride,
            cudaStream_t st) {
-  ACX_CHECK((cols & 7) == 0 && (x.ld & 7) == 0 && cols <= 8 * CS_THREADS * CS_MAXV, "colsum: cols must be a multiple of 8, <= 4096");
-  const int nv = cols >> 3;
+  ACX_CHECK((cols & 7) == 0 && (x.ld & 7) == 0, "colsum: cols and ld must be multiples of 8");
+  const int cb = cols < CS_COLBLOCK ? cols : CS_COLBLOCK;
+  const int nv = cb >> 3;
   const int lanes_r = nv >= CS_THREADS ? 1 : CS_THREADS / nv;
   int chunks = ceil_div(rows, lanes_r * 4);          // at least ~4 rows per lane
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
   const int rpc = ceil_div(rows, chunks);
   chunks = ceil_div(rows, rpc);
-  const size_t smem = (size_t)lanes_r * cols * sizeof(float);
+  const size_t smem = (size_t)lanes_r * cb * sizeof(float);
   static bool configured = false;
   if (!configured) {
     ACX_CUDA(cudaFuncSetAttribute(colsum_stage1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     configured = true;
   }
-  colsum_stage1_kernel<<<chunks, CS_THREADS, smem, st>>>(x, rows, cols, rpc, partial);
+  colsum_stage1_kernel<<<dim3(chunks, ceil_div(cols, CS_COLBLOCK)), CS_THREADS, smem, st>>>(x, rows, cols, rpc, partial);
   ACX_LAUNCH_CHECK();
   colsum_stage2_kernel<<<ceil_div(cols, 32), dim3(32, 8), 0, st>>>(partial, chunks, cols, scale, out, out_stride);
   ACX_LAUNCH_CHECK();
   return 0;
 }
+
+// batch sum of the conv input (uint8 observations or bf16-plane activations), then the window sums = border of A_l
+int conv_border(const uint8_t* obs_u8, const Planes* act, int n_rows, int hw_in, int c, int k, int s, int hw_out, float scale,
+                float* partial, int max_chunks, float* sum_tmp, float* out, cudaStream_t st) {
+  const int cols = hw_in * hw_in * c;
+  if (obs_u8) {
+    ACX_CHECK((cols & 15) == 0, "conv_border: cols must be a multiple of 16");
+    int chunks = ceil_div(n_rows, 16);
+    if (chunks > max_chunks) chunks = max_chunks;
+    const int rpc = ceil_div(n_rows, chunks);
+    chunks = ceil_div(n_rows, rpc);
+    colsum_u8_kernel<<<dim3(chunks, ceil_div(cols, 4096)), 256, 0, st>>>(obs_u8, n_rows, cols, rpc, partial);
+    ACX_LAUNCH_CHECK();
+    colsum_stage2_kernel<<<ceil_div(cols, 32), dim3(32, 8), 0, st>>>(partial, chunks, cols, 1.0f, sum_tmp, 1);
+    ACX_LAUNCH_CHECK();
+  } else {
+    Planes v = *act;
+    v.ld = cols;
+    int r = colsum(v, n_rows, cols, 1.0f, partial, max_chunks, sum_tmp, 1, st);
+    if (r) return r;
+  }
+  window_sum_kernel<<<ceil_div(k * k * c, 128), 128, 0, st>>>(sum_tmp, hw_in, c, k, s, hw_out, scale, out);
+  ACX_LAUNCH_CHECK();
+  return 0;
+}
+
 int transpose_split(const float* in, int k_rows, int c_cols, bf16* p0, bf16* p1, bf16* p2, int num_planes, int ld_out,
                     cudaStream_t st) {
   dim3 grid(ceil_div(ld_out, 32), ceil_div(c_cols, 32));

@@ -38,6 +38,8 @@ int heads_bwd(const float* dheads, const float* vpol, const float* vval, const P
 int heads_gfactor(const float* dheads_fisher, int n_rows, int num_actions, float* g_pol, float* g_val, cudaStream_t st);
 int colsum(const Planes& x, int rows, int cols, float scale, float* partial, int max_chunks, float* out, int out_stride,
            cudaStream_t st);
+int conv_border(const uint8_t* obs_u8, const Planes* act, int n_rows, int hw_in, int c, int k, int s, int hw_out, float scale,
+                float* partial, int max_chunks, float* sum_tmp, float* out, cudaStream_t st);
 int transpose_split(const float* in, int k_rows, int c_cols, bf16* p0, bf16* p1, bf16* p2, int num_planes, int ld_out,
                     cudaStream_t st);
 int sample_actions(const float* logits, const float* uniform, uint64_t seed, uint64_t step, int rows, int num_actions, int greedy,
@@ -51,11 +53,21 @@ struct InvJob {          // one SPD inverse: M = debias * S + damp * I  (fp64) -
   int n;
   int damp_index;        // index into the device damping array
   double* work_m;        // [n, n] fp64 scratch (inverted in place)
-  double* work_x;        // [32, n] row panel + [32, 32] pivot-block inverse
+  double* work_x;        // R [32, n] | old column panel [n, 32] | new column panel [n, 32] | pivot-block inverse [32, 32]
   float* inv;            // [n, n] fp32 result
   bf16* planes[3];       // [n, ld_planes]
   int ld_planes;
 };
+struct PreconJob {       // one small block: U = A^-1 (V G^-1) * scale, all fp32, C <= 64
+  const float* v;        // [d, c] gradient block (weight rows + bias row)
+  const float* ginv;     // [c, c]
+  const float* ainv;     // [d, d]
+  float* w;              // [d, c] scratch
+  float* u;              // [d, c] preconditioned block
+  int d, c;
+  float scale;           // 1 / T~_l
+};
+int precondition_small(const PreconJob* d_jobs, int num_jobs, int max_d, cudaStream_t st);
 int homog_border(float* a, int d, const float* colsum_scaled, cudaStream_t st);
 int ema_update(float* s, const float* c, size_t count, float decay, float scale_c, cudaStream_t st);
 int compute_dampings(const float* const* d_a_ptrs, const float* const* d_g_ptrs, const int* d_a_dims, const int* d_g_dims,

@@ -90,6 +90,10 @@ struct acx_learner {
   int *d_a_dims, *d_g_dims;
   InvJob h_jobs[12];
   InvJob* d_jobs;
+  PreconJob h_pjobs[6];
+  PreconJob* d_pjobs;
+  int num_pjobs, pjobs_max_d;
+  float* precon_w;
   // inputs
   uint8_t *obs, *actions, *terminals;
   float* rewards;
@@ -118,6 +122,7 @@ struct acx_learner {
 namespace acx {
 
 static const int kColsumChunks = 592;
+static const int kBorderChunks = 64;
 static const int kDotPartials = 64;
 
 static int pad8(int x) { return (x + 7) / 8 * 8; }
@@ -221,6 +226,8 @@ static size_t layout(acx_learner* l, uint8_t* base) {
   l->d_a_dims = reinterpret_cast<int*>(ar.take(6 * sizeof(int)));
   l->d_g_dims = reinterpret_cast<int*>(ar.take(6 * sizeof(int)));
   l->d_jobs = reinterpret_cast<InvJob*>(ar.take(12 * sizeof(InvJob)));
+  l->d_pjobs = reinterpret_cast<PreconJob*>(ar.take(6 * sizeof(PreconJob)));
+  l->precon_w = f32(P);
   for (int i = 0; i < 6; ++i) {
     const int d = l->L[i].K + 1, c = l->L[i].C;
     l->ainv_pl[i] = take_planes(ar, 3, d, pad8(d));
@@ -234,7 +241,7 @@ static size_t layout(acx_learner* l, uint8_t* base) {
     ja.n = d;
     ja.damp_index = 2 * i;
     ja.work_m = reinterpret_cast<double*>(ar.take((size_t)d * d * sizeof(double)));
-    ja.work_x = reinterpret_cast<double*>(ar.take(((size_t)32 * d + 32 * 32) * sizeof(double)));
+    ja.work_x = reinterpret_cast<double*>(ar.take(((size_t)3 * 32 * d + 2 * 32 * 32) * sizeof(double)));
     ja.inv = l->inv + l->ainv_off[i];
     for (int q = 0; q < 3; ++q) ja.planes[q] = l->ainv_pl[i].p[q];
     ja.ld_planes = l->ainv_pl[i].ld;
@@ -243,10 +250,26 @@ static size_t layout(acx_learner* l, uint8_t* base) {
     jg.n = c;
     jg.damp_index = 2 * i + 1;
     jg.work_m = reinterpret_cast<double*>(ar.take((size_t)c * c * sizeof(double)));
-    jg.work_x = reinterpret_cast<double*>(ar.take(((size_t)32 * c + 32 * 32) * sizeof(double)));
+    jg.work_x = reinterpret_cast<double*>(ar.take(((size_t)3 * 32 * c + 2 * 32 * 32) * sizeof(double)));
     jg.inv = l->inv + l->ginv_off[i];
     for (int q = 0; q < 3; ++q) jg.planes[q] = l->ginv_pl[i].p[q];
     jg.ld_planes = l->ginv_pl[i].ld;
+  }
+  // small blocks (C <= 64) are preconditioned by the batched fp32 SIMT kernels
+  l->num_pjobs = 0;
+  l->pjobs_max_d = 0;
+  for (int i = 0; i < 6; ++i) {
+    if (l->L[i].C > 64) continue;
+    PreconJob& pj = l->h_pjobs[l->num_pjobs++];
+    pj.v = l->grads + l->L[i].off;
+    pj.ginv = l->inv + l->ginv_off[i];
+    pj.ainv = l->inv + l->ainv_off[i];
+    pj.w = l->precon_w + l->L[i].off;
+    pj.u = l->precon + l->L[i].off;
+    pj.d = l->L[i].K + 1;
+    pj.c = l->L[i].C;
+    pj.scale = 1.0f / (float)l->L[i].Tnorm;
+    l->pjobs_max_d = std::max(l->pjobs_max_d, pj.d);
   }
   // ---- inputs
   l->obs = reinterpret_cast<uint8_t*>(ar.take((size_t)R * 28224));
@@ -285,8 +308,8 @@ static size_t layout(acx_learner* l, uint8_t* base) {
   }
   l->Vp = take_planes(ar, 3, dmax, pad8(cmax));
   l->Wt = take_planes(ar, 3, cmax, pad8(dmax));
-  l->colsum_partial = f32((size_t)kColsumChunks * (size_t)std::max(49 * c3, 576));
-  l->colsum_tmp = f32(std::max(49 * c3, 576) + 8);
+  l->colsum_partial = f32(std::max((size_t)kColsumChunks * (size_t)std::max(49 * c3, 576), (size_t)kBorderChunks * 28224));
+  l->colsum_tmp = f32(4096 + 28224 + 8);   // [0,4096): border / column-sum vectors, then the batch-summed conv input
   l->dot_partials = f32(kDotPartials);
   const size_t kpad = align_up((size_t)49 * c3, 128);
   l->ws_bytes = std::max<size_t>((size_t)48 << 20, kpad * kpad * sizeof(float) + (1 << 20));
@@ -463,6 +486,23 @@ static int input_factor(acx_learner* l, int fac, const Planes& x, int rows, int 
   return 0;
 }
 
+// input factor of a conv layer: SYRK over the patch matrix; the homogeneous border P^T 1 / rows comes from the batch-summed
+// layer input through window sums (one pass over the un-im2col'd input instead of a pass over the k^2/s^2 times larger P)
+static int conv_input_factor(acx_learner* l, int li, const Planes& patches, const uint8_t* obs_u8, const Planes* act_in,
+                             float scale_sq, float border_scale, cudaStream_t st) {
+  const Layer& L = l->L[li];
+  const int d = L.K + 1, rows = l->N * L.T;
+  float* dst = l->stats + l->aoff[li];
+  GemmOut o;
+  o.c = dst;
+  o.ldc = d;
+  ACX_TRY(run_gemm(l, patches, patches, 1, L.K, L.K, rows, l->lvl_factor, scale_sq, 1, o, st));
+  ACX_TRY(conv_border(obs_u8, act_in, l->N, L.hw_in, L.cin, L.k, L.s, L.hw_out, border_scale, l->colsum_partial, kBorderChunks,
+                      l->colsum_tmp + 4096, l->colsum_tmp, st));
+  ACX_TRY(homog_border(dst, d, l->colsum_tmp, st));
+  return 0;
+}
+
 // weight gradient V_l[:K] = X^T g over the true-loss rows, bias row = column sums of g
 static int weight_grad(acx_learner* l, int li, const Planes& x, const Planes& g, int rows, float alpha, cudaStream_t st) {
   const Layer& L = l->L[li];
@@ -539,9 +579,9 @@ static int issue_phase1(acx_learner* l, const int32_t* fisher_labels, const floa
     ACX_TRY(output_factor(l, 1, offset_rows(l->dpre2, (size_t)N * 81), N * 81, st));
     ACX_TRY(output_factor(l, 0, offset_rows(l->dpre1, (size_t)N * 400), N * 400, st));
     const float r1 = 1.0f / (float)(N * 400), r2 = 1.0f / (float)(N * 81), r3 = 1.0f / (float)(N * 49), r4 = 1.0f / (float)N;
-    ACX_TRY(input_factor(l, 0, l->P1, N * 400, 256, r1 / (255.0f * 255.0f), r1 / 255.0f, st));
-    ACX_TRY(input_factor(l, 1, l->P2, N * 81, 512, r2, r2, st));
-    ACX_TRY(input_factor(l, 2, l->P3, N * 49, 576, r3, r3, st));
+    ACX_TRY(conv_input_factor(l, 0, l->P1, l->obs, nullptr, r1 / (255.0f * 255.0f), r1 / 255.0f, st));
+    ACX_TRY(conv_input_factor(l, 1, l->P2, nullptr, &l->act1, r2, r2, st));
+    ACX_TRY(conv_input_factor(l, 2, l->P3, nullptr, &l->act2, r3, r3, st));
     ACX_TRY(input_factor(l, 3, flat3, N, 49 * c3, r4, r4, st));
     ACX_TRY(input_factor(l, 4, l->act4, N, 512, r4, r4, st));
   }
@@ -550,9 +590,11 @@ static int issue_phase1(acx_learner* l, const int32_t* fisher_labels, const floa
 }
 
 static int precondition(acx_learner* l, cudaStream_t st) {
+  ACX_TRY(precondition_small(l->d_pjobs, l->num_pjobs, l->pjobs_max_d, st));
   for (int i = 0; i < 6; ++i) {
     const Layer& L = l->L[i];
     const int d = L.K + 1, C = L.C;
+    if (C <= 64) continue;   // done above
     Planes vp = l->Vp;
     vp.ld = pad8(C);
     Planes wt = l->Wt;
@@ -786,6 +828,7 @@ acx_learner_t* acx_learner_create(const acx_learner_config_t* cfg, void* d_arena
   cudaMemcpy(l->d_g_dims, gd, sizeof(gd), cudaMemcpyHostToDevice);
   cudaMemcpy(l->lambdas, lam, sizeof(lam), cudaMemcpyHostToDevice);
   std::stable_sort(l->h_jobs, l->h_jobs + 12, [](const InvJob& a, const InvJob& b) { return a.n > b.n; });
+  cudaMemcpy(l->d_pjobs, l->h_pjobs, sizeof(l->h_pjobs), cudaMemcpyHostToDevice);
   e = cudaMemcpy(l->d_jobs, l->h_jobs, sizeof(l->h_jobs), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     acx::set_error(std::string("acx_learner_create: cudaMemcpy: ") + cudaGetErrorString(e));

@@ -311,6 +311,53 @@ class Engine:
             self.rewards.copy_(as_t(rewards, torch.float32), non_blocking=non_blocking)
             self.terminals.copy_(as_t(terminals, torch.uint8), non_blocking=non_blocking)
 
+    # --- double-buffered host feed: the H2D copy of the next batch overlaps the current update ---------------
+    def _ensure_staging(self):
+        if getattr(self, "_staging", None) is not None:
+            return
+        n, e, t = self.rows, self.num_envs, self.num_steps
+        mk = lambda shape, dt: torch.empty(shape, dtype=dt, device=self.device)     # noqa: E731
+        self._staging = [dict(observations=mk((e, t) + OBS_SHAPE, torch.uint8), bootstrap_observations=mk((e,) + OBS_SHAPE, torch.uint8),
+                              actions=mk((e, t), torch.uint8), rewards=mk((e, t), torch.float32), terminals=mk((e, t), torch.uint8))
+                         for _ in range(2)]
+        self._copy_stream = torch.cuda.Stream(self.device)
+        self._ready = [torch.cuda.Event() for _ in range(2)]
+        self._free = [torch.cuda.Event() for _ in range(2)]
+        self._stage_put = 0
+        self._stage_get = 0
+        del n
+
+    def stage_batch(self, batch):
+        """Start the asynchronous host-to-device copy of a batch (pinned host tensors) into one of two staging slots on
+        a dedicated copy stream; `update(staged=True)` consumes the slots in order.  At most two batches in flight."""
+        self._ensure_staging()
+        k = self._stage_put % 2
+        slot = self._staging[k]
+        with torch.cuda.stream(self._copy_stream):
+            if self._stage_put >= 2:
+                self._copy_stream.wait_event(self._free[k])
+            for name, dst in slot.items():
+                src = batch[name]
+                if not isinstance(src, torch.Tensor):
+                    src = torch.from_numpy(np.ascontiguousarray(src))
+                if src.dtype == torch.bool:
+                    src = src.to(torch.uint8)
+                dst.copy_(src, non_blocking=True)
+            self._ready[k].record(self._copy_stream)
+        self._stage_put += 1
+
+    def _consume_staged(self):
+        if getattr(self, "_staging", None) is None or self._stage_get >= self._stage_put:
+            raise _lib.AcxError("update(staged=True) without a staged batch (call stage_batch first)")
+        k = self._stage_get % 2
+        slot = self._staging[k]
+        with self.on_stream():
+            self.stream.wait_event(self._ready[k])
+            self.load_batch(slot["observations"], slot["bootstrap_observations"], slot["actions"], slot["rewards"],
+                            slot["terminals"])
+            self._free[k].record(self.stream)
+        self._stage_get += 1
+
     def phase1(self, fisher_labels=None, fisher_eps=None):
         fl = ctypes.c_void_p(fisher_labels.data_ptr()) if fisher_labels is not None else None
         fe = ctypes.c_void_p(fisher_eps.data_ptr()) if fisher_eps is not None else None
@@ -327,9 +374,11 @@ class Engine:
         with self.on_stream():
             _lib.check(self.lib.acx_learner_phase2(self._h, self._stream()))
 
-    def update(self, batch=None, fisher_labels=None, fisher_eps=None, fetch=True, group=None):
+    def update(self, batch=None, fisher_labels=None, fisher_eps=None, fetch=True, group=None, staged=False):
         """The reference's `session.run([..., optimize_op], feed_dict)` (a2c_acktr.py:117-126)."""
-        if batch is not None:
+        if staged:
+            self._consume_staged()
+        elif batch is not None:
             self.load_batch(batch["observations"], batch["bootstrap_observations"], batch["actions"], batch["rewards"],
                             batch["terminals"])
         self.phase1(fisher_labels, fisher_eps)
