@@ -326,6 +326,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
     const uint32_t lbo = MAJOR == 0 ? 16u : p.mn_lbo;
     const uint32_t sbo = MAJOR == 0 ? 1024u : p.mn_sbo;
     const uint32_t kstep = MAJOR == 0 ? 32u : p.mn_kstep;
+    const uint64_t kstep16 = (uint64_t)(kstep >> 4);
     int it = 0, lt = 0;
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++lt) {
       int tm, tn, split;
@@ -347,13 +348,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
           const int ksteps = (kvalid + 15) >> 4;
           const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
           const uint32_t b_addr = a_addr + (uint32_t)(p.npa * A_TILE_BYTES);
+          // the descriptor of a tile advanced by `off` bytes is base + (off >> 4): only the 14-bit address field moves
+          // (tiles are 1024-byte aligned inside the < 256 KB shared window, so the add never carries out of the field)
+          const uint64_t a_desc0 = make_smem_desc(a_addr, lbo, sbo);
+          const uint64_t b_desc0 = make_smem_desc(b_addr, lbo, sbo);
+          uint32_t acc_flag = kb > kb0 ? 1u : 0u;
           for (int pr = 0; pr < p.num_pairs; ++pr) {
-            const uint32_t aa = a_addr + (uint32_t)(p.pair_a[pr] * A_TILE_BYTES);
-            const uint32_t bb = b_addr + (uint32_t)(p.pair_b[pr] * b_tile_bytes);
+            uint64_t ad = a_desc0 + (uint64_t)((uint32_t)(p.pair_a[pr] * A_TILE_BYTES) >> 4);
+            uint64_t bd = b_desc0 + (uint64_t)((uint32_t)(p.pair_b[pr] * b_tile_bytes) >> 4);
             for (int kk = 0; kk < ksteps; ++kk) {
-              const uint64_t ad = make_smem_desc(aa + kk * kstep, lbo, sbo);
-              const uint64_t bd = make_smem_desc(bb + kk * kstep, lbo, sbo);
-              umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || pr > 0 || kk > 0) ? 1u : 0u);
+              umma_bf16(d_tmem, ad, bd, idesc, acc_flag);
+              acc_flag = 1u;
+              ad += kstep16;
+              bd += kstep16;
             }
           }
           umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
@@ -731,7 +738,7 @@ struct TcPlan {
 };
 
 static int pick_bn(const acx_gemm_t* g) {
-  if (g->symmetric) return 128;
+  if (g->symmetric) return g->n <= 64 ? 64 : 128;   // one tile (0,0) when n <= 64; otherwise square 128-tiles
   if (g->trans_a) return g->n <= 64 ? 64 : 128;
   if (g->n <= 32) return 32;
   if (g->n <= 64) return 64;

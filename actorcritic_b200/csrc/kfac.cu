@@ -447,49 +447,41 @@ __global__ void __launch_bounds__(256) precon_vg_kernel(const PreconJob* __restr
   }
 }
 
-// U[r, c] = scale * sum_k Ainv[r, k] W[k, c];  grid (ceil(d / 64), 1, jobs), 256 threads, k in chunks of 32
+// U[r, c] = scale * sum_k Ainv[r, k] W[k, c];  grid (ceil(d / 16), 1, jobs), 256 threads = 16 rows x 16 column lanes
+// (4 columns each), k in chunks of 64
 __global__ void __launch_bounds__(256) precon_aw_kernel(const PreconJob* __restrict__ jobs) {
   const PreconJob jb = jobs[blockIdx.z];
   const int d = jb.d, c = jb.c;
-  const int r0 = blockIdx.x * 64;
+  const int r0 = blockIdx.x * 16;
   if (r0 >= d) return;
-  __shared__ float as[64][33];
-  __shared__ float ws[32][65];
+  __shared__ float as[16][65];
+  __shared__ float ws[64][65];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  float acc[4][4] = {};
-  for (int k0 = 0; k0 < d; k0 += 32) {
-    for (int i = threadIdx.x; i < 64 * 32; i += 256) {
-      const int r = i >> 5, k = i & 31;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k0 = 0; k0 < d; k0 += 64) {
+    for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+      const int r = i >> 6, k = i & 63;
       as[r][k] = (r0 + r < d && k0 + k < d) ? jb.ainv[(size_t)(r0 + r) * d + k0 + k] : 0.0f;
     }
-    for (int i = threadIdx.x; i < 32 * 64; i += 256) {
+    for (int i = threadIdx.x; i < 64 * 64; i += 256) {
       const int k = i >> 6, j = i & 63;
       ws[k][j] = (k0 + k < d && j < c) ? jb.w[(size_t)(k0 + k) * c + j] : 0.0f;
     }
     __syncthreads();
 #pragma unroll 8
-    for (int k = 0; k < 32; ++k) {
-      float a[4], b[4];
+    for (int k = 0; k < 64; ++k) {
+      const float a = as[ty][k];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        a[q] = as[ty + 16 * q][k];
-        b[q] = ws[k][tx + 16 * q];
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-#pragma unroll
-        for (int r = 0; r < 4; ++r) acc[q][r] = fmaf(a[q], b[r], acc[q][r]);
+      for (int q = 0; q < 4; ++q) acc[q] = fmaf(a, ws[k][tx + 16 * q], acc[q]);
     }
     __syncthreads();
   }
+  const int r = r0 + ty;
+  if (r < d) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int r = r0 + ty + 16 * q;
-    if (r >= d) continue;
-#pragma unroll
-    for (int rr = 0; rr < 4; ++rr) {
-      const int col = tx + 16 * rr;
-      if (col < c) jb.u[(size_t)r * c + col] = acc[q][rr] * jb.scale;
+    for (int q = 0; q < 4; ++q) {
+      const int col = tx + 16 * q;
+      if (col < c) jb.u[(size_t)r * c + col] = acc[q] * jb.scale;
     }
   }
 }
@@ -609,7 +601,7 @@ int precondition_small(const PreconJob* d_jobs, int num_jobs, int max_d, cudaStr
   dim3 grid(ceil_div(max_d, 64), 1, num_jobs);
   precon_vg_kernel<<<grid, 256, 0, st>>>(d_jobs);
   ACX_LAUNCH_CHECK();
-  precon_aw_kernel<<<grid, 256, 0, st>>>(d_jobs);
+  precon_aw_kernel<<<dim3(ceil_div(max_d, 16), 1, num_jobs), 256, 0, st>>>(d_jobs);
   ACX_LAUNCH_CHECK();
   return 0;
 }

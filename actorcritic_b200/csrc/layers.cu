@@ -33,24 +33,34 @@ __global__ void im2col_conv1_kernel(const uint8_t* __restrict__ obs, bf16* __res
 }
 
 // generic NHWC bf16 im2col, patch order (ky, kx, c): each (row, ky) segment is k*C contiguous elements.
-// grid.y = plane.
-__global__ void im2col_bf16_kernel(const Planes pin, const Planes pout, int rows_total, int hw_in, int c, int k, int s,
-                                   int hw_out) {
-  const bf16* __restrict__ in = pin.p[blockIdx.y];
-  bf16* __restrict__ out = pout.p[blockIdx.y];
-  const int seg_vec = k * c / 8;               // uint4 per (row, ky) segment
-  const long long total = (long long)rows_total * k * seg_vec;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int v = (int)(i % seg_vec);
-  const long long t = i / seg_vec;
-  const int ky = (int)(t % k);
-  const int row = (int)(t / k);
+// One warp per patch row (grid-stride): the row decode is warp-uniform, lanes own 16-byte vectors, every plane is
+// copied by the same thread (the index math is shared), reads are k*C*2-byte runs, writes are whole contiguous rows.
+__global__ void __launch_bounds__(256) im2col_bf16_kernel(const Planes pin, const Planes pout, int rows_total, int hw_in, int c,
+                                                          int k, int s, int hw_out) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int seg_vec = k * c / 8;        // uint4 per (row, ky) segment
+  const int row_vec = k * seg_vec;      // uint4 per patch row
   const int per = hw_out * hw_out;
-  const int n = row / per, loc = row % per, oy = loc / hw_out, ox = loc % hw_out;
-  const uint4* src = reinterpret_cast<const uint4*>(in + ((size_t)(n * hw_in + oy * s + ky) * hw_in + ox * s) * c) + v;
-  uint4* dst = reinterpret_cast<uint4*>(out + (size_t)row * (k * k * c) + ky * (k * c)) + v;
-  *dst = __ldg(src);
+  const int np = pin.n < pout.n ? pin.n : pout.n;
+  for (int row = warp; row < rows_total; row += nwarps) {
+    const int n = row / per, loc = row - n * per, oy = loc / hw_out, ox = loc - oy * hw_out;
+    const size_t src_base = ((size_t)(n * hw_in + oy * s) * hw_in + ox * s) * c;
+    const size_t dst_base = (size_t)row * (k * k * c);
+    for (int v = lane; v < row_vec; v += 32) {
+      const int ky = v / seg_vec, off = v - ky * seg_vec;
+      const size_t src = src_base + (size_t)ky * hw_in * c + (size_t)off * 8;
+      const size_t dst = dst_base + (size_t)v * 8;
+      const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(pin.p[0] + src));
+      uint4 q1, q2;
+      if (np > 1) q1 = __ldg(reinterpret_cast<const uint4*>(pin.p[1] + src));
+      if (np > 2) q2 = __ldg(reinterpret_cast<const uint4*>(pin.p[2] + src));
+      *reinterpret_cast<uint4*>(pout.p[0] + dst) = q0;
+      if (np > 1) *reinterpret_cast<uint4*>(pout.p[1] + dst) = q1;
+      if (np > 2) *reinterpret_cast<uint4*>(pout.p[2] + dst) = q2;
+    }
+  }
 }
 
 // col2im (adjoint of im2col) as a gather + ReLU mask + bf16 split:
@@ -415,15 +425,20 @@ __global__ void __launch_bounds__(256) colsum_u8_kernel(const uint8_t* __restric
 
 // border of a conv input factor from the batch-summed input S [hw_in, hw_in, c]:
 //   out[(ky*k + kx)*c + ch] = scale * sum_{oy,ox} S[(oy*s + ky), (ox*s + kx), ch]      (= P^T 1 without touching P)
-__global__ void window_sum_kernel(const float* __restrict__ sum_in, int hw_in, int c, int k, int s, int hw_out, float scale,
-                                  float* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per output element, lanes over the output locations
+__global__ void __launch_bounds__(256) window_sum_kernel(const float* __restrict__ sum_in, int hw_in, int c, int k, int s,
+                                                         int hw_out, float scale, float* __restrict__ out) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (i >= k * k * c) return;
   const int ch = i % c, kx = (i / c) % k, ky = i / (c * k);
   float acc = 0.f;
-  for (int oy = 0; oy < hw_out; ++oy)
-    for (int ox = 0; ox < hw_out; ++ox) acc += sum_in[((size_t)(oy * s + ky) * hw_in + ox * s + kx) * c + ch];
-  out[i] = acc * scale;
+  for (int loc = lane; loc < hw_out * hw_out; loc += 32) {
+    const int oy = loc / hw_out, ox = loc - oy * hw_out;
+    acc += sum_in[((size_t)(oy * s + ky) * hw_in + ox * s + kx) * c + ch];
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[i] = acc * scale;
 }
 
 __global__ void __launch_bounds__(256) colsum_stage2_kernel(const float* __restrict__ partial, int chunks, int cols, float scale,
@@ -514,10 +529,9 @@ int im2col_conv1(const uint8_t* obs, bf16* out, int rows_total, cudaStream_t st)
   return 0;
 }
 int im2col_bf16(const Planes& in, const Planes& out, int rows_total, int hw_in, int c, int k, int s, int hw_out, cudaStream_t st) {
-  const long long total = (long long)rows_total * k * (k * c / 8);
-  const int np = in.n < out.n ? in.n : out.n;
-  dim3 grid((unsigned)((total + 255) / 256), np);
-  im2col_bf16_kernel<<<grid, 256, 0, st>>>(in, out, rows_total, hw_in, c, k, s, hw_out);
+  int blocks = ceil_div(rows_total, 8);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  im2col_bf16_kernel<<<blocks, 256, 0, st>>>(in, out, rows_total, hw_in, c, k, s, hw_out);
   ACX_LAUNCH_CHECK();
   return 0;
 }
@@ -602,7 +616,7 @@ int conv_border(const uint8_t* obs_u8, const Planes* act, int n_rows, int hw_in,
     int r = colsum(v, n_rows, cols, 1.0f, partial, max_chunks, sum_tmp, 1, st);
     if (r) return r;
   }
-  window_sum_kernel<<<ceil_div(k * k * c, 128), 128, 0, st>>>(sum_tmp, hw_in, c, k, s, hw_out, scale, out);
+  window_sum_kernel<<<ceil_div(k * k * c, 8), 256, 0, st>>>(sum_tmp, hw_in, c, k, s, hw_out, scale, out);
   ACX_LAUNCH_CHECK();
   return 0;
 }
