@@ -216,19 +216,37 @@ __global__ void __launch_bounds__(256) inv_update_kernel(const InvDev* __restric
   const int nb = min(IB, n - p0);
   const double* cold = scratch_cold(jb);
   const double* rb = scratch_r(jb);
-  for (int idx = threadIdx.x; idx < 64 * IB; idx += 256) {
-    const int r = idx / IB, k = idx % IB;
-    const int gi = i0 + r;
-    cs[r][k] = (gi < n && k < nb && !(gi >= p0 && gi < p0 + IB)) ? cold[(size_t)gi * IB + k] : 0.0;
-  }
-  for (int idx = threadIdx.x; idx < IB * 64; idx += 256) {
-    const int k = idx / 64, c = idx % 64;
-    const int gj = j0 + c;
-    rs[k][c] = (gj < n && k < nb && !(gj >= p0 && gj < p0 + IB)) ? rb[(size_t)k * n + gj] : 0.0;
+  {
+    // issue every global load before the first shared-memory store
+    double rc[8], rr[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int idx = threadIdx.x + 256 * q;
+      const int r = idx / IB, k = idx % IB;
+      const int gi = i0 + r;
+      rc[q] = (gi < n && k < nb && !(gi >= p0 && gi < p0 + IB)) ? cold[(size_t)gi * IB + k] : 0.0;
+      const int k2 = idx / 64, c = idx % 64;
+      const int gj = j0 + c;
+      rr[q] = (gj < n && k2 < nb && !(gj >= p0 && gj < p0 + IB)) ? rb[(size_t)k2 * n + gj] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int idx = threadIdx.x + 256 * q;
+      cs[idx / IB][idx % IB] = rc[q];
+      rs[idx / 64][idx % 64] = rr[q];
+    }
   }
   __syncthreads();
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  double acc[4][4] = {};
+  // the 16 matrix elements this thread updates are fetched up front (independent loads, overlapped with the math)
+  double acc[4][4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int gi = i0 + ty + 16 * q, gj = j0 + tx + 16 * r;
+      acc[q][r] = (gi < n && gj < n) ? jb.m[(size_t)gi * n + gj] : 0.0;
+    }
 #pragma unroll 4
   for (int k = 0; k < IB; ++k) {
     double a[4], b[4];
@@ -240,7 +258,7 @@ __global__ void __launch_bounds__(256) inv_update_kernel(const InvDev* __restric
 #pragma unroll
     for (int q = 0; q < 4; ++q)
 #pragma unroll
-      for (int r = 0; r < 4; ++r) acc[q][r] += a[q] * b[r];
+      for (int r = 0; r < 4; ++r) acc[q][r] -= a[q] * b[r];
   }
   const double* cnew = scratch_cnew(jb);
   const double* dinv = scratch_dinv(jb, p);
@@ -262,7 +280,7 @@ __global__ void __launch_bounds__(256) inv_update_kernel(const InvDev* __restric
       else if (jp)
         *dst = cnew[(size_t)gi * IB + (gj - p0)];
       else
-        *dst -= acc[q][r];
+        *dst = acc[q][r];
     }
   }
   // next pivot block (p+1) lies inside exactly one 64 x 64 tile; that CTA inverts it now
@@ -414,11 +432,20 @@ __global__ void __launch_bounds__(256) precon_vg_kernel(const PreconJob* __restr
   if (r0 >= d) return;
   __shared__ float gs[64][65];
   __shared__ float vs[64][65];
-  for (int i = threadIdx.x; i < 64 * 64; i += 256) {
-    const int k = i >> 6, j = i & 63;
-    gs[k][j] = (k < c && j < c) ? jb.ginv[(size_t)k * c + j] : 0.0f;
-    const int r = r0 + k;
-    vs[k][j] = (r < d && j < c) ? jb.v[(size_t)r * c + j] : 0.0f;
+  {
+    float rg[16], rv[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int i = threadIdx.x + 256 * q, k = i >> 6, j = i & 63;
+      rg[q] = (k < c && j < c) ? __ldg(jb.ginv + (size_t)k * c + j) : 0.0f;
+      rv[q] = (r0 + k < d && j < c) ? jb.v[(size_t)(r0 + k) * c + j] : 0.0f;
+    }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int i = threadIdx.x + 256 * q;
+      gs[i >> 6][i & 63] = rg[q];
+      vs[i >> 6][i & 63] = rv[q];
+    }
   }
   __syncthreads();
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -459,13 +486,27 @@ __global__ void __launch_bounds__(256) precon_aw_kernel(const PreconJob* __restr
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (int k0 = 0; k0 < d; k0 += 64) {
-    for (int i = threadIdx.x; i < 16 * 64; i += 256) {
-      const int r = i >> 6, k = i & 63;
-      as[r][k] = (r0 + r < d && k0 + k < d) ? jb.ainv[(size_t)(r0 + r) * d + k0 + k] : 0.0f;
+    // all global loads are issued before the first shared-memory store (otherwise each load -> store pair serialises)
+    float ra[4], rw[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = threadIdx.x + 256 * q, r = i >> 6, k = i & 63;
+      ra[q] = (r0 + r < d && k0 + k < d) ? __ldg(jb.ainv + (size_t)(r0 + r) * d + k0 + k) : 0.0f;
     }
-    for (int i = threadIdx.x; i < 64 * 64; i += 256) {
-      const int k = i >> 6, j = i & 63;
-      ws[k][j] = (k0 + k < d && j < c) ? jb.w[(size_t)(k0 + k) * c + j] : 0.0f;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int i = threadIdx.x + 256 * q, k = i >> 6, j = i & 63;
+      rw[q] = (k0 + k < d && j < c) ? jb.w[(size_t)(k0 + k) * c + j] : 0.0f;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = threadIdx.x + 256 * q;
+      as[i >> 6][i & 63] = ra[q];
+    }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int i = threadIdx.x + 256 * q;
+      ws[i >> 6][i & 63] = rw[q];
     }
     __syncthreads();
 #pragma unroll 8
