@@ -112,13 +112,23 @@ __global__ void inv_prepare_kernel(const InvDev* __restrict__ jobs, const Sched*
   }
 }
 
+// fp64 reciprocal from an fp32 seed and three Newton steps (2^-24 -> 2^-48 -> 2^-96): a short dependent chain instead of
+// the IEEE division sequence; pivots of the damped SPD factors are far inside the fp32 exponent range
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r = (double)__frcp_rn((float)x);
+  r = r * (2.0 - x * r);
+  r = r * (2.0 - x * r);
+  r = r * (2.0 - x * r);
+  return r;
+}
+
 // invert an IB x IB block held in shared memory, in place (unblocked Gauss-Jordan without pivoting; rows/columns >= nb
 // are identity padding).  Works for any block size that is a multiple of 32 threads; every thread must call it.
 __device__ void invert_block_smem(double (*d)[IB + 1]) {
   const int nthreads = blockDim.x;
   for (int k = 0; k < IB; ++k) {
     __syncthreads();
-    const double inv_p = 1.0 / d[k][k];
+    const double inv_p = fast_rcp(d[k][k]);
     double v[4];
     int cnt = 0;
     for (int e = threadIdx.x; e < IB * IB; e += nthreads, ++cnt) {

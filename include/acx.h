@@ -126,7 +126,9 @@ typedef struct {
   int gemm_impl;               /* 0 tensor core, 1 SIMT (debug) */
   int precision;               /* activations / gradients are held as bf16 planes (x = hi + mid + lo); a GEMM of level L
                                   accumulates the plane pairs (i,j) with i+j <= L (1 pair, 3 pairs ~2^-17, 6 pairs fp32 class):
-                                  0 = parity grade: 3 planes, forward/backward 6 pairs, factor SYRKs 3 pairs, preconditioning 6
+                                  0 = parity grade: forward and backward on 3 planes / 6 pairs (fp32 class: ReLU masks hinge on the
+                                      sign of cancelling sums), factor SYRKs 3 pairs, preconditioning 6
+                                  4 = as 0 but gradients on 2 planes / 3 pairs (conv gradients ~6e-4 on iid-uniform inputs)
                                   1 = 2 planes, forward/backward/factors 3 pairs, preconditioning 6
                                   2 = as 1 with the factor SYRKs on the hi plane only (bf16 inputs)
                                   3 = single-plane bf16 everywhere (fastest; not parity grade) */
