@@ -769,6 +769,11 @@ static void plan_tc(const acx_gemm_t* g, TcPlan* pl) {
 constexpr int SMEM_LIMIT = 232448;                       // 227 KB per CTA on sm_100
 constexpr int SMEM_FIXED = EPI_BYTES + 256;              // epilogue staging + barriers (the base is 1024-aligned)
 
+// optional timing probe: when enabled, every tensor-core kernel launch (the kernel alone, not the finalize step) is
+// bracketed by two library-owned events on the launching stream; acx_gemm_last_ms() reads the last pair
+static bool g_probe_on = false;
+static cudaEvent_t g_probe_ev[2] = {nullptr, nullptr};
+
 template <int MAJOR>
 static int launch_tc(const CUtensorMap* ta, const CUtensorMap* tb, const TcParams& p, int grid, int smem, cudaStream_t st) {
   static bool configured = false;
@@ -776,8 +781,10 @@ static int launch_tc(const CUtensorMap* ta, const CUtensorMap* tb, const TcParam
     ACX_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MAJOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     configured = true;
   }
+  if (g_probe_on) ACX_CUDA(cudaEventRecord(g_probe_ev[0], st));
   gemm_tc_kernel<MAJOR><<<grid, 192, smem, st>>>(ta[0], ta[1], ta[2], tb[0], tb[1], tb[2], p);
   ACX_LAUNCH_CHECK();
+  if (g_probe_on) ACX_CUDA(cudaEventRecord(g_probe_ev[1], st));
   return 0;
 }
 
@@ -955,5 +962,24 @@ void acx_debug_set_mn_desc(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t kste
 }
 
 int acx_debug_tc_error(void) { return acx::tc_error_flag(); }
+
+int acx_gemm_enable_timing(int enable) {
+  if (enable && !acx::g_probe_on) {
+    for (int i = 0; i < 2; ++i) ACX_CUDA(cudaEventCreate(&acx::g_probe_ev[i]));
+    acx::g_probe_on = true;
+  } else if (!enable && acx::g_probe_on) {
+    for (int i = 0; i < 2; ++i) cudaEventDestroy(acx::g_probe_ev[i]);
+    acx::g_probe_on = false;
+  }
+  return 0;
+}
+
+int acx_gemm_last_ms(float* h_ms) {
+  ACX_CHECK(h_ms != nullptr, "null argument");
+  ACX_CHECK(acx::g_probe_on, "timing probe is off (acx_gemm_enable_timing)");
+  ACX_CUDA(cudaEventSynchronize(acx::g_probe_ev[1]));
+  ACX_CUDA(cudaEventElapsedTime(h_ms, acx::g_probe_ev[0], acx::g_probe_ev[1]));
+  return 0;
+}
 
 }  // extern "C"

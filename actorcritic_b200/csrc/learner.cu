@@ -340,6 +340,7 @@ static void register_buffers(acx_learner* l) {
   reg(l, "values", l->values, (size_t)l->R * 4);
   reg(l, "targets", l->targets, (size_t)l->N * 4);
   reg(l, "advantages", l->adv, (size_t)l->N * 4);
+  reg(l, "patches/conv1", l->P1.p[0], (size_t)l->R * 400 * 256 * 2);   // bf16 [R*400, 256], raw byte values
   reg(l, "dheads", l->dheads, (size_t)2 * l->N * (l->A + 1) * 4);
   static const char* an[5] = {"conv1", "conv2", "conv3", "fc4", "heads"};
   for (int i = 0; i < 5; ++i) {

@@ -83,8 +83,29 @@ static int ensure_taps() {
 
 __device__ __forceinline__ uint32_t max_u8x4(uint32_t a, uint32_t b) { return __vmaxu4(a, b); }
 
-// gray of 16 source bytes worth of pixels is awkward (3-byte pixels straddle words), so phase 1 works on
-// a 480-byte row as 30 uint4 loads into shared memory bytes, then one thread per pixel converts.
+// 16 RGB pixels held in 12 little-endian words -> 16 gray bytes (cv2 RGB2GRAY, 15-bit fixed point)
+__device__ __forceinline__ uint4 gray16(const uint32_t* w) {
+  uint32_t g[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+  for (int px = 0; px < 16; ++px) {
+    const int b0 = px * 3;
+    const uint32_t r = (w[b0 >> 2] >> (8 * (b0 & 3))) & 0xffu;
+    const uint32_t gg = (w[(b0 + 1) >> 2] >> (8 * ((b0 + 1) & 3))) & 0xffu;
+    const uint32_t b = (w[(b0 + 2) >> 2] >> (8 * ((b0 + 2) & 3))) & 0xffu;
+    const uint32_t y = (r * 9798u + gg * 19235u + b * 3735u + 16384u) >> 15;
+    g[px >> 2] |= y << (8 * (px & 3));
+  }
+  return make_uint4(g[0], g[1], g[2], g[3]);
+}
+
+// One CTA per (environment, band of 12 output rows = 30 source rows).
+//   phase 1: each thread streams 48 contiguous bytes (16 pixels) of both frames with 16-byte loads, takes the byte-wise
+//            max and leaves 16 gray bytes in shared memory (the raw bytes never touch shared memory)
+//   phase 2: horizontal area taps; a thread owns one output column, so its taps live in registers across the 30 rows
+//   phase 3: vertical taps, round-half-even, saturate, frame-stack push with coalesced 32-bit stores
+// Environments whose previous step was terminal run phases 1-3 twice: first on the reset frame (whose observation only
+// seeds the stack: 4 copies), then on the step frames.  Every fp32 multiply and add is a separate rounding (no FMA), in
+// OpenCV's order, which is what makes the result bit-exact.
 template <bool RESET>
 __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restrict__ raw_a, const uint8_t* __restrict__ raw_b,
                                                          const uint8_t* __restrict__ terminal,
@@ -92,111 +113,99 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restri
                                                          const uint8_t* __restrict__ reset_raw,
                                                          const uint8_t* stack_in, uint8_t* stack_out,
                                                          size_t out_env_stride, int num_envs) {
-  __shared__ __align__(16) uint8_t s_raw[BAND_SRC * RAW_ROW_BYTES];  // 14400 B (max of the two frames)
-  __shared__ float s_h[BAND_SRC][OUT];                                // 10080 B
-  __shared__ __align__(16) uint8_t s_raw2[RESET ? 1 : BAND_SRC * RAW_ROW_BYTES];
-  __shared__ float s_h2[RESET ? 1 : BAND_SRC][RESET ? 1 : OUT];
+  __shared__ __align__(16) uint8_t s_gray[BAND_SRC][RAW_W];   // 4800 B
+  __shared__ float s_h[BAND_SRC][OUT];                         // 10080 B
+  __shared__ uint8_t s_q2[BAND_OUT * OUT];                     // reset-frame pixels of this band
 
   const int env = blockIdx.x / NUM_BANDS;
   const int band = blockIdx.x % NUM_BANDS;
   if (env >= num_envs) return;
   const int tid = threadIdx.x;
   const size_t band_off = (size_t)env * RAW_FRAME_BYTES + (size_t)band * BAND_SRC * RAW_ROW_BYTES;
-
-  // does this env also need the reset frame (previous step was terminal)?
-  bool do_reset = false;
-  if (!RESET) do_reset = (reset_mask != nullptr) && reset_mask[env] != 0;
-
-  // ---- phase 1: stream the band (14400 B = 900 uint4) of both frames, byte-wise max ----
-  const uint4* pa = reinterpret_cast<const uint4*>(raw_a + band_off);
-  const uint4* pb = reinterpret_cast<const uint4*>(raw_b + band_off);
-  uint4* ps = reinterpret_cast<uint4*>(s_raw);
-  constexpr int NVEC = BAND_SRC * RAW_ROW_BYTES / 16;  // 900
-  for (int i = tid; i < NVEC; i += 256) {
-    uint4 a = __ldg(pa + i);
-    if (RESET) {
-      ps[i] = a;
-    } else {
-      uint4 b = __ldg(pb + i);
-      ps[i] = make_uint4(max_u8x4(a.x, b.x), max_u8x4(a.y, b.y), max_u8x4(a.z, b.z), max_u8x4(a.w, b.w));
-    }
-  }
-  if (!RESET && do_reset) {
-    const uint4* pr = reinterpret_cast<const uint4*>(reset_raw + band_off);
-    uint4* ps2 = reinterpret_cast<uint4*>(s_raw2);
-    for (int i = tid; i < NVEC; i += 256) ps2[i] = __ldg(pr + i);
-  }
-  __syncthreads();
-
-  // ---- phase 2: gray + horizontal area taps.  One thread per (source row, output column). ----
-  for (int i = tid; i < BAND_SRC * OUT; i += 256) {
-    const int r = i / OUT, dx = i % OUT;
-    const int n = c_taps.xn[dx];
-    const uint8_t* row = s_raw + r * RAW_ROW_BYTES;
-    float acc = 0.0f;
-#pragma unroll
-    for (int t = 0; t < 3; ++t) {
-      if (t < n) {
-        const uint8_t* px = row + c_taps.xsrc[dx][t] * 3;
-        const int y = (px[0] * 9798 + px[1] * 19235 + px[2] * 3735 + 16384) >> 15;
-        acc = __fadd_rn(acc, __fmul_rn((float)y, c_taps.xw[dx][t]));
-      }
-    }
-    s_h[r][dx] = acc;
-    if (!RESET && do_reset) {
-      const uint8_t* row2 = s_raw2 + r * RAW_ROW_BYTES;
-      float acc2 = 0.0f;
-#pragma unroll
-      for (int t = 0; t < 3; ++t) {
-        if (t < n) {
-          const uint8_t* px = row2 + c_taps.xsrc[dx][t] * 3;
-          const int y = (px[0] * 9798 + px[1] * 19235 + px[2] * 3735 + 16384) >> 15;
-          acc2 = __fadd_rn(acc2, __fmul_rn((float)y, c_taps.xw[dx][t]));
-        }
-      }
-      s_h2[r][dx] = acc2;
-    }
-  }
-  __syncthreads();
-
-  // ---- phase 3: vertical taps, round-half-even, saturate, stack push.  One thread per output pixel. ----
+  const bool do_reset = (!RESET) && (reset_mask != nullptr) && reset_mask[env] != 0;
   const bool term = (!RESET) && (terminal != nullptr) && terminal[env] != 0;
   const uint32_t* sin = reinterpret_cast<const uint32_t*>(stack_in + (size_t)env * STACK_BYTES);
   uint32_t* sout = reinterpret_cast<uint32_t*>(stack_out + (size_t)env * out_env_stride);
-  for (int i = tid; i < BAND_OUT * OUT; i += 256) {
-    const int dyl = i / OUT, dx = i % OUT;
-    const int dy = band * BAND_OUT + dyl;
-    float sum = 0.0f, sum2 = 0.0f;
+
+  // phase-2 ownership: output column dx for rows rg, rg + 3, ...
+  const int dx = tid % OUT, rg = tid / OUT;   // rg in 0..3 (only 0..2 work: 252 threads)
+  int xs[3];
+  float xw[3];
+  const int xn = c_taps.xn[dx];
 #pragma unroll
-    for (int t = 0; t < 3; ++t) {
-      const int sr = c_taps.ysrc[dy][t] - band * BAND_SRC;  // all y outputs have exactly 3 taps
-      const float w = c_taps.yw[dy][t];
-      const float term_v = __fmul_rn(w, s_h[sr][dx]);
-      sum = t == 0 ? term_v : __fadd_rn(sum, term_v);
-      if (!RESET && do_reset) {
-        const float tv2 = __fmul_rn(w, s_h2[sr][dx]);
-        sum2 = t == 0 ? tv2 : __fadd_rn(sum2, tv2);
+  for (int t = 0; t < 3; ++t) {
+    xs[t] = c_taps.xsrc[dx][t];
+    xw[t] = c_taps.xw[dx][t];
+  }
+
+  for (int pass = do_reset ? 0 : 1; pass < 2; ++pass) {
+    const bool reset_pass = pass == 0;
+    const uint8_t* fa = reset_pass ? reset_raw : raw_a;
+    const uint8_t* fb = reset_pass ? reset_raw : raw_b;
+    const bool single = RESET || reset_pass;
+    // ---- phase 1: 300 groups of 48 bytes (16 pixels) ----
+    constexpr int GROUPS = BAND_SRC * RAW_ROW_BYTES / 48;   // 300
+    for (int gidx = tid; gidx < GROUPS; gidx += 256) {
+      const uint4* pa = reinterpret_cast<const uint4*>(fa + band_off) + gidx * 3;
+      uint32_t w[12];
+      {
+        const uint4 a0 = __ldg(pa), a1 = __ldg(pa + 1), a2 = __ldg(pa + 2);
+        w[0] = a0.x; w[1] = a0.y; w[2] = a0.z; w[3] = a0.w;
+        w[4] = a1.x; w[5] = a1.y; w[6] = a1.z; w[7] = a1.w;
+        w[8] = a2.x; w[9] = a2.y; w[10] = a2.z; w[11] = a2.w;
+      }
+      if (!single) {
+        const uint4* pb = reinterpret_cast<const uint4*>(fb + band_off) + gidx * 3;
+        const uint4 b0 = __ldg(pb), b1 = __ldg(pb + 1), b2 = __ldg(pb + 2);
+        w[0] = max_u8x4(w[0], b0.x); w[1] = max_u8x4(w[1], b0.y); w[2] = max_u8x4(w[2], b0.z); w[3] = max_u8x4(w[3], b0.w);
+        w[4] = max_u8x4(w[4], b1.x); w[5] = max_u8x4(w[5], b1.y); w[6] = max_u8x4(w[6], b1.z); w[7] = max_u8x4(w[7], b1.w);
+        w[8] = max_u8x4(w[8], b2.x); w[9] = max_u8x4(w[9], b2.y); w[10] = max_u8x4(w[10], b2.z); w[11] = max_u8x4(w[11], b2.w);
+      }
+      // group gidx covers pixels [16 * gidx, 16 * gidx + 16) of the band's 30 x 160 pixel raster (rows are 10 groups)
+      *reinterpret_cast<uint4*>(&s_gray[0][0] + gidx * 16) = gray16(w);
+    }
+    __syncthreads();
+    // ---- phase 2: horizontal taps (gray byte -> float, multiply, add: separate roundings, table order) ----
+    if (rg < 3) {
+      for (int r = rg; r < BAND_SRC; r += 3) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+          if (t < xn) acc = __fadd_rn(acc, __fmul_rn((float)s_gray[r][xs[t]], xw[t]));
+        s_h[r][dx] = acc;
       }
     }
-    int q = __float2int_rn(sum);  // cvRound: round half to even
-    q = q < 0 ? 0 : (q > 255 ? 255 : q);
-    const int pix = dy * OUT + dx;
-    uint32_t word;
-    if (RESET) {
-      word = (uint32_t)q * 0x01010101u;  // wrappers.py:234: 4 copies
-    } else {
-      uint32_t prev;
-      if (do_reset) {  // multi_env.py:127-132: reset first, its observation is discarded, then step
-        int q2 = __float2int_rn(sum2);
-        q2 = q2 < 0 ? 0 : (q2 > 255 ? 255 : q2);
-        prev = (uint32_t)q2 * 0x01010101u;
+    __syncthreads();
+    // ---- phase 3: vertical taps, round half to even, saturate, push ----
+    for (int i = tid; i < BAND_OUT * OUT; i += 256) {
+      const int dyl = i / OUT, ox = i - dyl * OUT;
+      const int dy = band * BAND_OUT + dyl;
+      float sum = 0.0f;
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {   // every output row has exactly 3 vertical taps (scale 2.5)
+        const int sr = c_taps.ysrc[dy][t] - band * BAND_SRC;
+        const float tv = __fmul_rn(c_taps.yw[dy][t], s_h[sr][ox]);
+        sum = t == 0 ? tv : __fadd_rn(sum, tv);
+      }
+      int q = __float2int_rn(sum);  // cvRound
+      q = q < 0 ? 0 : (q > 255 ? 255 : q);
+      if (reset_pass) {
+        s_q2[i] = (uint8_t)q;
+        continue;
+      }
+      const int pix = dy * OUT + ox;
+      uint32_t word;
+      if (RESET) {
+        word = (uint32_t)q * 0x01010101u;  // wrappers.py:234: 4 copies
       } else {
-        prev = sin[pix];
+        // multi_env.py:127-132: an env that was terminal is reset first (its observation is discarded), then stepped
+        const uint32_t prev = do_reset ? (uint32_t)s_q2[i] * 0x01010101u : sin[pix];
+        word = term ? 0u : (prev >> 8);          // roll -1 along channels (little endian), zero on terminal
+        word |= (uint32_t)q << 24;               // newest frame in channel 3
       }
-      word = term ? 0u : (prev >> 8);          // roll -1 along channels (little endian), zero on terminal
-      word |= (uint32_t)q << 24;               // newest frame in channel 3
+      sout[pix] = word;
     }
-    sout[pix] = word;
+    __syncthreads();
   }
 }
 

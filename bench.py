@@ -19,6 +19,7 @@ timed on this box.  `--impl reference` times that CPU restatement alone (TensorF
 reference's real dependencies, are not installable offline - see DESIGN.md).
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -289,13 +290,76 @@ def run_native(args, rank, world, local_rank):
             stage_sum.setdefault(k, []).append(v)
     e.set_profiling(False)
     stage_ms = {k: float(np.mean(v)) for k, v in stage_sum.items()}
-    stage_ms["inverse"] = float(np.sum(stage_sum["inverse"]) / max(1, sum(1 for x in stage_sum["inverse"] if x > 0.01)))
+    stage_ms["inverse_per_refresh"] = float(np.sum(stage_sum["inverse"]) / max(1, sum(1 for x in stage_sum["inverse"] if x > 0.01)))
     flops = algorithmic_flops(n, envs, c3)
+
+    # dominant kernel, timed alone and live: the largest single launch of the update = the conv1 input-factor SYRK
+    # A1 = P1^T P1 (gemm_tc_kernel<1>, 256 x 256 output, K = N*400 patch rows, MN-major operands read once, symmetric
+    # tiles only, split-K over the SMs) on the engine's own patch matrix of the last update (131 MB > L2: every launch
+    # streams it from HBM).  Events are recorded by the library around the kernel itself on the launching stream.
+    from actorcritic_b200 import ops
+    lib = _lib.load()
+    k_rows = n * 400
+    p1 = e.buffer("patches/conv1", torch.bfloat16).view(-1, 256)[:k_rows]
+    lib.acx_gemm_enable_timing(1)
+    durs = []
+    with torch.cuda.stream(e.stream):
+        for i in range(13):
+            ops.gemm([p1], [p1], 256, 256, k_rows, trans=True, symmetric=True, pairs=[(0, 0)], alpha=1.0 / (255.0 * 255.0 * k_rows))
+            ms = ctypes.c_float(0)
+            _lib.check(lib.acx_gemm_last_ms(ctypes.byref(ms)))
+            if i >= 3:
+                durs.append(ms.value)
+    lib.acx_gemm_enable_timing(0)
+    syrk_ms = float(np.mean(durs))
+    syrk_flops = float(k_rows) * 256 * 257          # rows * d * (d + 1), symmetric half
+    syrk_tflops = syrk_flops / (syrk_ms * 1e-3) / 1e12
+
+    # K-PRE (BASELINE.json config 5): raw 210x160x3 frame pairs -> gray -> 84x84 -> frame-stack push, HBM bound
+    pre = {}
+    if rank == 0:
+        for pe in (64, 1024, 4096):
+            ra = torch.randint(0, 256, (pe, 210, 160, 3), dtype=torch.uint8, device=dev)
+            rb = torch.randint(0, 256, (pe, 210, 160, 3), dtype=torch.uint8, device=dev)
+            stk = torch.randint(0, 256, (pe, 84, 84, 4), dtype=torch.uint8, device=dev)
+            out = torch.empty_like(stk)
+            for _ in range(3):
+                ops.preprocess_stack(ra, rb, stk, out=out, out_env_stride=28224)
+            torch.cuda.synchronize()
+            reps = 20 if pe <= 1024 else 10
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for _ in range(reps):
+                ops.preprocess_stack(ra, rb, stk, out=out, out_env_stride=28224)
+            ev1.record()
+            torch.cuda.synchronize()
+            ms = ev0.elapsed_time(ev1) / reps
+            gbs = pe * 258048 / (ms * 1e-3) / 1e9
+            pre["envs_%d" % pe] = {"ms": ms, "env_steps_per_sec": pe / (ms * 1e-3), "GB/s": gbs, "frac_hbm": gbs / peaks["hbm"]}
+            del ra, rb, stk, out
+
+    # rollout side of the path (agents.py:202-216): T x (K-PRE on E raw frame pairs + forward on E rows + sample)
+    from actorcritic_b200.envs.atari.device_env import DeviceAtariMultiEnv
+    env = DeviceAtariMultiEnv(envs, pool_frames=32, seed=rank, device=dev)
+    cur = env.reset()
+    with torch.cuda.stream(e.stream):
+        for _ in range(3):
+            for t in range(t_count):
+                cur, _, _ = env.step_device(e.act(cur))
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(5):
+            for t in range(t_count):
+                cur, _, _ = env.step_device(e.act(cur))
+        ev1.record()
+        torch.cuda.synchronize()
+    rollout_ms = ev0.elapsed_time(ev1) / 5
+
     total_envs = envs * world
     ms_step = ms_dev / args.steps
     value = total_envs * t_count / (ms_step * 1e-3)
     e2e_value = total_envs * t_count / (ms_e2e / args.steps * 1e-3)
-    fac_tflops = flops["factors"] / (stage_ms["factors"] * 1e-3) / 1e12 if stage_ms["factors"] > 0 else 0.0
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -306,16 +370,25 @@ def run_native(args, rank, world, local_rank):
                    "l2": "8 resident input batches rotated (152 MB > 126 MB L2); per-step intermediates ~0.9 GB, self-flushing",
                    "parallelism": "dp%d (envs sharded, one NCCL all-reduce of grads+factor statistics per update)" % world},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 64,
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps,
+                "note": "Engine.stage_batch + Engine.update(staged=True): pinned host -> staging slot on a copy stream (double "
+                        "buffered), loss scalars read back every step"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel, factor-statistics stage (11 SYRKs A=[P 1]^T[P 1], G=g^T g)",
-                     "achieved": fac_tflops, "peak": peaks["tensor_sustained"], "unit": "TFLOP/s",
-                     "frac": fac_tflops / peaks["tensor_sustained"], "traffic": None,
-                     "algorithmic_gflop_per_launch_group": flops["factors"] / 1e9, "peak_source": peaks["source"] + ", sustained bf16",
+        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel<1>: conv1 input-factor SYRK A1 = P1^T P1 (256x256, K=%d), the largest launch of the update" % k_rows,
+                     "achieved": syrk_tflops, "peak": peaks["tensor_burst"], "unit": "TFLOP/s",
+                     "frac": syrk_tflops / peaks["tensor_burst"], "traffic": None,
+                     "algorithmic_gflop_per_launch": syrk_flops / 1e9, "launch_ms": syrk_ms,
+                     "peak_source": peaks["source"] + ", burst bf16 (kernel timed alone)",
+                     "hbm_GB/s_of_this_launch": k_rows * 256 * 2 / (syrk_ms * 1e-3) / 1e9,
                      "stage_ms": stage_ms,
-                     "stage_tflops": {k: flops[k] / (stage_ms[k] * 1e-3) / 1e12 for k in ("forward", "backward", "factors", "precondition", "inverse")
+                     "stage_tflops": {k: flops[k] / (stage_ms[k] * 1e-3) / 1e12 for k in ("forward", "backward", "factors", "precondition")
                                       if stage_ms.get(k, 0) > 0}},
+        "preprocess": pre,
+        "rollout": {"ms_per_%d_steps" % t_count: rollout_ms, "env_steps_per_sec": envs * t_count / (rollout_ms * 1e-3),
+                    "note": "per GPU: T x (K-PRE on E raw frame pairs -> stacks, Nature-CNN forward on E rows, categorical sample); "
+                            "not part of `value`"},
+        "env_steps_per_sec_with_rollout": total_envs * t_count / ((ms_step + rollout_ms) * 1e-3),
         "losses": scal,
     }
     if rank == 0:

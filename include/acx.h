@@ -106,6 +106,12 @@ size_t acx_gemm_workspace_bytes(const acx_gemm_t* g);
 /* fp32 [rows, cols] (ld_in) -> num_planes bf16 planes (ld_out multiple of 8); scale applied first. */
 int acx_split_planes(const float* d_in, int ld_in, int rows, int cols, float scale,
                      void* const* d_planes, int num_planes, int ld_out, void* stream);
+/* timing probe for bench.py's live roofline: when enabled, each tensor-core kernel launch (the kernel alone, without the
+ * split-K finalize step) is bracketed by two library-owned CUDA events recorded on the launching stream;
+ * acx_gemm_last_ms synchronises on them and returns the duration of the most recent launch. */
+int acx_gemm_enable_timing(int enable);
+int acx_gemm_last_ms(float* h_ms);
+int acx_debug_tc_error(void);
 /* debug hook: override the UMMA shared-memory descriptor strides (bytes) used for MN-major operands;
  * 0 restores the built-in values. */
 void acx_debug_set_mn_desc(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t kstep_bytes);
