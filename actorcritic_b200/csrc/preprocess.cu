@@ -36,7 +36,9 @@ struct Taps {
   float yw[OUT][3];
   int yn[OUT];
 };
-__constant__ Taps c_taps;
+// the tap tables live in global memory and are read through the read-only path: constant memory serialises the
+// per-lane indexed reads (measured: MIO-bound), the L1/texture path does not
+__device__ Taps c_taps;
 static bool g_taps_ready = false;
 
 // OpenCV computeResizeAreaTab (resize.cpp), cn = 1; weights are computed in double and stored as float.
@@ -131,11 +133,11 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restri
   const int dx = tid % OUT, rg = tid / OUT;   // rg in 0..3 (only 0..2 work: 252 threads)
   int xs[3];
   float xw[3];
-  const int xn = c_taps.xn[dx];
+  const int xn = __ldg(&c_taps.xn[dx]);
 #pragma unroll
   for (int t = 0; t < 3; ++t) {
-    xs[t] = c_taps.xsrc[dx][t];
-    xw[t] = c_taps.xw[dx][t];
+    xs[t] = __ldg(&c_taps.xsrc[dx][t]);
+    xw[t] = __ldg(&c_taps.xw[dx][t]);
   }
 
   for (int pass = do_reset ? 0 : 1; pass < 2; ++pass) {
@@ -183,8 +185,8 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restri
       float sum = 0.0f;
 #pragma unroll
       for (int t = 0; t < 3; ++t) {   // every output row has exactly 3 vertical taps (scale 2.5)
-        const int sr = c_taps.ysrc[dy][t] - band * BAND_SRC;
-        const float tv = __fmul_rn(c_taps.yw[dy][t], s_h[sr][ox]);
+        const int sr = __ldg(&c_taps.ysrc[dy][t]) - band * BAND_SRC;
+        const float tv = __fmul_rn(__ldg(&c_taps.yw[dy][t]), s_h[sr][ox]);
         sum = t == 0 ? tv : __fadd_rn(sum, tv);
       }
       int q = __float2int_rn(sum);  // cvRound
