@@ -197,7 +197,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": r["env_steps_per_sec"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_native(args, rank, world, local_rank):
@@ -397,12 +397,30 @@ def run_native(args, rank, world, local_rank):
             line["cpu_baseline"] = {"value": r["env_steps_per_sec"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                                     "sample": "%d whole %dx%d ACKTR updates of the CPU restatement (oracle/learner.py, fp32), "
                                               "%.2f s each" % (r["updates"], envs, t_count, r["sec_per_update"])}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line goes to the real stdout; everything else this process (or NCCL, which announces its version
+    on stdout) prints is diverted to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -414,7 +432,7 @@ def main():
         # launched without torchrun: re-launch ourselves under torch.distributed.run
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
-        sys.exit(subprocess.call(cmd))
+        sys.exit(subprocess.call(cmd, stdout=_REAL_STDOUT))
     run_native(args, rank, world, local_rank)
 
 
