@@ -123,29 +123,33 @@ __device__ __forceinline__ double fast_rcp(double x) {
 }
 
 // invert an IB x IB block held in shared memory, in place (unblocked Gauss-Jordan without pivoting; rows/columns >= nb
-// are identity padding).  Works for any block size that is a multiple of 32 threads; every thread must call it.
-__device__ void invert_block_smem(double (*d)[IB + 1]) {
-  const int nthreads = blockDim.x;
+// are identity padding).  NT = threads of the CTA (all must call it); each owns IB*IB/NT elements, fully unrolled so
+// the per-thread values stay in registers.
+template <int NT>
+__device__ __forceinline__ void invert_block_smem(double (*d)[IB + 1]) {
+  constexpr int PER = IB * IB / NT;
   for (int k = 0; k < IB; ++k) {
     __syncthreads();
     const double inv_p = fast_rcp(d[k][k]);
-    double v[4];
-    int cnt = 0;
-    for (int e = threadIdx.x; e < IB * IB; e += nthreads, ++cnt) {
+    double v[PER];
+#pragma unroll
+    for (int c = 0; c < PER; ++c) {
+      const int e = threadIdx.x + c * NT;
       const int ty = e >> 5, tx = e & 31;
       const double row_k = d[k][tx], col_k = d[ty][k];
-      if (ty == k && tx == k)
-        v[cnt] = inv_p;
-      else if (ty == k)
-        v[cnt] = row_k * inv_p;
-      else if (tx == k)
-        v[cnt] = -col_k * inv_p;
-      else
-        v[cnt] = d[ty][tx] - col_k * row_k * inv_p;
+      const double scaled = row_k * inv_p;
+      double r = d[ty][tx] - col_k * scaled;
+      if (ty == k) r = scaled;
+      if (tx == k) r = -col_k * inv_p;
+      if (ty == k && tx == k) r = inv_p;
+      v[c] = r;
     }
     __syncthreads();
-    cnt = 0;
-    for (int e = threadIdx.x; e < IB * IB; e += nthreads, ++cnt) d[e >> 5][e & 31] = v[cnt];
+#pragma unroll
+    for (int c = 0; c < PER; ++c) {
+      const int e = threadIdx.x + c * NT;
+      d[e >> 5][e & 31] = v[c];
+    }
   }
   __syncthreads();
 }
@@ -169,7 +173,7 @@ __global__ void __launch_bounds__(256) inv_diag0_kernel(const InvDev* __restrict
     const int ty = e >> 5, tx = e & 31;
     d[ty][tx] = (ty < nb && tx < nb) ? jb.m[(size_t)ty * n + tx] : (ty == tx ? 1.0 : 0.0);
   }
-  invert_block_smem(d);
+  invert_block_smem<256>(d);
   double* dinv = scratch_dinv(jb, 0);
   for (int e = threadIdx.x; e < IB * IB; e += 256) dinv[e] = d[e >> 5][e & 31];
 }
@@ -303,7 +307,7 @@ __global__ void __launch_bounds__(256) inv_update_kernel(const InvDev* __restric
       const int yy = e >> 5, xx = e & 31;
       d[yy][xx] = (yy < nbq && xx < nbq) ? jb.m[(size_t)(q0 + yy) * n + q0 + xx] : (yy == xx ? 1.0 : 0.0);
     }
-    invert_block_smem(d);
+    invert_block_smem<256>(d);
     double* out = scratch_dinv(jb, p + 1);
     for (int e = threadIdx.x; e < IB * IB; e += 256) out[e] = d[e >> 5][e & 31];
   }

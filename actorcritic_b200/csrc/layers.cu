@@ -68,7 +68,9 @@ __global__ void __launch_bounds__(256) im2col_bf16_kernel(const Planes pin, cons
 //   dPre[n,y,x,c] = dX * 1[act(n % mask_n, y, x, c) > 0]       (true rows and Fisher rows share the mask)
 // One thread per (n, y, x, 4 channels).
 __global__ void col2im_mask_split_kernel(const float* __restrict__ dp, const bf16* __restrict__ act_hi, const Planes out,
-                                         int n_total, int mask_n, int hw_in, int c, int k, int s, int hw_out) {
+                                         int n_begin, int n_total, int mask_n, int hw_in, int c, int k, int s, int hw_out) {
+  // dp holds the patch gradients of samples [n_begin, n_begin + n_total) only (one L2-sized chunk); outputs and masks are
+  // indexed by the global sample number
   const int cv = c / 4;
   const long long total = (long long)n_total * hw_in * hw_in * cv;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -97,8 +99,9 @@ __global__ void col2im_mask_split_kernel(const float* __restrict__ dp, const bf1
       acc.w += v.w;
     }
   }
-  const size_t pix = ((size_t)((n % mask_n) * hw_in + y) * hw_in + x) * c + c4;
-  const size_t opix = ((size_t)(n * hw_in + y) * hw_in + x) * c + c4;
+  const int ng = n + n_begin;
+  const size_t pix = ((size_t)((ng % mask_n) * hw_in + y) * hw_in + x) * c + c4;
+  const size_t opix = ((size_t)(ng * hw_in + y) * hw_in + x) * c + c4;
   const float vals[4] = {acc.x, acc.y, acc.z, acc.w};
   __align__(8) bf16 hi[4], mid[4], lo[4];
 #pragma unroll
@@ -535,11 +538,11 @@ int im2col_bf16(const Planes& in, const Planes& out, int rows_total, int hw_in, 
   ACX_LAUNCH_CHECK();
   return 0;
 }
-int col2im_mask_split(const float* dp, const bf16* act_hi, const Planes& out, int n_total, int mask_n, int hw_in, int c, int k, int s,
-                      int hw_out, cudaStream_t st) {
+int col2im_mask_split(const float* dp, const bf16* act_hi, const Planes& out, int n_begin, int n_total, int mask_n, int hw_in, int c,
+                      int k, int s, int hw_out, cudaStream_t st) {
   const long long total = (long long)n_total * hw_in * hw_in * (c / 4);
-  col2im_mask_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dp, act_hi, out, n_total, mask_n, hw_in, c, k, s,
-                                                                           hw_out);
+  col2im_mask_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dp, act_hi, out, n_begin, n_total, mask_n, hw_in, c, k,
+                                                                           s, hw_out);
   ACX_LAUNCH_CHECK();
   return 0;
 }

@@ -12,6 +12,7 @@
 //            apply; or the A2C RMSProp step (a2c_acktr.py:250-251).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -101,6 +102,7 @@ struct acx_learner {
   Planes P1, act1, P2, act2, P3, act3, act4;
   Planes dpre4, dpre3, dpre2, dpre1;
   float *dP, *logits, *values, *targets, *adv, *dheads;
+  size_t dgrad_chunk_bytes;
   Planes wT[4], wN[4];
   Planes Vp, Wt;
   float *colsum_partial, *colsum_tmp, *dot_partials;
@@ -123,6 +125,9 @@ namespace acx {
 
 static const int kColsumChunks = 592;
 static const int kBorderChunks = 64;
+static const size_t kDgradChunkBytes = 0;   // 0 = whole batch in one piece.  Measured on B200 at 32x20 (ACX_DGRAD_CHUNK_MB sweep):
+                                            // whole 1.510 ms/update, 128 MB 1.533, 64 MB 1.551, 32 MB 1.599, 16 MB 1.681 - the
+                                            // extra launches and wave tails cost more than the HBM round trip saves
 static const int kDotPartials = 64;
 
 static int pad8(int x) { return (x + 7) / 8 * 8; }
@@ -300,7 +305,13 @@ static size_t layout(acx_learner* l, uint8_t* base) {
   l->dpre3 = take_planes(ar, ng, B2 * 49, c3);
   l->dpre2 = take_planes(ar, ng, B2 * 81, 64);
   l->dpre1 = take_planes(ar, ng, B2 * 400, 32);
-  l->dP = f32(std::max(B2 * 49 * 576, B2 * 81 * 512));
+  {
+    const char* env = getenv("ACX_DGRAD_CHUNK_MB");   // tuning knob (0 = whole batch in one piece)
+    size_t mb = env ? (size_t)atoi(env) : (size_t)(kDgradChunkBytes >> 20);
+    const size_t whole = std::max(B2 * 49 * 576, B2 * 81 * 512) * sizeof(float);
+    l->dgrad_chunk_bytes = (mb == 0 || (mb << 20) > whole) ? whole : (mb << 20);
+  }
+  l->dP = f32(l->dgrad_chunk_bytes / sizeof(float) + 81 * 512);   // one chunk of patch gradients
   // ---- preconditioning scratch
   int dmax = 0, cmax = 0;
   for (int i = 0; i < 6; ++i) {
@@ -516,6 +527,25 @@ static int weight_grad(acx_learner* l, int li, const Planes& x, const Planes& g,
   return 0;
 }
 
+// input gradient of conv layer li: dP = g W^T (fp32) then col2im + ReLU mask of the layer below + bf16 split.  Done in
+// chunks of samples (optional, see kDgradChunkBytes: an L2-sized chunk keeps dP on chip, but measured slower).
+static int conv_dgrad(acx_learner* l, int li, const Planes& g, const bf16* act_below_hi, const Planes& g_below, int samples,
+                      cudaStream_t st) {
+  const Layer& L = l->L[li];
+  const size_t per_sample = (size_t)L.T * L.K * sizeof(float);
+  int chunk = (int)(l->dgrad_chunk_bytes / per_sample);
+  if (chunk < 1) chunk = 1;
+  for (int n0 = 0; n0 < samples; n0 += chunk) {
+    const int ns = std::min(chunk, samples - n0);
+    GemmOut o;
+    o.c = l->dP;
+    o.ldc = L.K;
+    ACX_TRY(run_gemm(l, offset_rows(g, (size_t)n0 * L.T), l->wN[li], 0, ns * L.T, L.K, L.C, l->lvl_bwd, 1.0f, 0, o, st));
+    ACX_TRY(col2im_mask_split(l->dP, act_below_hi, g_below, n0, ns, l->N, L.hw_in, L.cin, L.k, L.s, L.hw_out, st));
+  }
+  return 0;
+}
+
 // output factor G_l = g^T g / rows over the Fisher-sample rows
 static int output_factor(acx_learner* l, int li, const Planes& g_fisher, int rows, cudaStream_t st) {
   const Layer& L = l->L[li];
@@ -554,22 +584,10 @@ static int issue_phase1(acx_learner* l, const int32_t* fisher_labels, const floa
   }
   // ---- conv3
   ACX_TRY(weight_grad(l, 2, l->P3, l->dpre3, N * 49, 1.0f, st));
-  {
-    GemmOut o;
-    o.c = l->dP;
-    o.ldc = 576;
-    ACX_TRY(run_gemm(l, l->dpre3, l->wN[2], 0, RB * 49, 576, c3, l->lvl_bwd, 1.0f, 0, o, st));
-    ACX_TRY(col2im_mask_split(l->dP, l->act2.p[0], l->dpre2, RB, N, 9, 64, 3, 1, 7, st));
-  }
+  ACX_TRY(conv_dgrad(l, 2, l->dpre3, l->act2.p[0], l->dpre2, RB, st));
   // ---- conv2
   ACX_TRY(weight_grad(l, 1, l->P2, l->dpre2, N * 81, 1.0f, st));
-  {
-    GemmOut o;
-    o.c = l->dP;
-    o.ldc = 512;
-    ACX_TRY(run_gemm(l, l->dpre2, l->wN[1], 0, RB * 81, 512, 64, l->lvl_bwd, 1.0f, 0, o, st));
-    ACX_TRY(col2im_mask_split(l->dP, l->act1.p[0], l->dpre1, RB, N, 20, 32, 4, 2, 9, st));
-  }
+  ACX_TRY(conv_dgrad(l, 1, l->dpre2, l->act1.p[0], l->dpre1, RB, st));
   // ---- conv1 (no input gradient: observations are constants, envs/atari/model.py:101-104)
   ACX_TRY(weight_grad(l, 0, l->P1, l->dpre1, N * 400, 1.0f / 255.0f, st));
   mark(l, 3, st);
