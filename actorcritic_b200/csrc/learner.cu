@@ -125,6 +125,7 @@ namespace acx {
 
 static const int kColsumChunks = 592;
 static const int kBorderChunks = 64;
+static const int kGramChunks = 444;   // 3 CTAs per SM
 static const size_t kDgradChunkBytes = 0;   // 0 = whole batch in one piece.  Measured on B200 at 32x20 (ACX_DGRAD_CHUNK_MB sweep):
                                             // whole 1.510 ms/update, 128 MB 1.533, 64 MB 1.551, 32 MB 1.599, 16 MB 1.681 - the
                                             // extra launches and wave tails cost more than the HBM round trip saves
@@ -320,7 +321,8 @@ static size_t layout(acx_learner* l, uint8_t* base) {
   }
   l->Vp = take_planes(ar, 3, dmax, pad8(cmax));
   l->Wt = take_planes(ar, 3, cmax, pad8(dmax));
-  l->colsum_partial = f32(std::max((size_t)kColsumChunks * (size_t)std::max(49 * c3, 576), (size_t)kBorderChunks * 28224));
+  l->colsum_partial = f32(std::max(std::max((size_t)kColsumChunks * (size_t)std::max(49 * c3, 576), (size_t)kBorderChunks * 28224),
+                                   (size_t)kGramChunks * 4096));
   l->colsum_tmp = f32(4096 + 28224 + 8);   // [0,4096): border / column-sum vectors, then the batch-summed conv input
   l->dot_partials = f32(kDotPartials);
   const size_t kpad = align_up((size_t)49 * c3, 128);
@@ -549,6 +551,8 @@ static int conv_dgrad(acx_learner* l, int li, const Planes& g, const bf16* act_b
 // output factor G_l = g^T g / rows over the Fisher-sample rows
 static int output_factor(acx_learner* l, int li, const Planes& g_fisher, int rows, cudaStream_t st) {
   const Layer& L = l->L[li];
+  if ((L.C == 32 || L.C == 64) && l->cfg.gemm_impl == 0)   // too narrow for a tensor-core tile: fp32 SIMT Gram kernel
+    return gram_small(g_fisher, rows, L.C, 1.0f / (float)rows, l->colsum_partial, kGramChunks, l->stats + l->goff[li], st);
   GemmOut o;
   o.c = l->stats + l->goff[li];
   o.ldc = L.C;
