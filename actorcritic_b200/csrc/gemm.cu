@@ -42,6 +42,7 @@ struct TcParams {
   int stages;            // shared-memory ring depth
   int tiles_m, tiles_n, num_tiles, splits, total_work;
   int symmetric;
+  int panel;             // SYRK panel mode: one work item = one k-split of the whole (<= 256 wide) symmetric product
   int to_workspace;
   float* ws;
   int ws_ld;
@@ -204,6 +205,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 
 constexpr int MAX_STAGES = 8;
+constexpr int PANEL_TILE_BYTES = 4 * BK * 128;           // panel mode: 64 k-rows x 256 columns of one plane
 constexpr int EPI_LD = 68;                              // padded row of the per-warp 32 x 64 fp32 staging tile (16-byte multiple)
 constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;          // four epilogue warps
 
@@ -229,7 +231,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
   }
   const int BN = p.bn;
   const int b_tile_bytes = BN * BK * 2;
-  const int stage_bytes = p.npa * A_TILE_BYTES + p.npb * b_tile_bytes;
+  // panel mode: a stage holds, per plane, the 64 k-rows x (up to) 256 columns of X once; the same shared memory feeds
+  // the A side and the B side of the three upper 128 x 128 sub-tiles of X^T X
+  const int stage_bytes = p.panel ? p.npa * PANEL_TILE_BYTES : p.npa * A_TILE_BYTES + p.npb * b_tile_bytes;
   float* epi = reinterpret_cast<float*>(smem + p.stages * stage_bytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(epi) + EPI_BYTES);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
@@ -238,7 +242,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tmem_cols = (uint32_t)(2 * BN);   // 64, 128 or 256: a power of two >= 32
+  const uint32_t tmem_cols = p.panel ? 512u : (uint32_t)(2 * BN);   // 64, 128 or 256 (two accumulators); panel: three + pad
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -259,6 +263,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
 
   // work item -> (tile_m, tile_n, split)
   auto decode = [&](int w, int& tm, int& tn, int& split) {
+    if (p.panel) {
+      split = w;
+      tm = tn = 0;
+      return;
+    }
     split = w / p.num_tiles;
     int t = w - split * p.num_tiles;
     if (p.symmetric) {
@@ -290,13 +299,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
         // shared memory only feeds accumulator rows/columns that are never stored)
         const int na = MAJOR == 0 ? 0 : min(BM / 64, (p.out.m - m0 + 63) / 64);
         const int nb = MAJOR == 0 ? 0 : min(BN / 64, (p.out.n - n0 + 63) / 64);
-        const uint32_t tx = MAJOR == 0 ? (uint32_t)stage_bytes : (uint32_t)((p.npa * na + p.npb * nb) * BK * 128);
+        const int nch = (p.out.n + 63) / 64;   // panel mode: 64-column chunks of X
+        const uint32_t tx = p.panel ? (uint32_t)(p.npa * nch * BK * 128)
+                                    : (MAJOR == 0 ? (uint32_t)stage_bytes : (uint32_t)((p.npa * na + p.npb * nb) * BK * 128));
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
           mbar_wait(&empty_bar[s], ph ^ 1u, 1);
           mbar_expect_tx(&full_bar[s], tx);
           uint8_t* a_s = smem + s * stage_bytes;
+          if (p.panel) {
+            for (int i = 0; i < p.npa; ++i) {
+              const CUtensorMap* ma = i == 0 ? &ta0 : (i == 1 ? &ta1 : &ta2);
+              for (int j = 0; j < nch; ++j)
+                tma_load_2d(a_s + i * PANEL_TILE_BYTES + j * (BK * 128), ma, &full_bar[s], 64 * j, kb * BK);
+            }
+            continue;
+          }
           uint8_t* b_s = a_s + p.npa * A_TILE_BYTES;
           for (int i = 0; i < p.npa; ++i) {
             const CUtensorMap* ma = i == 0 ? &ta0 : (i == 1 ? &ta1 : &ta2);
@@ -333,11 +352,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
       decode(w, tm, tn, split);
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-      const int buf = lt & 1;
-      const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
+      const int buf = p.panel ? 0 : (lt & 1);
+      const uint32_t aph = p.panel ? ((uint32_t)lt & 1u) : ((uint32_t)(lt >> 1) & 1u);
       mbar_wait(&acc_empty[buf], aph ^ 1u, 4);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(p.panel ? 0 : buf * BN);
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
@@ -353,14 +372,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
           const uint64_t a_desc0 = make_smem_desc(a_addr, lbo, sbo);
           const uint64_t b_desc0 = make_smem_desc(b_addr, lbo, sbo);
           uint32_t acc_flag = kb > kb0 ? 1u : 0u;
-          for (int pr = 0; pr < p.num_pairs; ++pr) {
-            uint64_t ad = a_desc0 + (uint64_t)((uint32_t)(p.pair_a[pr] * A_TILE_BYTES) >> 4);
-            uint64_t bd = b_desc0 + (uint64_t)((uint32_t)(p.pair_b[pr] * b_tile_bytes) >> 4);
-            for (int kk = 0; kk < ksteps; ++kk) {
-              umma_bf16(d_tmem, ad, bd, idesc, acc_flag);
-              acc_flag = 1u;
-              ad += kstep16;
-              bd += kstep16;
+          if (p.panel) {
+            // three upper sub-tiles (0,0) (0,1) (1,1): accumulators at TMEM columns 0, 128, 256
+            for (int pr = 0; pr < p.num_pairs; ++pr) {
+              for (int sub = 0; sub < 3; ++sub) {
+                const int ti = sub == 2 ? 1 : 0, tj = sub >= 1 ? 1 : 0;
+                uint64_t ad = a_desc0 + (uint64_t)((uint32_t)(p.pair_a[pr] * PANEL_TILE_BYTES + ti * A_TILE_BYTES) >> 4);
+                uint64_t bd = a_desc0 + (uint64_t)((uint32_t)(p.pair_b[pr] * PANEL_TILE_BYTES + tj * A_TILE_BYTES) >> 4);
+                uint32_t flag = (kb > kb0 || pr > 0) ? 1u : 0u;
+                for (int kk = 0; kk < ksteps; ++kk) {
+                  umma_bf16(d_tmem + (uint32_t)(sub * 128), ad, bd, idesc, flag);
+                  flag = 1u;
+                  ad += kstep16;
+                  bd += kstep16;
+                }
+              }
+            }
+          } else {
+            for (int pr = 0; pr < p.num_pairs; ++pr) {
+              uint64_t ad = a_desc0 + (uint64_t)((uint32_t)(p.pair_a[pr] * A_TILE_BYTES) >> 4);
+              uint64_t bd = b_desc0 + (uint64_t)((uint32_t)(p.pair_b[pr] * b_tile_bytes) >> 4);
+              for (int kk = 0; kk < ksteps; ++kk) {
+                umma_bf16(d_tmem, ad, bd, idesc, acc_flag);
+                acc_flag = 1u;
+                ad += kstep16;
+                bd += kstep16;
+              }
             }
           }
           umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
@@ -403,14 +440,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++lt) {
       int tm, tn, split;
       decode(w, tm, tn, split);
-      const int m0 = tm * BM + q * 32, n0 = tn * BN;
-      const int buf = lt & 1;
-      const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
+      const int buf = p.panel ? 0 : (lt & 1);
+      const uint32_t aph = p.panel ? ((uint32_t)lt & 1u) : ((uint32_t)(lt >> 1) & 1u);
       mbar_wait(&acc_full[buf], aph, 3);
       tc_fence_after();
+      const int nsub = p.panel ? 3 : 1;
+      for (int sub = 0; sub < nsub; ++sub) {
+      const int m0 = (p.panel ? (sub == 2 ? BM : 0) : tm * BM) + q * 32;
+      const int n0 = p.panel ? (sub >= 1 ? BN : 0) : tn * BN;
+      const int col_base = p.panel ? sub * 128 : buf * BN;
       for (int c0 = 0; c0 < BN; c0 += CH) {
         uint32_t raw[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(col_base + c0);
         tmem_ld32(taddr, raw);
         float4* strow = reinterpret_cast<float4*>(st + lane * EPI_LD);
 #pragma unroll
@@ -424,7 +465,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
             strow[8 + j] = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
                                        __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3]));
         }
-        if (c0 + CH >= BN) {   // the accumulator has been drained: hand the TMEM buffer back to the MMA warp
+        if (c0 + CH >= BN && sub == nsub - 1) {   // the accumulator has been drained: hand the TMEM buffer back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
@@ -537,6 +578,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
           }
         }
         __syncwarp();
+      }
       }
     }
   }
@@ -769,7 +811,7 @@ static void fill_out(const acx_gemm_t* g, OutParams* o) {
 }
 
 struct TcPlan {
-  int bn, tiles_m, tiles_n, splits, kb_total, kb_per_split, to_ws;
+  int bn, tiles_m, tiles_n, splits, kb_total, kb_per_split, to_ws, panel;
   size_t ws_bytes;
 };
 
@@ -788,6 +830,10 @@ static void plan_tc(const acx_gemm_t* g, TcPlan* pl) {
   pl->kb_total = ceil_div(g->k, BK);
   int tiles = pl->tiles_m * pl->tiles_n;
   if (g->symmetric) tiles = pl->tiles_n * (pl->tiles_n + 1) / 2;
+  // SYRK panel mode: X^T X with 128 < n <= 256 (MN-major): every CTA streams its k-range of X once and feeds all three
+  // upper sub-tiles from the same shared memory
+  pl->panel = (g->symmetric && g->trans_a && pl->bn == 128 && pl->tiles_n == 2 && g->a.planes[0] == g->b.planes[0]) ? 1 : 0;
+  if (pl->panel) tiles = 1;
   int splits = g->splits;
   if (splits <= 0) {  // auto: about one work item per SM, at least 4 k-blocks per split
     splits = 148 / (tiles > 0 ? tiles : 1);
@@ -890,13 +936,15 @@ static int gemm_tc(const acx_gemm_t* g, cudaStream_t st) {
     }
   }
   p.bn = pl.bn;
-  const int stage_bytes = p.npa * A_TILE_BYTES + p.npb * pl.bn * BK * 2;
+  p.panel = pl.panel;
+  if (pl.panel && p.npb > p.npa) p.npa = p.npb;   // one plane set serves both operand sides
+  const int stage_bytes = pl.panel ? p.npa * PANEL_TILE_BYTES : p.npa * A_TILE_BYTES + p.npb * pl.bn * BK * 2;
   p.stages = (SMEM_LIMIT - SMEM_FIXED) / stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   ACX_CHECK(p.stages >= 2, "tile does not fit the shared-memory ring");
   p.tiles_m = pl.tiles_m;
   p.tiles_n = pl.tiles_n;
-  p.num_tiles = g->symmetric ? pl.tiles_n * (pl.tiles_n + 1) / 2 : pl.tiles_m * pl.tiles_n;
+  p.num_tiles = pl.panel ? 1 : (g->symmetric ? pl.tiles_n * (pl.tiles_n + 1) / 2 : pl.tiles_m * pl.tiles_n);
   p.splits = pl.splits;
   p.total_work = p.num_tiles * pl.splits;
   p.symmetric = g->symmetric;
