@@ -559,9 +559,32 @@ __global__ void sched_advance_kernel(Sched* s, int gs_inc, int ncov_inc, float e
   }
 }
 
+// whole schedule transition of one phase-2 call in one launch: learning rate from the step the update starts with, then
+// the counters (nothing later in the phase reads global_step; the inverse refresh reads the new debias factor)
+__global__ void sched_step_kernel(Sched* s, float lr_start, float lr_end, double decay_steps, float* out_lr, int gs_inc,
+                                  int ncov_inc, float ema_decay, int zero_debias) {
+  double g = (double)s->gs;
+  if (g > decay_steps) g = decay_steps;
+  s->lr = (float)(((double)lr_start - (double)lr_end) * (1.0 - g / decay_steps) + (double)lr_end);
+  if (out_lr) *out_lr = s->lr;
+  s->gs += (unsigned long long)gs_inc;
+  s->ncov += (unsigned long long)ncov_inc;
+  if (ncov_inc) {
+    double d = 1.0;
+    if (zero_debias && s->ncov > 0) d = 1.0 / (1.0 - pow((double)ema_decay, (double)s->ncov));
+    s->debias = (float)d;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
+int sched_step(Sched* s, float lr_start, float lr_end, double decay_steps, float* out_lr, int gs_inc, int ncov_inc,
+               float ema_decay, int zero_debias, cudaStream_t st) {
+  sched_step_kernel<<<1, 1, 0, st>>>(s, lr_start, lr_end, decay_steps, out_lr, gs_inc, ncov_inc, ema_decay, zero_debias);
+  ACX_LAUNCH_CHECK();
+  return 0;
+}
 int sched_begin(Sched* s, float lr_start, float lr_end, double decay_steps, float* out_lr, cudaStream_t st) {
   sched_begin_kernel<<<1, 1, 0, st>>>(s, lr_start, lr_end, decay_steps, out_lr);
   ACX_LAUNCH_CHECK();

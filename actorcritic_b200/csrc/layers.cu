@@ -66,33 +66,26 @@ __global__ void __launch_bounds__(256) im2col_bf16_kernel(const Planes pin, cons
 // col2im (adjoint of im2col) as a gather + ReLU mask + bf16 split:
 //   dX[n,y,x,c] = sum_{ky,kx : (y-ky)%s==0, (x-kx)%s==0, in range} dP[(n,oy,ox), (ky,kx,c)]
 //   dPre[n,y,x,c] = dX * 1[act(n % mask_n, y, x, c) > 0]       (true rows and Fisher rows share the mask)
-// One thread per (n, y, x, 4 channels).
-__global__ void col2im_mask_split_kernel(const float* __restrict__ dp, const bf16* __restrict__ act_hi, const Planes out,
-                                         int n_begin, int n_total, int mask_n, int hw_in, int c, int k, int s, int hw_out) {
-  // dp holds the patch gradients of samples [n_begin, n_begin + n_total) only (one L2-sized chunk); outputs and masks are
-  // indexed by the global sample number
-  const int cv = c / 4;
-  const long long total = (long long)n_total * hw_in * hw_in * cv;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c4 = (int)(i % cv) * 4;
-  long long t = i / cv;
-  const int x = (int)(t % hw_in);
-  t /= hw_in;
-  const int y = (int)(t % hw_in);
-  const int n = (int)(t / hw_in);
+// One CTA per (sample, input row y); a thread owns (x, 4 channels), so the only integer division is per CTA.
+__global__ void __launch_bounds__(256) col2im_mask_split_kernel(const float* __restrict__ dp, const bf16* __restrict__ act_hi,
+                                                                const Planes out, int n_begin, int mask_n, int hw_in, int c, int k,
+                                                                int s, int hw_out) {
+  // dp holds the patch gradients of samples [n_begin, n_begin + gridDim.x / hw_in) only; outputs and masks are indexed by
+  // the global sample number
+  const int cv = c >> 2;
+  const int n = blockIdx.x / hw_in, y = blockIdx.x - n * hw_in;
+  const int x = threadIdx.x / cv, c4 = (threadIdx.x - x * cv) << 2;
+  if (x >= hw_in) return;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   const int kkc = k * k * c;
-  for (int ky = y % s; ky < k; ky += s) {
+  const float* base = dp + (size_t)n * hw_out * hw_out * kkc + c4;
+  for (int ky = y % s; ky < k && ky <= y; ky += s) {
     const int oy = (y - ky) / s;
-    if (y - ky < 0) break;
     if (oy >= hw_out) continue;
-    for (int kx = x % s; kx < k; kx += s) {
+    for (int kx = x % s; kx < k && kx <= x; kx += s) {
       const int ox = (x - kx) / s;
-      if (x - kx < 0) break;
       if (ox >= hw_out) continue;
-      const float4 v = __ldg(reinterpret_cast<const float4*>(
-          dp + ((size_t)(n * hw_out + oy) * hw_out + ox) * kkc + (ky * k + kx) * c + c4));
+      const float4 v = __ldg(reinterpret_cast<const float4*>(base + (size_t)(oy * hw_out + ox) * kkc + (ky * k + kx) * c));
       acc.x += v.x;
       acc.y += v.y;
       acc.z += v.z;
@@ -102,14 +95,12 @@ __global__ void col2im_mask_split_kernel(const float* __restrict__ dp, const bf1
   const int ng = n + n_begin;
   const size_t pix = ((size_t)((ng % mask_n) * hw_in + y) * hw_in + x) * c + c4;
   const size_t opix = ((size_t)(ng * hw_in + y) * hw_in + x) * c + c4;
-  const float vals[4] = {acc.x, acc.y, acc.z, acc.w};
+  const uint2 mw = *reinterpret_cast<const uint2*>(act_hi + pix);   // 4 bf16 of the forward activation (ReLU mask)
+  const float vals[4] = {__uint_as_float(mw.x << 16) > 0.0f ? acc.x : 0.0f, __uint_as_float(mw.x & 0xffff0000u) > 0.0f ? acc.y : 0.0f,
+                         __uint_as_float(mw.y << 16) > 0.0f ? acc.z : 0.0f, __uint_as_float(mw.y & 0xffff0000u) > 0.0f ? acc.w : 0.0f};
   __align__(8) bf16 hi[4], mid[4], lo[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float m = __bfloat162float(act_hi[pix + j]);
-    const float v = m > 0.0f ? vals[j] : 0.0f;
-    split3(v, hi[j], mid[j], lo[j]);
-  }
+  for (int j = 0; j < 4; ++j) split3(vals[j], hi[j], mid[j], lo[j]);
   *reinterpret_cast<uint2*>(out.p[0] + opix) = *reinterpret_cast<const uint2*>(hi);
   if (out.n > 1) *reinterpret_cast<uint2*>(out.p[1] + opix) = *reinterpret_cast<const uint2*>(mid);
   if (out.n > 2) *reinterpret_cast<uint2*>(out.p[2] + opix) = *reinterpret_cast<const uint2*>(lo);
@@ -430,7 +421,7 @@ __global__ void __launch_bounds__(256) colsum_u8_kernel(const uint8_t* __restric
 //   out[(ky*k + kx)*c + ch] = scale * sum_{oy,ox} S[(oy*s + ky), (ox*s + kx), ch]      (= P^T 1 without touching P)
 // one warp per output element, lanes over the output locations
 __global__ void __launch_bounds__(256) window_sum_kernel(const float* __restrict__ sum_in, int hw_in, int c, int k, int s,
-                                                         int hw_out, float scale, float* __restrict__ out) {
+                                                         int hw_out, float scale, float* __restrict__ a, int d) {
   const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (i >= k * k * c) return;
@@ -441,11 +432,16 @@ __global__ void __launch_bounds__(256) window_sum_kernel(const float* __restrict
     acc += sum_in[((size_t)(oy * s + ky) * hw_in + ox * s + kx) * c + ch];
   }
   acc = warp_sum(acc);
-  if (lane == 0) out[i] = acc * scale;
+  if (lane == 0) {   // straight into the factor: column d-1, row d-1, and the corner (the constant 1 of [P 1]^T [P 1] / rows)
+    a[(size_t)i * d + (d - 1)] = acc * scale;
+    a[(size_t)(d - 1) * d + i] = acc * scale;
+    if (i == 0) a[(size_t)d * d - 1] = 1.0f;
+  }
 }
 
 __global__ void __launch_bounds__(256) colsum_stage2_kernel(const float* __restrict__ partial, int chunks, int cols, float scale,
-                                                            float* __restrict__ out, int out_stride) {
+                                                            float* __restrict__ out, int out_stride, float* __restrict__ out2,
+                                                            int out2_stride, float* __restrict__ corner) {
   __shared__ float red[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;   // block (32, 8)
   float acc = 0.f;
@@ -458,6 +454,8 @@ __global__ void __launch_bounds__(256) colsum_stage2_kernel(const float* __restr
 #pragma unroll
     for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
     out[(size_t)c * out_stride] = t * scale;
+    if (out2) out2[(size_t)c * out2_stride] = t * scale;   // homogeneous border: the same vector as a row and as a column
+    if (corner && c == 0) *corner = 1.0f;
   }
 }
 
@@ -555,6 +553,51 @@ __global__ void transpose_split_kernel(const float* __restrict__ in, int k_rows,
   }
 }
 
+// all GEMM operand planes of the trunk weights in ONE launch: for layer l (grid.z) a 32 x 32 tile of W_l [K, C] is read
+// once and written as W^T planes [C, ldT] (forward B operand) and, if requested, as W planes [K, ldN] (dgrad B operand)
+struct WeightPlanesJob {
+  const float* w;          // [K, C] fp32 (the weight rows of V_l)
+  int k_rows, c_cols;
+  bf16* t[3];              // W^T planes [C, ld_t]
+  int ld_t;
+  bf16* n[3];              // W planes [K, ld_n] or null
+  int ld_n;
+};
+struct WeightPlanesArgs {
+  WeightPlanesJob job[4];
+};
+__global__ void weight_planes_kernel(const WeightPlanesArgs a) {
+  const WeightPlanesJob& jb = a.job[blockIdx.z];
+  const int k0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  if (k0 >= jb.ld_t || c0 >= jb.c_cols) return;
+  __shared__ float tile[32][33];
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int k = k0 + i, c = c0 + threadIdx.x;
+    const float v = (k < jb.k_rows && c < jb.c_cols) ? jb.w[(size_t)k * jb.c_cols + c] : 0.0f;
+    tile[i][threadIdx.x] = v;
+    if (jb.n[0] != nullptr && k < jb.k_rows && c < jb.ld_n) {
+      bf16 x, y, z;
+      split3(v, x, y, z);
+      const size_t idx = (size_t)k * jb.ld_n + c;
+      jb.n[0][idx] = x;
+      jb.n[1][idx] = y;
+      jb.n[2][idx] = z;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, k = k0 + threadIdx.x;
+    if (c < jb.c_cols && k < jb.ld_t) {
+      bf16 x, y, z;
+      split3(k < jb.k_rows ? tile[threadIdx.x][i] : 0.0f, x, y, z);
+      const size_t idx = (size_t)c * jb.ld_t + k;
+      jb.t[0][idx] = x;
+      jb.t[1][idx] = y;
+      jb.t[2][idx] = z;
+    }
+  }
+}
+
 // categorical sample (inverse CDF on softmax(logits)) or argmax  (policies.py:86-87)
 __global__ void sample_actions_kernel(const float* __restrict__ logits, const float* __restrict__ uniform, uint64_t seed,
                                       uint64_t step, int rows, int num_actions, int greedy, int32_t* __restrict__ actions) {
@@ -611,9 +654,9 @@ int im2col_bf16(const Planes& in, const Planes& out, int rows_total, int hw_in, 
 }
 int col2im_mask_split(const float* dp, const bf16* act_hi, const Planes& out, int n_begin, int n_total, int mask_n, int hw_in, int c,
                       int k, int s, int hw_out, cudaStream_t st) {
-  const long long total = (long long)n_total * hw_in * hw_in * (c / 4);
-  col2im_mask_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dp, act_hi, out, n_begin, n_total, mask_n, hw_in, c, k,
-                                                                           s, hw_out);
+  const int threads = (hw_in * (c / 4) + 31) / 32 * 32;
+  ACX_CHECK(threads <= 256 && (c & 3) == 0, "col2im: row does not fit one CTA");
+  col2im_mask_split_kernel<<<n_total * hw_in, threads, 0, st>>>(dp, act_hi, out, n_begin, mask_n, hw_in, c, k, s, hw_out);
   ACX_LAUNCH_CHECK();
   return 0;
 }
@@ -647,7 +690,7 @@ int heads_gfactor(const float* dheads_fisher, int n_rows, int num_actions, float
   return 0;
 }
 int colsum(const Planes& x, int rows, int cols, float scale, float* partial, int max_chunks, float* out, int out_stride,
-           cudaStream_t st) {
+           cudaStream_t st, float* out2, int out2_stride, float* corner) {
   ACX_CHECK((cols & 7) == 0 && (x.ld & 7) == 0, "colsum: cols and ld must be multiples of 8");
   const int cb = cols < CS_COLBLOCK ? cols : CS_COLBLOCK;
   const int nv = cb >> 3;
@@ -665,7 +708,7 @@ int colsum(const Planes& x, int rows, int cols, float scale, float* partial, int
   }
   colsum_stage1_kernel<<<dim3(chunks, ceil_div(cols, CS_COLBLOCK)), CS_THREADS, smem, st>>>(x, rows, cols, rpc, partial);
   ACX_LAUNCH_CHECK();
-  colsum_stage2_kernel<<<ceil_div(cols, 32), dim3(32, 8), 0, st>>>(partial, chunks, cols, scale, out, out_stride);
+  colsum_stage2_kernel<<<ceil_div(cols, 32), dim3(32, 8), 0, st>>>(partial, chunks, cols, scale, out, out_stride, out2, out2_stride, corner);
   ACX_LAUNCH_CHECK();
   return 0;
 }
@@ -684,14 +727,14 @@ int gram_small(const Planes& x, int rows, int c, float scale, float* partial, in
     gram_stage1_kernel<64><<<chunks, 256, 0, st>>>(x, rows, rpc, partial);
   ACX_LAUNCH_CHECK();
   const int parts = chunks * (c == 32 ? 4 : 1);   // C = 32: four row groups per chunk
-  colsum_stage2_kernel<<<ceil_div(c * c, 32), dim3(32, 8), 0, st>>>(partial, parts, c * c, scale, out, 1);
+  colsum_stage2_kernel<<<ceil_div(c * c, 32), dim3(32, 8), 0, st>>>(partial, parts, c * c, scale, out, 1, nullptr, 0, nullptr);
   ACX_LAUNCH_CHECK();
   return 0;
 }
 
 // batch sum of the conv input (uint8 observations or bf16-plane activations), then the window sums = border of A_l
 int conv_border(const uint8_t* obs_u8, const Planes* act, int n_rows, int hw_in, int c, int k, int s, int hw_out, float scale,
-                float* partial, int max_chunks, float* sum_tmp, float* out, cudaStream_t st) {
+                float* partial, int max_chunks, float* sum_tmp, float* a, int d, cudaStream_t st) {
   const int cols = hw_in * hw_in * c;
   if (obs_u8) {
     ACX_CHECK((cols & 15) == 0, "conv_border: cols must be a multiple of 16");
@@ -701,15 +744,15 @@ int conv_border(const uint8_t* obs_u8, const Planes* act, int n_rows, int hw_in,
     chunks = ceil_div(n_rows, rpc);
     colsum_u8_kernel<<<dim3(chunks, ceil_div(cols, 4096)), 256, 0, st>>>(obs_u8, n_rows, cols, rpc, partial);
     ACX_LAUNCH_CHECK();
-    colsum_stage2_kernel<<<ceil_div(cols, 32), dim3(32, 8), 0, st>>>(partial, chunks, cols, 1.0f, sum_tmp, 1);
+    colsum_stage2_kernel<<<ceil_div(cols, 32), dim3(32, 8), 0, st>>>(partial, chunks, cols, 1.0f, sum_tmp, 1, nullptr, 0, nullptr);
     ACX_LAUNCH_CHECK();
   } else {
     Planes v = *act;
     v.ld = cols;
-    int r = colsum(v, n_rows, cols, 1.0f, partial, max_chunks, sum_tmp, 1, st);
+    int r = colsum(v, n_rows, cols, 1.0f, partial, max_chunks, sum_tmp, 1, st, nullptr, 0, nullptr);
     if (r) return r;
   }
-  window_sum_kernel<<<ceil_div(k * k * c, 8), 256, 0, st>>>(sum_tmp, hw_in, c, k, s, hw_out, scale, out);
+  window_sum_kernel<<<ceil_div(k * k * c, 8), 256, 0, st>>>(sum_tmp, hw_in, c, k, s, hw_out, scale, a, d);
   ACX_LAUNCH_CHECK();
   return 0;
 }
@@ -718,6 +761,32 @@ int transpose_split(const float* in, int k_rows, int c_cols, bf16* p0, bf16* p1,
                     cudaStream_t st) {
   dim3 grid(ceil_div(ld_out, 32), ceil_div(c_cols, 32));
   transpose_split_kernel<<<grid, dim3(32, 8), 0, st>>>(in, k_rows, c_cols, p0, p1, p2, num_planes, ld_out);
+  ACX_LAUNCH_CHECK();
+  return 0;
+}
+int weight_planes(const float* const* w, const int* k_rows, const int* c_cols, bf16* const (*t)[3], const int* ld_t,
+                  bf16* const (*n)[3], const int* ld_n, int num_layers, cudaStream_t st) {
+  ACX_CHECK(num_layers >= 1 && num_layers <= 4, "weight_planes: 1..4 layers");
+  WeightPlanesArgs a;
+  int max_k = 0, max_c = 0;
+  for (int i = 0; i < 4; ++i) {
+    const int s = i < num_layers ? i : 0;
+    a.job[i].w = w[s];
+    a.job[i].k_rows = k_rows[s];
+    a.job[i].c_cols = c_cols[s];
+    a.job[i].ld_t = ld_t[s];
+    a.job[i].ld_n = ld_n[s];
+    for (int q = 0; q < 3; ++q) {
+      a.job[i].t[q] = t[s][q];
+      a.job[i].n[q] = n[s][q];
+    }
+    if (i < num_layers) {
+      max_k = ld_t[s] > max_k ? ld_t[s] : max_k;
+      max_c = ld_n[s] > c_cols[s] ? (ld_n[s] > max_c ? ld_n[s] : max_c) : (c_cols[s] > max_c ? c_cols[s] : max_c);
+    }
+  }
+  dim3 grid(ceil_div(max_k, 32), ceil_div(max_c, 32), num_layers);
+  weight_planes_kernel<<<grid, dim3(32, 8), 0, st>>>(a);
   ACX_LAUNCH_CHECK();
   return 0;
 }

@@ -37,12 +37,14 @@ int heads_bwd(const float* dheads, const float* vpol, const float* vval, const P
               int num_actions, const Planes& dpre4, float* gpol, float* gval, cudaStream_t st);
 int heads_gfactor(const float* dheads_fisher, int n_rows, int num_actions, float* g_pol, float* g_val, cudaStream_t st);
 int colsum(const Planes& x, int rows, int cols, float scale, float* partial, int max_chunks, float* out, int out_stride,
-           cudaStream_t st);
+           cudaStream_t st, float* out2 = nullptr, int out2_stride = 0, float* corner = nullptr);
 int gram_small(const Planes& x, int rows, int c, float scale, float* partial, int max_chunks, float* out, cudaStream_t st);
 int conv_border(const uint8_t* obs_u8, const Planes* act, int n_rows, int hw_in, int c, int k, int s, int hw_out, float scale,
-                float* partial, int max_chunks, float* sum_tmp, float* out, cudaStream_t st);
+                float* partial, int max_chunks, float* sum_tmp, float* a, int d, cudaStream_t st);
 int transpose_split(const float* in, int k_rows, int c_cols, bf16* p0, bf16* p1, bf16* p2, int num_planes, int ld_out,
                     cudaStream_t st);
+int weight_planes(const float* const* w, const int* k_rows, const int* c_cols, bf16* const (*t)[3], const int* ld_t,
+                  bf16* const (*n)[3], const int* ld_n, int num_layers, cudaStream_t st);
 int sample_actions(const float* logits, const float* uniform, uint64_t seed, uint64_t step, int rows, int num_actions, int greedy,
                    int32_t* actions, cudaStream_t st);
 int split_planes(const float* in, int ld_in, int rows, int cols, float scale, bf16* p0, bf16* p1, bf16* p2, int num_planes,
@@ -75,6 +77,8 @@ int compute_dampings(const float* const* d_a_ptrs, const float* const* d_g_ptrs,
                      const float* d_lambda, int num_layers, float* d_damp, cudaStream_t st);
 int spd_inverse_batched(const InvJob* h_jobs, const InvJob* d_jobs, int num_jobs, const Sched* sched, const float* d_damp,
                         cudaStream_t st);
+int sched_step(Sched* s, float lr_start, float lr_end, double decay_steps, float* out_lr, int gs_inc, int ncov_inc,
+               float ema_decay, int zero_debias, cudaStream_t st);
 int sched_begin(Sched* s, float lr_start, float lr_end, double decay_steps, float* out_lr, cudaStream_t st);
 int sched_advance(Sched* s, int gs_inc, int ncov_inc, float ema_decay, int zero_debias, cudaStream_t st);
 int dot_partial(const float* a, const float* b, size_t count, float* partial, int num_partials, cudaStream_t st);

@@ -452,13 +452,23 @@ static void mark(acx_learner* l, int k, cudaStream_t st) {
   } while (0)
 
 static int refresh_weight_planes(acx_learner* l, cudaStream_t st) {
+  const float* w[4];
+  int kr[4], cc[4], ldt[4], ldn[4];
+  bf16* t[4][3];
+  bf16* n[4][3];
   for (int i = 0; i < 4; ++i) {
     const Layer& L = l->L[i];
-    ACX_TRY(transpose_split(l->params + L.off, L.K, L.C, l->wT[i].p[0], l->wT[i].p[1], l->wT[i].p[2], 3, l->wT[i].ld, st));
-    if (i > 0)
-      ACX_TRY(split_planes(l->params + L.off, L.C, L.K, L.C, 1.0f, l->wN[i].p[0], l->wN[i].p[1], l->wN[i].p[2], 3, l->wN[i].ld, st));
+    w[i] = l->params + L.off;
+    kr[i] = L.K;
+    cc[i] = L.C;
+    ldt[i] = l->wT[i].ld;
+    ldn[i] = l->wN[i].ld;
+    for (int q = 0; q < 3; ++q) {
+      t[i][q] = l->wT[i].p[q];
+      n[i][q] = i > 0 ? l->wN[i].p[q] : nullptr;   // conv1 has no input gradient
+    }
   }
-  return 0;
+  return weight_planes(w, kr, cc, t, ldt, n, ldn, 4, st);
 }
 
 // Nature-CNN forward on `rows` observations (envs/atari/model.py:173-217): im2col + GEMM with bias/ReLU epilogues
@@ -496,8 +506,9 @@ static int input_factor(acx_learner* l, int fac, const Planes& x, int rows, int 
   o.c = dst;
   o.ldc = d;
   ACX_TRY(run_gemm(l, x, x, 1, K, K, rows, l->lvl_factor, scale_sq, 1, o, st));
-  ACX_TRY(colsum(x, rows, K, scale_lin, l->colsum_partial, kColsumChunks, l->colsum_tmp, 1, st));
-  ACX_TRY(homog_border(dst, d, l->colsum_tmp, st));
+  // homogeneous border straight from the column sums: column d-1 (stride d), row d-1 (stride 1), corner 1
+  ACX_TRY(colsum(x, rows, K, scale_lin, l->colsum_partial, kColsumChunks, dst + (d - 1), d, st, dst + (size_t)(d - 1) * d, 1,
+                 dst + (size_t)d * d - 1));
   return 0;
 }
 
@@ -513,8 +524,7 @@ static int conv_input_factor(acx_learner* l, int li, const Planes& patches, cons
   o.ldc = d;
   ACX_TRY(run_gemm(l, patches, patches, 1, L.K, L.K, rows, l->lvl_factor, scale_sq, 1, o, st));
   ACX_TRY(conv_border(obs_u8, act_in, l->N, L.hw_in, L.cin, L.k, L.s, L.hw_out, border_scale, l->colsum_partial, kBorderChunks,
-                      l->colsum_tmp + 4096, l->colsum_tmp, st));
-  ACX_TRY(homog_border(dst, d, l->colsum_tmp, st));
+                      l->colsum_tmp + 4096, dst, d, st));
   return 0;
 }
 
@@ -675,12 +685,14 @@ static int issue_phase2(acx_learner* l, const Plan2& p, cudaStream_t st) {
   mark(l, 5, st);
   if (c.world_size > 1) ACX_TRY(scale_f32(l->bucket, l->bucket_floats, 1.0f / (float)c.world_size, st));
   ACX_CUDA(cudaMemcpyAsync(l->scalars, l->bscalars, 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  ACX_TRY(sched_begin(l->sched, c.lr_start, c.lr_end, c.lr_decay_steps, l->scalars + 7, st));
+  // one launch for the whole schedule transition (kfac_utils.py:38-53): lr from the step the update starts with, then
+  // global_step += (cold ? 2 : 1) [A2C: 1], covariance counter += (cold ? 0 : 1)
+  ACX_TRY(sched_step(l->sched, c.lr_start, c.lr_end, c.lr_decay_steps, l->scalars + 7, p.a2c ? 1 : (p.cold ? 2 : 1),
+                     (p.a2c || p.cold) ? 0 : 1, c.cov_ema_decay, 1, st));
   if (p.a2c) {   // ClipGlobalNorm(RMSProp)   a2c_acktr.py:250-251
     ACX_TRY(dot_partial(l->grads, l->grads, P, l->dot_partials, kDotPartials, st));
     ACX_TRY(rmsprop_clip_step(l->params, l->accum, l->grads, P, l->dot_partials, kDotPartials, l->sched, c.rms_decay,
                               c.rms_epsilon, c.clip_norm, l->scalars + 6, st));
-    ACX_TRY(sched_advance(l->sched, 1, 0, c.cov_ema_decay, 1, st));
     ACX_TRY(refresh_weight_planes(l, st));
     for (int k = 6; k <= 9; ++k) mark(l, k, st);
     return 0;
@@ -689,10 +701,8 @@ static int issue_phase2(acx_learner* l, const Plan2& p, cudaStream_t st) {
     ACX_TRY(dot_partial(l->grads, l->grads, P, l->dot_partials, kDotPartials, st));
     ACX_TRY(momentum_clip_step(l->params, l->accum, l->grads, P, l->dot_partials, kDotPartials, c.cold_lr, c.cold_momentum,
                                c.clip_norm, l->scalars + 6, st));
-    ACX_TRY(sched_advance(l->sched, 1, 0, c.cov_ema_decay, 1, st));
   } else {          // kfac_utils.py:44: all covariance updates
     ACX_TRY(ema_update(l->sums, l->stats, l->factor_floats, c.cov_ema_decay, 1.0f, st));
-    ACX_TRY(sched_advance(l->sched, 0, 1, c.cov_ema_decay, 1, st));
   }
   mark(l, 6, st);
   if (p.invert) {
@@ -707,7 +717,6 @@ static int issue_phase2(acx_learner* l, const Plan2& p, cudaStream_t st) {
     ACX_TRY(kfac_step(l->params, l->velocity, l->precon, P, l->dot_partials, kDotPartials, l->sched, c.momentum,
                       c.norm_constraint, l->scalars + 4, st));
   }
-  ACX_TRY(sched_advance(l->sched, 1, 0, c.cov_ema_decay, 1, st));
   if (p.refresh) ACX_TRY(refresh_weight_planes(l, st));
   if (!p.kfac_apply) mark(l, 8, st);
   mark(l, 9, st);

@@ -375,12 +375,18 @@ def run_native(args, rank, world, local_rank):
                         "buffered), loss scalars read back every step"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel<1>: conv1 input-factor SYRK A1 = P1^T P1 (256x256, K=%d), the largest launch of the update" % k_rows,
-                     "achieved": syrk_tflops, "peak": peaks["tensor_burst"], "unit": "TFLOP/s",
-                     "frac": syrk_tflops / peaks["tensor_burst"], "traffic": None,
-                     "algorithmic_gflop_per_launch": syrk_flops / 1e9, "launch_ms": syrk_ms,
-                     "peak_source": peaks["source"] + ", burst bf16 (kernel timed alone)",
-                     "hbm_GB/s_of_this_launch": k_rows * 256 * 2 / (syrk_ms * 1e-3) / 1e9,
+        # the kernel's arithmetic intensity is 16.8 GFLOP / 131 MB = 128 FLOP/B, below the machine balance
+        # (1665 TFLOP/s / 6.56 TB/s = 254 FLOP/B): it is bound by streaming the patch matrix from HBM once
+        "roofline": {"bound": "hbm",
+                     "kernel": "gemm_tc_kernel<1> (SYRK panel mode): conv1 input factor A1 = P1^T P1, 256x256 output, K=%d patch rows - "
+                               "the largest launch of the update" % k_rows,
+                     "achieved": k_rows * 256 * 2 / (syrk_ms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                     "frac": k_rows * 256 * 2 / (syrk_ms * 1e-3) / 1e9 / peaks["hbm"],
+                     "traffic": 135727104,   # dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r1_prof_syrk_conv1_panel_details.txt
+                     "algorithmic_bytes_per_launch": k_rows * 256 * 2, "launch_ms": syrk_ms,
+                     "peak_source": peaks["source"] + ", HBM copy bandwidth",
+                     "tensor": {"algorithmic_gflop_per_launch": syrk_flops / 1e9, "achieved_tflops": syrk_tflops,
+                                "frac_of_burst_bf16_peak": syrk_tflops / peaks["tensor_burst"]},
                      "stage_ms": stage_ms,
                      "stage_tflops": {k: flops[k] / (stage_ms[k] * 1e-3) / 1e12 for k in ("forward", "backward", "factors", "precondition")
                                       if stage_ms.get(k, 0) > 0}},
