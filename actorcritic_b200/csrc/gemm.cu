@@ -616,11 +616,12 @@ __global__ void __launch_bounds__(256) gemm_finalize_kernel(OutParams o, const f
   if (threadIdx.y == 0 && n < o.n) store_value(o, m, n, finish_value(o, m, n, acc));
 }
 
-// symmetric results: only upper 128-tiles were computed.  One CTA per 32 x 32 block pair (bi <= bj): the upper block is
-// reduced over the splits with row-contiguous reads, stored, transposed through shared memory and stored again as the
-// mirrored block - both stores are row contiguous (the per-element mirror read of the generic kernel is not).
-__global__ void __launch_bounds__(256) gemm_finalize_sym_kernel(OutParams o, const float* __restrict__ ws, int ws_ld,
-                                                                long long ws_split_stride, int splits, int nblk) {
+// symmetric results: only upper 128-tiles were computed.  One CTA (32 x 32 threads) per 32 x 32 block pair (bi <= bj):
+// every thread reduces one element of the upper block over the splits (row-contiguous, independent loads), stores it,
+// and the block is transposed through shared memory and stored again as the mirrored block - both stores are row
+// contiguous (the per-element mirror read of the generic kernel is not).
+__global__ void __launch_bounds__(1024) gemm_finalize_sym_kernel(OutParams o, const float* __restrict__ ws, int ws_ld,
+                                                                 long long ws_split_stride, int splits, int nblk) {
   __shared__ float tile[32][33];
   int t = blockIdx.x, bi = 0, cnt = nblk;
   while (t >= cnt) {
@@ -630,25 +631,30 @@ __global__ void __launch_bounds__(256) gemm_finalize_sym_kernel(OutParams o, con
   }
   const int bj = bi + t;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-#pragma unroll
-  for (int rr = 0; rr < 4; ++rr) {
-    const int r = ty + 8 * rr;
-    const int m = bi * 32 + r, n = bj * 32 + tx;
+  {
+    const int m = bi * 32 + ty, n = bj * 32 + tx;
     float acc = 0.0f;
     if (m < o.m && n < o.n) {
       const float* src = ws + (size_t)m * ws_ld + n;
-      for (int s = 0; s < splits; ++s) acc += src[(size_t)s * ws_split_stride];
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int s = 0;
+      for (; s + 3 < splits; s += 4) {   // fixed association order: deterministic
+        a0 += src[(size_t)s * ws_split_stride];
+        a1 += src[(size_t)(s + 1) * ws_split_stride];
+        a2 += src[(size_t)(s + 2) * ws_split_stride];
+        a3 += src[(size_t)(s + 3) * ws_split_stride];
+      }
+      for (; s < splits; ++s) a0 += src[(size_t)s * ws_split_stride];
+      acc = (a0 + a1) + (a2 + a3);
       store_value(o, m, n, finish_value(o, m, n, acc));
     }
-    tile[r][tx] = acc;
+    tile[ty][tx] = acc;
   }
   if (bi == bj) return;
   __syncthreads();
-#pragma unroll
-  for (int rr = 0; rr < 4; ++rr) {
-    const int r = ty + 8 * rr;
-    const int m = bj * 32 + r, n = bi * 32 + tx;
-    if (m < o.m && n < o.n) store_value(o, m, n, finish_value(o, m, n, tile[tx][r]));
+  {
+    const int m = bj * 32 + ty, n = bi * 32 + tx;
+    if (m < o.m && n < o.n) store_value(o, m, n, finish_value(o, m, n, tile[tx][ty]));
   }
 }
 
@@ -959,9 +965,9 @@ static int gemm_tc(const acx_gemm_t* g, cudaStream_t st) {
   const int smem = SMEM_FIXED + p.stages * stage_bytes;
   int r = major == 0 ? launch_tc<0>(ta, tb, p, grid, smem, st) : launch_tc<1>(ta, tb, p, grid, smem, st);
   if (r) return r;
-  if (pl.to_ws && g->symmetric && g->n >= 384 && pl.splits <= 16) {   // enough 32 x 32 block pairs to fill the GPU
+  if (pl.to_ws && g->symmetric && g->n > 64) {
     const int nblk = ceil_div(g->n, 32);
-    gemm_finalize_sym_kernel<<<nblk * (nblk + 1) / 2, 256, 0, st>>>(p.out, g->workspace, p.ws_ld, p.ws_split_stride, pl.splits, nblk);
+    gemm_finalize_sym_kernel<<<nblk * (nblk + 1) / 2, 1024, 0, st>>>(p.out, g->workspace, p.ws_ld, p.ws_split_stride, pl.splits, nblk);
     ACX_LAUNCH_CHECK();
   } else if (pl.to_ws) {
     const int lanes = pl.splits >= 8 ? 8 : (pl.splits >= 4 ? 4 : (pl.splits >= 2 ? 2 : 1));

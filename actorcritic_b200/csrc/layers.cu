@@ -717,7 +717,8 @@ int colsum(const Planes& x, int rows, int cols, float scale, float* partial, int
 int gram_small(const Planes& x, int rows, int c, float scale, float* partial, int max_chunks, float* out, cudaStream_t st) {
   ACX_CHECK(c == 32 || c == 64, "gram_small: 32 or 64 columns");
   int chunks = ceil_div(rows, 256);
-  if (chunks > max_chunks) chunks = max_chunks;
+  const int cap = c == 32 ? max_chunks / 2 : max_chunks;   // C = 32 writes four partials per chunk: keep stage 2 short
+  if (chunks > cap) chunks = cap;
   if (chunks < 1) chunks = 1;
   const int rpc = ceil_div(rows, chunks);
   chunks = ceil_div(rows, rpc);
