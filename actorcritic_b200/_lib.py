@@ -44,7 +44,8 @@ class LearnerConfig(ctypes.Structure):
                 ("cold_lr", ctypes.c_float), ("cold_momentum", ctypes.c_float), ("clip_norm", ctypes.c_float),
                 ("rms_decay", ctypes.c_float), ("rms_epsilon", ctypes.c_float),
                 ("num_locations_mode", ctypes.c_int), ("world_size", ctypes.c_int), ("gemm_impl", ctypes.c_int),
-                ("precision", ctypes.c_int), ("use_graphs", ctypes.c_int), ("seed", ctypes.c_uint64)]
+                ("precision", ctypes.c_int), ("use_graphs", ctypes.c_int), ("num_lanes", ctypes.c_int),
+                ("seed", ctypes.c_uint64)]
 
 
 # every symbol include/acx.h declares: name -> (restype, argtypes)

@@ -48,6 +48,16 @@ struct Arena {
   }
 };
 
+// Per-lane scratch: kernels of different lanes run concurrently (streams forked from the caller's stream, also inside a
+// captured graph), so each lane owns its split-K workspace and reduction partials.
+struct Scratch {
+  float* ws = nullptr;
+  size_t ws_bytes = 0;
+  float* colsum_partial = nullptr;
+  float* colsum_tmp = nullptr;
+};
+constexpr int kMaxLanes = 3;   // lane 0 = the caller's stream (forward, loss, dgrad chain); 1 = input factors; 2 = wgrad + output factors
+
 struct GraphKey {
   int phase, variant;
   const void* p0;
@@ -105,9 +115,13 @@ struct acx_learner {
   size_t dgrad_chunk_bytes;
   Planes wT[4], wN[4];
   Planes Vp, Wt;
-  float *colsum_partial, *colsum_tmp, *dot_partials;
-  float* ws;
-  size_t ws_bytes;
+  float* dot_partials;
+  Scratch scr[kMaxLanes];
+  int lanes = 1;                          // active lanes (1 = everything on the caller's stream)
+  cudaStream_t side[kMaxLanes - 1] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> lane_events;   // fork / join events (timing disabled), reused every update
+  size_t ev_next = 0;
+  bool lane_forked[kMaxLanes] = {false, false, false};
   // host mirror of the schedule
   int64_t gs, ncov;
   bool inverses_valid;
@@ -321,13 +335,16 @@ static size_t layout(acx_learner* l, uint8_t* base) {
   }
   l->Vp = take_planes(ar, 3, dmax, pad8(cmax));
   l->Wt = take_planes(ar, 3, cmax, pad8(dmax));
-  l->colsum_partial = f32(std::max(std::max((size_t)kColsumChunks * (size_t)std::max(49 * c3, 576), (size_t)kBorderChunks * 28224),
-                                   (size_t)kGramChunks * 4096));
-  l->colsum_tmp = f32(4096 + 28224 + 8);   // [0,4096): border / column-sum vectors, then the batch-summed conv input
   l->dot_partials = f32(kDotPartials);
   const size_t kpad = align_up((size_t)49 * c3, 128);
-  l->ws_bytes = std::max<size_t>((size_t)48 << 20, kpad * kpad * sizeof(float) + (1 << 20));
-  l->ws = reinterpret_cast<float*>(ar.take(l->ws_bytes));
+  for (int i = 0; i < kMaxLanes; ++i) {
+    Scratch& sc = l->scr[i];
+    sc.colsum_partial = f32(std::max(std::max((size_t)kColsumChunks * (size_t)std::max(49 * c3, 576), (size_t)kBorderChunks * 28224),
+                                     (size_t)kGramChunks * 4096));
+    sc.colsum_tmp = f32(4096 + 28224 + 8);   // [0,4096): border / column-sum vectors, then the batch-summed conv input
+    sc.ws_bytes = std::max<size_t>((size_t)48 << 20, kpad * kpad * sizeof(float) + (1 << 20));
+    sc.ws = reinterpret_cast<float*>(ar.take(sc.ws_bytes));
+  }
   return align_up(ar.used, 256);
 }
 
@@ -378,6 +395,48 @@ static void register_buffers(acx_learner* l) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// lanes: a lane = a stream + its scratch.  Lane 0 is the caller's stream; side lanes are forked from it with events and
+// joined back before a phase returns, so the caller still sees one stream (and a stream capture records the fork /
+// join structure as parallel graph branches).
+// ------------------------------------------------------------------------------------------------
+struct Lane {
+  cudaStream_t st;
+  const Scratch* sc;
+  int index;
+};
+
+static Lane lane_of(acx_learner* l, int i, cudaStream_t main_st) {
+  if (i >= l->lanes || l->profiling) i = 0;   // stage timing brackets serial work on the caller's stream
+  return Lane{i == 0 ? main_st : l->side[i - 1], &l->scr[i], i};
+}
+
+// everything enqueued on `from` so far happens before whatever is enqueued on `to` from now on
+static int order_after(acx_learner* l, cudaStream_t from, cudaStream_t to) {
+  if (from == to) return 0;
+  if (l->ev_next == l->lane_events.size()) {
+    cudaEvent_t e;
+    ACX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    l->lane_events.push_back(e);
+  }
+  cudaEvent_t e = l->lane_events[l->ev_next++];
+  ACX_CUDA(cudaEventRecord(e, from));
+  ACX_CUDA(cudaStreamWaitEvent(to, e, 0));
+  return 0;
+}
+// fork: `ln` continues after everything issued on `main_st` so far; join: `main_st` waits for the lane (a lane that was
+// never forked in this phase has nothing to wait for - and inside a stream capture it is not part of the graph)
+static int fork_lane(acx_learner* l, cudaStream_t main_st, const Lane& ln) {
+  if (ln.index == 0) return 0;
+  l->lane_forked[ln.index] = true;
+  return order_after(l, main_st, ln.st);
+}
+static int join_lane(acx_learner* l, const Lane& ln, cudaStream_t main_st) {
+  if (ln.index == 0 || !l->lane_forked[ln.index]) return 0;
+  l->lane_forked[ln.index] = false;
+  return order_after(l, ln.st, main_st);
+}
+
+// ------------------------------------------------------------------------------------------------
 // GEMM helper: picks the plane pairs from the precision level (pairs (i,j) with i + j <= level)
 // ------------------------------------------------------------------------------------------------
 struct GemmOut {
@@ -391,7 +450,7 @@ struct GemmOut {
 };
 
 static int run_gemm(acx_learner* l, const Planes& a, const Planes& b, int trans, int m, int n, int k, int level, float alpha,
-                    int symmetric, const GemmOut& o, cudaStream_t st) {
+                    int symmetric, const GemmOut& o, const Lane& ln) {
   acx_gemm_t g;
   memset(&g, 0, sizeof(g));
   for (int i = 0; i < a.n; ++i) g.a.planes[i] = a.p[i];
@@ -433,9 +492,9 @@ static int run_gemm(acx_learner* l, const Planes& a, const Planes& b, int trans,
   g.mask_ld = o.mask_ld;
   g.mask_rows = o.mask_rows;
   g.splits = 0;
-  g.workspace = l->ws;
-  g.workspace_bytes = l->ws_bytes;
-  return gemm_dispatch(&g, l->cfg.gemm_impl, st);
+  g.workspace = ln.sc->ws;
+  g.workspace_bytes = ln.sc->ws_bytes;
+  return gemm_dispatch(&g, l->cfg.gemm_impl, ln.st);
 }
 
 // stage boundaries: mark k closes stage k-1 (phase 1: marks 0..4, phase 2: marks 5..9)
@@ -471,43 +530,17 @@ static int refresh_weight_planes(acx_learner* l, cudaStream_t st) {
   return weight_planes(w, kr, cc, t, ldt, n, ldn, 4, st);
 }
 
-// Nature-CNN forward on `rows` observations (envs/atari/model.py:173-217): im2col + GEMM with bias/ReLU epilogues
-static int forward(acx_learner* l, const uint8_t* obs, int rows, cudaStream_t st) {
-  const int c3 = l->c3;
-  GemmOut o;
-  o.relu = 1;
-  // conv1: raw bytes are exact in bf16; the /255 of envs/atari/model.py:93 is the GEMM alpha
-  ACX_TRY(im2col_conv1(obs, l->P1.p[0], rows * 400, st));
-  o.bias = l->params + l->L[0].off + (size_t)l->L[0].K * l->L[0].C;
-  o.planes = &l->act1;
-  ACX_TRY(run_gemm(l, l->P1, l->wT[0], 0, rows * 400, 32, 256, l->lvl_fwd, 1.0f / 255.0f, 0, o, st));
-  ACX_TRY(im2col_bf16(l->act1, l->P2, rows * 81, 20, 32, 4, 2, 9, st));
-  o.bias = l->params + l->L[1].off + (size_t)l->L[1].K * l->L[1].C;
-  o.planes = &l->act2;
-  ACX_TRY(run_gemm(l, l->P2, l->wT[1], 0, rows * 81, 64, 512, l->lvl_fwd, 1.0f, 0, o, st));
-  ACX_TRY(im2col_bf16(l->act2, l->P3, rows * 49, 9, 64, 3, 1, 7, st));
-  o.bias = l->params + l->L[2].off + (size_t)l->L[2].K * l->L[2].C;
-  o.planes = &l->act3;
-  ACX_TRY(run_gemm(l, l->P3, l->wT[2], 0, rows * 49, c3, 576, l->lvl_fwd, 1.0f, 0, o, st));
-  // fc4 on the (h, w, c)-flattened conv3 output (nn.py:125-126)
-  o.bias = l->params + l->L[3].off + (size_t)l->L[3].K * l->L[3].C;
-  o.planes = &l->act4;
-  ACX_TRY(run_gemm(l, with_ld(l->act3, 49 * c3), l->wT[3], 0, rows, 512, 49 * c3, l->lvl_fwd, 1.0f, 0, o, st));
-  ACX_TRY(heads_fwd(l->act4, l->params + l->L[4].off, l->params + l->L[5].off, rows, l->A, l->logits, l->values, st));
-  return 0;
-}
-
 // input factor of layer `li` from the patch/input planes `x` (first `rows` rows, K columns): SYRK + homogeneous border
 static int input_factor(acx_learner* l, int fac, const Planes& x, int rows, int K, float scale_sq, float scale_lin,
-                        cudaStream_t st) {
+                        const Lane& ln) {
   const int d = K + 1;
   float* dst = l->stats + l->aoff[fac];
   GemmOut o;
   o.c = dst;
   o.ldc = d;
-  ACX_TRY(run_gemm(l, x, x, 1, K, K, rows, l->lvl_factor, scale_sq, 1, o, st));
+  ACX_TRY(run_gemm(l, x, x, 1, K, K, rows, l->lvl_factor, scale_sq, 1, o, ln));
   // homogeneous border straight from the column sums: column d-1 (stride d), row d-1 (stride 1), corner 1
-  ACX_TRY(colsum(x, rows, K, scale_lin, l->colsum_partial, kColsumChunks, dst + (d - 1), d, st, dst + (size_t)(d - 1) * d, 1,
+  ACX_TRY(colsum(x, rows, K, scale_lin, ln.sc->colsum_partial, kColsumChunks, dst + (d - 1), d, ln.st, dst + (size_t)(d - 1) * d, 1,
                  dst + (size_t)d * d - 1));
   return 0;
 }
@@ -515,34 +548,86 @@ static int input_factor(acx_learner* l, int fac, const Planes& x, int rows, int 
 // input factor of a conv layer: SYRK over the patch matrix; the homogeneous border P^T 1 / rows comes from the batch-summed
 // layer input through window sums (one pass over the un-im2col'd input instead of a pass over the k^2/s^2 times larger P)
 static int conv_input_factor(acx_learner* l, int li, const Planes& patches, const uint8_t* obs_u8, const Planes* act_in,
-                             float scale_sq, float border_scale, cudaStream_t st) {
+                             float scale_sq, float border_scale, const Lane& ln) {
   const Layer& L = l->L[li];
   const int d = L.K + 1, rows = l->N * L.T;
   float* dst = l->stats + l->aoff[li];
   GemmOut o;
   o.c = dst;
   o.ldc = d;
-  ACX_TRY(run_gemm(l, patches, patches, 1, L.K, L.K, rows, l->lvl_factor, scale_sq, 1, o, st));
-  ACX_TRY(conv_border(obs_u8, act_in, l->N, L.hw_in, L.cin, L.k, L.s, L.hw_out, border_scale, l->colsum_partial, kBorderChunks,
-                      l->colsum_tmp + 4096, dst, d, st));
+  ACX_TRY(run_gemm(l, patches, patches, 1, L.K, L.K, rows, l->lvl_factor, scale_sq, 1, o, ln));
+  ACX_TRY(conv_border(obs_u8, act_in, l->N, L.hw_in, L.cin, L.k, L.s, L.hw_out, border_scale, ln.sc->colsum_partial, kBorderChunks,
+                      ln.sc->colsum_tmp + 4096, dst, d, ln.st));
+  return 0;
+}
+
+// the five input factors, each as soon as its operand exists: `stage` = 0 P1, 1 P2, 2 P3, 3 act3, 4 act4
+static int input_factor_stage(acx_learner* l, int stage, const Lane& ln) {
+  const int N = l->N, c3 = l->c3;
+  const float r1 = 1.0f / (float)(N * 400), r2 = 1.0f / (float)(N * 81), r3 = 1.0f / (float)(N * 49), r4 = 1.0f / (float)N;
+  switch (stage) {
+    case 0: return conv_input_factor(l, 0, l->P1, l->obs, nullptr, r1 / (255.0f * 255.0f), r1 / 255.0f, ln);
+    case 1: return conv_input_factor(l, 1, l->P2, nullptr, &l->act1, r2, r2, ln);
+    case 2: return conv_input_factor(l, 2, l->P3, nullptr, &l->act2, r3, r3, ln);
+    case 3: return input_factor(l, 3, with_ld(l->act3, 49 * c3), N, 49 * c3, r4, r4, ln);
+    default: return input_factor(l, 4, l->act4, N, 512, r4, r4, ln);
+  }
+}
+
+// Nature-CNN forward on `rows` observations (envs/atari/model.py:173-217): im2col + GEMM with bias/ReLU epilogues.
+// With `fac` (an ACKTR update past the cold phase) every input factor is issued on lane `fac` the moment its operand
+// is complete, so the factor SYRKs overlap the rest of the forward and the whole backward.
+static int forward(acx_learner* l, const uint8_t* obs, int rows, const Lane& ln, const Lane* fac) {
+  const int c3 = l->c3;
+  cudaStream_t st = ln.st;
+  auto factor = [&](int stage) -> int {
+    if (!fac) return 0;
+    ACX_TRY(fork_lane(l, st, *fac));
+    return input_factor_stage(l, stage, *fac);
+  };
+  GemmOut o;
+  o.relu = 1;
+  // conv1: raw bytes are exact in bf16; the /255 of envs/atari/model.py:93 is the GEMM alpha
+  ACX_TRY(im2col_conv1(obs, l->P1.p[0], rows * 400, st));
+  ACX_TRY(factor(0));
+  o.bias = l->params + l->L[0].off + (size_t)l->L[0].K * l->L[0].C;
+  o.planes = &l->act1;
+  ACX_TRY(run_gemm(l, l->P1, l->wT[0], 0, rows * 400, 32, 256, l->lvl_fwd, 1.0f / 255.0f, 0, o, ln));
+  ACX_TRY(im2col_bf16(l->act1, l->P2, rows * 81, 20, 32, 4, 2, 9, st));
+  ACX_TRY(factor(1));
+  o.bias = l->params + l->L[1].off + (size_t)l->L[1].K * l->L[1].C;
+  o.planes = &l->act2;
+  ACX_TRY(run_gemm(l, l->P2, l->wT[1], 0, rows * 81, 64, 512, l->lvl_fwd, 1.0f, 0, o, ln));
+  ACX_TRY(im2col_bf16(l->act2, l->P3, rows * 49, 9, 64, 3, 1, 7, st));
+  ACX_TRY(factor(2));
+  o.bias = l->params + l->L[2].off + (size_t)l->L[2].K * l->L[2].C;
+  o.planes = &l->act3;
+  ACX_TRY(run_gemm(l, l->P3, l->wT[2], 0, rows * 49, c3, 576, l->lvl_fwd, 1.0f, 0, o, ln));
+  ACX_TRY(factor(3));
+  // fc4 on the (h, w, c)-flattened conv3 output (nn.py:125-126)
+  o.bias = l->params + l->L[3].off + (size_t)l->L[3].K * l->L[3].C;
+  o.planes = &l->act4;
+  ACX_TRY(run_gemm(l, with_ld(l->act3, 49 * c3), l->wT[3], 0, rows, 512, 49 * c3, l->lvl_fwd, 1.0f, 0, o, ln));
+  ACX_TRY(factor(4));
+  ACX_TRY(heads_fwd(l->act4, l->params + l->L[4].off, l->params + l->L[5].off, rows, l->A, l->logits, l->values, st));
   return 0;
 }
 
 // weight gradient V_l[:K] = X^T g over the true-loss rows, bias row = column sums of g
-static int weight_grad(acx_learner* l, int li, const Planes& x, const Planes& g, int rows, float alpha, cudaStream_t st) {
+static int weight_grad(acx_learner* l, int li, const Planes& x, const Planes& g, int rows, float alpha, const Lane& ln) {
   const Layer& L = l->L[li];
   GemmOut o;
   o.c = l->grads + L.off;
   o.ldc = L.C;
-  ACX_TRY(run_gemm(l, x, g, 1, L.K, L.C, rows, l->lvl_bwd, alpha, 0, o, st));
-  ACX_TRY(colsum(g, rows, L.C, 1.0f, l->colsum_partial, kColsumChunks, l->grads + L.off + (size_t)L.K * L.C, 1, st));
+  ACX_TRY(run_gemm(l, x, g, 1, L.K, L.C, rows, l->lvl_bwd, alpha, 0, o, ln));
+  ACX_TRY(colsum(g, rows, L.C, 1.0f, ln.sc->colsum_partial, kColsumChunks, l->grads + L.off + (size_t)L.K * L.C, 1, ln.st));
   return 0;
 }
 
 // input gradient of conv layer li: dP = g W^T (fp32) then col2im + ReLU mask of the layer below + bf16 split.  Done in
 // chunks of samples (optional, see kDgradChunkBytes: an L2-sized chunk keeps dP on chip, but measured slower).
 static int conv_dgrad(acx_learner* l, int li, const Planes& g, const bf16* act_below_hi, const Planes& g_below, int samples,
-                      cudaStream_t st) {
+                      const Lane& ln) {
   const Layer& L = l->L[li];
   const size_t per_sample = (size_t)L.T * L.K * sizeof(float);
   int chunk = (int)(l->dgrad_chunk_bytes / per_sample);
@@ -552,30 +637,37 @@ static int conv_dgrad(acx_learner* l, int li, const Planes& g, const bf16* act_b
     GemmOut o;
     o.c = l->dP;
     o.ldc = L.K;
-    ACX_TRY(run_gemm(l, offset_rows(g, (size_t)n0 * L.T), l->wN[li], 0, ns * L.T, L.K, L.C, l->lvl_bwd, 1.0f, 0, o, st));
-    ACX_TRY(col2im_mask_split(l->dP, act_below_hi, g_below, n0, ns, l->N, L.hw_in, L.cin, L.k, L.s, L.hw_out, st));
+    ACX_TRY(run_gemm(l, offset_rows(g, (size_t)n0 * L.T), l->wN[li], 0, ns * L.T, L.K, L.C, l->lvl_bwd, 1.0f, 0, o, ln));
+    ACX_TRY(col2im_mask_split(l->dP, act_below_hi, g_below, n0, ns, l->N, L.hw_in, L.cin, L.k, L.s, L.hw_out, ln.st));
   }
   return 0;
 }
 
 // output factor G_l = g^T g / rows over the Fisher-sample rows
-static int output_factor(acx_learner* l, int li, const Planes& g_fisher, int rows, cudaStream_t st) {
+static int output_factor(acx_learner* l, int li, const Planes& g_fisher, int rows, const Lane& ln) {
   const Layer& L = l->L[li];
   if ((L.C == 32 || L.C == 64) && l->cfg.gemm_impl == 0)   // too narrow for a tensor-core tile: fp32 SIMT Gram kernel
-    return gram_small(g_fisher, rows, L.C, 1.0f / (float)rows, l->colsum_partial, kGramChunks, l->stats + l->goff[li], st);
+    return gram_small(g_fisher, rows, L.C, 1.0f / (float)rows, ln.sc->colsum_partial, kGramChunks, l->stats + l->goff[li], ln.st);
   GemmOut o;
   o.c = l->stats + l->goff[li];
   o.ldc = L.C;
-  return run_gemm(l, g_fisher, g_fisher, 1, L.C, L.C, rows, l->lvl_factor, 1.0f / (float)rows, 1, o, st);
+  return run_gemm(l, g_fisher, g_fisher, 1, L.C, L.C, rows, l->lvl_factor, 1.0f / (float)rows, 1, o, ln);
 }
 
+// Phase 1 as three lanes (each a chain; arrows = events):
+//   lane 0  forward -> returns, loss, heads backward -> fc4 dgrad -> conv3 dgrad -> conv2 dgrad -> conv1 wgrad
+//   lane 1  input factors A_l, each forked from the forward as soon as its operand exists
+//   lane 2  wgrad + output factor G_l of a layer, forked as soon as that layer's pre-activation gradient exists
+// With one lane (profiling, ACX lanes = 1) the same calls run back to back on the caller's stream.
 static int issue_phase1(acx_learner* l, const int32_t* fisher_labels, const float* fisher_eps, cudaStream_t st) {
   const int N = l->N, E = l->E, T = l->T, A = l->A, c3 = l->c3;
   const bool acktr = l->cfg.acktr != 0;
   const bool fisher = acktr && l->gs >= l->cfg.num_cold_updates;   // kfac_utils.py:42-44: covariances only after the cold phase
   const int RB = fisher ? 2 * N : N;
+  l->ev_next = 0;
+  const Lane main_ln = lane_of(l, 0, st), fac_ln = lane_of(l, 1, st), wg_ln = lane_of(l, 2, st);
   mark(l, 0, st);
-  ACX_TRY(forward(l, l->obs, l->R, st));
+  ACX_TRY(forward(l, l->obs, l->R, main_ln, fisher ? &fac_ln : nullptr));
   mark(l, 1, st);
   // targets use the bootstrap tower's values = rows [N, N+E) (envs/atari/model.py:116,126-127)
   ACX_TRY(returns_launch(l->rewards, l->terminals, l->values, l->values + N, l->cfg.gamma, E, T, l->targets, l->adv, st));
@@ -586,7 +678,12 @@ static int issue_phase1(acx_learner* l, const int32_t* fisher_labels, const floa
   const Planes flat3 = with_ld(l->act3, 49 * c3);
   mark(l, 2, st);
   // ---- fc4
-  ACX_TRY(weight_grad(l, 3, flat3, l->dpre4, N, 1.0f, st));
+  ACX_TRY(fork_lane(l, st, wg_ln));
+  ACX_TRY(weight_grad(l, 3, flat3, l->dpre4, N, 1.0f, wg_ln));
+  if (fisher) {
+    ACX_TRY(heads_gfactor(l->dheads + (size_t)N * (A + 1), N, A, l->stats + l->goff[4], l->stats + l->goff[5], wg_ln.st));
+    ACX_TRY(output_factor(l, 3, offset_rows(l->dpre4, N), N, wg_ln));
+  }
   {
     GemmOut o;   // d(act3) = dpre4 W4^T, masked by ReLU(conv3) -> dpre3  (rows of the Fisher half reuse the mask)
     const Planes out = with_ld(l->dpre3, 49 * c3);
@@ -594,37 +691,37 @@ static int issue_phase1(acx_learner* l, const int32_t* fisher_labels, const floa
     o.mask = l->act3.p[0];
     o.mask_ld = 49 * c3;
     o.mask_rows = N;
-    ACX_TRY(run_gemm(l, l->dpre4, l->wN[3], 0, RB, 49 * c3, 512, l->lvl_bwd, 1.0f, 0, o, st));
+    ACX_TRY(run_gemm(l, l->dpre4, l->wN[3], 0, RB, 49 * c3, 512, l->lvl_bwd, 1.0f, 0, o, main_ln));
   }
   // ---- conv3
-  ACX_TRY(weight_grad(l, 2, l->P3, l->dpre3, N * 49, 1.0f, st));
-  ACX_TRY(conv_dgrad(l, 2, l->dpre3, l->act2.p[0], l->dpre2, RB, st));
+  ACX_TRY(fork_lane(l, st, wg_ln));
+  ACX_TRY(weight_grad(l, 2, l->P3, l->dpre3, N * 49, 1.0f, wg_ln));
+  if (fisher) ACX_TRY(output_factor(l, 2, offset_rows(l->dpre3, (size_t)N * 49), N * 49, wg_ln));
+  ACX_TRY(conv_dgrad(l, 2, l->dpre3, l->act2.p[0], l->dpre2, RB, main_ln));
   // ---- conv2
-  ACX_TRY(weight_grad(l, 1, l->P2, l->dpre2, N * 81, 1.0f, st));
-  ACX_TRY(conv_dgrad(l, 1, l->dpre2, l->act1.p[0], l->dpre1, RB, st));
+  ACX_TRY(fork_lane(l, st, wg_ln));
+  ACX_TRY(weight_grad(l, 1, l->P2, l->dpre2, N * 81, 1.0f, wg_ln));
+  if (fisher) ACX_TRY(output_factor(l, 1, offset_rows(l->dpre2, (size_t)N * 81), N * 81, wg_ln));
+  ACX_TRY(conv_dgrad(l, 1, l->dpre2, l->act1.p[0], l->dpre1, RB, main_ln));
   // ---- conv1 (no input gradient: observations are constants, envs/atari/model.py:101-104)
-  ACX_TRY(weight_grad(l, 0, l->P1, l->dpre1, N * 400, 1.0f / 255.0f, st));
-  mark(l, 3, st);
   if (fisher) {
-    // ---- the 11 batch factor statistics
-    ACX_TRY(heads_gfactor(l->dheads + (size_t)N * (A + 1), N, A, l->stats + l->goff[4], l->stats + l->goff[5], st));
-    ACX_TRY(output_factor(l, 3, offset_rows(l->dpre4, N), N, st));
-    ACX_TRY(output_factor(l, 2, offset_rows(l->dpre3, (size_t)N * 49), N * 49, st));
-    ACX_TRY(output_factor(l, 1, offset_rows(l->dpre2, (size_t)N * 81), N * 81, st));
-    ACX_TRY(output_factor(l, 0, offset_rows(l->dpre1, (size_t)N * 400), N * 400, st));
-    const float r1 = 1.0f / (float)(N * 400), r2 = 1.0f / (float)(N * 81), r3 = 1.0f / (float)(N * 49), r4 = 1.0f / (float)N;
-    ACX_TRY(conv_input_factor(l, 0, l->P1, l->obs, nullptr, r1 / (255.0f * 255.0f), r1 / 255.0f, st));
-    ACX_TRY(conv_input_factor(l, 1, l->P2, nullptr, &l->act1, r2, r2, st));
-    ACX_TRY(conv_input_factor(l, 2, l->P3, nullptr, &l->act2, r3, r3, st));
-    ACX_TRY(input_factor(l, 3, flat3, N, 49 * c3, r4, r4, st));
-    ACX_TRY(input_factor(l, 4, l->act4, N, 512, r4, r4, st));
+    ACX_TRY(fork_lane(l, st, wg_ln));
+    ACX_TRY(output_factor(l, 0, offset_rows(l->dpre1, (size_t)N * 400), N * 400, wg_ln));
   }
+  ACX_TRY(weight_grad(l, 0, l->P1, l->dpre1, N * 400, 1.0f / 255.0f, main_ln));
+  mark(l, 3, st);
+  // ---- join: the caller's stream now also covers the 11 batch factor statistics and every weight gradient
+  ACX_TRY(join_lane(l, fac_ln, st));
+  ACX_TRY(join_lane(l, wg_ln, st));
   mark(l, 4, st);
   return 0;
 }
 
 static int precondition(acx_learner* l, cudaStream_t st) {
-  ACX_TRY(precondition_small(l->d_pjobs, l->num_pjobs, l->pjobs_max_d, st));
+  // blocks with <= 64 output channels: batched fp32 SIMT kernels on a side lane, next to fc4's two GEMMs
+  const Lane main_ln = lane_of(l, 0, st), small_ln = lane_of(l, 1, st);
+  ACX_TRY(fork_lane(l, st, small_ln));
+  ACX_TRY(precondition_small(l->d_pjobs, l->num_pjobs, l->pjobs_max_d, small_ln.st));
   for (int i = 0; i < 6; ++i) {
     const Layer& L = l->L[i];
     const int d = L.K + 1, C = L.C;
@@ -636,12 +733,13 @@ static int precondition(acx_learner* l, cudaStream_t st) {
     ACX_TRY(split_planes(l->grads + L.off, C, d, C, 1.0f, vp.p[0], vp.p[1], vp.p[2], 3, vp.ld, st));
     GemmOut o1;   // Wt [C, d] = G^-1 V^T
     o1.planes = &wt;
-    ACX_TRY(run_gemm(l, l->ginv_pl[i], vp, 0, C, d, C, l->lvl_precon, 1.0f, 0, o1, st));
+    ACX_TRY(run_gemm(l, l->ginv_pl[i], vp, 0, C, d, C, l->lvl_precon, 1.0f, 0, o1, main_ln));
     GemmOut o2;   // U [d, C] = A^-1 W / T~
     o2.c = l->precon + L.off;
     o2.ldc = C;
-    ACX_TRY(run_gemm(l, l->ainv_pl[i], wt, 0, d, C, d, l->lvl_precon, 1.0f / (float)L.Tnorm, 0, o2, st));
+    ACX_TRY(run_gemm(l, l->ainv_pl[i], wt, 0, d, C, d, l->lvl_precon, 1.0f / (float)L.Tnorm, 0, o2, main_ln));
   }
+  ACX_TRY(join_lane(l, small_ln, st));
   return 0;
 }
 
@@ -682,6 +780,7 @@ static void advance_phase2(acx_learner* l, const Plan2& p) {
 static int issue_phase2(acx_learner* l, const Plan2& p, cudaStream_t st) {
   const acx_learner_config_t& c = l->cfg;
   const size_t P = l->num_params;
+  l->ev_next = 0;
   mark(l, 5, st);
   if (c.world_size > 1) ACX_TRY(scale_f32(l->bucket, l->bucket_floats, 1.0f / (float)c.world_size, st));
   ACX_CUDA(cudaMemcpyAsync(l->scalars, l->bscalars, 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -835,6 +934,13 @@ acx_learner_t* acx_learner_create(const acx_learner_config_t* cfg, void* d_arena
   l->ncov = 0;
   l->inverses_valid = false;
   l->act_calls = 0;
+  l->lanes = cfg->num_lanes <= 0 ? kMaxLanes : std::min(cfg->num_lanes, kMaxLanes);
+  for (int i = 0; i + 1 < l->lanes; ++i)
+    if (cudaStreamCreateWithFlags(&l->side[i], cudaStreamNonBlocking) != cudaSuccess) {
+      acx::set_error("acx_learner_create: cudaStreamCreateWithFlags failed");
+      delete l;
+      return nullptr;
+    }
   // zero everything persistent; RMSProp's ms starts at one (TF-1 default)
   cudaError_t e = cudaMemset(d_arena, 0, need);
   if (e != cudaSuccess) {
@@ -882,6 +988,11 @@ void acx_learner_destroy(acx_learner_t* l) {
       if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   if (l && l->profiling)
     for (int k = 0; k < ACX_NUM_STAGES + 2; ++k) cudaEventDestroy(l->ev[k]);
+  if (l) {
+    for (cudaEvent_t e : l->lane_events) cudaEventDestroy(e);
+    for (cudaStream_t s : l->side)
+      if (s) cudaStreamDestroy(s);
+  }
   delete l;
 }
 
@@ -1011,7 +1122,7 @@ int acx_learner_act(acx_learner_t* l, const uint8_t* d_obs, int rows, const floa
   ACX_CHECK(l && d_obs && d_actions, "null argument");
   ACX_CHECK(rows > 0 && rows <= l->R, "rows must be in [1, num_envs * num_steps + num_envs]");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  int r = forward(l, d_obs, rows, st);
+  int r = forward(l, d_obs, rows, lane_of(l, 0, st), nullptr);
   if (r) return r;
   r = sample_actions(l->logits, d_uniform, l->cfg.seed, l->act_calls++, rows, l->A, greedy, d_actions, st);
   if (r) return r;

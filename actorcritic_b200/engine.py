@@ -54,6 +54,7 @@ class EngineConfig:
     gemm_impl: int = 0
     precision: int = 0
     use_graphs: bool = True                 # replay each update as CUDA graphs (captured on the second use of a variant)
+    num_lanes: int = 0                      # 0 = default (3 concurrent lanes inside an update), 1 = serial
     seed: int = 0
 
     @staticmethod
@@ -82,6 +83,7 @@ class EngineConfig:
         c.num_locations_mode = 0 if self.num_locations_mode == "true" else 1
         c.world_size, c.gemm_impl, c.precision, c.seed = self.world_size, self.gemm_impl, self.precision, self.seed
         c.use_graphs = int(bool(self.use_graphs))
+        c.num_lanes = int(self.num_lanes)
         return c
 
 

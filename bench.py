@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--conv3", type=int, default=32)
     ap.add_argument("--precision", type=int, default=0)
     ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--lanes", type=int, default=0, help="concurrent lanes inside an update (0 = library default 3, 1 = serial)")
     ap.add_argument("--invert-every", type=int, default=10, help="diagnostic only: the reference uses 10 (a2c_acktr.py:245)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=15.0)
@@ -215,7 +216,7 @@ def run_native(args, rank, world, local_rank):
     n = envs * t_count
     cfg = eng.EngineConfig(num_envs=envs, num_steps=t_count, conv3_filters=c3, precision=args.precision,
                            world_size=world, seed=1234 + rank, use_graphs=not args.no_graphs,
-                           invert_every=args.invert_every)
+                           invert_every=args.invert_every, num_lanes=args.lanes)
     e = eng.Engine(cfg, dev)
     e.set_params(eng.orthogonal_init(4, c3, seed=0))
     # synthetic inputs: 8 resident batches (8 x 19 MB > L2) + the same in pinned host memory for the e2e leg
@@ -367,6 +368,7 @@ def run_native(args, rank, world, local_rank):
         "data": "synthetic",
         "updates_per_sec": 1e3 / ms_step, "env_frames_per_sec": value * FRAMESKIP,
         "config": {"workload": workload_name(args, world), "precision": args.precision, "cuda_graphs": not args.no_graphs,
+                   "lanes": args.lanes if args.lanes > 0 else 3,
                    "l2": "8 resident input batches rotated (152 MB > 126 MB L2); per-step intermediates ~0.9 GB, self-flushing",
                    "parallelism": "dp%d (envs sharded, one NCCL all-reduce of grads+factor statistics per update)" % world},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 64,

@@ -140,6 +140,9 @@ typedef struct {
                                   3 = single-plane bf16 everywhere (fastest; not parity grade) */
   int use_graphs;              /* 1 = capture each (phase, schedule variant) into a CUDA graph on its second use and replay
                                   it afterwards (needs a non-NULL stream); 0 = launch kernel by kernel */
+  int num_lanes;               /* concurrent lanes inside one update: 0 = default (3: forward/dgrad chain | input factors |
+                                  wgrad + output factors, forked and joined with events on library-owned streams, so the
+                                  caller still orders everything through `stream`); 1 = strictly serial on `stream` */
   uint64_t seed;               /* Philox seed for on-device Fisher sampling */
 } acx_learner_config_t;
 
