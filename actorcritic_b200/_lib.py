@@ -33,6 +33,16 @@ class Gemm(ctypes.Structure):
                 ("splits", ctypes.c_int), ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t)]
 
 
+class Conv(ctypes.Structure):
+    _fields_ = [("dgrad", ctypes.c_int), ("samples", ctypes.c_int),
+                ("hw_in", ctypes.c_int), ("c_in", ctypes.c_int), ("k", ctypes.c_int), ("stride", ctypes.c_int),
+                ("hw_out", ctypes.c_int), ("c_out", ctypes.c_int),
+                ("x", Planes), ("w", Planes), ("out", Planes),
+                ("bias", ctypes.c_void_p), ("relu", ctypes.c_int),
+                ("mask_plane", ctypes.c_void_p), ("mask_samples", ctypes.c_int),
+                ("num_pairs", ctypes.c_int), ("pair_a", ctypes.c_int * 6), ("pair_b", ctypes.c_int * 6)]
+
+
 class LearnerConfig(ctypes.Structure):
     _fields_ = [("num_envs", ctypes.c_int), ("num_steps", ctypes.c_int), ("num_actions", ctypes.c_int),
                 ("conv3_filters", ctypes.c_int), ("acktr", ctypes.c_int),
@@ -44,7 +54,7 @@ class LearnerConfig(ctypes.Structure):
                 ("cold_lr", ctypes.c_float), ("cold_momentum", ctypes.c_float), ("clip_norm", ctypes.c_float),
                 ("rms_decay", ctypes.c_float), ("rms_epsilon", ctypes.c_float),
                 ("num_locations_mode", ctypes.c_int), ("world_size", ctypes.c_int), ("gemm_impl", ctypes.c_int),
-                ("precision", ctypes.c_int), ("use_graphs", ctypes.c_int), ("num_lanes", ctypes.c_int),
+                ("precision", ctypes.c_int), ("use_graphs", ctypes.c_int), ("conv_impl", ctypes.c_int), ("num_lanes", ctypes.c_int),
                 ("seed", ctypes.c_uint64)]
 
 
@@ -66,6 +76,10 @@ SIGNATURES = {
     "acx_debug_tc_error": (ctypes.c_int, []),
     "acx_gemm_enable_timing": (ctypes.c_int, [ctypes.c_int]),
     "acx_gemm_last_ms": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float)]),
+    "acx_conv_supported": (ctypes.c_int, [ctypes.POINTER(Conv)]),
+    "acx_conv": (ctypes.c_int, [ctypes.POINTER(Conv), _P]),
+    "acx_conv_dgrad_weights": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                              ctypes.c_int, ctypes.POINTER(_P), ctypes.c_int, _P]),
     "acx_learner_arena_bytes": (ctypes.c_size_t, [ctypes.POINTER(LearnerConfig)]),
     "acx_learner_create": (_P, [ctypes.POINTER(LearnerConfig), _P, ctypes.c_size_t]),
     "acx_learner_destroy": (None, [_P]),

@@ -1,0 +1,638 @@
+// conv.cu - implicit-GEMM convolution kernels for sm_100a: the patch matrix is never materialised.
+//
+// The im2col GEMM of nn.conv2d (nn.py:88-110; NHWC, VALID, HWIO weights) reads, for one kernel tap, a BOX of the
+// activation tensor: with the kernel size a multiple of the stride (k = s*m: 4x4/2 and 3x3/1 of the Nature-CNN,
+// envs/atari/model.py:180-199) the input rows/columns split as y = s*yq + y1, x = s*xq + x1 and the tensor is the
+// 5-D array  [r][yq][y1][xq][(x1, c)]  whose innermost run (x1, c) has s*c_in = 64 bf16 = one 128-byte swizzle row.
+// A TMA tile load of the box [hw_out yq][hw_out xq][64] at (yq, y1, xq) = (kh / s, kh % s, kw / s) delivers exactly
+// the K-major A tile "all output locations of a sample x 64 patch columns" of tap (kh, kw / s), already swizzled for
+// tcgen05.mma - forward needs no im2col pass and reads the activation (L2 resident) instead of the k^2/s^2 larger P.
+//
+// The input gradient uses the gather form of the transposed convolution (no fp32 dP matrix, no col2im pass):
+//   dX[r, s*a + py, s*b + px, ci] = sum_{i,j<m} sum_co g[r, a - i, b - j, co] * W[s*i + py, s*j + px, ci, co]
+// i.e. ONE GEMM with rows (r, a, b), columns (py, px, ci) and K = (i, j, co); the A tile of tap (i, j) is the box
+// [hq a][hq b][c_out] of g at (-i, -j): out-of-range coordinates are zero-filled by TMA, which is the padding.  The
+// epilogue scatters (pixel shuffle), applies the ReLU mask of the layer below and splits into bf16 planes.
+//
+// Warp roles as in gemm.cu (192 threads): warp 0 TMA producer, warp 1 TMEM + MMA issuer, warps 2..5 epilogue.
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+
+#include "layers.cuh"
+#include "tc.cuh"
+
+namespace acx {
+
+constexpr int CV_BM = 128;
+constexpr int CV_BK = 64;
+constexpr int CV_A_TILE = CV_BM * CV_BK * 2;   // one plane of one k-block (1 x 64-wide or 2 x 32-wide sub-tiles)
+constexpr int CV_MAX_SUB = 16;
+constexpr int CV_MAX_STAGES = 4;
+constexpr int CV_EPI_LD = 68;
+constexpr int CV_EPI_BYTES = 4 * 32 * CV_EPI_LD * 4;
+constexpr int CV_SMEM_LIMIT = 232448;
+constexpr int CV_SMEM_FIXED = CV_EPI_BYTES + 256;
+
+struct ConvTcParams {
+  int num_tiles, ts, rows_valid, total_rows;   // a tile = ts samples = rows_valid GEMM rows (<= 128)
+  int bn;                                      // GEMM columns (= tile width: 32, 64 or 128)
+  int kb_total, nsub, num_sub;                 // k-blocks of 64; sub-tiles per k-block (1 or 2); sub-tiles over all of K
+  int sub_bytes;                               // bytes one sub-tile box delivers
+  signed char tc1[CV_MAX_SUB], tc2[CV_MAX_SUB], tc3[CV_MAX_SUB];   // box coordinates of every sub-tile (dims 1..3)
+  int num_pairs, pair_a[6], pair_b[6], npa, npb, stages;
+  // epilogue
+  int dgrad;                                   // 0: output row = GEMM row; 1: pixel-shuffle scatter
+  int hw_in, c_in, s, hq;
+  float alpha;
+  const float* bias;
+  int relu;
+  bf16* cp[3];
+  int npl, ldcp;
+  const bf16* mask;
+  int mask_samples;
+};
+
+__global__ void __launch_bounds__(192, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ CUtensorMap ta1,
+               const __grid_constant__ CUtensorMap ta2, const __grid_constant__ CUtensorMap tb0,
+               const __grid_constant__ CUtensorMap tb1, const __grid_constant__ CUtensorMap tb2, const ConvTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem_raw) & 1023u) != 0) {
+    if (threadIdx.x == 0) atomicExch(&g_tc_error, 9);
+    return;
+  }
+  const int BN = p.bn;
+  const int b_tile_bytes = BN * CV_BK * 2;
+  const int stage_bytes = p.npa * CV_A_TILE + p.npb * b_tile_bytes;
+  float* epi = reinterpret_cast<float*>(smem + p.stages * stage_bytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(epi) + CV_EPI_BYTES);
+  uint64_t* empty_bar = full_bar + CV_MAX_STAGES;
+  uint64_t* acc_full = empty_bar + CV_MAX_STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tmem_cols = (uint32_t)(2 * BN);   // two accumulators: 64, 128 or 256 columns
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int sub_tile_bytes = CV_A_TILE / p.nsub;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer: per k-block one box per (plane, sub-tile) of the activation + the weight tile =====
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int sample0 = tile * p.ts;
+        for (int kb = 0; kb < p.kb_total; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+          const int nload = min(p.nsub, p.num_sub - kb * p.nsub);
+          mbar_wait(&empty_bar[s], ph ^ 1u, 1);
+          mbar_expect_tx(&full_bar[s], (uint32_t)(p.npa * nload * p.sub_bytes + p.npb * b_tile_bytes));
+          uint8_t* a_s = smem + s * stage_bytes;
+          uint8_t* b_s = a_s + p.npa * CV_A_TILE;
+          for (int i = 0; i < p.npa; ++i) {
+            const CUtensorMap* ma = i == 0 ? &ta0 : (i == 1 ? &ta1 : &ta2);
+            for (int j = 0; j < nload; ++j) {
+              const int t = kb * p.nsub + j;
+              tma_load_5d(a_s + i * CV_A_TILE + j * sub_tile_bytes, ma, &full_bar[s], 0, p.tc1[t], p.tc2[t], p.tc3[t], sample0);
+            }
+          }
+          for (int i = 0; i < p.npb; ++i) {
+            const CUtensorMap* mb = i == 0 ? &tb0 : (i == 1 ? &tb1 : &tb2);
+            tma_load_2d(b_s + i * b_tile_bytes, mb, &full_bar[s], kb * CV_BK, 0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one elected lane) =====
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(CV_BM >> 4) << 24);
+    const uint32_t a_layout = p.nsub == 1 ? 2u : 4u;      // SWIZZLE_128B / SWIZZLE_64B
+    const uint32_t a_sbo = p.nsub == 1 ? 1024u : 512u;    // 8 rows of 128 / 64 bytes
+    const int ksteps = (CV_BK / p.nsub) >> 4;             // MMAs (K = 16) per sub-tile
+    int it = 0, lt = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
+      mbar_wait(&acc_empty[buf], aph ^ 1u, 4);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+      for (int kb = 0; kb < p.kb_total; ++kb, ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        mbar_wait(&full_bar[s], ph, 2);
+        tc_fence_after();
+        if (lane == 0) {
+          const int nload = min(p.nsub, p.num_sub - kb * p.nsub);
+          const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+          const uint32_t b_addr = a_addr + (uint32_t)(p.npa * CV_A_TILE);
+          uint32_t acc_flag = kb > 0 ? 1u : 0u;
+          for (int pr = 0; pr < p.num_pairs; ++pr) {
+            const uint64_t b_desc0 = make_smem_desc_sw(b_addr + (uint32_t)(p.pair_b[pr] * b_tile_bytes), 16u, 1024u, 2u);
+            for (int j = 0; j < nload; ++j) {
+              uint64_t ad = make_smem_desc_sw(a_addr + (uint32_t)(p.pair_a[pr] * CV_A_TILE + j * sub_tile_bytes), 16u, a_sbo, a_layout);
+              // the weight tile is 64 K-columns wide (128-byte rows): sub-tile j starts j * (128 / nsub) bytes into the row
+              uint64_t bd = b_desc0 + (uint64_t)((uint32_t)(j * (128 / p.nsub)) >> 4);
+              for (int kk = 0; kk < ksteps; ++kk) {
+                umma_bf16(d_tmem, ad, bd, idesc, acc_flag);
+                acc_flag = 1u;
+                ad += 2;   // 16 bf16 = 32 bytes along K inside the swizzle row
+                bd += 2;
+              }
+            }
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        __syncwarp();
+      }
+      if (lane == 0) umma_commit(&acc_full[buf]);
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> per-warp shared-memory transpose -> bf16 planes =====
+    const int q = warp & 3;
+    float* st = epi + (size_t)q * 32 * CV_EPI_LD;
+    const int CH = BN >= 64 ? 64 : 32;
+    const int lpr = CH >> 2;
+    const int rpi = 32 / lpr;
+    const int rsub = lane / lpr;
+    const int cl = (lane - rsub * lpr) * 4;
+    bf16* const cp0 = p.cp[0];
+    bf16* const cp1 = p.cp[1];
+    bf16* const cp2 = p.cp[2];
+    const int npl = p.npl, ldcp = p.ldcp;
+    const float alpha = p.alpha;
+    const float* const bias = p.bias;
+    const bool relu = p.relu != 0;
+    const bf16* const mask = p.mask;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
+      mbar_wait(&acc_full[buf], aph, 3);
+      tc_fence_after();
+      const int sample0 = tile * p.ts;
+      for (int c0 = 0; c0 < BN; c0 += CH) {
+        uint32_t raw[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0);
+        tmem_ld32(taddr, raw);
+        float4* strow = reinterpret_cast<float4*>(st + lane * CV_EPI_LD);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          strow[j] = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]), __uint_as_float(raw[4 * j + 2]),
+                                 __uint_as_float(raw[4 * j + 3]));
+        if (CH == 64) {
+          tmem_ld32(taddr + 32u, raw);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            strow[8 + j] = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
+                                       __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3]));
+        }
+        if (c0 + CH >= BN) {   // accumulator drained: hand the TMEM buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+        __syncwarp();
+        const int n = c0 + cl;
+        float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+        if (bias) {
+          b0 = __ldg(bias + n);
+          b1 = __ldg(bias + n + 1);
+          b2 = __ldg(bias + n + 2);
+          b3 = __ldg(bias + n + 3);
+        }
+        size_t col_off = (size_t)n;
+        if (p.dgrad) {   // column (py, px, ci) -> offset of pixel (py, px) inside the s x s output cell
+          const int pp = n / p.c_in, ci = n - pp * p.c_in;
+          const int py = pp / p.s, px = pp - py * p.s;
+          col_off = (size_t)(py * p.hw_in + px) * p.c_in + ci;
+        }
+        const float* src = st + rsub * CV_EPI_LD + cl;
+        for (int r = rsub; r < 32; r += rpi, src += rpi * CV_EPI_LD) {
+          const int i = q * 32 + r;
+          if (i >= p.rows_valid) break;
+          size_t row_off, mrow_off = 0;
+          if (!p.dgrad) {
+            const int out_row = tile * p.rows_valid + i;
+            if (out_row >= p.total_rows) break;
+            row_off = (size_t)out_row * ldcp;
+          } else {   // row (a, b) of sample r -> pixel (s*a, s*b); cells that start beyond the input edge do not exist
+            const int a = i / p.hq, b = i - a * p.hq;
+            const size_t pix = (size_t)(p.s * a) * p.hw_in + p.s * b;
+            row_off = ((size_t)sample0 * p.hw_in * p.hw_in + pix) * p.c_in;
+            mrow_off = ((size_t)(sample0 % p.mask_samples) * p.hw_in * p.hw_in + pix) * p.c_in;
+          }
+          const float4 a4 = *reinterpret_cast<const float4*>(src);
+          float v0 = fmaf(alpha, a4.x, b0), v1 = fmaf(alpha, a4.y, b1), v2 = fmaf(alpha, a4.z, b2), v3 = fmaf(alpha, a4.w, b3);
+          if (relu) {
+            v0 = fmaxf(v0, 0.0f);
+            v1 = fmaxf(v1, 0.0f);
+            v2 = fmaxf(v2, 0.0f);
+            v3 = fmaxf(v3, 0.0f);
+          }
+          if (mask) {
+            const uint2 mw = *reinterpret_cast<const uint2*>(mask + mrow_off + col_off);
+            if (!(__uint_as_float(mw.x << 16) > 0.0f)) v0 = 0.0f;
+            if (!(__uint_as_float(mw.x & 0xffff0000u) > 0.0f)) v1 = 0.0f;
+            if (!(__uint_as_float(mw.y << 16) > 0.0f)) v2 = 0.0f;
+            if (!(__uint_as_float(mw.y & 0xffff0000u) > 0.0f)) v3 = 0.0f;
+          }
+          bf16 h0, h1, h2, h3, m0, m1, m2, m3, l0, l1, l2, l3;
+          split3(v0, h0, m0, l0);
+          split3(v1, h1, m1, l1);
+          split3(v2, h2, m2, l2);
+          split3(v3, h3, m3, l3);
+          const size_t idx = row_off + col_off;
+          *reinterpret_cast<uint2*>(cp0 + idx) = pack4(h0, h1, h2, h3);
+          if (npl > 1) *reinterpret_cast<uint2*>(cp1 + idx) = pack4(m0, m1, m2, m3);
+          if (npl > 2) *reinterpret_cast<uint2*>(cp2 + idx) = pack4(l0, l1, l2, l3);
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// B operand of the gather-form input gradient: rows (py, px, ci), K columns (i, j, co):
+//   Bd[(py*s + px)*c_in + ci][(i*m + j)*c_out + co] = W[((s*i + py)*k + (s*j + px))*c_in + ci][co]      (k = s*m)
+__global__ void __launch_bounds__(256) dgrad_weight_planes_kernel(const float* __restrict__ w, int c_in, int c_out, int k, int s,
+                                                                  bf16* __restrict__ p0, bf16* __restrict__ p1, bf16* __restrict__ p2,
+                                                                  int ld) {
+  const int m = k / s;
+  const int rows = s * s * c_in, cols = m * m * c_out;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < rows * ld; e += gridDim.x * blockDim.x) {
+    const int n = e / ld, kk = e - n * ld;
+    float v = 0.0f;
+    if (kk < cols) {
+      const int pp = n / c_in, ci = n - pp * c_in, py = pp / s, px = pp - py * s;
+      const int tap = kk / c_out, co = kk - tap * c_out, i = tap / m, j = tap - i * m;
+      v = w[(size_t)(((s * i + py) * k + (s * j + px)) * c_in + ci) * c_out + co];
+    }
+    bf16 a, b, c;
+    split3(v, a, b, c);
+    p0[e] = a;
+    p1[e] = b;
+    p2[e] = c;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn conv_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+struct ViewKey {
+  const void* ptr;
+  long long dim[5], stride[4];
+  int box[5], swz;
+  bool operator==(const ViewKey& o) const {
+    if (ptr != o.ptr || swz != o.swz) return false;
+    for (int i = 0; i < 5; ++i)
+      if (dim[i] != o.dim[i] || box[i] != o.box[i]) return false;
+    for (int i = 0; i < 4; ++i)
+      if (stride[i] != o.stride[i]) return false;
+    return true;
+  }
+};
+struct ViewKeyHash {
+  size_t operator()(const ViewKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr) ^ (size_t)k.swz;
+    for (int i = 0; i < 5; ++i) h = h * 1000003u ^ (size_t)(k.dim[i] * 131 + k.box[i]);
+    for (int i = 0; i < 4; ++i) h = h * 1000003u ^ (size_t)k.stride[i];
+    return h;
+  }
+};
+static std::unordered_map<ViewKey, CUtensorMap, ViewKeyHash> g_views;
+static std::mutex g_views_mu;
+
+// bf16 tensor view of rank `rank` (<= 5): dim / box innermost first, stride[i] = byte stride of dim i+1
+static int get_view_map(const void* ptr, int rank, const long long* dim, const long long* stride_bytes, const int* box, int swizzle_bytes,
+                        CUtensorMap* out) {
+  ViewKey key;
+  key.ptr = ptr;
+  key.swz = swizzle_bytes;
+  for (int i = 0; i < 5; ++i) {
+    key.dim[i] = i < rank ? dim[i] : 1;
+    key.box[i] = i < rank ? box[i] : 1;
+  }
+  for (int i = 0; i < 4; ++i) key.stride[i] = i + 1 < rank ? stride_bytes[i] : 0;
+  std::lock_guard<std::mutex> lock(g_views_mu);
+  auto it = g_views.find(key);
+  if (it != g_views.end()) {
+    *out = it->second;
+    return 0;
+  }
+  EncodeTiledFn fn = conv_encode_fn();
+  ACX_CHECK(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  ACX_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "tensor pointer must be 16-byte aligned");
+  cuuint64_t gdim[5];
+  cuuint64_t gstride[4];
+  cuuint32_t gbox[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = (cuuint64_t)dim[i];
+    gbox[i] = (cuuint32_t)box[i];
+    estr[i] = 1;
+    ACX_CHECK(box[i] >= 1 && box[i] <= 256, "box dimension out of range");
+  }
+  for (int i = 0; i + 1 < rank; ++i) {
+    ACX_CHECK(stride_bytes[i] > 0 && (stride_bytes[i] & 15) == 0, "tensor strides must be multiples of 16 bytes");
+    gstride[i] = (cuuint64_t)stride_bytes[i];
+  }
+  CUtensorMap m;
+  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstride, gbox, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ACX_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (conv view) failed with code " + std::to_string((int)r));
+  if (g_views.size() > 1024) g_views.clear();
+  g_views[key] = m;
+  *out = m;
+  return 0;
+}
+
+static int conv_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+bool conv_tc_supported(const ConvGeom& g, int dgrad) {
+  if (g.s < 1 || g.k % g.s != 0 || g.hw_in % g.s != 0) return false;
+  const int m = g.k / g.s, hq = g.hw_in / g.s;
+  if (g.hw_out != (g.hw_in - g.k) / g.s + 1) return false;
+  if (!dgrad) {
+    // forward: innermost run (x1, c) must be one 128-byte swizzle row; a tile holds whole samples
+    if (g.s * g.c_in != 64) return false;
+    if (g.hw_out * g.hw_out > CV_BM || g.k * m > CV_MAX_SUB) return false;
+    return g.c_out == 32 || g.c_out == 64 || g.c_out == 128;
+  }
+  if (g.c_out != 32 && g.c_out != 64) return false;                       // one tap = 64 or 128 bytes of K
+  const int n = g.s * g.s * g.c_in;
+  if (n != 32 && n != 64 && n != 128) return false;
+  if (hq * hq > CV_BM) return false;
+  if (hq < g.hw_out) return false;                                        // every g location must be reached
+  return m * m <= CV_MAX_SUB;
+}
+
+static int fill_pairs(ConvTcParams* p, int num_pairs, const int* pair_a, const int* pair_b, int a_planes, int b_planes) {
+  ACX_CHECK(num_pairs >= 1 && num_pairs <= 6, "num_pairs out of range");
+  p->num_pairs = num_pairs;
+  p->npa = p->npb = 1;
+  for (int i = 0; i < 6; ++i) {
+    p->pair_a[i] = i < num_pairs ? pair_a[i] : 0;
+    p->pair_b[i] = i < num_pairs ? pair_b[i] : 0;
+    if (i < num_pairs) {
+      ACX_CHECK(pair_a[i] >= 0 && pair_a[i] < a_planes && pair_b[i] >= 0 && pair_b[i] < b_planes, "plane pair index");
+      p->npa = std::max(p->npa, pair_a[i] + 1);
+      p->npb = std::max(p->npb, pair_b[i] + 1);
+    }
+  }
+  return 0;
+}
+
+static int launch_conv(const CUtensorMap* ta, const CUtensorMap* tb, ConvTcParams& p, cudaStream_t st) {
+  const int stage_bytes = p.npa * CV_A_TILE + p.npb * p.bn * CV_BK * 2;
+  p.stages = (CV_SMEM_LIMIT - CV_SMEM_FIXED) / stage_bytes;
+  if (p.stages > CV_MAX_STAGES) p.stages = CV_MAX_STAGES;
+  ACX_CHECK(p.stages >= 2, "conv tile does not fit the shared-memory ring");
+  static bool configured = false;
+  if (!configured) {
+    ACX_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM_LIMIT));
+    configured = true;
+  }
+  const int grid = std::min(p.num_tiles, conv_num_sms());
+  const int smem = CV_SMEM_FIXED + p.stages * stage_bytes;
+  conv_tc_kernel<<<grid, 192, smem, st>>>(ta[0], ta[1], ta[2], tb[0], tb[1], tb[2], p);
+  ACX_LAUNCH_CHECK();
+  return 0;
+}
+
+// weight operand: K-major [rows, kcols] planes, 128B-swizzled 64-column boxes
+static int weight_maps(const Planes& w, int rows, int kcols, int bn, CUtensorMap* tb) {
+  ACX_CHECK((w.ld & 7) == 0, "weight plane leading dimension must be a multiple of 8");
+  for (int i = 0; i < 3; ++i) {
+    const bf16* ptr = w.p[i < w.n ? i : 0];
+    const long long dim[2] = {kcols, rows};
+    const long long stride[1] = {(long long)w.ld * 2};
+    const int box[2] = {CV_BK, bn};
+    int r = get_view_map(ptr, 2, dim, stride, box, 128, &tb[i]);
+    if (r) return r;
+  }
+  return 0;
+}
+
+// y = relu(conv(x, W) + bias) as bf16 planes; x planes [samples, hw_in, hw_in, c_in], wT planes [c_out, k*k*c_in]
+int conv_tc_forward(const Planes& x, const Planes& wT, const ConvGeom& g, int samples, const float* bias, int relu, const Planes& y,
+                    int num_pairs, const int* pair_a, const int* pair_b, cudaStream_t st) {
+  ACX_CHECK(conv_tc_supported(g, 0), "unsupported convolution geometry for the implicit-GEMM forward");
+  ACX_CHECK(samples > 0 && x.n >= 1 && wT.n >= 1 && y.n >= 1 && y.ld == g.c_out, "bad operands");
+  const int m = g.k / g.s, hq = g.hw_in / g.s;
+  ConvTcParams p;
+  memset(&p, 0, sizeof(p));
+  int r = fill_pairs(&p, num_pairs, pair_a, pair_b, x.n, wT.n);
+  if (r) return r;
+  const int rps = g.hw_out * g.hw_out;
+  p.ts = CV_BM / rps;
+  p.rows_valid = p.ts * rps;
+  p.num_tiles = ceil_div(samples, p.ts);
+  p.total_rows = samples * rps;
+  p.bn = g.c_out;
+  const int K = g.k * g.k * g.c_in;
+  p.kb_total = K / CV_BK;
+  p.nsub = 1;
+  p.num_sub = g.k * m;
+  p.sub_bytes = p.rows_valid * CV_BK * 2;
+  for (int kh = 0; kh < g.k; ++kh)
+    for (int kw2 = 0; kw2 < m; ++kw2) {
+      const int t = kh * m + kw2;
+      p.tc1[t] = (signed char)kw2;        // xq
+      p.tc2[t] = (signed char)(kh % g.s); // y1
+      p.tc3[t] = (signed char)(kh / g.s); // yq
+    }
+  p.dgrad = 0;
+  p.hw_in = g.hw_in;
+  p.c_in = g.c_in;
+  p.s = g.s;
+  p.hq = hq;
+  p.alpha = 1.0f;
+  p.bias = bias;
+  p.relu = relu;
+  for (int i = 0; i < 3; ++i) p.cp[i] = i < y.n ? y.p[i] : nullptr;
+  p.npl = y.n;
+  p.ldcp = y.ld;
+  p.mask = nullptr;
+  p.mask_samples = 1;
+  CUtensorMap ta[3], tb[3];
+  const long long row = (long long)g.hw_in * g.c_in;   // elements of one input row
+  for (int i = 0; i < 3; ++i) {
+    const bf16* ptr = x.p[i < x.n ? i : 0];
+    const long long dim[5] = {64, hq, g.s, hq, samples};
+    const long long stride[4] = {64 * 2, row * 2, row * g.s * 2, row * g.hw_in * 2};
+    const int box[5] = {64, g.hw_out, 1, g.hw_out, p.ts};
+    r = get_view_map(ptr, 5, dim, stride, box, 128, &ta[i]);
+    if (r) return r;
+  }
+  r = weight_maps(wT, g.c_out, K, p.bn, tb);
+  if (r) return r;
+  return launch_conv(ta, tb, p, st);
+}
+
+// dx = relu'(act_below) * conv_transpose(gout, W) as bf16 planes [samples, hw_in, hw_in, c_in];
+// gout planes [samples, hw_out, hw_out, c_out]; wD = the rearranged weight planes of conv_dgrad_weight_planes;
+// mask_hi = hi plane of the forward activation below ([mask_samples, hw_in, hw_in, c_in]; sample r uses r % mask_samples)
+int conv_tc_dgrad(const Planes& gout, const Planes& wD, const ConvGeom& g, int samples, const bf16* mask_hi, int mask_samples,
+                  const Planes& dx, int num_pairs, const int* pair_a, const int* pair_b, cudaStream_t st) {
+  ACX_CHECK(conv_tc_supported(g, 1), "unsupported convolution geometry for the gather-form input gradient");
+  ACX_CHECK(samples > 0 && gout.n >= 1 && wD.n >= 1 && dx.n >= 1 && dx.ld == g.c_in && gout.ld == g.c_out, "bad operands");
+  const int m = g.k / g.s, hq = g.hw_in / g.s;
+  ConvTcParams p;
+  memset(&p, 0, sizeof(p));
+  int r = fill_pairs(&p, num_pairs, pair_a, pair_b, gout.n, wD.n);
+  if (r) return r;
+  p.ts = 1;
+  p.rows_valid = hq * hq;
+  p.num_tiles = samples;
+  p.total_rows = samples * p.rows_valid;
+  p.bn = g.s * g.s * g.c_in;
+  const int K = m * m * g.c_out;
+  p.kb_total = ceil_div(K, CV_BK);
+  p.nsub = CV_BK / g.c_out;            // c_out = 64: one tap per k-block; 32: two taps (64-byte swizzle sub-tiles)
+  p.num_sub = m * m;
+  p.sub_bytes = p.rows_valid * g.c_out * 2;
+  for (int i = 0; i < m; ++i)
+    for (int j = 0; j < m; ++j) {
+      const int t = i * m + j;
+      p.tc1[t] = (signed char)(-j);    // b - j
+      p.tc2[t] = (signed char)(-i);    // a - i
+      p.tc3[t] = 0;
+    }
+  p.dgrad = 1;
+  p.hw_in = g.hw_in;
+  p.c_in = g.c_in;
+  p.s = g.s;
+  p.hq = hq;
+  p.alpha = 1.0f;
+  p.bias = nullptr;
+  p.relu = 0;
+  for (int i = 0; i < 3; ++i) p.cp[i] = i < dx.n ? dx.p[i] : nullptr;
+  p.npl = dx.n;
+  p.ldcp = dx.ld;
+  p.mask = mask_hi;
+  p.mask_samples = mask_samples > 0 ? mask_samples : samples;
+  CUtensorMap ta[3], tb[3];
+  const long long row = (long long)g.hw_out * g.c_out;
+  for (int i = 0; i < 3; ++i) {
+    const bf16* ptr = gout.p[i < gout.n ? i : 0];
+    const long long dim[5] = {g.c_out, g.hw_out, g.hw_out, 1, samples};
+    const long long stride[4] = {(long long)g.c_out * 2, row * 2, row * g.hw_out * 2, row * g.hw_out * 2};
+    const int box[5] = {g.c_out, hq, hq, 1, 1};
+    r = get_view_map(ptr, 5, dim, stride, box, g.c_out == 64 ? 128 : 64, &ta[i]);
+    if (r) return r;
+  }
+  r = weight_maps(wD, p.bn, K, p.bn, tb);
+  if (r) return r;
+  return launch_conv(ta, tb, p, st);
+}
+
+int conv_dgrad_weight_planes(const float* w, const ConvGeom& g, const Planes& out, cudaStream_t st) {
+  ACX_CHECK(out.n == 3, "dgrad weight planes: 3 planes expected");
+  const int m = g.k / g.s;
+  ACX_CHECK(out.ld >= m * m * g.c_out, "dgrad weight planes: leading dimension too small");
+  const int total = g.s * g.s * g.c_in * out.ld;
+  dgrad_weight_planes_kernel<<<std::min(ceil_div(total, 256), 296), 256, 0, st>>>(w, g.c_in, g.c_out, g.k, g.s, out.p[0], out.p[1],
+                                                                                 out.p[2], out.ld);
+  ACX_LAUNCH_CHECK();
+  return 0;
+}
+
+int conv_error_flag() {
+  int v = 0;
+  cudaMemcpyFromSymbol(&v, g_tc_error, sizeof(int));
+  return v;
+}
+
+}  // namespace acx
+
+extern "C" {
+
+static acx::Planes to_planes(const acx_planes_t& a) {
+  acx::Planes p;
+  p.n = a.num_planes;
+  p.ld = a.ld;
+  for (int i = 0; i < a.num_planes && i < 3; ++i) p.p[i] = reinterpret_cast<acx::bf16*>(const_cast<void*>(a.planes[i]));
+  return p;
+}
+
+int acx_conv_supported(const acx_conv_t* c) {
+  if (!c) return 0;
+  const acx::ConvGeom g = {c->hw_in, c->c_in, c->k, c->stride, c->hw_out, c->c_out};
+  return acx::conv_tc_supported(g, c->dgrad) ? 1 : 0;
+}
+
+int acx_conv(const acx_conv_t* c, void* stream) {
+  ACX_CHECK(c != nullptr, "null argument");
+  ACX_CHECK(c->x.num_planes >= 1 && c->x.num_planes <= 3 && c->w.num_planes >= 1 && c->w.num_planes <= 3 &&
+                c->out.num_planes >= 1 && c->out.num_planes <= 3,
+            "plane counts");
+  const acx::ConvGeom g = {c->hw_in, c->c_in, c->k, c->stride, c->hw_out, c->c_out};
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (c->dgrad)
+    return acx::conv_tc_dgrad(to_planes(c->x), to_planes(c->w), g, c->samples, reinterpret_cast<const acx::bf16*>(c->mask_plane),
+                              c->mask_samples, to_planes(c->out), c->num_pairs, c->pair_a, c->pair_b, st);
+  return acx::conv_tc_forward(to_planes(c->x), to_planes(c->w), g, c->samples, c->bias, c->relu, to_planes(c->out), c->num_pairs,
+                              c->pair_a, c->pair_b, st);
+}
+
+int acx_conv_dgrad_weights(const float* d_w, int hw_in, int c_in, int k, int stride, int hw_out, int c_out, void* const* d_planes,
+                           int ld, void* stream) {
+  ACX_CHECK(d_w != nullptr && d_planes != nullptr, "null argument");
+  const acx::ConvGeom g = {hw_in, c_in, k, stride, hw_out, c_out};
+  acx::Planes out;
+  out.n = 3;
+  out.ld = ld;
+  for (int i = 0; i < 3; ++i) out.p[i] = reinterpret_cast<acx::bf16*>(d_planes[i]);
+  return acx::conv_dgrad_weight_planes(d_w, g, out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

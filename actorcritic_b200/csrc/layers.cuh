@@ -50,6 +50,18 @@ int sample_actions(const float* logits, const float* uniform, uint64_t seed, uin
 int split_planes(const float* in, int ld_in, int rows, int cols, float scale, bf16* p0, bf16* p1, bf16* p2, int num_planes,
                  int ld_out, cudaStream_t st);
 
+// conv.cu: implicit-GEMM convolution (forward) and gather-form input gradient on the tensor cores; NHWC, VALID
+struct ConvGeom {
+  int hw_in, c_in, k, s, hw_out, c_out;
+};
+bool conv_tc_supported(const ConvGeom& g, int dgrad);
+int conv_tc_forward(const Planes& x, const Planes& wT, const ConvGeom& g, int samples, const float* bias, int relu, const Planes& y,
+                    int num_pairs, const int* pair_a, const int* pair_b, cudaStream_t st);
+int conv_tc_dgrad(const Planes& gout, const Planes& wD, const ConvGeom& g, int samples, const bf16* mask_hi, int mask_samples,
+                  const Planes& dx, int num_pairs, const int* pair_a, const int* pair_b, cudaStream_t st);
+int conv_dgrad_weight_planes(const float* w, const ConvGeom& g, const Planes& out, cudaStream_t st);
+int conv_error_flag();
+
 // kfac.cu
 struct InvJob {          // one SPD inverse: M = debias * S + damp * I  (fp64) -> inverse fp32 + 3 bf16 planes
   const float* s;        // [n, n] running covariance sum

@@ -54,6 +54,7 @@ class EngineConfig:
     gemm_impl: int = 0
     precision: int = 0
     use_graphs: bool = True                 # replay each update as CUDA graphs (captured on the second use of a variant)
+    conv_impl: int = 0                      # 0 = implicit-GEMM conv2/conv3 forward + gather-form dgrad, 1 = im2col route
     num_lanes: int = 0                      # 0 = default (3 concurrent lanes inside an update), 1 = serial
     seed: int = 0
 
@@ -84,6 +85,7 @@ class EngineConfig:
         c.world_size, c.gemm_impl, c.precision, c.seed = self.world_size, self.gemm_impl, self.precision, self.seed
         c.use_graphs = int(bool(self.use_graphs))
         c.num_lanes = int(self.num_lanes)
+        c.conv_impl = int(self.conv_impl)
         return c
 
 

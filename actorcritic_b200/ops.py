@@ -140,3 +140,59 @@ def gemm(a_planes, b_planes, m, n, k, trans=False, pairs=None, alpha=1.0, bias=N
         g.workspace, g.workspace_bytes = ws.data_ptr(), ws_bytes
     _lib.check(lib.acx_gemm(ctypes.byref(g), impl, _stream()))
     return c, cps
+
+
+def _tensor_planes(planes, rows, cols):
+    s = _lib.Planes()
+    for i, p in enumerate(planes):
+        s.planes[i] = p.data_ptr()
+    s.num_planes = len(planes)
+    s.rows, s.cols, s.ld = rows, cols, cols
+    return s
+
+
+def conv(x_planes, w_planes, geom, samples, dgrad=False, bias=None, relu=False, mask=None, mask_samples=0, pairs=None,
+         out_planes=3):
+    """acx_conv: implicit-GEMM conv forward (x planes [samples,hw_in,hw_in,c_in], w = W^T planes [c_out, k*k*c_in]) or
+    gather-form input gradient (x = output-gradient planes [samples,hw_out,hw_out,c_out], w = conv_dgrad_weights planes).
+    geom = (hw_in, c_in, k, stride, hw_out, c_out).  Returns the list of bf16 output planes."""
+    lib = _lib.load()
+    hw_in, c_in, k, stride, hw_out, c_out = geom
+    dev = x_planes[0].device
+    c = _lib.Conv()
+    c.dgrad, c.samples = int(dgrad), samples
+    c.hw_in, c.c_in, c.k, c.stride, c.hw_out, c.c_out = geom
+    if dgrad:
+        c.x = _tensor_planes(x_planes, samples * hw_out * hw_out, c_out)
+        out_shape = (samples, hw_in, hw_in, c_in)
+    else:
+        c.x = _tensor_planes(x_planes, samples * hw_in * hw_in, c_in)
+        out_shape = (samples, hw_out, hw_out, c_out)
+    c.w = _planes_struct(w_planes, w_planes[0].shape[0], w_planes[0].shape[1])
+    outs = [torch.zeros(out_shape, dtype=torch.bfloat16, device=dev) for _ in range(out_planes)]
+    c.out = _tensor_planes(outs, out_shape[0] * out_shape[1] * out_shape[2], out_shape[3])
+    c.bias = bias.data_ptr() if bias is not None else None
+    c.relu = int(relu)
+    if mask is not None:
+        c.mask_plane, c.mask_samples = mask.data_ptr(), mask_samples or mask.shape[0]
+    if pairs is None:
+        pairs = PAIRS[{1: 1, 2: 3, 3: 6}[min(len(x_planes), len(w_planes))]]
+    c.num_pairs = len(pairs)
+    for i, (pa, pb) in enumerate(pairs):
+        c.pair_a[i], c.pair_b[i] = pa, pb
+    if not lib.acx_conv_supported(ctypes.byref(c)):
+        raise _lib.AcxError("acx_conv: unsupported geometry %r (dgrad=%s)" % (geom, dgrad))
+    _lib.check(lib.acx_conv(ctypes.byref(c), _stream()))
+    return outs
+
+
+def conv_dgrad_weights(w, geom):
+    """fp32 HWIO weights [k*k*c_in, c_out] -> 3 bf16 planes [stride^2*c_in, pad8((k/stride)^2*c_out)] (acx_conv_dgrad_weights)."""
+    hw_in, c_in, k, stride, hw_out, c_out = geom
+    m = k // stride
+    rows, ld = stride * stride * c_in, pad8(m * m * c_out)
+    planes = [torch.empty((rows, ld), dtype=torch.bfloat16, device=w.device) for _ in range(3)]
+    arr = (ctypes.c_void_p * 3)(*[p.data_ptr() for p in planes])
+    _lib.check(_lib.load().acx_conv_dgrad_weights(_ptr(w.contiguous().float()), hw_in, c_in, k, stride, hw_out, c_out, arr, ld,
+                                                  _stream()))
+    return planes

@@ -116,6 +116,34 @@ int acx_debug_tc_error(void);
  * 0 restores the built-in values. */
 void acx_debug_set_mn_desc(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t kstep_bytes);
 
+/* ---- implicit-GEMM convolution on bf16 planes (tcgen05 / TMEM / N-d TMA boxes) ---------------- */
+/* nn.conv2d (nn.py:88-110: NHWC, VALID, HWIO weights) without a patch matrix, for kernels whose size is a multiple of the
+ * stride (the 4x4/2 and 3x3/1 layers of envs/atari/model.py:180-199):
+ *   dgrad == 0:  out[samples, hw_out, hw_out, c_out] = relu?(conv(x, W) + bias);
+ *                x planes [samples, hw_in, hw_in, c_in] (stride * c_in == 64), w planes = W^T [c_out, k*k*c_in] (K-major)
+ *   dgrad == 1:  out[samples, hw_in, hw_in, c_in] = (mask > 0) * conv_transpose(x, W)   (what tf.gradients computes for
+ *                objectives.py:79); x planes = the output gradient [samples, hw_out, hw_out, c_out], w planes = the
+ *                rearranged weights written by acx_conv_dgrad_weights, mask_plane = hi plane of the forward activation
+ *                below ([mask_samples, hw_in, hw_in, c_in]; sample r uses r % mask_samples) or NULL.
+ * The result is written as out.num_planes bf16 planes (ld = channels).  acx_conv_supported tells whether a geometry is
+ * implemented; anything else must use the im2col + acx_gemm route. */
+typedef struct {
+  int dgrad;
+  int samples;
+  int hw_in, c_in, k, stride, hw_out, c_out;
+  acx_planes_t x, w, out;
+  const float* bias;                   /* [c_out] or NULL (forward only) */
+  int relu;                            /* forward only */
+  const void* mask_plane; int mask_samples;   /* dgrad only */
+  int num_pairs; int pair_a[6], pair_b[6];    /* plane pairs (x plane, w plane) accumulated in fp32 */
+} acx_conv_t;
+int acx_conv_supported(const acx_conv_t* c);
+int acx_conv(const acx_conv_t* c, void* stream);
+/* fp32 HWIO weights [k*k*c_in, c_out] -> 3 bf16 planes [stride^2 * c_in, ld] (ld >= (k/stride)^2 * c_out, multiple of 8):
+ * row (py, px, ci), column (i, j, co) holds W[stride*i + py, stride*j + px, ci, co]. */
+int acx_conv_dgrad_weights(const float* d_w, int hw_in, int c_in, int k, int stride, int hw_out, int c_out,
+                           void* const* d_planes, int ld, void* stream);
+
 /* ---- learner (one process per GPU) ----------------------------------------------------------- */
 typedef struct {
   int num_envs, num_steps, num_actions, conv3_filters;
@@ -140,6 +168,8 @@ typedef struct {
                                   3 = single-plane bf16 everywhere (fastest; not parity grade) */
   int use_graphs;              /* 1 = capture each (phase, schedule variant) into a CUDA graph on its second use and replay
                                   it afterwards (needs a non-NULL stream); 0 = launch kernel by kernel */
+  int conv_impl;               /* 0 = implicit-GEMM forward and gather-form input gradient for conv2 / conv3 (acx_conv) when the
+                                  geometry is supported (conv3_filters 32 or 64), 1 = im2col + GEMM + col2im everywhere */
   int num_lanes;               /* concurrent lanes inside one update: 0 = default (3: forward/dgrad chain | input factors |
                                   wgrad + output factors, forked and joined with events on library-owned streams, so the
                                   caller still orders everything through `stream`); 1 = strictly serial on `stream` */
