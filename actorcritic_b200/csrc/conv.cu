@@ -16,6 +16,7 @@
 //
 // Warp roles as in gemm.cu (192 threads): warp 0 TMA producer, warp 1 TMEM + MMA issuer, warps 2..5 epilogue.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
@@ -52,6 +53,7 @@ struct ConvTcParams {
   int npl, ldcp;
   const bf16* mask;
   int mask_samples;
+  int debug;   // ACX_CONV_DEBUG bits (performance triage only): 1 skip activation loads, 2 skip weight loads, 4 skip MMAs, 8 skip stores
 };
 
 __global__ void __launch_bounds__(192, 1)
@@ -75,7 +77,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tmem_cols = (uint32_t)(2 * BN);   // two accumulators: 64, 128 or 256 columns
+  const uint32_t tmem_cols = (uint32_t)((p.debug & 16) ? 4 * BN : 2 * BN);   // two accumulators: 64, 128 or 256 columns
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -96,7 +98,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
   const int sub_tile_bytes = CV_A_TILE / p.nsub;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       // ===== TMA producer: per k-block one box per (plane, sub-tile) of the activation + the weight tile =====
       int it = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -106,17 +108,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
           const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
           const int nload = min(p.nsub, p.num_sub - kb * p.nsub);
           mbar_wait(&empty_bar[s], ph ^ 1u, 1);
-          mbar_expect_tx(&full_bar[s], (uint32_t)(p.npa * nload * p.sub_bytes + p.npb * b_tile_bytes));
+          __syncwarp();
+          if (!elect_one()) continue;
+          mbar_expect_tx(&full_bar[s], (uint32_t)(((p.debug & 1) ? 0 : p.npa * nload * p.sub_bytes) +
+                                                  ((p.debug & 2) ? 0 : p.npb * b_tile_bytes)));
           uint8_t* a_s = smem + s * stage_bytes;
           uint8_t* b_s = a_s + p.npa * CV_A_TILE;
-          for (int i = 0; i < p.npa; ++i) {
+          for (int i = 0; i < p.npa && !(p.debug & 1); ++i) {
             const CUtensorMap* ma = i == 0 ? &ta0 : (i == 1 ? &ta1 : &ta2);
             for (int j = 0; j < nload; ++j) {
               const int t = kb * p.nsub + j;
               tma_load_5d(a_s + i * CV_A_TILE + j * sub_tile_bytes, ma, &full_bar[s], 0, p.tc1[t], p.tc2[t], p.tc3[t], sample0);
             }
           }
-          for (int i = 0; i < p.npb; ++i) {
+          for (int i = 0; i < p.npb && !(p.debug & 2); ++i) {
             const CUtensorMap* mb = i == 0 ? &tb0 : (i == 1 ? &tb1 : &tb2);
             tma_load_2d(b_s + i * b_tile_bytes, mb, &full_bar[s], kb * CV_BK, 0);
           }
@@ -141,19 +146,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
         mbar_wait(&full_bar[s], ph, 2);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const int nload = min(p.nsub, p.num_sub - kb * p.nsub);
           const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
           const uint32_t b_addr = a_addr + (uint32_t)(p.npa * CV_A_TILE);
           uint32_t acc_flag = kb > 0 ? 1u : 0u;
-          for (int pr = 0; pr < p.num_pairs; ++pr) {
+          for (int pr = 0; pr < p.num_pairs && !(p.debug & 4); ++pr) {
+            // triage knob 16: odd pairs accumulate into a second, independent accumulator
+            const uint32_t d_acc = d_tmem + (uint32_t)(((p.debug & 16) && (pr & 1)) ? 2 * BN : 0);
             const uint64_t b_desc0 = make_smem_desc_sw(b_addr + (uint32_t)(p.pair_b[pr] * b_tile_bytes), 16u, 1024u, 2u);
             for (int j = 0; j < nload; ++j) {
               uint64_t ad = make_smem_desc_sw(a_addr + (uint32_t)(p.pair_a[pr] * CV_A_TILE + j * sub_tile_bytes), 16u, a_sbo, a_layout);
               // the weight tile is 64 K-columns wide (128-byte rows): sub-tile j starts j * (128 / nsub) bytes into the row
               uint64_t bd = b_desc0 + (uint64_t)((uint32_t)(j * (128 / p.nsub)) >> 4);
               for (int kk = 0; kk < ksteps; ++kk) {
-                umma_bf16(d_tmem, ad, bd, idesc, acc_flag);
+                umma_bf16(d_acc, ad, bd, idesc, acc_flag);
                 acc_flag = 1u;
                 ad += 2;   // 16 bf16 = 32 bytes along K inside the swizzle row
                 bd += 2;
@@ -164,11 +171,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
         }
         __syncwarp();
       }
-      if (lane == 0) umma_commit(&acc_full[buf]);
+      if (elect_one()) umma_commit(&acc_full[buf]);
       __syncwarp();
     }
   } else {
     // ===== epilogue: TMEM -> registers -> per-warp shared-memory transpose -> bf16 planes =====
+    // A lane owns 4 consecutive columns of CH / 4-lane rows.  Which output element a (tile row, column) pair lands on
+    // does not depend on the tile, only its sample base does: the per-lane row and column offsets are computed once.
     const int q = warp & 3;
     float* st = epi + (size_t)q * 32 * CV_EPI_LD;
     const int CH = BN >= 64 ? 64 : 32;
@@ -179,19 +188,55 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
     bf16* const cp0 = p.cp[0];
     bf16* const cp1 = p.cp[1];
     bf16* const cp2 = p.cp[2];
-    const int npl = p.npl, ldcp = p.ldcp;
+    const int npl = p.npl;
     const float alpha = p.alpha;
-    const float* const bias = p.bias;
     const bool relu = p.relu != 0;
     const bf16* const mask = p.mask;
+    constexpr int MAX_IT = 16;
+    constexpr uint32_t NO_ROW = 0xffffffffu;
+    const int nit = 32 / rpi;
+    uint32_t row_off[MAX_IT];   // element offset of tile row (q*32 + rsub + t*rpi) relative to the tile's base
+#pragma unroll
+    for (int t = 0; t < MAX_IT; ++t) {
+      const int i = q * 32 + rsub + t * rpi;
+      row_off[t] = NO_ROW;
+      if (t < nit && i < p.rows_valid && !(p.debug & 8)) {
+        if (!p.dgrad) {
+          row_off[t] = (uint32_t)(i * p.ldcp);
+        } else {   // row (a, b) of the sample -> the s x s output cell at pixel (s*a, s*b)
+          const int a = i / p.hq, b = i - a * p.hq;
+          row_off[t] = (uint32_t)(((p.s * a) * p.hw_in + p.s * b) * p.c_in);
+        }
+      }
+    }
+    uint32_t col_off[2];        // element offset of this lane's 4 columns, per 64-column chunk
+    float4 bias4[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int n = c * CH + cl;
+      col_off[c] = (uint32_t)n;
+      bias4[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n < BN) {
+        if (p.dgrad) {   // column (py, px, ci) -> pixel (py, px) inside the cell
+          const int pp = n / p.c_in, ci = n - pp * p.c_in;
+          const int py = pp / p.s, px = pp - py * p.s;
+          col_off[c] = (uint32_t)((py * p.hw_in + px) * p.c_in + ci);
+        }
+        if (p.bias) bias4[c] = make_float4(__ldg(p.bias + n), __ldg(p.bias + n + 1), __ldg(p.bias + n + 2), __ldg(p.bias + n + 3));
+      }
+    }
+    const size_t tile_stride = p.dgrad ? (size_t)p.hw_in * p.hw_in * p.c_in : (size_t)p.rows_valid * p.ldcp;
     int lt = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
       const int buf = lt & 1;
       const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
       mbar_wait(&acc_full[buf], aph, 3);
       tc_fence_after();
-      const int sample0 = tile * p.ts;
-      for (int c0 = 0; c0 < BN; c0 += CH) {
+      const size_t base = (size_t)tile * tile_stride;
+      const size_t mbase = p.dgrad ? (size_t)(tile % p.mask_samples) * tile_stride : 0;
+      // forward: rows of the last tile beyond the batch do not exist
+      const uint32_t row_limit = p.dgrad ? 0xfffffffeu : (uint32_t)min(p.rows_valid, p.total_rows - tile * p.rows_valid) * (uint32_t)p.ldcp;
+      for (int c0 = 0, c = 0; c0 < BN; c0 += CH, ++c) {
         uint32_t raw[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0);
         tmem_ld32(taddr, raw);
@@ -213,59 +258,46 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
         __syncwarp();
-        const int n = c0 + cl;
-        float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
-        if (bias) {
-          b0 = __ldg(bias + n);
-          b1 = __ldg(bias + n + 1);
-          b2 = __ldg(bias + n + 2);
-          b3 = __ldg(bias + n + 3);
-        }
-        size_t col_off = (size_t)n;
-        if (p.dgrad) {   // column (py, px, ci) -> offset of pixel (py, px) inside the s x s output cell
-          const int pp = n / p.c_in, ci = n - pp * p.c_in;
-          const int py = pp / p.s, px = pp - py * p.s;
-          col_off = (size_t)(py * p.hw_in + px) * p.c_in + ci;
+        const uint32_t coff = c == 0 ? col_off[0] : col_off[1];
+        const float4 b4 = c == 0 ? bias4[0] : bias4[1];
+        // pass 1: every ReLU-mask word of this chunk is requested before the first one is used (one L2 round trip per
+        // chunk instead of one per row)
+        uint2 mw[MAX_IT];
+        if (mask) {
+#pragma unroll
+          for (int t = 0; t < MAX_IT; ++t) {
+            mw[t] = make_uint2(0x3f803f80u, 0x3f803f80u);   // bf16 1.0: keep
+            if (row_off[t] < row_limit) mw[t] = __ldg(reinterpret_cast<const uint2*>(mask + mbase + row_off[t] + coff));
+          }
         }
         const float* src = st + rsub * CV_EPI_LD + cl;
-        for (int r = rsub; r < 32; r += rpi, src += rpi * CV_EPI_LD) {
-          const int i = q * 32 + r;
-          if (i >= p.rows_valid) break;
-          size_t row_off, mrow_off = 0;
-          if (!p.dgrad) {
-            const int out_row = tile * p.rows_valid + i;
-            if (out_row >= p.total_rows) break;
-            row_off = (size_t)out_row * ldcp;
-          } else {   // row (a, b) of sample r -> pixel (s*a, s*b); cells that start beyond the input edge do not exist
-            const int a = i / p.hq, b = i - a * p.hq;
-            const size_t pix = (size_t)(p.s * a) * p.hw_in + p.s * b;
-            row_off = ((size_t)sample0 * p.hw_in * p.hw_in + pix) * p.c_in;
-            mrow_off = ((size_t)(sample0 % p.mask_samples) * p.hw_in * p.hw_in + pix) * p.c_in;
+#pragma unroll
+        for (int t = 0; t < MAX_IT; ++t) {
+          if (row_off[t] < row_limit) {
+            const float4 a4 = *reinterpret_cast<const float4*>(src + t * rpi * CV_EPI_LD);
+            float v0 = fmaf(alpha, a4.x, b4.x), v1 = fmaf(alpha, a4.y, b4.y), v2 = fmaf(alpha, a4.z, b4.z), v3 = fmaf(alpha, a4.w, b4.w);
+            if (relu) {
+              v0 = fmaxf(v0, 0.0f);
+              v1 = fmaxf(v1, 0.0f);
+              v2 = fmaxf(v2, 0.0f);
+              v3 = fmaxf(v3, 0.0f);
+            }
+            if (mask) {
+              if (!(__uint_as_float(mw[t].x << 16) > 0.0f)) v0 = 0.0f;
+              if (!(__uint_as_float(mw[t].x & 0xffff0000u) > 0.0f)) v1 = 0.0f;
+              if (!(__uint_as_float(mw[t].y << 16) > 0.0f)) v2 = 0.0f;
+              if (!(__uint_as_float(mw[t].y & 0xffff0000u) > 0.0f)) v3 = 0.0f;
+            }
+            bf16 h0, h1, h2, h3, m0, m1, m2, m3, l0, l1, l2, l3;
+            split3(v0, h0, m0, l0);
+            split3(v1, h1, m1, l1);
+            split3(v2, h2, m2, l2);
+            split3(v3, h3, m3, l3);
+            const size_t idx = base + row_off[t] + coff;
+            *reinterpret_cast<uint2*>(cp0 + idx) = pack4(h0, h1, h2, h3);
+            if (npl > 1) *reinterpret_cast<uint2*>(cp1 + idx) = pack4(m0, m1, m2, m3);
+            if (npl > 2) *reinterpret_cast<uint2*>(cp2 + idx) = pack4(l0, l1, l2, l3);
           }
-          const float4 a4 = *reinterpret_cast<const float4*>(src);
-          float v0 = fmaf(alpha, a4.x, b0), v1 = fmaf(alpha, a4.y, b1), v2 = fmaf(alpha, a4.z, b2), v3 = fmaf(alpha, a4.w, b3);
-          if (relu) {
-            v0 = fmaxf(v0, 0.0f);
-            v1 = fmaxf(v1, 0.0f);
-            v2 = fmaxf(v2, 0.0f);
-            v3 = fmaxf(v3, 0.0f);
-          }
-          if (mask) {
-            const uint2 mw = *reinterpret_cast<const uint2*>(mask + mrow_off + col_off);
-            if (!(__uint_as_float(mw.x << 16) > 0.0f)) v0 = 0.0f;
-            if (!(__uint_as_float(mw.x & 0xffff0000u) > 0.0f)) v1 = 0.0f;
-            if (!(__uint_as_float(mw.y << 16) > 0.0f)) v2 = 0.0f;
-            if (!(__uint_as_float(mw.y & 0xffff0000u) > 0.0f)) v3 = 0.0f;
-          }
-          bf16 h0, h1, h2, h3, m0, m1, m2, m3, l0, l1, l2, l3;
-          split3(v0, h0, m0, l0);
-          split3(v1, h1, m1, l1);
-          split3(v2, h2, m2, l2);
-          split3(v3, h3, m3, l3);
-          const size_t idx = row_off + col_off;
-          *reinterpret_cast<uint2*>(cp0 + idx) = pack4(h0, h1, h2, h3);
-          if (npl > 1) *reinterpret_cast<uint2*>(cp1 + idx) = pack4(m0, m1, m2, m3);
-          if (npl > 2) *reinterpret_cast<uint2*>(cp2 + idx) = pack4(l0, l1, l2, l3);
         }
         __syncwarp();
       }
@@ -440,6 +472,14 @@ static int launch_conv(const CUtensorMap* ta, const CUtensorMap* tb, ConvTcParam
   if (!configured) {
     ACX_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM_LIMIT));
     configured = true;
+  }
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("ACX_CONV_DEBUG");
+      dbg = e ? atoi(e) : 0;
+    }
+    p.debug = dbg;
   }
   const int grid = std::min(p.num_tiles, conv_num_sms());
   const int smem = CV_SMEM_FIXED + p.stages * stage_bytes;

@@ -190,8 +190,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
   };
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
+    {
+      // ===== TMA producer (whole warp waits, one elected lane issues) =====
       int it = 0;
       for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
         int tm, tn, split;
@@ -210,6 +210,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
           const int s = it % p.stages;
           const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
           mbar_wait(&empty_bar[s], ph ^ 1u, 1);
+          __syncwarp();
+          if (!elect_one()) continue;
           mbar_expect_tx(&full_bar[s], tx);
           uint8_t* a_s = smem + s * stage_bytes;
           if (p.panel) {
@@ -266,7 +268,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
         mbar_wait(&full_bar[s], ph, 2);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const int kvalid = min(BK, p.k - kb * BK);
           const int ksteps = (kvalid + 15) >> 4;
           const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
@@ -308,7 +310,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
         }
         __syncwarp();
       }
-      if (lane == 0) umma_commit(&acc_full[buf]);
+      if (elect_one()) umma_commit(&acc_full[buf]);
       __syncwarp();
     }
   } else {
@@ -431,7 +433,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
             // general path: ragged right edge and / or ReLU mask of the forward activation
             int mrow = mask ? (m0 + rsub) % mask_rows : 0;
             const int mstep = mask ? rpi % mask_rows : 0;
-            for (int r = rsub; r < rows_valid; r += rpi, src += rpi * EPI_LD) {
+            // every mask word of this chunk is requested before the first one is used: one L2 round trip per chunk
+            // instead of one per row (whole 4-column groups; the ragged edge loads element-wise below)
+            uint2 mwp[16];
+            if (mask && n + 3 < on) {
+              int mr = mrow;
+#pragma unroll
+              for (int t = 0; t < 16; ++t) {
+                mwp[t] = make_uint2(0u, 0u);
+                if (rsub + t * rpi < rows_valid) {
+                  mwp[t] = __ldg(reinterpret_cast<const uint2*>(mask + (size_t)mr * mask_ld + n));   // mask_ld % 8 == 0, n % 4 == 0
+                  mr += mstep;
+                  if (mr >= mask_rows) mr -= mask_rows;
+                }
+              }
+            }
+            int t_it = 0;
+            for (int r = rsub; r < rows_valid; r += rpi, src += rpi * EPI_LD, ++t_it) {
               const int m = m0 + r;
               const float4 a4 = *reinterpret_cast<const float4*>(src);
               float v[4] = {fmaf(alpha, a4.x, b0), fmaf(alpha, a4.y, b1), fmaf(alpha, a4.z, b2), fmaf(alpha, a4.w, b3)};
@@ -442,7 +460,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
               if (mask) {
                 const bf16* mk = mask + (size_t)mrow * mask_ld + n;
                 if (n + 3 < on) {
-                  const uint2 mw = *reinterpret_cast<const uint2*>(mk);   // mask_ld % 8 == 0, n % 4 == 0
+                  uint2 mw = mwp[0];
+#pragma unroll
+                  for (int t = 1; t < 16; ++t)
+                    if (t == t_it) mw = mwp[t];
                   if (!(__uint_as_float(mw.x << 16) > 0.0f)) v[0] = 0.0f;
                   if (!(__uint_as_float(mw.x & 0xffff0000u) > 0.0f)) v[1] = 0.0f;
                   if (!(__uint_as_float(mw.y << 16) > 0.0f)) v[2] = 0.0f;

@@ -114,6 +114,8 @@ struct acx_learner {
   float *dP, *logits, *values, *targets, *adv, *dheads;
   size_t dgrad_chunk_bytes;
   Planes wT[4], wN[4];
+  Planes wD[4];              // gather-form dgrad operand of conv2 / conv3 (conv.cu), unused otherwise
+  bool conv_tc[4];           // layer computes its input gradient with the gather-form tensor-core kernel (conv.cu)
   Planes Vp, Wt;
   float* dot_partials;
   Scratch scr[kMaxLanes];
@@ -301,6 +303,16 @@ static size_t layout(acx_learner* l, uint8_t* base) {
     l->wT[i] = take_planes(ar, 3, l->L[i].C, pad8(l->L[i].K));   // W^T [C, K]   (forward: B operand, K-major)
     l->wN[i] = take_planes(ar, 3, l->L[i].K, pad8(l->L[i].C));   // W   [K, C]   (dgrad:   B operand, K-major)
   }
+  for (int i = 1; i <= 2; ++i) {
+    const Layer& L = l->L[i];
+    const ConvGeom g = {L.hw_in, L.cin, L.k, L.s, L.hw_out, L.C};
+    l->conv_tc[i] = l->cfg.conv_impl == 0 && l->cfg.gemm_impl == 0 && conv_tc_supported(g, 1);
+    if (l->conv_tc[i]) {
+      const int m = L.k / L.s;
+      l->wD[i] = take_planes(ar, 3, (size_t)L.s * L.s * L.cin, pad8(m * m * L.C));   // rows (py,px,ci), K = (i,j,co)
+    }
+  }
+  l->conv_tc[0] = l->conv_tc[3] = false;
   // ---- activations (forward rows R = N + E; backward rows 2N = true-loss rows then Fisher-sample rows)
   const int np = l->act_planes;
   l->P1 = take_planes(ar, 1, (size_t)R * 400, 256);
@@ -410,9 +422,8 @@ static Lane lane_of(acx_learner* l, int i, cudaStream_t main_st) {
   return Lane{i == 0 ? main_st : l->side[i - 1], &l->scr[i], i};
 }
 
-// everything enqueued on `from` so far happens before whatever is enqueued on `to` from now on
-static int order_after(acx_learner* l, cudaStream_t from, cudaStream_t to) {
-  if (from == to) return 0;
+// an event from the per-update pool, recorded at the current tail of `from`
+static int record_tail(acx_learner* l, cudaStream_t from, cudaEvent_t* out) {
   if (l->ev_next == l->lane_events.size()) {
     cudaEvent_t e;
     ACX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -420,6 +431,15 @@ static int order_after(acx_learner* l, cudaStream_t from, cudaStream_t to) {
   }
   cudaEvent_t e = l->lane_events[l->ev_next++];
   ACX_CUDA(cudaEventRecord(e, from));
+  *out = e;
+  return 0;
+}
+// everything enqueued on `from` so far happens before whatever is enqueued on `to` from now on
+static int order_after(acx_learner* l, cudaStream_t from, cudaStream_t to) {
+  if (from == to) return 0;
+  cudaEvent_t e;
+  int r = record_tail(l, from, &e);
+  if (r) return r;
   ACX_CUDA(cudaStreamWaitEvent(to, e, 0));
   return 0;
 }
@@ -449,6 +469,23 @@ struct GemmOut {
   int mask_ld = 0, mask_rows = 0;
 };
 
+// plane pairs (i, j) with i + j <= level, low orders first
+static int level_pairs(int level, int a_planes, int b_planes, int* pa, int* pb) {
+  int np = 0;
+  for (int s = 0; s <= level && np < 6; ++s)
+    for (int i = 0; i <= s && np < 6; ++i) {
+      const int j = s - i;
+      if (i < a_planes && j < b_planes) {
+        pa[np] = i;
+        pb[np] = j;
+        ++np;
+      }
+    }
+  return np;
+}
+
+static ConvGeom geom_of(const Layer& L) { return ConvGeom{L.hw_in, L.cin, L.k, L.s, L.hw_out, L.C}; }
+
 static int run_gemm(acx_learner* l, const Planes& a, const Planes& b, int trans, int m, int n, int k, int level, float alpha,
                     int symmetric, const GemmOut& o, const Lane& ln) {
   acx_gemm_t g;
@@ -466,17 +503,7 @@ static int run_gemm(acx_learner* l, const Planes& a, const Planes& b, int trans,
   }
   g.trans_a = g.trans_b = trans;
   g.m = m; g.n = n; g.k = k;
-  int np = 0;
-  for (int s = 0; s <= level && np < 6; ++s)
-    for (int i = 0; i <= s && np < 6; ++i) {
-      const int j = s - i;
-      if (i < a.n && j < b.n) {
-        g.pair_a[np] = i;
-        g.pair_b[np] = j;
-        ++np;
-      }
-    }
-  g.num_pairs = np;
+  g.num_pairs = level_pairs(level, a.n, b.n, g.pair_a, g.pair_b);
   g.alpha = alpha;
   g.bias = o.bias;
   g.relu = o.relu;
@@ -527,7 +554,14 @@ static int refresh_weight_planes(acx_learner* l, cudaStream_t st) {
       n[i][q] = i > 0 ? l->wN[i].p[q] : nullptr;   // conv1 has no input gradient
     }
   }
-  return weight_planes(w, kr, cc, t, ldt, n, ldn, 4, st);
+  ACX_TRY(weight_planes(w, kr, cc, t, ldt, n, ldn, 4, st));
+  for (int i = 1; i <= 2; ++i)
+    if (l->conv_tc[i]) {
+      const Layer& L = l->L[i];
+      const ConvGeom g = {L.hw_in, L.cin, L.k, L.s, L.hw_out, L.C};
+      ACX_TRY(conv_dgrad_weight_planes(l->params + L.off, g, l->wD[i], st));
+    }
+  return 0;
 }
 
 // input factor of layer `li` from the patch/input planes `x` (first `rows` rows, K columns): SYRK + homogeneous border
@@ -575,6 +609,9 @@ static int input_factor_stage(acx_learner* l, int stage, const Lane& ln) {
 }
 
 // Nature-CNN forward on `rows` observations (envs/atari/model.py:173-217): im2col + GEMM with bias/ReLU epilogues.
+// (The implicit-GEMM forward of conv.cu is NOT used here: a sample's 81 / 49 output locations fill a 128-row MMA tile
+// only to 63-77 %, and with the patch matrices needed anyway by wgrad and the factor SYRKs it measured slower -
+// 72.7 vs 41.4 us for conv2, 47.7 vs 26.0 us for conv3 at 32 x 20.)
 // With `fac` (an ACKTR update past the cold phase) every input factor is issued on lane `fac` the moment its operand
 // is complete, so the factor SYRKs overlap the rest of the forward and the whole backward.
 static int forward(acx_learner* l, const uint8_t* obs, int rows, const Lane& ln, const Lane* fac) {
@@ -629,6 +666,11 @@ static int weight_grad(acx_learner* l, int li, const Planes& x, const Planes& g,
 static int conv_dgrad(acx_learner* l, int li, const Planes& g, const bf16* act_below_hi, const Planes& g_below, int samples,
                       const Lane& ln) {
   const Layer& L = l->L[li];
+  if (l->conv_tc[li]) {   // gather form on the tensor cores: no dP matrix, no col2im pass (conv.cu)
+    int pa[6], pb[6];
+    const int np = level_pairs(l->lvl_bwd, g.n, l->wD[li].n, pa, pb);
+    return conv_tc_dgrad(g, l->wD[li], geom_of(L), samples, act_below_hi, l->N, g_below, np, pa, pb, ln.st);
+  }
   const size_t per_sample = (size_t)L.T * L.K * sizeof(float);
   int chunk = (int)(l->dgrad_chunk_bytes / per_sample);
   if (chunk < 1) chunk = 1;

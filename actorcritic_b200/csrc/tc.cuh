@@ -107,6 +107,18 @@ __device__ __forceinline__ uint2 pack4(bf16 a, bf16 b, bf16 c, bf16 d) {
   return r;
 }
 
+// one lane of a converged warp (elect.sync): unlike `lane == 0`, ptxas then knows that a single thread executes the
+// guarded block, so the uniform-register operands of UTMALDG / UTCHMMA need no per-instruction election loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // N-dimensional TMA tile loads (coordinates innermost first; out-of-range elements are zero-filled)
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
                                             int c3) {

@@ -54,7 +54,7 @@ class EngineConfig:
     gemm_impl: int = 0
     precision: int = 0
     use_graphs: bool = True                 # replay each update as CUDA graphs (captured on the second use of a variant)
-    conv_impl: int = 0                      # 0 = implicit-GEMM conv2/conv3 forward + gather-form dgrad, 1 = im2col route
+    conv_impl: int = 0                      # 0 = gather-form conv2/conv3 input gradient (acx_conv), 1 = GEMM + col2im
     num_lanes: int = 0                      # 0 = default (3 concurrent lanes inside an update), 1 = serial
     seed: int = 0
 

@@ -152,7 +152,7 @@ def _tensor_planes(planes, rows, cols):
 
 
 def conv(x_planes, w_planes, geom, samples, dgrad=False, bias=None, relu=False, mask=None, mask_samples=0, pairs=None,
-         out_planes=3):
+         out_planes=3, outs=None):
     """acx_conv: implicit-GEMM conv forward (x planes [samples,hw_in,hw_in,c_in], w = W^T planes [c_out, k*k*c_in]) or
     gather-form input gradient (x = output-gradient planes [samples,hw_out,hw_out,c_out], w = conv_dgrad_weights planes).
     geom = (hw_in, c_in, k, stride, hw_out, c_out).  Returns the list of bf16 output planes."""
@@ -169,7 +169,8 @@ def conv(x_planes, w_planes, geom, samples, dgrad=False, bias=None, relu=False, 
         c.x = _tensor_planes(x_planes, samples * hw_in * hw_in, c_in)
         out_shape = (samples, hw_out, hw_out, c_out)
     c.w = _planes_struct(w_planes, w_planes[0].shape[0], w_planes[0].shape[1])
-    outs = [torch.zeros(out_shape, dtype=torch.bfloat16, device=dev) for _ in range(out_planes)]
+    if outs is None:
+        outs = [torch.zeros(out_shape, dtype=torch.bfloat16, device=dev) for _ in range(out_planes)]
     c.out = _tensor_planes(outs, out_shape[0] * out_shape[1] * out_shape[2], out_shape[3])
     c.bias = bias.data_ptr() if bias is not None else None
     c.relu = int(relu)

@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--conv3", type=int, default=32)
     ap.add_argument("--precision", type=int, default=0)
     ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--conv-impl", type=int, default=0, help="0 = gather-form conv dgrad (default), 1 = dgrad GEMM + col2im")
     ap.add_argument("--lanes", type=int, default=0, help="concurrent lanes inside an update (0 = library default 3, 1 = serial)")
     ap.add_argument("--invert-every", type=int, default=10, help="diagnostic only: the reference uses 10 (a2c_acktr.py:245)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -216,7 +217,7 @@ def run_native(args, rank, world, local_rank):
     n = envs * t_count
     cfg = eng.EngineConfig(num_envs=envs, num_steps=t_count, conv3_filters=c3, precision=args.precision,
                            world_size=world, seed=1234 + rank, use_graphs=not args.no_graphs,
-                           invert_every=args.invert_every, num_lanes=args.lanes)
+                           invert_every=args.invert_every, num_lanes=args.lanes, conv_impl=args.conv_impl)
     e = eng.Engine(cfg, dev)
     e.set_params(eng.orthogonal_init(4, c3, seed=0))
     # synthetic inputs: 8 resident batches (8 x 19 MB > L2) + the same in pinned host memory for the e2e leg
@@ -369,6 +370,7 @@ def run_native(args, rank, world, local_rank):
         "updates_per_sec": 1e3 / ms_step, "env_frames_per_sec": value * FRAMESKIP,
         "config": {"workload": workload_name(args, world), "precision": args.precision, "cuda_graphs": not args.no_graphs,
                    "lanes": args.lanes if args.lanes > 0 else 3,
+                   "conv": "conv2/conv3 input gradient in gather form on the tensor cores (no patch-gradient matrix, no col2im)" if args.conv_impl == 0 else "dgrad GEMM + col2im",
                    "l2": "8 resident input batches rotated (152 MB > 126 MB L2); per-step intermediates ~0.9 GB, self-flushing",
                    "parallelism": "dp%d (envs sharded, one NCCL all-reduce of grads+factor statistics per update)" % world},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 64,

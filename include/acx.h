@@ -168,8 +168,9 @@ typedef struct {
                                   3 = single-plane bf16 everywhere (fastest; not parity grade) */
   int use_graphs;              /* 1 = capture each (phase, schedule variant) into a CUDA graph on its second use and replay
                                   it afterwards (needs a non-NULL stream); 0 = launch kernel by kernel */
-  int conv_impl;               /* 0 = implicit-GEMM forward and gather-form input gradient for conv2 / conv3 (acx_conv) when the
-                                  geometry is supported (conv3_filters 32 or 64), 1 = im2col + GEMM + col2im everywhere */
+  int conv_impl;               /* 0 = gather-form input gradient of conv2 / conv3 on the tensor cores (acx_conv, dgrad) when the
+                                  geometry is supported (conv3_filters 32 or 64), 1 = GEMM to an fp32 patch-gradient matrix +
+                                  col2im everywhere */
   int num_lanes;               /* concurrent lanes inside one update: 0 = default (3: forward/dgrad chain | input factors |
                                   wgrad + output factors, forked and joined with events on library-owned streams, so the
                                   caller still orders everything through `stream`); 1 = strictly serial on `stream` */

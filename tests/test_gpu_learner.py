@@ -24,10 +24,10 @@ def _engine_mod():
     return engine
 
 
-def _compute(precision, e_count, t_count, c3, obs_kind, mode="true"):
+def _compute(precision, e_count, t_count, c3, obs_kind, mode="true", **kw):
     eng = _engine_mod()
     cfg = eng.EngineConfig(num_envs=e_count, num_steps=t_count, conv3_filters=c3, precision=precision,
-                           num_locations_mode=mode)
+                           num_locations_mode=mode, **kw)
     e, o = LC.make_pair(cfg, seed=1)
     e.set_state(30, 0, False)
     o.global_step = 30
@@ -44,6 +44,21 @@ def _compute(precision, e_count, t_count, c3, obs_kind, mode="true"):
 @pytest.mark.parametrize("e_count,t_count,c3", [(4, 5, 32), (3, 7, 64), (16, 5, 64)])
 def test_phase1_matches_oracle(e_count, t_count, c3):
     errs = _compute(0, e_count, t_count, c3, "sparse")
+    bad = {k: v for k, v in errs.items() if not v["rel"] <= TOL_DEFAULT}
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("kw", [dict(conv_impl=1), dict(num_lanes=1), dict(conv_impl=1, num_lanes=1), dict(use_graphs=False)])
+def test_phase1_alternative_routes_match_oracle(kw):
+    """the im2col + GEMM + col2im route (conv_impl=1, also what an unsupported conv3 width uses) and the strictly serial
+    schedule (num_lanes=1) must give the same results as the default implicit-GEMM / three-lane update."""
+    errs = _compute(0, 4, 5, 32, "sparse", **kw)
+    bad = {k: v for k, v in errs.items() if not v["rel"] <= TOL_DEFAULT}
+    assert not bad, bad
+
+
+def test_phase1_conv3_width_without_implicit_gemm_support():
+    errs = _compute(0, 3, 4, 48, "sparse")
     bad = {k: v for k, v in errs.items() if not v["rel"] <= TOL_DEFAULT}
     assert not bad, bad
 

@@ -1,0 +1,45 @@
+"""One acx_conv launch per case at the headline sizes (32 x 20: 672 forward samples, 1280 backward samples), for ncu.
+usage: conv_one.py [f2|f3|d2|d3] [pairs]"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from actorcritic_b200 import ops  # noqa: E402
+
+case = sys.argv[1] if len(sys.argv) > 1 else "f2"
+npairs = int(sys.argv[2]) if len(sys.argv) > 2 else 6
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 20
+geom = {"f2": (20, 32, 4, 2, 9, 64), "d2": (20, 32, 4, 2, 9, 64), "f3": (9, 64, 3, 1, 7, 32), "d3": (9, 64, 3, 1, 7, 32)}[case]
+hw_in, c_in, k, s, hw_out, c_out = geom
+dgrad = case[0] == "d"
+samples = 1280 if dgrad else 672
+gen = torch.Generator(device="cuda").manual_seed(0)
+w = torch.randn((k * k * c_in, c_out), device="cuda", generator=gen) * 0.05
+pairs = ops.PAIRS[npairs]
+if dgrad:
+    x = torch.randn((samples * hw_out * hw_out, c_out), device="cuda", generator=gen)
+    xp = [p.reshape(samples, hw_out, hw_out, c_out) for p in ops.split_planes(x, 3)]
+    wp = ops.conv_dgrad_weights(w, geom)
+    act = torch.rand((samples // 2, hw_in, hw_in, c_in), device="cuda", generator=gen).to(torch.bfloat16)
+    outs = ops.conv(xp, wp, geom, samples, dgrad=True, mask=act, mask_samples=samples // 2, pairs=pairs)
+    run = lambda: ops.conv(xp, wp, geom, samples, dgrad=True, mask=act, mask_samples=samples // 2, pairs=pairs, outs=outs)
+else:
+    x = torch.rand((samples * hw_in * hw_in, c_in), device="cuda", generator=gen)
+    xp = [p.reshape(samples, hw_in, hw_in, c_in) for p in ops.split_planes(x, 3)]
+    wp = ops.split_planes(w.t().contiguous(), 3)
+    bias = torch.zeros(c_out, device="cuda")
+    outs = ops.conv(xp, wp, geom, samples, bias=bias, relu=True, pairs=pairs)
+    run = lambda: ops.conv(xp, wp, geom, samples, bias=bias, relu=True, pairs=pairs, outs=outs)
+for _ in range(2):
+    run()
+torch.cuda.synchronize()
+ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+ev0.record()
+for _ in range(reps):
+    run()
+ev1.record()
+torch.cuda.synchronize()
+print(case, "pairs", npairs, "dbg", os.environ.get("ACX_CONV_DEBUG", "0"), "us per call", 1e3 * ev0.elapsed_time(ev1) / reps)

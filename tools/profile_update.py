@@ -20,9 +20,12 @@ ap.add_argument("--steps", type=int, default=20)
 ap.add_argument("--conv3", type=int, default=32)
 ap.add_argument("--precision", type=int, default=0)
 ap.add_argument("--with-refresh", action="store_true")
+ap.add_argument("--conv-impl", type=int, default=0)
+ap.add_argument("--lanes", type=int, default=0)
 args = ap.parse_args()
 
-cfg = eng.EngineConfig(num_envs=args.envs, num_steps=args.steps, conv3_filters=args.conv3, precision=args.precision)
+cfg = eng.EngineConfig(num_envs=args.envs, num_steps=args.steps, conv3_filters=args.conv3, precision=args.precision,
+                       conv_impl=args.conv_impl, num_lanes=args.lanes)
 e = eng.Engine(cfg)
 e.set_params(eng.orthogonal_init(4, args.conv3, 0))
 b = synth.rollout(3, args.envs, args.steps, 4)
