@@ -6,6 +6,7 @@
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
 // warps 2..5 = epilogue (one TMEM lane quarter each).
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -15,8 +16,7 @@
 namespace acx {
 
 constexpr int BM = 128;
-constexpr int BK = 64;  // bf16 elements per k-block = one 128-byte swizzle row
-constexpr int A_TILE_BYTES = BM * BK * 2;
+constexpr int BK = 64;  // bf16 elements per k-block: one 128-byte swizzle row (TcParams.bk = 32: half rows, 64-byte swizzle - tuning knob)
 
 struct OutParams {
   int m, n;
@@ -40,6 +40,7 @@ struct TcParams {
   int pair_a[6], pair_b[6];
   int npa, npb;          // planes of A / B that the pairs reference (each is loaded once per k-block)
   int bn;                // tile width (32, 64, 128)
+  int bk;                // k-block depth (64 or 32)
   int stages;            // shared-memory ring depth
   int tiles_m, tiles_n, num_tiles, splits, total_work;
   int symmetric;
@@ -109,7 +110,6 @@ __device__ __forceinline__ void store_pair(const OutParams& o, int m, int n, flo
 
 
 constexpr int MAX_STAGES = 8;
-constexpr int PANEL_TILE_BYTES = 4 * BK * 128;           // panel mode: 64 k-rows x 256 columns of one plane
 constexpr int EPI_LD = 68;                              // padded row of the per-warp 32 x 64 fp32 staging tile (16-byte multiple)
 constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;          // four epilogue warps
 
@@ -134,10 +134,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
     return;
   }
   const int BN = p.bn;
-  const int b_tile_bytes = BN * BK * 2;
+  const int bk = p.bk;
+  const int a_tile_bytes = BM * bk * 2;
+  const int b_tile_bytes = BN * bk * 2;
+  const int panel_tile_bytes = 4 * bk * 128;   // panel mode: bk k-rows x 256 columns of one plane
   // panel mode: a stage holds, per plane, the 64 k-rows x (up to) 256 columns of X once; the same shared memory feeds
   // the A side and the B side of the three upper 128 x 128 sub-tiles of X^T X
-  const int stage_bytes = p.panel ? p.npa * PANEL_TILE_BYTES : p.npa * A_TILE_BYTES + p.npb * b_tile_bytes;
+  const int stage_bytes = p.panel ? p.npa * panel_tile_bytes : p.npa * a_tile_bytes + p.npb * b_tile_bytes;
   float* epi = reinterpret_cast<float*>(smem + p.stages * stage_bytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(epi) + EPI_BYTES);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
@@ -204,8 +207,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
         const int na = MAJOR == 0 ? 0 : min(BM / 64, (p.out.m - m0 + 63) / 64);
         const int nb = MAJOR == 0 ? 0 : min(BN / 64, (p.out.n - n0 + 63) / 64);
         const int nch = (p.out.n + 63) / 64;   // panel mode: 64-column chunks of X
-        const uint32_t tx = p.panel ? (uint32_t)(p.npa * nch * BK * 128)
-                                    : (MAJOR == 0 ? (uint32_t)stage_bytes : (uint32_t)((p.npa * na + p.npb * nb) * BK * 128));
+        const uint32_t tx = p.panel ? (uint32_t)(p.npa * nch * bk * 128)
+                                    : (MAJOR == 0 ? (uint32_t)stage_bytes : (uint32_t)((p.npa * na + p.npb * nb) * bk * 128));
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
@@ -218,27 +221,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
             for (int i = 0; i < p.npa; ++i) {
               const CUtensorMap* ma = i == 0 ? &ta0 : (i == 1 ? &ta1 : &ta2);
               for (int j = 0; j < nch; ++j)
-                tma_load_2d(a_s + i * PANEL_TILE_BYTES + j * (BK * 128), ma, &full_bar[s], 64 * j, kb * BK);
+                tma_load_2d(a_s + i * panel_tile_bytes + j * (bk * 128), ma, &full_bar[s], 64 * j, kb * bk);
             }
             continue;
           }
-          uint8_t* b_s = a_s + p.npa * A_TILE_BYTES;
+          uint8_t* b_s = a_s + p.npa * a_tile_bytes;
           for (int i = 0; i < p.npa; ++i) {
             const CUtensorMap* ma = i == 0 ? &ta0 : (i == 1 ? &ta1 : &ta2);
-            uint8_t* dst = a_s + i * A_TILE_BYTES;
+            uint8_t* dst = a_s + i * a_tile_bytes;
             if (MAJOR == 0) {
-              tma_load_2d(dst, ma, &full_bar[s], kb * BK, m0);
+              tma_load_2d(dst, ma, &full_bar[s], kb * bk, m0);
             } else {
-              for (int j = 0; j < na; ++j) tma_load_2d(dst + j * (BK * 128), ma, &full_bar[s], m0 + 64 * j, kb * BK);
+              for (int j = 0; j < na; ++j) tma_load_2d(dst + j * (bk * 128), ma, &full_bar[s], m0 + 64 * j, kb * bk);
             }
           }
           for (int i = 0; i < p.npb; ++i) {
             const CUtensorMap* mb = i == 0 ? &tb0 : (i == 1 ? &tb1 : &tb2);
             uint8_t* dst = b_s + i * b_tile_bytes;
             if (MAJOR == 0) {
-              tma_load_2d(dst, mb, &full_bar[s], kb * BK, n0);
+              tma_load_2d(dst, mb, &full_bar[s], kb * bk, n0);
             } else {
-              for (int j = 0; j < nb; ++j) tma_load_2d(dst + j * (BK * 128), mb, &full_bar[s], n0 + 64 * j, kb * BK);
+              for (int j = 0; j < nb; ++j) tma_load_2d(dst + j * (bk * 128), mb, &full_bar[s], n0 + 64 * j, kb * bk);
             }
           }
         }
@@ -248,8 +251,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
     // ===== MMA issuer (one elected lane) =====
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)MAJOR << 15) | ((uint32_t)MAJOR << 16) |
                            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    // K-major tiles: rows of bk elements = one 128-byte (bk = 64) or 64-byte (bk = 32) swizzle row, 8-row atoms
     const uint32_t lbo = MAJOR == 0 ? 16u : p.mn_lbo;
-    const uint32_t sbo = MAJOR == 0 ? 1024u : p.mn_sbo;
+    const uint32_t sbo = MAJOR == 0 ? (bk == 64 ? 1024u : 512u) : p.mn_sbo;
+    const uint32_t layout = (MAJOR == 0 && bk == 32) ? 4u : 2u;   // SWIZZLE_64B : SWIZZLE_128B
     const uint32_t kstep = MAJOR == 0 ? 32u : p.mn_kstep;
     const uint64_t kstep16 = (uint64_t)(kstep >> 4);
     int it = 0, lt = 0;
@@ -269,22 +274,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
         mbar_wait(&full_bar[s], ph, 2);
         tc_fence_after();
         if (elect_one()) {
-          const int kvalid = min(BK, p.k - kb * BK);
+          const int kvalid = min(bk, p.k - kb * bk);
           const int ksteps = (kvalid + 15) >> 4;
           const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-          const uint32_t b_addr = a_addr + (uint32_t)(p.npa * A_TILE_BYTES);
+          const uint32_t b_addr = a_addr + (uint32_t)(p.npa * a_tile_bytes);
           // the descriptor of a tile advanced by `off` bytes is base + (off >> 4): only the 14-bit address field moves
           // (tiles are 1024-byte aligned inside the < 256 KB shared window, so the add never carries out of the field)
-          const uint64_t a_desc0 = make_smem_desc(a_addr, lbo, sbo);
-          const uint64_t b_desc0 = make_smem_desc(b_addr, lbo, sbo);
+          const uint64_t a_desc0 = make_smem_desc_sw(a_addr, lbo, sbo, layout);
+          const uint64_t b_desc0 = make_smem_desc_sw(b_addr, lbo, sbo, layout);
           uint32_t acc_flag = kb > kb0 ? 1u : 0u;
           if (p.panel) {
             // three upper sub-tiles (0,0) (0,1) (1,1): accumulators at TMEM columns 0, 128, 256
             for (int pr = 0; pr < p.num_pairs; ++pr) {
               for (int sub = 0; sub < 3; ++sub) {
                 const int ti = sub == 2 ? 1 : 0, tj = sub >= 1 ? 1 : 0;
-                uint64_t ad = a_desc0 + (uint64_t)((uint32_t)(p.pair_a[pr] * PANEL_TILE_BYTES + ti * A_TILE_BYTES) >> 4);
-                uint64_t bd = a_desc0 + (uint64_t)((uint32_t)(p.pair_b[pr] * PANEL_TILE_BYTES + tj * A_TILE_BYTES) >> 4);
+                uint64_t ad = a_desc0 + (uint64_t)((uint32_t)(p.pair_a[pr] * panel_tile_bytes + ti * a_tile_bytes) >> 4);
+                uint64_t bd = a_desc0 + (uint64_t)((uint32_t)(p.pair_b[pr] * panel_tile_bytes + tj * a_tile_bytes) >> 4);
                 uint32_t flag = (kb > kb0 || pr > 0) ? 1u : 0u;
                 for (int kk = 0; kk < ksteps; ++kk) {
                   umma_bf16(d_tmem + (uint32_t)(sub * 128), ad, bd, idesc, flag);
@@ -296,7 +301,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
             }
           } else {
             for (int pr = 0; pr < p.num_pairs; ++pr) {
-              uint64_t ad = a_desc0 + (uint64_t)((uint32_t)(p.pair_a[pr] * A_TILE_BYTES) >> 4);
+              uint64_t ad = a_desc0 + (uint64_t)((uint32_t)(p.pair_a[pr] * a_tile_bytes) >> 4);
               uint64_t bd = b_desc0 + (uint64_t)((uint32_t)(p.pair_b[pr] * b_tile_bytes) >> 4);
               for (int kk = 0; kk < ksteps; ++kk) {
                 umma_bf16(d_tmem, ad, bd, idesc, acc_flag);
@@ -695,7 +700,8 @@ struct MapKeyHash {
 static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 static std::mutex g_maps_mu;
 
-// row-major bf16 [rows, cols] with leading dimension ld; box = box0 columns x box1 rows, 128B swizzle
+// row-major bf16 [rows, cols] with leading dimension ld; box = box0 columns x box1 rows; the swizzle span is the box row
+// (64 columns: 128B, 32 columns: 64B)
 static int get_tensor_map(const void* ptr, int rows, int cols, int ld, int box0, int box1, CUtensorMap* out) {
   MapKey key{ptr, rows, cols, ld, box0, box1};
   std::lock_guard<std::mutex> lock(g_maps_mu);
@@ -714,8 +720,8 @@ static int get_tensor_map(const void* ptr, int rows, int cols, int ld, int box0,
   cuuint32_t estr[2] = {1, 1};
   CUtensorMap m;
   CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, box0 == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   ACX_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
   if (g_maps.size() > 4096) g_maps.clear();
   g_maps[key] = m;
@@ -742,9 +748,20 @@ static void fill_out(const acx_gemm_t* g, OutParams* o) {
 }
 
 struct TcPlan {
-  int bn, tiles_m, tiles_n, splits, kb_total, kb_per_split, to_ws, panel;
+  int bn, bk, npa, npb, stages, tiles_m, tiles_n, splits, kb_total, kb_per_split, to_ws, panel;
   size_t ws_bytes;
 };
+
+constexpr int SMEM_LIMIT = 232448;                       // 227 KB per CTA on sm_100
+constexpr int SMEM_FIXED = EPI_BYTES + 256;              // epilogue staging + barriers (the base is 1024-aligned)
+static int force_bk() {                                  // tuning knob: ACX_GEMM_BK=32 / 64 overrides the automatic k-block depth
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ACX_GEMM_BK");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
 
 static int pick_bn(const acx_gemm_t* g) {
   if (g->symmetric) return g->n <= 64 ? 64 : 128;   // one tile (0,0) when n <= 64; otherwise square 128-tiles
@@ -758,17 +775,33 @@ static void plan_tc(const acx_gemm_t* g, TcPlan* pl) {
   pl->bn = pick_bn(g);
   pl->tiles_m = ceil_div(g->m, BM);
   pl->tiles_n = ceil_div(g->n, pl->bn);
-  pl->kb_total = ceil_div(g->k, BK);
   int tiles = pl->tiles_m * pl->tiles_n;
   if (g->symmetric) tiles = pl->tiles_n * (pl->tiles_n + 1) / 2;
   // SYRK panel mode: X^T X with 128 < n <= 256 (MN-major): every CTA streams its k-range of X once and feeds all three
   // upper sub-tiles from the same shared memory
   pl->panel = (g->symmetric && g->trans_a && pl->bn == 128 && pl->tiles_n == 2 && g->a.planes[0] == g->b.planes[0]) ? 1 : 0;
   if (pl->panel) tiles = 1;
+  // planes each side loads per k-block, and the ring depth they leave
+  pl->npa = pl->npb = 1;
+  for (int i = 0; i < g->num_pairs && i < 6; ++i) {
+    pl->npa = g->pair_a[i] + 1 > pl->npa ? g->pair_a[i] + 1 : pl->npa;
+    pl->npb = g->pair_b[i] + 1 > pl->npb ? g->pair_b[i] + 1 : pl->npb;
+  }
+  if (pl->panel && pl->npb > pl->npa) pl->npa = pl->npb;   // one plane set serves both operand sides
+  auto stages_for = [&](int bk) {
+    const int stage_bytes = pl->panel ? pl->npa * 4 * bk * 128 : (pl->npa * BM + pl->npb * pl->bn) * bk * 2;
+    const int st = (SMEM_LIMIT - SMEM_FIXED) / stage_bytes;
+    return st > MAX_STAGES ? MAX_STAGES : st;
+  };
+  // Measured at 32 x 20 (ACX_GEMM_BK=32): halving the k-block to get 4-5 ring stages instead of 2 for the 3 + 3 plane GEMMs
+  // is SLOWER (1.26 vs 1.16 ms/update): twice the stage hand-offs, and 64-byte swizzle rows; so 64 unless asked.
+  pl->bk = force_bk() == 32 ? 32 : BK;
+  pl->stages = stages_for(pl->bk);
+  pl->kb_total = ceil_div(g->k, pl->bk);
   int splits = g->splits;
-  if (splits <= 0) {  // auto: about one work item per SM, at least 4 k-blocks per split
+  if (splits <= 0) {  // auto: about one work item per SM, at least 256 elements of K per split
     splits = 148 / (tiles > 0 ? tiles : 1);
-    int cap = pl->kb_total / 4;
+    int cap = pl->kb_total / (4 * (BK / pl->bk));
     if (splits > cap) splits = cap;
     if (splits < 1) splits = 1;
   }
@@ -778,9 +811,6 @@ static void plan_tc(const acx_gemm_t* g, TcPlan* pl) {
   pl->to_ws = (pl->splits > 1 || g->symmetric) ? 1 : 0;
   pl->ws_bytes = pl->to_ws ? (size_t)pl->splits * pl->tiles_m * BM * pl->tiles_n * pl->bn * sizeof(float) : 0;
 }
-
-constexpr int SMEM_LIMIT = 232448;                       // 227 KB per CTA on sm_100
-constexpr int SMEM_FIXED = EPI_BYTES + 256;              // epilogue staging + barriers (the base is 1024-aligned)
 
 // optional timing probe: when enabled, every tensor-core kernel launch (the kernel alone, not the finalize step) is
 // bracketed by two library-owned events on the launching stream; acx_gemm_last_ms() reads the last pair
@@ -840,14 +870,14 @@ static int gemm_tc(const acx_gemm_t* g, cudaStream_t st) {
     const int ia = i < g->a.num_planes ? i : 0, ib = i < g->b.num_planes ? i : 0;
     int r;
     if (major == 0) {
-      r = get_tensor_map(g->a.planes[ia], g->m, g->k, g->a.ld, BK, BM, &ta[i]);
+      r = get_tensor_map(g->a.planes[ia], g->m, g->k, g->a.ld, pl.bk, BM, &ta[i]);
       if (r) return r;
-      r = get_tensor_map(g->b.planes[ib], g->n, g->k, g->b.ld, BK, pl.bn, &tb[i]);
+      r = get_tensor_map(g->b.planes[ib], g->n, g->k, g->b.ld, pl.bk, pl.bn, &tb[i]);
       if (r) return r;
     } else {
-      r = get_tensor_map(g->a.planes[ia], g->k, g->m, g->a.ld, 64, BK, &ta[i]);
+      r = get_tensor_map(g->a.planes[ia], g->k, g->m, g->a.ld, 64, pl.bk, &ta[i]);
       if (r) return r;
-      r = get_tensor_map(g->b.planes[ib], g->k, g->n, g->b.ld, 64, BK, &tb[i]);
+      r = get_tensor_map(g->b.planes[ib], g->k, g->n, g->b.ld, 64, pl.bk, &tb[i]);
       if (r) return r;
     }
   }
@@ -857,21 +887,17 @@ static int gemm_tc(const acx_gemm_t* g, cudaStream_t st) {
   p.kb_total = pl.kb_total;
   p.kb_per_split = pl.kb_per_split;
   p.num_pairs = g->num_pairs;
-  p.npa = p.npb = 1;
   for (int i = 0; i < 6; ++i) {
     p.pair_a[i] = g->pair_a[i];
     p.pair_b[i] = g->pair_b[i];
-    if (i < g->num_pairs) {
-      if (g->pair_a[i] + 1 > p.npa) p.npa = g->pair_a[i] + 1;
-      if (g->pair_b[i] + 1 > p.npb) p.npb = g->pair_b[i] + 1;
-    }
   }
+  p.npa = pl.npa;
+  p.npb = pl.npb;
   p.bn = pl.bn;
+  p.bk = pl.bk;
   p.panel = pl.panel;
-  if (pl.panel && p.npb > p.npa) p.npa = p.npb;   // one plane set serves both operand sides
-  const int stage_bytes = pl.panel ? p.npa * PANEL_TILE_BYTES : p.npa * A_TILE_BYTES + p.npb * pl.bn * BK * 2;
-  p.stages = (SMEM_LIMIT - SMEM_FIXED) / stage_bytes;
-  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  const int stage_bytes = pl.panel ? p.npa * 4 * pl.bk * 128 : (p.npa * BM + p.npb * pl.bn) * pl.bk * 2;
+  p.stages = pl.stages;
   ACX_CHECK(p.stages >= 2, "tile does not fit the shared-memory ring");
   p.tiles_m = pl.tiles_m;
   p.tiles_n = pl.tiles_n;
@@ -883,7 +909,7 @@ static int gemm_tc(const acx_gemm_t* g, cudaStream_t st) {
   p.ws = g->workspace;
   p.ws_ld = pl.tiles_n * pl.bn;
   p.ws_split_stride = (long long)pl.tiles_m * BM * p.ws_ld;
-  p.mn_lbo = g_mn_lbo ? g_mn_lbo : (uint32_t)(BK * 128);
+  p.mn_lbo = g_mn_lbo ? g_mn_lbo : (uint32_t)(pl.bk * 128);
   p.mn_sbo = g_mn_sbo ? g_mn_sbo : 1024u;
   p.mn_kstep = g_mn_kstep ? g_mn_kstep : 2048u;
   const int grid = p.total_work < num_sms() ? p.total_work : num_sms();

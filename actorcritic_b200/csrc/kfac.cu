@@ -154,11 +154,10 @@ __device__ __forceinline__ void invert_block_smem(double (*d)[IB + 1]) {
   __syncthreads();
 }
 
-// per-job scratch inside InvDev::rbuf:  R [IB][n] | Cold [n][IB] | Cnew [n][IB] | Dinv [2][IB][IB] (by pivot parity: the
+// per-job scratch inside InvDev::rbuf:  R [IB][n] | Rold [IB][n] | (spare [IB][n]) | Dinv [2][IB][IB] (by pivot parity: the
 // update kernel of step p reads D_p^-1 while one of its CTAs already writes D_{p+1}^-1)
 __device__ __forceinline__ double* scratch_r(const InvDev& jb) { return jb.rbuf; }
-__device__ __forceinline__ double* scratch_cold(const InvDev& jb) { return jb.rbuf + (size_t)IB * jb.n; }
-__device__ __forceinline__ double* scratch_cnew(const InvDev& jb) { return jb.rbuf + (size_t)2 * IB * jb.n; }
+__device__ __forceinline__ double* scratch_rold(const InvDev& jb) { return jb.rbuf + (size_t)IB * jb.n; }
 __device__ __forceinline__ double* scratch_dinv(const InvDev& jb, int p) {
   return jb.rbuf + (size_t)3 * IB * jb.n + (size_t)(p & 1) * IB * IB;
 }
@@ -178,15 +177,21 @@ __global__ void __launch_bounds__(256) inv_diag0_kernel(const InvDev* __restrict
   for (int e = threadIdx.x; e < IB * IB; e += 256) dinv[e] = d[e >> 5][e & 31];
 }
 
-// step kernel A (panels): grid.x = 2 * nblk.  CTAs [0, nblk): R_j = D^-1 M_pj.  CTAs [nblk, 2 nblk): copy of the old
-// column panel M_ip and Cnew_i = -M_ip D^-1.  1024 threads = one 32 x 32 block.
+// Symmetry.  For an SPD input the Gauss-Jordan iterates keep a signed symmetry: with S = the pivot blocks already
+// processed (blocks < p, pivots go in order), M_ij = M_ji^T when i and j are both in S or both outside, and
+// M_ij = -M_ji^T otherwise.  So only the upper 64 x 64 TILES (tile_i <= tile_j; diagonal tiles in full) are stored and
+// updated - half the flops and half the CTAs of the full update - and everything a step needs follows from the true
+// row panel  Rold_i = M_pi  (stored for tile(i) >= tile(p), else -M_ip^T)  and  R = D^-1 Rold:
+//   M_ij -= sigma_i Rold_i^T R_j   (sigma_i = -1 for processed i, +1 otherwise; i, j != p)
+//   M_pj  = R_j,   M_ip = -sigma_i R_i^T,   M_pp = D^-1.
+//
+// step kernel A (panels): one CTA (1024 threads = one 32 x 32 block) per block b != p: Rold_b and R_b = D^-1 Rold_b.
 __global__ void __launch_bounds__(1024) inv_panels_kernel(const InvDev* __restrict__ jobs, int p, int nblk) {
   const InvDev jb = jobs[blockIdx.z];
   const int n = jb.n;
   const int p0 = p * IB;
   if (p0 >= n) return;
-  const bool is_col_cta = (int)blockIdx.x >= nblk;
-  const int blk = is_col_cta ? blockIdx.x - nblk : blockIdx.x;
+  const int blk = blockIdx.x;
   const int b0 = blk * IB;
   if (b0 >= n || blk == p) return;
   __shared__ double d[IB][IB + 1];
@@ -194,41 +199,38 @@ __global__ void __launch_bounds__(1024) inv_panels_kernel(const InvDev* __restri
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int nb = min(IB, n - p0);
   d[ty][tx] = scratch_dinv(jb, p)[ty * IB + tx];
-  if (!is_col_cta) {
+  if ((b0 >> 6) >= (p0 >> 6)) {   // stored as a row of the pivot
     const int cj = b0 + tx;
     t[ty][tx] = (ty < nb && cj < n) ? jb.m[(size_t)(p0 + ty) * n + cj] : 0.0;
-    __syncthreads();
-    double acc = 0.0;
-#pragma unroll 8
-    for (int k = 0; k < IB; ++k) acc += d[ty][k] * t[k][tx];
-    if (cj < n) scratch_r(jb)[(size_t)ty * n + cj] = acc;
-  } else {
+  } else {                        // only its mirror M_bp is stored (b processed, p not): M_pb = -M_bp^T
     const int gi = b0 + ty;
-    const double c = (gi < n && tx < nb) ? jb.m[(size_t)gi * n + p0 + tx] : 0.0;
-    t[ty][tx] = c;
-    if (gi < n) scratch_cold(jb)[(size_t)gi * IB + tx] = c;
-    __syncthreads();
-    double acc = 0.0;
+    t[tx][ty] = (gi < n && tx < nb) ? -jb.m[(size_t)gi * n + p0 + tx] : 0.0;
+  }
+  __syncthreads();
+  const int cj = b0 + tx;
+  double acc = 0.0;
 #pragma unroll 8
-    for (int k = 0; k < IB; ++k) acc += t[ty][k] * d[k][tx];
-    if (gi < n) scratch_cnew(jb)[(size_t)gi * IB + tx] = -acc;
+  for (int k = 0; k < IB; ++k) acc += d[ty][k] * t[k][tx];
+  if (cj < n) {
+    scratch_rold(jb)[(size_t)ty * n + cj] = t[ty][tx];
+    scratch_r(jb)[(size_t)ty * n + cj] = acc;
   }
 }
 
-// step kernel B (update), CTA tile 64 x 64, 256 threads, 4 x 4 per thread:
-//   M_ij -= Cold_i R_j (i, j != p);  M_ip = Cnew_i;  M_pj = R_j;  M_pp = D^-1;
-// the CTA that owns pivot block p+1 then inverts it (it is final after this update) for the next step.
+// step kernel B (update) over the upper tiles, CTA tile 64 x 64, 256 threads, 4 x 4 per thread; the CTA that owns pivot
+// block p+1 (always inside a diagonal tile) then inverts it - it is final after this update - for the next step.
 __global__ void __launch_bounds__(256) inv_update_kernel(const InvDev* __restrict__ jobs, int p) {
+  if (blockIdx.y > blockIdx.x) return;   // lower tiles are never read
   const InvDev jb = jobs[blockIdx.z];
   const int n = jb.n;
   const int p0 = p * IB;
   if (p0 >= n) return;
   const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
   if (i0 >= n || j0 >= n) return;
-  __shared__ double cs[64][IB + 1];  // Cold tile [64 rows][32]
-  __shared__ double rs[IB][64 + 1];  // R tile    [32][64 cols]
+  __shared__ double cs[64][IB + 1];  // sigma_i Rold^T tile [64 rows][32]
+  __shared__ double rs[IB][64 + 1];  // R tile [32][64 cols]
   const int nb = min(IB, n - p0);
-  const double* cold = scratch_cold(jb);
+  const double* rold = scratch_rold(jb);
   const double* rb = scratch_r(jb);
   {
     // issue every global load before the first shared-memory store
@@ -236,17 +238,16 @@ __global__ void __launch_bounds__(256) inv_update_kernel(const InvDev* __restric
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const int idx = threadIdx.x + 256 * q;
-      const int r = idx / IB, k = idx % IB;
-      const int gi = i0 + r;
-      rc[q] = (gi < n && k < nb && !(gi >= p0 && gi < p0 + IB)) ? cold[(size_t)gi * IB + k] : 0.0;
-      const int k2 = idx / 64, c = idx % 64;
-      const int gj = j0 + c;
-      rr[q] = (gj < n && k2 < nb && !(gj >= p0 && gj < p0 + IB)) ? rb[(size_t)k2 * n + gj] : 0.0;
+      const int k = idx / 64, c = idx % 64;
+      const int gi = i0 + c, gj = j0 + c;
+      const double v = (gi < n && k < nb && !(gi >= p0 && gi < p0 + IB)) ? rold[(size_t)k * n + gi] : 0.0;
+      rc[q] = gi < p0 ? -v : v;
+      rr[q] = (gj < n && k < nb && !(gj >= p0 && gj < p0 + IB)) ? rb[(size_t)k * n + gj] : 0.0;
     }
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const int idx = threadIdx.x + 256 * q;
-      cs[idx / IB][idx % IB] = rc[q];
+      cs[idx % 64][idx / 64] = rc[q];
       rs[idx / 64][idx % 64] = rr[q];
     }
   }
@@ -274,7 +275,6 @@ __global__ void __launch_bounds__(256) inv_update_kernel(const InvDev* __restric
 #pragma unroll
       for (int r = 0; r < 4; ++r) acc[q][r] -= a[q] * b[r];
   }
-  const double* cnew = scratch_cnew(jb);
   const double* dinv = scratch_dinv(jb, p);
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -290,14 +290,15 @@ __global__ void __launch_bounds__(256) inv_update_kernel(const InvDev* __restric
       if (ip && jp)
         *dst = dinv[(gi - p0) * IB + (gj - p0)];
       else if (ip)
-        *dst = rb[(size_t)(gi - p0) * n + gj];
-      else if (jp)
-        *dst = cnew[(size_t)gi * IB + (gj - p0)];
-      else
+        *dst = rb[(size_t)(gi - p0) * n + gj];                 // M_pj = R_j
+      else if (jp) {
+        const double v = rb[(size_t)(gj - p0) * n + gi];       // M_ip = -sigma_i R_i^T
+        *dst = gi < p0 ? v : -v;
+      } else
         *dst = acc[q][r];
     }
   }
-  // next pivot block (p+1) lies inside exactly one 64 x 64 tile; that CTA inverts it now
+  // next pivot block (p+1) lies inside exactly one (diagonal) 64 x 64 tile; that CTA inverts it now
   const int q0 = p0 + IB;
   if (q0 < n && q0 >= i0 && q0 < i0 + 64 && q0 >= j0 && q0 < j0 + 64) {
     __syncthreads();   // this CTA's global writes above are visible to its own threads after the barrier
@@ -322,7 +323,10 @@ __global__ void inv_finish_kernel(const InvDev* __restrict__ jobs) {
     const int r = (int)(i / jb.ld_planes), c = (int)(i % jb.ld_planes);
     float v = 0.0f;
     if (c < n) {
-      v = (float)(0.5 * (jb.m[(size_t)r * n + c] + jb.m[(size_t)c * n + r]));
+      // only the upper 64-tiles hold the inverse (diagonal tiles in full: average their two halves)
+      const int tr = r >> 6, tc = c >> 6;
+      const double up = tr <= tc ? jb.m[(size_t)r * n + c] : jb.m[(size_t)c * n + r];
+      v = (float)(tr == tc ? 0.5 * (up + jb.m[(size_t)c * n + r]) : up);
       jb.inv[(size_t)r * n + c] = v;
     }
     bf16 p0, p1, p2;
@@ -660,7 +664,7 @@ int spd_inverse_batched(const InvJob* h_jobs, const InvJob* d_jobs, int num_jobs
     if (active == 0) break;
     const int nblk = ceil_div(nact, IB);
     if (nblk > 1) {
-      inv_panels_kernel<<<dim3(2 * nblk, 1, active), 1024, 0, st>>>(dj, p, nblk);
+      inv_panels_kernel<<<dim3(nblk, 1, active), 1024, 0, st>>>(dj, p, nblk);
       ACX_LAUNCH_CHECK();
     }
     inv_update_kernel<<<dim3(ceil_div(nact, 64), ceil_div(nact, 64), active), 256, 0, st>>>(dj, p);
