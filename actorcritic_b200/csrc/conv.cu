@@ -14,7 +14,7 @@
 // [hq a][hq b][c_out] of g at (-i, -j): out-of-range coordinates are zero-filled by TMA, which is the padding.  The
 // epilogue scatters (pixel shuffle), applies the ReLU mask of the layer below and splits into bf16 planes.
 //
-// Warp roles as in gemm.cu (192 threads): warp 0 TMA producer, warp 1 TMEM + MMA issuer, warps 2..5 epilogue.
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM + MMA issuer, warps 2..9 epilogue (two per TMEM lane quarter).
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -31,8 +31,8 @@ constexpr int CV_BK = 64;
 constexpr int CV_A_TILE = CV_BM * CV_BK * 2;   // one plane of one k-block (1 x 64-wide or 2 x 32-wide sub-tiles)
 constexpr int CV_MAX_SUB = 16;
 constexpr int CV_MAX_STAGES = 4;
-constexpr int CV_EPI_LD = 68;
-constexpr int CV_EPI_BYTES = 4 * 32 * CV_EPI_LD * 4;
+constexpr int CV_THREADS = 320;                 // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
+constexpr int CV_EPI_BYTES = 8 * 32 * 32 * 4;   // one swizzled 32 x 32 fp32 staging tile per epilogue warp
 constexpr int CV_SMEM_LIMIT = 232448;
 constexpr int CV_SMEM_FIXED = CV_EPI_BYTES + 256;
 
@@ -56,7 +56,7 @@ struct ConvTcParams {
   int debug;   // ACX_CONV_DEBUG bits (performance triage only): 1 skip activation loads, 2 skip weight loads, 4 skip MMAs, 8 skip stores
 };
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(CV_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ CUtensorMap ta1,
                const __grid_constant__ CUtensorMap ta2, const __grid_constant__ CUtensorMap tb0,
                const __grid_constant__ CUtensorMap tb1, const __grid_constant__ CUtensorMap tb2, const ConvTcParams p) {
@@ -86,7 +86,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], 4);
+      mbar_init(&acc_empty[b], BN > 32 ? 8 : 4);   // epilogue warps that drain an accumulator
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -175,16 +175,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
       __syncwarp();
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> per-warp shared-memory transpose -> bf16 planes =====
-    // A lane owns 4 consecutive columns of CH / 4-lane rows.  Which output element a (tile row, column) pair lands on
-    // does not depend on the tile, only its sample base does: the per-lane row and column offsets are computed once.
+    // ===== epilogue (8 warps): TMEM -> registers -> per-warp shared-memory transpose -> bf16 planes =====
+    // Warp w may read the TMEM lane quarter w % 4 (= 32 tile rows); the two warps of a quarter split the 32-column chunks
+    // (chunk c goes to group c & 1).  After the transpose a lane owns 4 consecutive columns of a row: 8 lanes write 64
+    // contiguous bytes per plane.  Which output element a (tile row, column) pair lands on does not depend on the tile,
+    // only its sample base does: the per-lane row and column offsets are computed once.
     const int q = warp & 3;
-    float* st = epi + (size_t)q * 32 * CV_EPI_LD;
-    const int CH = BN >= 64 ? 64 : 32;
-    const int lpr = CH >> 2;
-    const int rpi = 32 / lpr;
-    const int rsub = lane / lpr;
-    const int cl = (lane - rsub * lpr) * 4;
+    const int grp = (warp - 2) >> 2;
+    const int nchunks = BN >> 5;
+    float* st = epi + (size_t)(warp - 2) * (32 * 32);   // 32 x 32 fp32, 16-byte groups XOR-swizzled by the row (no padding)
+    constexpr int CH = 32, LPR = 8, RPI = 4, NIT = 8;
+    const int rsub = lane >> 3;
+    const int cg = lane & 7;              // 4-column group inside the chunk
     bf16* const cp0 = p.cp[0];
     bf16* const cp1 = p.cp[1];
     bf16* const cp2 = p.cp[2];
@@ -192,15 +194,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
     const float alpha = p.alpha;
     const bool relu = p.relu != 0;
     const bf16* const mask = p.mask;
-    constexpr int MAX_IT = 16;
     constexpr uint32_t NO_ROW = 0xffffffffu;
-    const int nit = 32 / rpi;
-    uint32_t row_off[MAX_IT];   // element offset of tile row (q*32 + rsub + t*rpi) relative to the tile's base
+    uint32_t row_off[NIT];   // element offset of tile row (q*32 + rsub + t*RPI) relative to the tile's base
 #pragma unroll
-    for (int t = 0; t < MAX_IT; ++t) {
-      const int i = q * 32 + rsub + t * rpi;
+    for (int t = 0; t < NIT; ++t) {
+      const int i = q * 32 + rsub + t * RPI;
       row_off[t] = NO_ROW;
-      if (t < nit && i < p.rows_valid && !(p.debug & 8)) {
+      if (i < p.rows_valid && !(p.debug & 8)) {
         if (!p.dgrad) {
           row_off[t] = (uint32_t)(i * p.ldcp);
         } else {   // row (a, b) of the sample -> the s x s output cell at pixel (s*a, s*b)
@@ -209,11 +209,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
         }
       }
     }
-    uint32_t col_off[2];        // element offset of this lane's 4 columns, per 64-column chunk
+    uint32_t col_off[2];        // element offset of this lane's 4 columns in the warp's first / second chunk
     float4 bias4[2];
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-      const int n = c * CH + cl;
+      const int n = (grp + 2 * c) * CH + cg * 4;
       col_off[c] = (uint32_t)n;
       bias4[c] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (n < BN) {
@@ -226,80 +226,78 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
       }
     }
     const size_t tile_stride = p.dgrad ? (size_t)p.hw_in * p.hw_in * p.c_in : (size_t)p.rows_valid * p.ldcp;
-    int lt = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
-      const int buf = lt & 1;
-      const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
-      mbar_wait(&acc_full[buf], aph, 3);
-      tc_fence_after();
-      const size_t base = (size_t)tile * tile_stride;
-      const size_t mbase = p.dgrad ? (size_t)(tile % p.mask_samples) * tile_stride : 0;
-      // forward: rows of the last tile beyond the batch do not exist
-      const uint32_t row_limit = p.dgrad ? 0xfffffffeu : (uint32_t)min(p.rows_valid, p.total_rows - tile * p.rows_valid) * (uint32_t)p.ldcp;
-      for (int c0 = 0, c = 0; c0 < BN; c0 += CH, ++c) {
-        uint32_t raw[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0);
-        tmem_ld32(taddr, raw);
-        float4* strow = reinterpret_cast<float4*>(st + lane * CV_EPI_LD);
+    if (grp < nchunks) {   // BN = 32: the second warp of each quarter has nothing to do (and is not counted by acc_empty)
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+        const int buf = lt & 1;
+        const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
+        mbar_wait(&acc_full[buf], aph, 3);
+        tc_fence_after();
+        const size_t base = (size_t)tile * tile_stride;
+        const size_t mbase = p.dgrad ? (size_t)(tile % p.mask_samples) * tile_stride : 0;
+        // forward: rows of the last tile beyond the batch do not exist
+        const uint32_t row_limit =
+            p.dgrad ? 0xfffffffeu : (uint32_t)min(p.rows_valid, p.total_rows - tile * p.rows_valid) * (uint32_t)p.ldcp;
+        for (int ch = grp, c = 0; ch < nchunks; ch += 2, ++c) {
+          uint32_t raw[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + ch * CH);
+          tmem_ld32(taddr, raw);
+          {
+            float4* strow = reinterpret_cast<float4*>(st + lane * 32);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          strow[j] = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]), __uint_as_float(raw[4 * j + 2]),
-                                 __uint_as_float(raw[4 * j + 3]));
-        if (CH == 64) {
-          tmem_ld32(taddr + 32u, raw);
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            strow[8 + j] = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
-                                       __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3]));
-        }
-        if (c0 + CH >= BN) {   // accumulator drained: hand the TMEM buffer back to the MMA warp
-          tc_fence_before();
+            for (int j = 0; j < 8; ++j)
+              strow[j ^ (lane & 7)] = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
+                                                  __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3]));
+          }
+          if (ch + 2 >= nchunks) {   // this warp's share of the accumulator is drained: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+          }
           __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[buf]);
-        }
-        __syncwarp();
-        const uint32_t coff = c == 0 ? col_off[0] : col_off[1];
-        const float4 b4 = c == 0 ? bias4[0] : bias4[1];
-        // pass 1: every ReLU-mask word of this chunk is requested before the first one is used (one L2 round trip per
-        // chunk instead of one per row)
-        uint2 mw[MAX_IT];
-        if (mask) {
+          const uint32_t coff = c == 0 ? col_off[0] : col_off[1];
+          const float4 b4 = c == 0 ? bias4[0] : bias4[1];
+          // pass 1: every ReLU-mask word of this chunk is requested before the first one is used (one L2 round trip per
+          // chunk instead of one per row)
+          uint2 mw[NIT];
+          if (mask) {
 #pragma unroll
-          for (int t = 0; t < MAX_IT; ++t) {
-            mw[t] = make_uint2(0x3f803f80u, 0x3f803f80u);   // bf16 1.0: keep
-            if (row_off[t] < row_limit) mw[t] = __ldg(reinterpret_cast<const uint2*>(mask + mbase + row_off[t] + coff));
+            for (int t = 0; t < NIT; ++t) {
+              mw[t] = make_uint2(0x3f803f80u, 0x3f803f80u);   // bf16 1.0: keep
+              if (row_off[t] < row_limit) mw[t] = __ldg(reinterpret_cast<const uint2*>(mask + mbase + row_off[t] + coff));
+            }
           }
-        }
-        const float* src = st + rsub * CV_EPI_LD + cl;
 #pragma unroll
-        for (int t = 0; t < MAX_IT; ++t) {
-          if (row_off[t] < row_limit) {
-            const float4 a4 = *reinterpret_cast<const float4*>(src + t * rpi * CV_EPI_LD);
-            float v0 = fmaf(alpha, a4.x, b4.x), v1 = fmaf(alpha, a4.y, b4.y), v2 = fmaf(alpha, a4.z, b4.z), v3 = fmaf(alpha, a4.w, b4.w);
-            if (relu) {
-              v0 = fmaxf(v0, 0.0f);
-              v1 = fmaxf(v1, 0.0f);
-              v2 = fmaxf(v2, 0.0f);
-              v3 = fmaxf(v3, 0.0f);
+          for (int t = 0; t < NIT; ++t) {
+            if (row_off[t] < row_limit) {
+              const int r = rsub + t * RPI;
+              const float4 a4 = *reinterpret_cast<const float4*>(st + r * 32 + ((cg ^ (r & 7)) << 2));
+              float v0 = fmaf(alpha, a4.x, b4.x), v1 = fmaf(alpha, a4.y, b4.y), v2 = fmaf(alpha, a4.z, b4.z), v3 = fmaf(alpha, a4.w, b4.w);
+              if (relu) {
+                v0 = fmaxf(v0, 0.0f);
+                v1 = fmaxf(v1, 0.0f);
+                v2 = fmaxf(v2, 0.0f);
+                v3 = fmaxf(v3, 0.0f);
+              }
+              if (mask) {
+                if (!(__uint_as_float(mw[t].x << 16) > 0.0f)) v0 = 0.0f;
+                if (!(__uint_as_float(mw[t].x & 0xffff0000u) > 0.0f)) v1 = 0.0f;
+                if (!(__uint_as_float(mw[t].y << 16) > 0.0f)) v2 = 0.0f;
+                if (!(__uint_as_float(mw[t].y & 0xffff0000u) > 0.0f)) v3 = 0.0f;
+              }
+              bf16 h0, h1, h2, h3, m0, m1, m2, m3, l0, l1, l2, l3;
+              split3(v0, h0, m0, l0);
+              split3(v1, h1, m1, l1);
+              split3(v2, h2, m2, l2);
+              split3(v3, h3, m3, l3);
+              const size_t idx = base + row_off[t] + coff;
+              *reinterpret_cast<uint2*>(cp0 + idx) = pack4(h0, h1, h2, h3);
+              if (npl > 1) *reinterpret_cast<uint2*>(cp1 + idx) = pack4(m0, m1, m2, m3);
+              if (npl > 2) *reinterpret_cast<uint2*>(cp2 + idx) = pack4(l0, l1, l2, l3);
             }
-            if (mask) {
-              if (!(__uint_as_float(mw[t].x << 16) > 0.0f)) v0 = 0.0f;
-              if (!(__uint_as_float(mw[t].x & 0xffff0000u) > 0.0f)) v1 = 0.0f;
-              if (!(__uint_as_float(mw[t].y << 16) > 0.0f)) v2 = 0.0f;
-              if (!(__uint_as_float(mw[t].y & 0xffff0000u) > 0.0f)) v3 = 0.0f;
-            }
-            bf16 h0, h1, h2, h3, m0, m1, m2, m3, l0, l1, l2, l3;
-            split3(v0, h0, m0, l0);
-            split3(v1, h1, m1, l1);
-            split3(v2, h2, m2, l2);
-            split3(v3, h3, m3, l3);
-            const size_t idx = base + row_off[t] + coff;
-            *reinterpret_cast<uint2*>(cp0 + idx) = pack4(h0, h1, h2, h3);
-            if (npl > 1) *reinterpret_cast<uint2*>(cp1 + idx) = pack4(m0, m1, m2, m3);
-            if (npl > 2) *reinterpret_cast<uint2*>(cp2 + idx) = pack4(l0, l1, l2, l3);
           }
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   }
@@ -483,7 +481,7 @@ static int launch_conv(const CUtensorMap* ta, const CUtensorMap* tb, ConvTcParam
   }
   const int grid = std::min(p.num_tiles, conv_num_sms());
   const int smem = CV_SMEM_FIXED + p.stages * stage_bytes;
-  conv_tc_kernel<<<grid, 192, smem, st>>>(ta[0], ta[1], ta[2], tb[0], tb[1], tb[2], p);
+  conv_tc_kernel<<<grid, CV_THREADS, smem, st>>>(ta[0], ta[1], ta[2], tb[0], tb[1], tb[2], p);
   ACX_LAUNCH_CHECK();
   return 0;
 }
