@@ -14,6 +14,12 @@
 // [hq a][hq b][c_out] of g at (-i, -j): out-of-range coordinates are zero-filled by TMA, which is the padding.  The
 // epilogue scatters (pixel shuffle), applies the ReLU mask of the layer below and splits into bf16 planes.
 //
+// Measured on B200 at 2N = 1280 samples (ACX_CONV_DEBUG triage, tools/conv_one.py): both dgrad launches are bound by the
+// tensor pipe's shared-memory operand reads - a 128 x 64 x 16 MMA costs ~86 cycles from 128-byte-swizzled tiles and ~127
+// from the 64-byte-swizzled 32-channel taps of conv3 (floor 32) - not by TMA (skipping every load changes nothing),
+// not by accumulator dependencies (alternating two accumulators changes nothing), and keeping the whole conv3 weight
+// operand resident in shared memory (tried) gains < 2 %.
+//
 // Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM + MMA issuer, warps 2..9 epilogue (two per TMEM lane quarter).
 #include <algorithm>
 #include <cstdlib>
@@ -77,7 +83,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tmem_cols = (uint32_t)((p.debug & 16) ? 4 * BN : 2 * BN);   // two accumulators: 64, 128 or 256 columns
+  const uint32_t tmem_cols = (uint32_t)(2 * BN);   // two accumulators: 64, 128 or 256 columns
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -152,15 +158,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
           const uint32_t b_addr = a_addr + (uint32_t)(p.npa * CV_A_TILE);
           uint32_t acc_flag = kb > 0 ? 1u : 0u;
           for (int pr = 0; pr < p.num_pairs && !(p.debug & 4); ++pr) {
-            // triage knob 16: odd pairs accumulate into a second, independent accumulator
-            const uint32_t d_acc = d_tmem + (uint32_t)(((p.debug & 16) && (pr & 1)) ? 2 * BN : 0);
             const uint64_t b_desc0 = make_smem_desc_sw(b_addr + (uint32_t)(p.pair_b[pr] * b_tile_bytes), 16u, 1024u, 2u);
             for (int j = 0; j < nload; ++j) {
               uint64_t ad = make_smem_desc_sw(a_addr + (uint32_t)(p.pair_a[pr] * CV_A_TILE + j * sub_tile_bytes), 16u, a_sbo, a_layout);
               // the weight tile is 64 K-columns wide (128-byte rows): sub-tile j starts j * (128 / nsub) bytes into the row
               uint64_t bd = b_desc0 + (uint64_t)((uint32_t)(j * (128 / p.nsub)) >> 4);
               for (int kk = 0; kk < ksteps; ++kk) {
-                umma_bf16(d_acc, ad, bd, idesc, acc_flag);
+                umma_bf16(d_tmem, ad, bd, idesc, acc_flag);
                 acc_flag = 1u;
                 ad += 2;   // 16 bf16 = 32 bytes along K inside the swizzle row
                 bd += 2;

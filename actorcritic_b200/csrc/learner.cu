@@ -651,13 +651,18 @@ static int forward(acx_learner* l, const uint8_t* obs, int rows, const Lane& ln,
 }
 
 // weight gradient V_l[:K] = X^T g over the true-loss rows, bias row = column sums of g
-static int weight_grad(acx_learner* l, int li, const Planes& x, const Planes& g, int rows, float alpha, const Lane& ln) {
+static int bias_grad(acx_learner* l, int li, const Planes& g, int rows, const Lane& ln) {
+  const Layer& L = l->L[li];
+  return colsum(g, rows, L.C, 1.0f, ln.sc->colsum_partial, kColsumChunks, l->grads + L.off + (size_t)L.K * L.C, 1, ln.st);
+}
+static int weight_grad(acx_learner* l, int li, const Planes& x, const Planes& g, int rows, float alpha, const Lane& ln,
+                       bool with_bias = true) {
   const Layer& L = l->L[li];
   GemmOut o;
   o.c = l->grads + L.off;
   o.ldc = L.C;
   ACX_TRY(run_gemm(l, x, g, 1, L.K, L.C, rows, l->lvl_bwd, alpha, 0, o, ln));
-  ACX_TRY(colsum(g, rows, L.C, 1.0f, ln.sc->colsum_partial, kColsumChunks, l->grads + L.off + (size_t)L.K * L.C, 1, ln.st));
+  if (with_bias) ACX_TRY(bias_grad(l, li, g, rows, ln));
   return 0;
 }
 
@@ -750,7 +755,10 @@ static int issue_phase1(acx_learner* l, const int32_t* fisher_labels, const floa
     ACX_TRY(fork_lane(l, st, wg_ln));
     ACX_TRY(output_factor(l, 0, offset_rows(l->dpre1, (size_t)N * 400), N * 400, wg_ln));
   }
-  ACX_TRY(weight_grad(l, 0, l->P1, l->dpre1, N * 400, 1.0f / 255.0f, main_ln));
+  // last link of the chain: the weight GEMM stays on the caller's stream, its bias row goes to the (by now idle) factor lane
+  ACX_TRY(fork_lane(l, st, fac_ln));
+  ACX_TRY(bias_grad(l, 0, l->dpre1, N * 400, fac_ln));
+  ACX_TRY(weight_grad(l, 0, l->P1, l->dpre1, N * 400, 1.0f / 255.0f, main_ln, false));
   mark(l, 3, st);
   // ---- join: the caller's stream now also covers the 11 batch factor statistics and every weight gradient
   ACX_TRY(join_lane(l, fac_ln, st));

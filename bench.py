@@ -32,7 +32,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 
-CONV_DGRAD_TRAFFIC = None   # filled from the ncu --set full capture of conv_tc_kernel (profiles/r1_prof_conv_dgrad2_raw.txt)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures of conv_tc_kernel at 2N = 1280
+# samples, conv3_filters = 32 (profiles/r1_prof_conv_dgrad2_raw.txt, r1_prof_conv_dgrad3_raw.txt)
+CONV_DGRAD_TRAFFIC = {"conv2": 113054720, "conv3": 19046912}
 METRIC = "acktr_learner_env_steps_per_sec"
 UNIT = "env-steps/s"
 FRAMESKIP = 4   # a2c_acktr.py:195 - emulator frames per env-step
@@ -319,31 +321,41 @@ def run_native(args, rank, world, local_rank):
     syrk_tflops = syrk_flops / (syrk_ms * 1e-3) / 1e12
 
     # dominant launch of the update since the gather-form input gradient replaced dgrad GEMM + col2im: conv_tc_kernel on
-    # conv2 (rows (r, a, b) = 2N x 100 of a 128-row tile, columns (py, px, ci) = 128, K = (i, j, co) = 256, 6 plane pairs),
-    # timed alone with CUDA events on the launching stream, on operands of the update's own shapes (true + Fisher rows)
-    geom2 = (20, 32, 4, 2, 9, 64)
-    s2 = 2 * n
-    gen = torch.Generator(device=dev).manual_seed(7)
-    gplanes = [pl.reshape(s2, 9, 9, 64) for pl in ops.split_planes(torch.randn((s2 * 81, 64), device=dev, generator=gen) * 1e-3, 3)]
-    wd2 = ops.conv_dgrad_weights(torch.randn((512, 64), device=dev, generator=gen) * 0.05, geom2)
-    act_mask = torch.rand((n, 20, 20, 32), device=dev, generator=gen).to(torch.bfloat16)
+    # conv3 / conv2 (true + Fisher rows = 2N samples), each timed alone with CUDA events on the launching stream on
+    # operands of the update's own shapes; the longer of the two is reported as `roofline`
     npairs = {0: 6, 4: 3, 1: 3, 2: 3, 3: 1}.get(args.precision, 6)
-    dg_out = ops.conv(gplanes, wd2, geom2, s2, dgrad=True, mask=act_mask, mask_samples=n, pairs=ops.PAIRS[npairs])
-    dg_durs = []
-    with torch.cuda.stream(e.stream):
-        for i in range(4):   # first round = warm-up; 10 back-to-back launches per measurement (no host gap inside)
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev0.record()
-            for _ in range(10):
-                ops.conv(gplanes, wd2, geom2, s2, dgrad=True, mask=act_mask, mask_samples=n, pairs=ops.PAIRS[npairs], outs=dg_out)
-            ev1.record()
-            ev1.synchronize()
-            if i >= 1:
-                dg_durs.append(ev0.elapsed_time(ev1) / 10.0)
-    dgrad_ms = float(np.mean(dg_durs))
-    dgrad_flops = 2.0 * s2 * 81 * 512 * 64                    # useful MACs of the transposed convolution x 2
-    dgrad_issued = 2.0 * npairs * s2 * 128 * 128 * 256        # what the tensor pipe executes: 128-row tiles, plane pairs
-    del gplanes, dg_out, act_mask
+    s2 = 2 * n
+
+    def time_conv_dgrad(geom, mask_samples):
+        hw_in, c_in, k, stride, hw_out, c_out = geom
+        gen = torch.Generator(device=dev).manual_seed(7)
+        gpl = [pl.reshape(s2, hw_out, hw_out, c_out)
+               for pl in ops.split_planes(torch.randn((s2 * hw_out * hw_out, c_out), device=dev, generator=gen) * 1e-3, 3)]
+        wd = ops.conv_dgrad_weights(torch.randn((k * k * c_in, c_out), device=dev, generator=gen) * 0.05, geom)
+        act_mask = torch.rand((mask_samples, hw_in, hw_in, c_in), device=dev, generator=gen).to(torch.bfloat16)
+        kw = dict(dgrad=True, mask=act_mask, mask_samples=mask_samples, pairs=ops.PAIRS[npairs])
+        out = ops.conv(gpl, wd, geom, s2, **kw)
+        durs = []
+        with torch.cuda.stream(e.stream):
+            for i in range(4):   # first round = warm-up; 10 back-to-back launches per measurement (no host gap inside)
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+                for _ in range(10):
+                    ops.conv(gpl, wd, geom, s2, outs=out, **kw)
+                ev1.record()
+                ev1.synchronize()
+                if i >= 1:
+                    durs.append(ev0.elapsed_time(ev1) / 10.0)
+        m = k // stride
+        hq = hw_in // stride
+        return dict(ms=float(np.mean(durs)),
+                    flops=2.0 * s2 * hw_out * hw_out * (k * k * c_in) * c_out,            # useful MACs x 2
+                    issued=2.0 * npairs * s2 * 128 * (stride * stride * c_in) * (m * m * c_out),   # 128-row tiles x plane pairs
+                    rows_used=hq * hq)
+
+    dg = {"conv2": time_conv_dgrad((20, 32, 4, 2, 9, 64), n), "conv3": time_conv_dgrad((9, 64, 3, 1, 7, c3), n)} \
+        if c3 in (32, 64) and args.conv_impl == 0 else {}
+    dom = max(dg, key=lambda kk: dg[kk]["ms"]) if dg else None
 
     # K-PRE (BASELINE.json config 5): raw 210x160x3 frame pairs -> gray -> 84x84 -> frame-stack push, HBM bound
     pre = {}
@@ -390,6 +402,43 @@ def run_native(args, rank, world, local_rank):
     ms_step = ms_dev / args.steps
     value = total_envs * t_count / (ms_step * 1e-3)
     e2e_value = total_envs * t_count / (ms_e2e / args.steps * 1e-3)
+    # `roofline` = the dominant (longest) launch of the update; `hbm_kernel` inside it = the largest HBM-bound launch
+    hbm_kernel = {
+        "bound": "hbm",
+        "kernel": "gemm_tc_kernel<1> (SYRK panel mode): conv1 input factor A1 = P1^T P1, 256x256 output, "
+                  "K=%d patch rows - the largest HBM-bound launch" % k_rows,
+        "achieved": k_rows * 256 * 2 / (syrk_ms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+        "frac": k_rows * 256 * 2 / (syrk_ms * 1e-3) / 1e9 / peaks["hbm"],
+        "traffic": 135727104,   # profiles/r1_prof_syrk_conv1_panel_details.txt
+        "algorithmic_bytes_per_launch": k_rows * 256 * 2, "launch_ms": syrk_ms,
+        "tensor": {"algorithmic_gflop_per_launch": syrk_flops / 1e9, "achieved_tflops": syrk_tflops,
+                   "frac_of_burst_bf16_peak": syrk_tflops / peaks["tensor_burst"]}}
+    if dom is None:   # im2col route / unsupported conv3 width: the largest launch is the HBM-bound conv1 factor SYRK
+        roofline = dict(hbm_kernel, stage_ms=stage_ms)
+    else:
+        roofline = {"bound": "tensor",
+                     "kernel": "conv_tc_kernel (conv.cu): %s input gradient in gather form, %d samples (true + Fisher rows), "
+                               "%d bf16 plane pairs into one fp32 TMEM accumulator - the longest launch of the update" % (dom, s2, npairs),
+                     "achieved": dg[dom]["flops"] / (dg[dom]["ms"] * 1e-3) / 1e12, "peak": peaks["tensor_burst"], "unit": "TFLOP/s",
+                     "frac": dg[dom]["flops"] / (dg[dom]["ms"] * 1e-3) / 1e12 / peaks["tensor_burst"],
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/r1_prof_conv_dgrad{2,3}_raw.txt)
+                     "traffic": CONV_DGRAD_TRAFFIC.get(dom),
+                     "algorithmic_gflop_per_launch": dg[dom]["flops"] / 1e9, "launch_ms": dg[dom]["ms"],
+                     "issued_gflop_per_launch": dg[dom]["issued"] / 1e9,
+                     "issued_tflops": dg[dom]["issued"] / (dg[dom]["ms"] * 1e-3) / 1e12,
+                     "issued_frac": dg[dom]["issued"] / (dg[dom]["ms"] * 1e-3) / 1e12 / peaks["tensor_burst"],
+                     "note": "fp32-class arithmetic from bf16 tensor cores costs %d plane pairs, and a sample's %d output cells fill "
+                             "%d of a tile's 128 rows: the tensor pipe executes %.1fx the algorithmic FLOPs the fraction is charged on"
+                             % (npairs, dg[dom]["rows_used"], dg[dom]["rows_used"], dg[dom]["issued"] / dg[dom]["flops"]),
+                     "conv_dgrad_launches": {kk: {"launch_ms": v["ms"], "algorithmic_gflop": v["flops"] / 1e9,
+                                                  "issued_gflop": v["issued"] / 1e9} for kk, v in dg.items()},
+                     "peak_source": peaks["source"] + ", dense bf16 (cuBLAS) burst",
+                     "hbm_kernel": hbm_kernel,
+                     "stage_ms": stage_ms,
+                     "stage_note": "stage times are taken with the lanes serialised (profiling mode); factor statistics are "
+                                   "issued from inside the forward / backward stages",
+                     "stage_tflops": {k: flops[k] / (stage_ms[k] * 1e-3) / 1e12 for k in ("forward", "backward", "precondition")
+                                      if stage_ms.get(k, 0) > 0}}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -409,35 +458,7 @@ def run_native(args, rank, world, local_rank):
         "clocks": clocks,
         # the kernel's arithmetic intensity is 16.8 GFLOP / 131 MB = 128 FLOP/B, below the machine balance
         # (1665 TFLOP/s / 6.56 TB/s = 254 FLOP/B): it is bound by streaming the patch matrix from HBM once
-        # `roofline` = the dominant (longest) launch of the update; `hbm_kernel` inside it = the largest HBM-bound launch
-        "roofline": {"bound": "tensor",
-                     "kernel": "conv_tc_kernel (conv.cu): conv2 input gradient in gather form, %d samples (true + Fisher rows), "
-                               "%d bf16 plane pairs into one fp32 TMEM accumulator - the longest launch of the update" % (s2, npairs),
-                     "achieved": dgrad_flops / (dgrad_ms * 1e-3) / 1e12, "peak": peaks["tensor_burst"], "unit": "TFLOP/s",
-                     "frac": dgrad_flops / (dgrad_ms * 1e-3) / 1e12 / peaks["tensor_burst"],
-                     "traffic": CONV_DGRAD_TRAFFIC,   # dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/)
-                     "algorithmic_gflop_per_launch": dgrad_flops / 1e9, "launch_ms": dgrad_ms,
-                     "issued_gflop_per_launch": dgrad_issued / 1e9,
-                     "issued_tflops": dgrad_issued / (dgrad_ms * 1e-3) / 1e12,
-                     "issued_frac": dgrad_issued / (dgrad_ms * 1e-3) / 1e12 / peaks["tensor_burst"],
-                     "note": "fp32-class arithmetic from bf16 tensor cores costs 6 plane pairs, and a sample's 100 output cells "
-                             "fill 100 of a tile's 128 rows: issued work = 9.4x the algorithmic FLOPs the fraction is charged on",
-                     "peak_source": peaks["source"] + ", dense bf16 (cuBLAS) burst",
-                     "hbm_kernel": {
-                         "bound": "hbm",
-                         "kernel": "gemm_tc_kernel<1> (SYRK panel mode): conv1 input factor A1 = P1^T P1, 256x256 output, "
-                                   "K=%d patch rows - the largest HBM-bound launch" % k_rows,
-                         "achieved": k_rows * 256 * 2 / (syrk_ms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
-                         "frac": k_rows * 256 * 2 / (syrk_ms * 1e-3) / 1e9 / peaks["hbm"],
-                         "traffic": 135727104,   # profiles/r1_prof_syrk_conv1_panel_details.txt
-                         "algorithmic_bytes_per_launch": k_rows * 256 * 2, "launch_ms": syrk_ms,
-                         "tensor": {"algorithmic_gflop_per_launch": syrk_flops / 1e9, "achieved_tflops": syrk_tflops,
-                                    "frac_of_burst_bf16_peak": syrk_tflops / peaks["tensor_burst"]}},
-                     "stage_ms": stage_ms,
-                     "stage_note": "stage times are taken with the lanes serialised (profiling mode); factor statistics are "
-                                   "issued from inside the forward / backward stages",
-                     "stage_tflops": {k: flops[k] / (stage_ms[k] * 1e-3) / 1e12 for k in ("forward", "backward", "precondition")
-                                      if stage_ms.get(k, 0) > 0}},
+        "roofline": roofline,
         "preprocess": pre,
         "rollout": {"ms_per_%d_steps" % t_count: rollout_ms, "env_steps_per_sec": envs * t_count / (rollout_ms * 1e-3),
                     "note": "per GPU: T x (K-PRE on E raw frame pairs -> stacks, Nature-CNN forward on E rows, categorical sample); "

@@ -26,6 +26,18 @@ bias = torch.randn(n, device="cuda") if outp else None
 for _ in range(iters):
     ops.gemm(a_pl, b_pl, m, n, k, trans=trans, symmetric=sym, out_planes=outp, want_f32=outp == 0, pairs=pairs, bias=bias, relu=bool(outp))
 torch.cuda.synchronize()
+import ctypes
+from actorcritic_b200 import _lib
+lib = _lib.load()
+lib.acx_gemm_enable_timing(1)
+durs = []
+for _ in range(max(iters, 5)):
+    ops.gemm(a_pl, b_pl, m, n, k, trans=trans, symmetric=sym, out_planes=outp, want_f32=outp == 0, pairs=pairs, bias=bias, relu=bool(outp))
+    ms = ctypes.c_float(0)
+    _lib.check(lib.acx_gemm_last_ms(ctypes.byref(ms)))
+    durs.append(ms.value)
+lib.acx_gemm_enable_timing(0)
+print(name, "kernel-only us (library events):", " ".join("%.1f" % (1e3 * d) for d in durs))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(iters):
