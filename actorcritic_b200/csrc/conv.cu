@@ -62,6 +62,10 @@ struct ConvTcParams {
   int debug;   // ACX_CONV_DEBUG bits (performance triage only): 1 skip activation loads, 2 skip weight loads, 4 skip MMAs, 8 skip stores
 };
 
+// triage (ACX_CONV_DEBUG bit 32): cycles CTA 0's MMA warp spends waiting for operands / for a drained accumulator / issuing,
+// and cycles its first epilogue warp spends waiting for an accumulator / working
+__device__ long long g_conv_trace[8];
+
 __global__ void __launch_bounds__(CV_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ CUtensorMap ta1,
                const __grid_constant__ CUtensorMap ta2, const __grid_constant__ CUtensorMap tb0,
@@ -140,34 +144,54 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
     const uint32_t a_layout = p.nsub == 1 ? 2u : 4u;      // SWIZZLE_128B / SWIZZLE_64B
     const uint32_t a_sbo = p.nsub == 1 ? 1024u : 512u;    // 8 rows of 128 / 64 bytes
     const int ksteps = (CV_BK / p.nsub) >> 4;             // MMAs (K = 16) per sub-tile
+    uint32_t a_off[6], b_off[6], a_step[4];               // descriptor offsets in 16-byte units
+#pragma unroll
+    for (int pr = 0; pr < 6; ++pr) {
+      a_off[pr] = (uint32_t)(p.pair_a[pr] * CV_A_TILE) >> 4;
+      b_off[pr] = (uint32_t)(p.pair_b[pr] * b_tile_bytes) >> 4;
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) a_step[t] = (uint32_t)((t / ksteps) * sub_tile_bytes + (t % ksteps) * 32) >> 4;
+    const int npairs = p.num_pairs;
     int it = 0, lt = 0;
+    const bool trace = (p.debug & 32) && blockIdx.x == 0;
+    long long w_full = 0, w_acc = 0, t_begin = trace ? clock64() : 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
       const int buf = lt & 1;
       const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
+      long long tw = trace ? clock64() : 0;
       mbar_wait(&acc_empty[buf], aph ^ 1u, 4);
+      if (trace) w_acc += clock64() - tw;
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
       for (int kb = 0; kb < p.kb_total; ++kb, ++it) {
         const int s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        tw = trace ? clock64() : 0;
         mbar_wait(&full_bar[s], ph, 2);
+        if (trace) w_full += clock64() - tw;
         tc_fence_after();
         if (elect_one()) {
           const int nload = min(p.nsub, p.num_sub - kb * p.nsub);
           const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
           const uint32_t b_addr = a_addr + (uint32_t)(p.npa * CV_A_TILE);
           uint32_t acc_flag = kb > 0 ? 1u : 0u;
-          for (int pr = 0; pr < p.num_pairs && !(p.debug & 4); ++pr) {
-            const uint64_t b_desc0 = make_smem_desc_sw(b_addr + (uint32_t)(p.pair_b[pr] * b_tile_bytes), 16u, 1024u, 2u);
-            for (int j = 0; j < nload; ++j) {
-              uint64_t ad = make_smem_desc_sw(a_addr + (uint32_t)(p.pair_a[pr] * CV_A_TILE + j * sub_tile_bytes), 16u, a_sbo, a_layout);
-              // the weight tile is 64 K-columns wide (128-byte rows): sub-tile j starts j * (128 / nsub) bytes into the row
-              uint64_t bd = b_desc0 + (uint64_t)((uint32_t)(j * (128 / p.nsub)) >> 4);
-              for (int kk = 0; kk < ksteps; ++kk) {
-                umma_bf16(d_tmem, ad, bd, idesc, acc_flag);
-                acc_flag = 1u;
-                ad += 2;   // 16 bf16 = 32 bytes along K inside the swizzle row
-                bd += 2;
+          // straight-line issue: a k-block is 4 MMA steps of K = 16 per plane pair (step t: A at a_step[t] inside the plane's
+          // tile - the second 32-wide sub-tile starts sub_tile_bytes in -, B 32 bytes further along its 128-byte row); pair
+          // offsets are hoisted out of the tile loop.  With run-time loop bounds and per-pair parameter loads the issue loop
+          // itself cost 110-150 cycles per MMA (trace, ACX_CONV_DEBUG=32) against 48-64 in the tensor pipe.
+          const uint64_t a_desc0 = make_smem_desc_sw(a_addr, 16u, a_sbo, a_layout);
+          const uint64_t b_desc0 = make_smem_desc_sw(b_addr, 16u, 1024u, 2u);
+          const int nsteps = nload * ksteps;
+          if (!(p.debug & 4)) {
+#pragma unroll
+            for (int pr = 0; pr < 6; ++pr) {
+              if (pr < npairs) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                  if (t < nsteps)
+                    umma_bf16(d_tmem, a_desc0 + (uint64_t)(a_off[pr] + a_step[t]), b_desc0 + (uint64_t)(b_off[pr] + 2u * (uint32_t)t), idesc,
+                              (pr | t) ? 1u : acc_flag);
               }
             }
           }
@@ -177,6 +201,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
       }
       if (elect_one()) umma_commit(&acc_full[buf]);
       __syncwarp();
+    }
+    if (trace && lane == 0) {
+      g_conv_trace[0] = clock64() - t_begin;
+      g_conv_trace[1] = w_full;
+      g_conv_trace[2] = w_acc;
+      g_conv_trace[3] = lt;
     }
   } else {
     // ===== epilogue (8 warps): TMEM -> registers -> per-warp shared-memory transpose -> bf16 planes =====
@@ -235,7 +265,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
         const int buf = lt & 1;
         const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
+        const bool etrace = (p.debug & 32) && blockIdx.x == 0 && warp == 2;
+        const long long te = etrace ? clock64() : 0;
         mbar_wait(&acc_full[buf], aph, 3);
+        if (etrace && lane == 0) g_conv_trace[5] = (lt == 0 ? 0 : g_conv_trace[5]) + (clock64() - te);
+        if (etrace && lane == 0 && lt == 0) g_conv_trace[6] = te;
+        if (etrace && lane == 0) g_conv_trace[7] = clock64() - g_conv_trace[6];
         tc_fence_after();
         const size_t base = (size_t)tile * tile_stride;
         const size_t mbase = p.dgrad ? (size_t)(tile % p.mask_samples) * tile_stride : 0;
@@ -628,6 +663,10 @@ int conv_dgrad_weight_planes(const float* w, const ConvGeom& g, const Planes& ou
   return 0;
 }
 
+int conv_trace(long long* out8) {
+  return cudaMemcpyFromSymbol(out8, g_conv_trace, 8 * sizeof(long long)) == cudaSuccess ? 0 : 1;
+}
+
 int conv_error_flag() {
   int v = 0;
   cudaMemcpyFromSymbol(&v, g_tc_error, sizeof(int));
@@ -665,6 +704,8 @@ int acx_conv(const acx_conv_t* c, void* stream) {
   return acx::conv_tc_forward(to_planes(c->x), to_planes(c->w), g, c->samples, c->bias, c->relu, to_planes(c->out), c->num_pairs,
                               c->pair_a, c->pair_b, st);
 }
+
+int acx_debug_conv_trace(long long* h_out8) { return acx::conv_trace(h_out8); }
 
 int acx_conv_dgrad_weights(const float* d_w, int hw_in, int c_in, int k, int stride, int hw_out, int c_out, void* const* d_planes,
                            int ld, void* stream) {

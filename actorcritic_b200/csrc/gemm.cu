@@ -257,6 +257,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
     const uint32_t layout = (MAJOR == 0 && bk == 32) ? 4u : 2u;   // SWIZZLE_64B : SWIZZLE_128B
     const uint32_t kstep = MAJOR == 0 ? 32u : p.mn_kstep;
     const uint64_t kstep16 = (uint64_t)(kstep >> 4);
+    // descriptor offsets (16-byte units) of every plane pair's A / B tile inside a stage
+    uint32_t a_off[6], b_off[6];
+#pragma unroll
+    for (int pr = 0; pr < 6; ++pr) {
+      a_off[pr] = (uint32_t)(p.pair_a[pr] * a_tile_bytes) >> 4;
+      b_off[pr] = (uint32_t)(p.pair_b[pr] * b_tile_bytes) >> 4;
+    }
+    const int npairs = p.num_pairs;
     int it = 0, lt = 0;
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++lt) {
       int tm, tn, split;
@@ -297,6 +305,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
                   ad += kstep16;
                   bd += kstep16;
                 }
+              }
+            }
+          } else if (ksteps == 4) {
+            // full 64-deep k-block: straight-line code (pair offsets hoisted out of the tile loop, both loops unrolled).
+            // The issuing thread is alone on its scheduler: with run-time loop bounds and per-pair parameter loads the
+            // issue loop itself cost ~110 cycles per MMA (measured, conv.cu trace) against 48-64 in the tensor pipe.
+#pragma unroll
+            for (int pr = 0; pr < 6; ++pr) {
+              if (pr < npairs) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  umma_bf16(d_tmem, a_desc0 + (uint64_t)(a_off[pr] + (uint32_t)kk * (uint32_t)kstep16),
+                            b_desc0 + (uint64_t)(b_off[pr] + (uint32_t)kk * (uint32_t)kstep16), idesc, (pr | kk) ? 1u : acc_flag);
               }
             }
           } else {

@@ -144,6 +144,11 @@ int acx_conv(const acx_conv_t* c, void* stream);
 int acx_conv_dgrad_weights(const float* d_w, int hw_in, int c_in, int k, int stride, int hw_out, int c_out,
                            void* const* d_planes, int ld, void* stream);
 
+/* triage: with ACX_CONV_DEBUG bit 32 set, CTA 0 of the last acx_conv launch records cycle counts: [0] MMA warp total,
+ * [1] waiting for operands, [2] waiting for a drained accumulator, [3] tiles, [5] epilogue warp waiting for an accumulator,
+ * [7] epilogue warp first wait -> last wake. */
+int acx_debug_conv_trace(long long* h_out8);
+
 /* ---- learner (one process per GPU) ----------------------------------------------------------- */
 typedef struct {
   int num_envs, num_steps, num_actions, conv3_filters;

@@ -43,3 +43,13 @@ for _ in range(reps):
 ev1.record()
 torch.cuda.synchronize()
 print(case, "pairs", npairs, "dbg", os.environ.get("ACX_CONV_DEBUG", "0"), "us per call", 1e3 * ev0.elapsed_time(ev1) / reps)
+
+if int(os.environ.get("ACX_CONV_DEBUG", "0")) & 32:
+    import ctypes
+    from actorcritic_b200 import _lib
+    arr = (ctypes.c_longlong * 8)()
+    _lib.load().acx_debug_conv_trace(arr)
+    t = list(arr)
+    print("  CTA 0 MMA warp: total %d cycles over %d tiles; waiting for operands %d (%.0f%%), for a drained accumulator %d (%.0f%%); "
+          "epilogue warp: waiting %d of %d cycles" % (t[0], t[3], t[1], 100.0 * t[1] / max(t[0], 1), t[2], 100.0 * t[2] / max(t[0], 1),
+                                                     t[5], t[7]))
