@@ -4,7 +4,7 @@
 // precision is chosen per call by how many bf16 plane pairs are accumulated (1 = bf16, 3 ~ 2^-17,
 // 6 = fp32-class) - see DESIGN.md "precision by plane pairs".
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
 // warps 2..5 = epilogue (one TMEM lane quarter each).
 #include <cstdlib>
 #include <mutex>
@@ -110,8 +110,8 @@ __device__ __forceinline__ void store_pair(const OutParams& o, int m, int n, flo
 
 
 constexpr int MAX_STAGES = 8;
-constexpr int EPI_LD = 68;                              // padded row of the per-warp 32 x 64 fp32 staging tile (16-byte multiple)
-constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;          // four epilogue warps
+constexpr int GEMM_THREADS = 320;                       // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
+constexpr int EPI_BYTES = 8 * 32 * 32 * 4;              // one XOR-swizzled 32 x 32 fp32 staging tile per epilogue warp
 
 // ------------------------------------------------------------------------------------------------
 // the tcgen05 kernel: persistent, warp specialised.
@@ -123,7 +123,7 @@ constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;          // four epilogue warps
 // Work items (tile, split) are taken round-robin: w = blockIdx.x, + gridDim.x, ...
 // ------------------------------------------------------------------------------------------------
 template <int MAJOR>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ CUtensorMap ta1,
                const __grid_constant__ CUtensorMap ta2, const __grid_constant__ CUtensorMap tb0,
                const __grid_constant__ CUtensorMap tb1, const __grid_constant__ CUtensorMap tb2, const TcParams p) {
@@ -158,7 +158,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], 4);
+      mbar_init(&acc_empty[b], BN > 32 ? 8 : 4);   // epilogue warps that drain an accumulator
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -341,16 +341,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
     }
   } else {
     // ===== epilogue: TMEM -> registers -> shared-memory transpose -> global =====
-    // A lane owns 4 consecutive columns; CH / 4 lanes cover one row of the chunk, so every global store instruction
-    // writes whole contiguous row segments (fp32: 16 B per lane, bf16 planes: 8 B per lane).  Shared-memory rows are
-    // padded to 68 floats: the 128-bit row writes and the 128-bit transposed reads are both conflict free.
+    // Eight warps: warp w may read the TMEM lane quarter w % 4 (32 tile rows); the two warps of a quarter take alternate
+    // 32-column chunks.  After the transpose a lane owns 4 consecutive columns and 8 lanes cover one row of the chunk, so
+    // every global store instruction writes whole contiguous row segments (fp32: 16 B per lane, bf16 planes: 8 B per
+    // lane).  The staging tile is 32 x 32 fp32 without padding; its 16-byte groups are XOR-swizzled by the row, which
+    // keeps the 128-bit row writes and the 128-bit transposed reads conflict free.
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    float* st = epi + (size_t)q * 32 * EPI_LD;
-    const int CH = BN >= 64 ? 64 : 32;
-    const int lpr = CH >> 2;              // lanes per row
-    const int rpi = 32 / lpr;             // rows per iteration
+    const int grp = (warp - 2) >> 2;
+    float* st = epi + (size_t)(warp - 2) * (32 * 32);
+    constexpr int CH = 32;
+    constexpr int lpr = CH >> 2;          // lanes per row
+    constexpr int rpi = 32 / lpr;         // rows per iteration
     const int rsub = lane / lpr;
     const int cl = (lane - rsub * lpr) * 4;
+    auto staged = [&](int r) -> const float* { return st + r * 32 + (((cl >> 2) ^ (r & 7)) << 2); };
     const OutParams& o = p.out;
     float* const oc = o.c;
     bf16* const cp0 = o.cp[0];
@@ -381,35 +385,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
       const int m0 = (p.panel ? (sub == 2 ? BM : 0) : tm * BM) + q * 32;
       const int n0 = p.panel ? (sub >= 1 ? BN : 0) : tn * BN;
       const int col_base = p.panel ? sub * 128 : buf * BN;
-      for (int c0 = 0; c0 < BN; c0 += CH) {
+      for (int c0 = grp * CH; c0 < BN; c0 += 2 * CH) {
         uint32_t raw[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(col_base + c0);
         tmem_ld32(taddr, raw);
-        float4* strow = reinterpret_cast<float4*>(st + lane * EPI_LD);
+        float4* strow = reinterpret_cast<float4*>(st + lane * 32);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          strow[j] = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]), __uint_as_float(raw[4 * j + 2]),
-                                 __uint_as_float(raw[4 * j + 3]));
-        if (CH == 64) {
-          tmem_ld32(taddr + 32u, raw);
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            strow[8 + j] = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
-                                       __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3]));
-        }
-        if (c0 + CH >= BN && sub == nsub - 1) {   // the accumulator has been drained: hand the TMEM buffer back to the MMA warp
+          strow[j ^ (lane & 7)] = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
+                                              __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3]));
+        if (c0 + 2 * CH >= BN && sub == nsub - 1) {   // this warp's share of the accumulator is drained: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
         __syncwarp();
         const int n = n0 + c0 + cl;
-        const float* src = st + rsub * EPI_LD + cl;
         if (to_ws) {
           float* dst = ws + (size_t)split * ws_split_stride + (size_t)(m0 + rsub) * ws_ld + n;
-#pragma unroll 4
-          for (int r = rsub; r < 32; r += rpi, dst += (size_t)rpi * ws_ld, src += rpi * EPI_LD)
-            *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(src);
+#pragma unroll
+          for (int r = rsub; r < 32; r += rpi, dst += (size_t)rpi * ws_ld)
+            *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(staged(r));
         } else if (n < on) {
           const int rows_valid = min(32, om - m0);
           float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
@@ -424,8 +420,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
             float* dc = oc ? oc + (size_t)(m0 + rsub) * ldc + n : nullptr;
             size_t idx = (size_t)(m0 + rsub) * ldcp + n;   // ldcp % 8 == 0 and n % 4 == 0: 8-byte aligned plane stores
 #pragma unroll 4
-            for (int r = rsub; r < rows_valid; r += rpi, src += rpi * EPI_LD, idx += (size_t)rpi * ldcp) {
-              const float4 a4 = *reinterpret_cast<const float4*>(src);
+            for (int r = rsub; r < rows_valid; r += rpi, idx += (size_t)rpi * ldcp) {
+              const float4 a4 = *reinterpret_cast<const float4*>(staged(r));
               float v0 = fmaf(alpha, a4.x, b0), v1 = fmaf(alpha, a4.y, b1), v2 = fmaf(alpha, a4.z, b2), v3 = fmaf(alpha, a4.w, b3);
               if (relu) {
                 v0 = fmaxf(v0, 0.0f);
@@ -475,9 +471,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
               }
             }
             int t_it = 0;
-            for (int r = rsub; r < rows_valid; r += rpi, src += rpi * EPI_LD, ++t_it) {
+            for (int r = rsub; r < rows_valid; r += rpi, ++t_it) {
               const int m = m0 + r;
-              const float4 a4 = *reinterpret_cast<const float4*>(src);
+              const float4 a4 = *reinterpret_cast<const float4*>(staged(r));
               float v[4] = {fmaf(alpha, a4.x, b0), fmaf(alpha, a4.y, b1), fmaf(alpha, a4.z, b2), fmaf(alpha, a4.w, b3)};
               if (relu) {
 #pragma unroll
@@ -846,7 +842,7 @@ static int launch_tc(const CUtensorMap* ta, const CUtensorMap* tb, const TcParam
     configured = true;
   }
   if (g_probe_on) ACX_CUDA(cudaEventRecord(g_probe_ev[0], st));
-  gemm_tc_kernel<MAJOR><<<grid, 192, smem, st>>>(ta[0], ta[1], ta[2], tb[0], tb[1], tb[2], p);
+  gemm_tc_kernel<MAJOR><<<grid, GEMM_THREADS, smem, st>>>(ta[0], ta[1], ta[2], tb[0], tb[1], tb[2], p);
   ACX_LAUNCH_CHECK();
   if (g_probe_on) ACX_CUDA(cudaEventRecord(g_probe_ev[1], st));
   return 0;
