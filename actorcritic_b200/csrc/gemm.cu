@@ -41,6 +41,7 @@ struct TcParams {
   int npa, npb;          // planes of A / B that the pairs reference (each is loaded once per k-block)
   int bn;                // tile width (32, 64, 128)
   int bk;                // k-block depth (64 or 32)
+  int trace;             // triage: record where CTA 0's MMA warp spends its cycles (ACX_GEMM_TRACE=1)
   int stages;            // shared-memory ring depth
   int tiles_m, tiles_n, num_tiles, splits, total_work;
   int symmetric;
@@ -122,6 +123,8 @@ constexpr int EPI_BYTES = 8 * 32 * 32 * 4;              // one XOR-swizzled 32 x
 // MAJOR 0: A stored [M,K], B stored [N,K] (both K-major).  MAJOR 1: A stored [K,M], B stored [K,N] (both MN-major).
 // Work items (tile, split) are taken round-robin: w = blockIdx.x, + gridDim.x, ...
 // ------------------------------------------------------------------------------------------------
+__device__ long long g_gemm_trace[4];   // triage: total / waiting for operands / waiting for an accumulator / k-blocks
+
 template <int MAJOR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ CUtensorMap ta1,
@@ -265,6 +268,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
       b_off[pr] = (uint32_t)(p.pair_b[pr] * b_tile_bytes) >> 4;
     }
     const int npairs = p.num_pairs;
+    const bool trace = p.trace != 0 && blockIdx.x == 0;   // ACX_GEMM_TRACE=1: where CTA 0's MMA warp spends its cycles
+    long long w_full = 0, w_acc = 0, tw = 0;
+    const long long t_begin = trace ? clock64() : 0;
     int it = 0, lt = 0;
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++lt) {
       int tm, tn, split;
@@ -273,13 +279,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
       const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
       const int buf = p.panel ? 0 : (lt & 1);
       const uint32_t aph = p.panel ? ((uint32_t)lt & 1u) : ((uint32_t)(lt >> 1) & 1u);
+      if (trace) tw = clock64();
       mbar_wait(&acc_empty[buf], aph ^ 1u, 4);
+      if (trace) w_acc += clock64() - tw;
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(p.panel ? 0 : buf * BN);
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        if (trace) tw = clock64();
         mbar_wait(&full_bar[s], ph, 2);
+        if (trace) w_full += clock64() - tw;
         tc_fence_after();
         if (elect_one()) {
           const int kvalid = min(bk, p.k - kb * bk);
@@ -338,6 +348,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
       }
       if (elect_one()) umma_commit(&acc_full[buf]);
       __syncwarp();
+    }
+    if (trace && lane == 0) {
+      g_gemm_trace[0] = clock64() - t_begin;
+      g_gemm_trace[1] = w_full;
+      g_gemm_trace[2] = w_acc;
+      g_gemm_trace[3] = it;
     }
   } else {
     // ===== epilogue: TMEM -> registers -> shared-memory transpose -> global =====
@@ -926,6 +942,14 @@ static int gemm_tc(const acx_gemm_t* g, cudaStream_t st) {
   p.ws = g->workspace;
   p.ws_ld = pl.tiles_n * pl.bn;
   p.ws_split_stride = (long long)pl.tiles_m * BM * p.ws_ld;
+  {
+    static int tr = -1;
+    if (tr < 0) {
+      const char* e = getenv("ACX_GEMM_TRACE");
+      tr = e ? atoi(e) : 0;
+    }
+    p.trace = tr;
+  }
   p.mn_lbo = g_mn_lbo ? g_mn_lbo : (uint32_t)(pl.bk * 128);
   p.mn_sbo = g_mn_sbo ? g_mn_sbo : 1024u;
   p.mn_kstep = g_mn_kstep ? g_mn_kstep : 2048u;
@@ -1026,6 +1050,10 @@ void acx_debug_set_mn_desc(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t kste
 int acx_debug_tc_error(void) {
   const int e = acx::tc_error_flag();
   return e ? e : acx::conv_error_flag();
+}
+
+int acx_debug_gemm_trace(long long* h_out4) {
+  return cudaMemcpyFromSymbol(h_out4, acx::g_gemm_trace, 4 * sizeof(long long)) == cudaSuccess ? 0 : 1;
 }
 
 int acx_gemm_enable_timing(int enable) {

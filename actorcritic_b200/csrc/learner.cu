@@ -116,6 +116,7 @@ struct acx_learner {
   Planes wT[4], wN[4];
   Planes wD[4];              // gather-form dgrad operand of conv2 / conv3 (conv.cu), unused otherwise
   bool conv_tc[4];           // layer computes its input gradient with the gather-form tensor-core kernel (conv.cu)
+  bool conv_fwd_tc[4];       // layer runs its forward on the implicit-GEMM kernel (patch matrix built on the aux lane)
   Planes Vp, Wt;
   float* dot_partials;
   Scratch scr[kMaxLanes];
@@ -124,6 +125,7 @@ struct acx_learner {
   std::vector<cudaEvent_t> lane_events;   // fork / join events (timing disabled), reused every update
   size_t ev_next = 0;
   bool lane_forked[kMaxLanes] = {false, false, false};
+  cudaEvent_t patches_ready[4] = {nullptr, nullptr, nullptr, nullptr};   // P_l complete on the aux lane (this update)
   // host mirror of the schedule
   int64_t gs, ncov;
   bool inverses_valid;
@@ -171,6 +173,11 @@ static Planes first_planes(const Planes& p, int n) {
   Planes q = p;
   q.n = n < p.n ? n : p.n;
   return q;
+}
+
+static bool fwd_tc_enabled() {   // tuning knob: ACX_CONV_FWD=0 keeps im2col + GEMM for the conv2 / conv3 forward
+  const char* e = getenv("ACX_CONV_FWD");
+  return e == nullptr || atoi(e) != 0;
 }
 
 static void setup_layers(acx_learner* l) {
@@ -313,6 +320,7 @@ static size_t layout(acx_learner* l, uint8_t* base) {
     }
   }
   l->conv_tc[0] = l->conv_tc[3] = false;
+
   // ---- activations (forward rows R = N + E; backward rows 2N = true-loss rows then Fisher-sample rows)
   const int np = l->act_planes;
   l->P1 = take_planes(ar, 1, (size_t)R * 400, 256);
@@ -608,19 +616,41 @@ static int input_factor_stage(acx_learner* l, int stage, const Lane& ln) {
   }
 }
 
-// Nature-CNN forward on `rows` observations (envs/atari/model.py:173-217): im2col + GEMM with bias/ReLU epilogues.
-// (The implicit-GEMM forward of conv.cu is NOT used here: a sample's 81 / 49 output locations fill a 128-row MMA tile
-// only to 63-77 %, and with the patch matrices needed anyway by wgrad and the factor SYRKs it measured slower -
-// 72.7 vs 41.4 us for conv2, 47.7 vs 26.0 us for conv3 at 32 x 20.)
-// With `fac` (an ACKTR update past the cold phase) every input factor is issued on lane `fac` the moment its operand
-// is complete, so the factor SYRKs overlap the rest of the forward and the whole backward.
-static int forward(acx_learner* l, const uint8_t* obs, int rows, const Lane& ln, const Lane* fac) {
+// Nature-CNN forward on `rows` observations (envs/atari/model.py:173-217).  conv1 and fc4: im2col / flatten + GEMM with
+// bias/ReLU epilogues.  conv2 / conv3 (`conv_fwd_tc`): implicit-GEMM kernel straight from the activation planes
+// (conv.cu); their patch matrices - still the MN-major operands of wgrad and of the factor SYRKs - are then built on the
+// `aux` lane, off the forward's critical path (`patches_ready[l]` is raised on that lane), and acting (aux == nullptr)
+// skips them altogether.  Otherwise im2col + GEMM on the caller's stream.
+// With `factors` every input factor is issued on the aux lane the moment its operand is complete, so the factor SYRKs
+// overlap the rest of the forward and the whole backward.
+static int forward(acx_learner* l, const uint8_t* obs, int rows, const Lane& ln, const Lane* aux, bool factors) {
   const int c3 = l->c3;
   cudaStream_t st = ln.st;
   auto factor = [&](int stage) -> int {
-    if (!fac) return 0;
-    ACX_TRY(fork_lane(l, st, *fac));
-    return input_factor_stage(l, stage, *fac);
+    if (!aux || !factors) return 0;
+    ACX_TRY(fork_lane(l, st, *aux));
+    return input_factor_stage(l, stage, *aux);
+  };
+  auto conv_layer = [&](int li, const Planes& in, const Planes& patches, const Planes& out) -> int {
+    const Layer& L = l->L[li];
+    GemmOut o;
+    o.relu = 1;
+    o.bias = l->params + L.off + (size_t)L.K * L.C;
+    o.planes = &out;
+    if (!l->conv_fwd_tc[li]) {
+      ACX_TRY(im2col_bf16(in, patches, rows * L.T, L.hw_in, L.cin, L.k, L.s, L.hw_out, st));
+      ACX_TRY(factor(li));
+      return run_gemm(l, patches, l->wT[li], 0, rows * L.T, L.C, L.K, l->lvl_fwd, 1.0f, 0, o, ln);
+    }
+    if (aux) {
+      ACX_TRY(fork_lane(l, st, *aux));
+      ACX_TRY(im2col_bf16(in, patches, rows * L.T, L.hw_in, L.cin, L.k, L.s, L.hw_out, aux->st));
+      if (aux->st != st) ACX_TRY(record_tail(l, aux->st, &l->patches_ready[li]));
+      ACX_TRY(factor(li));
+    }
+    int pa[6], pb[6];
+    const int np = level_pairs(l->lvl_fwd, in.n, l->wT[li].n, pa, pb);
+    return conv_tc_forward(in, l->wT[li], geom_of(L), rows, o.bias, 1, out, np, pa, pb, st);
   };
   GemmOut o;
   o.relu = 1;
@@ -630,16 +660,8 @@ static int forward(acx_learner* l, const uint8_t* obs, int rows, const Lane& ln,
   o.bias = l->params + l->L[0].off + (size_t)l->L[0].K * l->L[0].C;
   o.planes = &l->act1;
   ACX_TRY(run_gemm(l, l->P1, l->wT[0], 0, rows * 400, 32, 256, l->lvl_fwd, 1.0f / 255.0f, 0, o, ln));
-  ACX_TRY(im2col_bf16(l->act1, l->P2, rows * 81, 20, 32, 4, 2, 9, st));
-  ACX_TRY(factor(1));
-  o.bias = l->params + l->L[1].off + (size_t)l->L[1].K * l->L[1].C;
-  o.planes = &l->act2;
-  ACX_TRY(run_gemm(l, l->P2, l->wT[1], 0, rows * 81, 64, 512, l->lvl_fwd, 1.0f, 0, o, ln));
-  ACX_TRY(im2col_bf16(l->act2, l->P3, rows * 49, 9, 64, 3, 1, 7, st));
-  ACX_TRY(factor(2));
-  o.bias = l->params + l->L[2].off + (size_t)l->L[2].K * l->L[2].C;
-  o.planes = &l->act3;
-  ACX_TRY(run_gemm(l, l->P3, l->wT[2], 0, rows * 49, c3, 576, l->lvl_fwd, 1.0f, 0, o, ln));
+  ACX_TRY(conv_layer(1, l->act1, l->P2, l->act2));
+  ACX_TRY(conv_layer(2, l->act2, l->P3, l->act3));
   ACX_TRY(factor(3));
   // fc4 on the (h, w, c)-flattened conv3 output (nn.py:125-126)
   o.bias = l->params + l->L[3].off + (size_t)l->L[3].K * l->L[3].C;
@@ -712,9 +734,10 @@ static int issue_phase1(acx_learner* l, const int32_t* fisher_labels, const floa
   const bool fisher = acktr && l->gs >= l->cfg.num_cold_updates;   // kfac_utils.py:42-44: covariances only after the cold phase
   const int RB = fisher ? 2 * N : N;
   l->ev_next = 0;
+  for (cudaEvent_t& e : l->patches_ready) e = nullptr;
   const Lane main_ln = lane_of(l, 0, st), fac_ln = lane_of(l, 1, st), wg_ln = lane_of(l, 2, st);
   mark(l, 0, st);
-  ACX_TRY(forward(l, l->obs, l->R, main_ln, fisher ? &fac_ln : nullptr));
+  ACX_TRY(forward(l, l->obs, l->R, main_ln, &fac_ln, fisher));
   mark(l, 1, st);
   // targets use the bootstrap tower's values = rows [N, N+E) (envs/atari/model.py:116,126-127)
   ACX_TRY(returns_launch(l->rewards, l->terminals, l->values, l->values + N, l->cfg.gamma, E, T, l->targets, l->adv, st));
@@ -740,13 +763,15 @@ static int issue_phase1(acx_learner* l, const int32_t* fisher_labels, const floa
     o.mask_rows = N;
     ACX_TRY(run_gemm(l, l->dpre4, l->wN[3], 0, RB, 49 * c3, 512, l->lvl_bwd, 1.0f, 0, o, main_ln));
   }
-  // ---- conv3
+  // ---- conv3  (patch matrices of implicit-GEMM forward layers come from the aux lane)
   ACX_TRY(fork_lane(l, st, wg_ln));
+  if (l->patches_ready[2] && wg_ln.st != fac_ln.st) ACX_CUDA(cudaStreamWaitEvent(wg_ln.st, l->patches_ready[2], 0));
   ACX_TRY(weight_grad(l, 2, l->P3, l->dpre3, N * 49, 1.0f, wg_ln));
   if (fisher) ACX_TRY(output_factor(l, 2, offset_rows(l->dpre3, (size_t)N * 49), N * 49, wg_ln));
   ACX_TRY(conv_dgrad(l, 2, l->dpre3, l->act2.p[0], l->dpre2, RB, main_ln));
   // ---- conv2
   ACX_TRY(fork_lane(l, st, wg_ln));
+  if (l->patches_ready[1] && wg_ln.st != fac_ln.st) ACX_CUDA(cudaStreamWaitEvent(wg_ln.st, l->patches_ready[1], 0));
   ACX_TRY(weight_grad(l, 1, l->P2, l->dpre2, N * 81, 1.0f, wg_ln));
   if (fisher) ACX_TRY(output_factor(l, 1, offset_rows(l->dpre2, (size_t)N * 81), N * 81, wg_ln));
   ACX_TRY(conv_dgrad(l, 1, l->dpre2, l->act1.p[0], l->dpre1, RB, main_ln));
@@ -985,6 +1010,12 @@ acx_learner_t* acx_learner_create(const acx_learner_config_t* cfg, void* d_arena
   l->inverses_valid = false;
   l->act_calls = 0;
   l->lanes = cfg->num_lanes <= 0 ? kMaxLanes : std::min(cfg->num_lanes, kMaxLanes);
+  // implicit-GEMM forward of conv2 / conv3 only pays when its patch matrix can be built concurrently on another lane
+  for (int i = 0; i < 4; ++i) {
+    const ConvGeom g = {l->L[i].hw_in, l->L[i].cin, l->L[i].k, l->L[i].s, l->L[i].hw_out, l->L[i].C};
+    l->conv_fwd_tc[i] = (i == 1 || i == 2) && l->cfg.conv_impl == 0 && l->cfg.gemm_impl == 0 && l->lanes > 1 && fwd_tc_enabled() &&
+                        conv_tc_supported(g, 0);
+  }
   for (int i = 0; i + 1 < l->lanes; ++i)
     if (cudaStreamCreateWithFlags(&l->side[i], cudaStreamNonBlocking) != cudaSuccess) {
       acx::set_error("acx_learner_create: cudaStreamCreateWithFlags failed");
@@ -1172,7 +1203,7 @@ int acx_learner_act(acx_learner_t* l, const uint8_t* d_obs, int rows, const floa
   ACX_CHECK(l && d_obs && d_actions, "null argument");
   ACX_CHECK(rows > 0 && rows <= l->R, "rows must be in [1, num_envs * num_steps + num_envs]");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  int r = forward(l, d_obs, rows, lane_of(l, 0, st), nullptr);
+  int r = forward(l, d_obs, rows, lane_of(l, 0, st), nullptr, false);
   if (r) return r;
   r = sample_actions(l->logits, d_uniform, l->cfg.seed, l->act_calls++, rows, l->A, greedy, d_actions, st);
   if (r) return r;

@@ -112,6 +112,9 @@ int acx_split_planes(const float* d_in, int ld_in, int rows, int cols, float sca
 int acx_gemm_enable_timing(int enable);
 int acx_gemm_last_ms(float* h_ms);
 int acx_debug_tc_error(void);
+/* triage: with ACX_GEMM_TRACE=1 in the environment, CTA 0 of the last acx_gemm launch records cycle counts of its MMA warp:
+ * [0] total, [1] waiting for operands, [2] waiting for a drained accumulator, [3] k-blocks processed. */
+int acx_debug_gemm_trace(long long* h_out4);
 /* debug hook: override the UMMA shared-memory descriptor strides (bytes) used for MN-major operands;
  * 0 restores the built-in values. */
 void acx_debug_set_mn_desc(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t kstep_bytes);

@@ -38,6 +38,13 @@ for _ in range(max(iters, 5)):
     durs.append(ms.value)
 lib.acx_gemm_enable_timing(0)
 print(name, "kernel-only us (library events):", " ".join("%.1f" % (1e3 * d) for d in durs))
+if os.environ.get("ACX_GEMM_TRACE"):
+    arr = (ctypes.c_longlong * 4)()
+    lib.acx_debug_gemm_trace(arr)
+    t = list(arr)
+    print("  CTA 0 MMA warp: %d cycles, %d k-blocks (%.0f cycles each); waiting for operands %.0f%%, for an accumulator %.0f%%"
+          % (t[0], t[3], t[0] / max(t[3], 1), 100.0 * t[1] / max(t[0], 1), 100.0 * t[2] / max(t[0], 1)))
+sys.exit(0)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(iters):
