@@ -151,6 +151,20 @@ def orthogonal_init(num_actions=4, c3=32, seed=None):
     return params
 
 
+class PendingScalars:
+    """Result of `Engine.update(fetch="async")`: the update's scalars once their device-to-host copy has landed."""
+
+    def __init__(self, pinned, event):
+        self._pinned, self._event = pinned, event
+
+    def done(self):
+        return self._event.query()
+
+    def result(self):
+        self._event.synchronize()
+        return dict(zip(SCALAR_NAMES, self._pinned.tolist()))
+
+
 class Engine:
     """One learner per process / GPU."""
 
@@ -390,7 +404,25 @@ class Engine:
         self.phase2()
         if not fetch:
             return None
+        if fetch == "async":
+            return self.fetch_scalars_async()
         return self.fetch_scalars()
+
+    def fetch_scalars_async(self):
+        """Start the device-to-host copy of this update's scalars (losses, clip coefficient, learning rate ...) and return
+        a handle; `handle.result()` waits for THAT copy only, so the host can enqueue the next update before it reads the
+        numbers of this one (`update(fetch="async")`).  Four pinned slots are cycled: resolve a handle before four more
+        updates have been fetched."""
+        if getattr(self, "_pending_slots", None) is None:
+            self._pending_slots = [torch.empty(16, dtype=torch.float32).pin_memory() for _ in range(4)]
+            self._pending_events = [torch.cuda.Event() for _ in range(4)]
+            self._pending_next = 0
+        k = self._pending_next % 4
+        self._pending_next += 1
+        with self.on_stream():
+            self._pending_slots[k].copy_(self.scalars, non_blocking=True)
+            self._pending_events[k].record(self.stream)
+        return PendingScalars(self._pending_slots[k], self._pending_events[k])
 
     def fetch_scalars(self):
         with self.on_stream():

@@ -199,6 +199,18 @@ def test_philox_fisher_sampling_statistics():
     assert abs(float(e.factor("stats", "G", "fc_baseline").cpu()) - 1.0) < 0.15
 
 
+def test_async_scalar_fetch_matches_the_synchronous_one():
+    eng = _engine_mod()
+    cfg = eng.EngineConfig(num_envs=4, num_steps=5, conv3_filters=32, num_cold_updates=2, invert_every=1)
+    e, _ = LC.make_pair(cfg, seed=2)
+    batch = synth.rollout(11, 4, 5, 4, obs_kind="sparse")
+    handles = [e.update(batch, fetch="async") for _ in range(3)]     # three updates enqueued before the first read
+    sync = e.fetch_scalars()
+    vals = [h.result() for h in handles]
+    assert vals[-1] == sync
+    assert all(np.isfinite(v["policy_loss"]) for v in vals) and vals[0] != vals[-1]
+
+
 def test_state_dict_roundtrip_resumes_identically():
     eng = _engine_mod()
     cfg = eng.EngineConfig(num_envs=4, num_steps=5, num_cold_updates=2, invert_every=1)
