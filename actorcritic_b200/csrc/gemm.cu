@@ -579,13 +579,12 @@ __global__ void __launch_bounds__(256) gemm_finalize_kernel(OutParams o, const f
   if (threadIdx.y == 0 && n < o.n) store_value(o, m, n, finish_value(o, m, n, acc));
 }
 
-// symmetric results: only upper 128-tiles were computed.  One CTA (32 x 32 threads) per 32 x 32 block pair (bi <= bj):
-// every thread reduces one element of the upper block over the splits (row-contiguous, independent loads), stores it,
-// and the block is transposed through shared memory and stored again as the mirrored block - both stores are row
-// contiguous (the per-element mirror read of the generic kernel is not).
-__global__ void __launch_bounds__(1024) gemm_finalize_sym_kernel(OutParams o, const float* __restrict__ ws, int ws_ld,
-                                                                 long long ws_split_stride, int splits, int nblk) {
-  __shared__ float tile[32][33];
+// symmetric results: only upper 128-tiles were computed.  Four CTAs (32 x 8 threads, one row quarter each) per 32 x 32 block
+// pair (bi <= bj): every thread reduces 1 element of the upper block over the splits (row-contiguous, independent loads),
+// stores it, and the 8 x 32 strip is transposed through shared memory and stored again as part of the mirrored block.
+__global__ void __launch_bounds__(256) gemm_finalize_sym_kernel(OutParams o, const float* __restrict__ ws, int ws_ld,
+                                                                long long ws_split_stride, int splits, int nblk) {
+  __shared__ float tile[8][33];
   int t = blockIdx.x, bi = 0, cnt = nblk;
   while (t >= cnt) {
     t -= cnt;
@@ -594,8 +593,9 @@ __global__ void __launch_bounds__(1024) gemm_finalize_sym_kernel(OutParams o, co
   }
   const int bj = bi + t;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int r0 = blockIdx.y * 8;   // row quarter of the block
   {
-    const int m = bi * 32 + ty, n = bj * 32 + tx;
+    const int m = bi * 32 + r0 + ty, n = bj * 32 + tx;
     float acc = 0.0f;
     if (m < o.m && n < o.n) {
       const float* src = ws + (size_t)m * ws_ld + n;
@@ -615,9 +615,11 @@ __global__ void __launch_bounds__(1024) gemm_finalize_sym_kernel(OutParams o, co
   }
   if (bi == bj) return;
   __syncthreads();
-  {
-    const int m = bj * 32 + ty, n = bi * 32 + tx;
-    if (m < o.m && n < o.n) store_value(o, m, n, finish_value(o, m, n, tile[tx][ty]));
+  // mirrored strip: rows bj*32 + (0..31), columns bi*32 + r0 + (0..7)
+  for (int e = threadIdx.x; e < 256; e += 256) {
+    const int rr = e >> 3, cc = e & 7;
+    const int m = bj * 32 + rr, n = bi * 32 + r0 + cc;
+    if (m < o.m && n < o.n) store_value(o, m, n, finish_value(o, m, n, tile[cc][rr]));
   }
 }
 
@@ -959,7 +961,7 @@ static int gemm_tc(const acx_gemm_t* g, cudaStream_t st) {
   if (r) return r;
   if (pl.to_ws && g->symmetric && g->n > 64) {
     const int nblk = ceil_div(g->n, 32);
-    gemm_finalize_sym_kernel<<<nblk * (nblk + 1) / 2, 1024, 0, st>>>(p.out, g->workspace, p.ws_ld, p.ws_split_stride, pl.splits, nblk);
+    gemm_finalize_sym_kernel<<<dim3(nblk * (nblk + 1) / 2, 4), 256, 0, st>>>(p.out, g->workspace, p.ws_ld, p.ws_split_stride, pl.splits, nblk);
     ACX_LAUNCH_CHECK();
   } else if (pl.to_ws) {
     const int lanes = pl.splits >= 8 ? 8 : (pl.splits >= 4 ? 4 : (pl.splits >= 2 ? 2 : 1));

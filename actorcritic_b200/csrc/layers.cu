@@ -439,24 +439,46 @@ __global__ void __launch_bounds__(256) window_sum_kernel(const float* __restrict
   }
 }
 
-__global__ void __launch_bounds__(256) colsum_stage2_kernel(const float* __restrict__ partial, int chunks, int cols, float scale,
-                                                            float* __restrict__ out, int out_stride, float* __restrict__ out2,
-                                                            int out2_stride, float* __restrict__ corner) {
-  __shared__ float red[8][33];
-  const int c = blockIdx.x * 32 + threadIdx.x;   // block (32, 8)
-  float acc = 0.f;
-  if (c < cols)
-    for (int k = threadIdx.y; k < chunks; k += 8) acc += partial[(size_t)k * cols + c];
-  red[threadIdx.y][threadIdx.x] = acc;
+// block (32 columns, LANES chunk lanes): every lane sums its chunks with four independent accumulators (the loads of a
+// lane are independent - without them one launch-latency-sized L2 round trip per chunk bounds this kernel), then the
+// lanes are combined through shared memory in a fixed order.  LANES = 8 for wide vectors, 32 for the narrow ones (bias
+// gradients: 32..64 columns over up to 592 chunks, where the grid is only 1-2 CTAs).
+template <int LANES>
+__global__ void __launch_bounds__(32 * LANES) colsum_stage2_kernel(const float* __restrict__ partial, int chunks, int cols, float scale,
+                                                                   float* __restrict__ out, int out_stride, float* __restrict__ out2,
+                                                                   int out2_stride, float* __restrict__ corner) {
+  __shared__ float red[LANES][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (c < cols) {
+    const float* src = partial + c;
+    int k = threadIdx.y;
+    for (; k + 3 * LANES < chunks; k += 4 * LANES) {
+      a0 += src[(size_t)k * cols];
+      a1 += src[(size_t)(k + LANES) * cols];
+      a2 += src[(size_t)(k + 2 * LANES) * cols];
+      a3 += src[(size_t)(k + 3 * LANES) * cols];
+    }
+    for (; k < chunks; k += LANES) a0 += src[(size_t)k * cols];
+  }
+  red[threadIdx.y][threadIdx.x] = (a0 + a1) + (a2 + a3);
   __syncthreads();
   if (threadIdx.y == 0 && c < cols) {
     float t = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+    for (int k = 0; k < LANES; ++k) t += red[k][threadIdx.x];
     out[(size_t)c * out_stride] = t * scale;
     if (out2) out2[(size_t)c * out2_stride] = t * scale;   // homogeneous border: the same vector as a row and as a column
     if (corner && c == 0) *corner = 1.0f;
   }
+}
+
+static void launch_colsum_stage2(const float* partial, int chunks, int cols, float scale, float* out, int out_stride, float* out2,
+                                 int out2_stride, float* corner, cudaStream_t st) {
+  if (cols <= 128 && chunks >= 64)
+    colsum_stage2_kernel<32><<<ceil_div(cols, 32), dim3(32, 32), 0, st>>>(partial, chunks, cols, scale, out, out_stride, out2, out2_stride, corner);
+  else
+    colsum_stage2_kernel<8><<<ceil_div(cols, 32), dim3(32, 8), 0, st>>>(partial, chunks, cols, scale, out, out_stride, out2, out2_stride, corner);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -708,7 +730,7 @@ int colsum(const Planes& x, int rows, int cols, float scale, float* partial, int
   }
   colsum_stage1_kernel<<<dim3(chunks, ceil_div(cols, CS_COLBLOCK)), CS_THREADS, smem, st>>>(x, rows, cols, rpc, partial);
   ACX_LAUNCH_CHECK();
-  colsum_stage2_kernel<<<ceil_div(cols, 32), dim3(32, 8), 0, st>>>(partial, chunks, cols, scale, out, out_stride, out2, out2_stride, corner);
+  launch_colsum_stage2(partial, chunks, cols, scale, out, out_stride, out2, out2_stride, corner, st);
   ACX_LAUNCH_CHECK();
   return 0;
 }
@@ -728,7 +750,7 @@ int gram_small(const Planes& x, int rows, int c, float scale, float* partial, in
     gram_stage1_kernel<64><<<chunks, 256, 0, st>>>(x, rows, rpc, partial);
   ACX_LAUNCH_CHECK();
   const int parts = chunks * (c == 32 ? 4 : 1);   // C = 32: four row groups per chunk
-  colsum_stage2_kernel<<<ceil_div(c * c, 32), dim3(32, 8), 0, st>>>(partial, parts, c * c, scale, out, 1, nullptr, 0, nullptr);
+  launch_colsum_stage2(partial, parts, c * c, scale, out, 1, nullptr, 0, nullptr, st);
   ACX_LAUNCH_CHECK();
   return 0;
 }
@@ -745,7 +767,7 @@ int conv_border(const uint8_t* obs_u8, const Planes* act, int n_rows, int hw_in,
     chunks = ceil_div(n_rows, rpc);
     colsum_u8_kernel<<<dim3(chunks, ceil_div(cols, 4096)), 256, 0, st>>>(obs_u8, n_rows, cols, rpc, partial);
     ACX_LAUNCH_CHECK();
-    colsum_stage2_kernel<<<ceil_div(cols, 32), dim3(32, 8), 0, st>>>(partial, chunks, cols, 1.0f, sum_tmp, 1, nullptr, 0, nullptr);
+    launch_colsum_stage2(partial, chunks, cols, 1.0f, sum_tmp, 1, nullptr, 0, nullptr, st);
     ACX_LAUNCH_CHECK();
   } else {
     Planes v = *act;

@@ -142,7 +142,7 @@ struct acx_learner {
 namespace acx {
 
 static const int kColsumChunks = 592;
-static const int kBorderChunks = 64;
+static const int kBorderChunks = 160;   // row chunks of the batch-sum pass over a conv input (4 samples per CTA at 32 x 20)
 static const int kGramChunks = 444;   // 3 CTAs per SM
 static const size_t kDgradChunkBytes = 0;   // 0 = whole batch in one piece.  Measured on B200 at 32x20 (ACX_DGRAD_CHUNK_MB sweep):
                                             // whole 1.510 ms/update, 128 MB 1.533, 64 MB 1.551, 32 MB 1.599, 16 MB 1.681 - the
@@ -572,9 +572,10 @@ static int refresh_weight_planes(acx_learner* l, cudaStream_t st) {
   return 0;
 }
 
-// input factor of layer `li` from the patch/input planes `x` (first `rows` rows, K columns): SYRK + homogeneous border
+// input factor of layer `li` from the patch/input planes `x` (first `rows` rows, K columns): SYRK on lane `ln`, homogeneous
+// border (column sums) on lane `lb`
 static int input_factor(acx_learner* l, int fac, const Planes& x, int rows, int K, float scale_sq, float scale_lin,
-                        const Lane& ln) {
+                        const Lane& ln, const Lane& lb) {
   const int d = K + 1;
   float* dst = l->stats + l->aoff[fac];
   GemmOut o;
@@ -582,7 +583,7 @@ static int input_factor(acx_learner* l, int fac, const Planes& x, int rows, int 
   o.ldc = d;
   ACX_TRY(run_gemm(l, x, x, 1, K, K, rows, l->lvl_factor, scale_sq, 1, o, ln));
   // homogeneous border straight from the column sums: column d-1 (stride d), row d-1 (stride 1), corner 1
-  ACX_TRY(colsum(x, rows, K, scale_lin, ln.sc->colsum_partial, kColsumChunks, dst + (d - 1), d, ln.st, dst + (size_t)(d - 1) * d, 1,
+  ACX_TRY(colsum(x, rows, K, scale_lin, lb.sc->colsum_partial, kColsumChunks, dst + (d - 1), d, lb.st, dst + (size_t)(d - 1) * d, 1,
                  dst + (size_t)d * d - 1));
   return 0;
 }
@@ -590,7 +591,7 @@ static int input_factor(acx_learner* l, int fac, const Planes& x, int rows, int 
 // input factor of a conv layer: SYRK over the patch matrix; the homogeneous border P^T 1 / rows comes from the batch-summed
 // layer input through window sums (one pass over the un-im2col'd input instead of a pass over the k^2/s^2 times larger P)
 static int conv_input_factor(acx_learner* l, int li, const Planes& patches, const uint8_t* obs_u8, const Planes* act_in,
-                             float scale_sq, float border_scale, const Lane& ln) {
+                             float scale_sq, float border_scale, const Lane& ln, const Lane& lb) {
   const Layer& L = l->L[li];
   const int d = L.K + 1, rows = l->N * L.T;
   float* dst = l->stats + l->aoff[li];
@@ -598,21 +599,23 @@ static int conv_input_factor(acx_learner* l, int li, const Planes& patches, cons
   o.c = dst;
   o.ldc = d;
   ACX_TRY(run_gemm(l, patches, patches, 1, L.K, L.K, rows, l->lvl_factor, scale_sq, 1, o, ln));
-  ACX_TRY(conv_border(obs_u8, act_in, l->N, L.hw_in, L.cin, L.k, L.s, L.hw_out, border_scale, ln.sc->colsum_partial, kBorderChunks,
-                      ln.sc->colsum_tmp + 4096, dst, d, ln.st));
+  ACX_TRY(conv_border(obs_u8, act_in, l->N, L.hw_in, L.cin, L.k, L.s, L.hw_out, border_scale, lb.sc->colsum_partial, kBorderChunks,
+                      lb.sc->colsum_tmp + 4096, dst, d, lb.st));
   return 0;
 }
 
-// the five input factors, each as soon as its operand exists: `stage` = 0 P1, 1 P2, 2 P3, 3 act3, 4 act4
-static int input_factor_stage(acx_learner* l, int stage, const Lane& ln) {
+// the five input factors, each as soon as its operand exists: `stage` = 0 P1, 1 P2, 2 P3, 3 act3, 4 act4.
+// The SYRK writes the K x K block of the factor, the border kernels its last row / column / corner: disjoint elements,
+// so the two may run on different lanes.
+static int input_factor_stage(acx_learner* l, int stage, const Lane& ln, const Lane& lb) {
   const int N = l->N, c3 = l->c3;
   const float r1 = 1.0f / (float)(N * 400), r2 = 1.0f / (float)(N * 81), r3 = 1.0f / (float)(N * 49), r4 = 1.0f / (float)N;
   switch (stage) {
-    case 0: return conv_input_factor(l, 0, l->P1, l->obs, nullptr, r1 / (255.0f * 255.0f), r1 / 255.0f, ln);
-    case 1: return conv_input_factor(l, 1, l->P2, nullptr, &l->act1, r2, r2, ln);
-    case 2: return conv_input_factor(l, 2, l->P3, nullptr, &l->act2, r3, r3, ln);
-    case 3: return input_factor(l, 3, with_ld(l->act3, 49 * c3), N, 49 * c3, r4, r4, ln);
-    default: return input_factor(l, 4, l->act4, N, 512, r4, r4, ln);
+    case 0: return conv_input_factor(l, 0, l->P1, l->obs, nullptr, r1 / (255.0f * 255.0f), r1 / 255.0f, ln, lb);
+    case 1: return conv_input_factor(l, 1, l->P2, nullptr, &l->act1, r2, r2, ln, lb);
+    case 2: return conv_input_factor(l, 2, l->P3, nullptr, &l->act2, r3, r3, ln, lb);
+    case 3: return input_factor(l, 3, with_ld(l->act3, 49 * c3), N, 49 * c3, r4, r4, ln, lb);
+    default: return input_factor(l, 4, l->act4, N, 512, r4, r4, ln, lb);
   }
 }
 
@@ -623,13 +626,14 @@ static int input_factor_stage(acx_learner* l, int stage, const Lane& ln) {
 // skips them altogether.  Otherwise im2col + GEMM on the caller's stream.
 // With `factors` every input factor is issued on the aux lane the moment its operand is complete, so the factor SYRKs
 // overlap the rest of the forward and the whole backward.
-static int forward(acx_learner* l, const uint8_t* obs, int rows, const Lane& ln, const Lane* aux, bool factors) {
+static int forward(acx_learner* l, const uint8_t* obs, int rows, const Lane& ln, const Lane* aux, const Lane* aux2, bool factors) {
   const int c3 = l->c3;
   cudaStream_t st = ln.st;
-  auto factor = [&](int stage) -> int {
+  auto factor = [&](int stage) -> int {   // SYRK on aux, its border on aux2 (idle until the backward pass starts)
     if (!aux || !factors) return 0;
     ACX_TRY(fork_lane(l, st, *aux));
-    return input_factor_stage(l, stage, *aux);
+    ACX_TRY(fork_lane(l, st, *aux2));
+    return input_factor_stage(l, stage, *aux, *aux2);
   };
   auto conv_layer = [&](int li, const Planes& in, const Planes& patches, const Planes& out) -> int {
     const Layer& L = l->L[li];
@@ -715,7 +719,15 @@ static int conv_dgrad(acx_learner* l, int li, const Planes& g, const bf16* act_b
 // output factor G_l = g^T g / rows over the Fisher-sample rows
 static int output_factor(acx_learner* l, int li, const Planes& g_fisher, int rows, const Lane& ln) {
   const Layer& L = l->L[li];
-  if ((L.C == 32 || L.C == 64) && l->cfg.gemm_impl == 0)   // too narrow for a tensor-core tile: fp32 SIMT Gram kernel
+  // Narrow output factors (C = 32 / 64 fill a 128 x 64 MMA tile to 1/8 .. 1/2) still run faster as a split-K SYRK on the
+  // tensor cores than on the fp32 SIMT Gram kernel (measured: 1.067 -> 1.043 ms/update; the MMAs are nearly free next to
+  // the one pass over g).  ACX_GRAM_TC=0 selects the SIMT kernel.
+  static int gram_tc = -1;
+  if (gram_tc < 0) {
+    const char* e = getenv("ACX_GRAM_TC");
+    gram_tc = e ? atoi(e) : 1;
+  }
+  if ((L.C == 32 || L.C == 64) && l->cfg.gemm_impl == 0 && !gram_tc)
     return gram_small(g_fisher, rows, L.C, 1.0f / (float)rows, ln.sc->colsum_partial, kGramChunks, l->stats + l->goff[li], ln.st);
   GemmOut o;
   o.c = l->stats + l->goff[li];
@@ -737,7 +749,7 @@ static int issue_phase1(acx_learner* l, const int32_t* fisher_labels, const floa
   for (cudaEvent_t& e : l->patches_ready) e = nullptr;
   const Lane main_ln = lane_of(l, 0, st), fac_ln = lane_of(l, 1, st), wg_ln = lane_of(l, 2, st);
   mark(l, 0, st);
-  ACX_TRY(forward(l, l->obs, l->R, main_ln, &fac_ln, fisher));
+  ACX_TRY(forward(l, l->obs, l->R, main_ln, &fac_ln, &wg_ln, fisher));
   mark(l, 1, st);
   // targets use the bootstrap tower's values = rows [N, N+E) (envs/atari/model.py:116,126-127)
   ACX_TRY(returns_launch(l->rewards, l->terminals, l->values, l->values + N, l->cfg.gamma, E, T, l->targets, l->adv, st));
@@ -1203,7 +1215,7 @@ int acx_learner_act(acx_learner_t* l, const uint8_t* d_obs, int rows, const floa
   ACX_CHECK(l && d_obs && d_actions, "null argument");
   ACX_CHECK(rows > 0 && rows <= l->R, "rows must be in [1, num_envs * num_steps + num_envs]");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  int r = forward(l, d_obs, rows, lane_of(l, 0, st), nullptr, false);
+  int r = forward(l, d_obs, rows, lane_of(l, 0, st), nullptr, nullptr, false);
   if (r) return r;
   r = sample_actions(l->logits, d_uniform, l->cfg.seed, l->act_calls++, rows, l->A, greedy, d_actions, st);
   if (r) return r;
