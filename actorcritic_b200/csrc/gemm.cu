@@ -566,7 +566,19 @@ __global__ void __launch_bounds__(256) gemm_finalize_kernel(OutParams o, const f
       nn = m;
     }
     const float* src = ws + (size_t)mm * ws_ld + nn;
-    for (int s = threadIdx.y; s < splits; s += blockDim.y) acc += src[(size_t)s * ws_split_stride];
+    // four independent partial sums per thread: the loads of a thread do not depend on each other, and without them one
+    // L2 round trip per split bounds this (tiny-grid) kernel
+    const int L = blockDim.y;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int s = threadIdx.y;
+    for (; s + 3 * L < splits; s += 4 * L) {
+      a0 += src[(size_t)s * ws_split_stride];
+      a1 += src[(size_t)(s + L) * ws_split_stride];
+      a2 += src[(size_t)(s + 2 * L) * ws_split_stride];
+      a3 += src[(size_t)(s + 3 * L) * ws_split_stride];
+    }
+    for (; s < splits; s += L) a0 += src[(size_t)s * ws_split_stride];
+    acc = (a0 + a1) + (a2 + a3);
   }
   if (blockDim.y > 1) {
     red[threadIdx.y * blockDim.x + threadIdx.x] = acc;
@@ -599,16 +611,20 @@ __global__ void __launch_bounds__(256) gemm_finalize_sym_kernel(OutParams o, con
     float acc = 0.0f;
     if (m < o.m && n < o.n) {
       const float* src = ws + (size_t)m * ws_ld + n;
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f;
       int s = 0;
-      for (; s + 3 < splits; s += 4) {   // fixed association order: deterministic
+      for (; s + 7 < splits; s += 8) {   // fixed association order: deterministic; 8 loads in flight per thread
         a0 += src[(size_t)s * ws_split_stride];
         a1 += src[(size_t)(s + 1) * ws_split_stride];
         a2 += src[(size_t)(s + 2) * ws_split_stride];
         a3 += src[(size_t)(s + 3) * ws_split_stride];
+        a4 += src[(size_t)(s + 4) * ws_split_stride];
+        a5 += src[(size_t)(s + 5) * ws_split_stride];
+        a6 += src[(size_t)(s + 6) * ws_split_stride];
+        a7 += src[(size_t)(s + 7) * ws_split_stride];
       }
       for (; s < splits; ++s) a0 += src[(size_t)s * ws_split_stride];
-      acc = (a0 + a1) + (a2 + a3);
+      acc = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
       store_value(o, m, n, finish_value(o, m, n, acc));
     }
     tile[ty][tx] = acc;

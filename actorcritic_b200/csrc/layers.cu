@@ -376,7 +376,26 @@ __global__ void __launch_bounds__(CS_THREADS) colsum_stage1_kernel(const Planes 
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   if (active) {
-    for (int r = r0 + row_lane; r < r1; r += lanes_r) {
+    // two rows (up to six 16-byte loads) in flight per thread: the loads are independent, the adds are not
+    int r = r0 + row_lane;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (; r + lanes_r < r1; r += 2 * lanes_r) {
+      const size_t i0 = (size_t)r * x.ld + col0 + (size_t)v * 8;
+      const size_t i1 = i0 + (size_t)lanes_r * x.ld;
+      const uint4 q00 = __ldg(reinterpret_cast<const uint4*>(x.p[0] + i0));
+      const uint4 q10 = __ldg(reinterpret_cast<const uint4*>(x.p[0] + i1));
+      const uint4 q01 = x.n > 1 ? __ldg(reinterpret_cast<const uint4*>(x.p[1] + i0)) : z;
+      const uint4 q11 = x.n > 1 ? __ldg(reinterpret_cast<const uint4*>(x.p[1] + i1)) : z;
+      const uint4 q02 = x.n > 2 ? __ldg(reinterpret_cast<const uint4*>(x.p[2] + i0)) : z;
+      const uint4 q12 = x.n > 2 ? __ldg(reinterpret_cast<const uint4*>(x.p[2] + i1)) : z;
+      add8(acc, q00);
+      add8(acc, q01);
+      add8(acc, q02);
+      add8(acc, q10);
+      add8(acc, q11);
+      add8(acc, q12);
+    }
+    for (; r < r1; r += lanes_r) {
       const size_t idx = (size_t)r * x.ld + col0 + (size_t)v * 8;
       add8(acc, __ldg(reinterpret_cast<const uint4*>(x.p[0] + idx)));
       if (x.n > 1) add8(acc, __ldg(reinterpret_cast<const uint4*>(x.p[1] + idx)));
