@@ -6,7 +6,9 @@
 //            returns/advantages (objectives.py:123-130), A2C loss and output gradients (objectives.py:132-154,78),
 //            backward for the true loss and - stacked as a second batch sharing weights and ReLU masks - for
 //            the Fisher-sample loss, weight gradients, and the 11 batch factor statistics.
-//            Everything a data-parallel job must sum lands in one flat fp32 bucket [grads | A | G | scalars].
+//            Everything a data-parallel job must sum lands in one flat fp32 bucket [A | G | grads | scalars]; the input
+//            factors A come first and are complete (event `a_ready`) long before the backward pass ends, so a caller may
+//            all-reduce that prefix on another stream while the rest of phase 1 still runs.
 //   phase 2  schedule of ColdStartPeriodicInvUpdateKfacOpt.apply_gradients as coded (kfac_utils.py:38-53):
 //            cold momentum-SGD step or factor EMA, scheduled inverse refresh, precondition, KL clip, momentum,
 //            apply; or the A2C RMSProp step (a2c_acktr.py:250-251).
@@ -126,6 +128,8 @@ struct acx_learner {
   size_t ev_next = 0;
   bool lane_forked[kMaxLanes] = {false, false, false};
   cudaEvent_t patches_ready[4] = {nullptr, nullptr, nullptr, nullptr};   // P_l complete on the aux lane (this update)
+  cudaEvent_t a_ready = nullptr;     // all input-factor statistics of the current phase 1 are complete (external event)
+  bool a_ready_valid = false;        // the last phase 1 recorded it
   // host mirror of the schedule
   int64_t gs, ncov;
   bool inverses_valid;
@@ -241,9 +245,9 @@ static size_t layout(acx_learner* l, uint8_t* base) {
   l->precon = f32(P);
   l->bucket_floats = P + F + 4;
   l->bucket = f32(l->bucket_floats);
-  l->grads = l->bucket;
-  l->stats = l->bucket + P;
-  l->bscalars = l->bucket + P + F;
+  l->stats = l->bucket;            // [A | G]: one contiguous block for the EMA, A first (the early all-reduce prefix)
+  l->grads = l->bucket + F;
+  l->bscalars = l->bucket + F + P;
   l->sums = f32(F);
   l->inv = f32(l->inv_floats);
   l->damp = f32(16);
@@ -377,6 +381,7 @@ static void register_buffers(acx_learner* l) {
   reg(l, "grads", l->grads, P * 4);
   reg(l, "reduce_bucket", l->bucket, l->bucket_floats * 4);
   reg(l, "factor_stats", l->stats, l->factor_floats * 4);
+  reg(l, "input_factor_stats", l->stats, l->goff[0] * 4);   // the A part = the prefix of the reduce bucket
   reg(l, "factor_sums", l->sums, l->factor_floats * 4);
   reg(l, "inverses", l->inv, l->inv_floats * 4);
   reg(l, "dampings", l->damp, 12 * 4);
@@ -750,6 +755,15 @@ static int issue_phase1(acx_learner* l, const int32_t* fisher_labels, const floa
   const Lane main_ln = lane_of(l, 0, st), fac_ln = lane_of(l, 1, st), wg_ln = lane_of(l, 2, st);
   mark(l, 0, st);
   ACX_TRY(forward(l, l->obs, l->R, main_ln, &fac_ln, &wg_ln, fisher));
+  if (fisher && fac_ln.index != 0) {
+    // every input factor has been issued: SYRKs on the factor lane, borders on the (so far otherwise idle) wgrad lane.
+    // Raise `a_ready` behind both; inside a stream capture it becomes an external event-record node of the graph.
+    ACX_TRY(order_after(l, wg_ln.st, fac_ln.st));
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    ACX_CUDA(cudaStreamIsCapturing(fac_ln.st, &cs));
+    ACX_CUDA(cudaEventRecordWithFlags(l->a_ready, fac_ln.st,
+                                      cs == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault));
+  }
   mark(l, 1, st);
   // targets use the bootstrap tower's values = rows [N, N+E) (envs/atari/model.py:116,126-127)
   ACX_TRY(returns_launch(l->rewards, l->terminals, l->values, l->values + N, l->cfg.gamma, E, T, l->targets, l->adv, st));
@@ -1022,6 +1036,11 @@ acx_learner_t* acx_learner_create(const acx_learner_config_t* cfg, void* d_arena
   l->inverses_valid = false;
   l->act_calls = 0;
   l->lanes = cfg->num_lanes <= 0 ? kMaxLanes : std::min(cfg->num_lanes, kMaxLanes);
+  if (cudaEventCreateWithFlags(&l->a_ready, cudaEventDisableTiming) != cudaSuccess) {
+    acx::set_error("acx_learner_create: cudaEventCreateWithFlags failed");
+    delete l;
+    return nullptr;
+  }
   // implicit-GEMM forward of conv2 / conv3 only pays when its patch matrix can be built concurrently on another lane
   for (int i = 0; i < 4; ++i) {
     const ConvGeom g = {l->L[i].hw_in, l->L[i].cin, l->L[i].k, l->L[i].s, l->L[i].hw_out, l->L[i].C};
@@ -1083,6 +1102,7 @@ void acx_learner_destroy(acx_learner_t* l) {
     for (int k = 0; k < ACX_NUM_STAGES + 2; ++k) cudaEventDestroy(l->ev[k]);
   if (l) {
     for (cudaEvent_t e : l->lane_events) cudaEventDestroy(e);
+    if (l->a_ready) cudaEventDestroy(l->a_ready);
     for (cudaStream_t s : l->side)
       if (s) cudaStreamDestroy(s);
   }
@@ -1175,7 +1195,16 @@ int acx_learner_phase1(acx_learner_t* l, const int32_t* d_fisher_labels, const f
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool fisher = l->cfg.acktr != 0 && l->gs >= l->cfg.num_cold_updates;
   GraphKey key = {1, fisher ? 1 : 0, d_fisher_labels, d_fisher_eps};
-  return run_cached(l, key, st, [&]() { return issue_phase1(l, d_fisher_labels, d_fisher_eps, st); });
+  const int r = run_cached(l, key, st, [&]() { return issue_phase1(l, d_fisher_labels, d_fisher_eps, st); });
+  l->a_ready_valid = r == 0 && fisher && l->lanes > 1 && !l->profiling;
+  return r;
+}
+
+int acx_learner_wait_input_factors(acx_learner_t* l, void* stream) {
+  ACX_CHECK(l, "null learner");
+  if (!l->a_ready_valid) return -1;   // nothing was raised by the last phase 1: the prefix is complete only when phase 1 is
+  ACX_CUDA(cudaStreamWaitEvent(reinterpret_cast<cudaStream_t>(stream), l->a_ready, 0));
+  return 0;
 }
 
 int acx_learner_phase2(acx_learner_t* l, void* stream) {

@@ -9,6 +9,7 @@ The hyper-parameters default to the literals of the reference's example
 """
 import contextlib
 import ctypes
+import os
 import dataclasses
 
 import numpy as np
@@ -382,11 +383,40 @@ class Engine:
         with self.on_stream():
             _lib.check(self.lib.acx_learner_phase1(self._h, fl, fe, self._stream()))
 
-    def allreduce(self, group=None):
-        """The one collective of the data-parallel path: sum of [grads | A | G | scalars]."""
-        if self.config.world_size > 1:
-            with self.on_stream():
-                torch.distributed.all_reduce(self.bucket, op=torch.distributed.ReduceOp.SUM, group=group)
+    def allreduce(self, group=None, overlap=None):
+        """The collective of the data-parallel path: sum of [A | G | grads | scalars] over the ranks.
+        With `overlap` the input-factor prefix A - three quarters of the bucket, complete long before the backward
+        pass ends - is all-reduced on a second communicator and stream as soon as the library raises its event
+        (acx_learner_wait_input_factors), while phase 1 is still running; only [G | grads | scalars] is reduced after it."""
+        if self.config.world_size <= 1:
+            return
+        dist = torch.distributed
+        early = False
+        if overlap is None:
+            # Opt-in (ACX_DP_OVERLAP=1 or overlap=True).  Measured on one 8 x B200 box it does not pay: 2 ranks 1.097 ms/update
+            # without vs 1.110 with, 8 ranks 1.154 vs 1.158 and a slower end-to-end loop (second collective's host cost) -
+            # the 18 MB all-reduce over NVSwitch is short and its CTAs compete with the backward pass for SMs.
+            overlap = os.environ.get("ACX_DP_OVERLAP", "0") != "0"
+        if overlap and dist.get_backend(group) == "nccl":
+            if getattr(self, "_comm_stream", None) is None:
+                self._comm_stream = torch.cuda.Stream(self.device)
+                self._comm_group = dist.new_group(ranks=dist.get_process_group_ranks(group or dist.group.WORLD), backend="nccl")
+                self._comm_done = torch.cuda.Event()
+                self._bucket_a = self.buffer("input_factor_stats", torch.float32)
+                self._bucket_rest = self.bucket[self._bucket_a.numel():]
+            rc = self.lib.acx_learner_wait_input_factors(self._h, ctypes.c_void_p(self._comm_stream.cuda_stream))
+            if rc > 0:
+                _lib.check(rc)
+            early = rc == 0
+        with self.on_stream():
+            if early:
+                with torch.cuda.stream(self._comm_stream):
+                    dist.all_reduce(self._bucket_a, op=dist.ReduceOp.SUM, group=self._comm_group)
+                    self._comm_done.record(self._comm_stream)
+                dist.all_reduce(self._bucket_rest, op=dist.ReduceOp.SUM, group=group)
+                self.stream.wait_event(self._comm_done)
+            else:
+                dist.all_reduce(self.bucket, op=dist.ReduceOp.SUM, group=group)
 
     def phase2(self):
         with self.on_stream():

@@ -205,8 +205,9 @@ int acx_learner_refresh_weights(acx_learner_t* l, void* stream);
  * inputs:  "observations" u8 [N+E,84,84,4] (train rows batch-major [E,T], then the E bootstrap rows),
  *          "actions" u8 [N], "rewards" f32 [N], "terminals" u8 [N]
  * state:   "params" "velocity" "accum" (cold momentum / RMSProp ms) "factor_sums" "inverses" "sched"
- * per update: "grads" "precon" "factor_stats" "reduce_bucket" (= grads | factor_stats | 4 scalars)
+ * per update: "grads" "precon" "factor_stats" "reduce_bucket" (= factor_stats [A | G] | grads | 4 scalars)
  *          "logits" f32 [N+E,A] "values" f32 [N+E] "targets" "advantages" f32 [N] "dampings" f32 [12]
+ *          "input_factor_stats" (the A prefix of "reduce_bucket")
  *          "scalars" f32 [16]: 0 policy_loss 1 baseline_loss 2 mean_entropy 3 loss 4 KL-clip coeff 5 <V,U>
  *                              6 gradient global norm (cold / A2C step) 7 learning rate used
  * per block views: "params/<layer>" "grads/<layer>" "precon/<layer>" "velocity/<layer>" "accum/<layer>" ([K+1, C]), "stats/A/<factor>"
@@ -223,6 +224,12 @@ void* acx_learner_buffer(acx_learner_t* l, const char* name, size_t* num_bytes);
  * d_fisher_labels (int32 [N]) / d_fisher_eps (f32 [N]) inject the Fisher samples (NULL = Philox). */
 int acx_learner_phase1(acx_learner_t* l, const int32_t* d_fisher_labels, const float* d_fisher_eps, void* stream);
 int acx_learner_phase2(acx_learner_t* l, void* stream);
+/* Data-parallel overlap: the reduce bucket is laid out [input factors A | output factors G | gradients | 4 scalars] and the
+ * A prefix (buffer "input_factor_stats", ~3/4 of the bucket) is complete long before phase 1 ends.  After
+ * acx_learner_phase1 has been called (i.e. enqueued) this makes `stream` wait for that prefix only, so the caller can
+ * all-reduce it on `stream` while the backward pass still runs; returns -1 (and makes nobody wait) when the last phase 1
+ * computed no factor statistics or ran serially - then the prefix is complete when phase 1 is. */
+int acx_learner_wait_input_factors(acx_learner_t* l, void* stream);
 /* optional stage timing with CUDA events on the launching stream (bench.py's live roofline numbers).
  * stages: 0 forward, 1 returns+loss+heads backward, 2 backward (dgrad+wgrad), 3 factor statistics,
  *         4 cold step / factor EMA, 5 inverse refresh, 6 preconditioning, 7 KL clip+momentum+apply+operand refresh.
