@@ -30,7 +30,8 @@ class Gemm(ctypes.Structure):
                 ("c", ctypes.c_void_p), ("ldc", ctypes.c_int),
                 ("c_planes", ctypes.c_void_p * MAX_PLANES), ("c_num_planes", ctypes.c_int), ("ldc_planes", ctypes.c_int),
                 ("mask_plane", ctypes.c_void_p), ("mask_ld", ctypes.c_int), ("mask_rows", ctypes.c_int),
-                ("splits", ctypes.c_int), ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t)]
+                ("splits", ctypes.c_int), ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
+                ("a_patch_u8", ctypes.c_void_p), ("a_patch_samples", ctypes.c_int)]
 
 
 class Conv(ctypes.Structure):

@@ -119,6 +119,7 @@ struct acx_learner {
   Planes wD[4];              // gather-form dgrad operand of conv2 / conv3 (conv.cu), unused otherwise
   bool conv_tc[4];           // layer computes its input gradient with the gather-form tensor-core kernel (conv.cu)
   bool conv_fwd_tc[4];       // layer runs its forward on the implicit-GEMM kernel (patch matrix built on the aux lane)
+  bool conv1_patch;          // conv1's patch matrix P1 is generated inside the GEMMs from the uint8 observations (never stored)
   Planes Vp, Wt;
   float* dot_partials;
   Scratch scr[kMaxLanes];
@@ -480,6 +481,8 @@ struct GemmOut {
   int relu = 0;
   const bf16* mask = nullptr;
   int mask_ld = 0, mask_rows = 0;
+  const uint8_t* a_patch = nullptr;   // A = conv1 patch matrix generated in the kernel from these observations
+  int a_patch_samples = 0;
 };
 
 // plane pairs (i, j) with i + j <= level, low orders first
@@ -531,6 +534,8 @@ static int run_gemm(acx_learner* l, const Planes& a, const Planes& b, int trans,
   g.mask_plane = o.mask;
   g.mask_ld = o.mask_ld;
   g.mask_rows = o.mask_rows;
+  g.a_patch_u8 = o.a_patch;
+  g.a_patch_samples = o.a_patch_samples;
   g.splits = 0;
   g.workspace = ln.sc->ws;
   g.workspace_bytes = ln.sc->ws_bytes;
@@ -603,7 +608,11 @@ static int conv_input_factor(acx_learner* l, int li, const Planes& patches, cons
   GemmOut o;
   o.c = dst;
   o.ldc = d;
-  ACX_TRY(run_gemm(l, patches, patches, 1, L.K, L.K, rows, l->lvl_factor, scale_sq, 1, o, ln));
+  if (li == 0 && l->conv1_patch) {   // P1^T P1 straight from the uint8 observations
+    o.a_patch = obs_u8;
+    o.a_patch_samples = l->N;
+  }
+  ACX_TRY(run_gemm(l, first_planes(patches, o.a_patch ? 1 : patches.n), patches, 1, L.K, L.K, rows, l->lvl_factor, scale_sq, 1, o, ln));
   ACX_TRY(conv_border(obs_u8, act_in, l->N, L.hw_in, L.cin, L.k, L.s, L.hw_out, border_scale, lb.sc->colsum_partial, kBorderChunks,
                       lb.sc->colsum_tmp + 4096, dst, d, lb.st));
   return 0;
@@ -664,11 +673,17 @@ static int forward(acx_learner* l, const uint8_t* obs, int rows, const Lane& ln,
   GemmOut o;
   o.relu = 1;
   // conv1: raw bytes are exact in bf16; the /255 of envs/atari/model.py:93 is the GEMM alpha
-  ACX_TRY(im2col_conv1(obs, l->P1.p[0], rows * 400, st));
+  // (with conv1_patch the GEMMs build the patch tiles themselves from `obs`: no im2col pass, no P1)
+  if (!l->conv1_patch) ACX_TRY(im2col_conv1(obs, l->P1.p[0], rows * 400, st));
   ACX_TRY(factor(0));
   o.bias = l->params + l->L[0].off + (size_t)l->L[0].K * l->L[0].C;
   o.planes = &l->act1;
+  if (l->conv1_patch) {
+    o.a_patch = obs;
+    o.a_patch_samples = rows;
+  }
   ACX_TRY(run_gemm(l, l->P1, l->wT[0], 0, rows * 400, 32, 256, l->lvl_fwd, 1.0f / 255.0f, 0, o, ln));
+  o.a_patch = nullptr;
   ACX_TRY(conv_layer(1, l->act1, l->P2, l->act2));
   ACX_TRY(conv_layer(2, l->act2, l->P3, l->act3));
   ACX_TRY(factor(3));
@@ -692,6 +707,10 @@ static int weight_grad(acx_learner* l, int li, const Planes& x, const Planes& g,
   GemmOut o;
   o.c = l->grads + L.off;
   o.ldc = L.C;
+  if (li == 0 && l->conv1_patch) {
+    o.a_patch = l->obs;
+    o.a_patch_samples = l->N;
+  }
   ACX_TRY(run_gemm(l, x, g, 1, L.K, L.C, rows, l->lvl_bwd, alpha, 0, o, ln));
   if (with_bias) ACX_TRY(bias_grad(l, li, g, rows, ln));
   return 0;
@@ -1040,6 +1059,14 @@ acx_learner_t* acx_learner_create(const acx_learner_config_t* cfg, void* d_arena
     acx::set_error("acx_learner_create: cudaEventCreateWithFlags failed");
     delete l;
     return nullptr;
+  }
+  {
+    // Opt-in (ACX_CONV1_PATCH=1): conv1's patch matrix generated inside the three GEMMs that read it (forward, wgrad, input
+    // factor) by eight producer warps from the uint8 observations - no im2col_conv1 pass, 550 MB less HBM traffic per
+    // update, bit-identical results - but measured slower on B200 (1.036 vs 1.016 ms/update: the ALU-built tiles arrive
+    // later than TMA's: forward 53 -> 67 us, wgrad 49 -> 60, SYRK 44 -> 53, against the 41 us im2col pass saved).
+    const char* e = getenv("ACX_CONV1_PATCH");
+    l->conv1_patch = cfg->gemm_impl == 0 && e != nullptr && atoi(e) != 0;
   }
   // implicit-GEMM forward of conv2 / conv3 only pays when its patch matrix can be built concurrently on another lane
   for (int i = 0; i < 4; ++i) {

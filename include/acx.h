@@ -97,6 +97,12 @@ typedef struct {
    * outputs above are produced by the finalize kernel. */
   int splits;
   float* workspace; size_t workspace_bytes;
+  /* optional: A is NOT read from `a.planes` but generated inside the kernel as the conv1 patch matrix of uint8
+   * observations [a_patch_samples, 84, 84, 4] (8x8 kernel, stride 4 - envs/atari/model.py:173-179):
+   * P1[(r, oy, ox)][(kh, kw, c)] = obs[r, 4 oy + kh, 4 ox + kw, c], exact in one bf16 plane (a.num_planes = 1, pair_a = 0).
+   * trans_a == 0: A = P1 [m = patch rows, k = 256];  trans_a == 1: A = P1 [k = patch rows, m = 256]; with `symmetric`
+   * (n = 256) both sides are P1 and `b` is ignored.  Replaces extract_image_patches + the materialised patch matrix. */
+  const uint8_t* a_patch_u8; int a_patch_samples;
 } acx_gemm_t;
 
 /* impl: 0 = tcgen05 tensor-core kernel (the product path), 1 = SIMT fp32 reference kernel on the

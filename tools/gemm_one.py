@@ -14,17 +14,24 @@ SHAPES = {  # name: (m, n, k, trans, sym, planes, out_planes)
     "fc4": (672, 512, 1568, False, False, 3, 3),
 }
 name = sys.argv[1]
+patch = name.endswith("_patch")
+if patch:
+    name = name[:-6]
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 m, n, k, trans, sym, npl, outp = SHAPES[name]
+obs = None
+if patch:   # the A operand is generated inside the kernel from uint8 observations (conv1 shapes only)
+    rows = k if trans else m
+    obs = torch.randint(0, 256, (rows // 400, 84, 84, 4), dtype=torch.uint8, device="cuda")
 x = torch.randn((k, m) if trans else (m, k), device="cuda")
-a_pl = ops.split_planes(x, npl if name != "fwd_conv1" else 1)
+a_pl = ops.split_planes(x, npl if name not in ("fwd_conv1", "wgrad_conv1") else 1)
 b_pl = a_pl if sym else ops.split_planes(torch.randn((k, n) if trans else (n, k), device="cuda"), npl)
 pairs = None
-if name == "fwd_conv1":
+if name in ("fwd_conv1", "wgrad_conv1"):
     pairs = [(0, 0), (0, 1), (0, 2)]
 bias = torch.randn(n, device="cuda") if outp else None
 for _ in range(iters):
-    ops.gemm(a_pl, b_pl, m, n, k, trans=trans, symmetric=sym, out_planes=outp, want_f32=outp == 0, pairs=pairs, bias=bias, relu=bool(outp))
+    ops.gemm(a_pl, b_pl, m, n, k, trans=trans, symmetric=sym, out_planes=outp, want_f32=outp == 0, pairs=pairs, bias=bias, relu=bool(outp), a_patch_obs=obs)
 torch.cuda.synchronize()
 import ctypes
 from actorcritic_b200 import _lib
@@ -32,7 +39,7 @@ lib = _lib.load()
 lib.acx_gemm_enable_timing(1)
 durs = []
 for _ in range(max(iters, 5)):
-    ops.gemm(a_pl, b_pl, m, n, k, trans=trans, symmetric=sym, out_planes=outp, want_f32=outp == 0, pairs=pairs, bias=bias, relu=bool(outp))
+    ops.gemm(a_pl, b_pl, m, n, k, trans=trans, symmetric=sym, out_planes=outp, want_f32=outp == 0, pairs=pairs, bias=bias, relu=bool(outp), a_patch_obs=obs)
     ms = ctypes.c_float(0)
     _lib.check(lib.acx_gemm_last_ms(ctypes.byref(ms)))
     durs.append(ms.value)
@@ -48,7 +55,7 @@ sys.exit(0)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(iters):
-    ops.gemm(a_pl, b_pl, m, n, k, trans=trans, symmetric=sym, out_planes=outp, want_f32=outp == 0, pairs=pairs, bias=bias, relu=bool(outp))
+    ops.gemm(a_pl, b_pl, m, n, k, trans=trans, symmetric=sym, out_planes=outp, want_f32=outp == 0, pairs=pairs, bias=bias, relu=bool(outp), a_patch_obs=obs)
 e1.record()
 torch.cuda.synchronize()
 print(name, "ms", e0.elapsed_time(e1) / iters)
