@@ -34,7 +34,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures of conv_tc_kernel at 2N = 1280
 # samples, conv3_filters = 32 (profiles/r1_prof_conv_dgrad2_raw.txt, r1_prof_conv_dgrad3_raw.txt)
-CONV_DGRAD_TRAFFIC = {"conv2": 113054720, "conv3": 19046912}
+CONV_DGRAD_TRAFFIC = {"conv2": 115638528, "conv3": 19423488}
 METRIC = "acktr_learner_env_steps_per_sec"
 UNIT = "env-steps/s"
 FRAMESKIP = 4   # a2c_acktr.py:195 - emulator frames per env-step
