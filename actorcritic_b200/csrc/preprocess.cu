@@ -16,8 +16,8 @@
 // rows [30*band, 30*band+30) (y scale is exactly 2.5: output row d uses rows floor(2.5d)..+2, and 12
 // output rows use exactly 30 source rows).  Phase 1: the CTA streams its 30 raw rows of both frames with
 // 16-byte loads (a 480-byte row = 30 uint4), takes the max, converts to gray, and leaves the gray band
-// in shared memory as float.  Phase 2: horizontal pass -> hbuf[30][84].  Phase 3: vertical pass + round +
-// stack push with coalesced 32-bit stores.
+// in shared memory as bytes.  Phase 2: a thread owns an output column and 10 source rows: horizontal taps into
+// registers, vertical taps of its 4 output rows, round + stack push with coalesced 32-bit stores.
 #include "common.cuh"
 
 namespace acx {
@@ -78,46 +78,91 @@ static int ensure_taps() {
   static Taps h;
   build_axis(RAW_W, OUT, h.xsrc, h.xw, h.xn);
   build_axis(RAW_H, OUT, h.ysrc, h.yw, h.yn);
+  // the kernel keeps a thread's 10 horizontal results in registers and indexes them statically: output row d must
+  // use exactly the source rows 10 (d / 4) + {0,1,2 | 2,3,4 | 5,6,7 | 7,8,9}[d % 4]
+  static const int first[4] = {0, 2, 5, 7};
+  for (int d = 0; d < OUT; ++d) {
+    ACX_CHECK(h.yn[d] == 3, "vertical tap count");
+    for (int t = 0; t < 3; ++t) ACX_CHECK(h.ysrc[d][t] == 10 * (d / 4) + first[d % 4] + t, "vertical tap pattern");
+  }
   ACX_CUDA(cudaMemcpyToSymbol(c_taps, &h, sizeof(Taps)));
   g_taps_ready = true;
   return 0;
 }
 
-__device__ __forceinline__ uint32_t max_u8x4(uint32_t a, uint32_t b) { return __vmaxu4(a, b); }
+// byte-wise unsigned max of two words in 5 instructions: the high byte of each 16-bit lane of max.u16x2(a, b) is the
+// max of the odd bytes whatever the even bytes hold; the even bytes are compared with the odd ones masked off
+// (`__vmaxu4` is emulated in ~8)
+__device__ __forceinline__ uint32_t max_u16x2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("max.u16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t max_u8x4(uint32_t a, uint32_t b) {
+  const uint32_t odd = max_u16x2(a, b);
+  const uint32_t even = max_u16x2(a & 0x00ff00ffu, b & 0x00ff00ffu);
+  return (odd & 0xff00ff00u) | even;
+}
 
-// 16 RGB pixels held in 12 little-endian words -> 16 gray bytes (cv2 RGB2GRAY, 15-bit fixed point)
+// 16 RGB pixels held in 12 little-endian words -> 16 gray bytes (cv2 RGB2GRAY, 15-bit fixed point:
+// y = (9798 r + 19235 g + 3735 b + 16384) >> 15).  Per pixel: one PRMT gathers [r,g,b,x] into a word, two IDP.2A
+// (16-bit coefficient x 8-bit sample dot products) accumulate 2*(9798 r + 19235 g + 3735 b) + 32768 < 2^24, whose
+// byte 2 is y (the doubled coefficients 19596 / 38470 / 7470 still fit 16 bits, so the >> 15 becomes a byte select
+// folded into the PRMTs that pack four pixels into a word): 3.5 instructions per pixel instead of 20.
+__device__ __forceinline__ uint32_t dp2a_lo(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t dp2a_hi(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
 __device__ __forceinline__ uint4 gray16(const uint32_t* w) {
-  uint32_t g[4] = {0u, 0u, 0u, 0u};
+  constexpr uint32_t C_RG = 19596u | (38470u << 16);   // 2 * 9798, 2 * 19235: bytes 0, 1 of the pixel word
+  constexpr uint32_t C_B = 7470u;                      // 2 * 3735: byte 2; byte 3 (the next pixel's r) gets 0
+  uint32_t y2[16];
 #pragma unroll
   for (int px = 0; px < 16; ++px) {
-    const int b0 = px * 3;
-    const uint32_t r = (w[b0 >> 2] >> (8 * (b0 & 3))) & 0xffu;
-    const uint32_t gg = (w[(b0 + 1) >> 2] >> (8 * ((b0 + 1) & 3))) & 0xffu;
-    const uint32_t b = (w[(b0 + 2) >> 2] >> (8 * ((b0 + 2) & 3))) & 0xffu;
-    const uint32_t y = (r * 9798u + gg * 19235u + b * 3735u + 16384u) >> 15;
-    g[px >> 2] |= y << (8 * (px & 3));
+    const int b0 = px * 3, wi = b0 >> 2, sh = b0 & 3;
+    const uint32_t p = sh == 0 ? w[wi] : __byte_perm(w[wi], w[wi < 11 ? wi + 1 : wi], 0x3210 + 0x1111 * sh);
+    y2[px] = dp2a_hi(C_B, p, dp2a_lo(C_RG, p, 32768u));
+  }
+  uint32_t g[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t lo = __byte_perm(y2[4 * q], y2[4 * q + 1], 0x0062);
+    const uint32_t hi = __byte_perm(y2[4 * q + 2], y2[4 * q + 3], 0x0062);
+    g[q] = __byte_perm(lo, hi, 0x5410);
   }
   return make_uint4(g[0], g[1], g[2], g[3]);
 }
 
-// One CTA per (environment, band of 12 output rows = 30 source rows).
-//   phase 1: each thread streams 48 contiguous bytes (16 pixels) of both frames with 16-byte loads, takes the byte-wise
-//            max and leaves 16 gray bytes in shared memory (the raw bytes never touch shared memory)
-//   phase 2: horizontal area taps; a thread owns one output column, so its taps live in registers across the 30 rows
-//   phase 3: vertical taps, round-half-even, saturate, frame-stack push with coalesced 32-bit stores
-// Environments whose previous step was terminal run phases 1-3 twice: first on the reset frame (whose observation only
-// seeds the stack: 4 copies), then on the step frames.  Every fp32 multiply and add is a separate rounding (no FMA), in
-// OpenCV's order, which is what makes the result bit-exact.
+// One CTA per (environment, band of 12 output rows = 30 source rows), 320 threads.
+//   phase 1: 300 threads each stream 48 contiguous bytes (16 pixels) of both frames with 16-byte loads, take the
+//            byte-wise max and leave 16 gray bytes in shared memory (the raw bytes never touch shared memory)
+//   phase 2: 252 threads = 84 output columns x 3 row groups.  The vertical scale is exactly 2.5, so 4 output rows use
+//            exactly 10 source rows: thread (dx, rg) runs the horizontal taps of column dx for source rows
+//            [10 rg, 10 rg + 10) into registers, then the vertical taps of output rows [4 rg, 4 rg + 4) from those
+//            registers, rounds half to even, saturates and pushes the frame stack with coalesced 32-bit accesses -
+//            no intermediate row buffer, one barrier per pass.
+// Environments whose previous step was terminal run both phases twice: first on the reset frame (whose observation only
+// seeds the stack: 4 copies, kept in registers), then on the step frames.  Every fp32 multiply and add is a separate
+// rounding (no FMA contraction of an add), in OpenCV's order, which is what makes the result bit-exact.  The one FFMA
+// below is exact-equivalent to I2F + FMUL: a gray byte y is read as the float 2^23 + y (0x4B000000 | y) and
+// fma(2^23 + y, w, -(2^23 w)) rounds the exact product y * w once, like the multiply would; it keeps the
+// byte -> float conversion off the quarter-rate conversion pipe.
+constexpr int KPRE_THREADS = 320;
 template <bool RESET>
-__global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restrict__ raw_a, const uint8_t* __restrict__ raw_b,
-                                                         const uint8_t* __restrict__ terminal,
-                                                         const uint8_t* __restrict__ reset_mask,
-                                                         const uint8_t* __restrict__ reset_raw,
-                                                         const uint8_t* stack_in, uint8_t* stack_out,
-                                                         size_t out_env_stride, int num_envs) {
+__global__ void __launch_bounds__(KPRE_THREADS, 4) preprocess_kernel(const uint8_t* __restrict__ raw_a,
+                                                                  const uint8_t* __restrict__ raw_b,
+                                                                  const uint8_t* __restrict__ terminal,
+                                                                  const uint8_t* __restrict__ reset_mask,
+                                                                  const uint8_t* __restrict__ reset_raw,
+                                                                  const uint8_t* stack_in, uint8_t* stack_out,
+                                                                  size_t out_env_stride, int num_envs) {
   __shared__ __align__(16) uint8_t s_gray[BAND_SRC][RAW_W];   // 4800 B
-  __shared__ float s_h[BAND_SRC][OUT];                         // 10080 B
-  __shared__ uint8_t s_q2[BAND_OUT * OUT];                     // reset-frame pixels of this band
 
   const int env = blockIdx.x / NUM_BANDS;
   const int band = blockIdx.x % NUM_BANDS;
@@ -129,15 +174,19 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restri
   const uint32_t* sin = reinterpret_cast<const uint32_t*>(stack_in + (size_t)env * STACK_BYTES);
   uint32_t* sout = reinterpret_cast<uint32_t*>(stack_out + (size_t)env * out_env_stride);
 
-  // phase-2 ownership: output column dx for rows rg, rg + 3, ...
+  // phase-2 ownership: output column dx, source rows [10 rg, 10 rg + 10) -> output rows [4 rg, 4 rg + 4)
   const int dx = tid % OUT, rg = tid / OUT;   // rg in 0..3 (only 0..2 work: 252 threads)
+  const bool worker = rg < 3;
   int xs[3];
-  float xw[3];
+  float xw[3], xc[3];
+  uint32_t prev[4], q2[4] = {0u, 0u, 0u, 0u};
   const int xn = __ldg(&c_taps.xn[dx]);
+  const int dy0 = band * BAND_OUT + 4 * (worker ? rg : 0);
 #pragma unroll
   for (int t = 0; t < 3; ++t) {
     xs[t] = __ldg(&c_taps.xsrc[dx][t]);
     xw[t] = __ldg(&c_taps.xw[dx][t]);
+    xc[t] = -8388608.0f * xw[t];   // exact (power-of-two scaling)
   }
 
   for (int pass = do_reset ? 0 : 1; pass < 2; ++pass) {
@@ -145,10 +194,10 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restri
     const uint8_t* fa = reset_pass ? reset_raw : raw_a;
     const uint8_t* fb = reset_pass ? reset_raw : raw_b;
     const bool single = RESET || reset_pass;
-    // ---- phase 1: 300 groups of 48 bytes (16 pixels) ----
+    // ---- phase 1: 300 groups of 48 bytes (16 pixels), one per thread ----
     constexpr int GROUPS = BAND_SRC * RAW_ROW_BYTES / 48;   // 300
-    for (int gidx = tid; gidx < GROUPS; gidx += 256) {
-      const uint4* pa = reinterpret_cast<const uint4*>(fa + band_off) + gidx * 3;
+    if (tid < GROUPS) {
+      const uint4* pa = reinterpret_cast<const uint4*>(fa + band_off) + tid * 3;
       uint32_t w[12];
       {
         const uint4 a0 = __ldg(pa), a1 = __ldg(pa + 1), a2 = __ldg(pa + 2);
@@ -157,57 +206,64 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restri
         w[8] = a2.x; w[9] = a2.y; w[10] = a2.z; w[11] = a2.w;
       }
       if (!single) {
-        const uint4* pb = reinterpret_cast<const uint4*>(fb + band_off) + gidx * 3;
+        const uint4* pb = reinterpret_cast<const uint4*>(fb + band_off) + tid * 3;
         const uint4 b0 = __ldg(pb), b1 = __ldg(pb + 1), b2 = __ldg(pb + 2);
         w[0] = max_u8x4(w[0], b0.x); w[1] = max_u8x4(w[1], b0.y); w[2] = max_u8x4(w[2], b0.z); w[3] = max_u8x4(w[3], b0.w);
         w[4] = max_u8x4(w[4], b1.x); w[5] = max_u8x4(w[5], b1.y); w[6] = max_u8x4(w[6], b1.z); w[7] = max_u8x4(w[7], b1.w);
         w[8] = max_u8x4(w[8], b2.x); w[9] = max_u8x4(w[9], b2.y); w[10] = max_u8x4(w[10], b2.z); w[11] = max_u8x4(w[11], b2.w);
       }
-      // group gidx covers pixels [16 * gidx, 16 * gidx + 16) of the band's 30 x 160 pixel raster (rows are 10 groups)
-      *reinterpret_cast<uint4*>(&s_gray[0][0] + gidx * 16) = gray16(w);
+      // group g covers pixels [16 g, 16 g + 16) of the band's 30 x 160 pixel raster (rows are 10 groups)
+      *reinterpret_cast<uint4*>(&s_gray[0][0] + tid * 16) = gray16(w);
     }
     __syncthreads();
-    // ---- phase 2: horizontal taps (gray byte -> float, multiply, add: separate roundings, table order) ----
-    if (rg < 3) {
-      for (int r = rg; r < BAND_SRC; r += 3) {
+    if (worker) {
+      // the old stack words are requested first so that their latency hides behind the horizontal taps
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        prev[j] = (!RESET && !reset_pass && !do_reset && !term) ? sin[(dy0 + j) * OUT + dx] : 0u;
+      // ---- phase 2a: horizontal taps of 10 source rows (table order, separate roundings) ----
+      float h[10];
+#pragma unroll
+      for (int r = 0; r < 10; ++r) {
+        const uint8_t* row = &s_gray[10 * rg + r][0];
         float acc = 0.0f;
 #pragma unroll
-        for (int t = 0; t < 3; ++t)
-          if (t < xn) acc = __fadd_rn(acc, __fmul_rn((float)s_gray[r][xs[t]], xw[t]));
-        s_h[r][dx] = acc;
+        for (int t = 0; t < 3; ++t) {
+          if (t < xn) {
+            const float m = __fmaf_rn(__uint_as_float(0x4B000000u | (uint32_t)row[xs[t]]), xw[t], xc[t]);
+            acc = t == 0 ? m : __fadd_rn(acc, m);
+          }
+        }
+        h[r] = acc;
       }
-    }
-    __syncthreads();
-    // ---- phase 3: vertical taps, round half to even, saturate, push ----
-    for (int i = tid; i < BAND_OUT * OUT; i += 256) {
-      const int dyl = i / OUT, ox = i - dyl * OUT;
-      const int dy = band * BAND_OUT + dyl;
-      float sum = 0.0f;
+      // ---- phase 2b: vertical taps (output row 4 rg + j uses local source rows KPRE_YLOCAL[j]), round half to
+      //      even, saturate, push ----
 #pragma unroll
-      for (int t = 0; t < 3; ++t) {   // every output row has exactly 3 vertical taps (scale 2.5)
-        const int sr = __ldg(&c_taps.ysrc[dy][t]) - band * BAND_SRC;
-        const float tv = __fmul_rn(__ldg(&c_taps.yw[dy][t]), s_h[sr][ox]);
-        sum = t == 0 ? tv : __fadd_rn(sum, tv);
+      for (int j = 0; j < 4; ++j) {
+        const int l0 = j == 0 ? 0 : (j == 1 ? 2 : (j == 2 ? 5 : 7));
+        const float* yw = c_taps.yw[dy0 + j];
+        float sum = __fmul_rn(__ldg(yw), h[l0]);
+        sum = __fadd_rn(sum, __fmul_rn(__ldg(yw + 1), h[l0 + 1]));
+        sum = __fadd_rn(sum, __fmul_rn(__ldg(yw + 2), h[l0 + 2]));
+        int q = __float2int_rn(sum);  // cvRound
+        q = q < 0 ? 0 : (q > 255 ? 255 : q);
+        if (reset_pass) {
+          q2[j] = (uint32_t)q;
+          continue;
+        }
+        uint32_t word;
+        if (RESET) {
+          word = (uint32_t)q * 0x01010101u;  // wrappers.py:234: 4 copies
+        } else {
+          // multi_env.py:127-132: an env that was terminal is reset first (its observation is discarded), then stepped
+          const uint32_t old = do_reset ? q2[j] * 0x01010101u : prev[j];
+          word = term ? 0u : (old >> 8);           // roll -1 along channels (little endian), zero on terminal
+          word |= (uint32_t)q << 24;               // newest frame in channel 3
+        }
+        sout[(dy0 + j) * OUT + dx] = word;
       }
-      int q = __float2int_rn(sum);  // cvRound
-      q = q < 0 ? 0 : (q > 255 ? 255 : q);
-      if (reset_pass) {
-        s_q2[i] = (uint8_t)q;
-        continue;
-      }
-      const int pix = dy * OUT + ox;
-      uint32_t word;
-      if (RESET) {
-        word = (uint32_t)q * 0x01010101u;  // wrappers.py:234: 4 copies
-      } else {
-        // multi_env.py:127-132: an env that was terminal is reset first (its observation is discarded), then stepped
-        const uint32_t prev = do_reset ? (uint32_t)s_q2[i] * 0x01010101u : sin[pix];
-        word = term ? 0u : (prev >> 8);          // roll -1 along channels (little endian), zero on terminal
-        word |= (uint32_t)q << 24;               // newest frame in channel 3
-      }
-      sout[pix] = word;
     }
-    __syncthreads();
+    if (pass == 0) __syncthreads();   // the step pass overwrites s_gray
   }
 }
 
@@ -229,7 +285,7 @@ int acx_preprocess_stack_u8(const uint8_t* d_raw_a, const uint8_t* d_raw_b, cons
             "misaligned buffer");
   int r = ensure_taps();
   if (r) return r;
-  preprocess_kernel<false><<<num_envs * NUM_BANDS, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  preprocess_kernel<false><<<num_envs * NUM_BANDS, KPRE_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       d_raw_a, d_raw_b, d_terminal, d_reset_mask, d_reset_raw, d_stack_in, d_stack_out, out_env_stride, num_envs);
   ACX_LAUNCH_CHECK();
   return 0;
@@ -244,7 +300,7 @@ int acx_preprocess_reset_u8(const uint8_t* d_raw, uint8_t* d_stack_out, size_t o
   ACX_CHECK(((uintptr_t)d_raw % 16) == 0 && ((uintptr_t)d_stack_out % 4) == 0, "misaligned buffer");
   int r = ensure_taps();
   if (r) return r;
-  preprocess_kernel<true><<<num_envs * NUM_BANDS, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  preprocess_kernel<true><<<num_envs * NUM_BANDS, KPRE_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       d_raw, d_raw, nullptr, nullptr, nullptr, d_stack_out, d_stack_out, out_env_stride, num_envs);
   ACX_LAUNCH_CHECK();
   return 0;
