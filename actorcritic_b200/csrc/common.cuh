@@ -71,4 +71,25 @@ __device__ __forceinline__ void split3(float x, bf16& p0, bf16& p1, bf16& p2) {
   p2 = __float2bfloat16_rn(r);
 }
 
+// the same split for two values at a time with packed conversions (F2FP.BF16.F32.PACK_AB converts two floats per
+// instruction on the ALU pipe; the scalar F2F.BF16.F32 goes through the conversion unit): bit-identical planes,
+// element 0 in the low half of each word.
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ void split3x2(float v0, float v1, uint32_t& p0, uint32_t& p1, uint32_t& p2) {
+  p0 = cvt_bf16x2(v0, v1);
+  float r0 = v0 - __uint_as_float(p0 << 16), r1 = v1 - __uint_as_float(p0 & 0xffff0000u);
+  p1 = cvt_bf16x2(r0, r1);
+  r0 -= __uint_as_float(p1 << 16);
+  r1 -= __uint_as_float(p1 & 0xffff0000u);
+  p2 = cvt_bf16x2(r0, r1);
+}
+__device__ __forceinline__ void split3x4(float v0, float v1, float v2, float v3, uint2& p0, uint2& p1, uint2& p2) {
+  split3x2(v0, v1, p0.x, p1.x, p2.x);
+  split3x2(v2, v3, p0.y, p1.y, p2.y);
+}
+
 }  // namespace acx

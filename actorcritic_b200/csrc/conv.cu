@@ -324,15 +324,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
                 if (!(__uint_as_float(mw[t].y << 16) > 0.0f)) v2 = 0.0f;
                 if (!(__uint_as_float(mw[t].y & 0xffff0000u) > 0.0f)) v3 = 0.0f;
               }
-              bf16 h0, h1, h2, h3, m0, m1, m2, m3, l0, l1, l2, l3;
-              split3(v0, h0, m0, l0);
-              split3(v1, h1, m1, l1);
-              split3(v2, h2, m2, l2);
-              split3(v3, h3, m3, l3);
+              uint2 ph, pm, pl;
+              split3x4(v0, v1, v2, v3, ph, pm, pl);
               const size_t idx = base + row_off[t] + coff;
-              *reinterpret_cast<uint2*>(cp0 + idx) = pack4(h0, h1, h2, h3);
-              if (npl > 1) *reinterpret_cast<uint2*>(cp1 + idx) = pack4(m0, m1, m2, m3);
-              if (npl > 2) *reinterpret_cast<uint2*>(cp2 + idx) = pack4(l0, l1, l2, l3);
+              *reinterpret_cast<uint2*>(cp0 + idx) = ph;
+              if (npl > 1) *reinterpret_cast<uint2*>(cp1 + idx) = pm;
+              if (npl > 2) *reinterpret_cast<uint2*>(cp2 + idx) = pl;
             }
           }
           __syncwarp();

@@ -97,18 +97,17 @@ __device__ __forceinline__ void store_pair(const OutParams& o, int m, int n, flo
     }
   }
   if (o.c_num_planes > 0) {
-    bf16 a0, a1, a2, b0, b1, b2;
-    split3(v0, a0, a1, a2);
-    split3(v1, b0, b1, b2);
+    uint32_t q0, q1, q2;
+    split3x2(v0, v1, q0, q1, q2);
     const size_t idx = (size_t)m * o.ldcp + n;   // ldcp % 8 == 0 and n even: 4-byte aligned
     if (two) {
-      *reinterpret_cast<__nv_bfloat162*>(o.cp[0] + idx) = __halves2bfloat162(a0, b0);
-      if (o.c_num_planes > 1) *reinterpret_cast<__nv_bfloat162*>(o.cp[1] + idx) = __halves2bfloat162(a1, b1);
-      if (o.c_num_planes > 2) *reinterpret_cast<__nv_bfloat162*>(o.cp[2] + idx) = __halves2bfloat162(a2, b2);
+      *reinterpret_cast<uint32_t*>(o.cp[0] + idx) = q0;
+      if (o.c_num_planes > 1) *reinterpret_cast<uint32_t*>(o.cp[1] + idx) = q1;
+      if (o.c_num_planes > 2) *reinterpret_cast<uint32_t*>(o.cp[2] + idx) = q2;
     } else {
-      o.cp[0][idx] = a0;
-      if (o.c_num_planes > 1) o.cp[1][idx] = a1;
-      if (o.c_num_planes > 2) o.cp[2][idx] = a2;
+      o.cp[0][idx] = __ushort_as_bfloat16((unsigned short)(q0 & 0xffffu));
+      if (o.c_num_planes > 1) o.cp[1][idx] = __ushort_as_bfloat16((unsigned short)(q1 & 0xffffu));
+      if (o.c_num_planes > 2) o.cp[2][idx] = __ushort_as_bfloat16((unsigned short)(q2 & 0xffffu));
     }
   }
 }
@@ -570,14 +569,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
                 dc += (size_t)rpi * ldc;
               }
               if (npl > 0) {
-                bf16 h0, h1, h2, h3, m0_, m1_, m2_, m3_, l0, l1, l2, l3;
-                split3(v0, h0, m0_, l0);
-                split3(v1, h1, m1_, l1);
-                split3(v2, h2, m2_, l2);
-                split3(v3, h3, m3_, l3);
-                *reinterpret_cast<uint2*>(cp0 + idx) = pack4(h0, h1, h2, h3);
-                if (npl > 1) *reinterpret_cast<uint2*>(cp1 + idx) = pack4(m0_, m1_, m2_, m3_);
-                if (npl > 2) *reinterpret_cast<uint2*>(cp2 + idx) = pack4(l0, l1, l2, l3);
+                uint2 ph, pm, pl;
+                split3x4(v0, v1, v2, v3, ph, pm, pl);
+                *reinterpret_cast<uint2*>(cp0 + idx) = ph;
+                if (npl > 1) *reinterpret_cast<uint2*>(cp1 + idx) = pm;
+                if (npl > 2) *reinterpret_cast<uint2*>(cp2 + idx) = pl;
               }
             }
           } else {
@@ -638,13 +634,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
                   }
                 }
                 if (npl > 0) {
-                  bf16 h[4], md[4], lo[4];
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) split3(v[j], h[j], md[j], lo[j]);
+                  uint2 ph, pm, pl;
+                  split3x4(v[0], v[1], v[2], v[3], ph, pm, pl);
                   const size_t idx = (size_t)m * ldcp + n;
-                  *reinterpret_cast<uint2*>(cp0 + idx) = pack4(h[0], h[1], h[2], h[3]);
-                  if (npl > 1) *reinterpret_cast<uint2*>(cp1 + idx) = pack4(md[0], md[1], md[2], md[3]);
-                  if (npl > 2) *reinterpret_cast<uint2*>(cp2 + idx) = pack4(lo[0], lo[1], lo[2], lo[3]);
+                  *reinterpret_cast<uint2*>(cp0 + idx) = ph;
+                  if (npl > 1) *reinterpret_cast<uint2*>(cp1 + idx) = pm;
+                  if (npl > 2) *reinterpret_cast<uint2*>(cp2 + idx) = pl;
                 }
               } else {
                 for (int j = 0; j < 4; ++j)

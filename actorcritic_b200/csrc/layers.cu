@@ -22,14 +22,21 @@ __global__ void im2col_conv1_kernel(const uint8_t* __restrict__ obs, bf16* __res
   const uint4 a = __ldg(reinterpret_cast<const uint4*>(src));
   const uint4 b = __ldg(reinterpret_cast<const uint4*>(src) + 1);
   const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-  __align__(16) bf16 t[32];
+  // byte -> bf16 without the conversion unit: PRMT builds the float 2^23 + y (0x4B000000 | y), one FADD removes the
+  // 2^23, and the upper halves of two such floats (exact: y has 8 significant bits) are the packed bf16 pair
+  uint32_t t[16];
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) t[j * 4 + q] = __float2bfloat16_rn((float)((w[j] >> (8 * q)) & 0xffu));
+  for (int j = 0; j < 8; ++j) {
+    const float f0 = __uint_as_float(__byte_perm(w[j], 0x4B000000u, 0x7540)) - 8388608.0f;
+    const float f1 = __uint_as_float(__byte_perm(w[j], 0x4B000000u, 0x7541)) - 8388608.0f;
+    const float f2 = __uint_as_float(__byte_perm(w[j], 0x4B000000u, 0x7542)) - 8388608.0f;
+    const float f3 = __uint_as_float(__byte_perm(w[j], 0x4B000000u, 0x7543)) - 8388608.0f;
+    t[2 * j] = __byte_perm(__float_as_uint(f0), __float_as_uint(f1), 0x7632);
+    t[2 * j + 1] = __byte_perm(__float_as_uint(f2), __float_as_uint(f3), 0x7632);
+  }
   uint4* dst = reinterpret_cast<uint4*>(out + (size_t)row * 256 + ky * 32);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) dst[j] = reinterpret_cast<const uint4*>(t)[j];
+  for (int j = 0; j < 4; ++j) dst[j] = make_uint4(t[4 * j], t[4 * j + 1], t[4 * j + 2], t[4 * j + 3]);
 }
 
 // generic NHWC bf16 im2col, patch order (ky, kx, c): each (row, ky) segment is k*C contiguous elements.
