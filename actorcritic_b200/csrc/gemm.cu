@@ -699,6 +699,81 @@ __global__ void __launch_bounds__(256) gemm_finalize_kernel(OutParams o, const f
   if (threadIdx.y == 0 && n < o.n) store_value(o, m, n, finish_value(o, m, n, acc));
 }
 
+// the same reduction for the common aligned case (n, every leading dimension a multiple of 4, no mirroring): a thread
+// owns 4 consecutive columns of one row - 16-byte loads of the partials with four splits in flight, one 16-byte fp32
+// store and one 8-byte store per bf16 plane instead of scalar accesses (the scalar kernel above spent 11-12 us on a
+// 672 x 512 result; this one is bound by the launch and one L2 round trip).  Fixed association order: deterministic.
+__global__ void __launch_bounds__(256) gemm_finalize_vec4_kernel(OutParams o, const float* __restrict__ ws, int ws_ld,
+                                                                 long long ws_split_stride, int splits) {
+  const int nq = o.n >> 2;
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= (long long)o.m * nq) return;
+  const int m = (int)(i / nq), n = (int)(i - (long long)m * nq) << 2;
+  const float4* src = reinterpret_cast<const float4*>(ws + (size_t)m * ws_ld + n);
+  const size_t st4 = (size_t)(ws_split_stride >> 2);
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+  int s = 0;
+  for (; s + 3 < splits; s += 4) {
+    const float4 x0 = src[(size_t)s * st4], x1 = src[(size_t)(s + 1) * st4], x2 = src[(size_t)(s + 2) * st4],
+                 x3 = src[(size_t)(s + 3) * st4];
+    a0.x += x0.x; a0.y += x0.y; a0.z += x0.z; a0.w += x0.w;
+    a1.x += x1.x; a1.y += x1.y; a1.z += x1.z; a1.w += x1.w;
+    a2.x += x2.x; a2.y += x2.y; a2.z += x2.z; a2.w += x2.w;
+    a3.x += x3.x; a3.y += x3.y; a3.z += x3.z; a3.w += x3.w;
+  }
+  for (; s < splits; ++s) {
+    const float4 x0 = src[(size_t)s * st4];
+    a0.x += x0.x; a0.y += x0.y; a0.z += x0.z; a0.w += x0.w;
+  }
+  float v[4] = {(a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y), (a0.z + a1.z) + (a2.z + a3.z),
+                (a0.w + a1.w) + (a2.w + a3.w)};
+  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (o.bias) b4 = __ldg(reinterpret_cast<const float4*>(o.bias + n));
+  v[0] = o.alpha * v[0];
+  v[1] = o.alpha * v[1];
+  v[2] = o.alpha * v[2];
+  v[3] = o.alpha * v[3];
+  if (o.bias) {
+    v[0] += b4.x;
+    v[1] += b4.y;
+    v[2] += b4.z;
+    v[3] += b4.w;
+  }
+  if (o.relu) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.0f);
+  }
+  if (o.mask) {
+    const uint2 mw = __ldg(reinterpret_cast<const uint2*>(o.mask + (size_t)(m % o.mask_rows) * o.mask_ld + n));
+    if (!(__uint_as_float(mw.x << 16) > 0.0f)) v[0] = 0.0f;
+    if (!(__uint_as_float(mw.x & 0xffff0000u) > 0.0f)) v[1] = 0.0f;
+    if (!(__uint_as_float(mw.y << 16) > 0.0f)) v[2] = 0.0f;
+    if (!(__uint_as_float(mw.y & 0xffff0000u) > 0.0f)) v[3] = 0.0f;
+  }
+  if (o.c) *reinterpret_cast<float4*>(o.c + (size_t)m * o.ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
+  if (o.c_num_planes > 0) {
+    uint2 ph, pm, pl;
+    split3x4(v[0], v[1], v[2], v[3], ph, pm, pl);
+    const size_t idx = (size_t)m * o.ldcp + n;
+    *reinterpret_cast<uint2*>(o.cp[0] + idx) = ph;
+    if (o.c_num_planes > 1) *reinterpret_cast<uint2*>(o.cp[1] + idx) = pm;
+    if (o.c_num_planes > 2) *reinterpret_cast<uint2*>(o.cp[2] + idx) = pl;
+  }
+}
+static bool finalize_vec4_ok(const OutParams& o, int ws_ld, long long ws_split_stride) {
+  auto al = [](const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; };
+  if ((o.n & 3) || (ws_ld & 3) || (ws_split_stride & 3)) return false;
+  if (o.c && ((o.ldc & 3) || !al(o.c, 16))) return false;
+  if (o.bias && !al(o.bias, 16)) return false;
+  if (o.mask && ((o.mask_ld & 3) || !al(o.mask, 8))) return false;
+  if (o.c_num_planes > 0) {
+    if (o.ldcp & 3) return false;
+    for (int i = 0; i < o.c_num_planes; ++i)
+      if (!al(o.cp[i], 8)) return false;
+  }
+  return true;
+}
+
 // symmetric results: only upper 128-tiles were computed.  Four CTAs (32 x 8 threads, one row quarter each) per 32 x 32 block
 // pair (bi <= bj): every thread reduces 1 element of the upper block over the splits (row-contiguous, independent loads),
 // stores it, and the 8 x 32 strip is transposed through shared memory and stored again as part of the mirrored block.
@@ -1108,6 +1183,11 @@ static int gemm_tc(const acx_gemm_t* g, cudaStream_t st) {
   if (pl.to_ws && g->symmetric && g->n > 64) {
     const int nblk = ceil_div(g->n, 32);
     gemm_finalize_sym_kernel<<<dim3(nblk * (nblk + 1) / 2, 4), 256, 0, st>>>(p.out, g->workspace, p.ws_ld, p.ws_split_stride, pl.splits, nblk);
+    ACX_LAUNCH_CHECK();
+  } else if (pl.to_ws && !g->symmetric && finalize_vec4_ok(p.out, p.ws_ld, p.ws_split_stride)) {
+    const long long quads = (long long)g->m * (g->n >> 2);
+    gemm_finalize_vec4_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, st>>>(p.out, g->workspace, p.ws_ld, p.ws_split_stride,
+                                                                              pl.splits);
     ACX_LAUNCH_CHECK();
   } else if (pl.to_ws) {
     const int lanes = pl.splits >= 8 ? 8 : (pl.splits >= 4 ? 4 : (pl.splits >= 2 ? 2 : 1));

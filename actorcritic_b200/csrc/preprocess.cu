@@ -430,8 +430,9 @@ static int launch_kpre(const uint8_t* raw_a, const uint8_t* raw_b, const uint8_t
   const int items = num_envs * NUM_BANDS;
   const int slots = kpre_sm_count() * KPRE_P_CTAS_PER_SM;
   const int mode = kpre_mode();
-  // the pipeline pays off once every CTA walks several bands
-  const bool persistent = mode == 1 || (mode == -1 && items >= 4 * slots);
+  // the pipeline pays off once every CTA walks many bands (measured: 256 envs 4.4 vs 4.1 TB/s for the band kernel,
+  // 1024 envs 4.7 vs 5.7, 4096 envs 5.3 vs 6.7 for the pipeline)
+  const bool persistent = mode == 1 || (mode == -1 && items >= 8 * slots);
   if (persistent) {
     static bool configured = false;
     if (!configured) {

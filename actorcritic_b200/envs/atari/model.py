@@ -10,6 +10,7 @@ learner engine, which is created on the first train step, when the [environments
 import numpy as np
 import torch
 
+from ... import checkpoint
 from ... import engine as eng
 from ... import spaces
 from ...baselines import StateValueFunction
@@ -35,6 +36,8 @@ class AtariModel(ActorCriticModel):
         self._bootstrap_values = Fetch("bootstrap_values", self, "bootstrap_values")
         self._engine = None
         self._engine_key = None
+        self._pending_checkpoint = None   # checkpoint.Saver.restore before the first train step (a2c_acktr.py:100-102)
+        checkpoint._register_model(self)
         self._layer_tokens = {n: (Fetch("inputs", self, n + "/inputs"), Fetch("outputs", self, n + "/outputs"))
                               for n in eng.LAYERS}
         # the two heads are registered with the SAME inputs tensor (envs/atari/model.py:243,246) -> one shared factor
@@ -96,6 +99,11 @@ class AtariModel(ActorCriticModel):
         if old is not None and old.config.acktr == cfg.acktr and old.num_params == e.num_params:
             sd = old.state_dict()
             e.load_state_dict(sd)        # the learner state does not depend on the batch shape
+        if self._pending_checkpoint is not None and (objective is None or objective._optimizer is not None):
+            pending = self._pending_checkpoint
+            if objective is not None:
+                self._pending_checkpoint = None      # an acting-only engine keeps it for the learner built later
+            checkpoint.arrays_to_state(e, pending)
         self._engine = e
         self._engine_key = (num_envs, num_steps, id(objective) if objective is not None else None)
         if objective is not None and objective._global_step is not None:

@@ -74,8 +74,9 @@ def test_framestack_sequence_matches_reference_golden(golden_dir):
         assert np.array_equal(stacks.cpu().numpy(), g["observations"][t]), "step %d" % t
 
 
-@pytest.mark.parametrize("num_envs", [1, 3, 64, 257])
+@pytest.mark.parametrize("num_envs", [1, 3, 64, 257, 700])
 def test_random_steps_against_oracle(num_envs):
+    """257 environments run the one-band-per-CTA kernel, 700 the persistent TMA-pipelined one (>= 8 bands per CTA)."""
     ops = _ops()
     rng = np.random.default_rng(num_envs)
     kinds = ["uniform", "palette", "blocky", "binary"]
