@@ -65,6 +65,7 @@ class MultiEnvAgent(Agent):
         if engine is None:
             engine = self._model._build_engine(session, e_count, t_count, None)
         cur = self._observations
+        info_steps = []
         for t in range(t_count):
             obs[:, t].copy_(cur)
             a = engine.act(cur)                                                    # int32 [E]
@@ -72,8 +73,11 @@ class MultiEnvAgent(Agent):
             actions[:, t] = a.to(torch.uint8)
             rewards[:, t] = r
             terminals[:, t] = term
+            # environments hosted on the CPU (envs.atari.raw_env.RawFrameMultiEnv) report their info dicts per step
+            info_steps.append(list(getattr(env, "last_infos", None) or [{} for _ in range(e_count)]))
+        cur = cur.clone()              # the environment reuses its stack buffer; the tuple must not alias it
         self._observations = cur
-        return obs, actions, rewards, terminals.bool(), cur, [[{} for _ in range(t_count)] for _ in range(e_count)]
+        return obs, actions, rewards, terminals.bool(), cur, transpose_list(info_steps)
 
 
 class SingleEnvAgent(Agent):

@@ -154,15 +154,17 @@ __device__ __forceinline__ void invert_block_smem(double (*d)[IB + 1]) {
   __syncthreads();
 }
 
-// per-job scratch inside InvDev::rbuf:  R [IB][n] | Rold [IB][n] | (spare [IB][n]) | Dinv [2][IB][IB] (by pivot parity: the
-// update kernel of step p reads D_p^-1 while one of its CTAs already writes D_{p+1}^-1)
+// per-job scratch inside InvDev::rbuf:  R [IB][n] | Rold [IB][n] | next pivot block before inversion ([IB][IB] of an
+// [IB][n] slot; only jobs with n > IB have a next pivot) | Dinv [2][IB][IB] (by pivot parity: the update kernel of step p
+// reads D_p^-1 while inv_pivot_kernel already writes D_{p+1}^-1)
 __device__ __forceinline__ double* scratch_r(const InvDev& jb) { return jb.rbuf; }
 __device__ __forceinline__ double* scratch_rold(const InvDev& jb) { return jb.rbuf + (size_t)IB * jb.n; }
+__device__ __forceinline__ double* scratch_next(const InvDev& jb) { return jb.rbuf + (size_t)2 * IB * jb.n; }   // IB x IB
 __device__ __forceinline__ double* scratch_dinv(const InvDev& jb, int p) {
   return jb.rbuf + (size_t)3 * IB * jb.n + (size_t)(p & 1) * IB * IB;
 }
 
-// D_0^-1 of every job (one CTA of 256 threads per job) - later pivot inverses come out of the update kernel
+// D_0^-1 of every job (one CTA of 256 threads per job) - later pivot inverses come from inv_pivot_kernel
 __global__ void __launch_bounds__(256) inv_diag0_kernel(const InvDev* __restrict__ jobs) {
   const InvDev jb = jobs[blockIdx.z];
   const int n = jb.n;
@@ -215,10 +217,37 @@ __global__ void __launch_bounds__(1024) inv_panels_kernel(const InvDev* __restri
     scratch_rold(jb)[(size_t)ty * n + cj] = t[ty][tx];
     scratch_r(jb)[(size_t)ty * n + cj] = acc;
   }
+  if (blk == p + 1) {
+    // look-ahead: the next pivot block as this step's update will leave it, D' = M_qq - Rold_q^T R_q (q = p + 1 is not
+    // processed yet: sigma = +1; same k order as the update kernel).  inv_pivot_kernel inverts it on a side stream
+    // WHILE the update kernel runs, which takes the serial 32-step Gauss-Jordan off the critical path.
+    __syncthreads();          // everyone is done reading d
+    d[ty][tx] = acc;          // R_q
+    __syncthreads();
+    const int nbq = min(IB, n - b0);
+    double v = (ty < nbq && tx < nbq) ? jb.m[(size_t)(b0 + ty) * n + b0 + tx] : (ty == tx ? 1.0 : 0.0);
+    if (ty < nbq && tx < nbq) {
+#pragma unroll 8
+      for (int k = 0; k < IB; ++k) v -= t[k][ty] * d[k][tx];
+    }
+    scratch_next(jb)[ty * IB + tx] = v;
+  }
 }
 
-// step kernel B (update) over the upper tiles, CTA tile 64 x 64, 256 threads, 4 x 4 per thread; the CTA that owns pivot
-// block p+1 (always inside a diagonal tile) then inverts it - it is final after this update - for the next step.
+// D_{p+1}^-1 from the block the panels kernel of step p left in scratch_next (one CTA of 256 threads per job)
+__global__ void __launch_bounds__(256) inv_pivot_kernel(const InvDev* __restrict__ jobs, int q) {
+  const InvDev jb = jobs[blockIdx.z];
+  if (q * IB >= jb.n) return;
+  __shared__ double d[IB][IB + 1];
+  const double* src = scratch_next(jb);
+  for (int e = threadIdx.x; e < IB * IB; e += 256) d[e >> 5][e & 31] = src[e];
+  invert_block_smem<256>(d);
+  double* out = scratch_dinv(jb, q);
+  for (int e = threadIdx.x; e < IB * IB; e += 256) out[e] = d[e >> 5][e & 31];
+}
+
+// step kernel B (update) over the upper tiles, CTA tile 64 x 64, 256 threads, 4 x 4 per thread.  (The next pivot block
+// is inverted concurrently by inv_pivot_kernel from the look-ahead copy the panels kernel made.)
 __global__ void __launch_bounds__(256) inv_update_kernel(const InvDev* __restrict__ jobs, int p) {
   if (blockIdx.y > blockIdx.x) return;   // lower tiles are never read
   const InvDev jb = jobs[blockIdx.z];
@@ -297,20 +326,6 @@ __global__ void __launch_bounds__(256) inv_update_kernel(const InvDev* __restric
       } else
         *dst = acc[q][r];
     }
-  }
-  // next pivot block (p+1) lies inside exactly one (diagonal) 64 x 64 tile; that CTA inverts it now
-  const int q0 = p0 + IB;
-  if (q0 < n && q0 >= i0 && q0 < i0 + 64 && q0 >= j0 && q0 < j0 + 64) {
-    __syncthreads();   // this CTA's global writes above are visible to its own threads after the barrier
-    double (*d)[IB + 1] = reinterpret_cast<double (*)[IB + 1]>(&cs[0][0]);   // 64*33 doubles >= 32*33
-    const int nbq = min(IB, n - q0);
-    for (int e = threadIdx.x; e < IB * IB; e += 256) {
-      const int yy = e >> 5, xx = e & 31;
-      d[yy][xx] = (yy < nbq && xx < nbq) ? jb.m[(size_t)(q0 + yy) * n + q0 + xx] : (yy == xx ? 1.0 : 0.0);
-    }
-    invert_block_smem<256>(d);
-    double* out = scratch_dinv(jb, p + 1);
-    for (int e = threadIdx.x; e < IB * IB; e += 256) out[e] = d[e >> 5][e & 31];
   }
 }
 
@@ -638,7 +653,15 @@ int compute_dampings(const float* const* d_a_ptrs, const float* const* d_g_ptrs,
 }
 
 int spd_inverse_batched(const InvJob* h_jobs, const InvJob* d_jobs, int num_jobs, const Sched* sched, const float* d_damp,
-                        cudaStream_t st) {
+                        cudaStream_t st, cudaStream_t side) {
+  // `side`: a second stream for the pivot-block inversions (forked after each panels kernel, joined before the next one;
+  // inside a stream capture these become parallel graph branches).  nullptr or == st: everything in order on `st`.
+  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  const bool forked = side != nullptr && side != st;
+  if (forked && ev_fork == nullptr) {
+    ACX_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    ACX_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+  }
   static_assert(sizeof(InvJob) == sizeof(InvDev), "InvJob and InvDev must have the same layout");
   const InvDev* dj = reinterpret_cast<const InvDev*>(d_jobs);
   int nmax = 0;
@@ -663,12 +686,24 @@ int spd_inverse_batched(const InvJob* h_jobs, const InvJob* d_jobs, int num_jobs
       }
     if (active == 0) break;
     const int nblk = ceil_div(nact, IB);
+    const bool has_next = nblk > p + 1;
     if (nblk > 1) {
       inv_panels_kernel<<<dim3(nblk, 1, active), 1024, 0, st>>>(dj, p, nblk);
       ACX_LAUNCH_CHECK();
     }
+    if (has_next) {
+      cudaStream_t ps = forked ? side : st;
+      if (forked) {
+        ACX_CUDA(cudaEventRecord(ev_fork, st));
+        ACX_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+      }
+      inv_pivot_kernel<<<dim3(1, 1, active), 256, 0, ps>>>(dj, p + 1);
+      ACX_LAUNCH_CHECK();
+      if (forked) ACX_CUDA(cudaEventRecord(ev_join, side));
+    }
     inv_update_kernel<<<dim3(ceil_div(nact, 64), ceil_div(nact, 64), active), 256, 0, st>>>(dj, p);
     ACX_LAUNCH_CHECK();
+    if (has_next && forked) ACX_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
   }
   {
     dim3 grid(grid_for((size_t)nmax * (nmax + 8), 256, 148 * 4), 1, num_jobs);

@@ -10,23 +10,25 @@ namespace acx {
 // ------------------------------------------------------------------------------------------------
 // im2col for conv1: obs uint8 [R,84,84,4] -> P1 bf16 [R*400, 256] holding the RAW byte values
 // (exact in bf16; the 1/255 of envs/atari/model.py:93 is folded into the GEMM alpha).
-// One thread per (patch row, ky): 32 contiguous input bytes -> 32 bf16.
+// One thread per 16 output bytes: (patch row, ky, quarter q) reads 8 contiguous input bytes and writes 8 bf16, so a
+// warp writes 512 contiguous bytes per store instruction (whole sectors) and reads 32-byte runs.
 // ------------------------------------------------------------------------------------------------
-__global__ void im2col_conv1_kernel(const uint8_t* __restrict__ obs, bf16* __restrict__ out, int rows_total) {
+__global__ void __launch_bounds__(256) im2col_conv1_kernel(const uint8_t* __restrict__ obs, bf16* __restrict__ out,
+                                                           int rows_total) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)rows_total * 8) return;
-  const int ky = (int)(i & 7);
-  const int row = (int)(i >> 3);
-  const int n = row / 400, loc = row % 400, oy = loc / 20, ox = loc % 20;
-  const uint8_t* src = obs + ((size_t)(n * 84 + oy * 4 + ky) * 84 + ox * 4) * 4;
-  const uint4 a = __ldg(reinterpret_cast<const uint4*>(src));
-  const uint4 b = __ldg(reinterpret_cast<const uint4*>(src) + 1);
-  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  if (i >= (long long)rows_total * 32) return;
+  const int q = (int)(i & 3);
+  const int ky = (int)(i >> 2) & 7;
+  const int row = (int)(i >> 5);
+  const int n = row / 400, loc = row - n * 400, oy = loc / 20, ox = loc - oy * 20;
+  const uint8_t* src = obs + ((size_t)(n * 84 + oy * 4 + ky) * 84 + ox * 4) * 4 + q * 8;
+  const uint2 a = __ldg(reinterpret_cast<const uint2*>(src));
+  const uint32_t w[2] = {a.x, a.y};
   // byte -> bf16 without the conversion unit: PRMT builds the float 2^23 + y (0x4B000000 | y), one FADD removes the
   // 2^23, and the upper halves of two such floats (exact: y has 8 significant bits) are the packed bf16 pair
-  uint32_t t[16];
+  uint32_t t[4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < 2; ++j) {
     const float f0 = __uint_as_float(__byte_perm(w[j], 0x4B000000u, 0x7540)) - 8388608.0f;
     const float f1 = __uint_as_float(__byte_perm(w[j], 0x4B000000u, 0x7541)) - 8388608.0f;
     const float f2 = __uint_as_float(__byte_perm(w[j], 0x4B000000u, 0x7542)) - 8388608.0f;
@@ -34,9 +36,7 @@ __global__ void im2col_conv1_kernel(const uint8_t* __restrict__ obs, bf16* __res
     t[2 * j] = __byte_perm(__float_as_uint(f0), __float_as_uint(f1), 0x7632);
     t[2 * j + 1] = __byte_perm(__float_as_uint(f2), __float_as_uint(f3), 0x7632);
   }
-  uint4* dst = reinterpret_cast<uint4*>(out + (size_t)row * 256 + ky * 32);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) dst[j] = make_uint4(t[4 * j], t[4 * j + 1], t[4 * j + 2], t[4 * j + 3]);
+  *reinterpret_cast<uint4*>(out + (size_t)row * 256 + ky * 32 + q * 8) = make_uint4(t[0], t[1], t[2], t[3]);
 }
 
 // generic NHWC bf16 im2col, patch order (ky, kx, c): each (row, ky) segment is k*C contiguous elements.
@@ -688,7 +688,7 @@ __global__ void sample_actions_kernel(const float* __restrict__ logits, const fl
 // launchers
 // ------------------------------------------------------------------------------------------------
 int im2col_conv1(const uint8_t* obs, bf16* out, int rows_total, cudaStream_t st) {
-  const long long total = (long long)rows_total * 8;
+  const long long total = (long long)rows_total * 32;
   im2col_conv1_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(obs, out, rows_total);
   ACX_LAUNCH_CHECK();
   return 0;

@@ -926,7 +926,8 @@ static int issue_phase2(acx_learner* l, const Plan2& p, cudaStream_t st) {
   mark(l, 6, st);
   if (p.invert) {
     ACX_TRY(compute_dampings(l->d_a_ptrs, l->d_g_ptrs, l->d_a_dims, l->d_g_dims, l->lambdas, 6, l->damp, st));
-    ACX_TRY(spd_inverse_batched(l->h_jobs, l->d_jobs, 12, l->sched, l->damp, st));
+    // the serial pivot-block inversions run on a side lane next to the trailing updates (joined inside, step by step)
+    ACX_TRY(spd_inverse_batched(l->h_jobs, l->d_jobs, 12, l->sched, l->damp, st, lane_of(l, 1, st).st));
   }
   mark(l, 7, st);
   if (p.kfac_apply) {
