@@ -705,7 +705,7 @@ __global__ void __launch_bounds__(256) gemm_finalize_kernel(OutParams o, const f
 // 672 x 512 result; this one is bound by the launch and one L2 round trip).  Fixed association order: deterministic.
 __global__ void __launch_bounds__(256) gemm_finalize_vec4_kernel(OutParams o, const float* __restrict__ ws, int ws_ld,
                                                                  long long ws_split_stride, int splits) {
-  const int nq = o.n >> 2;
+  const int nq = (o.n + 3) >> 2;   // a ragged last quad is allowed for plane-only outputs whose rows are padded (see below)
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i >= (long long)o.m * nq) return;
   const int m = (int)(i / nq), n = (int)(i - (long long)m * nq) << 2;
@@ -752,6 +752,11 @@ __global__ void __launch_bounds__(256) gemm_finalize_vec4_kernel(OutParams o, co
   }
   if (o.c) *reinterpret_cast<float4*>(o.c + (size_t)m * o.ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
   if (o.c_num_planes > 0) {
+    if (n + 3 >= o.n) {   // ragged last quad: the padding columns of the planes are kept zero
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (n + j >= o.n) v[j] = 0.0f;
+    }
     uint2 ph, pm, pl;
     split3x4(v[0], v[1], v[2], v[3], ph, pm, pl);
     const size_t idx = (size_t)m * o.ldcp + n;
@@ -762,7 +767,10 @@ __global__ void __launch_bounds__(256) gemm_finalize_vec4_kernel(OutParams o, co
 }
 static bool finalize_vec4_ok(const OutParams& o, int ws_ld, long long ws_split_stride) {
   auto al = [](const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; };
-  if ((o.n & 3) || (ws_ld & 3) || (ws_split_stride & 3)) return false;
+  if ((ws_ld & 3) || (ws_split_stride & 3)) return false;
+  if (o.n & 3) {   // ragged width: only plane outputs whose padded rows hold the whole last quad, nothing read per column
+    if (o.c || o.bias || o.mask || o.c_num_planes == 0 || o.ldcp < ((o.n + 3) & ~3) || ws_ld < ((o.n + 3) & ~3)) return false;
+  }
   if (o.c && ((o.ldc & 3) || !al(o.c, 16))) return false;
   if (o.bias && !al(o.bias, 16)) return false;
   if (o.mask && ((o.mask_ld & 3) || !al(o.mask, 8))) return false;
@@ -1187,7 +1195,7 @@ static int gemm_tc(const acx_gemm_t* g, cudaStream_t st) {
   } else if (pl.to_ws && !g->symmetric && pl.splits <= 16 && finalize_vec4_ok(p.out, p.ws_ld, p.ws_split_stride)) {
     // (deep split-K of a small result - the conv wgrads - keeps the kernel whose thread lanes share the splits: measured
     // 5.4 vs 14.1 us at 146 splits of a 256 x 32 result)
-    const long long quads = (long long)g->m * (g->n >> 2);
+    const long long quads = (long long)g->m * ((g->n + 3) >> 2);
     gemm_finalize_vec4_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, st>>>(p.out, g->workspace, p.ws_ld, p.ws_split_stride,
                                                                               pl.splits);
     ACX_LAUNCH_CHECK();

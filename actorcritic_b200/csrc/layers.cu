@@ -131,18 +131,37 @@ __global__ void heads_fwd_kernel(const Planes act4, const float* __restrict__ vp
     if (act4.n > 2) v += __bfloat162float(act4.p[2][idx]);
     x[j] = v;
   }
-  for (int a = 0; a <= num_actions; ++a) {
-    const float* w = a < num_actions ? vpol + a : vval;
-    const int ld = a < num_actions ? num_actions : 1;
-    float acc = 0.0f;
+  // up to 8 outputs at a time: their 16-term dot products and butterfly reductions are independent chains (one output
+  // after the other, as before, left the warp waiting on each reduction); per output the summation order is unchanged
+  for (int a0 = 0; a0 <= num_actions; a0 += 8) {
+    float acc[8];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc = fmaf(x[j], __ldg(w + (size_t)(lane + 32 * j) * ld), acc);
-    acc = warp_sum(acc);
+    for (int u = 0; u < 8; ++u) acc[u] = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int k = lane + 32 * j;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int a = a0 + u;
+        if (a <= num_actions) {
+          const float w = a < num_actions ? __ldg(vpol + (size_t)k * num_actions + a) : __ldg(vval + k);
+          acc[u] = fmaf(x[j], w, acc[u]);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
     if (lane == 0) {
-      if (a < num_actions)
-        logits[(size_t)row * num_actions + a] = acc + vpol[(size_t)512 * num_actions + a];
-      else
-        values[row] = acc + vval[512];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int a = a0 + u;
+        if (a < num_actions)
+          logits[(size_t)row * num_actions + a] = acc[u] + vpol[(size_t)512 * num_actions + a];
+        else if (a == num_actions)
+          values[row] = acc[u] + vval[512];
+      }
     }
   }
 }
@@ -170,14 +189,14 @@ __device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5
 // block reduction for the three scalars.  inv_count = 1/N_global_rows_per_rank (the means are per rank;
 // data-parallel ranks average them afterwards).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) loss_grad_kernel(const float* __restrict__ logits, const float* __restrict__ values,
+__global__ void __launch_bounds__(1024) loss_grad_kernel(const float* __restrict__ logits, const float* __restrict__ values,
                                                         const uint8_t* __restrict__ actions, const float* __restrict__ targets,
                                                         const int32_t* __restrict__ fisher_labels,
                                                         const float* __restrict__ fisher_eps, uint64_t seed,
                                                         const Sched* __restrict__ sched, int n_rows, int num_actions, float beta, float value_weight,
                                                         float* __restrict__ dheads, float* __restrict__ scalars,
                                                         int want_fisher) {
-  __shared__ float red[3][8];
+  __shared__ float red[3][32];
   const uint64_t step = sched ? sched->gs : 0ull;
   float s_obj = 0.f, s_ent = 0.f, s_val = 0.f;
   const float inv_n = 1.0f / (float)n_rows;
@@ -717,8 +736,10 @@ int heads_fwd(const Planes& act4, const float* vpol, const float* vval, int rows
 int loss_grad(const float* logits, const float* values, const uint8_t* actions, const float* targets, const int32_t* fl,
               const float* fe, uint64_t seed, const Sched* sched, int n_rows, int num_actions, float beta, float vw, float* dheads,
               float* scalars, int want_fisher, cudaStream_t st) {
-  loss_grad_kernel<<<1, 256, 0, st>>>(logits, values, actions, targets, fl, fe, seed, sched, n_rows, num_actions, beta, vw, dheads,
-                                      scalars, want_fisher);
+  // one row per thread up to 1024 rows (the serial exp / log chains of a row are the kernel's latency)
+  const int threads = n_rows >= 1024 ? 1024 : (n_rows + 31) / 32 * 32;
+  loss_grad_kernel<<<1, threads, 0, st>>>(logits, values, actions, targets, fl, fe, seed, sched, n_rows, num_actions, beta, vw,
+                                          dheads, scalars, want_fisher);
   ACX_LAUNCH_CHECK();
   return 0;
 }
