@@ -49,6 +49,7 @@ struct ConvTcParams {
   int sub_bytes;                               // bytes one sub-tile box delivers
   signed char tc1[CV_MAX_SUB], tc2[CV_MAX_SUB], tc3[CV_MAX_SUB];   // box coordinates of every sub-tile (dims 1..3)
   int num_pairs, pair_a[6], pair_b[6], npa, npb, stages;
+  int lo_from_tile, num_pairs_lo;              // tiles >= lo_from_tile accumulate only the first num_pairs_lo plane pairs
   // epilogue
   int dgrad;                                   // 0: output row = GEMM row; 1: pixel-shuffle scatter
   int hw_in, c_in, s, hq;
@@ -152,13 +153,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
     }
 #pragma unroll
     for (int t = 0; t < 4; ++t) a_step[t] = (uint32_t)((t / ksteps) * sub_tile_bytes + (t % ksteps) * 32) >> 4;
-    const int npairs = p.num_pairs;
     int it = 0, lt = 0;
     const bool trace = (p.debug & 32) && blockIdx.x == 0;
     long long w_full = 0, w_acc = 0, t_begin = trace ? clock64() : 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
       const int buf = lt & 1;
       const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
+      // rows that only feed the K-FAC output factors (the Fisher-sample half of the stacked backward batch) need the
+      // precision of those factors, not of the true gradient: fewer plane pairs for their tiles
+      const int npairs = tile >= p.lo_from_tile ? p.num_pairs_lo : p.num_pairs;
       long long tw = trace ? clock64() : 0;
       mbar_wait(&acc_empty[buf], aph ^ 1u, 4);
       if (trace) w_acc += clock64() - tw;
@@ -550,6 +553,8 @@ int conv_tc_forward(const Planes& x, const Planes& wT, const ConvGeom& g, int sa
   p.ts = CV_BM / rps;
   p.rows_valid = p.ts * rps;
   p.num_tiles = ceil_div(samples, p.ts);
+  p.lo_from_tile = p.num_tiles;          // every tile at full precision
+  p.num_pairs_lo = num_pairs;
   p.total_rows = samples * rps;
   p.bn = g.c_out;
   const int K = g.k * g.k * g.c_in;
@@ -596,8 +601,10 @@ int conv_tc_forward(const Planes& x, const Planes& wT, const ConvGeom& g, int sa
 // gout planes [samples, hw_out, hw_out, c_out]; wD = the rearranged weight planes of conv_dgrad_weight_planes;
 // mask_hi = hi plane of the forward activation below ([mask_samples, hw_in, hw_in, c_in]; sample r uses r % mask_samples)
 int conv_tc_dgrad(const Planes& gout, const Planes& wD, const ConvGeom& g, int samples, const bf16* mask_hi, int mask_samples,
-                  const Planes& dx, int num_pairs, const int* pair_a, const int* pair_b, cudaStream_t st) {
+                  const Planes& dx, int num_pairs, const int* pair_a, const int* pair_b, cudaStream_t st, int lo_from_sample,
+                  int num_pairs_lo) {
   ACX_CHECK(conv_tc_supported(g, 1), "unsupported convolution geometry for the gather-form input gradient");
+  ACX_CHECK(lo_from_sample < 0 || (num_pairs_lo >= 1 && num_pairs_lo <= num_pairs), "num_pairs_lo out of range");
   ACX_CHECK(samples > 0 && gout.n >= 1 && wD.n >= 1 && dx.n >= 1 && dx.ld == g.c_in && gout.ld == g.c_out, "bad operands");
   const int m = g.k / g.s, hq = g.hw_in / g.s;
   ConvTcParams p;
@@ -607,6 +614,8 @@ int conv_tc_dgrad(const Planes& gout, const Planes& wD, const ConvGeom& g, int s
   p.ts = 1;
   p.rows_valid = hq * hq;
   p.num_tiles = samples;
+  p.lo_from_tile = lo_from_sample >= 0 ? lo_from_sample : samples;   // one sample per tile
+  p.num_pairs_lo = lo_from_sample >= 0 ? num_pairs_lo : num_pairs;
   p.total_rows = samples * p.rows_valid;
   p.bn = g.s * g.s * g.c_in;
   const int K = m * m * g.c_out;

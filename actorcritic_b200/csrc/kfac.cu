@@ -362,8 +362,17 @@ __global__ void __launch_bounds__(256) dot_partial_kernel(const float* __restric
   const size_t per = (count + gridDim.x - 1) / gridDim.x;
   const size_t i0 = (size_t)blockIdx.x * per;
   const size_t i1 = i0 + per < count ? i0 + per : count;
-  double acc = 0.0;
-  for (size_t i = i0 + threadIdx.x; i < i1; i += 256) acc += (double)a[i] * (double)b[i];
+  // four independent accumulators: the loads of one thread do not wait for each other's DFMA
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  size_t i = i0 + threadIdx.x;
+  for (; i + 768 < i1; i += 1024) {
+    a0 += (double)a[i] * (double)b[i];
+    a1 += (double)a[i + 256] * (double)b[i + 256];
+    a2 += (double)a[i + 512] * (double)b[i + 512];
+    a3 += (double)a[i + 768] * (double)b[i + 768];
+  }
+  for (; i < i1; i += 256) a0 += (double)a[i] * (double)b[i];
+  double acc = (a0 + a1) + (a2 + a3);
   acc = warp_sum_d(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
@@ -404,7 +413,30 @@ __global__ void __launch_bounds__(256) kfac_step_kernel(float* __restrict__ para
     out_scalars[3] = lr;
   }
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+  const size_t tid0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t done = 0;
+  if ((((uintptr_t)params | (uintptr_t)vel | (uintptr_t)precon) & 15) == 0) {   // 16-byte accesses for the bulk
+    const size_t quads = count >> 2;
+    float4* p4 = reinterpret_cast<float4*>(params);
+    float4* v4 = reinterpret_cast<float4*>(vel);
+    const float4* u4 = reinterpret_cast<const float4*>(precon);
+    for (size_t i = tid0; i < quads; i += stride) {
+      float4 v = v4[i], th = p4[i];
+      const float4 u = u4[i];
+      v.x = mu * v.x + c * u.x;
+      v.y = mu * v.y + c * u.y;
+      v.z = mu * v.z + c * u.z;
+      v.w = mu * v.w + c * u.w;
+      th.x -= lr * v.x;
+      th.y -= lr * v.y;
+      th.z -= lr * v.z;
+      th.w -= lr * v.w;
+      v4[i] = v;
+      p4[i] = th;
+    }
+    done = quads << 2;
+  }
+  for (size_t i = done + tid0; i < count; i += stride) {
     const float v = mu * vel[i] + c * precon[i];
     vel[i] = v;
     params[i] -= lr * v;

@@ -58,7 +58,8 @@ bool conv_tc_supported(const ConvGeom& g, int dgrad);
 int conv_tc_forward(const Planes& x, const Planes& wT, const ConvGeom& g, int samples, const float* bias, int relu, const Planes& y,
                     int num_pairs, const int* pair_a, const int* pair_b, cudaStream_t st);
 int conv_tc_dgrad(const Planes& gout, const Planes& wD, const ConvGeom& g, int samples, const bf16* mask_hi, int mask_samples,
-                  const Planes& dx, int num_pairs, const int* pair_a, const int* pair_b, cudaStream_t st);
+                  const Planes& dx, int num_pairs, const int* pair_a, const int* pair_b, cudaStream_t st, int lo_from_sample = -1,
+                  int num_pairs_lo = 0);
 int conv_dgrad_weight_planes(const float* w, const ConvGeom& g, const Planes& out, cudaStream_t st);
 int conv_error_flag();
 

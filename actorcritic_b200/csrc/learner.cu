@@ -135,7 +135,7 @@ struct acx_learner {
   int64_t gs, ncov;
   bool inverses_valid;
   uint64_t act_calls;
-  int lvl_fwd, lvl_bwd, lvl_factor, lvl_precon, act_planes, grad_planes;
+  int lvl_fwd, lvl_bwd, lvl_fisher, lvl_factor, lvl_precon, act_planes, grad_planes;
   // optional stage timing (CUDA events on the launching stream)
   bool profiling = false;
   cudaEvent_t ev[ACX_NUM_STAGES + 2];
@@ -152,7 +152,7 @@ static const int kGramChunks = 444;   // 3 CTAs per SM
 static const size_t kDgradChunkBytes = 0;   // 0 = whole batch in one piece.  Measured on B200 at 32x20 (ACX_DGRAD_CHUNK_MB sweep):
                                             // whole 1.510 ms/update, 128 MB 1.533, 64 MB 1.551, 32 MB 1.599, 16 MB 1.681 - the
                                             // extra launches and wave tails cost more than the HBM round trip saves
-static const int kDotPartials = 64;
+static const int kDotPartials = 296;   // two chunks per SM: ~11 elements per thread at 865 k parameters
 
 static int pad8(int x) { return (x + 7) / 8 * 8; }
 
@@ -397,6 +397,12 @@ static void register_buffers(acx_learner* l) {
   reg(l, "targets", l->targets, (size_t)l->N * 4);
   reg(l, "advantages", l->adv, (size_t)l->N * 4);
   reg(l, "patches/conv1", l->P1.p[0], (size_t)l->R * 400 * 256 * 2);   // bf16 [R*400, 256], raw byte values
+  // hi planes of the forward activations = the ReLU masks the backward pass applies (act > 0); exposed so that the parity
+  // tests can tell arithmetic error from units whose pre-activation is within rounding of zero
+  reg(l, "act_hi/conv1", l->act1.p[0], (size_t)l->R * 400 * 32 * 2);
+  reg(l, "act_hi/conv2", l->act2.p[0], (size_t)l->R * 81 * 64 * 2);
+  reg(l, "act_hi/conv3", l->act3.p[0], (size_t)l->R * 49 * l->c3 * 2);
+  reg(l, "act_hi/fc4", l->act4.p[0], (size_t)l->R * 512 * 2);
   reg(l, "dheads", l->dheads, (size_t)2 * l->N * (l->A + 1) * 4);
   static const char* an[5] = {"conv1", "conv2", "conv3", "fc4", "heads"};
   for (int i = 0; i < 5; ++i) {
@@ -724,7 +730,14 @@ static int conv_dgrad(acx_learner* l, int li, const Planes& g, const bf16* act_b
   if (l->conv_tc[li]) {   // gather form on the tensor cores: no dP matrix, no col2im pass (conv.cu)
     int pa[6], pb[6];
     const int np = level_pairs(l->lvl_bwd, g.n, l->wD[li].n, pa, pb);
-    return conv_tc_dgrad(g, l->wD[li], geom_of(L), samples, act_below_hi, l->N, g_below, np, pa, pb, ln.st);
+    // samples beyond N are the Fisher-sample rows of the stacked backward batch: they only feed the output factors
+    // G_l (accumulated at lvl_factor), so their input gradients are taken at lvl_fisher (level_pairs orders the pairs
+    // by level: a lower level is a prefix)
+    int pa2[6], pb2[6];
+    const int np_lo = level_pairs(l->lvl_fisher, g.n, l->wD[li].n, pa2, pb2);
+    const bool lo = samples > l->N && np_lo < np;
+    return conv_tc_dgrad(g, l->wD[li], geom_of(L), samples, act_below_hi, l->N, g_below, np, pa, pb, ln.st, lo ? l->N : -1,
+                         np_lo);
   }
   const size_t per_sample = (size_t)L.T * L.K * sizeof(float);
   int chunk = (int)(l->dgrad_chunk_bytes / per_sample);
@@ -901,6 +914,7 @@ static int issue_phase2(acx_learner* l, const Plan2& p, cudaStream_t st) {
   const acx_learner_config_t& c = l->cfg;
   const size_t P = l->num_params;
   l->ev_next = 0;
+  Lane ema_ln = lane_of(l, 0, st);
   mark(l, 5, st);
   if (c.world_size > 1) ACX_TRY(scale_f32(l->bucket, l->bucket_floats, 1.0f / (float)c.world_size, st));
   ACX_CUDA(cudaMemcpyAsync(l->scalars, l->bscalars, 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -921,7 +935,14 @@ static int issue_phase2(acx_learner* l, const Plan2& p, cudaStream_t st) {
     ACX_TRY(momentum_clip_step(l->params, l->accum, l->grads, P, l->dot_partials, kDotPartials, c.cold_lr, c.cold_momentum,
                                c.clip_norm, l->scalars + 6, st));
   } else {          // kfac_utils.py:44: all covariance updates
-    ACX_TRY(ema_update(l->sums, l->stats, l->factor_floats, c.cov_ema_decay, 1.0f, st));
+    // nothing else in this phase reads the running sums unless the inverses are refreshed: the HBM-bound EMA pass then
+    // runs on a side lane next to the preconditioning (joined at the end of the phase, before the next update's
+    // statistics overwrite its input)
+    if (!p.invert) {
+      ema_ln = lane_of(l, 2, st);
+      ACX_TRY(fork_lane(l, st, ema_ln));
+    }
+    ACX_TRY(ema_update(l->sums, l->stats, l->factor_floats, c.cov_ema_decay, 1.0f, ema_ln.st));
   }
   mark(l, 6, st);
   if (p.invert) {
@@ -938,6 +959,7 @@ static int issue_phase2(acx_learner* l, const Plan2& p, cudaStream_t st) {
                       c.norm_constraint, l->scalars + 4, st));
   }
   if (p.refresh) ACX_TRY(refresh_weight_planes(l, st));
+  ACX_TRY(join_lane(l, ema_ln, st));
   if (!p.kfac_apply) mark(l, 8, st);
   mark(l, 9, st);
   return 0;
@@ -1022,6 +1044,14 @@ static void init_dims(acx_learner* l, const acx_learner_config_t* cfg) {
     case 4: l->act_planes = 3; l->grad_planes = 2; l->lvl_fwd = 2; l->lvl_bwd = 1; l->lvl_factor = 1; l->lvl_precon = 2; break;
     // default (parity grade): forward and backward fp32 class (6 pairs on 3 planes), factor SYRKs 3 pairs
     default: l->act_planes = 3; l->grad_planes = 3; l->lvl_fwd = 2; l->lvl_bwd = 2; l->lvl_factor = 1; l->lvl_precon = 2; break;
+  }
+  // Fisher-sample rows of the backward pass (conv input gradients): they only feed the output factors G_l, which are
+  // themselves accumulated at lvl_factor = 3 pairs and held to 1e-3, so 3 pairs are enough there (measured G-factor error
+  // in profiles/r1_precision.md); the true-gradient rows keep lvl_bwd.  ACX_FISHER_LEVEL=2 restores 6 pairs everywhere.
+  l->lvl_fisher = l->lvl_bwd < 1 ? l->lvl_bwd : 1;
+  if (const char* e = getenv("ACX_FISHER_LEVEL")) {
+    const int v = atoi(e);
+    if (v >= 0 && v <= l->lvl_bwd) l->lvl_fisher = v;
   }
   l->E = cfg->num_envs;
   l->T = cfg->num_steps;

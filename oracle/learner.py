@@ -49,7 +49,7 @@ class OracleLearner:
             self.rms = {name: torch.ones_like(net.join_vmat(name, self.params)) for name in net.LAYERS}
 
     # ------------------------------------------------------------------ gradient side
-    def compute(self, batch, y_hat=None, eps=None, need_fisher=True):
+    def compute(self, batch, y_hat=None, eps=None, need_fisher=True, masks=None):
         """Forward both towers, targets, losses, loss gradients, and (optionally) the Fisher-sample
         backward + the 11 batch factors.  Nothing is mutated."""
         obs = np.asarray(batch["observations"])
@@ -67,12 +67,12 @@ class OracleLearner:
         actions = np.asarray(batch["actions"]).reshape(n)
         losses = net.a2c_loss(fwd["logits"], fwd["value"], actions, targets, self.beta, self.value_weight)
         dz, dv = net.output_grads(fwd["logits"], fwd["value"], actions, targets, self.beta, self.value_weight)
-        grads, pre_grads = net.backward(self.params, fwd, dz, dv)
+        grads, pre_grads = net.backward(self.params, fwd, dz, dv, masks)
         out = dict(fwd=fwd, bootstrap_values=boot["value"], targets=targets, losses=losses, grads=grads,
                    pre_grads=pre_grads, dlogits=dz, dvalue=dv)
         if need_fisher:
             fz, fv = net.fisher_output_grads(fwd["logits"], fwd["value"], y_hat, eps)
-            _, fisher_pre = net.backward(self.params, fwd, fz, fv)
+            _, fisher_pre = net.backward(self.params, fwd, fz, fv, masks)
             out["fisher_pre_grads"] = fisher_pre
             out["new_a"], out["new_g"] = K.batch_factors(fwd, fisher_pre)
         return out

@@ -181,12 +181,19 @@ def fisher_output_grads(logits, values, y_hat, eps):
     return p - onehot, -torch.as_tensor(np.asarray(eps)).to(values.dtype)
 
 
-def backward(params, fwd, dlogits, dvalue):
+def backward(params, fwd, dlogits, dvalue, masks=None):
     """Hand-derived backward through the trunk for output gradients (dlogits [R,A], dvalue [R]).
 
     Returns (grads, pre_grads): grads[name] = V_l = [dW reshaped [K_l, C_l]; db] as one [K_l+1, C_l]
     matrix (SURVEY A.5 'Precondition'), pre_grads[name] = dL/d(pre-activation) [rows_l, C_l].
+
+    masks: optional {layer: bool [rows_l, C_l]} replacing the ReLU derivative `pre > 0` - the parity tests pass the
+    masks of the implementation under test, so that a unit whose pre-activation is within rounding of zero (and takes
+    the other branch there) does not drown the arithmetic comparison (tests/test_gpu_learner.py).
     """
+    def relu_mask(name, pre):
+        return (pre > 0) if masks is None or name not in masks else torch.as_tensor(masks[name]).reshape(pre.shape)
+
     grads, g = {}, {}
     act4 = fwd["heads_inputs"]
     g["fc_policy"] = dlogits
@@ -194,7 +201,7 @@ def backward(params, fwd, dlogits, dvalue):
     grads["fc_policy"] = torch.cat([act4.T @ dlogits, dlogits.sum(0, keepdim=True)], 0)
     grads["fc_baseline"] = torch.cat([act4.T @ g["fc_baseline"], g["fc_baseline"].sum(0, keepdim=True)], 0)
     d_act4 = dlogits @ params["fc_policy/weights"].T + g["fc_baseline"] @ params["fc_baseline/weights"].T
-    g4 = d_act4 * (fwd["fc4"]["pre"] > 0)
+    g4 = d_act4 * relu_mask("fc4", fwd["fc4"]["pre"])
     g["fc4"] = g4
     grads["fc4"] = torch.cat([fwd["fc4"]["inputs"].T @ g4, g4.sum(0, keepdim=True)], 0)
     d_flat = g4 @ params["fc4/weights"].T                       # [R, 49*c3]
@@ -203,7 +210,7 @@ def backward(params, fwd, dlogits, dvalue):
     for name in ("conv3", "conv2", "conv1"):
         k, s, cin, in_hw, out_hw = CONV_GEOM[name]
         layer = fwd[name]
-        gl = d_act * (layer["pre"] > 0)
+        gl = d_act * relu_mask(name, layer["pre"])
         g[name] = gl
         grads[name] = torch.cat([layer["patches"].T @ gl, gl.sum(0, keepdim=True)], 0)
         if name != "conv1":

@@ -53,6 +53,32 @@ def make_pair(cfg, seed=0):
     return e, o
 
 
+def engine_relu_masks(e):
+    """The ReLU masks the engine's backward pass applies: hi plane of each forward activation > 0, train rows only
+    ({layer: bool [rows_l, C_l]} in the oracle's row order)."""
+    n, c3 = e.rows, e.config.conv3_filters
+    geom = {"conv1": (400, 32), "conv2": (81, 64), "conv3": (49, c3), "fc4": (1, 512)}
+    masks = {}
+    for name, (locs, ch) in geom.items():
+        hi = e.buffer("act_hi/" + name, torch.bfloat16).view(-1, ch)[: n * locs]
+        masks[name] = (hi.float() > 0).cpu()
+    return masks
+
+
+def mask_disagreement(masks, fwd):
+    """Units where the engine's ReLU branch differs from the fp64 oracle's: {layer: (count, fraction, largest
+    |pre-activation| among them relative to the layer's rms pre-activation)}."""
+    out = {}
+    for name, m in masks.items():
+        pre = fwd[name]["pre"].detach()
+        diff = m.reshape(pre.shape) != (pre > 0)
+        cnt = int(diff.sum())
+        rms = float(pre.pow(2).mean().sqrt())
+        worst = float(pre[diff].abs().max()) / rms if cnt else 0.0
+        out[name] = (cnt, cnt / pre.numel(), worst)
+    return out
+
+
 def oracle_flat_params(o):
     return np.concatenate([onet.join_vmat(name, o.params).detach().numpy().ravel() for name in onet.LAYERS])
 
