@@ -1042,8 +1042,13 @@ static void init_dims(acx_learner* l, const acx_learner_config_t* cfg) {
     // on 2 planes / 3 pairs: 2^-17 relative to sum|terms| per GEMM, which compounds to ~6e-4 on the conv1/conv2 gradients
     // for iid-uniform observations (measured, profiles/r1_precision.md) - inside the contract but without margin
     case 4: l->act_planes = 3; l->grad_planes = 2; l->lvl_fwd = 2; l->lvl_bwd = 1; l->lvl_factor = 1; l->lvl_precon = 2; break;
-    // default (parity grade): forward and backward fp32 class (6 pairs on 3 planes), factor SYRKs 3 pairs
-    default: l->act_planes = 3; l->grad_planes = 3; l->lvl_fwd = 2; l->lvl_bwd = 2; l->lvl_factor = 1; l->lvl_precon = 2; break;
+    // 5: forward and backward with 6 pairs on 3 planes (the round-1 default until the mask-synchronised measurement
+    // showed that the third plane is below the accumulator's own rounding: no quantity improves, profiles/r1_precision.md)
+    case 5: l->act_planes = 3; l->grad_planes = 3; l->lvl_fwd = 2; l->lvl_bwd = 2; l->lvl_factor = 1; l->lvl_precon = 2; break;
+    // default (parity grade): activations and gradients on 2 bf16 planes, 3 plane pairs (hi*hi + hi*lo + lo*hi: ~2^-17,
+    // at the level of the fp32 tensor-core accumulation itself) for forward, backward and factor SYRKs; the
+    // preconditioning products 6 pairs on 3 planes (inverses and gradient blocks have a wide dynamic range)
+    default: l->act_planes = 2; l->grad_planes = 2; l->lvl_fwd = 1; l->lvl_bwd = 1; l->lvl_factor = 1; l->lvl_precon = 2; break;
   }
   // Fisher-sample rows of the backward pass (conv input gradients): they only feed the output factors G_l, which are
   // themselves accumulated at lvl_factor = 3 pairs and held to 1e-3, so 3 pairs are enough there (measured G-factor error

@@ -82,13 +82,14 @@ class OracleLearner:
         c = self.cfg
         return K.linear_decay(c.learning_rate_start, c.learning_rate_end, self.global_step, c.decay_steps)
 
-    def update(self, batch, y_hat=None, eps=None):
+    def update(self, batch, y_hat=None, eps=None, masks=None):
+        """One learner update.  masks: see network.backward (ReLU derivative taken at the given masks)."""
         if not self.acktr:
-            return self._update_a2c(batch)
+            return self._update_a2c(batch, masks)
         cfg = self.cfg
         gs0 = self.global_step
         cold = gs0 < cfg.num_cold_updates
-        info = self.compute(batch, y_hat, eps, need_fisher=not cold)
+        info = self.compute(batch, y_hat, eps, need_fisher=not cold, masks=masks)
         grads = info["grads"]
         lr = self.learning_rate()
         if cold:                                                     # kfac_utils.py:42-43
@@ -112,9 +113,9 @@ class OracleLearner:
         info.update(clip_coeff=coeff, fisher_norm=s, precon=precon, lr=lr)
         return info
 
-    def _update_a2c(self, batch):
+    def _update_a2c(self, batch, masks=None):
         cfg = self.cfg
-        info = self.compute(batch, need_fisher=False)
+        info = self.compute(batch, need_fisher=False, masks=masks)
         lr = self.learning_rate()
         clipped, norm = K.clip_by_global_norm(info["grads"], cfg.clip_norm)
         for name in net.LAYERS:

@@ -151,7 +151,12 @@ def run_schedule(cfg, num_updates, seed=0, obs_kind="uniform", collect=None, res
         assert gs_before == o.global_step
         params_before = oracle_flat_params(o)
         scal = e.update(batch, fl if cfg.acktr else None, fe if cfg.acktr else None)
-        info = o.update(batch, y_hat, eps) if cfg.acktr else o.update(batch)
+        # the oracle differentiates its ReLUs at the engine's masks (the forward activations of this update are still in
+        # the arena), and the units where that differs from its own branch must be within rounding of zero
+        masks = engine_relu_masks(e)
+        info = o.update(batch, y_hat, eps, masks=masks) if cfg.acktr else o.update(batch, masks=masks)
+        for name, (count, frac, worst) in mask_disagreement(masks, info["fwd"]).items():
+            assert worst <= 1e-4 and frac <= 1e-3, ("ReLU branch disagreement", u, name, count, frac, worst)
         torch.cuda.synchronize()
         rec = dict(update=u, gs_before=gs_before, gs_after=e.global_step, oracle_gs_after=o.global_step,
                    params_rel=rel_err(e.get_params_flat(), oracle_flat_params(o)),

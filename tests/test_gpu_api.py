@@ -64,7 +64,8 @@ def test_train_step_contract_matches_oracle(acktr):
                            model.actions_placeholder: batch["actions"].tolist(),
                            model.rewards_placeholder: batch["rewards"].tolist(),
                            model.terminals_placeholder: batch["terminals"].tolist()})
-            info = oracle.update(batch, y_hat, eps) if acktr else oracle.update(batch)
+            masks = LC.engine_relu_masks(model.engine)       # ReLU derivative at the engine's branch (see learner_checks)
+            info = oracle.update(batch, y_hat, eps, masks=masks) if acktr else oracle.update(batch, masks=masks)
             assert step == oracle.global_step
             assert abs(policy_loss - float(info["losses"]["policy_loss"])) <= 1e-4
             assert abs(baseline_loss - float(info["losses"]["baseline_loss"])) <= 1e-4
