@@ -131,37 +131,44 @@ __global__ void heads_fwd_kernel(const Planes act4, const float* __restrict__ vp
     if (act4.n > 2) v += __bfloat162float(act4.p[2][idx]);
     x[j] = v;
   }
-  // up to 8 outputs at a time: their 16-term dot products and butterfly reductions are independent chains (one output
-  // after the other, as before, left the warp waiting on each reduction); per output the summation order is unchanged
-  for (int a0 = 0; a0 <= num_actions; a0 += 8) {
-    float acc[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) acc[u] = 0.0f;
+  if (num_actions == 4 && ((uintptr_t)vpol & 15) == 0) {
+    // 4 actions (Breakout, a2c_acktr.py): the policy weights of one input are one 16-byte vector, and the five dot
+    // products / butterfly reductions run as independent chains (per output the summation order is that of the loop below)
+    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const int k = lane + 32 * j;
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int a = a0 + u;
-        if (a <= num_actions) {
-          const float w = a < num_actions ? __ldg(vpol + (size_t)k * num_actions + a) : __ldg(vval + k);
-          acc[u] = fmaf(x[j], w, acc[u]);
-        }
-      }
+      const float4 w = __ldg(reinterpret_cast<const float4*>(vpol) + k);
+      const float wv = __ldg(vval + k);
+      acc[0] = fmaf(x[j], w.x, acc[0]);
+      acc[1] = fmaf(x[j], w.y, acc[1]);
+      acc[2] = fmaf(x[j], w.z, acc[2]);
+      acc[3] = fmaf(x[j], w.w, acc[3]);
+      acc[4] = fmaf(x[j], wv, acc[4]);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-      for (int u = 0; u < 8; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+      for (int u = 0; u < 5; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
     if (lane == 0) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int a = a0 + u;
-        if (a < num_actions)
-          logits[(size_t)row * num_actions + a] = acc[u] + vpol[(size_t)512 * num_actions + a];
-        else if (a == num_actions)
-          values[row] = acc[u] + vval[512];
-      }
+      for (int u = 0; u < 4; ++u) logits[(size_t)row * 4 + u] = acc[u] + vpol[(size_t)512 * 4 + u];
+      values[row] = acc[4] + vval[512];
+    }
+    return;
+  }
+  for (int a = 0; a <= num_actions; ++a) {
+    const float* w = a < num_actions ? vpol + a : vval;
+    const int ld = a < num_actions ? num_actions : 1;
+    float acc = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc = fmaf(x[j], __ldg(w + (size_t)(lane + 32 * j) * ld), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      if (a < num_actions)
+        logits[(size_t)row * num_actions + a] = acc + vpol[(size_t)512 * num_actions + a];
+      else
+        values[row] = acc + vval[512];
     }
   }
 }

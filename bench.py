@@ -33,8 +33,11 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures of conv_tc_kernel at 2N = 1280
-# samples, conv3_filters = 32 (profiles/r1_prof_conv_dgrad2_raw.txt, r1_prof_conv_dgrad3_raw.txt)
-CONV_DGRAD_TRAFFIC = {"conv2": 115638528, "conv3": 19423488}
+# samples, conv3_filters = 32: default precision (2 planes, 3 pairs: profiles/r1_prof_conv_dgrad2_raw.txt, 43.92 MB read +
+# 17.14 MB written) and the former 3-plane / 6-pair preset 5 (profiles/r1_prof_conv_dgrad3_6pairs_raw.txt and the round's
+# earlier conv2 capture)
+CONV_DGRAD_TRAFFIC = {"conv2": 61060000}
+CONV_DGRAD_TRAFFIC_6PAIRS = {"conv2": 115638528, "conv3": 19423488}
 METRIC = "acktr_learner_env_steps_per_sec"
 UNIT = "env-steps/s"
 FRAMESKIP = 4   # a2c_acktr.py:195 - emulator frames per env-step
@@ -334,18 +337,21 @@ def run_native(args, rank, world, local_rank):
     # dominant launch of the update since the gather-form input gradient replaced dgrad GEMM + col2im: conv_tc_kernel on
     # conv3 / conv2 (true + Fisher rows = 2N samples), each timed alone with CUDA events on the launching stream on
     # operands of the update's own shapes; the longer of the two is reported as `roofline`
-    npairs = {0: 6, 4: 3, 1: 3, 2: 3, 3: 1}.get(args.precision, 6)
+    # plane pairs / gradient planes of the backward pass per precision preset (learner.cu init_dims): the default keeps
+    # activations and gradients on 2 bf16 planes and accumulates 3 plane pairs; preset 5 is the former 3-plane / 6-pair one
+    npairs = {0: 3, 4: 3, 1: 3, 2: 3, 3: 1, 5: 6}.get(args.precision, 3)
+    gplanes = {0: 2, 4: 2, 1: 2, 2: 2, 3: 1, 5: 3}.get(args.precision, 2)
     s2 = 2 * n
 
     def time_conv_dgrad(geom, mask_samples):
         hw_in, c_in, k, stride, hw_out, c_out = geom
         gen = torch.Generator(device=dev).manual_seed(7)
         gpl = [pl.reshape(s2, hw_out, hw_out, c_out)
-               for pl in ops.split_planes(torch.randn((s2 * hw_out * hw_out, c_out), device=dev, generator=gen) * 1e-3, 3)]
+               for pl in ops.split_planes(torch.randn((s2 * hw_out * hw_out, c_out), device=dev, generator=gen) * 1e-3, gplanes)]
         wd = ops.conv_dgrad_weights(torch.randn((k * k * c_in, c_out), device=dev, generator=gen) * 0.05, geom)
         act_mask = torch.rand((mask_samples, hw_in, hw_in, c_in), device=dev, generator=gen).to(torch.bfloat16)
         kw = dict(dgrad=True, mask=act_mask, mask_samples=mask_samples, pairs=ops.PAIRS[npairs])
-        out = ops.conv(gpl, wd, geom, s2, **kw)
+        out = ops.conv(gpl, wd, geom, s2, out_planes=gplanes, **kw)
         durs = []
         with torch.cuda.stream(e.stream):
             for i in range(4):   # first round = warm-up; 10 back-to-back launches per measurement (no host gap inside)
@@ -432,14 +438,14 @@ def run_native(args, rank, world, local_rank):
                                "%d bf16 plane pairs into one fp32 TMEM accumulator - the longest launch of the update" % (dom, s2, npairs),
                      "achieved": dg[dom]["flops"] / (dg[dom]["ms"] * 1e-3) / 1e12, "peak": peaks["tensor_burst"], "unit": "TFLOP/s",
                      "frac": dg[dom]["flops"] / (dg[dom]["ms"] * 1e-3) / 1e12 / peaks["tensor_burst"],
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/r1_prof_conv_dgrad{2,3}_raw.txt)
-                     "traffic": CONV_DGRAD_TRAFFIC.get(dom),
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/r1_prof_conv_dgrad2_raw.txt)
+                     "traffic": (CONV_DGRAD_TRAFFIC_6PAIRS if npairs == 6 else CONV_DGRAD_TRAFFIC).get(dom),
                      "algorithmic_gflop_per_launch": dg[dom]["flops"] / 1e9, "launch_ms": dg[dom]["ms"],
                      "issued_gflop_per_launch": dg[dom]["issued"] / 1e9,
                      "issued_tflops": dg[dom]["issued"] / (dg[dom]["ms"] * 1e-3) / 1e12,
                      "issued_frac": dg[dom]["issued"] / (dg[dom]["ms"] * 1e-3) / 1e12 / peaks["tensor_burst"],
-                     "note": "fp32-class arithmetic from bf16 tensor cores costs %d plane pairs, and a sample's %d output cells fill "
-                             "%d of a tile's 128 rows: the tensor pipe executes %.1fx the algorithmic FLOPs the fraction is charged on"
+                     "note": "fp32-grade products from bf16 tensor cores cost %d plane pairs (hi*hi + hi*lo + lo*hi), and a sample's %d "
+                             "output cells fill %d of a tile's 128 rows: the tensor pipe executes %.1fx the algorithmic FLOPs the fraction is charged on"
                              % (npairs, dg[dom]["rows_used"], dg[dom]["rows_used"], dg[dom]["issued"] / dg[dom]["flops"]),
                      "conv_dgrad_launches": {kk: {"launch_ms": v["ms"], "algorithmic_gflop": v["flops"] / 1e9,
                                                   "issued_gflop": v["issued"] / 1e9} for kk, v in dg.items()},
@@ -453,7 +459,7 @@ def run_native(args, rank, world, local_rank):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16x3 planes, fp32 accumulate (fp32-class)" if args.precision == 0 else "bf16 planes, precision preset %d" % args.precision,
+        "dtype": "bf16x2 planes (3 plane pairs), fp32 accumulate" if args.precision == 0 else "bf16 planes, precision preset %d" % args.precision,
         "data": "synthetic",
         "updates_per_sec": 1e3 / ms_step, "env_frames_per_sec": value * FRAMESKIP,
         "config": {"workload": workload_name(args, world), "precision": args.precision, "cuda_graphs": not args.no_graphs,

@@ -1,5 +1,5 @@
 """One acx_conv launch per case at the headline sizes (32 x 20: 672 forward samples, 1280 backward samples), for ncu.
-usage: conv_one.py [f2|f3|d2|d3] [pairs]"""
+usage: conv_one.py [f2|f3|d2|d3] [pairs] [reps] [planes]   (planes defaults to 2 for <= 3 pairs - the learner's default - else 3)"""
 import os
 import sys
 
@@ -12,6 +12,7 @@ from actorcritic_b200 import ops  # noqa: E402
 case = sys.argv[1] if len(sys.argv) > 1 else "f2"
 npairs = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 20
+planes = int(sys.argv[4]) if len(sys.argv) > 4 else (2 if npairs <= 3 else 3)
 geom = {"f2": (20, 32, 4, 2, 9, 64), "d2": (20, 32, 4, 2, 9, 64), "f3": (9, 64, 3, 1, 7, 32), "d3": (9, 64, 3, 1, 7, 32)}[case]
 hw_in, c_in, k, s, hw_out, c_out = geom
 dgrad = case[0] == "d"
@@ -21,17 +22,17 @@ w = torch.randn((k * k * c_in, c_out), device="cuda", generator=gen) * 0.05
 pairs = ops.PAIRS[npairs]
 if dgrad:
     x = torch.randn((samples * hw_out * hw_out, c_out), device="cuda", generator=gen)
-    xp = [p.reshape(samples, hw_out, hw_out, c_out) for p in ops.split_planes(x, 3)]
+    xp = [p.reshape(samples, hw_out, hw_out, c_out) for p in ops.split_planes(x, planes)]
     wp = ops.conv_dgrad_weights(w, geom)
     act = torch.rand((samples // 2, hw_in, hw_in, c_in), device="cuda", generator=gen).to(torch.bfloat16)
-    outs = ops.conv(xp, wp, geom, samples, dgrad=True, mask=act, mask_samples=samples // 2, pairs=pairs)
+    outs = ops.conv(xp, wp, geom, samples, dgrad=True, mask=act, mask_samples=samples // 2, pairs=pairs, out_planes=planes)
     run = lambda: ops.conv(xp, wp, geom, samples, dgrad=True, mask=act, mask_samples=samples // 2, pairs=pairs, outs=outs)
 else:
     x = torch.rand((samples * hw_in * hw_in, c_in), device="cuda", generator=gen)
-    xp = [p.reshape(samples, hw_in, hw_in, c_in) for p in ops.split_planes(x, 3)]
-    wp = ops.split_planes(w.t().contiguous(), 3)
+    xp = [p.reshape(samples, hw_in, hw_in, c_in) for p in ops.split_planes(x, planes)]
+    wp = ops.split_planes(w.t().contiguous(), planes)
     bias = torch.zeros(c_out, device="cuda")
-    outs = ops.conv(xp, wp, geom, samples, bias=bias, relu=True, pairs=pairs)
+    outs = ops.conv(xp, wp, geom, samples, bias=bias, relu=True, pairs=pairs, out_planes=planes)
     run = lambda: ops.conv(xp, wp, geom, samples, bias=bias, relu=True, pairs=pairs, outs=outs)
 for _ in range(2):
     run()
