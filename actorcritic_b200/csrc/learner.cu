@@ -138,6 +138,8 @@ struct acx_learner {
   int lvl_fwd, lvl_bwd, lvl_fisher, lvl_factor, lvl_precon, act_planes, grad_planes;
   // optional stage timing (CUDA events on the launching stream)
   bool profiling = false;
+  int defer_request = 0;                  // acx_learner_defer_input_factors: mask for the next phase 1
+  int deferred = 0;                       // what the last phase 1 actually left to phase 2
   cudaEvent_t ev[ACX_NUM_STAGES + 2];
   bool ev_set[ACX_NUM_STAGES + 2];
   std::map<std::string, Buf> named;
@@ -646,11 +648,31 @@ static int input_factor_stage(acx_learner* l, int stage, const Lane& ln, const L
 // skips them altogether.  Otherwise im2col + GEMM on the caller's stream.
 // With `factors` every input factor is issued on the aux lane the moment its operand is complete, so the factor SYRKs
 // overlap the rest of the forward and the whole backward.
+// Input-factor stages (bit s = input_factor_stage s) that phase 1 leaves to phase 2.  Only the next inverse refresh reads
+// the factor statistics, while the parameter update needs nothing but the gradients: on a single GPU the big conv SYRKs
+// therefore run on a side lane of phase 2, under its chain of small latency-bound kernels (preconditioning, KL clip,
+// apply, operand planes - ~90 us during which the SMs were mostly idle), instead of queueing behind the other heavy
+// kernels of phase 1.  Their operands (patch matrices, activations) stay intact until the next update's forward pass.
+// Data-parallel learners all-reduce the statistics between the phases and keep everything in phase 1; so does a caller
+// that runs phase 1 alone (acx_learner_defer_input_factors is opt-in per update).
+static int deferred_factors(const acx_learner* l) { return l->deferred; }
+static int resolve_deferred(const acx_learner* l) {
+  if (l->cfg.world_size > 1 || l->lanes < 3 || l->profiling || !l->cfg.acktr || l->defer_request == 0) return 0;
+  if (l->defer_request > 0) return l->defer_request & 31;
+  static int mask = -1;
+  if (mask < 0) {
+    const char* e = getenv("ACX_DEFER_FACTORS");
+    mask = e ? atoi(e) & 31 : 6;   // the library's choice: the conv2 and conv3 input factors
+  }
+  return mask;
+}
+
 static int forward(acx_learner* l, const uint8_t* obs, int rows, const Lane& ln, const Lane* aux, const Lane* aux2, bool factors) {
   const int c3 = l->c3;
   cudaStream_t st = ln.st;
   auto factor = [&](int stage) -> int {   // SYRK on aux, its border on aux2 (idle until the backward pass starts)
     if (!aux || !factors) return 0;
+    if (deferred_factors(l) & (1 << stage)) return 0;   // issued next to phase 2's latency-bound chain instead
     ACX_TRY(fork_lane(l, st, *aux));
     ACX_TRY(fork_lane(l, st, *aux2));
     return input_factor_stage(l, stage, *aux, *aux2);
@@ -942,6 +964,8 @@ static int issue_phase2(acx_learner* l, const Plan2& p, cudaStream_t st) {
       ema_ln = lane_of(l, 2, st);
       ACX_TRY(fork_lane(l, st, ema_ln));
     }
+    for (int stage = 0; stage < 5; ++stage)   // input factors that phase 1 left to this lane (see deferred_factors)
+      if (deferred_factors(l) & (1 << stage)) ACX_TRY(input_factor_stage(l, stage, ema_ln, ema_ln));
     ACX_TRY(ema_update(l->sums, l->stats, l->factor_floats, c.cov_ema_decay, 1.0f, ema_ln.st));
   }
   mark(l, 6, st);
@@ -1007,9 +1031,11 @@ static int run_cached(acx_learner* l, const GraphKey& key, cudaStream_t st, F&& 
 
 static int phase2(acx_learner* l, cudaStream_t st) {
   const Plan2 p = plan_phase2(l);
-  GraphKey key = {2, p.key(), nullptr, nullptr};
+  if (p.a2c || p.cold) l->deferred = 0;   // no covariance update in this phase: nothing can have been left to it
+  GraphKey key = {2, p.key() | (l->deferred << 5), nullptr, nullptr};
   const int r = run_cached(l, key, st, [&]() { return issue_phase2(l, p, st); });
   if (r) return r;
+  l->deferred = 0;
   advance_phase2(l, p);
   return 0;
 }
@@ -1257,10 +1283,19 @@ int acx_learner_phase1(acx_learner_t* l, const int32_t* d_fisher_labels, const f
   ACX_CHECK((d_fisher_labels == nullptr) == (d_fisher_eps == nullptr), "inject both Fisher labels and eps, or neither");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool fisher = l->cfg.acktr != 0 && l->gs >= l->cfg.num_cold_updates;
-  GraphKey key = {1, fisher ? 1 : 0, d_fisher_labels, d_fisher_eps};
+  l->deferred = fisher ? resolve_deferred(l) : 0;
+  l->defer_request = 0;   // one-shot
+  GraphKey key = {1, (fisher ? 1 : 0) | (l->deferred << 1), d_fisher_labels, d_fisher_eps};
   const int r = run_cached(l, key, st, [&]() { return issue_phase1(l, d_fisher_labels, d_fisher_eps, st); });
   l->a_ready_valid = r == 0 && fisher && l->lanes > 1 && !l->profiling;
   return r;
+}
+
+int acx_learner_defer_input_factors(acx_learner_t* l, int stage_mask) {
+  ACX_CHECK(l, "null learner");
+  ACX_CHECK(stage_mask >= -1 && stage_mask <= 31, "stage_mask out of range");
+  l->defer_request = stage_mask;
+  return 0;
 }
 
 int acx_learner_wait_input_factors(acx_learner_t* l, void* stream) {

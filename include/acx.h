@@ -236,6 +236,15 @@ int acx_learner_phase2(acx_learner_t* l, void* stream);
  * all-reduce it on `stream` while the backward pass still runs; returns -1 (and makes nobody wait) when the last phase 1
  * computed no factor statistics or ran serially - then the prefix is complete when phase 1 is. */
 int acx_learner_wait_input_factors(acx_learner_t* l, void* stream);
+/* Deferred input factors.  Only the next inverse refresh reads the K-FAC factor statistics, while the parameter update of
+ * phase 2 needs nothing but the gradients.  With a non-zero `stage_mask` (bit s = input factor of conv1, conv2, conv3, fc4,
+ * heads) the NEXT acx_learner_phase1 leaves those factor products to the following acx_learner_phase2, which runs them on
+ * a side lane under its chain of small latency-bound kernels.  Callers that read the statistics, or all-reduce them,
+ * between the two phases (data-parallel learners; world_size > 1 ignores the mask) keep the default 0.  -1 = the
+ * library's choice (the conv2 and conv3 factors, or ACX_DEFER_FACTORS).  Measured on B200 (32 x 20): no gain - the factor
+ * SYRKs are persistent CTAs that hold an SM's whole shared memory, so phase 2's small kernels queue behind them (end-to-end
+ * 0.87 -> 0.93 .. 1.09 ms per update): opt-in only, results are identical either way (tests/test_gpu_learner.py). */
+int acx_learner_defer_input_factors(acx_learner_t* l, int stage_mask);
 /* optional stage timing with CUDA events on the launching stream (bench.py's live roofline numbers).
  * stages: 0 forward, 1 returns+loss+heads backward, 2 backward (dgrad+wgrad), 3 factor statistics,
  *         4 cold step / factor EMA, 5 inverse refresh, 6 preconditioning, 7 KL clip+momentum+apply+operand refresh.
