@@ -138,6 +138,7 @@ struct acx_learner {
   int lvl_fwd, lvl_bwd, lvl_fisher, lvl_factor, lvl_precon, act_planes, grad_planes;
   // optional stage timing (CUDA events on the launching stream)
   bool profiling = false;
+  bool external_ema = false;              // acx_learner_set_external_ema: phase 2 leaves statistics scaling + EMA to acx_learner_ema
   int defer_request = 0;                  // acx_learner_defer_input_factors: mask for the next phase 1
   int deferred = 0;                       // what the last phase 1 actually left to phase 2
   cudaEvent_t ev[ACX_NUM_STAGES + 2];
@@ -938,7 +939,13 @@ static int issue_phase2(acx_learner* l, const Plan2& p, cudaStream_t st) {
   l->ev_next = 0;
   Lane ema_ln = lane_of(l, 0, st);
   mark(l, 5, st);
-  if (c.world_size > 1) ACX_TRY(scale_f32(l->bucket, l->bucket_floats, 1.0f / (float)c.world_size, st));
+  const bool ext_ema = l->external_ema && !p.a2c && !p.cold;   // the caller runs acx_learner_ema on its own stream
+  if (c.world_size > 1) {
+    if (ext_ema)   // only what this phase reads: [grads | scalars]; the statistics are scaled by acx_learner_ema
+      ACX_TRY(scale_f32(l->grads, l->bucket_floats - l->factor_floats, 1.0f / (float)c.world_size, st));
+    else
+      ACX_TRY(scale_f32(l->bucket, l->bucket_floats, 1.0f / (float)c.world_size, st));
+  }
   ACX_CUDA(cudaMemcpyAsync(l->scalars, l->bscalars, 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   // one launch for the whole schedule transition (kfac_utils.py:38-53): lr from the step the update starts with, then
   // global_step += (cold ? 2 : 1) [A2C: 1], covariance counter += (cold ? 0 : 1)
@@ -956,7 +963,7 @@ static int issue_phase2(acx_learner* l, const Plan2& p, cudaStream_t st) {
     ACX_TRY(dot_partial(l->grads, l->grads, P, l->dot_partials, kDotPartials, st));
     ACX_TRY(momentum_clip_step(l->params, l->accum, l->grads, P, l->dot_partials, kDotPartials, c.cold_lr, c.cold_momentum,
                                c.clip_norm, l->scalars + 6, st));
-  } else {          // kfac_utils.py:44: all covariance updates
+  } else if (!ext_ema) {          // kfac_utils.py:44: all covariance updates
     // nothing else in this phase reads the running sums unless the inverses are refreshed: the HBM-bound EMA pass then
     // runs on a side lane next to the preconditioning (joined at the end of the phase, before the next update's
     // statistics overwrite its input)
@@ -1032,7 +1039,7 @@ static int run_cached(acx_learner* l, const GraphKey& key, cudaStream_t st, F&& 
 static int phase2(acx_learner* l, cudaStream_t st) {
   const Plan2 p = plan_phase2(l);
   if (p.a2c || p.cold) l->deferred = 0;   // no covariance update in this phase: nothing can have been left to it
-  GraphKey key = {2, p.key() | (l->deferred << 5), nullptr, nullptr};
+  GraphKey key = {2, p.key() | (l->deferred << 5) | (l->external_ema ? 1 << 10 : 0), nullptr, nullptr};
   const int r = run_cached(l, key, st, [&]() { return issue_phase2(l, p, st); });
   if (r) return r;
   l->deferred = 0;
@@ -1289,6 +1296,30 @@ int acx_learner_phase1(acx_learner_t* l, const int32_t* d_fisher_labels, const f
   const int r = run_cached(l, key, st, [&]() { return issue_phase1(l, d_fisher_labels, d_fisher_eps, st); });
   l->a_ready_valid = r == 0 && fisher && l->lanes > 1 && !l->profiling;
   return r;
+}
+
+int acx_learner_update_plan(const acx_learner_t* l, int* has_factors, int* will_invert) {
+  ACX_CHECK(l, "null learner");
+  const Plan2 p = plan_phase2(l);
+  if (has_factors) *has_factors = (!p.a2c && !p.cold) ? 1 : 0;
+  if (will_invert) *will_invert = p.invert ? 1 : 0;
+  return 0;
+}
+
+int acx_learner_set_external_ema(acx_learner_t* l, int on) {
+  ACX_CHECK(l, "null learner");
+  l->external_ema = on != 0;
+  return 0;
+}
+
+int acx_learner_ema(acx_learner_t* l, void* stream) {
+  ACX_CHECK(l, "null learner");
+  ACX_CHECK(l->cfg.acktr, "acx_learner_ema: not a K-FAC learner");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const acx_learner_config_t& c = l->cfg;
+  if (c.world_size > 1) ACX_TRY(scale_f32(l->stats, l->factor_floats, 1.0f / (float)c.world_size, st));
+  ACX_TRY(ema_update(l->sums, l->stats, l->factor_floats, c.cov_ema_decay, 1.0f, st));
+  return 0;
 }
 
 int acx_learner_defer_input_factors(acx_learner_t* l, int stage_mask) {

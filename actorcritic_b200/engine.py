@@ -302,6 +302,9 @@ class Engine:
         return sd
 
     def load_state_dict(self, sd):
+        if getattr(self, "_ema_pending", False):   # a split exchange's EMA may still be writing the running sums
+            self.stream.wait_event(self._ema_done)
+            self._ema_pending = False
         for k in ("params", "velocity", "accum", "factor_sums", "inverses"):
             self.buffer(k, torch.float32).copy_(sd[k].to(self.device))
         self.refresh_derived()
@@ -386,6 +389,9 @@ class Engine:
         if defer_factors and self.config.world_size == 1:
             _lib.check(self.lib.acx_learner_defer_input_factors(self._h, -1))
         with self.on_stream():
+            if getattr(self, "_ema_pending", False):     # the previous update's EMA (split exchange) still reads the statistics
+                self.stream.wait_event(self._ema_done)
+                self._ema_pending = False
             _lib.check(self.lib.acx_learner_phase1(self._h, fl, fe, self._stream()))
 
     def allreduce(self, group=None, overlap=None):
@@ -413,6 +419,8 @@ class Engine:
             if rc > 0:
                 _lib.check(rc)
             early = rc == 0
+        if not overlap and self._split_exchange(group):
+            return
         with self.on_stream():
             if early:
                 with torch.cuda.stream(self._comm_stream):
@@ -423,7 +431,48 @@ class Engine:
             else:
                 dist.all_reduce(self.bucket, op=dist.ReduceOp.SUM, group=group)
 
+    def _split_exchange(self, group):
+        """NCCL groups, K-FAC learners, covariance updates: phase 2 reads only [grads | scalars] of the bucket, so only
+        [G | grads | scalars] (4.5 MB at conv3 = 32) is all-reduced on the engine's stream; the input-factor prefix A (13.6 MB)
+        is all-reduced on a second stream and communicator UNDER phase 2, followed there by the statistics' 1/k scaling and
+        the EMA (acx_learner_ema).  The engine's stream waits for that only before an inverse refresh and before the next
+        phase 1 overwrites the statistics.  Same arithmetic in the same order as the single all-reduce: bit-identical
+        (tools/dp_overlap_check.py).  ACX_DP_SPLIT=0 switches it off."""
+        dist = torch.distributed
+        if (not self.config.acktr or os.environ.get("ACX_DP_SPLIT", "1") == "0" or dist.get_backend(group) != "nccl"):
+            return False
+        has_factors, will_invert = ctypes.c_int(0), ctypes.c_int(0)
+        _lib.check(self.lib.acx_learner_update_plan(self._h, ctypes.byref(has_factors), ctypes.byref(will_invert)))
+        if not has_factors.value:
+            return False
+        if getattr(self, "_split_stream", None) is None:
+            self._split_stream = torch.cuda.Stream(self.device)
+            self._split_group = dist.new_group(ranks=dist.get_process_group_ranks(group or dist.group.WORLD), backend="nccl")
+            self._p1_done, self._rest_done = torch.cuda.Event(), torch.cuda.Event()
+            self._ema_done = torch.cuda.Event()
+            self._split_a = self.buffer("input_factor_stats", torch.float32)
+            self._split_rest = self.bucket[self._split_a.numel():]
+        with self.on_stream():
+            self._p1_done.record(self.stream)
+            dist.all_reduce(self._split_rest, op=dist.ReduceOp.SUM, group=group)
+            self._rest_done.record(self.stream)
+            with torch.cuda.stream(self._split_stream):
+                self._split_stream.wait_event(self._p1_done)
+                dist.all_reduce(self._split_a, op=dist.ReduceOp.SUM, group=self._split_group)
+                self._split_stream.wait_event(self._rest_done)      # the G statistics travel with the gradients
+                _lib.check(self.lib.acx_learner_ema(self._h, ctypes.c_void_p(self._split_stream.cuda_stream)))
+                self._ema_done.record(self._split_stream)
+            if will_invert.value:
+                self.stream.wait_event(self._ema_done)
+        self._ema_external = True
+        self._ema_pending = True
+        return True
+
     def phase2(self):
+        external = bool(getattr(self, "_ema_external", False))
+        if self.config.world_size > 1:
+            _lib.check(self.lib.acx_learner_set_external_ema(self._h, int(external)))
+        self._ema_external = False
         with self.on_stream():
             _lib.check(self.lib.acx_learner_phase2(self._h, self._stream()))
 

@@ -236,6 +236,18 @@ int acx_learner_phase2(acx_learner_t* l, void* stream);
  * all-reduce it on `stream` while the backward pass still runs; returns -1 (and makes nobody wait) when the last phase 1
  * computed no factor statistics or ran serially - then the prefix is complete when phase 1 is. */
 int acx_learner_wait_input_factors(acx_learner_t* l, void* stream);
+/* Split exchange for data-parallel learners.  Phase 2 reads only [grads | scalars] of the reduce bucket (and the stored
+ * inverses); the factor statistics [A | G] are read by the EMA alone, whose result nothing needs before the next inverse
+ * refresh.  A caller may therefore reduce the statistics on a second stream / communicator while phase 2 runs:
+ *   acx_learner_update_plan        what the next phase 2 will do: has_factors (a covariance update: the statistics of this
+ *                                  phase 1 are live), will_invert (it refreshes the inverses: the EMA must be complete first)
+ *   acx_learner_set_external_ema   on: the next phase 2 calls scale only [grads | scalars] by 1 / world_size and skip the EMA
+ *   acx_learner_ema                scales the statistics by 1 / world_size and applies the EMA on `stream` (the caller orders
+ *                                  it after its all-reduce of the statistics and before the next phase 1 / a refreshing phase 2)
+ * (actorcritic_b200.Engine.allreduce does this for NCCL groups; bit-identical to the single all-reduce.) */
+int acx_learner_update_plan(const acx_learner_t* l, int* has_factors, int* will_invert);
+int acx_learner_set_external_ema(acx_learner_t* l, int on);
+int acx_learner_ema(acx_learner_t* l, void* stream);
 /* Deferred input factors.  Only the next inverse refresh reads the K-FAC factor statistics, while the parameter update of
  * phase 2 needs nothing but the gradients.  With a non-zero `stage_mask` (bit s = input factor of conv1, conv2, conv3, fc4,
  * heads) the NEXT acx_learner_phase1 leaves those factor products to the following acx_learner_phase2, which runs them on

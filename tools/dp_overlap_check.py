@@ -19,7 +19,8 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 envs, steps, updates = 8, 5, 26
 
 
-def run(overlap):
+def run(overlap, split="0"):
+    os.environ["ACX_DP_SPLIT"] = split
     cfg = eng.EngineConfig(num_envs=envs, num_steps=steps, conv3_filters=32, world_size=world, num_cold_updates=4, invert_every=3,
                            seed=7)
     e = eng.Engine(cfg)
@@ -34,16 +35,19 @@ def run(overlap):
         early += int(overlap and e.lib.acx_learner_wait_input_factors(e._h, None) == 0)
         e.phase2()
     torch.cuda.synchronize()
-    return e.get_params_flat().copy(), early
+    sums = e.buffer("factor_sums", torch.float32).cpu().numpy().copy()
+    return np.concatenate([e.get_params_flat().copy(), sums]), early
 
 
 p_plain, _ = run(False)
 p_over, early = run(True)
-same = bool(np.array_equal(p_plain, p_over))
+p_split, _ = run(False, split="1")
+same = bool(np.array_equal(p_plain, p_over)) and bool(np.array_equal(p_plain, p_split))
 t = torch.tensor([int(same)], device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print("overlapped == plain:", bool(t.item()), "| updates with an early all-reduce:", early, "of", updates,
+    print("overlapped == plain == split exchange (parameters and factor sums):", bool(t.item()), "| split max |diff|",
+          float(np.abs(p_plain - p_split).max()), "| overlapped:", "| updates with an early all-reduce:", early, "of", updates,
           "| max |diff|", float(np.abs(p_plain - p_over).max()))
 dist.destroy_process_group()
 sys.exit(0 if t.item() else 1)
