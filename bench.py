@@ -250,9 +250,12 @@ def run_native(args, rank, world, local_rank):
         e.phase2()
         return e.fetch_scalars() if fetch else None
 
-    # prime: post-cold state, then enough updates to pass the first inverse refresh (not part of warm-up or timing)
+    # prime: post-cold state, then enough updates to pass TWO inverse refreshes (not part of warm-up or timing): the
+    # library captures the CUDA graph of a schedule variant on its second use, so after 23 updates (refreshes at
+    # global_step 40 and 50) both the plain and the refreshing update replay as graphs from the first timed step on,
+    # whatever --warmup is
     e.set_state(30, 0, False)
-    for i in range(11):
+    for i in range(23):
         step(i, resident, False)
     torch.cuda.synchronize()
     assert e.get_state()["inverses_valid"]
