@@ -221,9 +221,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
     const int grp = (warp - 2) >> 2;
     const int nchunks = BN >> 5;
     float* st = epi + (size_t)(warp - 2) * (32 * 32);   // 32 x 32 fp32, 16-byte groups XOR-swizzled by the row (no padding)
-    constexpr int CH = 32, LPR = 8, RPI = 4, NIT = 8;
-    const int rsub = lane >> 3;
-    const int cg = lane & 7;              // 4-column group inside the chunk
+    // a lane owns 8 consecutive columns of a row (two 16-byte staging groups): 16-byte stores / mask loads per plane, 4 lanes
+    // per 32-column row, 8 rows per iteration (8-byte stores cost conv2's input gradient 15 of its 53 us: ACX_CONV_DEBUG=8)
+    constexpr int CH = 32, LPR = 4, RPI = 8, NIT = 4;
+    const int rsub = lane >> 2;
+    const int cg = lane & 3;              // 8-column group inside the chunk
     bf16* const cp0 = p.cp[0];
     bf16* const cp1 = p.cp[1];
     bf16* const cp2 = p.cp[2];
@@ -246,20 +248,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
         }
       }
     }
-    uint32_t col_off[2];        // element offset of this lane's 4 columns in the warp's first / second chunk
-    float4 bias4[2];
+    uint32_t col_off[2];        // element offset of this lane's 8 columns in the warp's first / second chunk
+    float4 bias4[2][2];
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-      const int n = (grp + 2 * c) * CH + cg * 4;
+      const int n = (grp + 2 * c) * CH + cg * 8;
       col_off[c] = (uint32_t)n;
-      bias4[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      bias4[c][0] = bias4[c][1] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (n < BN) {
-        if (p.dgrad) {   // column (py, px, ci) -> pixel (py, px) inside the cell
+        if (p.dgrad) {   // column (py, px, ci) -> pixel (py, px) inside the cell (c_in is a multiple of 8: one pixel)
           const int pp = n / p.c_in, ci = n - pp * p.c_in;
           const int py = pp / p.s, px = pp - py * p.s;
           col_off[c] = (uint32_t)((py * p.hw_in + px) * p.c_in + ci);
         }
-        if (p.bias) bias4[c] = make_float4(__ldg(p.bias + n), __ldg(p.bias + n + 1), __ldg(p.bias + n + 2), __ldg(p.bias + n + 3));
+        if (p.bias) {
+          bias4[c][0] = make_float4(__ldg(p.bias + n), __ldg(p.bias + n + 1), __ldg(p.bias + n + 2), __ldg(p.bias + n + 3));
+          bias4[c][1] = make_float4(__ldg(p.bias + n + 4), __ldg(p.bias + n + 5), __ldg(p.bias + n + 6), __ldg(p.bias + n + 7));
+        }
       }
     }
     const size_t tile_stride = p.dgrad ? (size_t)p.hw_in * p.hw_in * p.c_in : (size_t)p.rows_valid * p.ldcp;
@@ -298,41 +303,45 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
           }
           __syncwarp();
           const uint32_t coff = c == 0 ? col_off[0] : col_off[1];
-          const float4 b4 = c == 0 ? bias4[0] : bias4[1];
+          const float4 b4a = c == 0 ? bias4[0][0] : bias4[1][0];
+          const float4 b4b = c == 0 ? bias4[0][1] : bias4[1][1];
           // pass 1: every ReLU-mask word of this chunk is requested before the first one is used (one L2 round trip per
           // chunk instead of one per row)
-          uint2 mw[NIT];
+          uint4 mw[NIT];
           if (mask) {
 #pragma unroll
             for (int t = 0; t < NIT; ++t) {
-              mw[t] = make_uint2(0x3f803f80u, 0x3f803f80u);   // bf16 1.0: keep
-              if (row_off[t] < row_limit) mw[t] = __ldg(reinterpret_cast<const uint2*>(mask + mbase + row_off[t] + coff));
+              mw[t] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);   // bf16 1.0: keep
+              if (row_off[t] < row_limit) mw[t] = __ldg(reinterpret_cast<const uint4*>(mask + mbase + row_off[t] + coff));
             }
           }
 #pragma unroll
           for (int t = 0; t < NIT; ++t) {
             if (row_off[t] < row_limit) {
               const int r = rsub + t * RPI;
-              const float4 a4 = *reinterpret_cast<const float4*>(st + r * 32 + ((cg ^ (r & 7)) << 2));
-              float v0 = fmaf(alpha, a4.x, b4.x), v1 = fmaf(alpha, a4.y, b4.y), v2 = fmaf(alpha, a4.z, b4.z), v3 = fmaf(alpha, a4.w, b4.w);
+              const float4 a4 = *reinterpret_cast<const float4*>(st + r * 32 + (((2 * cg) ^ (r & 7)) << 2));
+              const float4 c4 = *reinterpret_cast<const float4*>(st + r * 32 + (((2 * cg + 1) ^ (r & 7)) << 2));
+              float v[8] = {fmaf(alpha, a4.x, b4a.x), fmaf(alpha, a4.y, b4a.y), fmaf(alpha, a4.z, b4a.z), fmaf(alpha, a4.w, b4a.w),
+                            fmaf(alpha, c4.x, b4b.x), fmaf(alpha, c4.y, b4b.y), fmaf(alpha, c4.z, b4b.z), fmaf(alpha, c4.w, b4b.w)};
               if (relu) {
-                v0 = fmaxf(v0, 0.0f);
-                v1 = fmaxf(v1, 0.0f);
-                v2 = fmaxf(v2, 0.0f);
-                v3 = fmaxf(v3, 0.0f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
               }
               if (mask) {
-                if (!(__uint_as_float(mw[t].x << 16) > 0.0f)) v0 = 0.0f;
-                if (!(__uint_as_float(mw[t].x & 0xffff0000u) > 0.0f)) v1 = 0.0f;
-                if (!(__uint_as_float(mw[t].y << 16) > 0.0f)) v2 = 0.0f;
-                if (!(__uint_as_float(mw[t].y & 0xffff0000u) > 0.0f)) v3 = 0.0f;
+                const uint32_t mwords[4] = {mw[t].x, mw[t].y, mw[t].z, mw[t].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  if (!(__uint_as_float(mwords[j] << 16) > 0.0f)) v[2 * j] = 0.0f;
+                  if (!(__uint_as_float(mwords[j] & 0xffff0000u) > 0.0f)) v[2 * j + 1] = 0.0f;
+                }
               }
-              uint2 ph, pm, pl;
-              split3x4(v0, v1, v2, v3, ph, pm, pl);
+              uint2 ph0, pm0, pl0, ph1, pm1, pl1;
+              split3x4(v[0], v[1], v[2], v[3], ph0, pm0, pl0);
+              split3x4(v[4], v[5], v[6], v[7], ph1, pm1, pl1);
               const size_t idx = base + row_off[t] + coff;
-              *reinterpret_cast<uint2*>(cp0 + idx) = ph;
-              if (npl > 1) *reinterpret_cast<uint2*>(cp1 + idx) = pm;
-              if (npl > 2) *reinterpret_cast<uint2*>(cp2 + idx) = pl;
+              *reinterpret_cast<uint4*>(cp0 + idx) = make_uint4(ph0.x, ph0.y, ph1.x, ph1.y);
+              if (npl > 1) *reinterpret_cast<uint4*>(cp1 + idx) = make_uint4(pm0.x, pm0.y, pm1.x, pm1.y);
+              if (npl > 2) *reinterpret_cast<uint4*>(cp2 + idx) = make_uint4(pl0.x, pl0.y, pl1.x, pl1.y);
             }
           }
           __syncwarp();
@@ -582,6 +591,8 @@ int conv_tc_forward(const Planes& x, const Planes& wT, const ConvGeom& g, int sa
   p.ldcp = y.ld;
   p.mask = nullptr;
   p.mask_samples = 1;
+  ACX_CHECK((g.c_out & 7) == 0, "forward: c_out % 8");   // the epilogue moves 8 channels (16 bytes) per lane
+  for (int i = 0; i < y.n; ++i) ACX_CHECK((reinterpret_cast<uintptr_t>(y.p[i]) & 15) == 0, "output planes must be 16-byte aligned");
   CUtensorMap ta[3], tb[3];
   const long long row = (long long)g.hw_in * g.c_in;   // elements of one input row
   for (int i = 0; i < 3; ++i) {
@@ -643,6 +654,9 @@ int conv_tc_dgrad(const Planes& gout, const Planes& wD, const ConvGeom& g, int s
   p.ldcp = dx.ld;
   p.mask = mask_hi;
   p.mask_samples = mask_samples > 0 ? mask_samples : samples;
+  // the epilogue moves 8 channels (16 bytes) per lane
+  ACX_CHECK((g.c_in & 7) == 0 && (reinterpret_cast<uintptr_t>(mask_hi) & 15) == 0, "input gradient: c_in % 8 / mask alignment");
+  for (int i = 0; i < dx.n; ++i) ACX_CHECK((reinterpret_cast<uintptr_t>(dx.p[i]) & 15) == 0, "output planes must be 16-byte aligned");
   CUtensorMap ta[3], tb[3];
   const long long row = (long long)g.hw_out * g.c_out;
   for (int i = 0; i < 3; ++i) {
