@@ -451,9 +451,71 @@ static int launch_kpre(const uint8_t* raw_a, const uint8_t* raw_b, const uint8_t
   return 0;
 }
 
+// ---- the stages of K-PRE on their own (the per-environment wrapper classes of the reference's API) ----------------------
+// byte-wise max of two frames (AtariFrameskipWrapper.step, wrappers.py:64-65); 16 bytes per thread, scalar tail
+__global__ void __launch_bounds__(256) frame_max_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
+                                                        uint8_t* __restrict__ out, size_t nbytes) {
+  const size_t quads = nbytes >> 4;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (size_t i = t0; i < quads; i += stride) {
+    const uint4 x = __ldg(reinterpret_cast<const uint4*>(a) + i), y = __ldg(reinterpret_cast<const uint4*>(b) + i);
+    reinterpret_cast<uint4*>(out)[i] = make_uint4(max_u8x4(x.x, y.x), max_u8x4(x.y, y.y), max_u8x4(x.z, y.z), max_u8x4(x.w, y.w));
+  }
+  for (size_t i = (quads << 4) + t0; i < nbytes; i += stride) out[i] = a[i] > b[i] ? a[i] : b[i];
+}
+
+// FrameStackWrapper.step / reset on already preprocessed frames (wrappers.py:224-235): frames uint8 [E,84,84] (one gray
+// byte per pixel), stacks one 32-bit word per pixel.  mode per environment: 0 = push, 1 = push after a terminal step
+// (all older frames zero), 2 = reset (4 copies)
+__global__ void __launch_bounds__(256) framestack_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restrict__ mode,
+                                                         const uint32_t* stack_in, uint32_t* stack_out, int num_envs) {
+  const int per = OUT * OUT;
+  const size_t total = (size_t)num_envs * per;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int env = (int)(i / per);
+    const uint32_t q = frames[i];
+    const int m = mode ? mode[env] : 0;
+    uint32_t word;
+    if (m == 2)
+      word = q * 0x01010101u;
+    else
+      word = (m == 1 ? 0u : (stack_in[i] >> 8)) | (q << 24);
+    stack_out[i] = word;
+  }
+}
+
 }  // namespace acx
 
 extern "C" {
+
+int acx_frame_max_u8(const uint8_t* d_a, const uint8_t* d_b, uint8_t* d_out, size_t nbytes, void* stream) {
+  using namespace acx;
+  if (nbytes == 0) return 0;
+  ACX_CHECK(d_a && d_b && d_out, "null pointer");
+  ACX_CHECK((((uintptr_t)d_a | (uintptr_t)d_b | (uintptr_t)d_out) & 15) == 0, "misaligned buffer");
+  size_t blocks = ((nbytes >> 4) + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  frame_max_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_a, d_b, d_out, nbytes);
+  ACX_LAUNCH_CHECK();
+  return 0;
+}
+
+int acx_framestack_push_u8(const uint8_t* d_frames, const uint8_t* d_mode, const uint8_t* d_stack_in, uint8_t* d_stack_out,
+                           int num_envs, void* stream) {
+  using namespace acx;
+  ACX_CHECK(num_envs >= 0, "num_envs < 0");
+  if (num_envs == 0) return 0;
+  ACX_CHECK(d_frames && d_stack_in && d_stack_out, "null pointer");
+  ACX_CHECK((((uintptr_t)d_stack_in | (uintptr_t)d_stack_out) & 3) == 0, "misaligned stack");
+  size_t blocks = ((size_t)num_envs * OUT * OUT + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  framestack_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      d_frames, d_mode, reinterpret_cast<const uint32_t*>(d_stack_in), reinterpret_cast<uint32_t*>(d_stack_out), num_envs);
+  ACX_LAUNCH_CHECK();
+  return 0;
+}
 
 int acx_preprocess_stack_u8(const uint8_t* d_raw_a, const uint8_t* d_raw_b, const uint8_t* d_terminal,
                             const uint8_t* d_reset_mask, const uint8_t* d_reset_raw, const uint8_t* d_stack_in,

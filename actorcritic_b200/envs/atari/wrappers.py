@@ -62,8 +62,38 @@ class AtariPreprocessFrameWrapper:
         return self.observation(observation), reward, terminal, info
 
 
+class AtariFrameskipWrapper:
+    """wrappers.py:36-70 for one environment: repeats the action `frameskip` times, sums the rewards, stops at a terminal
+    step, and returns the byte-wise max of the last two frames (acx_frame_max_u8) - or the only frame when the first
+    sub-step was terminal."""
+
+    def __init__(self, env, frameskip):
+        self.env = env
+        self._frameskip = frameskip
+        self.action_space = getattr(env, "action_space", None)
+        self.observation_space = getattr(env, "observation_space", None)
+
+    def step(self, action):
+        frames, total_reward, terminal, info = [], 0.0, False, None
+        for _ in range(self._frameskip):
+            next_frame, reward, terminal, info = self.env.step(action)
+            frames.append(next_frame)
+            total_reward += reward
+            if terminal:
+                break
+        if len(frames) >= 2:
+            a = torch.from_numpy(np.ascontiguousarray(frames[-2], dtype=np.uint8)).cuda()
+            b = torch.from_numpy(np.ascontiguousarray(frames[-1], dtype=np.uint8)).cuda()
+            return ops.frame_max(a, b).cpu().numpy(), total_reward, terminal, info
+        return frames[0], total_reward, terminal, info
+
+    def reset(self, **kwargs):
+        return self.env.reset(**kwargs)
+
+
 class FrameStackWrapper:
-    """wrappers.py:201-235 for one environment that already yields [84,84,1] frames (host arrays)."""
+    """wrappers.py:201-235 for one environment that already yields [84,84,1] frames (host arrays); the stack lives on the
+    device and is pushed by acx_framestack_push_u8."""
 
     def __init__(self, env, num_stacked_frames):
         if num_stacked_frames != 4:
@@ -73,18 +103,15 @@ class FrameStackWrapper:
         self.observation_space = spaces.Box(low=0, high=255, shape=(84, 84, 4), dtype=np.uint8)
         self._stack = torch.zeros((1, 84, 84, 4), dtype=torch.uint8, device="cuda")
 
+    def _push(self, frame, mode):
+        f = torch.from_numpy(np.ascontiguousarray(frame, np.uint8).reshape(1, 84, 84)).cuda()
+        m = torch.tensor([mode], dtype=torch.uint8, device="cuda")
+        ops.framestack_push(f, self._stack, mode=m, out=self._stack)
+        return self._stack[0].cpu().numpy()
+
     def step(self, action):
         frame, reward, terminal, info = self.env.step(action)
-        word = self._stack.view(torch.int32)
-        f = torch.from_numpy(np.ascontiguousarray(frame, np.uint8).reshape(1, 84, 84, 1)).cuda()
-        shifted = torch.zeros_like(self._stack) if terminal else torch.roll(self._stack, -1, dims=-1)
-        shifted[..., 3:4] = f
-        self._stack = shifted
-        del word
-        return self._stack[0].cpu().numpy(), reward, terminal, info
+        return self._push(frame, 1 if terminal else 0), reward, terminal, info       # wrappers.py:226-229
 
     def reset(self, **kwargs):
-        frame = self.env.reset(**kwargs)
-        f = torch.from_numpy(np.ascontiguousarray(frame, np.uint8).reshape(1, 84, 84, 1)).cuda()
-        self._stack = f.repeat(1, 1, 1, 4)
-        return self._stack[0].cpu().numpy()
+        return self._push(self.env.reset(**kwargs), 2)                                 # wrappers.py:234

@@ -54,6 +54,29 @@ def preprocess_reset(raw, out=None, out_env_stride=None):
     return out
 
 
+def frame_max(a, b):
+    """acx_frame_max_u8: byte-wise max of two uint8 CUDA tensors of the same shape (wrappers.py:64-65)."""
+    _need_cuda(a, b)
+    assert a.dtype == torch.uint8 and b.dtype == torch.uint8 and a.shape == b.shape and a.is_contiguous() and b.is_contiguous()
+    out = torch.empty_like(a)
+    _lib.check(_lib.load().acx_frame_max_u8(_ptr(a), _ptr(b), _ptr(out), ctypes.c_size_t(a.numel()), _stream()))
+    return out
+
+
+def framestack_push(frames, stack_in, mode=None, out=None):
+    """acx_framestack_push_u8: frames uint8 [E,84,84(,1)], stacks uint8 [E,84,84,4]; mode uint8 [E]: 0 push, 1 push after
+    a terminal step, 2 reset (wrappers.py:224-235)."""
+    _need_cuda(frames, stack_in)
+    e = stack_in.shape[0]
+    assert frames.dtype == torch.uint8 and frames.is_contiguous() and frames.numel() == e * 84 * 84
+    assert stack_in.dtype == torch.uint8 and stack_in.is_contiguous() and tuple(stack_in.shape[1:]) == (84, 84, 4)
+    assert mode is None or (mode.dtype == torch.uint8 and mode.is_contiguous() and mode.numel() == e)
+    if out is None:
+        out = torch.empty_like(stack_in)
+    _lib.check(_lib.load().acx_framestack_push_u8(_ptr(frames), _ptr(mode), _ptr(stack_in), _ptr(out), e, _stream()))
+    return out
+
+
 def returns_adv(rewards, terminals, values, bootstrap_values, gamma):
     """K-RET.  rewards f32 [E,T], terminals uint8/bool [E,T], values f32 [E,T], bootstrap f32 [E]."""
     _need_cuda(rewards, terminals, values, bootstrap_values)

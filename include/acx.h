@@ -58,6 +58,15 @@ int acx_preprocess_stack_u8(const uint8_t* d_raw_a, const uint8_t* d_raw_b, cons
 int acx_preprocess_reset_u8(const uint8_t* d_raw, uint8_t* d_stack_out, size_t out_env_stride,
                             int num_envs, void* stream);
 
+/* The stages of K-PRE on their own, for the per-environment wrapper classes of the reference's API:
+ * acx_frame_max_u8        byte-wise max of two frames of nbytes each (AtariFrameskipWrapper.step, wrappers.py:64-65);
+ * acx_framestack_push_u8  FrameStackWrapper.step / reset on preprocessed frames (wrappers.py:224-235): d_frames uint8
+ *                         [E,84,84], d_mode uint8 [E] (NULL = all 0): 0 push, 1 push after a terminal step (older frames
+ *                         zeroed), 2 reset (4 copies); stacks uint8 [E,84,84,4], in place allowed. */
+int acx_frame_max_u8(const uint8_t* d_a, const uint8_t* d_b, uint8_t* d_out, size_t nbytes, void* stream);
+int acx_framestack_push_u8(const uint8_t* d_frames, const uint8_t* d_mode, const uint8_t* d_stack_in, uint8_t* d_stack_out,
+                           int num_envs, void* stream);
+
 /* ---- K-RET: n-step returns and advantages --------------------------------------------------- */
 /* Replaces objectives._discount/_discount_bootstrap + targets/advantage (objectives.py:123-130,
  * 178-214).  rewards f32 [E,T], terminals u8 [E,T], values f32 [E,T], bootstrap f32 [E]

@@ -128,3 +128,56 @@ def test_idempotent_channel_shift_property_large():
     for _ in range(4):
         stacks = ops.preprocess_stack(a, a, stacks)
     assert torch.equal(stacks, ops.preprocess_reset(a))
+
+
+def test_standalone_frame_max_and_framestack_wrappers_match_the_reference_lines():
+    """The per-environment wrapper classes of the reference's API (wrappers.py:36-70, 201-235) on the stand-alone C-ABI
+    entry points, against the reference's NumPy lines restated by the oracle."""
+    from actorcritic_b200.envs.atari import wrappers as W
+    ops = _ops()
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 256, (3, 210, 160, 3), dtype=np.uint8)
+    b = rng.integers(0, 256, (3, 210, 160, 3), dtype=np.uint8)
+    assert np.array_equal(ops.frame_max(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()).cpu().numpy(), np.maximum(a, b))
+    odd = rng.integers(0, 256, 1003, dtype=np.uint8)            # ragged tail (not a multiple of 16 bytes)
+    odd2 = rng.integers(0, 256, 1003, dtype=np.uint8)
+    assert np.array_equal(ops.frame_max(torch.from_numpy(odd).cuda(), torch.from_numpy(odd2).cuda()).cpu().numpy(),
+                          np.maximum(odd, odd2))
+
+    class Scripted:
+        def __init__(self, frames, terminals):
+            self.frames, self.terminals, self.i = frames, terminals, 0
+            self.action_space = None
+
+        def reset(self):
+            self.i += 1
+            return self.frames[self.i - 1]
+
+        def step(self, action):
+            self.i += 1
+            return self.frames[self.i - 1], 1.0, self.terminals[self.i - 1], {"i": self.i}
+
+    # AtariFrameskipWrapper: max of the last two of 4 frames; a terminal first sub-step returns that single frame
+    raw = [rng.integers(0, 256, (210, 160, 3), dtype=np.uint8) for _ in range(12)]
+    term = [False] * 12
+    term[6] = True                                               # third sub-step of the second window
+    term[7] = True                                               # first sub-step of the third window
+    env = W.AtariFrameskipWrapper(Scripted(raw, term), 4)
+    assert np.array_equal(env.reset(), raw[0])
+    obs, rew, done, _ = env.step(0)
+    assert np.array_equal(obs, np.maximum(raw[3], raw[4])) and rew == 4.0 and not done
+    obs, rew, done, _ = env.step(0)
+    assert np.array_equal(obs, np.maximum(raw[5], raw[6])) and rew == 2.0 and done
+    obs, rew, done, _ = env.step(0)
+    assert np.array_equal(obs, raw[7]) and rew == 1.0 and done
+
+    # FrameStackWrapper: reset = 4 copies, step = roll / zero on terminal / newest last
+    gray = [rng.integers(0, 256, (84, 84, 1), dtype=np.uint8) for _ in range(6)]
+    fs_term = [False, False, False, True, False, False]
+    fs = W.FrameStackWrapper(Scripted(gray, fs_term), 4)
+    ref = P.FrameStack(4)
+    assert np.array_equal(fs.reset(), ref.reset(gray[0]))
+    for i in range(1, 6):
+        obs, _, done, _ = fs.step(0)
+        assert np.array_equal(obs, ref.step(gray[i], fs_term[i])), i
+        assert done == fs_term[i]
