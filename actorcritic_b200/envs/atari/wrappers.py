@@ -74,18 +74,18 @@ class AtariFrameskipWrapper:
         self.observation_space = getattr(env, "observation_space", None)
 
     def step(self, action):
-        frames, total_reward, terminal, info = [], 0.0, False, None
+        older = newest = None            # only the last two frames of the window matter
+        reward_sum, done, info = 0.0, False, None
         for _ in range(self._frameskip):
-            next_frame, reward, terminal, info = self.env.step(action)
-            frames.append(next_frame)
-            total_reward += reward
-            if terminal:
+            frame, reward, done, info = self.env.step(action)
+            older, newest = newest, frame
+            reward_sum += reward
+            if done:
                 break
-        if len(frames) >= 2:
-            a = torch.from_numpy(np.ascontiguousarray(frames[-2], dtype=np.uint8)).cuda()
-            b = torch.from_numpy(np.ascontiguousarray(frames[-1], dtype=np.uint8)).cuda()
-            return ops.frame_max(a, b).cpu().numpy(), total_reward, terminal, info
-        return frames[0], total_reward, terminal, info
+        if older is None:                # the first sub-step ended the episode: a one-frame window (wrappers.py:66-67)
+            return newest, reward_sum, done, info
+        pair = torch.from_numpy(np.ascontiguousarray(np.stack([older, newest]), dtype=np.uint8)).cuda()
+        return ops.frame_max(pair[0], pair[1]).cpu().numpy(), reward_sum, done, info
 
     def reset(self, **kwargs):
         return self.env.reset(**kwargs)
