@@ -399,6 +399,9 @@ def run_native(args, rank, world, local_rank):
             gbs = pe * 258048 / (ms * 1e-3) / 1e9
             pre["envs_%d" % pe] = {"ms": ms, "env_steps_per_sec": pe / (ms * 1e-3), "GB/s": gbs, "frac_hbm": gbs / peaks["hbm"]}
             del ra, rb, stk, out
+        pre["note"] = ("258048 algorithmic bytes per env-step (ncu: dram__bytes = algorithmic, profiles/r1_prof_kpre_raw.txt); frac_hbm is "
+                       "against the measured read+write COPY bandwidth of MEASURED_PEAKS.json - K-PRE is 89 % reads, which is why it can "
+                       "reach ~1.0 of that figure (ncu: 80 % of the DRAM peak); 64 envs (16.5 MB) fit L2 and are launch bound")
 
     # rollout side of the path (agents.py:202-216): T x (K-PRE on E raw frame pairs + forward on E rows + sample)
     from actorcritic_b200.envs.atari.device_env import DeviceAtariMultiEnv
