@@ -115,3 +115,43 @@ class FrameStackWrapper:
 
     def reset(self, **kwargs):
         return self._push(self.env.reset(**kwargs), 2)                                 # wrappers.py:234
+
+
+class EpisodeInfoWrapper:
+    """wrappers.py:263-323: accumulates the rewards of an episode and, on its terminal step, reports them as
+    info['episode']['total_reward'] (host-side bookkeeping; stacks on any environment, also on those a RawFrameMultiEnv
+    hosts)."""
+
+    def __init__(self, env):
+        self.env = env
+        self.action_space = getattr(env, "action_space", None)
+        self.observation_space = getattr(env, "observation_space", None)
+        self.total_reward = 0.0
+
+    def step(self, action):
+        observation, reward, terminal, info = self.env.step(action)
+        self.total_reward += reward
+        if terminal:
+            info = dict(info) if info is not None else {}
+            info["episode"] = {"total_reward": self.total_reward}
+            self.total_reward = 0.0
+        return observation, reward, terminal, info
+
+    def reset(self, **kwargs):
+        self.total_reward = 0.0
+        return self.env.reset(**kwargs)
+
+    @staticmethod
+    def get_episode_rewards_from_info_batch(infos):
+        """Batch-major [environment][step] infos (as `Agent.interact` returns them) -> float32 array of the same shape
+        with the episode reward where an episode ended and NaN elsewhere (wrappers.py:296-323); the caller takes
+        `np.nanmean` of it for the 'episode_reward' summary (a2c_acktr.py:112-114)."""
+        environments = len(infos)
+        steps = len(infos[0]) if environments else 0
+        rewards = np.full((environments, steps), np.nan, np.float32)
+        for e, row in enumerate(infos):
+            for t, info in enumerate(row):
+                episode = info.get("episode") if info else None
+                if episode is not None:
+                    rewards[e, t] = episode["total_reward"]
+        return rewards

@@ -28,7 +28,7 @@ class Placeholder:
 class Fetch:
     """Something `Session.run` can evaluate.  kind: one of
     policy_loss baseline_loss mean_entropy loss clip_coeff learning_rate global_step optimize
-    sample mode logits log_prob entropy value bootstrap_values"""
+    sample mode logits log_prob entropy value bootstrap_values summary no_op"""
 
     def __init__(self, kind, owner, name=None):
         self.kind, self.owner, self.name = kind, owner, name or kind
@@ -91,6 +91,24 @@ class Session:
         return out[0] if single else out
 
     def _evaluate(self, flist, feed):
+        # summary ops (actorcritic_b200.summary) are evaluated from the same step as the other fetches: their sources are
+        # added to the work list, the serialized Summary is assembled at the end; no_op fetches yield None
+        requested = flist
+        summaries = [f for f in requested if f.kind == "summary"]
+        flist = [f for f in requested if f.kind not in ("summary", "no_op")]
+        for sm in summaries:
+            for src in sm.sources():
+                if all(src is not g for g in flist):
+                    flist.append(src)
+        results = self._evaluate_plain(flist, feed) if flist else {}
+        for sm in summaries:
+            results[id(sm)] = sm.build(results, feed)
+        for f in requested:
+            if f.kind == "no_op":
+                results[id(f)] = None
+        return [results[id(f)] for f in requested]
+
+    def _evaluate_plain(self, flist, feed):
         kinds = {f.kind for f in flist}
         results = {}
         train_kinds = {"optimize", "policy_loss", "baseline_loss", "mean_entropy", "loss", "clip_coeff", "learning_rate"}
@@ -139,4 +157,4 @@ class Session:
                     results[id(f)] = model._bootstrap_only(self, feed)
                 else:
                     raise NotImplementedError("fetch %r is not available outside the learner hot path" % f)
-        return [results[id(f)] for f in flist]
+        return results

@@ -117,3 +117,51 @@ def test_device_resident_rollout_feeds_the_train_step():
                                          model.actions_placeholder: act, model.rewards_placeholder: rew,
                                          model.terminals_placeholder: term})
         assert np.isfinite(loss) and global_step.eval() == 2
+
+
+def test_summaries_written_like_the_reference_example(tmp_path):
+    """a2c_acktr.py:80-133: scalars registered under name scopes, merged, fetched WITH the train step, written to an
+    event file; the logged values are the step's own losses."""
+    from actorcritic_b200 import summary
+    from actorcritic_b200.envs.atari.wrappers import EpisodeInfoWrapper
+    summary.reset_default_collection()
+    ac, model, objective, global_step, optimize_op = _build(True, 4, 5)
+    episode_reward_placeholder = summary.placeholder(np.float32, [])
+    with summary.name_scope("model"):
+        summary.scalar("policy_loss", objective.policy_loss)
+        summary.scalar("baseline_loss", objective.baseline_loss)
+        summary.scalar("policy_entropy", objective.mean_entropy)
+    with summary.name_scope("environment"):
+        summary.scalar("episode_reward", episode_reward_placeholder)
+    summary_op = summary.merge_all()
+    writer = summary.FileWriter(str(tmp_path), None)
+    logged = []
+    with ac.Session() as session:
+        for u in range(3):
+            batch = synth.rollout(900 + u, 4, 5, 4, obs_kind="sparse")
+            infos = [[{"episode": {"total_reward": 7.0 + u}} if (e, t) == (1, 2) else {} for t in range(5)] for e in range(4)]
+            rewards = EpisodeInfoWrapper.get_episode_rewards_from_info_batch(infos)
+            mean_reward = np.nan if np.all(np.isnan(rewards)) else np.nanmean(rewards)
+            summ, step, _, pl, bl, ent = session.run(
+                [summary_op, global_step, optimize_op, objective.policy_loss, objective.baseline_loss, objective.mean_entropy],
+                feed_dict={model.observations_placeholder: batch["observations"],
+                           model.bootstrap_observations_placeholder: batch["bootstrap_observations"],
+                           model.actions_placeholder: batch["actions"], model.rewards_placeholder: batch["rewards"],
+                           model.terminals_placeholder: batch["terminals"], episode_reward_placeholder: mean_reward})
+            writer.add_summary(summ, step)
+            logged.append((int(step), float(pl), float(bl), float(ent), float(mean_reward)))
+        nothing, _ = session.run([summary.no_op(), optimize_op],
+                                 feed_dict={model.observations_placeholder: batch["observations"],
+                                            model.bootstrap_observations_placeholder: batch["bootstrap_observations"],
+                                            model.actions_placeholder: batch["actions"],
+                                            model.rewards_placeholder: batch["rewards"],
+                                            model.terminals_placeholder: batch["terminals"]})
+        assert nothing is None
+    writer.close()
+    events = [e for e in summary.read_events(writer.path) if e["scalars"]]
+    assert len(events) == 3
+    for ev, (step, pl, bl, ent, rew) in zip(events, logged):
+        assert ev["step"] == step
+        assert ev["scalars"] == {"model/policy_loss": np.float32(pl), "model/baseline_loss": np.float32(bl),
+                                 "model/policy_entropy": np.float32(ent), "environment/episode_reward": np.float32(rew)}
+    summary.reset_default_collection()
