@@ -1087,6 +1087,10 @@ static void init_dims(acx_learner* l, const acx_learner_config_t* cfg) {
   // themselves accumulated at lvl_factor = 3 pairs and held to 1e-3, so 3 pairs are enough there (measured G-factor error
   // in profiles/r1_precision.md); the true-gradient rows keep lvl_bwd.  ACX_FISHER_LEVEL=2 restores 6 pairs everywhere.
   l->lvl_fisher = l->lvl_bwd < 1 ? l->lvl_bwd : 1;
+  if (const char* e = getenv("ACX_PRECON_LEVEL")) {   // triage: plane-pair level of the fc4 preconditioning GEMMs
+    const int v = atoi(e);
+    if (v >= 0 && v <= 2) l->lvl_precon = v;
+  }
   if (const char* e = getenv("ACX_FISHER_LEVEL")) {
     const int v = atoi(e);
     if (v >= 0 && v <= l->lvl_bwd) l->lvl_fisher = v;
