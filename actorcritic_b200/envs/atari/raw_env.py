@@ -32,6 +32,10 @@ class RawFrameMultiEnv:
     def __init__(self, envs, frameskip=4, device=None, num_threads=None):
         if len(envs) == 0:
             raise ValueError("at least one environment is required")
+        if not torch.cuda.is_available():
+            from ... import _lib
+            raise _lib.AcxError("RawFrameMultiEnv needs a CUDA device (the frame work runs in libacx's K-PRE kernel); there is "
+                                "no CPU fallback")
         if frameskip < 1:
             raise ValueError("frameskip must be >= 1")
         self._envs = list(envs)
@@ -111,7 +115,9 @@ class RawFrameMultiEnv:
             raise ValueError("expected %d actions, got %d" % (self.num_envs, len(actions)))
         self._wait_staging_free()
         list(self._executor.map(self._step_one, range(self.num_envs), actions))
-        self._d_frames.copy_(self._h_frames, non_blocking=True)
+        # the reset frames (slot 2) only travel when some environment was reset before this step
+        slots = 3 if self._np_flags[1].any() else 2
+        self._d_frames[:slots].copy_(self._h_frames[:slots], non_blocking=True)
         self._d_flags.copy_(self._h_flags, non_blocking=True)
         self._d_rewards.copy_(self._h_rewards, non_blocking=True)
         self._staged.record()

@@ -104,6 +104,9 @@ def test_no_cuda_means_no_session_and_no_engine():
         ac.Session()
     with pytest.raises(_lib.AcxError):
         eng.Engine(eng.EngineConfig(num_envs=2, num_steps=2))
+    from actorcritic_b200.envs.atari.raw_env import RawFrameMultiEnv
+    with pytest.raises(_lib.AcxError):
+        RawFrameMultiEnv([object()])
 
 
 def test_transpose_list_docstring_example():
