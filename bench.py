@@ -423,6 +423,42 @@ def run_native(args, rank, world, local_rank):
 
     total_envs = envs * world
     ms_step = ms_dev / args.steps
+    # the other long launch of the update: the conv2 input-factor SYRK A2 = P2^T P2 / rows (gemm_tc_kernel<1>, MN-major
+    # operands, upper 128-tiles only, split-K, 3 plane pairs on 2 planes), timed like the conv1 SYRK on operands of the
+    # update's shape.  Informational (`roofline.factor_syrk`): a failure here must not cost the bench line.
+    factor_syrk = None
+    try:
+        rows2 = n * 81
+        gen = torch.Generator(device=dev).manual_seed(11)
+        x2 = ops.split_planes(torch.rand((rows2, 512), device=dev, generator=gen), 2)
+        torch.cuda.synchronize()
+        lib.acx_gemm_enable_timing(1)
+        d2 = []
+        with torch.cuda.stream(e.stream):
+            for i in range(9):
+                ops.gemm(x2, x2, 512, 512, rows2, trans=True, symmetric=True, pairs=ops.PAIRS[3], alpha=1.0 / rows2)
+                ms = ctypes.c_float(0)
+                _lib.check(lib.acx_gemm_last_ms(ctypes.byref(ms)))
+                if i >= 3:
+                    d2.append(ms.value)
+        lib.acx_gemm_enable_timing(0)
+        ms2 = float(np.mean(d2))
+        alg = float(rows2) * 512 * 513                       # rows * d * (d + 1): the symmetric half
+        issued = 3.0 * 10 * 2.0 * rows2 * 128 * 128           # 3 plane pairs x 10 upper 128-tiles of the 4 x 4 tile grid
+        factor_syrk = {"kernel": "gemm_tc_kernel<1>: conv2 input factor A2 = P2^T P2 (512 x 512, K = %d patch rows, 3 plane pairs, "
+                                 "upper tiles, split-K; the split-K finalize is a separate launch)" % rows2,
+                       "bound": "tensor", "launch_ms": ms2, "algorithmic_gflop_per_launch": alg / 1e9,
+                       "achieved": alg / (ms2 * 1e-3) / 1e12, "peak": peaks["tensor_burst"], "unit": "TFLOP/s",
+                       "frac": alg / (ms2 * 1e-3) / 1e12 / peaks["tensor_burst"],
+                       "issued_gflop_per_launch": issued / 1e9, "issued_frac": issued / (ms2 * 1e-3) / 1e12 / peaks["tensor_burst"]}
+        del x2
+    except Exception as exc:  # noqa: BLE001
+        factor_syrk = {"error": repr(exc)}
+        try:
+            lib.acx_gemm_enable_timing(0)
+        except Exception:  # noqa: BLE001
+            pass
+
     value = total_envs * t_count / (ms_step * 1e-3)
     e2e_value = total_envs * t_count / (ms_e2e / args.steps * 1e-3)
     # `roofline` = the dominant (longest) launch of the update; `hbm_kernel` inside it = the largest HBM-bound launch
@@ -441,7 +477,7 @@ def run_native(args, rank, world, local_rank):
     else:
         roofline = {"bound": "tensor",
                      "kernel": "conv_tc_kernel (conv.cu): %s input gradient in gather form, %d samples (true + Fisher rows), "
-                               "%d bf16 plane pairs into one fp32 TMEM accumulator - the longest launch of the update" % (dom, s2, npairs),
+                               "%d bf16 plane pairs into one fp32 TMEM accumulator - with the conv2 input-factor SYRK (`factor_syrk`) the longest launch of the update" % (dom, s2, npairs),
                      "achieved": dg[dom]["flops"] / (dg[dom]["ms"] * 1e-3) / 1e12, "peak": peaks["tensor_burst"], "unit": "TFLOP/s",
                      "frac": dg[dom]["flops"] / (dg[dom]["ms"] * 1e-3) / 1e12 / peaks["tensor_burst"],
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/r1_prof_conv_dgrad2_raw.txt)
@@ -457,6 +493,7 @@ def run_native(args, rank, world, local_rank):
                                                   "issued_gflop": v["issued"] / 1e9} for kk, v in dg.items()},
                      "peak_source": peaks["source"] + ", dense bf16 (cuBLAS) burst",
                      "hbm_kernel": hbm_kernel,
+                     "factor_syrk": factor_syrk,
                      "stage_ms": stage_ms,
                      "stage_note": "stage times are taken with the lanes serialised (profiling mode); factor statistics are "
                                    "issued from inside the forward / backward stages",
