@@ -141,3 +141,34 @@ def test_episode_info_wrapper_and_reward_aggregation():
     assert np.isnan(r[0, 0]) and np.all(np.isnan(r[1]))
     assert np.nanmean(r) == 10.5                                   # a2c_acktr.py:112-114
     assert np.all(np.isnan(EpisodeInfoWrapper.get_episode_rewards_from_info_batch([[{}]])))
+
+
+def test_session_expands_summary_sources_and_no_op_without_a_device(monkeypatch):
+    """Host logic of Session.run for summary ops: the summary's sources join the work list once, the serialized Summary is
+    assembled from the same evaluation, no_op yields None (a2c_acktr.py:117-126 fetches [summary_op, global_step, op])."""
+    from actorcritic_b200.session import Session
+    summary.reset_default_collection()
+    owner = object()
+    policy_loss, entropy, step = Fetch("policy_loss", owner), Fetch("mean_entropy", owner), Fetch("global_step", None)
+    reward = summary.placeholder(np.float32, [])
+    with summary.name_scope("model"):
+        summary.scalar("policy_loss", policy_loss)
+        summary.scalar("policy_entropy", entropy)
+    with summary.name_scope("environment"):
+        summary.scalar("episode_reward", reward)
+    op = summary.merge_all()
+    seen = []
+
+    def fake_plain(self, flist, feed):
+        seen.append([f.kind for f in flist])
+        return {id(f): {"policy_loss": 0.25, "mean_entropy": 1.5, "global_step": 42}[f.kind] for f in flist}
+
+    monkeypatch.setattr(Session, "_evaluate_plain", fake_plain)
+    session = Session.__new__(Session)                       # no CUDA device needed for the host logic
+    out = session.run([op, step, policy_loss, summary.no_op()], feed_dict={reward: 3.0})
+    assert seen == [["global_step", "policy_loss", "mean_entropy"]]          # policy_loss evaluated once, entropy added
+    assert out[1] == 42 and out[2] == 0.25 and out[3] is None
+    ev = summary._decode_event(summary.encode_event(0.0, step=out[1], summary=out[0]))
+    assert ev["scalars"] == {"model/policy_loss": 0.25, "model/policy_entropy": 1.5, "environment/episode_reward": 3.0}
+    assert session.run(summary.no_op()) is None and seen == [["global_step", "policy_loss", "mean_entropy"]]
+    summary.reset_default_collection()
