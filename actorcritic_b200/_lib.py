@@ -56,7 +56,8 @@ class LearnerConfig(ctypes.Structure):
                 ("rms_decay", ctypes.c_float), ("rms_epsilon", ctypes.c_float),
                 ("num_locations_mode", ctypes.c_int), ("world_size", ctypes.c_int), ("gemm_impl", ctypes.c_int),
                 ("precision", ctypes.c_int), ("use_graphs", ctypes.c_int), ("conv_impl", ctypes.c_int), ("num_lanes", ctypes.c_int),
-                ("seed", ctypes.c_uint64)]
+                ("seed", ctypes.c_uint64),
+                ("cov_init_identity", ctypes.c_int), ("no_zero_debias", ctypes.c_int), ("inv_init_identity", ctypes.c_int)]
 
 
 # every symbol include/acx.h declares: name -> (restype, argtypes)

@@ -899,6 +899,9 @@ static int precondition(acx_learner* l, cudaStream_t st) {
   return 0;
 }
 
+// the 1 / (1 - decay^n) factor belongs to zero-initialised running sums
+static bool zero_debias_on(const acx_learner_config_t& c) { return !c.no_zero_debias && !c.cov_init_identity; }
+
 // what one phase-2 call does, decided on the host from the schedule counters (kfac_utils.py:38-53)
 struct Plan2 {
   bool a2c, cold, invert, kfac_apply, refresh;
@@ -950,7 +953,7 @@ static int issue_phase2(acx_learner* l, const Plan2& p, cudaStream_t st) {
   // one launch for the whole schedule transition (kfac_utils.py:38-53): lr from the step the update starts with, then
   // global_step += (cold ? 2 : 1) [A2C: 1], covariance counter += (cold ? 0 : 1)
   ACX_TRY(sched_step(l->sched, c.lr_start, c.lr_end, c.lr_decay_steps, l->scalars + 7, p.a2c ? 1 : (p.cold ? 2 : 1),
-                     (p.a2c || p.cold) ? 0 : 1, c.cov_ema_decay, 1, st));
+                     (p.a2c || p.cold) ? 0 : 1, c.cov_ema_decay, zero_debias_on(c) ? 1 : 0, st));
   if (p.a2c) {   // ClipGlobalNorm(RMSProp)   a2c_acktr.py:250-251
     ACX_TRY(dot_partial(l->grads, l->grads, P, l->dot_partials, kDotPartials, st));
     ACX_TRY(rmsprop_clip_step(l->params, l->accum, l->grads, P, l->dot_partials, kDotPartials, l->sched, c.rms_decay,
@@ -1167,6 +1170,25 @@ acx_learner_t* acx_learner_create(const acx_learner_config_t* cfg, void* d_arena
   }
   Sched s0 = {0ull, 0ull, cfg->lr_start, 1.0f};
   cudaMemcpy(l->sched, &s0, sizeof(s0), cudaMemcpyHostToDevice);
+  if (cfg->acktr && (cfg->cov_init_identity || cfg->inv_init_identity)) {   // SURVEY A.7-U3 (the arena is zero so far)
+    std::vector<float> eye;
+    auto put_eye = [&](float* dst, int d) {
+      eye.assign((size_t)d * d, 0.0f);
+      for (int i = 0; i < d; ++i) eye[(size_t)i * d + i] = 1.0f;
+      cudaMemcpy(dst, eye.data(), eye.size() * sizeof(float), cudaMemcpyHostToDevice);
+    };
+    if (cfg->cov_init_identity) {
+      for (int i = 0; i < 5; ++i) put_eye(l->sums + l->aoff[i], l->adim[i]);
+      for (int i = 0; i < 6; ++i) put_eye(l->sums + l->goff[i], l->L[i].C);
+    }
+    if (cfg->inv_init_identity) {
+      for (int i = 0; i < 6; ++i) {
+        put_eye(l->inv + l->ainv_off[i], l->L[i].K + 1);
+        put_eye(l->inv + l->ginv_off[i], l->L[i].C);
+      }
+      l->inverses_valid = true;   // the K-FAC apply is a real step from the first update on
+    }
+  }
   const float* ap[6];
   const float* gp[6];
   int ad[6], gd[6];
@@ -1190,6 +1212,12 @@ acx_learner_t* acx_learner_create(const acx_learner_config_t* cfg, void* d_arena
     acx::set_error(std::string("acx_learner_create: cudaMemcpy: ") + cudaGetErrorString(e));
     delete l;
     return nullptr;
+  }
+  if (cfg->acktr && cfg->inv_init_identity) {   // bf16 operand planes of the identity inverses
+    if (acx_learner_refresh_weights(l, nullptr) != 0 || cudaDeviceSynchronize() != cudaSuccess) {
+      delete l;
+      return nullptr;
+    }
   }
   return l;
 }
@@ -1358,7 +1386,8 @@ int acx_learner_set_state(acx_learner_t* l, int64_t global_step, int64_t num_cov
   s.gs = (unsigned long long)global_step;
   s.ncov = (unsigned long long)num_cov_updates;
   s.lr = l->cfg.lr_start;
-  s.debias = num_cov_updates > 0 ? (float)(1.0 / (1.0 - pow((double)l->cfg.cov_ema_decay, (double)num_cov_updates))) : 1.0f;
+  s.debias = (num_cov_updates > 0 && zero_debias_on(l->cfg))
+                 ? (float)(1.0 / (1.0 - pow((double)l->cfg.cov_ema_decay, (double)num_cov_updates))) : 1.0f;
   ACX_CUDA(cudaMemcpyAsync(l->sched, &s, sizeof(s), cudaMemcpyHostToDevice, st));
   ACX_CUDA(cudaStreamSynchronize(st));
   return 0;

@@ -58,6 +58,9 @@ class EngineConfig:
     conv_impl: int = 0                      # 0 = gather-form conv2/conv3 input gradient (acx_conv), 1 = GEMM + col2im
     num_lanes: int = 0                      # 0 = default (3 concurrent lanes inside an update), 1 = serial
     seed: int = 0
+    cov_init: str = "zero"                  # "zero" (kfac 0.1.x) | "identity" (older tf.contrib.kfac)
+    zero_debias: bool = True                # U3
+    inv_init: str = "zero"                  # U3: "zero" | "identity"
 
     @staticmethod
     def a2c(num_envs=16, num_steps=5, num_actions=4, **kw):
@@ -87,6 +90,12 @@ class EngineConfig:
         c.use_graphs = int(bool(self.use_graphs))
         c.num_lanes = int(self.num_lanes)
         c.conv_impl = int(self.conv_impl)
+        for name in ("cov_init", "inv_init"):
+            if getattr(self, name) not in ("zero", "identity"):
+                raise ValueError("%s must be 'zero' or 'identity'" % name)
+        c.cov_init_identity = int(self.cov_init == "identity")
+        c.no_zero_debias = int(not self.zero_debias)
+        c.inv_init_identity = int(self.inv_init == "identity")
         return c
 
 

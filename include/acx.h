@@ -198,6 +198,13 @@ typedef struct {
                                   wgrad + output factors, forked and joined with events on library-owned streams, so the
                                   caller still orders everything through `stream`); 1 = strictly serial on `stream` */
   uint64_t seed;               /* Philox seed for on-device Fisher sampling */
+  /* initialisation conventions of kfac that the reference does not pin (all 0 = kfac 0.1.x as SURVEY A.5
+   * records it: zero-initialised running covariances with zero-debias, zero-initialised inverses) */
+  int cov_init_identity;       /* 1 = running covariance sums start as identity matrices (older tf.contrib.kfac); implies
+                                  no zero-debias */
+  int no_zero_debias;          /* 1 = the running sums are used as they are (no 1 / (1 - decay^n) factor) */
+  int inv_init_identity;       /* 1 = stored inverses start as identity: the always-run K-FAC apply (kfac_utils.py:52-53)
+                                  takes real steps U = V / T~ before the first refresh instead of being a no-op */
 } acx_learner_config_t;
 
 typedef struct acx_learner acx_learner_t;

@@ -43,10 +43,25 @@ class KfacConfig:
     num_locations_mode: str = "true"           # or "input_div_stride" (U1)
     zero_debias: bool = True                   # U3
     cov_init: str = "zero"                     # U3 ("zero" | "identity")
+    inv_init: str = "zero"                     # U3 ("zero" | "identity"): initial value of the stored inverses
 
     def locations(self, layer):
         table = TRUE_LOCATIONS if self.num_locations_mode == "true" else INPUT_DIV_STRIDE_LOCATIONS
         return table[layer]
+
+
+def schedule_events(global_step, num_cold_updates, invert_every):
+    """What ONE call of ColdStartPeriodicInvUpdateKfacOpt.apply_gradients does when it starts at `global_step`, as coded
+    (kfac_utils.py:38-53; pinned by tests/golden/schedule.npz, recorded from the reference class itself):
+      :41-44  global_step < num_cold_updates ? cold optimizer (increments global_step) : covariance updates
+      :47-50  then, reading the CURRENT global_step: > num_cold_updates and (gs - num_cold_updates) % invert_every == 0
+              -> inverse updates
+      :52-53  then always KfacOptimizer.apply_gradients (increments global_step).
+    Returns dict(cold, cov, inv, kfac_apply, gs_after)."""
+    cold = global_step < num_cold_updates
+    gs1 = global_step + (1 if cold else 0)
+    inv = gs1 > num_cold_updates and (gs1 - num_cold_updates) % invert_every == 0
+    return dict(cold=cold, cov=not cold, inv=inv, kfac_apply=True, gs_after=gs1 + 1)
 
 
 def linear_decay(start, end, step, total_steps):
@@ -100,8 +115,11 @@ class KfacState:
         self.sum_a = {k: init(d) for k, d in dims_a.items()}
         self.sum_g = {k: init(d) for k, d in dims_g.items()}
         self.num_cov_updates = 0
-        self.inv_a = {name: torch.zeros((dims_a[A_FACTOR_OF[name]],) * 2, dtype=dtype) for name in net.LAYERS}
-        self.inv_g = {name: torch.zeros((dims_g[name],) * 2, dtype=dtype) for name in net.LAYERS}
+
+        def init_inv(d):   # kfac 0.1.x: zeros (the K-FAC step is a no-op until the first refresh); older contrib.kfac: identity
+            return torch.eye(d, dtype=dtype) if cfg.inv_init == "identity" else torch.zeros((d, d), dtype=dtype)
+        self.inv_a = {name: init_inv(dims_a[A_FACTOR_OF[name]]) for name in net.LAYERS}
+        self.inv_g = {name: init_inv(dims_g[name]) for name in net.LAYERS}
         self.velocity = {name: torch.zeros_like(net.join_vmat(name, params)) for name in net.LAYERS}
 
     def update_covs(self, new_a, new_g):

@@ -87,8 +87,8 @@ class OracleLearner:
         if not self.acktr:
             return self._update_a2c(batch, masks)
         cfg = self.cfg
-        gs0 = self.global_step
-        cold = gs0 < cfg.num_cold_updates
+        plan = K.schedule_events(self.global_step, cfg.num_cold_updates, cfg.invert_every)
+        cold = plan["cold"]
         info = self.compute(batch, y_hat, eps, need_fisher=not cold, masks=masks)
         grads = info["grads"]
         lr = self.learning_rate()
@@ -103,13 +103,13 @@ class OracleLearner:
             info["grad_norm"] = norm
         else:                                                        # :44
             self.kfac.update_covs(info["new_a"], info["new_g"])
-        gs1 = self.global_step
-        if gs1 > cfg.num_cold_updates and (gs1 - cfg.num_cold_updates) % cfg.invert_every == 0:   # :47-50
+        if plan["inv"]:                                              # :47-50
             self.kfac.update_inverses()
             info["inverted"] = True
         # :52-53 - always.  Gradients were computed before the cold step (same session.run).
         coeff, s, precon = self.kfac.step(self.params, grads, lr)
         self.global_step += 1
+        assert self.global_step == plan["gs_after"]
         info.update(clip_coeff=coeff, fisher_norm=s, precon=precon, lr=lr)
         return info
 

@@ -10,6 +10,9 @@ What each file pins:
   framestack.npz  FrameStackWrapper (wrappers.py:201-235) inside MultiEnv's _AutoResetWrapper
                   (multi_env.py:121-137) driven through a scripted terminal sequence
   returns.npz     objectives._discount / _discount_bootstrap (objectives.py:178-214)
+  schedule.npz    ColdStartPeriodicInvUpdateKfacOpt.apply_gradients (kfac_utils.py:38-53), the reference's own class
+                  on a recording kfac.KfacOptimizer skeleton: which of {cold step, covariance update, inverse
+                  update, K-FAC apply} each update runs and how global_step moves, for three (num_cold, every) pairs
   network.npz     AtariModel (envs/atari/model.py) + A2CObjective (objectives.py:100-154) +
                   the shared loss of optimize_shared (:78): logits, values, bootstrap values, the three
                   loss scalars and d(shared loss)/d(all 12 variables) by autograd through the
@@ -222,6 +225,34 @@ def gen_network():
     np.savez_compressed(os.path.join(HERE, "network.npz"), **out)
 
 
+def gen_schedule():
+    """Runs the UNMODIFIED kfac_utils.ColdStartPeriodicInvUpdateKfacOpt.apply_gradients once per update, eagerly (the
+    shim's tf.cond / control_dependencies execute in program order; predicates read the current global_step), and records
+    per update: global_step before / after and whether the cold optimizer, the covariance thunks, the inverse thunks and
+    the base KfacOptimizer.apply_gradients ran.  Rows: [gs_before, cold, cov, inv, kfac_apply, gs_after]."""
+    import actorcritic.kfac_utils as ref_kfac_utils
+    out = {}
+    for tag, (num_cold, every, updates) in {"reference": (30, 10, 60), "short": (4, 2, 16), "odd": (5, 3, 24)}.items():
+        gs = ref_shims.StepVariable(0)
+        opt = ref_kfac_utils.ColdStartPeriodicInvUpdateKfacOpt(
+            num_cold_updates=num_cold, cold_optimizer=ref_shims.RecordingOptimizer("cold"), invert_every=every,
+            learning_rate=0.25, cov_ema_decay=0.99, damping=0.01, layer_collection=None, momentum=0.9, norm_constraint=1e-4)
+        rows = []
+        for _ in range(updates):
+            del ref_shims.EVENTS[:]
+            before = gs.value
+            opt.apply_gradients([], global_step=gs)
+            names = [e[0] for e in ref_shims.EVENTS]
+            # order as coded: (cold | cov) -> [inv] -> kfac_apply
+            assert names[-1] == "kfac_apply" and names[0] in ("cold", "cov"), names
+            assert names == [n for n in ("cold", "cov", "inv", "kfac_apply") if n in names], names
+            rows.append([before, int("cold" in names), int("cov" in names), int("inv" in names),
+                         int("kfac_apply" in names), gs.value])
+        out[tag] = np.array(rows, np.int64)
+        out[tag + "_config"] = np.array([num_cold, every], np.int64)
+    np.savez_compressed(os.path.join(HERE, "schedule.npz"), **out)
+
+
 def gen_transpose():
     v = [[1, 2, 3, 4], [5, 6, 7, 8], [9, 10, 11, 12]]
     np.savez_compressed(os.path.join(HERE, "transpose.npz"), inp=np.array(v), out=np.array(transpose_list(v)))
@@ -232,6 +263,7 @@ if __name__ == "__main__":
     gen_framestack()
     gen_returns()
     gen_network()
+    gen_schedule()
     gen_transpose()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

@@ -9,8 +9,12 @@ vectors from the reference's own Python code.
                      the value registered for that placeholder name (FEEDS), ``tf.get_variable``
                      returns the injected parameter (VARIABLES) - so building the reference's
                      AtariModel / A2CObjective *is* evaluating them on that data.
-  * ``kfac``       : empty KfacOptimizer / LayerCollection skeleton (kfac_utils.py only needs the
-                     base class to import).  The K-FAC arithmetic itself is NOT available.
+  * ``kfac``       : KfacOptimizer / LayerCollection skeleton.  The K-FAC arithmetic itself is NOT
+                     available; the skeleton KfacOptimizer RECORDS which of its pieces the
+                     reference's subclass (kfac_utils.ColdStartPeriodicInvUpdateKfacOpt) runs
+                     and in which order (covariance thunks, inverse thunks, the base
+                     apply_gradients, which increments global_step like kfac's does), so that
+                     the schedule golden (schedule.npz) comes from the reference class itself.
 
 Only used by make_golden.py (run in the build container; /root/reference does not exist on the
 GPU box).  The TF-op semantics restated here (conv2d NHWC/HWIO VALID cross-correlation, softmax
@@ -183,6 +187,22 @@ def _make_tf():
     tf.group = lambda ops, name=None: ops
     tf.no_op = lambda name=None: None
 
+    # --- eager control flow (kfac_utils.py:38-53): everything executes in program order, so a
+    # `control_dependencies` block is simply "after what ran before"; predicates read the CURRENT value of a StepVariable
+    @contextlib.contextmanager
+    def control_dependencies(ops):
+        yield
+    tf.control_dependencies = control_dependencies
+    tf.less = lambda a, b, name=None: _val(a) < _val(b)
+    tf.greater = lambda a, b, name=None: _val(a) > _val(b)
+    tf.equal = lambda a, b, name=None: _val(a) == _val(b)
+    tf.mod = lambda a, b, name=None: _val(a) % _val(b)
+    tf.logical_and = lambda a, b, name=None: bool(a) and bool(b)
+
+    def cond(pred, true_fn, false_fn, name=None):
+        return true_fn() if bool(pred) else false_fn()
+    tf.cond = cond
+
     def py_func(fn, inputs, dtype, stateful=True, name=None):
         # objectives.py:198,213: inputs reach the Python function as NumPy values of their graph
         # dtype (terminals: bool; discount_factor: a Python float converted to a float32 tensor)
@@ -243,12 +263,66 @@ def _make_tf():
     return tf
 
 
+class StepVariable(object):
+    """A global_step stand-in: a mutable integer read at the moment an op uses it."""
+
+    def __init__(self, value=0):
+        self.value = int(value)
+
+    def assign_add(self, n):
+        self.value += int(n)
+        return self.value
+
+    def __sub__(self, other):
+        return self.value - _val(other)
+
+    def __int__(self):
+        return self.value
+
+
+def _val(x):
+    return x.value if isinstance(x, StepVariable) else x
+
+
+EVENTS = []       # (name, global_step value when it ran) recorded by the kfac / optimizer skeletons below
+
+
+class RecordingOptimizer(object):
+    """Stands in for the cold optimizer (tf.train.MomentumOptimizer behind nn.ClipGlobalNormOptimizer): like every
+    tf.train.Optimizer.apply_gradients it increments the global_step it is handed."""
+
+    def __init__(self, name="cold"):
+        self.name = name
+
+    def apply_gradients(self, grads_and_vars, global_step=None, name=None):
+        EVENTS.append((self.name, _val(global_step)))
+        if global_step is not None:
+            global_step.assign_add(1)
+        return self.name
+
+
 def _make_kfac():
     kfac = types.ModuleType("kfac")
 
     class KfacOptimizer(object):
         def __init__(self, **kwargs):
             self.kwargs = kwargs
+
+        def make_vars_and_create_op_thunks(self):
+            def cov():
+                EVENTS.append(("cov", None))
+                return "cov"
+
+            def inv():
+                EVENTS.append(("inv", None))
+                return "inv"
+            return [cov], [inv]
+
+        def apply_gradients(self, grads_and_vars, global_step=None, name=None):
+            EVENTS.append(("kfac_apply", _val(global_step)))
+            if global_step is not None:
+                global_step.assign_add(1)
+            return "kfac_apply"
 
     class LayerCollection(object):
         """Records registrations so the golden file can list what the reference registers."""

@@ -40,7 +40,8 @@ def oracle_config(cfg):
                         norm_constraint=cfg.norm_constraint, invert_every=cfg.invert_every,
                         num_cold_updates=cfg.num_cold_updates, cold_learning_rate=cfg.cold_lr,
                         cold_momentum=cfg.cold_momentum, clip_norm=cfg.clip_norm,
-                        num_locations_mode=cfg.num_locations_mode)
+                        num_locations_mode=cfg.num_locations_mode, zero_debias=cfg.zero_debias, cov_init=cfg.cov_init,
+                        inv_init=cfg.inv_init)
 
 
 def make_pair(cfg, seed=0):

@@ -303,3 +303,152 @@ def test_data_parallel_equivalence_single_device():
         assert np.array_equal(halves[0].get_params_flat(), halves[1].get_params_flat())
         assert LC.rel_err(halves[0].get_params_flat(), full.get_params_flat()) <= 1e-6
     assert LC.rel_err(halves[0].buffer("factor_sums").cpu().numpy(), full.buffer("factor_sums").cpu().numpy()) <= 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE sizes, end to end
+def _refreshing_update(cfg, obs_kind):
+    """Two updates from global_step 0 with no cold phase and invert_every = 1: the first accumulates covariances (the
+    K-FAC apply is the exact no-op of zero-initialised inverses), the second runs the WHOLE path - forward, backward,
+    Fisher backward, 11 factor statistics, EMA, pi-damping, all 12 inverses, preconditioning, KL clip, momentum, apply -
+    and is compared quantity by quantity from identical state."""
+    records = LC.run_schedule(cfg, 2, obs_kind=obs_kind)
+    last = records[-1]
+    assert [r["gs_after"] for r in records] == [1, 2]
+    for key in ("sums_A", "sums_G", "inv_A", "inv_G", "precon", "clip_coeff", "fisher_norm"):
+        assert key in last, key
+    return records
+
+
+@pytest.mark.parametrize("kind", ["sparse", "uniform"])
+def test_full_update_with_inverse_refresh_headline_size(kind):
+    """BASELINE.json configs[2] (32 envs x 20 steps, conv3 = 32): factor sums, all inverses (1569^2 for fc4), the
+    preconditioned update of every block, the KL-clip coefficient, <V,U> and the parameter step against the fp64 oracle:
+    contract 1e-3, default precision held to 2e-4."""
+    eng = _engine_mod()
+    cfg = eng.EngineConfig(num_envs=32, num_steps=20, conv3_filters=32, num_cold_updates=0, invert_every=1)
+    records = _refreshing_update(cfg, kind)
+    _check_schedule(records, TOL_DEFAULT)
+    assert records[-1]["step_rel"] <= TOL_DEFAULT, records[-1]["step_rel"]
+    assert 0.0 < records[-1]["clip_coeff"][0] <= 1.0
+
+
+def test_full_update_with_inverse_refresh_conv3_64():
+    """The class default conv3 = 64 (envs/atari/model.py:45): the 3137 x 3137 input factor of fc4 that north_star names
+    is accumulated, inverted and used by the fc4 preconditioning GEMMs."""
+    eng = _engine_mod()
+    cfg = eng.EngineConfig(num_envs=8, num_steps=5, conv3_filters=64, num_cold_updates=0, invert_every=1)
+    records = _refreshing_update(cfg, "sparse")
+    assert records[-1]["inv_A"]["fc4"] <= TOL_DEFAULT
+    _check_schedule(records, TOL_DEFAULT)
+    assert records[-1]["step_rel"] <= TOL_DEFAULT, records[-1]["step_rel"]
+
+
+@pytest.mark.parametrize("tag", ["reference", "short", "odd"])
+def test_engine_schedule_matches_the_reference_class(golden_dir, tag):
+    """a17 against tests/golden/schedule.npz (recorded from kfac_utils.ColdStartPeriodicInvUpdateKfacOpt itself): per
+    update, whether the covariances are updated, whether the inverses are refreshed, and how global_step moves."""
+    import ctypes
+    import os
+    eng = _engine_mod()
+    g = np.load(os.path.join(golden_dir, "schedule.npz"))
+    num_cold, every = (int(v) for v in g[tag + "_config"])
+    cfg = eng.EngineConfig(num_envs=2, num_steps=3, num_cold_updates=num_cold, invert_every=every)
+    e, _ = LC.make_pair(cfg, seed=3)
+    batch = synth.rollout(5, 2, 3, 4, obs_kind="sparse")
+    ncov = 0
+    for gs_before, cold, cov, inv, _, gs_after in g[tag][:45]:
+        assert e.global_step == gs_before
+        has_factors, will_invert = ctypes.c_int(0), ctypes.c_int(0)
+        e.lib.acx_learner_update_plan(e._h, ctypes.byref(has_factors), ctypes.byref(will_invert))
+        assert (has_factors.value, will_invert.value) == (cov, inv), (tag, gs_before)
+        inv_before = e.buffer("inverses").clone()
+        e.update(batch, fetch=False)
+        torch.cuda.synchronize()
+        ncov += int(cov)
+        assert e.global_step == gs_after
+        assert e.get_state()["num_cov_updates"] == ncov
+        assert (not torch.equal(inv_before, e.buffer("inverses"))) == bool(inv), (tag, gs_before)
+
+
+@pytest.mark.parametrize("kw", [dict(inv_init="identity"), dict(cov_init="identity"), dict(zero_debias=False),
+                                dict(cov_init="identity", inv_init="identity", zero_debias=False)])
+def test_acktr_init_conventions(kw):
+    """SURVEY A.7-U3 knobs (older tf.contrib.kfac conventions), engine against oracle update by update: identity inverses
+    make the always-run K-FAC apply a real step in the cold phase and before the first refresh."""
+    eng = _engine_mod()
+    cfg = eng.EngineConfig(num_envs=4, num_steps=5, num_cold_updates=2, invert_every=2, **kw)
+    records = LC.run_schedule(cfg, 5, obs_kind="sparse")
+    _check_schedule(records, TOL_DEFAULT)
+    if kw.get("inv_init") == "identity":
+        assert all("precon" in r for r in records)          # K-FAC steps from the very first update
+        assert records[0]["step_rel"] <= TOL_DEFAULT
+    else:
+        assert "precon" not in records[0]
+
+
+# ------------------------------------------------------------------------------------------------ NCCL, 2 ranks
+def _nccl_worker(rank, world, port, out_dir):
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "tests"), os.path.join(root, "tests", "golden")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    from actorcritic_b200 import engine as eng
+    from actorcritic_b200 import parallel
+    torch.cuda.set_device(rank)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        kw = dict(num_steps=5, num_cold_updates=2, invert_every=2, lr_decay_steps=1000.0)
+        params = onet.perturbed_params(4, 32, 7)
+        results = {}
+        for split in ("1", "0"):      # split exchange (default) and the single all-reduce
+            os.environ["ACX_DP_SPLIT"] = split
+            e = eng.Engine(eng.EngineConfig(num_envs=8 // world, world_size=world, **kw))
+            e.set_params(params)
+            for u in range(7):
+                batch = parallel.shard_batch(synth.rollout(60 + u, 8, 5, 4, obs_kind="sparse"), rank, world)
+                y, eps = synth.fisher_samples(70 + u, 40)
+                lo, hi = parallel.shard_range(8, rank, world)
+                yy = torch.from_numpy(y.reshape(8, 5)[lo:hi].reshape(-1).copy()).cuda()
+                ee = torch.from_numpy(eps.reshape(8, 5)[lo:hi].reshape(-1).copy()).cuda()
+                e.update(batch, yy, ee, fetch=False)
+            torch.cuda.synchronize()
+            results[split] = dict(params=e.get_params_flat().copy(), sums=e.buffer("factor_sums").cpu().numpy().copy(),
+                                  inv=e.buffer("inverses").cpu().numpy().copy(), gs=e.global_step)
+        np.savez(os.path.join(out_dir, "rank%d.npz" % rank),
+                 **{"%s_%s" % (k, s): v for s, r in results.items() for k, v in r.items()})
+    finally:
+        dist.destroy_process_group()
+
+
+def test_nccl_two_ranks_split_exchange_equals_single_device(tmp_path):
+    """G6 over NCCL: 2 ranks x 4 environments through Engine.update (the split exchange: [G | grads | scalars] on the
+    engine's stream, the input-factor prefix on a second communicator under phase 2) against one engine over all 8
+    environments; the split exchange must be bit-identical to the single all-reduce and both ranks identical."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 CUDA devices")
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_nccl_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = (np.load(str(tmp_path / ("rank%d.npz" % r))) for r in (0, 1))
+    for key in ("params", "sums", "inv"):
+        assert np.array_equal(r0[key + "_1"], r1[key + "_1"]), key            # ranks never diverge
+        assert np.array_equal(r0[key + "_1"], r0[key + "_0"]), key            # split exchange == single all-reduce
+    eng = _engine_mod()
+    full = eng.Engine(eng.EngineConfig(num_envs=8, num_steps=5, num_cold_updates=2, invert_every=2, lr_decay_steps=1000.0))
+    full.set_params(onet.perturbed_params(4, 32, 7))
+    for u in range(7):
+        batch = synth.rollout(60 + u, 8, 5, 4, obs_kind="sparse")
+        y, eps = synth.fisher_samples(70 + u, 40)
+        full.update(batch, torch.from_numpy(y).cuda(), torch.from_numpy(eps).cuda(), fetch=False)
+    torch.cuda.synchronize()
+    assert full.global_step == int(r0["gs_1"])
+    assert LC.rel_err(r0["sums_1"], full.buffer("factor_sums").cpu().numpy()) <= 1e-5
+    # seven free-running K-FAC updates (lr 0.25): the 2-rank sum order differs from the single-device one by fp32 rounding
+    assert LC.rel_err(r0["params_1"], full.get_params_flat()) <= 1e-4
