@@ -1286,8 +1286,9 @@ void acx_debug_set_mn_desc(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t kste
 }
 
 int acx_debug_tc_error(void) {
-  const int e = acx::tc_error_flag();
-  return e ? e : acx::conv_error_flag();
+  int e = acx::tc_error_flag();
+  if (!e) e = acx::conv_error_flag();
+  return e ? e : acx::inv_error_flag();
 }
 
 int acx_debug_gemm_trace(long long* h_out4) {

@@ -103,6 +103,7 @@ struct acx_learner {
   int *d_a_dims, *d_g_dims;
   InvJob h_jobs[12];
   InvJob* d_jobs;
+  unsigned int* inv_bar;     // grid-barrier counter of the persistent inverse kernel
   PreconJob h_pjobs[6];
   PreconJob* d_pjobs;
   int num_pjobs, pjobs_max_d;
@@ -264,6 +265,7 @@ static size_t layout(acx_learner* l, uint8_t* base) {
   l->d_g_dims = reinterpret_cast<int*>(ar.take(6 * sizeof(int)));
   l->d_jobs = reinterpret_cast<InvJob*>(ar.take(12 * sizeof(InvJob)));
   l->d_pjobs = reinterpret_cast<PreconJob*>(ar.take(6 * sizeof(PreconJob)));
+  l->inv_bar = reinterpret_cast<unsigned int*>(ar.take(256));
   l->precon_w = f32(P);
   for (int i = 0; i < 6; ++i) {
     const int d = l->L[i].K + 1, c = l->L[i].C;
@@ -980,9 +982,19 @@ static int issue_phase2(acx_learner* l, const Plan2& p, cudaStream_t st) {
   }
   mark(l, 6, st);
   if (p.invert) {
-    ACX_TRY(compute_dampings(l->d_a_ptrs, l->d_g_ptrs, l->d_a_dims, l->d_g_dims, l->lambdas, 6, l->damp, st));
-    // the serial pivot-block inversions run on a side lane next to the trailing updates (joined inside, step by step)
-    ACX_TRY(spd_inverse_batched(l->h_jobs, l->d_jobs, 12, l->sched, l->damp, st, lane_of(l, 1, st).st));
+    static int inv_impl = -1;   // ACX_INV_IMPL=0: the round-1 chain of ~150 launches (A/B and bit-identity checks)
+    if (inv_impl < 0) {
+      const char* e = getenv("ACX_INV_IMPL");
+      inv_impl = e ? atoi(e) : 1;
+    }
+    if (inv_impl == 1) {   // dampings, fp64 working copies, 49 pivot steps and the operand planes in ONE persistent kernel
+      ACX_TRY(spd_inverse_persistent(l->h_jobs, l->d_jobs, 12, l->sched, l->damp, l->d_a_ptrs, l->d_g_ptrs, l->d_a_dims,
+                                     l->d_g_dims, l->lambdas, 6, l->inv_bar, st));
+    } else {
+      ACX_TRY(compute_dampings(l->d_a_ptrs, l->d_g_ptrs, l->d_a_dims, l->d_g_dims, l->lambdas, 6, l->damp, st));
+      // the serial pivot-block inversions run on a side lane next to the trailing updates (joined inside, step by step)
+      ACX_TRY(spd_inverse_batched(l->h_jobs, l->d_jobs, 12, l->sched, l->damp, st, lane_of(l, 1, st).st));
+    }
   }
   mark(l, 7, st);
   if (p.kfac_apply) {

@@ -166,7 +166,8 @@ def run_schedule(cfg, num_updates, seed=0, obs_kind="uniform", collect=None, res
                    policy_loss=[scal["policy_loss"], float(info["losses"]["policy_loss"])],
                    baseline_loss=[scal["baseline_loss"], float(info["losses"]["baseline_loss"])],
                    mean_entropy=[scal["mean_entropy"], float(info["losses"]["mean_entropy"])])
-        if cfg.acktr and "clip_coeff" in info and o.kfac.num_cov_updates > 0 and e.get_state()["inverses_valid"]:
+        if (cfg.acktr and "clip_coeff" in info and (o.kfac.num_cov_updates > 0 or cfg.inv_init == "identity")
+                and e.get_state()["inverses_valid"]):
             rec["clip_coeff"] = [scal["clip_coeff"], float(info["clip_coeff"])]
             rec["fisher_norm"] = [scal["fisher_norm"], float(info["fisher_norm"])]
             rec["precon"] = {layer: rel_err(e.layer_matrix("precon", layer).cpu().numpy(), info["precon"][layer].numpy())

@@ -1,0 +1,51 @@
+"""python tools/inv_check.py [c3]: runs 4 refreshing updates (invert_every = 1) and prints a digest of the inverses plus the
+inverse-stage time; run once with ACX_INV_IMPL=1 (persistent kernel) and once with ACX_INV_IMPL=0 (kernel chain): the
+digests must be identical (same arithmetic in the same order)."""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import synth  # noqa: E402
+from actorcritic_b200 import engine as eng  # noqa: E402
+from actorcritic_b200 import _lib  # noqa: E402
+
+c3 = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+envs, steps = (32, 20) if c3 == 32 else (8, 5)
+cfg = eng.EngineConfig(num_envs=envs, num_steps=steps, conv3_filters=c3, num_cold_updates=0, invert_every=1)
+e = eng.Engine(cfg)
+e.set_params(eng.orthogonal_init(4, c3, seed=0))
+b = synth.rollout(1, envs, steps, 4, obs_kind="uniform")
+y, eps = synth.fisher_samples(2, envs * steps)
+fl, fe = torch.from_numpy(y).cuda(), torch.from_numpy(eps).cuda()
+for u in range(4):
+    e.update(b, fl, fe, fetch=False)
+torch.cuda.synchronize()
+inv = e.buffer("inverses").cpu().numpy()
+print("impl", os.environ.get("ACX_INV_IMPL", "1"), "c3", c3, "tc_error", _lib.load().acx_debug_tc_error(),
+      "finite", bool(np.isfinite(inv).all()), "digest", hashlib.sha1(inv.tobytes()).hexdigest()[:16],
+      "params", hashlib.sha1(e.get_params_flat().tobytes()).hexdigest()[:16])
+e.set_profiling(True)
+ts = []
+for u in range(6):
+    e.update(b, fl, fe, fetch=False)
+    torch.cuda.synchronize()
+    ts.append(e.stage_ms()["inverse"])
+e.set_profiling(False)
+print("inverse stage ms per refresh (serial, eager):", ["%.3f" % t for t in ts])
+# graph-replayed whole update with refresh
+ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+with torch.cuda.stream(e.stream):
+    for u in range(3):
+        e.update(b, fl, fe, fetch=False)
+    ev0.record()
+    for u in range(10):
+        e.update(b, fl, fe, fetch=False)
+    ev1.record()
+torch.cuda.synchronize()
+print("ms per refreshing update (graphs): %.3f" % (ev0.elapsed_time(ev1) / 10), "tc_error", _lib.load().acx_debug_tc_error())
