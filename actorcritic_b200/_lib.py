@@ -85,6 +85,7 @@ SIGNATURES = {
     "acx_conv_dgrad_weights": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                               ctypes.c_int, ctypes.POINTER(_P), ctypes.c_int, _P]),
     "acx_debug_gemm_trace": (ctypes.c_int, [ctypes.POINTER(ctypes.c_longlong)]),
+    "acx_debug_inv_trace": (ctypes.c_int, [ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]),
     "acx_debug_conv_trace": (ctypes.c_int, [ctypes.POINTER(ctypes.c_longlong)]),
     "acx_learner_arena_bytes": (ctypes.c_size_t, [ctypes.POINTER(LearnerConfig)]),
     "acx_learner_create": (_P, [ctypes.POINTER(LearnerConfig), _P, ctypes.c_size_t]),

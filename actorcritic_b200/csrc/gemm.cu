@@ -1288,7 +1288,13 @@ void acx_debug_set_mn_desc(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t kste
 int acx_debug_tc_error(void) {
   int e = acx::tc_error_flag();
   if (!e) e = acx::conv_error_flag();
-  return e ? e : acx::inv_error_flag();
+  if (!e) e = acx::inv_error_flag();
+  return e ? e : acx::inv_resident_error_flag();
+}
+
+int acx_debug_inv_trace(long long* h_out, int count) {
+  const char* e = getenv("ACX_INV_IMPL");
+  return (e && atoi(e) == 1) ? acx::inv_trace_read(h_out, count) : acx::inv_resident_trace_read(h_out, count);
 }
 
 int acx_debug_gemm_trace(long long* h_out4) {

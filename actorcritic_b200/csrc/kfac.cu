@@ -372,6 +372,10 @@ __global__ void inv_finish_kernel(const InvDev* __restrict__ jobs) {
 // at a barrier for longer than ~2 s records an error and leaves instead of hanging the device.
 // ------------------------------------------------------------------------------------------------
 static __device__ int g_inv_error = 0;
+// triage (ACX_INV_TRACE=1): per pivot step, clock64 stamps of thread 0 of the LAST CTA (a generic worker) [0] step start,
+// [1] panels done, [2] barrier 1 passed, [3] update done, [4] barrier 2 passed; of CTA 0 (look-ahead of the largest job):
+// [5] step start, [6] look-ahead panel + pivot inversion done
+static __device__ long long g_inv_trace[128 * 8];
 
 struct InvPersistArgs {
   const InvDev* jobs;
@@ -386,6 +390,7 @@ struct InvPersistArgs {
   const float* lambdas;
   int num_layers;
   unsigned int* bar;           // grid barrier counter, zero at launch
+  int trace;
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
@@ -629,12 +634,17 @@ __global__ void __launch_bounds__(256, 1) inv_persistent_kernel(const InvPersist
     const int wbase = dedicated ? nact : 0;
     const int nworkers = G - wbase;
     const int wid = cta - wbase;
+    const bool tr_w = a.trace && p < 128 && cta == G - 1 && threadIdx.x == 0;
+    const bool tr_0 = a.trace && p < 128 && cta == 0 && threadIdx.x == 0;
+    if (tr_w) g_inv_trace[p * 8 + 0] = clock64();
+    if (tr_0) g_inv_trace[p * 8 + 5] = clock64();
     // panels
     for (int j0 = cta; j0 < nact; j0 += G) {
       const InvDev jb = a.jobs[j0];
       const int nblk = (jb.n + IB - 1) / IB;
       if (p + 1 < nblk) inv_panel_item(jb, p, p + 1, true, pd, pt);
     }
+    if (tr_0) g_inv_trace[p * 8 + 6] = clock64();
     if (wid >= 0) {
       int base = 0;
       for (int j = 0; j < nact; ++j) {
@@ -654,7 +664,9 @@ __global__ void __launch_bounds__(256, 1) inv_persistent_kernel(const InvPersist
         base += cnt;
       }
     }
+    if (tr_w) g_inv_trace[p * 8 + 1] = clock64();
     if (!grid_barrier(a.bar, epoch)) return;
+    if (tr_w) g_inv_trace[p * 8 + 2] = clock64();
     // update
     if (wid >= 0) {
       int base = 0;
@@ -675,7 +687,9 @@ __global__ void __launch_bounds__(256, 1) inv_persistent_kernel(const InvPersist
         base += cnt;
       }
     }
+    if (tr_w) g_inv_trace[p * 8 + 3] = clock64();
     if (!grid_barrier(a.bar, epoch)) return;
+    if (tr_w) g_inv_trace[p * 8 + 4] = clock64();
   }
   // ---- phase F: fp32 inverse + bf16 planes (inv_finish_kernel)
   for (int j = 0; j < a.num_jobs; ++j) {
@@ -1093,6 +1107,10 @@ int spd_inverse_batched(const InvJob* h_jobs, const InvJob* d_jobs, int num_jobs
   return 0;
 }
 
+int inv_trace_read(long long* h_out, int count) {
+  if (count > 128 * 8) count = 128 * 8;
+  return cudaMemcpyFromSymbol(h_out, g_inv_trace, (size_t)count * sizeof(long long)) == cudaSuccess ? 0 : 1;
+}
 int inv_error_flag() {
   int v = 0;
   cudaMemcpyFromSymbol(&v, g_inv_error, sizeof(int));
@@ -1135,6 +1153,14 @@ int spd_inverse_persistent(const InvJob* h_jobs, const InvJob* d_jobs, int num_j
   a.lambdas = d_lambda;
   a.num_layers = num_layers;
   a.bar = d_bar;
+  {
+    static int tr = -1;
+    if (tr < 0) {
+      const char* e = getenv("ACX_INV_TRACE");
+      tr = e ? atoi(e) : 0;
+    }
+    a.trace = tr;
+  }
   inv_persistent_kernel<<<grid, 256, 0, st>>>(a);
   ACX_LAUNCH_CHECK();
   return 0;

@@ -280,7 +280,7 @@ static size_t layout(acx_learner* l, uint8_t* base) {
     ja.n = d;
     ja.damp_index = 2 * i;
     ja.work_m = reinterpret_cast<double*>(ar.take((size_t)d * d * sizeof(double)));
-    ja.work_x = reinterpret_cast<double*>(ar.take(((size_t)3 * 32 * d + 2 * 32 * 32) * sizeof(double)));
+    ja.work_x = reinterpret_cast<double*>(ar.take(((size_t)3 * 32 * d + 2 * 32 * 32 + 2048) * sizeof(double)));
     ja.inv = l->inv + l->ainv_off[i];
     for (int q = 0; q < 3; ++q) ja.planes[q] = l->ainv_pl[i].p[q];
     ja.ld_planes = l->ainv_pl[i].ld;
@@ -289,7 +289,7 @@ static size_t layout(acx_learner* l, uint8_t* base) {
     jg.n = c;
     jg.damp_index = 2 * i + 1;
     jg.work_m = reinterpret_cast<double*>(ar.take((size_t)c * c * sizeof(double)));
-    jg.work_x = reinterpret_cast<double*>(ar.take(((size_t)3 * 32 * c + 2 * 32 * 32) * sizeof(double)));
+    jg.work_x = reinterpret_cast<double*>(ar.take(((size_t)3 * 32 * c + 2 * 32 * 32 + 2048) * sizeof(double)));
     jg.inv = l->inv + l->ginv_off[i];
     for (int q = 0; q < 3; ++q) jg.planes[q] = l->ginv_pl[i].p[q];
     jg.ld_planes = l->ginv_pl[i].ld;
@@ -982,15 +982,26 @@ static int issue_phase2(acx_learner* l, const Plan2& p, cudaStream_t st) {
   }
   mark(l, 6, st);
   if (p.invert) {
-    static int inv_impl = -1;   // ACX_INV_IMPL=0: the round-1 chain of ~150 launches (A/B and bit-identity checks)
+    // ACX_INV_IMPL: 2 (default) = fp32, all factor tiles resident in shared memory, one persistent kernel (kfac_inv.cu);
+    // 1 = the fp64 Gauss-Jordan as one persistent kernel; 0 = the round-1 fp64 chain of ~150 launches (also the fallback when
+    // the tiles do not fit the SMs' shared memory)
+    static int inv_impl = -1;
     if (inv_impl < 0) {
       const char* e = getenv("ACX_INV_IMPL");
-      inv_impl = e ? atoi(e) : 1;
+      inv_impl = e ? atoi(e) : 2;
     }
-    if (inv_impl == 1) {   // dampings, fp64 working copies, 49 pivot steps and the operand planes in ONE persistent kernel
+    int done = 0;
+    if (inv_impl == 2) {
+      const int r = spd_inverse_resident(l->h_jobs, 12, l->sched, l->damp, l->d_a_ptrs, l->d_g_ptrs, l->d_a_dims, l->d_g_dims,
+                                         l->lambdas, 6, l->inv_bar, st);
+      if (r > 0) return r;
+      done = r == 0;
+    } else if (inv_impl == 1) {
       ACX_TRY(spd_inverse_persistent(l->h_jobs, l->d_jobs, 12, l->sched, l->damp, l->d_a_ptrs, l->d_g_ptrs, l->d_a_dims,
                                      l->d_g_dims, l->lambdas, 6, l->inv_bar, st));
-    } else {
+      done = 1;
+    }
+    if (!done) {
       ACX_TRY(compute_dampings(l->d_a_ptrs, l->d_g_ptrs, l->d_a_dims, l->d_g_dims, l->lambdas, 6, l->damp, st));
       // the serial pivot-block inversions run on a side lane next to the trailing updates (joined inside, step by step)
       ACX_TRY(spd_inverse_batched(l->h_jobs, l->d_jobs, 12, l->sched, l->damp, st, lane_of(l, 1, st).st));

@@ -30,6 +30,20 @@ inv = e.buffer("inverses").cpu().numpy()
 print("impl", os.environ.get("ACX_INV_IMPL", "1"), "c3", c3, "tc_error", _lib.load().acx_debug_tc_error(),
       "finite", bool(np.isfinite(inv).all()), "digest", hashlib.sha1(inv.tobytes()).hexdigest()[:16],
       "params", hashlib.sha1(e.get_params_flat().tobytes()).hexdigest()[:16])
+# accuracy of every stored inverse against numpy fp64 on the engine's own running sums and dampings
+damp = e.buffer("dampings").cpu().numpy().astype(np.float64)
+ncov = e.get_state()["num_cov_updates"]
+debias = 1.0 / (1.0 - 0.99 ** ncov)
+worst = {}
+for li, layer in enumerate(eng.LAYERS):
+    fac = "heads" if layer.startswith("fc_p") or layer.startswith("fc_b") else layer
+    for which, name, d in (("A", fac, damp[2 * li]), ("G", layer, damp[2 * li + 1])):
+        sm = e.factor("sums", which, name).cpu().numpy().astype(np.float64)
+        m = 0.5 * (sm + sm.T) * debias + d * np.eye(sm.shape[0])
+        want = np.linalg.inv(m)
+        got = e.factor("inv", which, layer).cpu().numpy().astype(np.float64)
+        worst["%s/%s" % (which, layer)] = float(np.linalg.norm(got - want) / np.linalg.norm(want))
+print("inverse rel err vs fp64:", {k: "%.1e" % v for k, v in worst.items()})
 e.set_profiling(True)
 ts = []
 for u in range(6):
@@ -49,3 +63,21 @@ with torch.cuda.stream(e.stream):
     ev1.record()
 torch.cuda.synchronize()
 print("ms per refreshing update (graphs): %.3f" % (ev0.elapsed_time(ev1) / 10), "tc_error", _lib.load().acx_debug_tc_error())
+
+if os.environ.get("ACX_INV_TRACE"):
+    import ctypes
+    buf = (ctypes.c_longlong * 1024)()
+    _lib.load().acx_debug_inv_trace(buf, 1024)
+    t = np.array(list(buf), np.int64).reshape(128, 8)
+    steps = (int(49 * c3 / 32) + 1 + 31) // 32 if False else None
+    print("step: panels | bar1 | update | bar2 | total (cycles)   || cta0: look-ahead")
+    for p in range(0, 100):
+        r = t[p]
+        if r[4] == 0:
+            break
+        if p < 6 or p % 8 == 0 or p > 44:
+            print(p, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[4] - r[0], "||", r[6] - r[5])
+    valid = t[(t[:, 4] > 0)]
+    tot = valid[:, 4] - valid[:, 0]
+    print("sum cycles", int(tot.sum()), "panels", int((valid[:, 1] - valid[:, 0]).sum()), "bar1", int((valid[:, 2] - valid[:, 1]).sum()),
+          "update", int((valid[:, 3] - valid[:, 2]).sum()), "bar2", int((valid[:, 4] - valid[:, 3]).sum()), "lookahead", int((valid[:, 6] - valid[:, 5]).sum()))
