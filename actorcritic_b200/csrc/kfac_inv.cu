@@ -31,7 +31,7 @@ constexpr int RES_JOBS = 12;
 constexpr int RES_THREADS = 256;
 constexpr int TILE_FLOATS = TS * TS;
 constexpr int STAGE_FLOATS = 2 * RB * OPLD + RB * (RB + 1) + 64;   // A piece | B piece | D^-1 [32][33] | slack
-constexpr int RES_SMEM_LIMIT = 232448;
+constexpr int RES_SMEM_LIMIT = 232448 - 1024;   // 227 KB per CTA minus the static shared memory (ownership tables)
 
 struct ResJob {
   const float* s;   // [n, n] running covariance sum
@@ -62,6 +62,7 @@ struct ResArgs {
   int num_layers;
   unsigned int* bar;
   int trace;
+  int debug;         // triage (ACX_INV_DEBUG): bit 1 = no operand prefetch
 };
 
 __device__ int g_res_error = 0;
@@ -108,33 +109,35 @@ __device__ __forceinline__ bool grid_wait(unsigned int* bar, unsigned int epoch)
   return __syncthreads_and(ok) != 0;
 }
 
-// in-place inverse of a 32 x 32 SPD block in shared memory (row stride 33), all 256 threads; unblocked Gauss-Jordan
-// without pivoting; rows / columns beyond the matrix are identity padding
-__device__ __forceinline__ void invert32(float (*d)[RB + 1]) {
+// inverse of a 32 x 32 SPD block in shared memory (row stride 33), all 256 threads; unblocked Gauss-Jordan without
+// pivoting; rows / columns beyond the matrix are identity padding.  The 32 elimination steps are a serial chain (this is
+// the critical path of the look-ahead CTA), so each step costs one barrier only: it reads buffer d, writes buffer e and
+// the two swap (32 steps: the result ends in d).
+__device__ __forceinline__ void invert32(float (*d)[RB + 1], float (*e2)[RB + 1]) {
+  __syncthreads();
+  float (*src)[RB + 1] = d;
+  float (*dst)[RB + 1] = e2;
+  const int tx = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll 2
   for (int k = 0; k < RB; ++k) {
-    __syncthreads();
-    const float inv_p = 1.0f / d[k][k];
-    float v[4];
+    const float inv_p = 1.0f / src[k][k];
+    const float row_k = src[k][tx];
+    const float scaled = row_k * inv_p;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      const int e = threadIdx.x + c * RES_THREADS;
-      const int ty = e >> 5, tx = e & 31;
-      const float row_k = d[k][tx], col_k = d[ty][k];
-      const float scaled = row_k * inv_p;
-      float r = fmaf(-col_k, scaled, d[ty][tx]);
+      const int ty = w + 8 * c;
+      const float col_k = src[ty][k];
+      float r = fmaf(-col_k, scaled, src[ty][tx]);
       if (ty == k) r = scaled;
       if (tx == k) r = -col_k * inv_p;
       if (ty == k && tx == k) r = inv_p;
-      v[c] = r;
+      dst[ty][tx] = r;
     }
     __syncthreads();
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int e = threadIdx.x + c * RES_THREADS;
-      d[e >> 5][e & 31] = v[c];
-    }
+    float (*t)[RB + 1] = src;
+    src = dst;
+    dst = t;
   }
-  __syncthreads();
 }
 
 __device__ __forceinline__ float prep_value(const ResJob& jb, int gi, int gj, float debias, float dv) {
@@ -351,6 +354,9 @@ __device__ __forceinline__ void finish_tile(const ResJob& jb, int ti, int tj, co
 __global__ void __launch_bounds__(RES_THREADS, 1) inv_resident_kernel(const __grid_constant__ ResArgs a) {
   extern __shared__ __align__(16) float smem[];
   __shared__ int s_job[16], s_ti[16], s_tj[16];
+  __shared__ ResJob s_jobs[RES_JOBS];      // the job table out of the parameter bank (dynamic indexing)
+  if (threadIdx.x < RES_JOBS) s_jobs[threadIdx.x] = a.jobs[threadIdx.x];
+  __syncthreads();
   const int G = gridDim.x, cta = blockIdx.x;
   const int ND = a.num_jobs;            // look-ahead CTAs [0, ND), owners [ND, G)
   const int W = G - ND;
@@ -368,8 +374,8 @@ __global__ void __launch_bounds__(RES_THREADS, 1) inv_resident_kernel(const __gr
     int job = -1, ti = 0, tj = 0;
     if (g < a.total_tiles) {
       job = 0;
-      while (job + 1 < a.num_jobs && a.jobs[job + 1].tile_base <= g) ++job;
-      const int it = g - a.jobs[job].tile_base;          // column-major upper triangle: it = tj (tj + 1) / 2 + ti
+      while (job + 1 < a.num_jobs && s_jobs[job + 1].tile_base <= g) ++job;
+      const int it = g - s_jobs[job].tile_base;          // column-major upper triangle: it = tj (tj + 1) / 2 + ti
       tj = (int)((sqrtf(8.0f * (float)it + 1.0f) - 1.0f) * 0.5f);
       while (tj * (tj + 1) / 2 > it) --tj;
       while ((tj + 1) * (tj + 2) / 2 <= it) ++tj;
@@ -407,7 +413,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) inv_resident_kernel(const __gr
     for (int s = 0; s < a.slots; ++s) {
       const int job = s_job[s];
       if (job < 0) continue;
-      const ResJob& jb = a.jobs[job];
+      const ResJob& jb = s_jobs[job];
       const int ti = s_ti[s], tj = s_tj[s];
       const float dv = __ldcg(a.damp + jb.damp_index);
       float* T = tiles + (size_t)s * TILE_FLOATS;
@@ -419,14 +425,14 @@ __global__ void __launch_bounds__(RES_THREADS, 1) inv_resident_kernel(const __gr
       publish_pair(jb, 0, ti, tj, T);     // blocks (0, 1) and (1, 1) for the look-ahead of step 0
     }
   } else {
-    const ResJob& jb = a.jobs[cta];
+    const ResJob& jb = s_jobs[cta];
     const int nb = min(RB, jb.n);
     const float dv = __ldcg(a.damp + jb.damp_index);
     for (int e = threadIdx.x; e < RB * RB; e += RES_THREADS) {
       const int y = e >> 5, x = e & 31;
       Ds[y][x] = (y < nb && x < nb) ? prep_value(jb, y, x, debias, dv) : (y == x ? 1.0f : 0.0f);
     }
-    invert32(Ds);
+    invert32(Ds, reinterpret_cast<float (*)[RB + 1]>(tiles) + 3 * RB);
     float* dinv = sc_dinv(jb, 0);
     for (int e = threadIdx.x; e < RB * RB; e += RES_THREADS) __stcg(dinv + e, Ds[e >> 5][e & 31]);
   }
@@ -437,10 +443,13 @@ __global__ void __launch_bounds__(RES_THREADS, 1) inv_resident_kernel(const __gr
     const int p0 = p * RB;
     if (!owner) {
       // look-ahead CTA of job `cta`: D_{p+1}^-1 from D_p^-1 (still in Ds) and the blocks published during step p - 1
-      const ResJob& jb = a.jobs[cta];
+      const ResJob& jb = s_jobs[cta];
       const bool tr = a.trace && p < 128 && cta == 0 && threadIdx.x == 0;
       if (tr) g_res_trace[p * 8 + 5] = clock64();
-      grid_arrive(a.bar, epoch);          // barrier 1 of this step: nothing here depends on the panels
+      // barrier 1 of this step: nothing here depends on the panels, so arrive at once - but the counter is cumulative, so
+      // this CTA must not arrive at barrier 2 before barrier 1 has completed (its arrival would be counted for barrier 1)
+      grid_arrive(a.bar, epoch);
+      const unsigned int epoch_b1 = epoch;
       const int nblk = (jb.n + RB - 1) / RB;
       if (jb.n > p0 && p + 1 < nblk) {
         float (*Ps)[RB + 1] = reinterpret_cast<float (*)[RB + 1]>(tiles);
@@ -475,11 +484,12 @@ __global__ void __launch_bounds__(RES_THREADS, 1) inv_resident_kernel(const __gr
         __syncthreads();
 #pragma unroll
         for (int c = 0; c < 4; ++c) Ds[w + 8 * c][x] = v[c];
-        invert32(Ds);
+        invert32(Ds, Rs + RB);
         float* dinv = sc_dinv(jb, p + 1);
         for (int e = threadIdx.x; e < RB * RB; e += RES_THREADS) __stcg(dinv + e, Ds[e >> 5][e & 31]);
       }
       if (tr) g_res_trace[p * 8 + 6] = clock64();
+      if (!grid_wait(a.bar, epoch_b1)) return;
       grid_arrive(a.bar, epoch);          // barrier 2
       if (!grid_wait(a.bar, epoch)) return;
       if (tr) g_res_trace[p * 8 + 7] = clock64();
@@ -490,10 +500,10 @@ __global__ void __launch_bounds__(RES_THREADS, 1) inv_resident_kernel(const __gr
     // panels
     for (int s = 0; s < a.slots; ++s) {
       const int job = s_job[s];
-      if (job < 0 || a.jobs[job].n <= p0) continue;
-      const int nblk = (a.jobs[job].n + RB - 1) / RB;
+      if (job < 0 || s_jobs[job].n <= p0) continue;
+      const int nblk = (s_jobs[job].n + RB - 1) / RB;
       if (nblk < 2) continue;
-      panel_piece(a.jobs[job], p, s_ti[s], s_tj[s], tiles + (size_t)s * TILE_FLOATS, As, Bs, Ds);
+      panel_piece(s_jobs[job], p, s_ti[s], s_tj[s], tiles + (size_t)s * TILE_FLOATS, As, Bs, Ds);
     }
     if (tr) g_res_trace[p * 8 + 1] = clock64();
     grid_arrive(a.bar, epoch);
@@ -503,23 +513,24 @@ __global__ void __launch_bounds__(RES_THREADS, 1) inv_resident_kernel(const __gr
     {
       int s = 0;
       auto next_active = [&](int from) {
-        while (from < a.slots && (s_job[from] < 0 || a.jobs[s_job[from]].n <= p0)) ++from;
+        while (from < a.slots && (s_job[from] < 0 || s_jobs[s_job[from]].n <= p0)) ++from;
         return from;
       };
       s = next_active(0);
       OpRegs regs;
-      if (s < a.slots) fetch_ops(a.jobs[s_job[s]], p, s_ti[s], s_tj[s], regs);
+      if (s < a.slots) fetch_ops(s_jobs[s_job[s]], p, s_ti[s], s_tj[s], regs);
       while (s < a.slots) {
-        const ResJob& jb = a.jobs[s_job[s]];
+        const ResJob& jb = s_jobs[s_job[s]];
         const int ti = s_ti[s], tj = s_tj[s];
         float* T = tiles + (size_t)s * TILE_FLOATS;
         __syncthreads();                 // the previous tile is done with the staging buffers
         stage_ops(regs, As, Bs);
         __syncthreads();
         const int sn = next_active(s + 1);
-        if (sn < a.slots) fetch_ops(a.jobs[s_job[sn]], p, s_ti[sn], s_tj[sn], regs);
+        if (sn < a.slots && !(a.debug & 2)) fetch_ops(s_jobs[s_job[sn]], p, s_ti[sn], s_tj[sn], regs);
         update_tile(jb, p, ti, tj, T, As, Bs);
         __syncthreads();
+        if (sn < a.slots && (a.debug & 2)) fetch_ops(s_jobs[s_job[sn]], p, s_ti[sn], s_tj[sn], regs);
         publish_pair(jb, p + 1, ti, tj, T);    // for the look-ahead of step p + 1
         s = sn;
       }
@@ -534,7 +545,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) inv_resident_kernel(const __gr
     for (int s = 0; s < a.slots; ++s) {
       const int job = s_job[s];
       if (job < 0) continue;
-      finish_tile(a.jobs[job], s_ti[s], s_tj[s], tiles + (size_t)s * TILE_FLOATS, stage);
+      finish_tile(s_jobs[job], s_ti[s], s_tj[s], tiles + (size_t)s * TILE_FLOATS, stage);
     }
   }
 }
@@ -588,7 +599,8 @@ int spd_inverse_resident(const InvJob* h_jobs, int num_jobs, const Sched* sched,
   }
   for (int i = num_jobs; i < RES_JOBS; ++i) a.jobs[i] = a.jobs[0];
   const int owners = grid - num_jobs;
-  const int slots = ceil_div(total, owners);
+  int slots = ceil_div(total, owners);
+  if (slots < 2) slots = 2;   // the look-ahead CTAs use the tile area for five 32 x 33 blocks
   const size_t smem = ((size_t)STAGE_FLOATS + (size_t)slots * TILE_FLOATS) * sizeof(float);
   if (slots > 16 || smem > (size_t)RES_SMEM_LIMIT) return -1;
   static size_t configured = 0;
@@ -616,6 +628,12 @@ int spd_inverse_resident(const InvJob* h_jobs, int num_jobs, const Sched* sched,
       tr = e ? atoi(e) : 0;
     }
     a.trace = tr;
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("ACX_INV_DEBUG");
+      dbg = e ? atoi(e) : 0;
+    }
+    a.debug = dbg;
   }
   ACX_CUDA(cudaMemsetAsync(d_bar, 0, sizeof(unsigned int), st));
   inv_resident_kernel<<<grid, RES_THREADS, smem, st>>>(a);

@@ -43,6 +43,16 @@ for li, layer in enumerate(eng.LAYERS):
         want = np.linalg.inv(m)
         got = e.factor("inv", which, layer).cpu().numpy().astype(np.float64)
         worst["%s/%s" % (which, layer)] = float(np.linalg.norm(got - want) / np.linalg.norm(want))
+        if which == "A" and layer == "fc4":
+            err = np.abs(got - want)
+            blk = err[: (err.shape[0] // 32) * 32, : (err.shape[0] // 32) * 32].reshape(err.shape[0] // 32, 32, -1, 32).max(axis=(1, 3))
+            top = np.dstack(np.unravel_index(np.argsort(blk.ravel())[::-1][:12], blk.shape))[0]
+            print("fc4 A: max |err| %.3e at %s, |want| max %.3e; worst 32-blocks (row, col, err):" % (
+                err.max(), np.unravel_index(err.argmax(), err.shape), np.abs(want).max()),
+                [(int(r), int(c), "%.1e" % blk[r, c]) for r, c in top])
+            print("   error by block row:", ["%.0e" % v for v in blk.max(axis=1)])
+            print("   edge rows/cols err:", "%.2e" % err[-1, :].max(), "%.2e" % err[:, -1].max(), "diag err max %.2e" % np.abs(np.diag(got - want)).max(),
+                  "asym %.2e" % np.abs(got - got.T).max())
 print("inverse rel err vs fp64:", {k: "%.1e" % v for k, v in worst.items()})
 e.set_profiling(True)
 ts = []
