@@ -108,6 +108,13 @@ SIGNATURES = {
     "acx_learner_set_state": (ctypes.c_int, [_P, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, _P]),
     "acx_learner_get_state": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64),
                                              ctypes.POINTER(ctypes.c_int)]),
+    "acx_learner_set_loss_weights": (ctypes.c_int, [_P, ctypes.c_float, ctypes.c_float]),
+    "acx_clip_rmsprop_step": (ctypes.c_int, [_P, _P, _P, ctypes.c_size_t, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                             ctypes.c_float, _P, _P, _P]),
+    "acx_clip_momentum_step": (ctypes.c_int, [_P, _P, _P, ctypes.c_size_t, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                              _P, _P, _P]),
+    "acx_sample_actions": (ctypes.c_int, [_P, _P, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          _P, _P]),
     "acx_learner_act": (ctypes.c_int, [_P, _P, ctypes.c_int, _P, ctypes.c_int, _P, _P, _P, _P]),
 }
 

@@ -829,8 +829,8 @@ __global__ void __launch_bounds__(256) rmsprop_clip_kernel(float* __restrict__ p
                                                            const float* __restrict__ grads, size_t count,
                                                            const float* __restrict__ partial, int num_partials,
                                                            const Sched* __restrict__ sched, float decay, float eps, float clip,
-                                                           float* __restrict__ out_scalars) {
-  const float lr = sched->lr;
+                                                           float* __restrict__ out_scalars, float lr_value) {
+  const float lr = sched ? sched->lr : lr_value;
   const float sq = sum_partials(partial, num_partials);
   const float norm = sqrtf(sq);
   const float scale = clip / fmaxf(norm, clip);
@@ -1196,11 +1196,42 @@ int momentum_clip_step(float* params, float* accum, const float* grads, size_t c
   return 0;
 }
 int rmsprop_clip_step(float* params, float* ms, const float* grads, size_t count, const float* sq_partials, int num_partials,
-                      const Sched* sched, float decay, float epsilon, float clip_norm, float* out_scalars, cudaStream_t st) {
+                      const Sched* sched, float decay, float epsilon, float clip_norm, float* out_scalars, cudaStream_t st,
+                      float lr_value) {
   rmsprop_clip_kernel<<<grid_for(count, 256, 148 * 4), 256, 0, st>>>(params, ms, grads, count, sq_partials, num_partials, sched,
-                                                                    decay, epsilon, clip_norm, out_scalars);
+                                                                    decay, epsilon, clip_norm, out_scalars, lr_value);
   ACX_LAUNCH_CHECK();
   return 0;
 }
 
 }  // namespace acx
+
+// ---- stand-alone optimizer steps (C ABI): what objectives.py:31-54 `optimize_separate` applies per loss -----------------
+extern "C" {
+
+static const int kStepPartials = 296;
+
+// ClipGlobalNormOptimizer(RMSPropOptimizer(lr, decay, momentum 0, eps)).apply_gradients (nn.py:185-189, a2c_acktr.py:250-251)
+int acx_clip_rmsprop_step(float* d_params, float* d_ms, const float* d_grads, size_t count, float lr, float decay, float epsilon,
+                          float clip_norm, float* d_scratch, float* d_out_norm, void* stream) {
+  ACX_CHECK(d_params && d_ms && d_grads && d_scratch && count > 0, "null argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int r = acx::dot_partial(d_grads, d_grads, count, d_scratch, kStepPartials, st);
+  if (r) return r;
+  return acx::rmsprop_clip_step(d_params, d_ms, d_grads, count, d_scratch, kStepPartials, nullptr, decay, epsilon, clip_norm,
+                                d_out_norm, st, lr);
+}
+
+// ClipGlobalNormOptimizer(MomentumOptimizer(lr, momentum)).apply_gradients (nn.py:185-189, a2c_acktr.py:240-241)
+int acx_clip_momentum_step(float* d_params, float* d_accum, const float* d_grads, size_t count, float lr, float momentum,
+                           float clip_norm, float* d_scratch, float* d_out_norm, void* stream) {
+  ACX_CHECK(d_params && d_accum && d_grads && d_scratch && count > 0, "null argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int r = acx::dot_partial(d_grads, d_grads, count, d_scratch, kStepPartials, st);
+  if (r) return r;
+  return acx::momentum_clip_step(d_params, d_accum, d_grads, count, d_scratch, kStepPartials, lr, momentum, clip_norm, d_out_norm,
+                                 st);
+}
+
+}  // extern "C"
+

@@ -30,8 +30,8 @@ constexpr int OPLD = 68;      // row stride (floats) of the staged operand piece
 constexpr int RES_JOBS = 12;
 constexpr int RES_THREADS = 256;
 constexpr int TILE_FLOATS = TS * TS;
-constexpr int STAGE_FLOATS = 2 * RB * OPLD + RB * (RB + 1) + 64;   // A piece | B piece | D^-1 [32][33] | slack
-constexpr int RES_SMEM_LIMIT = 232448 - 1024;   // 227 KB per CTA minus the static shared memory (ownership tables)
+constexpr int STAGE_FLOATS = 3 * RB * OPLD + RB * (RB + 1) + 64;   // A piece | B piece | C piece | D^-1 [32][33 (34)] | slack
+constexpr int RES_SMEM_TOTAL = 232448;   // 227 KB per CTA on sm_100 (static + dynamic)
 
 struct ResJob {
   const float* s;   // [n, n] running covariance sum
@@ -76,68 +76,85 @@ __device__ __forceinline__ float* sc_dinv(const ResJob& jb, int p) { return jb.x
 __device__ __forceinline__ float* sc_pq(const ResJob& jb, int s) { return jb.x + (size_t)2 * RB * jb.ldp + 2048 + (s & 1) * 1024; }
 __device__ __forceinline__ float* sc_qq(const ResJob& jb, int s) { return jb.x + (size_t)2 * RB * jb.ldp + 4096 + (s & 1) * 1024; }
 
-__device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
+__device__ __forceinline__ unsigned int ld_relaxed(const unsigned int* p) {
   unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 
-// grid barrier on a monotonically increasing counter.  arrive: this CTA's writes are published and counted; wait: until all
-// CTAs have arrived `epoch` times.  An early arrival for barrier k + 1 is only legal after this CTA has PASSED barrier k.
+// grid barrier on a monotonically increasing counter.  arrive: this CTA's writes are published and counted (one release
+// reduction: no separate full fence); wait: relaxed polling until all CTAs have arrived `epoch` times, then one acquire
+// fence.  An early arrival for barrier k + 1 is only legal after this CTA has PASSED barrier k.
 __device__ __forceinline__ void grid_arrive(unsigned int* bar, unsigned int& epoch) {
   ++epoch;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(bar, 1u);
-  }
+  if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
 }
 __device__ __forceinline__ bool grid_wait(unsigned int* bar, unsigned int epoch) {
   int ok = 1;
   if (threadIdx.x == 0) {
     const unsigned int target = epoch * gridDim.x;
-    const long long t0 = clock64();
-    while (ld_acquire(bar) < target) {
-      if (clock64() - t0 > 4000000000ll) {   // ~2 s: some CTA of the grid is not running
-        atomicExch(&g_res_error, 31);
-        ok = 0;
-        break;
+    if (ld_relaxed(bar) < target) {
+      const long long t0 = clock64();
+      while (ld_relaxed(bar) < target) {
+        if (clock64() - t0 > 4000000000ll) {   // ~2 s: some CTA of the grid is not running
+          atomicExch(&g_res_error, 31);
+          ok = 0;
+          break;
+        }
       }
     }
-    __threadfence();
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
   }
   return __syncthreads_and(ok) != 0;
 }
 
 // inverse of a 32 x 32 SPD block in shared memory (row stride 33), all 256 threads; unblocked Gauss-Jordan without
-// pivoting; rows / columns beyond the matrix are identity padding.  The 32 elimination steps are a serial chain (this is
-// the critical path of the look-ahead CTA), so each step costs one barrier only: it reads buffer d, writes buffer e and
-// the two swap (32 steps: the result ends in d).
-__device__ __forceinline__ void invert32(float (*d)[RB + 1], float (*e2)[RB + 1]) {
-  __syncthreads();
-  float (*src)[RB + 1] = d;
-  float (*dst)[RB + 1] = e2;
+// pivoting; rows / columns beyond the matrix are identity padding.  The 32 elimination steps are a serial chain (the
+// critical path of the look-ahead CTA): every thread keeps its four elements (rows w, w+8, w+16, w+24 of column tx) in
+// registers for all steps; per step only the pivot row and the pivot column are exchanged through a small double-buffered
+// shared array, with ONE barrier:  barrier -> read row k / column k -> reciprocal -> 4 FMAs -> publish row / column k+1.
+__device__ __forceinline__ void invert32(float (*d)[RB + 1], float* xbuf /* [2][64] */) {
   const int tx = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll 2
+  __syncthreads();
+  float v[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) v[c] = d[w + 8 * c][tx];
+  if (w == 0) xbuf[tx] = v[0];                     // row 0
+  if (tx == 0) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) xbuf[32 + w + 8 * c] = v[c];   // column 0
+  }
+  __syncthreads();
+#pragma unroll
   for (int k = 0; k < RB; ++k) {
-    const float inv_p = 1.0f / src[k][k];
-    const float row_k = src[k][tx];
-    const float scaled = row_k * inv_p;
+    const float* rb = xbuf + (k & 1) * 64;
+    const float* cb = rb + 32;
+    const float inv_p = __frcp_rn(rb[k]);
+    const float scaled = rb[tx] * inv_p;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       const int ty = w + 8 * c;
-      const float col_k = src[ty][k];
-      float r = fmaf(-col_k, scaled, src[ty][tx]);
+      const float col_k = cb[ty];
+      float r = fmaf(-col_k, scaled, v[c]);
       if (ty == k) r = scaled;
       if (tx == k) r = -col_k * inv_p;
       if (ty == k && tx == k) r = inv_p;
-      dst[ty][tx] = r;
+      v[c] = r;
+    }
+    if (k + 1 < RB) {
+      float* nb = xbuf + ((k + 1) & 1) * 64;
+      if (w == ((k + 1) & 7)) nb[tx] = v[(k + 1) >> 3];          // row k + 1 lives in warp (k + 1) % 8, register (k + 1) / 8
+      if (tx == k + 1) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) nb[32 + w + 8 * c] = v[c];     // column k + 1
+      }
     }
     __syncthreads();
-    float (*t)[RB + 1] = src;
-    src = dst;
-    dst = t;
   }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) d[w + 8 * c][tx] = v[c];
+  __syncthreads();
 }
 
 __device__ __forceinline__ float prep_value(const ResJob& jb, int gi, int gj, float debias, float dv) {
@@ -173,6 +190,7 @@ __device__ __forceinline__ void publish_pair(const ResJob& jb, int s, int ti, in
 }
 
 // panels of step p from an owned tile that intersects the pivot rows: its 32 x 64 piece of Rold and R = D_p^-1 Rold
+template <int DBG = 0>   // triage (tools/micro/inv_micro.cu): 1 = no D^-1 load, 2 = no stores, 4 = no product, 8 = no Rold extraction
 __device__ __forceinline__ void panel_piece(const ResJob& jb, int p, int ti, int tj, const float* T, float* As, float* Bs,
                                             float (*Ds)[RB + 1]) {
   const int n = jb.n, tp = p >> 1, pr0 = (p & 1) * RB, p0 = p * RB;
@@ -182,8 +200,16 @@ __device__ __forceinline__ void panel_piece(const ResJob& jb, int p, int ti, int
   const int col0 = (row_stored ? tj : ti) * TS;
   __syncthreads();   // staging may still be in use
   const float* dinv = sc_dinv(jb, p);
-  for (int e = threadIdx.x; e < RB * RB; e += RES_THREADS) Ds[e >> 5][e & 31] = __ldcg(dinv + e);
-  if (row_stored) {
+  float* Dt = &Ds[0][0];   // D_p^-1 transposed, row stride 34: Dt[m * 34 + k] = D^-1[k][m] (8-byte aligned row pairs)
+  if (!(DBG & 1)) {
+    float dreg[4];   // all four loads in flight before the first shared-memory store
+#pragma unroll
+    for (int c = 0; c < 4; ++c) dreg[c] = __ldcg(dinv + threadIdx.x + c * RES_THREADS);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) Dt[(threadIdx.x & 31) * 34 + (threadIdx.x >> 5) + 8 * c] = dreg[c];
+  }
+  if (DBG & 8) {
+  } else if (row_stored) {
     for (int e = threadIdx.x; e < RB * TS; e += RES_THREADS) {
       const int k = e >> 6, c = e & 63;
       As[k * OPLD + c] = (k < nb && col0 + c < n) ? T[(pr0 + k) * TS + c] : 0.0f;
@@ -195,43 +221,48 @@ __device__ __forceinline__ void panel_piece(const ResJob& jb, int p, int ti, int
     }
   }
   __syncthreads();
-  // R piece: thread -> row k2, 8 consecutive columns
-  const int k2 = threadIdx.x >> 3, c8 = (threadIdx.x & 7) * 8;
-  float acc[8];
+  // R piece = D^-1 Rold as 32 outer products: thread -> rows 2 ty, 2 ty + 1, columns 4 tx .. 4 tx + 3.  Per m and warp
+  // one 8-byte broadcast load of the D^-1 column pair and one conflict-free 16-byte load of the Rold row: 6 shared-memory
+  // wavefronts for 8 FMAs (the row-per-thread mapping this replaces needed 17 and was bound by shared-memory bandwidth)
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  float acc[2][4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
 #pragma unroll 8
-  for (int m = 0; m < RB; ++m) {
-    const float dkm = Ds[k2][m];
-    const float4 x0 = *reinterpret_cast<const float4*>(As + m * OPLD + c8);
-    const float4 x1 = *reinterpret_cast<const float4*>(As + m * OPLD + c8 + 4);
-    acc[0] = fmaf(dkm, x0.x, acc[0]);
-    acc[1] = fmaf(dkm, x0.y, acc[1]);
-    acc[2] = fmaf(dkm, x0.z, acc[2]);
-    acc[3] = fmaf(dkm, x0.w, acc[3]);
-    acc[4] = fmaf(dkm, x1.x, acc[4]);
-    acc[5] = fmaf(dkm, x1.y, acc[5]);
-    acc[6] = fmaf(dkm, x1.z, acc[6]);
-    acc[7] = fmaf(dkm, x1.w, acc[7]);
+  for (int m = 0; m < ((DBG & 4) ? 0 : RB); ++m) {
+    const float2 d2 = *reinterpret_cast<const float2*>(Dt + m * 34 + 2 * ty);
+    const float4 x = *reinterpret_cast<const float4*>(As + m * OPLD + 4 * tx);
+    acc[0][0] = fmaf(d2.x, x.x, acc[0][0]);
+    acc[0][1] = fmaf(d2.x, x.y, acc[0][1]);
+    acc[0][2] = fmaf(d2.x, x.z, acc[0][2]);
+    acc[0][3] = fmaf(d2.x, x.w, acc[0][3]);
+    acc[1][0] = fmaf(d2.y, x.x, acc[1][0]);
+    acc[1][1] = fmaf(d2.y, x.y, acc[1][1]);
+    acc[1][2] = fmaf(d2.y, x.z, acc[1][2]);
+    acc[1][3] = fmaf(d2.y, x.w, acc[1][3]);
   }
-  float* rold = sc_rold(jb) + (size_t)k2 * jb.ldp + col0 + c8;
-  float* rr = sc_r(jb) + (size_t)k2 * jb.ldp + col0 + c8;
-  if (col0 + c8 < jb.ldp) {   // ldp is a multiple of 4 and >= n: whole float4s, columns in [n, ldp) receive zeros
-    const float4 o0 = *reinterpret_cast<const float4*>(As + k2 * OPLD + c8);
-    __stcg(reinterpret_cast<float4*>(rold), o0);
-    __stcg(reinterpret_cast<float4*>(rr), make_float4(acc[0], acc[1], acc[2], acc[3]));
+  if (DBG & 2) {
+    if (acc[0][0] + acc[1][3] + acc[0][1] + acc[0][2] + acc[0][3] + acc[1][0] + acc[1][1] + acc[1][2] == 12345.0f) sc_rold(jb)[0] = acc[0][3];
+    return;
   }
-  if (col0 + c8 + 4 < jb.ldp) {
-    const float4 o1 = *reinterpret_cast<const float4*>(As + k2 * OPLD + c8 + 4);
-    __stcg(reinterpret_cast<float4*>(rold + 4), o1);
-    __stcg(reinterpret_cast<float4*>(rr + 4), make_float4(acc[4], acc[5], acc[6], acc[7]));
+  if (col0 + 4 * tx < jb.ldp) {   // ldp is a multiple of 4 and >= n: whole float4s, columns in [n, ldp) receive zeros
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int k2 = 2 * ty + i;
+      const float4 o = *reinterpret_cast<const float4*>(As + k2 * OPLD + 4 * tx);
+      __stcg(reinterpret_cast<float4*>(sc_rold(jb) + (size_t)k2 * jb.ldp + col0 + 4 * tx), o);
+      __stcg(reinterpret_cast<float4*>(sc_r(jb) + (size_t)k2 * jb.ldp + col0 + 4 * tx),
+             make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+    }
   }
   (void)Bs;
 }
 
 // operand pieces of one tile update, fetched into registers (issued before the previous tile is computed)
 struct OpRegs {
-  float4 a[2], b[2];
+  float4 a[2], b[2], c[2];   // c: R for the tile's ROW range (pivot-column tiles only: M_ip = -sigma_i R_i^T)
 };
 __device__ __forceinline__ void fetch_ops(const ResJob& jb, int p, int ti, int tj, OpRegs& o) {
   const int n = jb.n, p0 = p * RB;
@@ -252,20 +283,24 @@ __device__ __forceinline__ void fetch_ops(const ResJob& jb, int p, int ti, int t
     if (gj < n && !(gj >= p0 && gj < p0 + RB)) vb = __ldcg(reinterpret_cast<const float4*>(rr + (size_t)k * jb.ldp + gj));
     o.a[h] = va;
     o.b[h] = vb;
+    if (tj == (p >> 1) && ti != tj)   // off-diagonal tile of the pivot's tile column (its rows are never pivot rows)
+      o.c[h] = gi < n ? __ldcg(reinterpret_cast<const float4*>(rr + (size_t)k * jb.ldp + gi)) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
-__device__ __forceinline__ void stage_ops(const OpRegs& o, float* As, float* Bs) {
+__device__ __forceinline__ void stage_ops(const OpRegs& o, float* As, float* Bs, float* Cs, bool with_c) {
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int e = threadIdx.x + h * RES_THREADS;
     const int k = e >> 4, c = (e & 15) * 4;
     *reinterpret_cast<float4*>(As + k * OPLD + c) = o.a[h];
     *reinterpret_cast<float4*>(Bs + k * OPLD + c) = o.b[h];
+    if (with_c) *reinterpret_cast<float4*>(Cs + k * OPLD + c) = o.c[h];
   }
 }
 
 // M_ij -= sigma_i Rold_i^T R_j on the resident tile; pivot rows / columns / block replaced (kfac.cu "Symmetry")
-__device__ __forceinline__ void update_tile(const ResJob& jb, int p, int ti, int tj, float* T, const float* As, const float* Bs) {
+__device__ __forceinline__ void update_tile(const ResJob& jb, int p, int ti, int tj, float* T, const float* As, const float* Bs,
+                                            const float* Cs) {
   const int n = jb.n, p0 = p * RB, tp = p >> 1;
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
   float acc[4][4];
@@ -274,10 +309,15 @@ __device__ __forceinline__ void update_tile(const ResJob& jb, int p, int ti, int
     const float4 t4 = *reinterpret_cast<const float4*>(T + (4 * ty + q) * TS + 4 * tx);
     acc[q][0] = t4.x; acc[q][1] = t4.y; acc[q][2] = t4.z; acc[q][3] = t4.w;
   }
-#pragma unroll 8
+  float4 a_nxt = *reinterpret_cast<const float4*>(As + 4 * ty);
+  float4 b_nxt = *reinterpret_cast<const float4*>(Bs + 4 * tx);
+#pragma unroll
   for (int k = 0; k < RB; ++k) {
-    const float4 a4 = *reinterpret_cast<const float4*>(As + k * OPLD + 4 * ty);
-    const float4 b4 = *reinterpret_cast<const float4*>(Bs + k * OPLD + 4 * tx);
+    const float4 a4 = a_nxt, b4 = b_nxt;
+    if (k + 1 < RB) {   // the next k's operands are in flight while this k's 16 FMAs issue
+      a_nxt = *reinterpret_cast<const float4*>(As + (k + 1) * OPLD + 4 * ty);
+      b_nxt = *reinterpret_cast<const float4*>(Bs + (k + 1) * OPLD + 4 * tx);
+    }
     const float a[4] = {a4.x, a4.y, a4.z, a4.w};
     const float b[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
@@ -287,7 +327,7 @@ __device__ __forceinline__ void update_tile(const ResJob& jb, int p, int ti, int
   }
   if (ti == tp || tj == tp) {
     const float* dinv = sc_dinv(jb, p);
-    const float* rr = sc_r(jb);
+    const float* Ri = ti == tj ? Bs : Cs;   // R for this tile's row range (diagonal tile: its own column piece)
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int gi = ti * TS + 4 * ty + q;
@@ -303,7 +343,7 @@ __device__ __forceinline__ void update_tile(const ResJob& jb, int p, int ti, int
         else if (ip)
           v = Bs[(gi - p0) * OPLD + 4 * tx + r];                       // M_pj = R_j (its column is not a pivot column)
         else {
-          const float x = __ldcg(rr + (size_t)(gj - p0) * jb.ldp + gi);   // M_ip = -sigma_i R_i^T
+          const float x = Ri[(gj - p0) * OPLD + 4 * ty + q];              // M_ip = -sigma_i R_i^T
           v = gi < p0 ? x : -x;
         }
         acc[q][r] = v;
@@ -363,7 +403,8 @@ __global__ void __launch_bounds__(RES_THREADS, 1) inv_resident_kernel(const __gr
   float* stage = smem;                  // operand pieces / D^-1 / transposition buffer
   float* As = stage;
   float* Bs = stage + RB * OPLD;
-  float (*Ds)[RB + 1] = reinterpret_cast<float (*)[RB + 1]>(stage + 2 * RB * OPLD);
+  float* Cs = stage + 2 * RB * OPLD;
+  float (*Ds)[RB + 1] = reinterpret_cast<float (*)[RB + 1]>(stage + 3 * RB * OPLD);
   float* tiles = smem + STAGE_FLOATS;
   unsigned int epoch = 0;
   const bool owner = cta >= ND;
@@ -417,9 +458,16 @@ __global__ void __launch_bounds__(RES_THREADS, 1) inv_resident_kernel(const __gr
       const int ti = s_ti[s], tj = s_tj[s];
       const float dv = __ldcg(a.damp + jb.damp_index);
       float* T = tiles + (size_t)s * TILE_FLOATS;
-      for (int e = threadIdx.x; e < TILE_FLOATS; e += RES_THREADS) {
-        const int gi = ti * TS + (e >> 6), gj = tj * TS + (e & 63);
-        T[e] = (gi < jb.n && gj < jb.n) ? prep_value(jb, gi, gj, debias, dv) : 0.0f;
+      for (int e0 = threadIdx.x; e0 < TILE_FLOATS; e0 += 4 * RES_THREADS) {
+        float pv[4];   // four pairs of loads in flight before the first shared-memory store
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int e = e0 + c * RES_THREADS;
+          const int gi = ti * TS + (e >> 6), gj = tj * TS + (e & 63);
+          pv[c] = (gi < jb.n && gj < jb.n) ? prep_value(jb, gi, gj, debias, dv) : 0.0f;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) T[e0 + c * RES_THREADS] = pv[c];
       }
       __syncthreads();
       publish_pair(jb, 0, ti, tj, T);     // blocks (0, 1) and (1, 1) for the look-ahead of step 0
@@ -432,7 +480,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) inv_resident_kernel(const __gr
       const int y = e >> 5, x = e & 31;
       Ds[y][x] = (y < nb && x < nb) ? prep_value(jb, y, x, debias, dv) : (y == x ? 1.0f : 0.0f);
     }
-    invert32(Ds, reinterpret_cast<float (*)[RB + 1]>(tiles) + 3 * RB);
+    invert32(Ds, tiles + 3 * RB * (RB + 1));
     float* dinv = sc_dinv(jb, 0);
     for (int e = threadIdx.x; e < RB * RB; e += RES_THREADS) __stcg(dinv + e, Ds[e >> 5][e & 31]);
   }
@@ -457,12 +505,21 @@ __global__ void __launch_bounds__(RES_THREADS, 1) inv_resident_kernel(const __gr
         float (*Rs)[RB + 1] = Qs + RB;
         const float* pq = sc_pq(jb, p);
         const float* qq = sc_qq(jb, p);
-        for (int e = threadIdx.x; e < RB * RB; e += RES_THREADS) {
-          Ps[e >> 5][e & 31] = __ldcg(pq + e);
-          Qs[e >> 5][e & 31] = __ldcg(qq + e);
+        const int x = threadIdx.x & 31, w = threadIdx.x >> 5;
+        {
+          float pr[4], qr[4];   // eight loads in flight
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            pr[c] = __ldcg(pq + threadIdx.x + c * RES_THREADS);
+            qr[c] = __ldcg(qq + threadIdx.x + c * RES_THREADS);
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            Ps[w + 8 * c][x] = pr[c];
+            Qs[w + 8 * c][x] = qr[c];
+          }
         }
         __syncthreads();
-        const int x = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {   // R_q = D_p^-1 M_pq
           const int y = w + 8 * c;
@@ -484,7 +541,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) inv_resident_kernel(const __gr
         __syncthreads();
 #pragma unroll
         for (int c = 0; c < 4; ++c) Ds[w + 8 * c][x] = v[c];
-        invert32(Ds, Rs + RB);
+        invert32(Ds, tiles + 3 * RB * (RB + 1));
         float* dinv = sc_dinv(jb, p + 1);
         for (int e = threadIdx.x; e < RB * RB; e += RES_THREADS) __stcg(dinv + e, Ds[e >> 5][e & 31]);
       }
@@ -524,11 +581,11 @@ __global__ void __launch_bounds__(RES_THREADS, 1) inv_resident_kernel(const __gr
         const int ti = s_ti[s], tj = s_tj[s];
         float* T = tiles + (size_t)s * TILE_FLOATS;
         __syncthreads();                 // the previous tile is done with the staging buffers
-        stage_ops(regs, As, Bs);
+        stage_ops(regs, As, Bs, Cs, tj == (p >> 1) && ti != tj);
         __syncthreads();
         const int sn = next_active(s + 1);
         if (sn < a.slots && !(a.debug & 2)) fetch_ops(s_jobs[s_job[sn]], p, s_ti[sn], s_tj[sn], regs);
-        update_tile(jb, p, ti, tj, T, As, Bs);
+        update_tile(jb, p, ti, tj, T, As, Bs, Cs);
         __syncthreads();
         if (sn < a.slots && (a.debug & 2)) fetch_ops(s_jobs[s_job[sn]], p, s_ti[sn], s_tj[sn], regs);
         publish_pair(jb, p + 1, ti, tj, T);    // for the look-ahead of step p + 1
@@ -602,12 +659,14 @@ int spd_inverse_resident(const InvJob* h_jobs, int num_jobs, const Sched* sched,
   int slots = ceil_div(total, owners);
   if (slots < 2) slots = 2;   // the look-ahead CTAs use the tile area for five 32 x 33 blocks
   const size_t smem = ((size_t)STAGE_FLOATS + (size_t)slots * TILE_FLOATS) * sizeof(float);
-  if (slots > 16 || smem > (size_t)RES_SMEM_LIMIT) return -1;
-  static size_t configured = 0;
-  if (smem > configured) {
-    ACX_CUDA(cudaFuncSetAttribute(inv_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RES_SMEM_LIMIT));
-    configured = RES_SMEM_LIMIT;
+  static int dyn_limit = -1;
+  if (dyn_limit < 0) {
+    cudaFuncAttributes fa;
+    ACX_CUDA(cudaFuncGetAttributes(&fa, inv_resident_kernel));
+    dyn_limit = RES_SMEM_TOTAL - (int)fa.sharedSizeBytes;   // the ownership / job tables are static shared memory
+    ACX_CUDA(cudaFuncSetAttribute(inv_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_limit));
   }
+  if (slots > 16 || smem > (size_t)dyn_limit) return -1;
   a.num_jobs = num_jobs;
   a.steps = ceil_div(nmax, RB);
   a.slots = slots;

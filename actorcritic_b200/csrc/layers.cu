@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(1024) loss_grad_kernel(const float* __restrict
                                                         const int32_t* __restrict__ fisher_labels,
                                                         const float* __restrict__ fisher_eps, uint64_t seed,
                                                         const Sched* __restrict__ sched, int n_rows, int num_actions, float beta, float value_weight,
-                                                        float* __restrict__ dheads, float* __restrict__ scalars,
+                                                        float policy_weight, float* __restrict__ dheads, float* __restrict__ scalars,
                                                         int want_fisher) {
   __shared__ float red[3][32];
   const uint64_t step = sched ? sched->gs : 0ull;
@@ -255,7 +255,8 @@ __global__ void __launch_bounds__(1024) loss_grad_kernel(const float* __restrict
     for (int a = 0; a < num_actions; ++a) {
       const float lp = z[a] - lse;
       const float p = expf(lp);
-      d_true[a] = -(adv * inv_n) * ((a == act ? 1.0f : 0.0f) - p) + (beta * inv_n) * p * (lp + ent);
+      const float dz = -(adv * inv_n) * ((a == act ? 1.0f : 0.0f) - p) + (beta * inv_n) * p * (lp + ent);
+      d_true[a] = policy_weight == 1.0f ? dz : policy_weight * dz;   // objectives.py:31-54: the policy loss on its own / switched off
       if (want_fisher) d_fish[a] = p - (a == yhat ? 1.0f : 0.0f);
     }
     d_true[num_actions] = -value_weight * (tg - v) * inv_n;
@@ -742,11 +743,11 @@ int heads_fwd(const Planes& act4, const float* vpol, const float* vval, int rows
 }
 int loss_grad(const float* logits, const float* values, const uint8_t* actions, const float* targets, const int32_t* fl,
               const float* fe, uint64_t seed, const Sched* sched, int n_rows, int num_actions, float beta, float vw, float* dheads,
-              float* scalars, int want_fisher, cudaStream_t st) {
+              float* scalars, int want_fisher, cudaStream_t st, float pw) {
   // one row per thread up to 1024 rows (the serial exp / log chains of a row are the kernel's latency)
   const int threads = n_rows >= 1024 ? 1024 : (n_rows + 31) / 32 * 32;
   loss_grad_kernel<<<1, threads, 0, st>>>(logits, values, actions, targets, fl, fe, seed, sched, n_rows, num_actions, beta, vw,
-                                          dheads, scalars, want_fisher);
+                                          pw, dheads, scalars, want_fisher);
   ACX_LAUNCH_CHECK();
   return 0;
 }
@@ -875,3 +876,11 @@ int sample_actions(const float* logits, const float* uniform, uint64_t seed, uin
 }
 
 }  // namespace acx
+
+extern "C" int acx_sample_actions(const float* d_logits, const float* d_uniform, uint64_t seed, uint64_t step, int rows,
+                                  int num_actions, int greedy, int32_t* d_actions, void* stream) {
+  ACX_CHECK(d_logits && d_actions, "null argument");
+  ACX_CHECK(rows > 0 && num_actions >= 1 && num_actions <= 1024, "rows / num_actions out of range");
+  return acx::sample_actions(d_logits, d_uniform, seed, step, rows, num_actions, greedy, d_actions,
+                             reinterpret_cast<cudaStream_t>(stream));
+}

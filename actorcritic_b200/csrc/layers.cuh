@@ -32,7 +32,7 @@ int heads_fwd(const Planes& act4, const float* vpol, const float* vval, int rows
               cudaStream_t st);
 int loss_grad(const float* logits, const float* values, const uint8_t* actions, const float* targets, const int32_t* fl,
               const float* fe, uint64_t seed, const Sched* sched, int n_rows, int num_actions, float beta, float vw, float* dheads,
-              float* scalars, int want_fisher, cudaStream_t st);
+              float* scalars, int want_fisher, cudaStream_t st, float pw = 1.0f);
 int heads_bwd(const float* dheads, const float* vpol, const float* vval, const Planes& act4, int n_rows, int rows_bwd,
               int num_actions, const Planes& dpre4, float* gpol, float* gval, cudaStream_t st);
 int heads_gfactor(const float* dheads_fisher, int n_rows, int num_actions, float* g_pol, float* g_val, cudaStream_t st);
@@ -111,7 +111,8 @@ int kfac_step(float* params, float* velocity, const float* precon, size_t count,
 int momentum_clip_step(float* params, float* accum, const float* grads, size_t count, const float* sq_partials, int num_partials,
                        float lr, float momentum, float clip_norm, float* out_scalars, cudaStream_t st);
 int rmsprop_clip_step(float* params, float* ms, const float* grads, size_t count, const float* sq_partials, int num_partials,
-                      const Sched* sched, float decay, float epsilon, float clip_norm, float* out_scalars, cudaStream_t st);
+                      const Sched* sched, float decay, float epsilon, float clip_norm, float* out_scalars, cudaStream_t st,
+                      float lr_value = 0.0f);
 int fill_f32(float* p, size_t count, float v, cudaStream_t st);
 int scale_f32(float* p, size_t count, float v, cudaStream_t st);
 

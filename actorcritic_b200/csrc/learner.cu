@@ -139,6 +139,8 @@ struct acx_learner {
   int lvl_fwd, lvl_bwd, lvl_fisher, lvl_factor, lvl_precon, act_planes, grad_planes;
   // optional stage timing (CUDA events on the launching stream)
   bool profiling = false;
+  float policy_weight = 1.0f, value_weight = 0.0f;   // acx_learner_set_loss_weights (value_weight is set from cfg at create)
+  int loss_variant = 0;                   // 0 = the configured weights; other values key separate CUDA graphs
   bool external_ema = false;              // acx_learner_set_external_ema: phase 2 leaves statistics scaling + EMA to acx_learner_ema
   int defer_request = 0;                  // acx_learner_defer_input_factors: mask for the next phase 1
   int deferred = 0;                       // what the last phase 1 actually left to phase 2
@@ -825,7 +827,7 @@ static int issue_phase1(acx_learner* l, const int32_t* fisher_labels, const floa
   // targets use the bootstrap tower's values = rows [N, N+E) (envs/atari/model.py:116,126-127)
   ACX_TRY(returns_launch(l->rewards, l->terminals, l->values, l->values + N, l->cfg.gamma, E, T, l->targets, l->adv, st));
   ACX_TRY(loss_grad(l->logits, l->values, l->actions, l->targets, fisher_labels, fisher_eps, l->cfg.seed, l->sched, N, A,
-                    l->cfg.entropy_beta, l->cfg.value_loss_weight, l->dheads, l->bscalars, fisher ? 1 : 0, st));
+                    l->cfg.entropy_beta, l->value_weight, l->dheads, l->bscalars, fisher ? 1 : 0, st, l->policy_weight));
   ACX_TRY(heads_bwd(l->dheads, l->params + l->L[4].off, l->params + l->L[5].off, l->act4, N, RB, A, l->dpre4,
                     l->grads + l->L[4].off, l->grads + l->L[5].off, st));
   const Planes flat3 = with_ld(l->act3, 49 * c3);
@@ -1151,6 +1153,7 @@ acx_learner_t* acx_learner_create(const acx_learner_config_t* cfg, void* d_arena
   register_buffers(l);
   l->gs = 0;
   l->ncov = 0;
+  l->value_weight = cfg->value_loss_weight;
   l->inverses_valid = false;
   l->act_calls = 0;
   l->lanes = cfg->num_lanes <= 0 ? kMaxLanes : std::min(cfg->num_lanes, kMaxLanes);
@@ -1347,10 +1350,27 @@ int acx_learner_phase1(acx_learner_t* l, const int32_t* d_fisher_labels, const f
   const bool fisher = l->cfg.acktr != 0 && l->gs >= l->cfg.num_cold_updates;
   l->deferred = fisher ? resolve_deferred(l) : 0;
   l->defer_request = 0;   // one-shot
-  GraphKey key = {1, (fisher ? 1 : 0) | (l->deferred << 1), d_fisher_labels, d_fisher_eps};
+  GraphKey key = {1, (fisher ? 1 : 0) | (l->deferred << 1) | (l->loss_variant << 8), d_fisher_labels, d_fisher_eps};
   const int r = run_cached(l, key, st, [&]() { return issue_phase1(l, d_fisher_labels, d_fisher_eps, st); });
   l->a_ready_valid = r == 0 && fisher && l->lanes > 1 && !l->profiling;
   return r;
+}
+
+int acx_learner_set_loss_weights(acx_learner_t* l, float policy_weight, float value_weight) {
+  ACX_CHECK(l, "null learner");
+  l->policy_weight = policy_weight;
+  l->value_weight = value_weight;
+  // every distinct pair replays its own captured graphs (kernel arguments are baked into a graph)
+  static std::vector<std::pair<float, float>> seen;
+  int id = -1;
+  for (size_t i = 0; i < seen.size(); ++i)
+    if (seen[i].first == policy_weight && seen[i].second == value_weight) id = (int)i;
+  if (id < 0) {
+    seen.push_back(std::make_pair(policy_weight, value_weight));
+    id = (int)seen.size() - 1;
+  }
+  l->loss_variant = (policy_weight == 1.0f && value_weight == l->cfg.value_loss_weight) ? 0 : 1 + id;
+  return 0;
 }
 
 int acx_learner_update_plan(const acx_learner_t* l, int* has_factors, int* will_invert) {

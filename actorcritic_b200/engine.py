@@ -503,6 +503,45 @@ class Engine:
             return self.fetch_scalars_async()
         return self.fetch_scalars()
 
+    def update_separate(self, batch, policy_spec, baseline_spec, step_increments=(1, 1)):
+        """objectives.py:31-54 `optimize_separate`: the gradient of the policy loss and the gradient of the baseline loss,
+        both at the current parameters, each applied by its own optimizer (nn.standalone_spec records) with its own slots.
+        `step_increments`: how often each `minimize` was handed the global step (it increments it once).  A2C-type
+        engines only (acktr=False)."""
+        from . import ops
+        if self.config.acktr:
+            raise _lib.AcxError("optimize_separate runs on a first-order engine (acktr=False)")
+        if batch is not None:
+            self.load_batch(batch["observations"], batch["bootstrap_observations"], batch["actions"], batch["rewards"],
+                            batch["terminals"])
+        if getattr(self, "_sep_slots", None) is None:
+            def slot(kind):   # TF-1: RMSProp's `ms` starts at one, Momentum's accumulator at zero
+                fill = torch.ones if kind == "rmsprop" else torch.zeros
+                return fill(self.num_params, dtype=torch.float32, device=self.device)
+            self._sep_slots = [slot(policy_spec[0]), slot(baseline_spec[0])]
+        params = self.buffer("params", torch.float32)[: self.num_params]
+        grads = self.buffer("grads", torch.float32)[: self.num_params]
+        gs = self.global_step
+        with self.on_stream(), torch.cuda.stream(self.stream):
+            _lib.check(self.lib.acx_learner_set_loss_weights(self._h, 1.0, 0.0))
+            _lib.check(self.lib.acx_learner_phase1(self._h, None, None, self._stream()))
+            g_policy = grads.clone()
+            scalars = self.bucket[-4:].clone()
+            _lib.check(self.lib.acx_learner_set_loss_weights(self._h, 0.0, 1.0))
+            _lib.check(self.lib.acx_learner_phase1(self._h, None, None, self._stream()))
+            _lib.check(self.lib.acx_learner_set_loss_weights(self._h, 1.0, float(self.config.value_loss_weight)))
+            norms = []
+            for (kind, lr, hp, clip), g, slot_t in ((policy_spec, g_policy, self._sep_slots[0]),
+                                                    (baseline_spec, grads, self._sep_slots[1])):
+                step_fn = ops.clip_rmsprop_step if kind == "rmsprop" else ops.clip_momentum_step
+                norms.append(step_fn(params, slot_t, g, lr.value_at(gs), clip_norm=clip, **hp))
+            _lib.check(self.lib.acx_learner_refresh_weights(self._h, self._stream()))
+        self.set_state(gs + int(sum(step_increments)), 0, False)
+        vals = scalars.cpu().tolist()
+        return dict(policy_loss=vals[0], baseline_loss=vals[1], mean_entropy=vals[2], loss=vals[0] + vals[1],
+                    clip_coeff=float("nan"), fisher_norm=float("nan"), grad_norm=float(norms[0]),
+                    learning_rate=float(policy_spec[1].value_at(gs)), baseline_grad_norm=float(norms[1]))
+
     def fetch_scalars_async(self):
         """Start the device-to-host copy of this update's scalars (losses, clip coefficient, learning rate ...) and return
         a handle; `handle.result()` waits for THAT copy only, so the host can enqueue the next update before it reads the

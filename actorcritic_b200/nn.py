@@ -1,6 +1,10 @@
-"""actorcritic/nn.py: parameter initialisers, `linear_decay`, `ClipGlobalNormOptimizer`, plus the two
-`tf.train` optimizers the example constructs (a2c_acktr.py:240,250).  The layer functions of the reference
-(`conv2d`, `fully_connected`, `flatten`) only exist fused inside the engine's kernels."""
+"""actorcritic/nn.py: parameter initialisers, the layer functions `fully_connected`, `conv2d`, `flatten`, `linear_decay`,
+`ClipGlobalNormOptimizer`, plus the two `tf.train` optimizers the example constructs (a2c_acktr.py:240,250).
+
+The layer functions take and return fp32 CUDA tensors; the products run on libacx's tcgen05 GEMM (`acx_gemm`, operands split
+into three bf16 planes and accumulated over six plane pairs: fp32-class results) or on the implicit-GEMM convolution
+(`acx_conv`).  AtariModel's train step does not call them - it runs the same layers fused inside the learner engine - they
+exist so that other `ActorCriticModel` subclasses can be built the way the reference builds them (model.py:107-133)."""
 import numpy as np
 
 
@@ -29,17 +33,77 @@ def conv2d_params(num_input_channels, num_filters, filter_extent, dtype=np.float
     return _orthogonal(shape, gain, rng).astype(dtype), np.zeros(num_filters, dtype)
 
 
-def _fused_only(name):
-    def fn(*a, **k):
-        raise NotImplementedError("nn.%s is fused into the engine's forward kernels (see envs.atari.model.AtariModel); it "
-                                  "has no stand-alone op in this framework" % name)
-    fn.__name__ = name
-    return fn
+def _device_f32(x, device=None):
+    import torch
+    if not isinstance(x, torch.Tensor):
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    if device is None and not x.is_cuda:
+        from . import _lib
+        raise _lib.AcxError("nn layers operate on CUDA tensors (libacx has no CPU fallback)")
+    if device is not None and x.device != device:
+        x = x.to(device)
+    return x.float() if x.dtype != torch.float32 else x
 
 
-fully_connected = _fused_only("fully_connected")
-conv2d = _fused_only("conv2d")
-flatten = _fused_only("flatten")
+# noinspection PyShadowingBuiltins
+def fully_connected(input, params):
+    """nn.py:37-52: `input @ weights + bias` for input [batch, in] (fp32 CUDA tensor), weights [in, out], bias [out]."""
+    from . import ops
+    x = _device_f32(input)
+    weights, bias = params
+    w = _device_f32(weights, x.device)
+    b = _device_f32(bias, x.device).contiguous()
+    if x.dim() != 2 or w.dim() != 2 or x.shape[1] != w.shape[0] or b.numel() != w.shape[1]:
+        raise ValueError("fully_connected: input %s, weights %s, bias %s" % (tuple(x.shape), tuple(w.shape), tuple(b.shape)))
+    m, k = x.shape
+    n = w.shape[1]
+    out, _ = ops.gemm(ops.split_planes(x, 3), ops.split_planes(w.t().contiguous(), 3), m, n, k, pairs=ops.PAIRS[6], bias=b)
+    return out
+
+
+# noinspection PyShadowingBuiltins
+def conv2d(input, params, stride, padding, impl="gemm"):
+    """nn.py:88-110: tf.nn.conv2d(input, weights, (1, stride, stride, 1), padding, 'NHWC') + bias - cross-correlation, HWIO
+    weights.  input [batch, h, w, cin] (fp32 CUDA tensor).  impl="gemm": patch rows in (kh, kw, cin) order x the reshaped
+    kernel on `acx_gemm`; impl="implicit": `acx_conv` (no patch matrix; VALID, kernel a multiple of the stride,
+    stride * cin == 64 - the 4x4/2 and 3x3/1 layers of envs/atari/model.py:180-199)."""
+    import torch
+    from . import ops
+    x = _device_f32(input)
+    weights, bias = params
+    w = _device_f32(weights, x.device)
+    b = _device_f32(bias, x.device).contiguous()
+    if x.dim() != 4 or w.dim() != 4 or w.shape[0] != w.shape[1] or w.shape[2] != x.shape[3]:
+        raise ValueError("conv2d: input %s (NHWC), weights %s (HWIO)" % (tuple(x.shape), tuple(w.shape)))
+    k, cin, cout = int(w.shape[0]), int(w.shape[2]), int(w.shape[3])
+    s = int(stride)
+    if padding == "SAME":     # TensorFlow's rule: out = ceil(in / stride), the odd pixel of padding goes to the bottom / right
+        pads = []
+        for size in (x.shape[2], x.shape[1]):
+            total = max((-(-size // s) - 1) * s + k - size, 0)
+            pads += [total // 2, total - total // 2]
+        x = torch.nn.functional.pad(x, (0, 0) + tuple(pads))
+    elif padding != "VALID":
+        raise ValueError("padding must be 'VALID' or 'SAME'")
+    n, h, wd, _ = x.shape
+    oh, ow = (h - k) // s + 1, (wd - k) // s + 1
+    if impl == "implicit":
+        if h != wd:
+            raise ValueError("the implicit-GEMM convolution takes square inputs")
+        geom = (int(h), cin, k, s, int(oh), cout)
+        xp = [p.view(n, h, wd, cin) for p in ops.split_planes(x.reshape(-1, cin), 3)]
+        wt = ops.split_planes(w.reshape(k * k * cin, cout).t().contiguous(), 3)
+        planes = ops.conv(xp, wt, geom, n, bias=b, relu=False, pairs=ops.PAIRS[6], out_planes=3)
+        return planes[0].float() + planes[1].float() + planes[2].float()
+    patches = x.unfold(1, k, s).unfold(2, k, s).permute(0, 1, 2, 4, 5, 3).reshape(n * oh * ow, k * k * cin)
+    out = fully_connected(patches, (w.reshape(k * k * cin, cout), b))
+    return out.view(n, oh, ow, cout)
+
+
+# noinspection PyShadowingBuiltins
+def flatten(input):
+    """nn.py:114-126: [batch, d1, ..., dn] -> [batch, d1 * ... * dn] (row-major: (h, w, c) order for NHWC)."""
+    return input.reshape(input.shape[0], -1)
 
 
 class LinearDecay:
@@ -73,6 +137,22 @@ class RMSPropOptimizer:
         if momentum != 0.0:
             raise NotImplementedError("RMSProp momentum is not on the hot path")
         self.learning_rate, self.decay, self.epsilon = learning_rate, decay, epsilon
+
+
+def standalone_spec(optimizer):
+    """(kind, learning-rate LinearDecay, hyper-parameters, clip norm) of an optimizer applied on its own
+    (objectives.py:31-54 `optimize_separate`): [ClipGlobalNorm](RMSProp | Momentum)."""
+    clip = 3.4e38
+    if isinstance(optimizer, ClipGlobalNormOptimizer):
+        clip, optimizer = float(optimizer.clip_norm), optimizer.optimizer
+    lr = optimizer.learning_rate if hasattr(optimizer, "learning_rate") else None
+    if not isinstance(lr, LinearDecay):
+        lr = LinearDecay(float(lr), float(lr), None, 1.0)
+    if isinstance(optimizer, RMSPropOptimizer):
+        return "rmsprop", lr, dict(decay=float(optimizer.decay), epsilon=float(optimizer.epsilon)), clip
+    if isinstance(optimizer, MomentumOptimizer):
+        return "momentum", lr, dict(momentum=float(optimizer.momentum)), clip
+    raise TypeError("unsupported optimizer %r" % (optimizer,))
 
 
 class ClipGlobalNormOptimizer:

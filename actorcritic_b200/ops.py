@@ -233,3 +233,34 @@ def conv_dgrad_weights(w, geom):
     _lib.check(_lib.load().acx_conv_dgrad_weights(_ptr(w.contiguous().float()), hw_in, c_in, k, stride, hw_out, c_out, arr, ld,
                                                   _stream()))
     return planes
+
+
+def sample_actions(logits, uniform=None, seed=0, step=0, greedy=False):
+    """acx_sample_actions: DistributionPolicy.sample / mode (policies.py:86-87) on device logits [rows, A] -> int32 [rows]."""
+    _need_cuda(logits, uniform)
+    logits = logits.contiguous().float()
+    rows, num_actions = logits.shape
+    actions = torch.empty(rows, dtype=torch.int32, device=logits.device)
+    _lib.check(_lib.load().acx_sample_actions(_ptr(logits), _ptr(uniform), ctypes.c_uint64(seed), ctypes.c_uint64(step), rows,
+                                              num_actions, int(bool(greedy)), _ptr(actions), _stream()))
+    return actions
+
+
+def clip_rmsprop_step(params, ms, grads, lr, decay=0.9, epsilon=1e-10, clip_norm=3.4e38):
+    """acx_clip_rmsprop_step on flat fp32 CUDA vectors, in place; returns the gradient's global norm (device scalar)."""
+    _need_cuda(params, ms, grads)
+    scratch = torch.empty(297, dtype=torch.float32, device=params.device)
+    _lib.check(_lib.load().acx_clip_rmsprop_step(_ptr(params), _ptr(ms), _ptr(grads), ctypes.c_size_t(params.numel()), float(lr),
+                                                 float(decay), float(epsilon), float(clip_norm), _ptr(scratch),
+                                                 ctypes.c_void_p(scratch.data_ptr() + 296 * 4), _stream()))
+    return scratch[296]
+
+
+def clip_momentum_step(params, accum, grads, lr, momentum=0.9, clip_norm=3.4e38):
+    """acx_clip_momentum_step on flat fp32 CUDA vectors, in place; returns the gradient's global norm (device scalar)."""
+    _need_cuda(params, accum, grads)
+    scratch = torch.empty(297, dtype=torch.float32, device=params.device)
+    _lib.check(_lib.load().acx_clip_momentum_step(_ptr(params), _ptr(accum), _ptr(grads), ctypes.c_size_t(params.numel()),
+                                                  float(lr), float(momentum), float(clip_norm), _ptr(scratch),
+                                                  ctypes.c_void_p(scratch.data_ptr() + 296 * 4), _stream()))
+    return scratch[296]

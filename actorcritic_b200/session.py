@@ -111,7 +111,8 @@ class Session:
     def _evaluate_plain(self, flist, feed):
         kinds = {f.kind for f in flist}
         results = {}
-        train_kinds = {"optimize", "policy_loss", "baseline_loss", "mean_entropy", "loss", "clip_coeff", "learning_rate"}
+        train_kinds = {"optimize", "optimize_separate", "policy_loss", "baseline_loss", "mean_entropy", "loss", "clip_coeff",
+                       "learning_rate"}
         act_kinds = {"sample", "mode", "logits", "value"}
         if kinds & train_kinds:
             objective = next(f.owner for f in flist if f.kind in train_kinds and f.owner is not None)
@@ -120,8 +121,15 @@ class Session:
             batch = model._train_feed(feed)
             engine.load_batch(*batch)
             injected = self.fisher_injection or (None, None)
-            engine.phase1(injected[0], injected[1])
-            if "optimize" in kinds:
+            if "optimize_separate" in kinds:       # objectives.py:31-54: two optimizers, two backward passes
+                sep = objective._separate
+                inc = (int(sep["policy_global_step"] is not None), int(sep["baseline_global_step"] is not None))
+                scal = engine.update_separate(None, sep["policy"], sep["baseline"], inc)
+            else:
+                engine.phase1(injected[0], injected[1])
+            if "optimize_separate" in kinds:
+                pass
+            elif "optimize" in kinds:
                 engine.allreduce(self.group)
                 engine.phase2()
                 scal = engine.fetch_scalars()
@@ -133,7 +141,7 @@ class Session:
             for f in flist:
                 if f.kind in _SCALARS:
                     results[id(f)] = np.float32(scal[_SCALARS[f.kind]])
-                elif f.kind == "optimize":
+                elif f.kind in ("optimize", "optimize_separate"):
                     results[id(f)] = None
             if "bootstrap_values" in kinds:
                 n = engine.rows

@@ -289,6 +289,22 @@ int64_t acx_learner_global_step(const acx_learner_t* l);
  * inverses have been computed at least once (kfac initialises them to zero). */
 int acx_learner_set_state(acx_learner_t* l, int64_t global_step, int64_t num_cov_updates, int inverses_valid, void* stream);
 int acx_learner_get_state(const acx_learner_t* l, int64_t* global_step, int64_t* num_cov_updates, int* inverses_valid);
+/* objectives.py:31-54 `optimize_separate` (two optimizers, two backward passes): the next acx_learner_phase1 calls
+ * differentiate  policy_weight * policy_loss + value_weight * baseline_loss  instead of the configured
+ * policy_loss + value_loss_weight * baseline_loss  ((1, 0) = the policy loss on its own, (0, 1) = the baseline loss). */
+int acx_learner_set_loss_weights(acx_learner_t* l, float policy_weight, float value_weight);
+/* the optimizer steps of nn.py:185-189 on caller-owned device vectors (count floats each): the global-norm clip
+ * g * clip / max(|g|, clip), then RMSProp (TF-1: ms <- decay ms + (1 - decay) g^2; theta -= lr g / sqrt(ms + eps), ms starts
+ * at one) or momentum (acc <- momentum acc + g; theta -= lr acc).  d_scratch: 296 floats; d_out_norm (may be NULL)
+ * receives |g|. */
+int acx_clip_rmsprop_step(float* d_params, float* d_ms, const float* d_grads, size_t count, float lr, float decay,
+                          float epsilon, float clip_norm, float* d_scratch, float* d_out_norm, void* stream);
+int acx_clip_momentum_step(float* d_params, float* d_accum, const float* d_grads, size_t count, float lr, float momentum,
+                           float clip_norm, float* d_scratch, float* d_out_norm, void* stream);
+/* DistributionPolicy.sample / mode (policies.py:86-87) on device logits [rows, num_actions]: inverse-CDF categorical draw
+ * from softmax(logits) with the given uniforms d_uniform [rows] (NULL = Philox(seed, step, row)), or argmax (greedy). */
+int acx_sample_actions(const float* d_logits, const float* d_uniform, uint64_t seed, uint64_t step, int rows,
+                       int num_actions, int greedy, int32_t* d_actions, void* stream);
 /* forward only on `rows` observations already in d_obs (uint8 [rows,84,84,4]) -> logits [rows,A],
  * values [rows]; then categorical sample (u in [0,1) given, or Philox) / argmax.  Replaces
  * ActorCriticModel.sample_actions / select_max_actions (model.py:135-169). */
