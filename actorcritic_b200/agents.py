@@ -58,23 +58,27 @@ class MultiEnvAgent(Agent):
         if self._observations is None:
             self._observations = env.reset()                                       # uint8 [E,84,84,4] on the device
         obs = torch.empty((e_count, t_count, 84, 84, 4), dtype=torch.uint8, device=dev)
-        actions = torch.empty((e_count, t_count), dtype=torch.uint8, device=dev)
-        rewards = torch.empty((e_count, t_count), dtype=torch.float32, device=dev)
-        terminals = torch.empty((e_count, t_count), dtype=torch.uint8, device=dev)
         engine = self._model.engine
         if engine is None:
             engine = self._model._build_engine(session, e_count, t_count, None)
+        # per-step results are gathered step-major in buffers the agent keeps (stable pointers: the library replays each
+        # acting step as a CUDA graph) and turned batch-major once at the end - one small kernel per tensor instead of one
+        # per tensor and step
+        if getattr(self, "_step_actions", None) is None or self._step_actions.shape != (t_count, e_count):
+            self._step_actions = torch.empty((t_count, e_count), dtype=torch.int32, device=dev)
         cur = self._observations
-        info_steps = []
+        reward_steps, terminal_steps, info_steps = [], [], []
         for t in range(t_count):
             obs[:, t].copy_(cur)
-            a = engine.act(cur)                                                    # int32 [E]
+            a = engine.act(cur, out=self._step_actions[t])                         # int32 [E]
             cur, r, term = env.step_device(a)
-            actions[:, t] = a.to(torch.uint8)
-            rewards[:, t] = r
-            terminals[:, t] = term
+            reward_steps.append(r)
+            terminal_steps.append(term)
             # environments hosted on the CPU (envs.atari.raw_env.RawFrameMultiEnv) report their info dicts per step
             info_steps.append(list(getattr(env, "last_infos", None) or [{} for _ in range(e_count)]))
+        actions = self._step_actions.t().to(torch.uint8)
+        rewards = torch.stack(reward_steps, dim=1).to(torch.float32)
+        terminals = torch.stack(terminal_steps, dim=1)
         cur = cur.clone()              # the environment reuses its stack buffer; the tuple must not alias it
         self._observations = cur
         return obs, actions, rewards, terminals.bool(), cur, transpose_list(info_steps)

@@ -78,9 +78,13 @@ def state_to_arrays(engine):
     return out
 
 
-def arrays_to_state(engine, arrays):
-    """Inverse of `state_to_arrays`: writes the arrays into the engine (device) and re-derives the operand planes."""
+def arrays_to_state(engine, arrays, params_only=False):
+    """Inverse of `state_to_arrays`: writes the arrays into the engine (device) and re-derives the operand planes.
+    params_only: an acting-only engine (built by sample_actions before the first train step) takes the variables and the
+    step counter; the optimizer state waits in `model._pending_checkpoint` for the learner engine."""
     cfg = engine.config
+    if hasattr(engine, "wait_pending_ema"):
+        engine.wait_pending_ema()   # a split exchange's EMA may still be writing the running sums
     if int(arrays["meta/num_actions"]) != cfg.num_actions or int(arrays["meta/conv3_filters"]) != cfg.conv3_filters:
         raise ValueError("checkpoint is for %d actions / conv3=%d, the model has %d / %d" % (
             int(arrays["meta/num_actions"]), int(arrays["meta/conv3_filters"]), cfg.num_actions, cfg.conv3_filters))
@@ -94,7 +98,8 @@ def arrays_to_state(engine, arrays):
     dev = engine.device
     with engine.on_stream():
         engine.buffer("params", torch.float32)[:engine.num_params].copy_(torch.from_numpy(flat("")).to(dev))
-        same_kind = bool(arrays["meta/acktr"]) == bool(cfg.acktr) and not bool(arrays.get("meta/params_only", False))
+        same_kind = (bool(arrays["meta/acktr"]) == bool(cfg.acktr) and not bool(arrays.get("meta/params_only", False))
+                     and not params_only)
         if same_kind:                       # slots only carry over between runs of the same optimizer
             if cfg.acktr:
                 engine.buffer("velocity", torch.float32)[:engine.num_params].copy_(
@@ -162,11 +167,17 @@ class Saver:
         directory = os.path.dirname(os.path.abspath(path))
         os.makedirs(directory, exist_ok=True)
         engine = self._model.engine
-        if engine is not None:
+        pending = getattr(self._model, "_pending_checkpoint", None)
+        if engine is not None and not getattr(engine, "is_learner", True) and pending is not None:
+            # only an acting engine exists so far (restore -> interact -> save, e.g. the reference's Ctrl-C handler during the
+            # first rollout): the restored optimizer state is still waiting for the learner engine - save THAT, with the
+            # engine's current variables
+            arrays = dict(pending)
+            arrays.update(engine.get_params())
+        elif engine is not None:
             arrays = state_to_arrays(engine)
         else:
             # no train step has run yet (the learner is built from the first feed): the variables are all there is
-            pending = getattr(self._model, "_pending_checkpoint", None)
             arrays = dict(pending) if pending is not None else dict(self._model.get_variables())
             if pending is None:
                 arrays.update({"global_step": np.int64(0), "kfac/num_cov_updates": np.int64(0),
@@ -196,11 +207,16 @@ class Saver:
             arrays = {k: z[k] for k in z.files}
         if int(arrays.get("meta/format_version", -1)) != FORMAT_VERSION:
             raise ValueError("%s: unknown checkpoint format" % save_path)
+        from . import session as _session
+        _session.restore_global_steps(int(arrays["global_step"]))      # `session.run(global_step)` right after a restore
         engine = self._model.engine
-        if engine is None:
-            # the learner is built lazily from the first feed: keep the arrays and apply them then
+        if engine is None or not getattr(engine, "is_learner", True):
+            # the learner is built lazily from the first train feed: keep the arrays and apply them then; the variables
+            # (and the step counter) go to the model / the acting-only engine now
             self._model._pending_checkpoint = arrays
             self._model.set_variables({k: arrays[k] for k in eng.param_shapes(self._model.num_actions,
                                                                                self._model.conv3_num_filters)})
+            if engine is not None:
+                arrays_to_state(engine, arrays, params_only=True)
             return
         arrays_to_state(engine, arrays)

@@ -674,41 +674,50 @@ __global__ void weight_planes_kernel(const WeightPlanesArgs a) {
 }
 
 // categorical sample (inverse CDF on softmax(logits)) or argmax  (policies.py:86-87)
-__global__ void sample_actions_kernel(const float* __restrict__ logits, const float* __restrict__ uniform, uint64_t seed,
-                                      uint64_t step, int rows, int num_actions, int greedy, int32_t* __restrict__ actions) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= rows) return;
-  const float* z = logits + (size_t)r * num_actions;
-  float mx = z[0];
-  int arg = 0;
-  for (int a = 1; a < num_actions; ++a)
-    if (z[a] > mx) {
-      mx = z[a];
-      arg = a;
+__global__ void __launch_bounds__(1024) sample_actions_kernel(const float* __restrict__ logits, const float* __restrict__ uniform,
+                                                             uint64_t seed, uint64_t step, unsigned long long* step_counter,
+                                                             int rows, int num_actions, int greedy,
+                                                             int32_t* __restrict__ actions) {
+  // one CTA (rows are looped): with a device-resident call counter the Philox step is read from it and advanced here, so
+  // a captured CUDA graph of an acting step stays valid from call to call
+  if (step_counter) step = *step_counter;
+  for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+    const float* z = logits + (size_t)r * num_actions;
+    float mx = z[0];
+    int arg = 0;
+    for (int a = 1; a < num_actions; ++a)
+      if (z[a] > mx) {
+        mx = z[a];
+        arg = a;
+      }
+    if (greedy) {
+      actions[r] = arg;
+      continue;
     }
-  if (greedy) {
-    actions[r] = arg;
-    return;
-  }
-  float se = 0.f;
-  for (int a = 0; a < num_actions; ++a) se += expf(z[a] - mx);
-  float u;
-  if (uniform)
-    u = uniform[r];
-  else
-    u = u01(philox4x32(make_uint4((uint32_t)r, (uint32_t)step, (uint32_t)(step >> 32), 0x41435421u),
-                       make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)))
-                .x);
-  float cum = 0.f;
-  int pick = num_actions - 1;
-  for (int a = 0; a < num_actions; ++a) {
-    cum += expf(z[a] - mx) / se;
-    if (u < cum) {
-      pick = a;
-      break;
+    float se = 0.f;
+    for (int a = 0; a < num_actions; ++a) se += expf(z[a] - mx);
+    float u;
+    if (uniform)
+      u = uniform[r];
+    else
+      u = u01(philox4x32(make_uint4((uint32_t)r, (uint32_t)step, (uint32_t)(step >> 32), 0x41435421u),
+                         make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)))
+                  .x);
+    float cum = 0.f;
+    int pick = num_actions - 1;
+    for (int a = 0; a < num_actions; ++a) {
+      cum += expf(z[a] - mx) / se;
+      if (u < cum) {
+        pick = a;
+        break;
+      }
     }
+    actions[r] = pick;
   }
-  actions[r] = pick;
+  if (step_counter) {
+    __syncthreads();
+    if (threadIdx.x == 0) *step_counter = step + 1;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -869,8 +878,9 @@ int weight_planes(const float* const* w, const int* k_rows, const int* c_cols, b
   return 0;
 }
 int sample_actions(const float* logits, const float* uniform, uint64_t seed, uint64_t step, int rows, int num_actions, int greedy,
-                   int32_t* actions, cudaStream_t st) {
-  sample_actions_kernel<<<ceil_div(rows, 128), 128, 0, st>>>(logits, uniform, seed, step, rows, num_actions, greedy, actions);
+                   int32_t* actions, cudaStream_t st, unsigned long long* step_counter) {
+  const int threads = rows >= 1024 ? 1024 : (rows + 31) / 32 * 32;
+  sample_actions_kernel<<<1, threads, 0, st>>>(logits, uniform, seed, step, step_counter, rows, num_actions, greedy, actions);
   ACX_LAUNCH_CHECK();
   return 0;
 }

@@ -46,7 +46,7 @@ int transpose_split(const float* in, int k_rows, int c_cols, bf16* p0, bf16* p1,
 int weight_planes(const float* const* w, const int* k_rows, const int* c_cols, bf16* const (*t)[3], const int* ld_t,
                   bf16* const (*n)[3], const int* ld_n, int num_layers, cudaStream_t st);
 int sample_actions(const float* logits, const float* uniform, uint64_t seed, uint64_t step, int rows, int num_actions, int greedy,
-                   int32_t* actions, cudaStream_t st);
+                   int32_t* actions, cudaStream_t st, unsigned long long* step_counter = nullptr);
 int split_planes(const float* in, int ld_in, int rows, int cols, float scale, bf16* p0, bf16* p1, bf16* p2, int num_planes,
                  int ld_out, cudaStream_t st);
 

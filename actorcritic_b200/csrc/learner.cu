@@ -64,11 +64,17 @@ struct GraphKey {
   int phase, variant;
   const void* p0;
   const void* p1;
+  const void* p2 = nullptr;
+  const void* p3 = nullptr;
+  const void* p4 = nullptr;
   bool operator<(const GraphKey& o) const {
     if (phase != o.phase) return phase < o.phase;
     if (variant != o.variant) return variant < o.variant;
     if (p0 != o.p0) return p0 < o.p0;
-    return p1 < o.p1;
+    if (p1 != o.p1) return p1 < o.p1;
+    if (p2 != o.p2) return p2 < o.p2;
+    if (p3 != o.p3) return p3 < o.p3;
+    return p4 < o.p4;
   }
 };
 struct GraphEntry {
@@ -104,6 +110,7 @@ struct acx_learner {
   InvJob h_jobs[12];
   InvJob* d_jobs;
   unsigned int* inv_bar;     // grid-barrier counter of the persistent inverse kernel
+  unsigned long long* act_counter;   // device-resident number of acting calls (Philox step of sample_actions)
   PreconJob h_pjobs[6];
   PreconJob* d_pjobs;
   int num_pjobs, pjobs_max_d;
@@ -268,6 +275,7 @@ static size_t layout(acx_learner* l, uint8_t* base) {
   l->d_jobs = reinterpret_cast<InvJob*>(ar.take(12 * sizeof(InvJob)));
   l->d_pjobs = reinterpret_cast<PreconJob*>(ar.take(6 * sizeof(PreconJob)));
   l->inv_bar = reinterpret_cast<unsigned int*>(ar.take(256));
+  l->act_counter = reinterpret_cast<unsigned long long*>(ar.take(256));
   l->precon_w = f32(P);
   for (int i = 0; i < 6; ++i) {
     const int d = l->L[i].K + 1, c = l->L[i].C;
@@ -1449,14 +1457,22 @@ int acx_learner_act(acx_learner_t* l, const uint8_t* d_obs, int rows, const floa
   ACX_CHECK(l && d_obs && d_actions, "null argument");
   ACX_CHECK(rows > 0 && rows <= l->R, "rows must be in [1, num_envs * num_steps + num_envs]");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  int r = forward(l, d_obs, rows, lane_of(l, 0, st), nullptr, nullptr, false);
-  if (r) return r;
-  r = sample_actions(l->logits, d_uniform, l->cfg.seed, l->act_calls++, rows, l->A, greedy, d_actions, st);
-  if (r) return r;
-  if (d_logits)
-    ACX_CUDA(cudaMemcpyAsync(d_logits, l->logits, (size_t)rows * l->A * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  if (d_values) ACX_CUDA(cudaMemcpyAsync(d_values, l->values, (size_t)rows * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  return 0;
+  // One acting step = ~8 small launches (32 rows: every kernel sits on the launch-latency floor).  With stable buffers
+  // (the usual rollout loop: the environment's stack buffer in, the agent's action buffer out) the step is captured once
+  // per pointer set and replayed as ONE graph launch; the call counter that seeds Philox lives on the device.
+  auto issue = [&]() -> int {
+    int r = forward(l, d_obs, rows, lane_of(l, 0, st), nullptr, nullptr, false);
+    if (r) return r;
+    r = sample_actions(l->logits, d_uniform, l->cfg.seed, 0, rows, l->A, greedy, d_actions, st, l->act_counter);
+    if (r) return r;
+    if (d_logits)
+      ACX_CUDA(cudaMemcpyAsync(d_logits, l->logits, (size_t)rows * l->A * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (d_values) ACX_CUDA(cudaMemcpyAsync(d_values, l->values, (size_t)rows * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+  };
+  l->act_calls++;
+  GraphKey key = {3, (greedy ? 1 : 0) | (rows << 1), d_obs, d_actions, d_uniform, d_logits, d_values};
+  return run_cached(l, key, st, issue);
 }
 
 }  // extern "C"

@@ -197,6 +197,7 @@ class Engine:
             self._h = self.lib.acx_learner_create(ctypes.byref(self._c), ctypes.c_void_p(base), ctypes.c_size_t(nbytes))
             if not self._h:
                 raise _lib.AcxError(self.lib.acx_last_error().decode())
+        self.is_learner = True          # AtariModel marks the engine it builds for acting only (no objective yet)
         self.num_params = int(self.lib.acx_learner_num_params(self._h))
         self.num_envs, self.num_steps = config.num_envs, config.num_steps
         self.rows = config.num_envs * config.num_steps
@@ -300,9 +301,17 @@ class Engine:
         with self.on_stream():
             _lib.check(self.lib.acx_learner_refresh_weights(self._h, self._stream()))
 
+    def wait_pending_ema(self):
+        """A split exchange's EMA (Engine._split_exchange) may still be reading the statistics / writing the running sums on
+        its own stream: order the engine's stream after it before anything else touches them."""
+        if getattr(self, "_ema_pending", False):
+            self.stream.wait_event(self._ema_done)
+            self._ema_pending = False
+
     def state_dict(self):
         """Everything `tf.train.Saver` would save for this path (a2c_acktr.py:101): parameters, optimiser slots,
         K-FAC running sums, stored inverses and the schedule counters - as host tensors."""
+        self.wait_pending_ema()
         torch.cuda.synchronize(self.device)
         sd = {k: self.buffer(k, torch.float32).cpu().clone() for k in ("params", "velocity", "accum", "factor_sums",
                                                                        "inverses")}
@@ -311,9 +320,7 @@ class Engine:
         return sd
 
     def load_state_dict(self, sd):
-        if getattr(self, "_ema_pending", False):   # a split exchange's EMA may still be writing the running sums
-            self.stream.wait_event(self._ema_done)
-            self._ema_pending = False
+        self.wait_pending_ema()
         for k in ("params", "velocity", "accum", "factor_sums", "inverses"):
             self.buffer(k, torch.float32).copy_(sd[k].to(self.device))
         self.refresh_derived()
@@ -362,6 +369,8 @@ class Engine:
         """Start the asynchronous host-to-device copy of a batch (pinned host tensors) into one of two staging slots on
         a dedicated copy stream; `update(staged=True)` consumes the slots in order.  At most two batches in flight."""
         self._ensure_staging()
+        if self._stage_put - self._stage_get >= 2:
+            raise _lib.AcxError("stage_batch: both staging slots hold batches that update(staged=True) has not consumed yet")
         k = self._stage_put % 2
         slot = self._staging[k]
         with torch.cuda.stream(self._copy_stream):
@@ -398,9 +407,7 @@ class Engine:
         if defer_factors and self.config.world_size == 1:
             _lib.check(self.lib.acx_learner_defer_input_factors(self._h, -1))
         with self.on_stream():
-            if getattr(self, "_ema_pending", False):     # the previous update's EMA (split exchange) still reads the statistics
-                self.stream.wait_event(self._ema_done)
-                self._ema_pending = False
+            self.wait_pending_ema()      # the previous update's EMA (split exchange) still reads the statistics
             _lib.check(self.lib.acx_learner_phase1(self._h, fl, fe, self._stream()))
 
     def allreduce(self, group=None, overlap=None):
@@ -577,16 +584,27 @@ class Engine:
         return dict(zip(self.STAGES, [float(x) for x in arr]))
 
     # ------------------------------------------------------------------ acting
-    def act(self, observations, uniform=None, greedy=False, want_logits=False):
+    def act(self, observations, uniform=None, greedy=False, want_logits=False, out=None):
         """Forward + categorical sample / argmax on [rows,84,84,4] uint8 device observations
-        (ActorCriticModel.sample_actions / select_max_actions, model.py:135-169)."""
+        (ActorCriticModel.sample_actions / select_max_actions, model.py:135-169).
+
+        The outputs live in buffers owned by the engine (one set per row count) unless `out` (int32 [rows]) is given: they
+        are valid until the next `act` call with the same row count.  Stable input / output pointers let the library replay
+        the whole acting step as one CUDA graph (acx_learner_act)."""
         if not observations.is_cuda:
             observations = observations.to(self.device, non_blocking=True)
         observations = observations.contiguous()
         rows = observations.shape[0]
-        actions = torch.empty(rows, dtype=torch.int32, device=self.device)
-        logits = torch.empty((rows, self.config.num_actions), dtype=torch.float32, device=self.device) if want_logits else None
-        values = torch.empty(rows, dtype=torch.float32, device=self.device) if want_logits else None
+        bufs = getattr(self, "_act_bufs", None)
+        if bufs is None:
+            bufs = self._act_bufs = {}
+        if rows not in bufs:
+            bufs[rows] = (torch.empty(rows, dtype=torch.int32, device=self.device),
+                          torch.empty((rows, self.config.num_actions), dtype=torch.float32, device=self.device),
+                          torch.empty(rows, dtype=torch.float32, device=self.device))
+        actions, logits, values = bufs[rows]
+        if out is not None:
+            actions = out
         with self.on_stream():
             _lib.check(self.lib.acx_learner_act(
                 self._h, ctypes.c_void_p(observations.data_ptr()), rows,

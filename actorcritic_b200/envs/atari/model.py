@@ -85,10 +85,19 @@ class AtariModel(ActorCriticModel):
                       value_loss_weight=objective._baseline_loss_weight)
             if objective._optimizer is not None:
                 kw.update(objective._optimizer.engine_overrides())
+            elif getattr(objective, "_separate", None) is not None:
+                kw.update(acktr=False)      # optimize_separate: first-order engine, the optimizers run on its gradients
         else:
             kw.update(acktr=False)
         if session.group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             kw.setdefault("world_size", torch.distributed.get_world_size(session.group))
+        if "seed" not in self.engine_options:
+            # every rank of a data-parallel job (and every model without a fixed seed) gets its own Philox stream for action
+            # sampling and Fisher sampling
+            base = self.random_seed if self.random_seed is not None else int.from_bytes(__import__("os").urandom(4), "little")
+            rank = (torch.distributed.get_rank(session.group)
+                    if torch.distributed.is_available() and torch.distributed.is_initialized() else 0)
+            kw["seed"] = (int(base) * 1000003 + rank) & 0x7FFFFFFFFFFFFFFF
         kw.update(self.engine_options)
         cfg = eng.EngineConfig(**kw)
         old = self._engine
@@ -104,6 +113,7 @@ class AtariModel(ActorCriticModel):
             if objective is not None:
                 self._pending_checkpoint = None      # an acting-only engine keeps it for the learner built later
             checkpoint.arrays_to_state(e, pending)
+        e.is_learner = objective is not None
         self._engine = e
         self._engine_key = (num_envs, num_steps, id(objective) if objective is not None else None)
         if objective is not None and objective._global_step is not None:

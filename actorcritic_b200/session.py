@@ -37,13 +37,29 @@ class Fetch:
         return "<Fetch %s>" % self.name
 
 
+_GLOBAL_STEPS = []    # weak references to every GlobalStep (checkpoint restore before the learner engine exists)
+
+
+def restore_global_steps(value):
+    """checkpoint.Saver.restore: global steps that are not bound to an engine yet report the restored value (the
+    reference reads `session.run(global_step)` right after `saver.restore`, a2c_acktr.py:100-104)."""
+    for ref in list(_GLOBAL_STEPS):
+        gs = ref()
+        if gs is None:
+            _GLOBAL_STEPS.remove(ref)
+        elif gs._engine is None or not getattr(gs._engine, "is_learner", True):
+            gs._pending = int(value)
+
+
 class GlobalStep(Fetch):
     """`tf.train.get_or_create_global_step()` stand-in: fetchable; the value lives in the engine."""
 
     def __init__(self):
+        import weakref
         super().__init__("global_step", None)
         self._engine = None
         self._pending = 0
+        _GLOBAL_STEPS.append(weakref.ref(self))
 
     def bind(self, engine):
         self._engine = engine

@@ -32,12 +32,23 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures of conv_tc_kernel at 2N = 1280
-# samples, conv3_filters = 32: default precision (2 planes, 3 pairs: profiles/r1_prof_conv_dgrad2_raw.txt, 43.92 MB read +
-# 17.14 MB written) and the former 3-plane / 6-pair preset 5 (profiles/r1_prof_conv_dgrad3_6pairs_raw.txt and the round's
-# earlier conv2 capture)
-CONV_DGRAD_TRAFFIC = {"conv2": 61060000}
-CONV_DGRAD_TRAFFIC_6PAIRS = {"conv2": 115638528, "conv3": 19423488}
+
+
+def ncu_traffic(raw_file):
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes, one launch) parsed from a committed `ncu --page raw` text dump
+    under profiles/ (None if the file or the metrics are missing)."""
+    path = os.path.join(ROOT, "profiles", raw_file)
+    if not os.path.exists(path):
+        return None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total, seen = 0.0, 0
+    for line in open(path):
+        f = line.split()
+        if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and f[1] in unit:
+            total += float(f[2].replace(",", "")) * unit[f[1]]
+            seen += 1
+    return int(total) if seen == 2 else None
+
 METRIC = "acktr_learner_env_steps_per_sec"
 UNIT = "env-steps/s"
 FRAMESKIP = 4   # a2c_acktr.py:195 - emulator frames per env-step
@@ -58,6 +69,7 @@ def parse():
     ap.add_argument("--lanes", type=int, default=0, help="concurrent lanes inside an update (0 = library default 3, 1 = serial)")
     ap.add_argument("--invert-every", type=int, default=10, help="diagnostic only: the reference uses 10 (a2c_acktr.py:245)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the conv3 = 64 and A2C 16 x 5 extra keys")
     ap.add_argument("--cpu-budget-s", type=float, default=15.0)
     return ap.parse_args()
 
@@ -75,6 +87,20 @@ def workload_name(args, world):
     return "ACKTR Nature-CNN, %d envs x %d steps per GPU (%d x %d total), conv3=%d, 4 actions, factor EMA every update, " \
            "inverse refresh every 10 updates" % (args.envs_per_gpu, args.num_steps, args.envs_per_gpu * world,
                                                  args.num_steps, args.conv3)
+
+
+def make_config(args, world):
+    """The `config` object of the JSON line - identical for the native and the reference arm."""
+    return {"workload": workload_name(args, world), "envs_per_gpu": args.envs_per_gpu, "num_steps": args.num_steps,
+            "total_envs": args.envs_per_gpu * world, "conv3": args.conv3, "num_actions": 4,
+            "schedule": "steady state after the cold phase: covariance EMA every update, inverse refresh every %d" % args.invert_every,
+            "inputs": "synthetic uint8 observations (iid uniform), 8 batches rotated (152 MB per GPU > 126 MB L2)",
+            "parallelism": "dp%d: environments sharded over the GPUs, one all-reduce of gradients + factor statistics per update" % world}
+
+
+def update_gflop(c3):
+    """Algorithmic GFLOP of one 32 x 20 learner update, symmetric-half counting."""
+    return {32: 78.2, 64: 100.2}.get(c3)
 
 
 def algorithmic_flops(n_rows, e_rows, c3, num_actions=4):
@@ -144,30 +170,33 @@ def make_batches(count, envs, steps, seed):
     return [synth.rollout(seed + i, envs, steps, 4, terminal_prob=0.05, obs_kind="uniform") for i in range(count)]
 
 
-def cpu_reference_rate(args, budget_s, warmup=1, steps=None):
+def cpu_reference_rate(args, budget_s, warmup=1, steps=None, envs=None, c3=None, acktr=True, t_count=None):
     """The CPU restatement of the reference's update (oracle/learner.py, fp32, reference_cost=True: materialised
     patch matrices, [E,T,T] discount matrices, two towers, separate Fisher backward, dense inverses) on a bounded
-    sample: whole 32x20 updates in the steady state (covariances every update, inverses every 10th)."""
+    sample: whole updates in the steady state (ACKTR: covariances every update, inverses every 10th; A2C: RMSProp)."""
     import torch
     import synth
     from oracle import kfac as K
     from oracle import learner as OL
     from oracle import network as onet
     torch.set_num_threads(os.cpu_count() or 1)
-    envs, t_count = args.envs_per_gpu, args.num_steps
-    params = onet.init_params(4, args.conv3, 0)
-    o = OL.OracleLearner(params, 4, args.conv3, acktr=True, cfg=K.KfacConfig(decay_steps=1e7 / (envs * t_count)),
-                         dtype=torch.float32, reference_cost=True)
-    o.global_step = 30
+    envs = args.envs_per_gpu if envs is None else envs
+    t_count = args.num_steps if t_count is None else t_count
+    c3 = args.conv3 if c3 is None else c3
+    params = onet.init_params(4, c3, 0)
+    cfg = K.KfacConfig(decay_steps=1e7 / (envs * t_count)) if acktr else OL.A2CConfig(decay_steps=1e7 / (envs * t_count))
+    o = OL.OracleLearner(params, 4, c3, acktr=acktr, cfg=cfg, dtype=torch.float32, reference_cost=True)
     batch = synth.rollout(1, envs, t_count, 4)
     n = envs * t_count
     y_hat, eps = synth.fisher_samples(2, n)
-    # reach the first inverse refresh outside the timed sample (9 cheap "updates" would be the honest way, but each
-    # costs ~1 s; instead run the covariance + inverse update once directly)
-    info = o.compute(batch, y_hat, eps, need_fisher=True)
-    o.kfac.update_covs(info["new_a"], info["new_g"])
-    o.kfac.update_inverses()
-    o.global_step = 40
+    if acktr:
+        # reach the first inverse refresh outside the timed sample (9 cheap "updates" would be the honest way, but each
+        # costs ~1 s; instead run the covariance + inverse update once directly)
+        o.global_step = 30
+        info = o.compute(batch, y_hat, eps, need_fisher=True)
+        o.kfac.update_covs(info["new_a"], info["new_g"])
+        o.kfac.update_inverses()
+        o.global_step = 40
     for _ in range(warmup):
         o.update(batch, y_hat, eps)
     times = []
@@ -186,22 +215,27 @@ def cpu_reference_rate(args, budget_s, warmup=1, steps=None):
 
 
 def run_reference(args, rank, world):
+    """`--impl reference`: the reference's own CPU implementation of the path (its TensorFlow-1.x + tensorflow/kfac
+    dependencies are not installable offline, so: the oracle's reference-cost restatement, fp32 torch-CPU) on all host
+    threads of rank 0, on the native arm's workload: envs_per_gpu x n_gpus environments x num_steps, the same number of
+    warm-up and timed updates."""
     if rank != 0:
         return
-    budget_steps = max(1, args.steps)
-    r = cpu_reference_rate(args, budget_s=1e9, warmup=max(1, min(args.warmup, 3)), steps=min(budget_steps, 60))
-    n = args.envs_per_gpu * args.num_steps
+    warmup = max(3, args.warmup)
+    total_envs = args.envs_per_gpu * args.gpus
+    r = cpu_reference_rate(args, budget_s=1e9, warmup=warmup, steps=max(1, args.steps), envs=total_envs)
+    n = total_envs * args.num_steps
     line = {
         "impl": "reference", "metric": METRIC, "value": r["env_steps_per_sec"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": r["updates"], "warmup": max(1, min(args.warmup, 3)), "ms_per_step": r["sec_per_update"] * 1e3,
+        "steps": args.steps, "warmup": warmup, "ms_per_step": r["sec_per_update"] * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "updates_per_sec": 1.0 / r["sec_per_update"], "env_frames_per_sec": r["env_steps_per_sec"] * FRAMESKIP,
-        "config": {"workload": workload_name(args, args.gpus),
-                   "note": "CPU restatement of the reference's TF+kfac update (oracle/learner.py, fp32 torch-CPU); the "
-                           "reference itself needs TensorFlow 1.x + tensorflow/kfac, not installable offline"},
+        "config": make_config(args, args.gpus),
+        "note": "CPU restatement of the reference's TF+kfac update (oracle/learner.py, fp32 torch-CPU, reference_cost=True); the "
+                "reference itself needs TensorFlow 1.x + tensorflow/kfac, not installable offline (DESIGN.md section 2)",
         "cpu_baseline": {"value": r["env_steps_per_sec"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                          "sample": "%d whole %dx%d ACKTR updates (%d rows each), steady state incl. inverse refresh every 10"
-                                   % (r["updates"], args.envs_per_gpu, args.num_steps, n)},
+                                   % (r["updates"], total_envs, args.num_steps, n)},
         "e2e": {"value": r["env_steps_per_sec"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -380,7 +414,7 @@ def run_native(args, rank, world, local_rank):
     # K-PRE (BASELINE.json config 5): raw 210x160x3 frame pairs -> gray -> 84x84 -> frame-stack push, HBM bound
     pre = {}
     if rank == 0:
-        for pe in (64, 1024, 4096):
+        for pe in (64, 128, 256, 512, 1024, 2048, 4096):
             ra = torch.randint(0, 256, (pe, 210, 160, 3), dtype=torch.uint8, device=dev)
             rb = torch.randint(0, 256, (pe, 210, 160, 3), dtype=torch.uint8, device=dev)
             stk = torch.randint(0, 256, (pe, 84, 84, 4), dtype=torch.uint8, device=dev)
@@ -472,8 +506,19 @@ def run_native(args, rank, world, local_rank):
         "algorithmic_bytes_per_launch": k_rows * 256 * 2, "launch_ms": syrk_ms,
         "tensor": {"algorithmic_gflop_per_launch": syrk_flops / 1e9, "achieved_tflops": syrk_tflops,
                    "frac_of_burst_bf16_peak": syrk_tflops / peaks["tensor_burst"]}}
+    # the whole update against the tensor roofline: algorithmic GFLOP (symmetric-half counting) over the
+    # device-timed step; inside a long loop the sustained peak is the relevant denominator
+    per_gpu_gflop = update_gflop(c3) * n / 640.0 if update_gflop(c3) else None
+    update_block = None
+    if per_gpu_gflop:
+        ach = per_gpu_gflop / ms_step          # GFLOP / ms = TFLOP/s, per GPU
+        update_block = {"bound": "tensor", "algorithmic_gflop_per_update_per_gpu": per_gpu_gflop, "ms_per_step": ms_step,
+                        "achieved": ach, "unit": "TFLOP/s", "peak": peaks["tensor_sustained"], "frac": ach / peaks["tensor_sustained"],
+                        "frac_of_burst": ach / peaks["tensor_burst"],
+                        "note": "every launch of the update (78 at 32 x 20: 22 tensor-core kernels, HBM- and latency-bound helpers, "
+                                "the inverse refresh amortised over 10 updates) against the dense bf16 peak"}
     if dom is None:   # im2col route / unsupported conv3 width: the largest launch is the HBM-bound conv1 factor SYRK
-        roofline = dict(hbm_kernel, stage_ms=stage_ms)
+        roofline = dict(hbm_kernel, stage_ms=stage_ms, update=update_block)
     else:
         roofline = {"bound": "tensor",
                      "kernel": "conv_tc_kernel (conv.cu): %s input gradient in gather form, %d samples (true + Fisher rows), "
@@ -481,7 +526,8 @@ def run_native(args, rank, world, local_rank):
                      "achieved": dg[dom]["flops"] / (dg[dom]["ms"] * 1e-3) / 1e12, "peak": peaks["tensor_burst"], "unit": "TFLOP/s",
                      "frac": dg[dom]["flops"] / (dg[dom]["ms"] * 1e-3) / 1e12 / peaks["tensor_burst"],
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/r1_prof_conv_dgrad2_raw.txt)
-                     "traffic": (CONV_DGRAD_TRAFFIC_6PAIRS if npairs == 6 else CONV_DGRAD_TRAFFIC).get(dom),
+                     "traffic": ncu_traffic({("conv2", 3): "r1_prof_conv_dgrad2_raw.txt",
+                                             ("conv3", 6): "r1_prof_conv_dgrad3_6pairs_raw.txt"}.get((dom, npairs), "none")),
                      "algorithmic_gflop_per_launch": dg[dom]["flops"] / 1e9, "launch_ms": dg[dom]["ms"],
                      "issued_gflop_per_launch": dg[dom]["issued"] / 1e9,
                      "issued_tflops": dg[dom]["issued"] / (dg[dom]["ms"] * 1e-3) / 1e12,
@@ -494,6 +540,7 @@ def run_native(args, rank, world, local_rank):
                      "peak_source": peaks["source"] + ", dense bf16 (cuBLAS) burst",
                      "hbm_kernel": hbm_kernel,
                      "factor_syrk": factor_syrk,
+                     "update": update_block,
                      "stage_ms": stage_ms,
                      "stage_note": "stage times are taken with the lanes serialised (profiling mode); factor statistics are "
                                    "issued from inside the forward / backward stages",
@@ -504,12 +551,15 @@ def run_native(args, rank, world, local_rank):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16x2 planes (3 plane pairs), fp32 accumulate" if args.precision == 0 else "bf16 planes, precision preset %d" % args.precision,
         "data": "synthetic",
-        "updates_per_sec": 1e3 / ms_step, "env_frames_per_sec": value * FRAMESKIP,
-        "config": {"workload": workload_name(args, world), "precision": args.precision, "cuda_graphs": not args.no_graphs,
-                   "lanes": args.lanes if args.lanes > 0 else 3,
+        "updates_per_sec": 1e3 / ms_step,
+        # emulator frames per second of the whole loop on the device: T x (K-PRE + acting forward + sample) + one update
+        "env_frames_per_sec": total_envs * t_count * FRAMESKIP / ((ms_step + rollout_ms) * 1e-3),
+        "env_frames_per_sec_learner_only": value * FRAMESKIP,
+        "config": make_config(args, world),
+        "engine": {"precision": args.precision, "cuda_graphs": not args.no_graphs, "lanes": args.lanes if args.lanes > 0 else 3,
                    "conv": "conv2/conv3 input gradient in gather form on the tensor cores (no patch-gradient matrix, no col2im)" if args.conv_impl == 0 else "dgrad GEMM + col2im",
-                   "l2": "8 resident input batches rotated (152 MB > 126 MB L2); per-step intermediates ~0.9 GB, self-flushing",
-                   "parallelism": "dp%d (envs sharded, one NCCL all-reduce of grads+factor statistics per update)" % world},
+                   "inverse": "fp32 blocked Gauss-Jordan, all factor tiles resident in shared memory, one persistent kernel (kfac_inv.cu)",
+                   "l2": "8 resident input batches rotated (152 MB > 126 MB L2); per-step intermediates ~0.9 GB, self-flushing"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 64,
                 "ms_per_step": ms_e2e / args.steps,
                 "note": "Engine.stage_batch + Engine.update(staged=True, fetch='async'): pinned host -> staging slot on a copy stream "
@@ -527,6 +577,56 @@ def run_native(args, rank, world, local_rank):
         "env_steps_per_sec_with_rollout": total_envs * t_count / ((ms_step + rollout_ms) * 1e-3),
         "losses": scal,
     }
+    if rank == 0 and world == 1 and not args.no_extra:
+        # the other single-GPU configurations of BASELINE.json as extra keys (same timing rules, own CPU baseline):
+        # configs[2] at the class-default conv3 = 64 (the 3137 x 3137 factor) and configs[1] = A2C 16 x 5
+        del resident, host
+        torch.cuda.empty_cache()
+
+        def extra_line(cfg_x, label, cpu_kw):
+            ex = eng.Engine(cfg_x, dev)
+            ex.set_params(eng.orthogonal_init(4, cfg_x.conv3_filters, seed=0))
+            bx = make_batches(8, cfg_x.num_envs, cfg_x.num_steps, seed=77)
+            rx = [{k: torch.from_numpy(np.ascontiguousarray(b[k] if b[k].dtype != bool else b[k].astype(np.uint8))).to(dev)
+                   for k in keys} for b in bx]
+            if cfg_x.acktr:
+                ex.set_state(30, 0, False)
+            with torch.cuda.stream(ex.stream):
+                for i in range(23 + 3):
+                    ex.update(rx[i % 8], fetch=False)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for i in range(args.steps):
+                    ex.update(rx[i % 8], fetch=False)
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.steps
+            rows = cfg_x.num_envs * cfg_x.num_steps
+            out = {"workload": label, "ms_per_step": ms, "value": rows / (ms * 1e-3), "unit": UNIT, "steps": args.steps}
+            g = update_gflop(cfg_x.conv3_filters) if cfg_x.acktr else None
+            if g:
+                out["roofline_update"] = {"algorithmic_gflop": g * rows / 640.0, "achieved_tflops": g * rows / 640.0 / ms,
+                                          "frac": g * rows / 640.0 / ms / peaks["tensor_sustained"], "peak": peaks["tensor_sustained"]}
+            if not args.no_cpu_baseline:
+                rc = cpu_reference_rate(args, min(args.cpu_budget_s, 8.0), **cpu_kw)
+                out["cpu_baseline"] = {"value": rc["env_steps_per_sec"], "unit": UNIT, "cores": rc["cores"], "kind": "port",
+                                       "sample": "%d whole updates of the CPU restatement, %.3f s each" % (rc["updates"], rc["sec_per_update"])}
+            del ex, rx
+            torch.cuda.empty_cache()
+            return out
+
+        try:
+            line["acktr_conv3_64"] = extra_line(
+                eng.EngineConfig(num_envs=envs, num_steps=t_count, conv3_filters=64, seed=7),
+                "ACKTR Nature-CNN %d envs x %d steps, conv3 = 64 (class default: 3137 x 3137 fc4 input factor)" % (envs, t_count),
+                dict(c3=64))
+            line["a2c_16x5"] = extra_line(
+                eng.EngineConfig.a2c(16, 5, seed=7),
+                "A2C Nature-CNN (no K-FAC) 16 envs x 5 steps, conv3 = 64, RMSProp + global-norm clip (BASELINE.json configs[1])",
+                dict(envs=16, t_count=5, c3=64, acktr=False))
+        except Exception as exc:  # noqa: BLE001  (informational keys must not cost the bench line)
+            line["extra_error"] = repr(exc)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_rate(args, args.cpu_budget_s)

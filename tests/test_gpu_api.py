@@ -165,3 +165,166 @@ def test_summaries_written_like_the_reference_example(tmp_path):
         assert ev["scalars"] == {"model/policy_loss": np.float32(pl), "model/baseline_loss": np.float32(bl),
                                  "model/policy_entropy": np.float32(ent), "environment/episode_reward": np.float32(rew)}
     summary.reset_default_collection()
+
+
+# ------------------------------------------------------------------------------------------------ nn.* layer ops
+def test_nn_layer_ops_match_the_oracle_network():
+    """nn.conv2d / nn.flatten / nn.fully_connected (nn.py:37-52,88-126) on device tensors reproduce the oracle's Nature-CNN
+    forward (oracle/network.py, pinned to the reference's graph code by tests/golden/network.npz) layer by layer; the
+    implicit-GEMM route (`acx_conv`) agrees with the im2col route on the two layers it covers."""
+    from actorcritic_b200 import nn
+    params = onet.perturbed_params(4, 32, 5)
+    obs = synth.rollout(31, 3, 2, 4, obs_kind="sparse")["observations"].reshape(6, 84, 84, 4)
+    fwd = onet.forward(onet.to_torch(params), obs)
+    x = torch.from_numpy(obs).cuda().float() / 255.0                       # envs/atari/model.py:93
+    acts = {}
+    for name, stride in (("conv1", 4), ("conv2", 2), ("conv3", 1)):
+        y = nn.conv2d(x, (params[name + "/weights"], params[name + "/bias"]), stride, "VALID")
+        if name != "conv1":
+            y2 = nn.conv2d(x, (params[name + "/weights"], params[name + "/bias"]), stride, "VALID", impl="implicit")
+            assert LC.rel_err(y2.cpu().numpy(), y.cpu().numpy()) <= 2e-6
+        want = fwd[name]["pre"].numpy().reshape(tuple(y.shape))
+        assert LC.rel_err(y.cpu().numpy(), want) <= 1e-5, name
+        x = torch.relu(y)
+        acts[name] = x
+    flat = nn.flatten(x)
+    assert tuple(flat.shape) == (6, 49 * 32)
+    np.testing.assert_array_equal(flat.cpu().numpy(), acts["conv3"].cpu().numpy().reshape(6, -1))    # (h, w, c) order
+    h = torch.relu(nn.fully_connected(flat, (params["fc4/weights"], params["fc4/bias"])))
+    logits = nn.fully_connected(h, (params["fc_policy/weights"], params["fc_policy/bias"]))
+    value = nn.fully_connected(h, (params["fc_baseline/weights"], params["fc_baseline/bias"]))
+    assert LC.rel_err(logits.cpu().numpy(), fwd["logits"].numpy()) <= 1e-5
+    assert LC.rel_err(value.cpu().numpy()[:, 0], fwd["value"].numpy()) <= 1e-5
+
+
+def test_nn_conv2d_same_padding_and_odd_geometry():
+    """A geometry outside the Nature-CNN (5x5 / 3, 3 -> 10 channels, SAME and VALID) against torch's convolution in fp64."""
+    from actorcritic_b200 import nn
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((2, 17, 17, 3)).astype(np.float32)
+    w = (0.2 * rng.standard_normal((5, 5, 3, 10))).astype(np.float32)
+    b = rng.standard_normal(10).astype(np.float32)
+    xt = torch.from_numpy(x).double().permute(0, 3, 1, 2)
+    wt = torch.from_numpy(w).double().permute(3, 2, 0, 1)
+    for padding, pad in (("VALID", 0), ("SAME", None)):
+        got = nn.conv2d(torch.from_numpy(x).cuda(), (w, b), 3, padding).cpu().numpy()
+        if pad is None:      # TF SAME for 17 / stride 3 / k 5: out 6, total padding 3 -> (1, 2)
+            want = torch.nn.functional.conv2d(torch.nn.functional.pad(xt, (1, 2, 1, 2)), wt, torch.from_numpy(b).double(), stride=3)
+        else:
+            want = torch.nn.functional.conv2d(xt, wt, torch.from_numpy(b).double(), stride=3)
+        want = want.permute(0, 2, 3, 1).numpy()
+        assert got.shape == want.shape and LC.rel_err(got, want) <= 1e-5, padding
+
+
+def test_non_atari_model_built_from_nn_layers():
+    """An ActorCriticModel subclass for a Box observation space assembled from nn.* like the reference assembles AtariModel
+    (model.py:107-133, envs/atari/model.py:173-217): sample_actions / select_max_actions through Session.run."""
+    import actorcritic_b200 as ac
+    from actorcritic_b200 import nn, spaces
+    from actorcritic_b200.baselines import StateValueFunction
+    from actorcritic_b200.model import ActorCriticModel
+    from actorcritic_b200.policies import SoftmaxPolicy
+
+    class VectorModel(ActorCriticModel):
+        def __init__(self, observation_space, action_space, seed=0):
+            super().__init__(observation_space, action_space)
+            rng = np.random.default_rng(seed)
+            self.random_seed = seed
+            self.fc1 = nn.fully_connected_params(observation_space.shape[0], 24, rng=rng, gain=2 ** 0.5)
+            self.fc_policy = nn.fully_connected_params(24, action_space.n, rng=rng, gain=1.0)
+            self.fc_baseline = nn.fully_connected_params(24, 1, rng=rng, gain=1.0)
+            self._policy = SoftmaxPolicy(self, action_space.n)
+            self._baseline = StateValueFunction(self)
+
+        def _forward_device(self, observations):
+            h = torch.relu(nn.fully_connected(nn.flatten(observations.float()), self.fc1))
+            return nn.fully_connected(h, self.fc_policy), nn.fully_connected(h, self.fc_baseline)[:, 0]
+
+    observation_space = spaces.Box(low=-1.0, high=1.0, shape=(11,), dtype=np.float32)
+    model = VectorModel(observation_space, spaces.Discrete(5), seed=2)
+    assert model.observations_placeholder.dtype == np.float32 and model.observations_placeholder.shape == (None, None, 11)
+    obs = np.random.default_rng(1).uniform(-1, 1, (7, 1, 11)).astype(np.float32)
+    w1, b1 = model.fc1
+    h = np.maximum(obs.reshape(7, 11).astype(np.float64) @ w1.astype(np.float64) + b1, 0.0)
+    want_logits = h @ model.fc_policy[0].astype(np.float64) + model.fc_policy[1]
+    with ac.Session() as session:
+        greedy = model.select_max_actions(obs, session)
+        sampled = model.sample_actions(obs, session)
+        logits, value = session.run([model.policy.logits, model.baseline.value],
+                                    feed_dict={model.observations_placeholder: obs})
+    assert LC.rel_err(logits.reshape(7, 5), want_logits) <= 1e-5
+    assert greedy == want_logits.argmax(1).tolist()
+    assert len(sampled) == 7 and all(0 <= a < 5 for a in sampled)
+    assert value.shape == (7, 1)
+    with pytest.raises(NotImplementedError):
+        model.register_layers(None)
+
+
+def test_box_action_space_placeholders():
+    """model.py:179-183: a Box action space gives a placeholder of the space's dtype and shape (f4)."""
+    from actorcritic_b200 import spaces
+    from actorcritic_b200.model import ActorCriticModel
+
+    class M(ActorCriticModel):
+        pass
+    m = M(spaces.Box(low=0, high=255, shape=(84, 84, 4), dtype=np.uint8), spaces.Box(low=-2.0, high=2.0, shape=(3,), dtype=np.float32))
+    assert m.actions_placeholder.dtype == np.float32 and m.actions_placeholder.shape == (None, None, 3)
+    assert m.observations_placeholder.dtype == np.uint8 and m.bootstrap_observations_placeholder.shape == (None, 84, 84, 4)
+
+
+# ------------------------------------------------------------------------------------------------ optimize_separate (f4)
+def test_optimize_separate_matches_oracle():
+    """objectives.py:31-54: policy loss and baseline loss minimised by two optimizers (two backward passes from the same
+    parameters, separate slots), against the oracle's gradients of each loss and the TF-1 RMSProp / Momentum recurrences."""
+    import actorcritic_b200 as ac
+    from actorcritic_b200 import nn, objectives, spaces
+    from actorcritic_b200.envs.atari.model import AtariModel
+    e_count, t_count, c3 = 4, 5, 64
+    model = AtariModel(spaces.Box(low=0, high=255, shape=(84, 84, 4), dtype=np.uint8), spaces.Discrete(4), c3, random_seed=0)
+    objective = objectives.A2CObjective(model, discount_factor=0.99, entropy_regularization_strength=0.01)
+    with pytest.raises(TypeError):      # the reference's default None kwargs: `**None` (SURVEY D.3)
+        objective.optimize_separate(nn.RMSPropOptimizer(1e-3), nn.RMSPropOptimizer(1e-3))
+    global_step = ac.GlobalStep()
+    policy_opt = nn.ClipGlobalNormOptimizer(nn.RMSPropOptimizer(learning_rate=7e-4), clip_norm=0.5)
+    baseline_opt = nn.MomentumOptimizer(learning_rate=3e-4, momentum=0.9)
+    op = objective.optimize_separate(policy_opt, baseline_opt, policy_kwargs=dict(global_step=global_step), baseline_kwargs={})
+    params = onet.perturbed_params(4, c3, 3)
+    model.set_variables(params)
+    o = OL.OracleLearner(params, 4, c3, acktr=False)
+    ms = {l: torch.ones_like(onet.join_vmat(l, o.params)) for l in onet.LAYERS}
+    mom = {l: torch.zeros_like(onet.join_vmat(l, o.params)) for l in onet.LAYERS}
+    with ac.Session() as session:
+        for u in range(3):
+            batch = synth.rollout(400 + u, e_count, t_count, 4, obs_kind="sparse")
+            if u > 0:      # compare each update from identical parameters
+                for l in onet.LAYERS:
+                    model.engine.layer_matrix("params", l).copy_(onet.join_vmat(l, o.params).float())
+                model.engine.refresh_derived()
+            pl, bl, _ = session.run([objective.policy_loss, objective.baseline_loss, op], feed_dict={
+                model.observations_placeholder: batch["observations"],
+                model.bootstrap_observations_placeholder: batch["bootstrap_observations"],
+                model.actions_placeholder: batch["actions"], model.rewards_placeholder: batch["rewards"],
+                model.terminals_placeholder: batch["terminals"]})
+            e = model.engine
+            masks = LC.engine_relu_masks(e)
+            info = o.compute(batch, need_fisher=False, masks=masks)
+            n = e_count * t_count
+            actions = batch["actions"].reshape(n)
+            dz, _ = onet.output_grads(info["fwd"]["logits"], info["fwd"]["value"], actions, info["targets"], 0.01, 0.0)
+            _, dv = onet.output_grads(info["fwd"]["logits"], info["fwd"]["value"], actions, info["targets"], 0.01, 1.0)
+            g_pol, _ = onet.backward(o.params, info["fwd"], dz, torch.zeros_like(dv), masks)
+            g_base, _ = onet.backward(o.params, info["fwd"], torch.zeros_like(dz), dv, masks)
+            clipped, _ = K.clip_by_global_norm(g_pol, 0.5)
+            before = LC.oracle_flat_params(o)
+            for l in onet.LAYERS:
+                ms[l] = 0.9 * ms[l] + 0.1 * clipped[l] * clipped[l]
+                mom[l] = 0.9 * mom[l] + g_base[l]
+                new = onet.join_vmat(l, o.params) - 7e-4 * clipped[l] / torch.sqrt(ms[l] + 1e-10) - 3e-4 * mom[l]
+                w, b = onet.split_vmat(l, new, o.params)
+                o.params[l + "/weights"], o.params[l + "/bias"] = w, b
+            assert abs(float(pl) - float(info["losses"]["policy_loss"])) <= 2e-4 * max(1.0, abs(float(info["losses"]["policy_loss"])))
+            assert abs(float(bl) - float(info["losses"]["baseline_loss"])) <= 2e-4 * max(1.0, abs(float(info["losses"]["baseline_loss"])))
+            got_step = e.get_params_flat().astype(np.float64) - before
+            want_step = LC.oracle_flat_params(o) - before
+            assert LC.rel_err(got_step, want_step) <= 1e-3, u
+            assert global_step.eval() == u + 1          # only the policy optimizer was handed the global step

@@ -80,3 +80,48 @@ def test_restore_rejects_a_different_architecture(tmp_path):
         session.run(op2, feed_dict=_feed(model2, batch))
         with pytest.raises(ValueError):
             checkpoint.Saver(model2).restore(session, path)
+
+
+def test_restore_then_act_then_save_keeps_the_optimizer_state(tmp_path):
+    """restore -> sample_actions (builds an acting-only engine) -> save -> restore -> train: the K-FAC running sums,
+    inverses, velocities and counters of the first checkpoint survive (the reference's Ctrl-C handler can save during the
+    first rollout of a resumed run, a2c_acktr.py:135-143), and `session.run(global_step)` right after the restore
+    reports the restored step."""
+    from actorcritic_b200 import checkpoint
+    e_count, t_count = 4, 5
+    batches = [synth.rollout(700 + u, e_count, t_count, 4, obs_kind="sparse") for u in range(6)]
+    y_hat, eps = synth.fisher_samples(800, e_count * t_count)
+    fisher = (torch.from_numpy(y_hat).cuda(), torch.from_numpy(eps).cuda())
+    ac, model, objective, global_step, optimize_op = _build(True, e_count, t_count, seed=5)
+    with ac.Session() as session:
+        session.fisher_injection = fisher
+        for u in range(4):
+            step, _ = session.run([global_step, optimize_op], feed_dict=_feed(model, batches[u]))
+        first = checkpoint.Saver(model).save(session, str(tmp_path / "a"), step)
+        want_state = checkpoint.state_to_arrays(model.engine)
+        session.run(optimize_op, feed_dict=_feed(model, batches[4]))
+        want_after = checkpoint.state_to_arrays(model.engine)
+
+    ac2, model2, objective2, global_step2, optimize_op2 = _build(True, e_count, t_count, seed=99)
+    saver2 = checkpoint.Saver(model2)
+    with ac2.Session() as session:
+        session.fisher_injection = fisher
+        saver2.restore(session, first)
+        assert int(session.run(global_step2)) == int(want_state["global_step"])      # before any engine exists
+        obs = batches[0]["observations"][:, :1]
+        model2.sample_actions(obs, session)                                           # acting-only engine
+        assert model2.engine is not None and not model2.engine.is_learner
+        second = saver2.save(session, str(tmp_path / "b"), int(want_state["global_step"]))
+        with np.load(second) as z:
+            assert bool(z["meta/acktr"]) and "kfac/cov/A/heads" in z.files and "conv2/weights/velocity" in z.files
+            for k in want_state:
+                assert np.array_equal(z[k], want_state[k]), k
+    ac3, model3, objective3, global_step3, optimize_op3 = _build(True, e_count, t_count, seed=7)
+    with ac3.Session() as session:
+        session.fisher_injection = fisher
+        checkpoint.Saver(model3).restore(session, second)
+        model3.sample_actions(batches[0]["observations"][:, :1], session)            # acting engine first, learner after
+        session.run(optimize_op3, feed_dict=_feed(model3, batches[4]))
+        got = checkpoint.state_to_arrays(model3.engine)
+    for k in want_after:
+        assert np.array_equal(got[k], want_after[k]), k
