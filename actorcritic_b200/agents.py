@@ -53,35 +53,89 @@ class MultiEnvAgent(Agent):
 
     def _interact_device(self, session):
         env, t_count = self._env, self._num_steps
-        e_count = env.num_envs
-        dev = env.device
-        if self._observations is None:
-            self._observations = env.reset()                                       # uint8 [E,84,84,4] on the device
-        obs = torch.empty((e_count, t_count, 84, 84, 4), dtype=torch.uint8, device=dev)
         engine = self._model.engine
         if engine is None:
-            engine = self._model._build_engine(session, e_count, t_count, None)
-        # per-step results are gathered step-major in buffers the agent keeps (stable pointers: the library replays each
-        # acting step as a CUDA graph) and turned batch-major once at the end - one small kernel per tensor instead of one
-        # per tensor and step
+            engine = self._model._build_engine(session, env.num_envs, t_count, None)
+        if self._observations is None:
+            self._observations = env.reset()                                       # uint8 [E,84,84,4] on the device
+        # A device environment whose rollouts of this length always touch the same buffers (rollout_repeats) is replayed as
+        # ONE CUDA graph: T x (K-PRE, acting forward, sample, bookkeeping copies) = ~14 T launches become one.  The first
+        # rollout runs eagerly (one-time host work of the library), the second is captured, later ones are replayed.
+        repeat = getattr(env, "rollout_repeats", None)
+        if engine.config.use_graphs and repeat is not None and repeat(t_count):
+            return self._interact_device_graph(session, engine)
+        return self._rollout_eager(engine)
+
+    def _rollout_buffers(self, engine):
+        env, t_count = self._env, self._num_steps
+        e_count, dev = env.num_envs, env.device
         if getattr(self, "_step_actions", None) is None or self._step_actions.shape != (t_count, e_count):
             self._step_actions = torch.empty((t_count, e_count), dtype=torch.int32, device=dev)
+            self._obs_buf = torch.empty((e_count, t_count, 84, 84, 4), dtype=torch.uint8, device=dev)
+            self._next_obs_buf = torch.empty((e_count, 84, 84, 4), dtype=torch.uint8, device=dev)
+            self._act_buf = torch.empty((e_count, t_count), dtype=torch.uint8, device=dev)
+            self._rew_buf = torch.empty((e_count, t_count), dtype=torch.float32, device=dev)
+            self._term_buf = torch.empty((e_count, t_count), dtype=torch.uint8, device=dev)
+
+    def _rollout_steps(self, engine):
+        """T steps into the agent's own buffers (stable pointers: the library replays each acting step as a CUDA graph;
+        per-step results are gathered step-major and turned batch-major once at the end)."""
+        env, t_count = self._env, self._num_steps
+        e_count = env.num_envs
+        self._rollout_buffers(engine)
         cur = self._observations
         reward_steps, terminal_steps, info_steps = [], [], []
         for t in range(t_count):
-            obs[:, t].copy_(cur)
+            self._obs_buf[:, t].copy_(cur)
             a = engine.act(cur, out=self._step_actions[t])                         # int32 [E]
             cur, r, term = env.step_device(a)
             reward_steps.append(r)
             terminal_steps.append(term)
             # environments hosted on the CPU (envs.atari.raw_env.RawFrameMultiEnv) report their info dicts per step
             info_steps.append(list(getattr(env, "last_infos", None) or [{} for _ in range(e_count)]))
-        actions = self._step_actions.t().to(torch.uint8)
-        rewards = torch.stack(reward_steps, dim=1).to(torch.float32)
-        terminals = torch.stack(terminal_steps, dim=1)
-        cur = cur.clone()              # the environment reuses its stack buffer; the tuple must not alias it
-        self._observations = cur
-        return obs, actions, rewards, terminals.bool(), cur, transpose_list(info_steps)
+        self._act_buf.copy_(self._step_actions.t())
+        torch.stack(reward_steps, dim=1, out=self._rew_buf)
+        torch.stack(terminal_steps, dim=1, out=self._term_buf)
+        self._next_obs_buf.copy_(cur)      # the environment reuses its stack buffer; the tuple must not alias it
+        return info_steps
+
+    def _result(self, info_steps):
+        self._observations = self._next_obs_buf.clone()
+        return (self._obs_buf.clone(), self._act_buf.clone(), self._rew_buf.clone(), self._term_buf.bool(),
+                self._next_obs_buf.clone(), transpose_list(info_steps))
+
+    def _rollout_eager(self, engine):
+        with engine.on_stream():
+            info_steps = self._rollout_steps(engine)
+            return self._result(info_steps)
+
+    def _interact_device_graph(self, session, engine):
+        env, t_count = self._env, self._num_steps
+        state = getattr(self, "_graph_state", 0)
+        if state == 0:                     # first rollout: eager
+            self._graph_state = 1
+            return self._rollout_eager(engine)
+        with engine.on_stream():
+            if state == 1:                 # second rollout: capture (the captured launches also execute on replay only)
+                # the rollout must start from the agent's persistent observation buffer
+                self._cur_buf = self._observations.clone()
+                self._observations = self._cur_buf
+                t0 = env.t
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=engine.stream):
+                    self._graph_infos = self._rollout_steps(engine)
+                    self._cur_buf.copy_(self._next_obs_buf)
+                env.t = t0                 # capture does not execute: the environment's host-side clock is advanced per replay
+                self._graph, self._graph_state = graph, 2
+                self._observations = self._cur_buf
+            # replay: the environment's own stack buffer and the agent's `_cur_buf` carry the state between rollouts
+            self._graph.replay()
+            env.t += t_count
+            out = (self._obs_buf.clone(), self._act_buf.clone(), self._rew_buf.clone(), self._term_buf.bool(),
+                   self._next_obs_buf.clone(), transpose_list(self._graph_infos))
+            self._observations = self._cur_buf
+            return out
 
 
 class SingleEnvAgent(Agent):

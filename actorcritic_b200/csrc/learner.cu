@@ -1040,6 +1040,12 @@ static int issue_phase2(acx_learner* l, const Plan2& p, cudaStream_t st) {
 template <typename F>
 static int run_cached(acx_learner* l, const GraphKey& key, cudaStream_t st, F&& issue) {
   if (!l->cfg.use_graphs || l->profiling || st == nullptr) return issue();
+  {
+    // the caller is capturing this stream itself (e.g. a whole rollout as one graph): the launches simply become nodes
+    // of the caller's graph
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive) return issue();
+  }
   GraphEntry& ge = l->graphs[key];
   if (ge.uses == 0) {
     ge.uses = 1;

@@ -26,6 +26,12 @@ class DeviceAtariMultiEnv:
         self.pre = BatchedAtariPreprocessor(num_envs, self.device)
         self.t = 0
 
+    def rollout_repeats(self, num_steps):
+        """True when every rollout of `num_steps` steps reads the same pool entries (frames are indexed by 2t + 1 .. 2t + 3,
+        rewards / terminals by t, all modulo pool_frames): such a rollout can be replayed as one CUDA graph
+        (agents.MultiEnvAgent) with exactly the results of stepping one by one."""
+        return num_steps % self.pool.shape[0] == 0 and self.t % num_steps == 0
+
     envs = property(lambda self: [self] * self.num_envs)
 
     def reset(self):
@@ -40,7 +46,7 @@ class DeviceAtariMultiEnv:
         j = (2 * self.t + 2) % n
         k = (2 * self.t + 3) % n
         term = self.terminals[self.t % n]
-        obs = self.pre.step(self.pool[i], self.pool[j], term, reset_raw=self.pool[k])
+        obs = self.pre.step(self.pool[i], self.pool[j], term, reset_raw=self.pool[k], keep_terminal_view=True)
         rew = self.rewards[self.t % n]
         self.t += 1
         return obs, rew, term

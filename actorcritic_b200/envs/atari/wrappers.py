@@ -29,7 +29,7 @@ class BatchedAtariPreprocessor:
         self.prev_terminal.zero_()
         return self.stacks
 
-    def step(self, raw_a, raw_b, terminal, reset_raw=None, out=None, out_env_stride=None):
+    def step(self, raw_a, raw_b, terminal, reset_raw=None, out=None, out_env_stride=None, keep_terminal_view=False):
         """One MultiEnv.step: raw_a/raw_b = the last two emulator frames of each frameskip window, `terminal` = this
         step's terminal flags; environments whose PREVIOUS step was terminal are first reset from reset_raw.
         `out` may be a slice [:, t] of a batch-major rollout buffer."""
@@ -38,7 +38,10 @@ class BatchedAtariPreprocessor:
                              out=self.stacks, out_env_stride=28224)
         if out is not None:
             out.copy_(self.stacks)
-        self.prev_terminal = terminal.clone() if terminal is not None else torch.zeros_like(self.prev_terminal)
+        if terminal is None:
+            self.prev_terminal = torch.zeros_like(self.prev_terminal)
+        else:       # keep_terminal_view: the caller guarantees that `terminal` is not overwritten before the next step
+            self.prev_terminal = terminal if keep_terminal_view else terminal.clone()
         return self.stacks
 
 

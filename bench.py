@@ -439,21 +439,25 @@ def run_native(args, rank, world, local_rank):
 
     # rollout side of the path (agents.py:202-216): T x (K-PRE on E raw frame pairs + forward on E rows + sample)
     from actorcritic_b200.envs.atari.device_env import DeviceAtariMultiEnv
-    env = DeviceAtariMultiEnv(envs, pool_frames=32, seed=rank, device=dev)
-    cur = env.reset()
+    from actorcritic_b200.agents import MultiEnvAgent
+
+    class _EngineModel:          # what MultiEnvAgent needs from a model whose engine already exists
+        engine = e
+    # pool_frames = T: every rollout reads the same synthetic frames, so the agent replays the whole rollout
+    # (T x (K-PRE, acting forward, sample) + bookkeeping) as ONE CUDA graph after its second call
+    env = DeviceAtariMultiEnv(envs, pool_frames=t_count, seed=rank, device=dev)
+    agent = MultiEnvAgent(env, _EngineModel(), t_count)
     with torch.cuda.stream(e.stream):
-        for _ in range(3):
-            for t in range(t_count):
-                cur, _, _ = env.step_device(e.act(cur))
+        for _ in range(4):
+            agent.interact(None)
         torch.cuda.synchronize()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-        for _ in range(5):
-            for t in range(t_count):
-                cur, _, _ = env.step_device(e.act(cur))
+        for _ in range(10):
+            agent.interact(None)
         ev1.record()
         torch.cuda.synchronize()
-    rollout_ms = ev0.elapsed_time(ev1) / 5
+    rollout_ms = ev0.elapsed_time(ev1) / 10
 
     total_envs = envs * world
     ms_step = ms_dev / args.steps
@@ -572,11 +576,75 @@ def run_native(args, rank, world, local_rank):
         "roofline": roofline,
         "preprocess": pre,
         "rollout": {"ms_per_%d_steps" % t_count: rollout_ms, "env_steps_per_sec": envs * t_count / (rollout_ms * 1e-3),
-                    "note": "per GPU: T x (K-PRE on E raw frame pairs -> stacks, Nature-CNN forward on E rows, categorical sample); "
-                            "not part of `value`"},
+                    "note": "per GPU, MultiEnvAgent.interact on the device-resident synthetic environment: T x (K-PRE on E raw frame "
+                            "pairs -> stacks, Nature-CNN forward on E rows, categorical sample) + the [E,T] rollout tensors, replayed "
+                            "as one CUDA graph; not part of `value`"},
         "env_steps_per_sec_with_rollout": total_envs * t_count / ((ms_step + rollout_ms) * 1e-3),
         "losses": scal,
     }
+    if world > 1 and not args.no_extra:
+        # (1) the collective on the critical path, timed alone: [G | grads | scalars] (what phase 2 waits for) and the
+        # input-factor prefix A (reduced under phase 2 on a second communicator), each as K back-to-back all-reduces
+        coll = {}
+        try:
+            a_part = e.buffer("input_factor_stats", torch.float32)
+            rest = e.bucket[a_part.numel():]
+            for name, buf in (("critical_G_grads_scalars", rest), ("input_factor_prefix_A", a_part)):
+                with torch.cuda.stream(e.stream):
+                    for _ in range(3):
+                        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+                    barrier()
+                    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    c0.record()
+                    for _ in range(20):
+                        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+                    c1.record()
+                    barrier()
+                t = torch.tensor([c0.elapsed_time(c1) / 20 * 1e3], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                coll[name] = {"bytes": buf.numel() * 4, "us": float(t.item())}
+            # restore a sane state (the buckets now hold sums of sums): one more full update rewrites them
+            step(0, resident, False)
+        except Exception as exc:  # noqa: BLE001
+            coll["error"] = repr(exc)
+        line["collective"] = coll
+        # (2) strong scaling of BASELINE.json configs[3]: 256 environments x 20 steps sharded over the ranks
+        try:
+            if 256 % world == 0:
+                es = 256 // world
+                cfg_s = eng.EngineConfig(num_envs=es, num_steps=t_count, conv3_filters=c3, precision=args.precision,
+                                         world_size=world, seed=4321 + rank, use_graphs=not args.no_graphs,
+                                         invert_every=args.invert_every, num_lanes=args.lanes, conv_impl=args.conv_impl)
+                del resident, host
+                torch.cuda.empty_cache()
+                e2 = eng.Engine(cfg_s, dev)
+                e2.set_params(eng.orthogonal_init(4, c3, seed=0))
+                bs = make_batches(4, es, t_count, seed=5000 * (rank + 1))
+                rs = [{k: torch.from_numpy(np.ascontiguousarray(b[k] if b[k].dtype != bool else b[k].astype(np.uint8))).to(dev)
+                       for k in keys} for b in bs]
+                e2.set_state(30, 0, False)
+
+                def step2(i):
+                    e2.update(rs[i % 4], fetch=False)
+
+                with torch.cuda.stream(e2.stream):
+                    for i in range(23 + 3):
+                        step2(i)
+                    barrier()
+                    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    s0.record()
+                    for i in range(args.steps):
+                        step2(i)
+                    s1.record()
+                    barrier()
+                t = torch.tensor([s0.elapsed_time(s1) / args.steps], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                line["strong_256x20"] = {"envs_per_rank": es, "total_envs": 256, "ms_per_step": float(t.item()),
+                                         "value": 256 * t_count / (float(t.item()) * 1e-3), "unit": UNIT, "scaling": "strong",
+                                         "steps": args.steps}
+                del e2, rs
+        except Exception as exc:  # noqa: BLE001
+            line["strong_256x20"] = {"error": repr(exc)}
     if rank == 0 and world == 1 and not args.no_extra:
         # the other single-GPU configurations of BASELINE.json as extra keys (same timing rules, own CPU baseline):
         # configs[2] at the class-default conv3 = 64 (the 3137 x 3137 factor) and configs[1] = A2C 16 x 5
