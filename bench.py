@@ -488,7 +488,12 @@ def run_native(args, rank, world, local_rank):
                        "bound": "tensor", "launch_ms": ms2, "algorithmic_gflop_per_launch": alg / 1e9,
                        "achieved": alg / (ms2 * 1e-3) / 1e12, "peak": peaks["tensor_burst"], "unit": "TFLOP/s",
                        "frac": alg / (ms2 * 1e-3) / 1e12 / peaks["tensor_burst"],
-                       "issued_gflop_per_launch": issued / 1e9, "issued_frac": issued / (ms2 * 1e-3) / 1e12 / peaks["tensor_burst"]}
+                       "issued_gflop_per_launch": issued / 1e9, "issued_frac": issued / (ms2 * 1e-3) / 1e12 / peaks["tensor_burst"],
+                       # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full, profiles/r2_prof_syrk_conv2_raw.txt;
+                       # algorithmic: 2 planes x rows x 512 x 2 B read once = 106 MB)
+                       "traffic": ncu_traffic("r2_prof_syrk_conv2_raw.txt"),
+                       "ncu": "profiles/r2_prof_syrk_conv2_details.txt: tensor pipe active 57.6 % of cycles, shared-memory "
+                              "operand wavefronts 45.6 % of peak, DRAM 27 %"}
         del x2
     except Exception as exc:  # noqa: BLE001
         factor_syrk = {"error": repr(exc)}
@@ -550,6 +555,23 @@ def run_native(args, rank, world, local_rank):
                                    "issued from inside the forward / backward stages",
                      "stage_tflops": {k: flops[k] / (stage_ms[k] * 1e-3) / 1e12 for k in ("forward", "backward", "precondition")
                                       if stage_ms.get(k, 0) > 0}}
+    # The dominant kernel = the longest launch of the dominant kernel family.  gemm_tc_kernel<1> (MN-major operands: the
+    # factor SYRKs and the weight gradients) is 13 launches and 29 % of the summed kernel time of an update
+    # (profiles/r2_launches_update.txt); its longest launch - the conv2 input-factor SYRK, 50 us - is also the longest launch
+    # of the whole update (the conv2 input gradient on conv_tc_kernel, round 1's headline, is 46 us: `roofline.conv_dgrad`).
+    if isinstance(roofline, dict) and dom is not None and isinstance(factor_syrk, dict) and "frac" in factor_syrk \
+            and factor_syrk["launch_ms"] >= dg[dom]["ms"]:
+        conv_block = {k: roofline[k] for k in ("bound", "kernel", "achieved", "peak", "unit", "frac", "traffic",
+                                               "algorithmic_gflop_per_launch", "launch_ms", "issued_gflop_per_launch",
+                                               "issued_tflops", "issued_frac", "note", "conv_dgrad_launches")}
+        rest = {k: v for k, v in roofline.items() if k not in conv_block and k != "factor_syrk"}
+        roofline = dict(factor_syrk)
+        roofline["peak_source"] = peaks["source"] + ", dense bf16 (cuBLAS) burst"
+        roofline["note"] = ("fp32-grade products from bf16 tensor cores cost 3 plane pairs (hi*hi + hi*lo + lo*hi) and the symmetric "
+                            "product is computed on 10 of 16 128-tiles: the tensor pipe executes 3.75x the algorithmic FLOPs the "
+                            "fraction is charged on (`issued_frac`)")
+        roofline.update(rest)
+        roofline["conv_dgrad"] = conv_block
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

