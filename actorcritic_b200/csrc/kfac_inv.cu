@@ -822,11 +822,13 @@ int spd_inverse_resident(const InvJob* h_jobs, int num_jobs, const Sched* sched,
     ACX_CUDA(cudaFuncSetAttribute(inv_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_limit));
   }
   if (slots > 16 || smem > (size_t)dyn_limit) return -1;
-  // four 64-thread update groups when their staging fits next to the tiles (conv3 = 32: yes; conv3 = 64: 12 slots, no)
+  // ACX_INV_GROUPS=4 (opt-in): the update phase as four 64-thread groups with 8 x 8 register tiles, when their staging fits
+  // next to the tiles.  Bit-identical, but measured SLOWER on B200 at 32 x 20 (0.98 vs 0.85 ms per refresh): late pivot steps
+  // have only 2-3 active tiles per CTA, and a 2-warp group cannot hide its own shared-memory latency.
   static int want_groups = -1;
   if (want_groups < 0) {
     const char* e = getenv("ACX_INV_GROUPS");
-    want_groups = e ? atoi(e) : 4;
+    want_groups = e ? atoi(e) : 1;
   }
   a.groups = 1;
   a.group_stage_off = STAGE_FLOATS + slots * TILE_FLOATS;

@@ -63,8 +63,9 @@ class GlobalStep(Fetch):
 
     def bind(self, engine):
         self._engine = engine
-        if self._pending:
-            engine.set_state(self._pending)
+        if self._pending and engine.global_step != self._pending:     # keep the engine's other schedule counters
+            st = engine.get_state()
+            engine.set_state(self._pending, st["num_cov_updates"], st["inverses_valid"])
 
     def eval(self):
         return self._engine.global_step if self._engine is not None else self._pending
