@@ -527,7 +527,8 @@ static int launch_conv(const CUtensorMap* ta, const CUtensorMap* tb, ConvTcParam
     }
     p.debug = dbg;
   }
-  const int grid = std::min(p.num_tiles, conv_num_sms());
+  int grid = std::min(p.num_tiles, conv_num_sms());
+  if (g_cta_cap > 0 && grid > g_cta_cap) grid = g_cta_cap;
   const int smem = CV_SMEM_FIXED + p.stages * stage_bytes;
   conv_tc_kernel<<<grid, CV_THREADS, smem, st>>>(ta[0], ta[1], ta[2], tb[0], tb[1], tb[2], p);
   ACX_LAUNCH_CHECK();

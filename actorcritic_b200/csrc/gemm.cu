@@ -1074,6 +1074,11 @@ static int launch_tc(const CUtensorMap* ta, const CUtensorMap* tb, const TcParam
   return 0;
 }
 
+// triage knob (ACX_MAIN_CTAS / ACX_SIDE_CTAS, learner.cu): cap on the persistent grid of the next tensor-core launches, so
+// that kernels of different lanes can share the SMs instead of queueing behind each other (0 = all SMs)
+int g_cta_cap = 0;
+void set_cta_cap(int cap) { g_cta_cap = cap; }
+
 static int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -1180,7 +1185,8 @@ static int gemm_tc(const acx_gemm_t* g, cudaStream_t st) {
   p.mn_lbo = g_mn_lbo ? g_mn_lbo : (uint32_t)(pl.bk * 128);
   p.mn_sbo = g_mn_sbo ? g_mn_sbo : 1024u;
   p.mn_kstep = g_mn_kstep ? g_mn_kstep : 2048u;
-  const int grid = p.total_work < num_sms() ? p.total_work : num_sms();
+  int grid = p.total_work < num_sms() ? p.total_work : num_sms();
+  if (g_cta_cap > 0 && grid > g_cta_cap) grid = g_cta_cap;
   const int smem = SMEM_FIXED + p.stages * stage_bytes;
   int r;
   if (patch)

@@ -21,6 +21,8 @@ struct Planes {
 };
 
 int gemm_dispatch(const acx_gemm_t* g, int impl, cudaStream_t st);
+extern int g_cta_cap;
+void set_cta_cap(int cap);
 int returns_launch(const float* rewards, const uint8_t* terminals, const float* values, const float* bootstrap, float gamma,
                    int num_envs, int num_steps, float* targets, float* adv, cudaStream_t st);
 

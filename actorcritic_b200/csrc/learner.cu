@@ -521,6 +521,18 @@ static int level_pairs(int level, int a_planes, int b_planes, int* pa, int* pb) 
   return np;
 }
 
+// triage: ACX_MAIN_CTAS / ACX_SIDE_CTAS cap the persistent grids of the tensor-core kernels of lane 0 / the side lanes
+static int lane_cta_cap(int lane_index) {
+  static int caps[2] = {-1, -1};
+  if (caps[0] < 0) {
+    const char* a = getenv("ACX_MAIN_CTAS");
+    const char* b = getenv("ACX_SIDE_CTAS");
+    caps[0] = a ? atoi(a) : 0;
+    caps[1] = b ? atoi(b) : 0;
+  }
+  return caps[lane_index == 0 ? 0 : 1];
+}
+
 static ConvGeom geom_of(const Layer& L) { return ConvGeom{L.hw_in, L.cin, L.k, L.s, L.hw_out, L.C}; }
 
 static int run_gemm(acx_learner* l, const Planes& a, const Planes& b, int trans, int m, int n, int k, int level, float alpha,
@@ -560,7 +572,10 @@ static int run_gemm(acx_learner* l, const Planes& a, const Planes& b, int trans,
   g.splits = 0;
   g.workspace = ln.sc->ws;
   g.workspace_bytes = ln.sc->ws_bytes;
-  return gemm_dispatch(&g, l->cfg.gemm_impl, ln.st);
+  set_cta_cap(lane_cta_cap(ln.index));
+  const int r = gemm_dispatch(&g, l->cfg.gemm_impl, ln.st);
+  set_cta_cap(0);
+  return r;
 }
 
 // stage boundaries: mark k closes stage k-1 (phase 1: marks 0..4, phase 2: marks 5..9)
@@ -709,7 +724,10 @@ static int forward(acx_learner* l, const uint8_t* obs, int rows, const Lane& ln,
     }
     int pa[6], pb[6];
     const int np = level_pairs(l->lvl_fwd, in.n, l->wT[li].n, pa, pb);
-    return conv_tc_forward(in, l->wT[li], geom_of(L), rows, o.bias, 1, out, np, pa, pb, st);
+    set_cta_cap(lane_cta_cap(0));
+    const int rc = conv_tc_forward(in, l->wT[li], geom_of(L), rows, o.bias, 1, out, np, pa, pb, st);
+    set_cta_cap(0);
+    return rc;
   };
   GemmOut o;
   o.relu = 1;
@@ -771,8 +789,11 @@ static int conv_dgrad(acx_learner* l, int li, const Planes& g, const bf16* act_b
     int pa2[6], pb2[6];
     const int np_lo = level_pairs(l->lvl_fisher, g.n, l->wD[li].n, pa2, pb2);
     const bool lo = samples > l->N && np_lo < np;
-    return conv_tc_dgrad(g, l->wD[li], geom_of(L), samples, act_below_hi, l->N, g_below, np, pa, pb, ln.st, lo ? l->N : -1,
-                         np_lo);
+    set_cta_cap(lane_cta_cap(ln.index));
+    const int rc = conv_tc_dgrad(g, l->wD[li], geom_of(L), samples, act_below_hi, l->N, g_below, np, pa, pb, ln.st, lo ? l->N : -1,
+                                 np_lo);
+    set_cta_cap(0);
+    return rc;
   }
   const size_t per_sample = (size_t)L.T * L.K * sizeof(float);
   int chunk = (int)(l->dgrad_chunk_bytes / per_sample);
@@ -1478,6 +1499,7 @@ int acx_learner_act(acx_learner_t* l, const uint8_t* d_obs, int rows, const floa
   };
   l->act_calls++;
   GraphKey key = {3, (greedy ? 1 : 0) | (rows << 1), d_obs, d_actions, d_uniform, d_logits, d_values};
+  if (l->graphs.size() > 512 && l->graphs.find(key) == l->graphs.end()) return issue();   // ever-changing buffers: do not hoard graphs
   return run_cached(l, key, st, issue);
 }
 

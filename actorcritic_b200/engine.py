@@ -588,23 +588,16 @@ class Engine:
         """Forward + categorical sample / argmax on [rows,84,84,4] uint8 device observations
         (ActorCriticModel.sample_actions / select_max_actions, model.py:135-169).
 
-        The outputs live in buffers owned by the engine (one set per row count) unless `out` (int32 [rows]) is given: they
-        are valid until the next `act` call with the same row count.  Stable input / output pointers let the library replay
-        the whole acting step as one CUDA graph (acx_learner_act)."""
+        `out` (int32 [rows], optional): where the actions go.  A rollout loop that passes the same observation buffer and
+        the same `out` every step has stable pointers, which lets the library replay the whole acting step as one CUDA
+        graph (acx_learner_act); without `out` every call returns fresh tensors."""
         if not observations.is_cuda:
             observations = observations.to(self.device, non_blocking=True)
         observations = observations.contiguous()
         rows = observations.shape[0]
-        bufs = getattr(self, "_act_bufs", None)
-        if bufs is None:
-            bufs = self._act_bufs = {}
-        if rows not in bufs:
-            bufs[rows] = (torch.empty(rows, dtype=torch.int32, device=self.device),
-                          torch.empty((rows, self.config.num_actions), dtype=torch.float32, device=self.device),
-                          torch.empty(rows, dtype=torch.float32, device=self.device))
-        actions, logits, values = bufs[rows]
-        if out is not None:
-            actions = out
+        actions = out if out is not None else torch.empty(rows, dtype=torch.int32, device=self.device)
+        logits = torch.empty((rows, self.config.num_actions), dtype=torch.float32, device=self.device) if want_logits else None
+        values = torch.empty(rows, dtype=torch.float32, device=self.device) if want_logits else None
         with self.on_stream():
             _lib.check(self.lib.acx_learner_act(
                 self._h, ctypes.c_void_p(observations.data_ptr()), rows,
