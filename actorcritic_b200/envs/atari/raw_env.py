@@ -11,9 +11,16 @@ Observations stay on the device (`device_resident`), so `MultiEnvAgent.interact`
 step without another copy.
 
 The environments need the gym surface the reference uses: `reset() -> frame`, `step(action) -> (frame, reward, terminal,
-info)`, `action_space`, optionally `close()`.  Emulator-side wrappers that do no array math (episodic life, fire / noop
-reset, reward clipping, episode info; wrappers.py:73-171,238-323) can be stacked on them unchanged - they are Python
-game logic and out of scope here.
+info)`, `action_space`, optionally `close()`.
+
+Wrapper order.  In the reference the frameskip sits BELOW the game-logic wrappers (a2c_acktr.py:190-208: NoopReset ->
+Frameskip -> Preprocess -> EpisodeInfo -> EpisodicLife -> FireReset -> ClipReward): rewards are clipped AFTER the 4-frame
+sum, and the FIRE / life logic sees agent steps, not emulator frames.  Here the frameskip is applied by this class, so
+wrappers stacked on the hosted environments sit below it and see single emulator frames: only wrappers that are indifferent
+to that may go there (AtariNoopResetWrapper, a2c_acktr.py:190).  What must act on agent steps is given to this class
+instead: `clip_rewards=True` clips the summed reward to [-1, 1] (AtariClipRewardWrapper, wrappers.py:73-86), and
+`step_hook(env_index, reward, terminal, info) -> (reward, terminal, info)` runs after every agent step (the place for
+episodic-life / episode-info logic).  The game-logic wrappers themselves are Python and out of scope.
 """
 import concurrent.futures
 
@@ -29,7 +36,7 @@ RAW_SHAPE = (210, 160, 3)
 class RawFrameMultiEnv:
     device_resident = True
 
-    def __init__(self, envs, frameskip=4, device=None, num_threads=None):
+    def __init__(self, envs, frameskip=4, device=None, num_threads=None, clip_rewards=False, step_hook=None):
         if len(envs) == 0:
             raise ValueError("at least one environment is required")
         if not torch.cuda.is_available():
@@ -41,6 +48,8 @@ class RawFrameMultiEnv:
         self._envs = list(envs)
         self.num_envs = len(self._envs)
         self.frameskip = int(frameskip)
+        self.clip_rewards = bool(clip_rewards)
+        self.step_hook = step_hook
         self.device = torch.device("cuda") if device is None else torch.device(device)
         self.observation_space = spaces.Box(low=0, high=255, shape=(84, 84, 4), dtype=np.uint8)
         self.action_space = self._envs[0].action_space
@@ -88,6 +97,10 @@ class RawFrameMultiEnv:
         # wrappers.py:64-67: max of the last two frames, or the only frame when the first sub-step was terminal
         self._np_frames[0, i] = last if prev is None else prev
         self._np_frames[1, i] = last
+        if self.clip_rewards:                           # wrappers.py:85-86, applied to the agent step's reward like the reference
+            total_reward = float(np.clip(total_reward, -1.0, 1.0))
+        if self.step_hook is not None:
+            total_reward, terminal, info = self.step_hook(i, total_reward, terminal, info)
         self._np_rewards[i] = total_reward
         self._np_flags[0, i] = 1 if terminal else 0
         self._terminated[i] = bool(terminal)

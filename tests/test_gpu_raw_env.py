@@ -129,3 +129,30 @@ def test_agent_rollout_over_raw_frame_envs_feeds_the_train_step():
         obs2, *_ = agent.interact(session)
         assert torch.equal(obs2[:, 0], nxt)             # the agent carries the last observations over (agents.py:155,219)
     env.close()
+
+
+def test_reward_clipping_and_step_hook_act_on_agent_steps():
+    """The reference clips rewards ABOVE the frameskip (a2c_acktr.py:190-208): the clip applies to the 4-frame sum, not to
+    each emulator frame.  `clip_rewards` / `step_hook` of RawFrameMultiEnv act there."""
+    from actorcritic_b200.envs.atari.raw_env import RawFrameMultiEnv
+
+    class Rewarding(FakeAtari):
+        def step(self, action):
+            f, _, terminal, info = super().step(action)
+            return f, 0.75, terminal, info               # 4 frames sum to 3.0: clipped AFTER the sum -> 1.0 (per frame it would be 3.0)
+
+    seen = []
+
+    def hook(i, reward, terminal, info):
+        seen.append((i, reward, terminal))
+        return reward * 2.0, terminal, dict(info, hooked=True)
+
+    envs = [Rewarding(5 + i, (50,)) for i in range(3)]
+    multi = RawFrameMultiEnv(envs, frameskip=4, clip_rewards=True, step_hook=hook)
+    multi.reset()
+    _, rew, term = multi.step_device(torch.zeros(3, dtype=torch.int32, device="cuda"))
+    torch.cuda.synchronize()
+    assert rew.cpu().tolist() == [2.0, 2.0, 2.0]        # clip(3.0) = 1.0, then the hook doubles it
+    assert sorted(s[0] for s in seen) == [0, 1, 2] and all(s[1] == 1.0 for s in seen)
+    assert all(info.get("hooked") for info in multi.last_infos)
+    multi.close()
