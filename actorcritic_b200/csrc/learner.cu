@@ -58,7 +58,10 @@ struct Scratch {
   float* colsum_partial = nullptr;
   float* colsum_tmp = nullptr;
 };
-constexpr int kMaxLanes = 3;   // lane 0 = the caller's stream (forward, loss, dgrad chain); 1 = input factors; 2 = wgrad + output factors
+// lane 0 = the caller's stream (forward, loss, dgrad chain); 1 = input-factor SYRKs; 2 = weight gradients; 3 = output-factor
+// SYRKs; 4 = the column-sum kernels (homogeneous borders, bias gradients).  With fewer configured lanes the higher ones fold
+// onto the last one (3 lanes: wgrad + output factors + column sums share lane 2 - round 1's arrangement).
+constexpr int kMaxLanes = 5;
 
 struct GraphKey {
   int phase, variant;
@@ -132,10 +135,10 @@ struct acx_learner {
   float* dot_partials;
   Scratch scr[kMaxLanes];
   int lanes = 1;                          // active lanes (1 = everything on the caller's stream)
-  cudaStream_t side[kMaxLanes - 1] = {nullptr, nullptr};
+  cudaStream_t side[kMaxLanes - 1] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> lane_events;   // fork / join events (timing disabled), reused every update
   size_t ev_next = 0;
-  bool lane_forked[kMaxLanes] = {false, false, false};
+  bool lane_forked[kMaxLanes] = {false, false, false, false, false};
   cudaEvent_t patches_ready[4] = {nullptr, nullptr, nullptr, nullptr};   // P_l complete on the aux lane (this update)
   cudaEvent_t a_ready = nullptr;     // all input-factor statistics of the current phase 1 are complete (external event)
   bool a_ready_valid = false;        // the last phase 1 recorded it
@@ -453,7 +456,8 @@ struct Lane {
 };
 
 static Lane lane_of(acx_learner* l, int i, cudaStream_t main_st) {
-  if (i >= l->lanes || l->profiling) i = 0;   // stage timing brackets serial work on the caller's stream
+  if (l->profiling) i = 0;                    // stage timing brackets serial work on the caller's stream
+  if (i >= l->lanes) i = l->lanes - 1;        // fewer lanes configured: the higher ones fold onto the last one
   return Lane{i == 0 ? main_st : l->side[i - 1], &l->scr[i], i};
 }
 
@@ -840,13 +844,14 @@ static int issue_phase1(acx_learner* l, const int32_t* fisher_labels, const floa
   const int RB = fisher ? 2 * N : N;
   l->ev_next = 0;
   for (cudaEvent_t& e : l->patches_ready) e = nullptr;
-  const Lane main_ln = lane_of(l, 0, st), fac_ln = lane_of(l, 1, st), wg_ln = lane_of(l, 2, st);
+  const Lane main_ln = lane_of(l, 0, st), fac_ln = lane_of(l, 1, st), wg_ln = lane_of(l, 2, st), gf_ln = lane_of(l, 3, st),
+             cs_ln = lane_of(l, 4, st);
   mark(l, 0, st);
-  ACX_TRY(forward(l, l->obs, l->R, main_ln, &fac_ln, &wg_ln, fisher));
+  ACX_TRY(forward(l, l->obs, l->R, main_ln, &fac_ln, &cs_ln, fisher));
   if (fisher && fac_ln.index != 0) {
-    // every input factor has been issued: SYRKs on the factor lane, borders on the (so far otherwise idle) wgrad lane.
+    // every input factor has been issued: SYRKs on the factor lane, borders on the column-sum lane.
     // Raise `a_ready` behind both; inside a stream capture it becomes an external event-record node of the graph.
-    ACX_TRY(order_after(l, wg_ln.st, fac_ln.st));
+    ACX_TRY(order_after(l, cs_ln.st, fac_ln.st));
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     ACX_CUDA(cudaStreamIsCapturing(fac_ln.st, &cs));
     ACX_CUDA(cudaEventRecordWithFlags(l->a_ready, fac_ln.st,
@@ -862,12 +867,21 @@ static int issue_phase1(acx_learner* l, const int32_t* fisher_labels, const floa
   const Planes flat3 = with_ld(l->act3, 49 * c3);
   mark(l, 2, st);
   // ---- fc4
-  ACX_TRY(fork_lane(l, st, wg_ln));
-  ACX_TRY(weight_grad(l, 3, flat3, l->dpre4, N, 1.0f, wg_ln));
-  if (fisher) {
-    ACX_TRY(heads_gfactor(l->dheads + (size_t)N * (A + 1), N, A, l->stats + l->goff[4], l->stats + l->goff[5], wg_ln.st));
-    ACX_TRY(output_factor(l, 3, offset_rows(l->dpre4, N), N, wg_ln));
-  }
+  // (each pre-activation gradient fans out to three side lanes: weight gradient | output factor | bias column sum)
+  auto fan_out = [&](int li, const Planes& x, const Planes& g, int rows) -> int {
+    ACX_TRY(fork_lane(l, st, wg_ln));
+    ACX_TRY(fork_lane(l, st, gf_ln));
+    ACX_TRY(fork_lane(l, st, cs_ln));
+    const bool split_bias = cs_ln.st != wg_ln.st;
+    ACX_TRY(weight_grad(l, li, x, g, rows, 1.0f, wg_ln, !split_bias));
+    if (split_bias) ACX_TRY(bias_grad(l, li, g, rows, cs_ln));
+    if (fisher) ACX_TRY(output_factor(l, li, offset_rows(g, (size_t)rows), rows, gf_ln));
+    return 0;
+  };
+  ACX_TRY(fork_lane(l, st, gf_ln));
+  if (fisher)
+    ACX_TRY(heads_gfactor(l->dheads + (size_t)N * (A + 1), N, A, l->stats + l->goff[4], l->stats + l->goff[5], gf_ln.st));
+  ACX_TRY(fan_out(3, flat3, l->dpre4, N));
   {
     GemmOut o;   // d(act3) = dpre4 W4^T, masked by ReLU(conv3) -> dpre3  (rows of the Fisher half reuse the mask)
     const Planes out = with_ld(l->dpre3, 49 * c3);
@@ -878,30 +892,34 @@ static int issue_phase1(acx_learner* l, const int32_t* fisher_labels, const floa
     ACX_TRY(run_gemm(l, l->dpre4, l->wN[3], 0, RB, 49 * c3, 512, l->lvl_bwd, 1.0f, 0, o, main_ln));
   }
   // ---- conv3  (patch matrices of implicit-GEMM forward layers come from the aux lane)
-  ACX_TRY(fork_lane(l, st, wg_ln));
-  if (l->patches_ready[2] && wg_ln.st != fac_ln.st) ACX_CUDA(cudaStreamWaitEvent(wg_ln.st, l->patches_ready[2], 0));
-  ACX_TRY(weight_grad(l, 2, l->P3, l->dpre3, N * 49, 1.0f, wg_ln));
-  if (fisher) ACX_TRY(output_factor(l, 2, offset_rows(l->dpre3, (size_t)N * 49), N * 49, wg_ln));
+  if (l->patches_ready[2] && wg_ln.st != fac_ln.st) {
+    ACX_TRY(fork_lane(l, st, wg_ln));
+    ACX_CUDA(cudaStreamWaitEvent(wg_ln.st, l->patches_ready[2], 0));
+  }
+  ACX_TRY(fan_out(2, l->P3, l->dpre3, N * 49));
   ACX_TRY(conv_dgrad(l, 2, l->dpre3, l->act2.p[0], l->dpre2, RB, main_ln));
   // ---- conv2
-  ACX_TRY(fork_lane(l, st, wg_ln));
-  if (l->patches_ready[1] && wg_ln.st != fac_ln.st) ACX_CUDA(cudaStreamWaitEvent(wg_ln.st, l->patches_ready[1], 0));
-  ACX_TRY(weight_grad(l, 1, l->P2, l->dpre2, N * 81, 1.0f, wg_ln));
-  if (fisher) ACX_TRY(output_factor(l, 1, offset_rows(l->dpre2, (size_t)N * 81), N * 81, wg_ln));
+  if (l->patches_ready[1] && wg_ln.st != fac_ln.st) {
+    ACX_TRY(fork_lane(l, st, wg_ln));
+    ACX_CUDA(cudaStreamWaitEvent(wg_ln.st, l->patches_ready[1], 0));
+  }
+  ACX_TRY(fan_out(1, l->P2, l->dpre2, N * 81));
   ACX_TRY(conv_dgrad(l, 1, l->dpre2, l->act1.p[0], l->dpre1, RB, main_ln));
   // ---- conv1 (no input gradient: observations are constants, envs/atari/model.py:101-104)
   if (fisher) {
-    ACX_TRY(fork_lane(l, st, wg_ln));
-    ACX_TRY(output_factor(l, 0, offset_rows(l->dpre1, (size_t)N * 400), N * 400, wg_ln));
+    ACX_TRY(fork_lane(l, st, gf_ln));
+    ACX_TRY(output_factor(l, 0, offset_rows(l->dpre1, (size_t)N * 400), N * 400, gf_ln));
   }
-  // last link of the chain: the weight GEMM stays on the caller's stream, its bias row goes to the (by now idle) factor lane
-  ACX_TRY(fork_lane(l, st, fac_ln));
-  ACX_TRY(bias_grad(l, 0, l->dpre1, N * 400, fac_ln));
+  // last link of the chain: the weight GEMM stays on the caller's stream, its bias row goes to the column-sum lane
+  ACX_TRY(fork_lane(l, st, cs_ln));
+  ACX_TRY(bias_grad(l, 0, l->dpre1, N * 400, cs_ln));
   ACX_TRY(weight_grad(l, 0, l->P1, l->dpre1, N * 400, 1.0f / 255.0f, main_ln, false));
   mark(l, 3, st);
   // ---- join: the caller's stream now also covers the 11 batch factor statistics and every weight gradient
   ACX_TRY(join_lane(l, fac_ln, st));
   ACX_TRY(join_lane(l, wg_ln, st));
+  ACX_TRY(join_lane(l, gf_ln, st));
+  ACX_TRY(join_lane(l, cs_ln, st));
   mark(l, 4, st);
   return 0;
 }

@@ -56,7 +56,7 @@ class EngineConfig:
     precision: int = 0
     use_graphs: bool = True                 # replay each update as CUDA graphs (captured on the second use of a variant)
     conv_impl: int = 0                      # 0 = gather-form conv2/conv3 input gradient (acx_conv), 1 = GEMM + col2im
-    num_lanes: int = 0                      # 0 = default (3 concurrent lanes inside an update), 1 = serial
+    num_lanes: int = 0                      # 0 = default (5 concurrent lanes inside an update), 1 = serial
     seed: int = 0
     cov_init: str = "zero"                  # "zero" (kfac 0.1.x) | "identity" (older tf.contrib.kfac)
     zero_debias: bool = True                # U3

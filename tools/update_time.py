@@ -12,7 +12,7 @@ import synth  # noqa: E402
 from actorcritic_b200 import engine as eng  # noqa: E402
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 100
-e = eng.Engine(eng.EngineConfig(num_envs=32, num_steps=20, conv3_filters=32, seed=1))
+e = eng.Engine(eng.EngineConfig(num_envs=32, num_steps=20, conv3_filters=32, seed=1, num_lanes=int(os.environ.get('LANES', '0'))))
 e.set_params(eng.orthogonal_init(4, 32, seed=0))
 batches = [synth.rollout(10 + i, 32, 20, 4) for i in range(8)]
 res = [{k: torch.from_numpy(v if v.dtype != bool else v.astype("uint8")).cuda() for k, v in b.items()} for b in batches]
@@ -27,5 +27,5 @@ with torch.cuda.stream(e.stream):
         e.update(res[i % 8], fetch=False)
     b.record()
     torch.cuda.synchronize()
-knobs = {k: v for k, v in os.environ.items() if k.startswith("ACX_")}
+knobs = {k: v for k, v in os.environ.items() if k.startswith("ACX_") or k == "LANES"}
 print("ms_per_update %.4f" % (a.elapsed_time(b) / steps), knobs)
