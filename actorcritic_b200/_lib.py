@@ -77,6 +77,7 @@ SIGNATURES = {
     "acx_split_planes": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                         ctypes.POINTER(_P), ctypes.c_int, ctypes.c_int, _P]),
     "acx_debug_set_mn_desc": (None, [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]),
+    "acx_debug_set_fuse_reduce": (None, [ctypes.c_int]),
     "acx_debug_tc_error": (ctypes.c_int, []),
     "acx_gemm_enable_timing": (ctypes.c_int, [ctypes.c_int]),
     "acx_gemm_last_ms": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float)]),

@@ -22,6 +22,7 @@
 //
 // Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM + MMA issuer, warps 2..9 epilogue (two per TMEM lane quarter).
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -43,13 +44,16 @@ constexpr int CV_SMEM_LIMIT = 232448;
 constexpr int CV_SMEM_FIXED = CV_EPI_BYTES + 256;
 
 struct ConvTcParams {
-  int num_tiles, ts, rows_valid, total_rows;   // a tile = ts samples = rows_valid GEMM rows (<= 128)
+  int num_tiles, ts, rows_valid, samples;      // a tile = ts samples x (by x bx) cells of the location grid = rows_valid GEMM rows (<= 128)
+  int gx, gy, bx, by, nx, cells, ydim;         // location grid gx x gy, cut into nx x (gy / by) boxes of bx x by cells (cells = boxes per
+                                               // sample group); ydim = the box coordinate (2 or 3) that carries the grid row
   int bn;                                      // GEMM columns (= tile width: 32, 64 or 128)
   int kb_total, nsub, num_sub;                 // k-blocks of 64; sub-tiles per k-block (1 or 2); sub-tiles over all of K
   int sub_bytes;                               // bytes one sub-tile box delivers
   signed char tc1[CV_MAX_SUB], tc2[CV_MAX_SUB], tc3[CV_MAX_SUB];   // box coordinates of every sub-tile (dims 1..3)
   int num_pairs, pair_a[6], pair_b[6], npa, npb, stages;
-  int lo_from_tile, num_pairs_lo;              // tiles >= lo_from_tile accumulate only the first num_pairs_lo plane pairs
+  int lo_from_tile, num_pairs_lo;              // tiles >= lo_from_tile accumulate only the first num_pairs_lo plane pairs (tiles are
+                                               // ordered sample group first)
   // epilogue
   int dgrad;                                   // 0: output row = GEMM row; 1: pixel-shuffle scatter
   int hw_in, c_in, s, hq;
@@ -113,7 +117,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
       // ===== TMA producer: per k-block one box per (plane, sub-tile) of the activation + the weight tile =====
       int it = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int sample0 = tile * p.ts;
+        const int grp = tile / p.cells, cell = tile - grp * p.cells;
+        const int cy = cell / p.nx, cx = cell - cy * p.nx;
+        const int sample0 = grp * p.ts, x0 = cx * p.bx, y0 = cy * p.by;
+        const int y2 = p.ydim == 2 ? y0 : 0, y3 = p.ydim == 3 ? y0 : 0;
         for (int kb = 0; kb < p.kb_total; ++kb, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
@@ -129,7 +136,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
             const CUtensorMap* ma = i == 0 ? &ta0 : (i == 1 ? &ta1 : &ta2);
             for (int j = 0; j < nload; ++j) {
               const int t = kb * p.nsub + j;
-              tma_load_5d(a_s + i * CV_A_TILE + j * sub_tile_bytes, ma, &full_bar[s], 0, p.tc1[t], p.tc2[t], p.tc3[t], sample0);
+              tma_load_5d(a_s + i * CV_A_TILE + j * sub_tile_bytes, ma, &full_bar[s], 0, p.tc1[t] + x0, p.tc2[t] + y2, p.tc3[t] + y3, sample0);
             }
           }
           for (int i = 0; i < p.npb && !(p.debug & 2); ++i) {
@@ -235,16 +242,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
     const bf16* const mask = p.mask;
     constexpr uint32_t NO_ROW = 0xffffffffu;
     uint32_t row_off[NIT];   // element offset of tile row (q*32 + rsub + t*RPI) relative to the tile's base
+    int row_smp[NIT];        // sample of that row inside the tile's sample group
+    const int img = p.hw_in * p.hw_in * p.c_in;   // input gradient: elements of one sample of the output tensor
 #pragma unroll
     for (int t = 0; t < NIT; ++t) {
       const int i = q * 32 + rsub + t * RPI;
       row_off[t] = NO_ROW;
+      row_smp[t] = 0;
       if (i < p.rows_valid && !(p.debug & 8)) {
-        if (!p.dgrad) {
-          row_off[t] = (uint32_t)(i * p.ldcp);
-        } else {   // row (a, b) of the sample -> the s x s output cell at pixel (s*a, s*b)
-          const int a = i / p.hq, b = i - a * p.hq;
-          row_off[t] = (uint32_t)(((p.s * a) * p.hw_in + p.s * b) * p.c_in);
+        const int per = p.bx * p.by;
+        const int sl = i / per, rem = i - sl * per;
+        const int yy = rem / p.bx, xx = rem - yy * p.bx;
+        row_smp[t] = sl;
+        if (!p.dgrad) {   // output row = (sample, y, x) of the gx x gy grid
+          row_off[t] = (uint32_t)((sl * p.gx * p.gy + yy * p.gx + xx) * p.ldcp);
+        } else {          // row (a, b) of the sample -> the s x s output cell at pixel (s*a, s*b)
+          row_off[t] = (uint32_t)(sl * img + ((p.s * yy) * p.hw_in + p.s * xx) * p.c_in);
         }
       }
     }
@@ -267,7 +280,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
         }
       }
     }
-    const size_t tile_stride = p.dgrad ? (size_t)p.hw_in * p.hw_in * p.c_in : (size_t)p.rows_valid * p.ldcp;
     if (grp < nchunks) {   // BN = 32: the second warp of each quarter has nothing to do (and is not counted by acc_empty)
       int lt = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
@@ -280,11 +292,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
         if (etrace && lane == 0 && lt == 0) g_conv_trace[6] = te;
         if (etrace && lane == 0) g_conv_trace[7] = clock64() - g_conv_trace[6];
         tc_fence_after();
-        const size_t base = (size_t)tile * tile_stride;
-        const size_t mbase = p.dgrad ? (size_t)(tile % p.mask_samples) * tile_stride : 0;
-        // forward: rows of the last tile beyond the batch do not exist
-        const uint32_t row_limit =
-            p.dgrad ? 0xfffffffeu : (uint32_t)min(p.rows_valid, p.total_rows - tile * p.rows_valid) * (uint32_t)p.ldcp;
+        const int sgrp = tile / p.cells, cell = tile - sgrp * p.cells;
+        const int cy = cell / p.nx, cx = cell - cy * p.nx;
+        const int sample0 = sgrp * p.ts, x0 = cx * p.bx, y0 = cy * p.by;
+        const size_t base = p.dgrad ? (size_t)sample0 * img + (size_t)(((p.s * y0) * p.hw_in + p.s * x0) * p.c_in)
+                                    : ((size_t)sample0 * p.gx * p.gy + (size_t)(y0 * p.gx + x0)) * p.ldcp;
+        // rows of samples beyond the batch do not exist; the ReLU mask of sample r is that of sample r % mask_samples
+        const int smp_limit = p.samples - sample0;
+        bool row_ok[NIT];
+        size_t mrow[NIT];
+#pragma unroll
+        for (int t = 0; t < NIT; ++t) {
+          row_ok[t] = row_off[t] != NO_ROW && row_smp[t] < smp_limit;
+          const int sm = sample0 + row_smp[t];
+          mrow[t] = base + row_off[t] - (size_t)(sm - sm % p.mask_samples) * img;
+        }
         for (int ch = grp, c = 0; ch < nchunks; ch += 2, ++c) {
           uint32_t raw[32];
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + ch * CH);
@@ -312,12 +334,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
 #pragma unroll
             for (int t = 0; t < NIT; ++t) {
               mw[t] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);   // bf16 1.0: keep
-              if (row_off[t] < row_limit) mw[t] = __ldg(reinterpret_cast<const uint4*>(mask + mbase + row_off[t] + coff));
+              if (row_ok[t]) mw[t] = __ldg(reinterpret_cast<const uint4*>(mask + mrow[t] + coff));
             }
           }
 #pragma unroll
           for (int t = 0; t < NIT; ++t) {
-            if (row_off[t] < row_limit) {
+            if (row_ok[t]) {
               const int r = rsub + t * RPI;
               const float4 a4 = *reinterpret_cast<const float4*>(st + r * 32 + (((2 * cg) ^ (r & 7)) << 2));
               const float4 c4 = *reinterpret_cast<const float4*>(st + r * 32 + (((2 * cg + 1) ^ (r & 7)) << 2));
@@ -549,6 +571,51 @@ static int weight_maps(const Planes& w, int rows, int kcols, int bn, CUtensorMap
   return 0;
 }
 
+// How a tile's 128 GEMM rows are cut out of the (samples x gy x gx) location space: a box of bx x by grid cells (bx | gx,
+// by | gy, so that no box straddles the grid edge) of ts consecutive samples.  All tiles cost the same (the MMA always runs
+// 128 rows), so the cut that needs the fewest rounds of the persistent grid wins; ties go to the larger spatial box (fewer,
+// longer runs per TMA box).  Whole samples per tile (bx = gx, by = gy: round 1's cut) fill only 38 - 78 % of the rows of the
+// Nature-CNN's 7x7 / 9x9 / 10x10 grids.  ACX_CONV_PACK=0 restores that cut.
+static void pick_tile_cut(int gx, int gy, int samples, int* bx, int* by, int* ts) {
+  static int pack = -1;
+  if (pack < 0) {
+    const char* e = getenv("ACX_CONV_PACK");
+    pack = e ? atoi(e) : 1;
+  }
+  if (const char* e = getenv("ACX_CONV_CUT")) {   // triage: "bx,by,ts" forces the cut (tools/conv_one.py)
+    int a = 0, b = 0, c = 0;
+    if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && a >= 1 && b >= 1 && c >= 1 && gx % a == 0 && gy % b == 0 && a * b * c <= CV_BM) {
+      *bx = a;
+      *by = b;
+      *ts = c < samples ? c : samples;
+      return;
+    }
+  }
+  const int sms = conv_num_sms();
+  long long best_rounds = -1;
+  int best_area = 0;
+  for (int cy = 1; cy <= gy; ++cy) {
+    if (gy % cy) continue;
+    for (int cx = 1; cx <= gx; ++cx) {
+      if (gx % cx) continue;
+      const int area = cx * cy;
+      if (area > CV_BM) continue;
+      if (!pack && (cx != gx || cy != gy)) continue;
+      int t = CV_BM / area;
+      if (t > samples) t = samples;
+      const long long tiles = (long long)(gx / cx) * (gy / cy) * ceil_div(samples, t);
+      const long long rounds = (tiles + sms - 1) / sms;
+      if (best_rounds < 0 || rounds < best_rounds || (rounds == best_rounds && area > best_area)) {
+        best_rounds = rounds;
+        best_area = area;
+        *bx = cx;
+        *by = cy;
+        *ts = t;
+      }
+    }
+  }
+}
+
 // y = relu(conv(x, W) + bias) as bf16 planes; x planes [samples, hw_in, hw_in, c_in], wT planes [c_out, k*k*c_in]
 int conv_tc_forward(const Planes& x, const Planes& wT, const ConvGeom& g, int samples, const float* bias, int relu, const Planes& y,
                     int num_pairs, const int* pair_a, const int* pair_b, cudaStream_t st) {
@@ -559,13 +626,16 @@ int conv_tc_forward(const Planes& x, const Planes& wT, const ConvGeom& g, int sa
   memset(&p, 0, sizeof(p));
   int r = fill_pairs(&p, num_pairs, pair_a, pair_b, x.n, wT.n);
   if (r) return r;
-  const int rps = g.hw_out * g.hw_out;
-  p.ts = CV_BM / rps;
-  p.rows_valid = p.ts * rps;
-  p.num_tiles = ceil_div(samples, p.ts);
+  p.gx = p.gy = g.hw_out;
+  pick_tile_cut(p.gx, p.gy, samples, &p.bx, &p.by, &p.ts);
+  p.nx = p.gx / p.bx;
+  p.cells = p.nx * (p.gy / p.by);
+  p.ydim = 3;                            // the grid row is the yq coordinate of the 5-D view
+  p.rows_valid = p.ts * p.bx * p.by;
+  p.num_tiles = p.cells * ceil_div(samples, p.ts);
   p.lo_from_tile = p.num_tiles;          // every tile at full precision
   p.num_pairs_lo = num_pairs;
-  p.total_rows = samples * rps;
+  p.samples = samples;
   p.bn = g.c_out;
   const int K = g.k * g.k * g.c_in;
   p.kb_total = K / CV_BK;
@@ -600,7 +670,7 @@ int conv_tc_forward(const Planes& x, const Planes& wT, const ConvGeom& g, int sa
     const bf16* ptr = x.p[i < x.n ? i : 0];
     const long long dim[5] = {64, hq, g.s, hq, samples};
     const long long stride[4] = {64 * 2, row * 2, row * g.s * 2, row * g.hw_in * 2};
-    const int box[5] = {64, g.hw_out, 1, g.hw_out, p.ts};
+    const int box[5] = {64, p.bx, 1, p.by, p.ts};
     r = get_view_map(ptr, 5, dim, stride, box, 128, &ta[i]);
     if (r) return r;
   }
@@ -623,12 +693,18 @@ int conv_tc_dgrad(const Planes& gout, const Planes& wD, const ConvGeom& g, int s
   memset(&p, 0, sizeof(p));
   int r = fill_pairs(&p, num_pairs, pair_a, pair_b, gout.n, wD.n);
   if (r) return r;
-  p.ts = 1;
-  p.rows_valid = hq * hq;
-  p.num_tiles = samples;
-  p.lo_from_tile = lo_from_sample >= 0 ? lo_from_sample : samples;   // one sample per tile
+  p.gx = p.gy = hq;
+  pick_tile_cut(p.gx, p.gy, samples, &p.bx, &p.by, &p.ts);
+  p.nx = p.gx / p.bx;
+  p.cells = p.nx * (p.gy / p.by);
+  p.ydim = 2;                            // the grid row is coordinate 2 (a) of the gradient view
+  p.rows_valid = p.ts * p.bx * p.by;
+  p.num_tiles = p.cells * ceil_div(samples, p.ts);
+  // tiles are ordered sample group first: the groups that hold only samples >= lo_from_sample run at the lower precision (a
+  // group that straddles the boundary keeps the full one)
+  p.lo_from_tile = lo_from_sample >= 0 ? p.cells * ceil_div(lo_from_sample, p.ts) : p.num_tiles;
   p.num_pairs_lo = lo_from_sample >= 0 ? num_pairs_lo : num_pairs;
-  p.total_rows = samples * p.rows_valid;
+  p.samples = samples;
   p.bn = g.s * g.s * g.c_in;
   const int K = m * m * g.c_out;
   p.kb_total = ceil_div(K, CV_BK);
@@ -664,7 +740,7 @@ int conv_tc_dgrad(const Planes& gout, const Planes& wD, const ConvGeom& g, int s
     const bf16* ptr = gout.p[i < gout.n ? i : 0];
     const long long dim[5] = {g.c_out, g.hw_out, g.hw_out, 1, samples};
     const long long stride[4] = {(long long)g.c_out * 2, row * 2, row * g.hw_out * 2, row * g.hw_out * 2};
-    const int box[5] = {g.c_out, hq, hq, 1, 1};
+    const int box[5] = {g.c_out, p.bx, p.by, 1, p.ts};
     r = get_view_map(ptr, 5, dim, stride, box, g.c_out == 64 ? 128 : 64, &ta[i]);
     if (r) return r;
   }

@@ -56,7 +56,18 @@ struct TcParams {
   int ws_ld;
   long long ws_split_stride;  // floats
   uint32_t mn_lbo, mn_sbo, mn_kstep;
+  // split-K reduction inside the kernel (no finalize launch): the CTA that completes a group of RED_GROUP consecutive
+  // splits of a tile sums them in split order; with more than one group the group sums go to `ws2` and the CTA that
+  // completes the last group sums those in group order - every association is fixed, so the result does not depend on
+  // which CTA arrives last.  Counters: per tile `groups` group counters + 1 tile counter, zero on entry, left zero.
+  int fuse, groups;
+  float* ws2;
+  long long ws2_stride;   // floats between group sums
+  int* counters;
 };
+constexpr int RED_GROUP = 8;
+constexpr size_t kFusedReduceBytes = 256 << 10;   // partial sums one CTA may have to read back for one tile
+constexpr int RED_COUNTER_BYTES = 16384;   // head of the workspace: 4096 counters
 
 // ------------------------------------------------------------------------------------------------
 // shared epilogue math: one result element -> alpha, bias, ReLU, mask
@@ -112,7 +123,84 @@ __device__ __forceinline__ void store_pair(const OutParams& o, int m, int n, flo
   }
 }
 
+// four consecutive result columns (n % 4 == 0) of row m: epilogue math + stores, ragged edges handled element-wise
+__device__ __forceinline__ void emit4(const OutParams& o, int m, int n, float4 acc) {
+  if (m >= o.m || n >= o.n) return;
+  const bool c_vec = o.c == nullptr || ((o.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(o.c) & 15) == 0);
+  if (n + 3 < o.n && c_vec && (o.ldcp & 3) == 0) {
+    float v[4] = {o.alpha * acc.x, o.alpha * acc.y, o.alpha * acc.z, o.alpha * acc.w};
+    if (o.bias) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] += __ldg(o.bias + n + j);
+    }
+    if (o.relu) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.0f);
+    }
+    if (o.mask) {
+      const bf16* mk = o.mask + (size_t)(m % o.mask_rows) * o.mask_ld + n;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (!(__bfloat162float(mk[j]) > 0.0f)) v[j] = 0.0f;
+    }
+    if (o.c) *reinterpret_cast<float4*>(o.c + (size_t)m * o.ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
+    if (o.c_num_planes > 0) {
+      uint2 ph, pm, pl;
+      split3x4(v[0], v[1], v[2], v[3], ph, pm, pl);
+      const size_t idx = (size_t)m * o.ldcp + n;
+      *reinterpret_cast<uint2*>(o.cp[0] + idx) = ph;
+      if (o.c_num_planes > 1) *reinterpret_cast<uint2*>(o.cp[1] + idx) = pm;
+      if (o.c_num_planes > 2) *reinterpret_cast<uint2*>(o.cp[2] + idx) = pl;
+    }
+    return;
+  }
+  const float a[4] = {acc.x, acc.y, acc.z, acc.w};
+  for (int j = 0; j < 4; ++j) {
+    if (n + j < o.n) {
+      store_value(o, m, n + j, finish_value(o, m, n + j, a[j]));
+    } else if (o.c_num_planes > 0 && n + j < o.ldcp) {   // the padding columns of plane outputs stay zero
+      const size_t idx = (size_t)m * o.ldcp + n + j;
+      o.cp[0][idx] = __float2bfloat16(0.0f);
+      if (o.c_num_planes > 1) o.cp[1][idx] = __float2bfloat16(0.0f);
+      if (o.c_num_planes > 2) o.cp[2][idx] = __float2bfloat16(0.0f);
+    }
+  }
+}
 
+// One warp sums `count` partial planes (`pstride` floats apart, row stride `ld`) of the 32 x 32 block at (m0, n0) in plane
+// order.  Lane layout: 8 lanes x float4 per row, 4 rows per pass, 8 passes: acc[t] = row m0 + (lane >> 3) + 4 t, columns
+// n0 + 4 (lane & 7) .. + 3.  Partials were written by other SMs: read through L2.
+__device__ __forceinline__ void reduce_block(const float* __restrict__ src, long long pstride, int count, int ld, int m0, int n0,
+                                             int lane, float4 (&acc)[8]) {
+  const float* base = src + (size_t)(m0 + (lane >> 3)) * ld + n0 + 4 * (lane & 7);
+#pragma unroll
+  for (int t = 0; t < 8; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int sidx = 0;
+  for (; sidx + 1 < count; sidx += 2, base += 2 * pstride) {   // two partials (16 loads per thread) in flight; summed in plane order
+    float4 x[8], y[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) x[t] = __ldcg(reinterpret_cast<const float4*>(base + (size_t)(4 * t) * ld));
+#pragma unroll
+    for (int t = 0; t < 8; ++t) y[t] = __ldcg(reinterpret_cast<const float4*>(base + pstride + (size_t)(4 * t) * ld));
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      acc[t].x = (acc[t].x + x[t].x) + y[t].x;
+      acc[t].y = (acc[t].y + x[t].y) + y[t].y;
+      acc[t].z = (acc[t].z + x[t].z) + y[t].z;
+      acc[t].w = (acc[t].w + x[t].w) + y[t].w;
+    }
+  }
+  if (sidx < count) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const float4 x = __ldcg(reinterpret_cast<const float4*>(base + (size_t)(4 * t) * ld));
+      acc[t].x += x.x;
+      acc[t].y += x.y;
+      acc[t].z += x.z;
+      acc[t].w += x.w;
+    }
+  }
+}
 
 constexpr int MAX_STAGES = 8;
 constexpr int GEMM_THREADS = 320;                       // warp 0 TMA producer, warp 1 MMA, warps 2..9 epilogue
@@ -130,13 +218,17 @@ constexpr int EPI_BYTES = 8 * 32 * 32 * 4;              // one XOR-swizzled 32 x
 // MAJOR 0: A stored [M,K], B stored [N,K] (both K-major).  MAJOR 1: A stored [K,M], B stored [K,N] (both MN-major).
 // Work items (tile, split) are taken round-robin: w = blockIdx.x, + gridDim.x, ...
 // ------------------------------------------------------------------------------------------------
-__device__ long long g_gemm_trace[4];   // triage: total / waiting for operands / waiting for an accumulator / k-blocks
+__device__ long long g_gemm_trace[12];   // triage: total / waiting for operands / waiting for an accumulator / k-blocks
 
 template <int MAJOR, bool PATCH>
 __global__ void __launch_bounds__(GEMM_THREADS + (PATCH ? PATCH_THREADS : 0), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ CUtensorMap ta1,
                const __grid_constant__ CUtensorMap ta2, const __grid_constant__ CUtensorMap tb0,
-               const __grid_constant__ CUtensorMap tb1, const __grid_constant__ CUtensorMap tb2, const TcParams p) {
+               const __grid_constant__ CUtensorMap tb1, const __grid_constant__ CUtensorMap tb2,
+               const __grid_constant__ TcParams p) {
+  // (p is __grid_constant__: the reduction path hands `p.out` to helper functions by reference; without it, taking the
+  // address of a parameter makes every later field read a generic-address load that is re-issued after each global store -
+  // measured ~700 cycles per store instruction)
   extern __shared__ __align__(1024) uint8_t smem_raw[];   // 128B-swizzled TMA tiles need 1024-byte alignment
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem_raw) & 1023u) != 0) {                 // never expected; fail loudly instead of corrupting tiles
@@ -157,6 +249,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
   uint64_t* acc_full = empty_bar + MAX_STAGES;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  volatile int* red_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);   // split-K reduction: the arrival order of this CTA
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tmem_cols = p.panel ? 512u : (uint32_t)(2 * BN);   // 64, 128 or 256 (two accumulators); panel: three + pad
@@ -651,6 +744,101 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
         __syncwarp();
       }
       }
+      if (to_ws && p.fuse) {
+        // ===== split-K reduction by whichever CTA completes a group / the tile (see TcParams) =====
+        auto epi_bar = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };   // the 8 epilogue warps
+        const int ew = warp - 2;
+        const int tile_id = p.panel ? 0 : w - split * p.num_tiles;
+        int* cnt = p.counters + tile_id * (p.groups + 1);
+        const int g = split / RED_GROUP;
+        const int gsize = min(RED_GROUP, p.splits - g * RED_GROUP);
+        const bool rtrace = p.trace != 0 && blockIdx.x == 0 && threadIdx.x == 64;
+        if (rtrace) g_gemm_trace[4] = clock64();
+        __threadfence();   // this thread's partial sums are visible device-wide before the CTA is counted
+        if (rtrace) g_gemm_trace[5] = clock64();
+        epi_bar();
+        if (threadIdx.x == 64) *red_flag = atomicAdd(&cnt[g], 1);
+        epi_bar();
+        if (rtrace) g_gemm_trace[6] = clock64();
+        if (*red_flag == gsize - 1) {
+          __threadfence();
+          if (rtrace) g_gemm_trace[7] = clock64();
+          const int tm0 = p.panel ? 0 : tm * BM, tn0 = p.panel ? 0 : tn * BN;
+          const int bw = (p.panel ? 2 * BN : BN) >> 5, bh = (p.panel ? 2 * BM : BM) >> 5;   // 32 x 32 blocks of the work item
+          // lower blocks of a symmetric result are written as mirrors of the upper ones; blocks outside the result do not exist
+          auto skip = [&](int m0, int n0) { return m0 >= om || n0 >= on || (p.symmetric && m0 > n0); };
+          bool final_pass = p.groups == 1;
+          if (!final_pass) {
+            for (int b = ew; b < bw * bh; b += 8) {
+              const int bi = b / bw, bj = b - bi * bw;
+              const int m0 = tm0 + bi * 32, n0 = tn0 + bj * 32;
+              if (skip(m0, n0)) continue;
+              float4 acc[8];
+              reduce_block(ws + (size_t)g * RED_GROUP * ws_split_stride, ws_split_stride, gsize, ws_ld, m0, n0, lane, acc);
+              float* dst = p.ws2 + (size_t)g * p.ws2_stride + (size_t)(m0 + (lane >> 3)) * ws_ld + n0 + 4 * (lane & 7);
+#pragma unroll
+              for (int t = 0; t < 8; ++t) *reinterpret_cast<float4*>(dst + (size_t)(4 * t) * ws_ld) = acc[t];
+            }
+            __threadfence();
+            epi_bar();
+            if (threadIdx.x == 64) *red_flag = atomicAdd(&cnt[p.groups], 1);
+            epi_bar();
+            final_pass = *red_flag == p.groups - 1;
+            if (final_pass) __threadfence();
+          }
+          if (final_pass) {
+            const float* src = p.groups == 1 ? ws : p.ws2;
+            const long long pst = p.groups == 1 ? ws_split_stride : p.ws2_stride;
+            const int cntp = p.groups == 1 ? p.splits : p.groups;
+            for (int b = ew; b < bw * bh; b += 8) {
+              const int bi = b / bw, bj = b - bi * bw;
+              const int m0 = tm0 + bi * 32, n0 = tn0 + bj * 32;
+              if (skip(m0, n0)) continue;
+              float4 acc[8];
+              if (rtrace && b == ew) g_gemm_trace[8] = clock64();
+              reduce_block(src, pst, cntp, ws_ld, m0, n0, lane, acc);
+              if (rtrace && b == ew) g_gemm_trace[9] = clock64();
+              // The sums go through the warp's staging tile (16-byte groups XOR-swizzled by the row) and ONE copy of the
+              // epilogue code walks them - first the block itself, then (symmetric, off-diagonal) its mirror image read
+              // transposed.  With the 16 calls unrolled this section was ~200 KB of straight-line code executed once per
+              // block: every instruction fetch missed (measured ~700 cycles per store instruction).
+              __syncwarp();
+#pragma unroll
+              for (int t = 0; t < 8; ++t) {
+                const int r = (lane >> 3) + 4 * t;
+                *reinterpret_cast<float4*>(st + r * 32 + (((lane & 7) ^ (r & 7)) << 2)) = acc[t];
+              }
+              __syncwarp();
+              const int passes = (p.symmetric && m0 < n0) ? 16 : 8;
+#pragma unroll 1
+              for (int it = 0; it < passes; ++it) {
+                const int r = (lane >> 3) + 4 * (it & 7), c4 = lane & 7;
+                float4 v;
+                int mm, nn;
+                if (it < 8) {
+                  v = *reinterpret_cast<const float4*>(st + r * 32 + ((c4 ^ (r & 7)) << 2));
+                  mm = m0 + r;
+                  nn = n0 + 4 * c4;
+                } else {   // row r of the mirrored block = column r of the upper one; its columns 4 c4 .. + 3 = rows of the upper one
+                  const int r0 = 4 * c4;
+                  v.x = st[(r0 + 0) * 32 + ((((r >> 2) ^ ((r0 + 0) & 7)) << 2) + (r & 3))];
+                  v.y = st[(r0 + 1) * 32 + ((((r >> 2) ^ ((r0 + 1) & 7)) << 2) + (r & 3))];
+                  v.z = st[(r0 + 2) * 32 + ((((r >> 2) ^ ((r0 + 2) & 7)) << 2) + (r & 3))];
+                  v.w = st[(r0 + 3) * 32 + ((((r >> 2) ^ ((r0 + 3) & 7)) << 2) + (r & 3))];
+                  mm = n0 + r;
+                  nn = m0 + r0;
+                }
+                emit4(o, mm, nn, v);
+              }
+              __syncwarp();
+              if (rtrace && b == ew) g_gemm_trace[10] = clock64();
+            }
+            if (threadIdx.x == 64 && p.groups > 1) cnt[p.groups] = 0;
+            if (rtrace) g_gemm_trace[11] = clock64();
+          }
+          if (threadIdx.x == 64) cnt[g] = 0;
+        }
+      }
     }
   }
   tc_fence_before();
@@ -785,9 +973,12 @@ static bool finalize_vec4_ok(const OutParams& o, int ws_ld, long long ws_split_s
 // symmetric results: only upper 128-tiles were computed.  Four CTAs (32 x 8 threads, one row quarter each) per 32 x 32 block
 // pair (bi <= bj): every thread reduces 1 element of the upper block over the splits (row-contiguous, independent loads),
 // stores it, and the 8 x 32 strip is transposed through shared memory and stored again as part of the mirrored block.
-__global__ void __launch_bounds__(256) gemm_finalize_sym_kernel(OutParams o, const float* __restrict__ ws, int ws_ld,
-                                                                long long ws_split_stride, int splits, int nblk) {
+__global__ void __launch_bounds__(1024) gemm_finalize_sym_kernel(OutParams o, const float* __restrict__ ws, int ws_ld,
+                                                                 long long ws_split_stride, int splits, int nblk) {
+  // blockDim = (256, L): L split lanes per element (deep splits - the conv1 panel SYRK has 143 - need more loads in flight
+  // than one thread per element provides); lane z sums splits z, z + L, ... and the lanes are combined in lane order
   __shared__ float tile[8][33];
+  __shared__ float red[3][256];
   int t = blockIdx.x, bi = 0, cnt = nblk;
   while (t >= cnt) {
     t -= cnt;
@@ -796,34 +987,46 @@ __global__ void __launch_bounds__(256) gemm_finalize_sym_kernel(OutParams o, con
   }
   const int bj = bi + t;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int L = blockDim.y, tz = threadIdx.y;
   const int r0 = blockIdx.y * 8;   // row quarter of the block
   {
     const int m = bi * 32 + r0 + ty, n = bj * 32 + tx;
     float acc = 0.0f;
-    if (m < o.m && n < o.n) {
+    const bool in = m < o.m && n < o.n;
+    if (in) {
       const float* src = ws + (size_t)m * ws_ld + n;
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f;
-      int s = 0;
-      for (; s + 7 < splits; s += 8) {   // fixed association order: deterministic; 8 loads in flight per thread
+      int s = tz;
+      for (; s + 7 * L < splits; s += 8 * L) {   // fixed association order: deterministic; 8 loads in flight per thread
         a0 += src[(size_t)s * ws_split_stride];
-        a1 += src[(size_t)(s + 1) * ws_split_stride];
-        a2 += src[(size_t)(s + 2) * ws_split_stride];
-        a3 += src[(size_t)(s + 3) * ws_split_stride];
-        a4 += src[(size_t)(s + 4) * ws_split_stride];
-        a5 += src[(size_t)(s + 5) * ws_split_stride];
-        a6 += src[(size_t)(s + 6) * ws_split_stride];
-        a7 += src[(size_t)(s + 7) * ws_split_stride];
+        a1 += src[(size_t)(s + L) * ws_split_stride];
+        a2 += src[(size_t)(s + 2 * L) * ws_split_stride];
+        a3 += src[(size_t)(s + 3 * L) * ws_split_stride];
+        a4 += src[(size_t)(s + 4 * L) * ws_split_stride];
+        a5 += src[(size_t)(s + 5 * L) * ws_split_stride];
+        a6 += src[(size_t)(s + 6 * L) * ws_split_stride];
+        a7 += src[(size_t)(s + 7 * L) * ws_split_stride];
       }
-      for (; s < splits; ++s) a0 += src[(size_t)s * ws_split_stride];
+      for (; s < splits; s += L) a0 += src[(size_t)s * ws_split_stride];
       acc = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
-      store_value(o, m, n, finish_value(o, m, n, acc));
     }
-    tile[ty][tx] = acc;
+    if (L > 1) {
+      if (tz > 0) red[tz - 1][threadIdx.x] = acc;
+      __syncthreads();
+      if (tz == 0)
+        for (int z = 1; z < L; ++z) acc += red[z - 1][threadIdx.x];
+    }
+    if (tz == 0) {
+      if (in) store_value(o, m, n, finish_value(o, m, n, acc));
+      tile[ty][tx] = acc;
+    }
   }
   if (bi == bj) return;
   __syncthreads();
+  if (tz != 0) return;
   // mirrored strip: rows bj*32 + (0..31), columns bi*32 + r0 + (0..7)
-  for (int e = threadIdx.x; e < 256; e += 256) {
+  {
+    const int e = threadIdx.x;
     const int rr = e >> 3, cc = e & 7;
     const int m = bj * 32 + rr, n = bi * 32 + r0 + cc;
     if (m < o.m && n < o.n) store_value(o, m, n, finish_value(o, m, n, tile[cc][rr]));
@@ -991,8 +1194,18 @@ static void fill_out(const acx_gemm_t* g, OutParams* o) {
 
 struct TcPlan {
   int bn, bk, npa, npb, stages, tiles_m, tiles_n, splits, kb_total, kb_per_split, to_ws, panel;
+  int fuse, groups;            // split-K reduction inside the kernel
+  size_t part_bytes;           // the split partials
   size_t ws_bytes;
 };
+static int g_fuse_mode = -1;
+static int fuse_reduce_enabled() {   // ACX_GEMM_FUSE_REDUCE / acx_debug_set_fuse_reduce: 0 = finalize launches, 1 = where cheap, 2 = always
+  if (g_fuse_mode < 0) {
+    const char* e = getenv("ACX_GEMM_FUSE_REDUCE");
+    g_fuse_mode = e ? atoi(e) : 1;
+  }
+  return g_fuse_mode;
+}
 
 constexpr int SMEM_LIMIT = 232448;                       // 227 KB per CTA on sm_100
 constexpr int SMEM_FIXED = EPI_BYTES + 256;              // epilogue staging + barriers (the base is 1024-aligned)
@@ -1049,10 +1262,30 @@ static void plan_tc(const acx_gemm_t* g, TcPlan* pl) {
     if (splits < 1) splits = 1;
   }
   if (splits > pl->kb_total) splits = pl->kb_total;
+  if (g->splits <= 0 && fuse_reduce_enabled() == 1 && !pl->panel) {
+    // shallow products (a handful of k-blocks per split: fc4 forward, the preconditioning GEMMs) are bound by pipeline
+    // fill, not by the number of CTAs: fewer splits, so that the reduction stays inside the kernel
+    const int max_fused = (int)(kFusedReduceBytes / ((size_t)BM * pl->bn * sizeof(float)));
+    if (splits > max_fused && pl->kb_total <= 8 * max_fused) splits = max_fused;
+  }
   pl->kb_per_split = ceil_div(pl->kb_total, splits);
   pl->splits = ceil_div(pl->kb_total, pl->kb_per_split);
   pl->to_ws = (pl->splits > 1 || g->symmetric) ? 1 : 0;
-  pl->ws_bytes = pl->to_ws ? (size_t)pl->splits * pl->tiles_m * BM * pl->tiles_n * pl->bn * sizeof(float) : 0;
+  const size_t plane_bytes = (size_t)pl->tiles_m * BM * pl->tiles_n * pl->bn * sizeof(float);
+  pl->part_bytes = pl->to_ws ? (size_t)pl->splits * plane_bytes : 0;
+  pl->groups = ceil_div(pl->splits, RED_GROUP);
+  const int num_tiles = pl->panel ? 1 : tiles;
+  // The reduction runs inside the kernel where ONE SM can sum a tile's partials in a few microseconds (measured: a single
+  // SM reads its peers' partials at some tens of GB/s, so deep splits of large tiles - the conv factor SYRKs and weight
+  // gradients - reduce faster in a finalize launch that spreads the sums over all SMs: 0.80 vs 1.32 ms/update with
+  // everything fused).  ACX_GEMM_FUSE_REDUCE: 0 = never, 1 = where cheap (default), 2 = always (two-level for > 8 splits).
+  const size_t tile_bytes = (size_t)(pl->panel ? 4 : 1) * BM * pl->bn * sizeof(float);
+  const bool cheap = pl->groups == 1 && (size_t)pl->splits * tile_bytes <= kFusedReduceBytes;
+  const int mode = fuse_reduce_enabled();
+  pl->fuse = (pl->to_ws && (mode >= 2 || (mode == 1 && cheap)) &&
+              (long long)num_tiles * (pl->groups + 1) * (long long)sizeof(int) <= RED_COUNTER_BYTES) ? 1 : 0;
+  // workspace: [counters (zero on entry, left zero) | split partials | group sums (two-level fused reduction only)]
+  pl->ws_bytes = pl->to_ws ? RED_COUNTER_BYTES + pl->part_bytes + (pl->fuse && pl->groups > 1 ? (size_t)pl->groups * plane_bytes : 0) : 0;
 }
 
 // optional timing probe: when enabled, every tensor-core kernel launch (the kernel alone, not the finalize step) is
@@ -1169,9 +1402,14 @@ static int gemm_tc(const acx_gemm_t* g, cudaStream_t st) {
   p.total_work = p.num_tiles * pl.splits;
   p.symmetric = g->symmetric;
   p.to_workspace = pl.to_ws;
-  p.ws = g->workspace;
   p.ws_ld = pl.tiles_n * pl.bn;
   p.ws_split_stride = (long long)pl.tiles_m * BM * p.ws_ld;
+  p.fuse = pl.fuse;
+  p.groups = pl.groups;
+  p.counters = reinterpret_cast<int*>(g->workspace);
+  p.ws = g->workspace + RED_COUNTER_BYTES / sizeof(float);   // partials always start behind the counter head
+  p.ws2 = p.ws + (size_t)pl.splits * p.ws_split_stride;
+  p.ws2_stride = p.ws_split_stride;
   {
     static int tr = -1;
     if (tr < 0) {
@@ -1194,21 +1432,23 @@ static int gemm_tc(const acx_gemm_t* g, cudaStream_t st) {
   else
     r = major == 0 ? launch_tc<0, false>(ta, tb, p, grid, smem, st) : launch_tc<1, false>(ta, tb, p, grid, smem, st);
   if (r) return r;
+  if (pl.fuse) return 0;   // the kernel reduced and finished its own split-K partials
   if (pl.to_ws && g->symmetric && g->n > 64) {
     const int nblk = ceil_div(g->n, 32);
-    gemm_finalize_sym_kernel<<<dim3(nblk * (nblk + 1) / 2, 4), 256, 0, st>>>(p.out, g->workspace, p.ws_ld, p.ws_split_stride, pl.splits, nblk);
+    const int zl = pl.splits >= 64 ? 4 : (pl.splits >= 24 ? 2 : 1);   // split lanes per element
+    gemm_finalize_sym_kernel<<<dim3(nblk * (nblk + 1) / 2, 4), dim3(256, zl), 0, st>>>(p.out, p.ws, p.ws_ld, p.ws_split_stride, pl.splits, nblk);
     ACX_LAUNCH_CHECK();
   } else if (pl.to_ws && !g->symmetric && pl.splits <= 16 && finalize_vec4_ok(p.out, p.ws_ld, p.ws_split_stride)) {
     // (deep split-K of a small result - the conv wgrads - keeps the kernel whose thread lanes share the splits: measured
     // 5.4 vs 14.1 us at 146 splits of a 256 x 32 result)
     const long long quads = (long long)g->m * ((g->n + 3) >> 2);
-    gemm_finalize_vec4_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, st>>>(p.out, g->workspace, p.ws_ld, p.ws_split_stride,
+    gemm_finalize_vec4_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, st>>>(p.out, p.ws, p.ws_ld, p.ws_split_stride,
                                                                               pl.splits);
     ACX_LAUNCH_CHECK();
   } else if (pl.to_ws) {
     const int lanes = pl.splits >= 8 ? 8 : (pl.splits >= 4 ? 4 : (pl.splits >= 2 ? 2 : 1));
     dim3 fg(ceil_div(g->n, 256 / lanes), g->m);
-    gemm_finalize_kernel<<<fg, dim3(256 / lanes, lanes), 0, st>>>(p.out, g->workspace, p.ws_ld, p.ws_split_stride, pl.splits, g->symmetric, BM,
+    gemm_finalize_kernel<<<fg, dim3(256 / lanes, lanes), 0, st>>>(p.out, p.ws, p.ws_ld, p.ws_split_stride, pl.splits, g->symmetric, BM,
                                             pl.bn);
     ACX_LAUNCH_CHECK();
   }
@@ -1291,6 +1531,8 @@ void acx_debug_set_mn_desc(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t kste
   acx::g_mn_kstep = kstep_bytes;
 }
 
+void acx_debug_set_fuse_reduce(int mode) { acx::g_fuse_mode = mode; }
+
 int acx_debug_tc_error(void) {
   int e = acx::tc_error_flag();
   if (!e) e = acx::conv_error_flag();
@@ -1304,7 +1546,7 @@ int acx_debug_inv_trace(long long* h_out, int count) {
 }
 
 int acx_debug_gemm_trace(long long* h_out4) {
-  return cudaMemcpyFromSymbol(h_out4, acx::g_gemm_trace, 4 * sizeof(long long)) == cudaSuccess ? 0 : 1;
+  return cudaMemcpyFromSymbol(h_out4, acx::g_gemm_trace, 12 * sizeof(long long)) == cudaSuccess ? 0 : 1;
 }
 
 int acx_gemm_enable_timing(int enable) {

@@ -172,7 +172,7 @@ def gemm(a_planes, b_planes, m, n, k, trans=False, pairs=None, alpha=1.0, bias=N
     ws_bytes = lib.acx_gemm_workspace_bytes(ctypes.byref(g))
     ws = None
     if ws_bytes:
-        ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)
+        ws = torch.zeros(ws_bytes // 4, dtype=torch.float32, device=dev)   # the counter head must be zero (acx.h)
         g.workspace, g.workspace_bytes = ws.data_ptr(), ws_bytes
     _lib.check(lib.acx_gemm(ctypes.byref(g), impl, _stream()))
     return c, cps

@@ -97,13 +97,16 @@ typedef struct {
   const float* bias;                   /* [n] or NULL */
   int relu;                            /* max(0, .) after bias */
   int symmetric;                       /* C = C^T known (SYRK): only tiles with tile_n >= tile_m are
-                                          computed; the finalize step mirrors them */
+                                          computed; the reduction step mirrors them */
   /* outputs (any subset): */
   float* c; int ldc;                   /* fp32 */
   void* c_planes[ACX_MAX_PLANES]; int c_num_planes; int ldc_planes; /* bf16 split of the result */
   const void* mask_plane; int mask_ld; int mask_rows; /* optional: result *= (mask[m % mask_rows][n] > 0) (bf16) */
-  /* split-K: splits > 1 writes partial sums to workspace [splits][m_pad][n_pad] fp32 and the
-   * outputs above are produced by the finalize kernel. */
+  /* split-K: splits > 1 (0 = automatic) writes partial sums [splits][m_pad][n_pad] fp32 to the workspace; the CTA that
+   * completes a tile sums them in a fixed order inside the same kernel (deterministic, no finalize launch) and produces
+   * the outputs above.  The first 16 KB of the workspace are arrival counters: they must be ZERO when a workspace is first
+   * used and every call leaves them zero, so a workspace can be reused by consecutive calls without clearing; two GEMMs
+   * that may run concurrently need separate workspaces. */
   int splits;
   float* workspace; size_t workspace_bytes;
   /* optional: A is NOT read from `a.planes` but generated inside the kernel as the conv1 patch matrix of uint8
@@ -137,6 +140,10 @@ int acx_debug_inv_trace(long long* h_out, int count);
 /* debug hook: override the UMMA shared-memory descriptor strides (bytes) used for MN-major operands;
  * 0 restores the built-in values. */
 void acx_debug_set_mn_desc(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t kstep_bytes);
+/* where the split-K partials are summed: 0 = a finalize launch, 1 = inside the GEMM kernel where one SM can sum a tile's
+ * partials in a few microseconds, else a finalize launch (default), 2 = always inside the kernel (two levels beyond 8
+ * splits).  Every mode is deterministic.  Also ACX_GEMM_FUSE_REDUCE. */
+void acx_debug_set_fuse_reduce(int mode);
 
 /* ---- implicit-GEMM convolution on bf16 planes (tcgen05 / TMEM / N-d TMA boxes) ---------------- */
 /* nn.conv2d (nn.py:88-110: NHWC, VALID, HWIO weights) without a patch matrix, for kernels whose size is a multiple of the
