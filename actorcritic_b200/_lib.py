@@ -21,6 +21,13 @@ class Planes(ctypes.Structure):
                 ("rows", ctypes.c_int), ("cols", ctypes.c_int), ("ld", ctypes.c_int)]
 
 
+class Gather(ctypes.Structure):
+    _fields_ = [("planes", ctypes.c_void_p * MAX_PLANES), ("num_planes", ctypes.c_int),
+                ("dim", ctypes.c_longlong * 5), ("stride_bytes", ctypes.c_longlong * 4),
+                ("gx", ctypes.c_int), ("gy", ctypes.c_int), ("samples", ctypes.c_int), ("num_chunks", ctypes.c_int),
+                ("c0", ctypes.c_byte * 16), ("c1", ctypes.c_byte * 16), ("c2", ctypes.c_byte * 16), ("c3", ctypes.c_byte * 16)]
+
+
 class Gemm(ctypes.Structure):
     _fields_ = [("a", Planes), ("b", Planes), ("trans_a", ctypes.c_int), ("trans_b", ctypes.c_int),
                 ("m", ctypes.c_int), ("n", ctypes.c_int), ("k", ctypes.c_int),
@@ -31,7 +38,9 @@ class Gemm(ctypes.Structure):
                 ("c_planes", ctypes.c_void_p * MAX_PLANES), ("c_num_planes", ctypes.c_int), ("ldc_planes", ctypes.c_int),
                 ("mask_plane", ctypes.c_void_p), ("mask_ld", ctypes.c_int), ("mask_rows", ctypes.c_int),
                 ("splits", ctypes.c_int), ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
-                ("a_patch_u8", ctypes.c_void_p), ("a_patch_samples", ctypes.c_int)]
+                ("a_patch_u8", ctypes.c_void_p), ("a_patch_samples", ctypes.c_int),
+                ("a_gather", ctypes.POINTER(Gather)), ("b_gather", ctypes.POINTER(Gather)),
+                ("perm_m", ctypes.c_int), ("perm_n", ctypes.c_int)]
 
 
 class Conv(ctypes.Structure):
@@ -78,6 +87,7 @@ SIGNATURES = {
                                         ctypes.POINTER(_P), ctypes.c_int, ctypes.c_int, _P]),
     "acx_debug_set_mn_desc": (None, [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]),
     "acx_debug_set_fuse_reduce": (None, [ctypes.c_int]),
+    "acx_obs_pairs_bf16": (ctypes.c_int, [_P, _P, ctypes.c_int, _P]),
     "acx_debug_tc_error": (ctypes.c_int, []),
     "acx_gemm_enable_timing": (ctypes.c_int, [ctypes.c_int]),
     "acx_gemm_last_ms": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float)]),

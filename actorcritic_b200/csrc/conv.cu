@@ -444,8 +444,8 @@ static std::unordered_map<ViewKey, CUtensorMap, ViewKeyHash> g_views;
 static std::mutex g_views_mu;
 
 // bf16 tensor view of rank `rank` (<= 5): dim / box innermost first, stride[i] = byte stride of dim i+1
-static int get_view_map(const void* ptr, int rank, const long long* dim, const long long* stride_bytes, const int* box, int swizzle_bytes,
-                        CUtensorMap* out) {
+int get_view_map(const void* ptr, int rank, const long long* dim, const long long* stride_bytes, const int* box, int swizzle_bytes,
+                 CUtensorMap* out) {
   ViewKey key;
   key.ptr = ptr;
   key.swz = swizzle_bytes;
@@ -675,6 +675,66 @@ int conv_tc_forward(const Planes& x, const Planes& wT, const ConvGeom& g, int sa
     if (r) return r;
   }
   r = weight_maps(wT, g.c_out, K, p.bn, tb);
+  if (r) return r;
+  return launch_conv(ta, tb, p, st);
+}
+
+// conv1 (8x8 / stride 4 on [84, 84, 4], envs/atari/model.py:173-179) straight from the row-pair interleaved observation copy
+// (obs_pairs_bf16, layers.cu): y = relu(alpha * conv(obs, W) + bias).  In that copy the two kernel rows kh = 2j, 2j + 1 of the
+// patch at (oy, ox) are one run of 64 elements at pair-row 2 oy + j, pixel 4 ox, so the K dimension is 4 chunks of 64 and the
+// view  [sample][oy + j / 2][j % 2][ox][64]  has the shape of the forward views above (x stride = 4 pixels = 64 bytes: the
+// runs of neighbouring locations overlap).  wT_perm: [32, 256] planes whose columns follow the copy's (kw, parity, c) order.
+int conv1_pairs_forward(const bf16* obs_pairs, const Planes& wT_perm, int samples, const float* bias, float alpha, const Planes& y,
+                        int num_pairs, const int* pair_a, const int* pair_b, cudaStream_t st) {
+  ACX_CHECK(samples > 0 && obs_pairs != nullptr && wT_perm.n >= 1 && y.n >= 1 && y.ld == 32, "bad operands");
+  ConvTcParams p;
+  memset(&p, 0, sizeof(p));
+  int r = fill_pairs(&p, num_pairs, pair_a, pair_b, 1, wT_perm.n);
+  if (r) return r;
+  p.gx = p.gy = 20;
+  pick_tile_cut(p.gx, p.gy, samples, &p.bx, &p.by, &p.ts);
+  p.nx = p.gx / p.bx;
+  p.cells = p.nx * (p.gy / p.by);
+  p.ydim = 3;
+  p.rows_valid = p.ts * p.bx * p.by;
+  p.num_tiles = p.cells * ceil_div(samples, p.ts);
+  p.lo_from_tile = p.num_tiles;
+  p.num_pairs_lo = num_pairs;
+  p.samples = samples;
+  p.bn = 32;
+  p.kb_total = 4;
+  p.nsub = 1;
+  p.num_sub = 4;
+  p.sub_bytes = p.rows_valid * CV_BK * 2;
+  for (int j = 0; j < 4; ++j) {
+    p.tc1[j] = 0;
+    p.tc2[j] = (signed char)(j & 1);    // pair-row parity
+    p.tc3[j] = (signed char)(j >> 1);   // + oy
+  }
+  p.dgrad = 0;
+  p.hw_in = 84;
+  p.c_in = 4;
+  p.s = 4;
+  p.hq = 21;
+  p.alpha = alpha;
+  p.bias = bias;
+  p.relu = 1;
+  for (int i = 0; i < 3; ++i) p.cp[i] = i < y.n ? y.p[i] : nullptr;
+  p.npl = y.n;
+  p.ldcp = y.ld;
+  p.mask = nullptr;
+  p.mask_samples = 1;
+  for (int i = 0; i < y.n; ++i) ACX_CHECK((reinterpret_cast<uintptr_t>(y.p[i]) & 15) == 0, "output planes must be 16-byte aligned");
+  CUtensorMap ta[3], tb[3];
+  const long long prow = 84 * 8;   // elements of one pair-row
+  const long long dim[5] = {64, 20, 2, 21, samples};
+  const long long stride[4] = {32 * 2, prow * 2, 2 * prow * 2, 42 * prow * 2};
+  const int box[5] = {64, p.bx, 1, p.by, p.ts};
+  for (int i = 0; i < 3; ++i) {
+    r = get_view_map(obs_pairs, 5, dim, stride, box, 128, &ta[i]);
+    if (r) return r;
+  }
+  r = weight_maps(wT_perm, 32, 256, p.bn, tb);
   if (r) return r;
   return launch_conv(ta, tb, p, st);
 }

@@ -31,7 +31,13 @@ struct OutParams {
   int ldcp;
   const bf16* mask;
   int mask_ld, mask_rows;
+  int perm_m, perm_n;   // result row / column i is stored at perm64(i) (acx.h: conv1 patches read from the row-pair copy)
 };
+
+// column order (kw, row parity, c) of a 64-wide conv1 patch chunk -> the reference's (kh, kw, c): 4-groups stay 4-groups
+__device__ __host__ __forceinline__ int perm64(int i) {
+  return (i & ~63) | (((i >> 2) & 1) << 5) | (((i >> 3) & 7) << 2) | (i & 3);
+}
 
 struct TcParams {
   OutParams out;
@@ -60,6 +66,11 @@ struct TcParams {
   // splits of a tile sums them in split order; with more than one group the group sums go to `ws2` and the CTA that
   // completes the last group sums those in group order - every association is fixed, so the result does not depend on
   // which CTA arrives last.  Counters: per tile `groups` group counters + 1 tile counter, zero on entry, left zero.
+  // gathered MN-major operands (acx_gather_t): k-block kb = the 64 locations of box (bx x by cells, ts samples) number
+  // kb % g_cells of sample group kb / g_cells; chunk q of a location comes from coordinates (c0, x + c1, c2, y + c3, sample)
+  int gather_a, gather_b;
+  int g_cells, g_nx, g_bx, g_by, g_ts;
+  signed char ga[4][16], gb[4][16];
   int fuse, groups;
   float* ws2;
   long long ws2_stride;   // floats between group sums
@@ -83,6 +94,8 @@ __device__ __forceinline__ float finish_value(const OutParams& o, int m, int n, 
   return v;
 }
 __device__ __forceinline__ void store_value(const OutParams& o, int m, int n, float v) {
+  if (o.perm_m) m = perm64(m);
+  if (o.perm_n) n = perm64(n);
   if (o.c) o.c[(size_t)m * o.ldc + n] = v;
   if (o.c_num_planes > 0) {
     bf16 p0, p1, p2;
@@ -143,11 +156,12 @@ __device__ __forceinline__ void emit4(const OutParams& o, int m, int n, float4 a
       for (int j = 0; j < 4; ++j)
         if (!(__bfloat162float(mk[j]) > 0.0f)) v[j] = 0.0f;
     }
-    if (o.c) *reinterpret_cast<float4*>(o.c + (size_t)m * o.ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
+    const int ms = o.perm_m ? perm64(m) : m, ns = o.perm_n ? perm64(n) : n;   // (a 4-group stays a 4-group)
+    if (o.c) *reinterpret_cast<float4*>(o.c + (size_t)ms * o.ldc + ns) = make_float4(v[0], v[1], v[2], v[3]);
     if (o.c_num_planes > 0) {
       uint2 ph, pm, pl;
       split3x4(v[0], v[1], v[2], v[3], ph, pm, pl);
-      const size_t idx = (size_t)m * o.ldcp + n;
+      const size_t idx = (size_t)ms * o.ldcp + ns;
       *reinterpret_cast<uint2*>(o.cp[0] + idx) = ph;
       if (o.c_num_planes > 1) *reinterpret_cast<uint2*>(o.cp[1] + idx) = pm;
       if (o.c_num_planes > 2) *reinterpret_cast<uint2*>(o.cp[2] + idx) = pl;
@@ -322,11 +336,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
           if (!elect_one()) continue;
           mbar_expect_tx(&full_bar[s], tx);
           uint8_t* a_s = smem + s * stage_bytes;
+          // gathered operands: where the 64 locations of this k-block sit in the (x, y, sample) space
+          int gx0 = 0, gy0 = 0, gn0 = 0;
+          if (MAJOR == 1 && (p.gather_a | p.gather_b)) {
+            const int grp = kb / p.g_cells, cell = kb - grp * p.g_cells;
+            const int cy = cell / p.g_nx;
+            gx0 = (cell - cy * p.g_nx) * p.g_bx;
+            gy0 = cy * p.g_by;
+            gn0 = grp * p.g_ts;
+          }
           if (p.panel) {
             for (int i = 0; i < p.npa && !patch; ++i) {
               const CUtensorMap* ma = i == 0 ? &ta0 : (i == 1 ? &ta1 : &ta2);
-              for (int j = 0; j < nch; ++j)
-                tma_load_2d(a_s + i * panel_tile_bytes + j * (bk * 128), ma, &full_bar[s], 64 * j, kb * bk);
+              for (int j = 0; j < nch; ++j) {
+                uint8_t* dst = a_s + i * panel_tile_bytes + j * (bk * 128);
+                if (MAJOR == 1 && p.gather_a)
+                  tma_load_5d(dst, ma, &full_bar[s], p.ga[0][j], gx0 + p.ga[1][j], p.ga[2][j], gy0 + p.ga[3][j], gn0);
+                else
+                  tma_load_2d(dst, ma, &full_bar[s], 64 * j, kb * bk);
+              }
             }
             continue;
           }
@@ -336,6 +364,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
             uint8_t* dst = a_s + i * a_tile_bytes;
             if (MAJOR == 0) {
               tma_load_2d(dst, ma, &full_bar[s], kb * bk, m0);
+            } else if (p.gather_a) {
+              for (int j = 0; j < na; ++j) {
+                const int q = (m0 >> 6) + j;
+                tma_load_5d(dst + j * (bk * 128), ma, &full_bar[s], p.ga[0][q], gx0 + p.ga[1][q], p.ga[2][q], gy0 + p.ga[3][q], gn0);
+              }
             } else {
               for (int j = 0; j < na; ++j) tma_load_2d(dst + j * (bk * 128), ma, &full_bar[s], m0 + 64 * j, kb * bk);
             }
@@ -345,6 +378,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
             uint8_t* dst = b_s + i * b_tile_bytes;
             if (MAJOR == 0) {
               tma_load_2d(dst, mb, &full_bar[s], kb * bk, n0);
+            } else if (p.gather_b) {
+              for (int j = 0; j < nb; ++j) {
+                const int q = (n0 >> 6) + j;
+                tma_load_5d(dst + j * (bk * 128), mb, &full_bar[s], p.gb[0][q], gx0 + p.gb[1][q], p.gb[2][q], gy0 + p.gb[3][q], gn0);
+              }
             } else {
               for (int j = 0; j < nb; ++j) tma_load_2d(dst + j * (bk * 128), mb, &full_bar[s], n0 + 64 * j, kb * bk);
             }
@@ -938,7 +976,8 @@ __global__ void __launch_bounds__(256) gemm_finalize_vec4_kernel(OutParams o, co
     if (!(__uint_as_float(mw.y << 16) > 0.0f)) v[2] = 0.0f;
     if (!(__uint_as_float(mw.y & 0xffff0000u) > 0.0f)) v[3] = 0.0f;
   }
-  if (o.c) *reinterpret_cast<float4*>(o.c + (size_t)m * o.ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
+  const int ms = o.perm_m ? perm64(m) : m, ns = o.perm_n ? perm64(n) : n;
+  if (o.c) *reinterpret_cast<float4*>(o.c + (size_t)ms * o.ldc + ns) = make_float4(v[0], v[1], v[2], v[3]);
   if (o.c_num_planes > 0) {
     if (n + 3 >= o.n) {   // ragged last quad: the padding columns of the planes are kept zero
 #pragma unroll
@@ -947,7 +986,7 @@ __global__ void __launch_bounds__(256) gemm_finalize_vec4_kernel(OutParams o, co
     }
     uint2 ph, pm, pl;
     split3x4(v[0], v[1], v[2], v[3], ph, pm, pl);
-    const size_t idx = (size_t)m * o.ldcp + n;
+    const size_t idx = (size_t)ms * o.ldcp + ns;
     *reinterpret_cast<uint2*>(o.cp[0] + idx) = ph;
     if (o.c_num_planes > 1) *reinterpret_cast<uint2*>(o.cp[1] + idx) = pm;
     if (o.c_num_planes > 2) *reinterpret_cast<uint2*>(o.cp[2] + idx) = pl;
@@ -1190,10 +1229,13 @@ static void fill_out(const acx_gemm_t* g, OutParams* o) {
   o->mask = reinterpret_cast<const bf16*>(g->mask_plane);
   o->mask_ld = g->mask_ld;
   o->mask_rows = g->mask_rows > 0 ? g->mask_rows : (g->m > 0 ? g->m : 1);
+  o->perm_m = g->perm_m;
+  o->perm_n = g->perm_n;
 }
 
 struct TcPlan {
   int bn, bk, npa, npb, stages, tiles_m, tiles_n, splits, kb_total, kb_per_split, to_ws, panel;
+  int g_bx, g_by, g_ts, g_nx, g_cells;   // gathered operands: the box of 64 locations that makes one k-block
   int fuse, groups;            // split-K reduction inside the kernel
   size_t part_bytes;           // the split partials
   size_t ws_bytes;
@@ -1202,7 +1244,7 @@ static int g_fuse_mode = -1;
 static int fuse_reduce_enabled() {   // ACX_GEMM_FUSE_REDUCE / acx_debug_set_fuse_reduce: 0 = finalize launches, 1 = where cheap, 2 = always
   if (g_fuse_mode < 0) {
     const char* e = getenv("ACX_GEMM_FUSE_REDUCE");
-    g_fuse_mode = e ? atoi(e) : 1;
+    g_fuse_mode = e ? atoi(e) : 0;
   }
   return g_fuse_mode;
 }
@@ -1234,8 +1276,9 @@ static void plan_tc(const acx_gemm_t* g, TcPlan* pl) {
   if (g->symmetric) tiles = pl->tiles_n * (pl->tiles_n + 1) / 2;
   // SYRK panel mode: X^T X with 128 < n <= 256 (MN-major): every CTA streams its k-range of X once and feeds all three
   // upper sub-tiles from the same shared memory
-  pl->panel = (g->symmetric && g->trans_a && pl->bn == 128 && pl->tiles_n == 2 &&
-               (g->a_patch_u8 != nullptr || g->a.planes[0] == g->b.planes[0])) ? 1 : 0;
+  const bool same_operand = g->a_gather ? (g->b_gather == nullptr || g->b_gather == g->a_gather)
+                                        : (g->a_patch_u8 != nullptr || g->a.planes[0] == g->b.planes[0]);
+  pl->panel = (g->symmetric && g->trans_a && pl->bn == 128 && pl->tiles_n == 2 && same_operand) ? 1 : 0;
   if (pl->panel) tiles = 1;
   // planes each side loads per k-block, and the ring depth they leave
   pl->npa = pl->npb = 1;
@@ -1251,9 +1294,24 @@ static void plan_tc(const acx_gemm_t* g, TcPlan* pl) {
   };
   // Measured at 32 x 20 (ACX_GEMM_BK=32): halving the k-block to get 4-5 ring stages instead of 2 for the 3 + 3 plane GEMMs
   // is SLOWER (1.26 vs 1.16 ms/update): twice the stage hand-offs, and 64-byte swizzle rows; so 64 unless asked.
-  pl->bk = force_bk() == 32 ? 32 : BK;
+  pl->bk = (force_bk() == 32 && !g->a_gather) ? 32 : BK;
   pl->stages = stages_for(pl->bk);
   pl->kb_total = ceil_div(g->k, pl->bk);
+  pl->g_bx = pl->g_by = pl->g_ts = pl->g_nx = pl->g_cells = 0;
+  if (g->a_gather) {
+    // one k-block = 64 locations = a box of bx x by grid cells (powers of two that divide the grid) of ts samples;
+    // sample groups beyond the batch read as zero rows
+    const acx_gather_t* ga = g->a_gather;
+    int bx = 1, by = 1;
+    while (bx < 8 && ga->gx % (2 * bx) == 0) bx *= 2;
+    while (bx * by < 64 && ga->gy % (2 * by) == 0) by *= 2;
+    pl->g_bx = bx;
+    pl->g_by = by;
+    pl->g_ts = 64 / (bx * by);
+    pl->g_nx = ga->gx / bx;
+    pl->g_cells = pl->g_nx * (ga->gy / by);
+    pl->kb_total = pl->g_cells * ceil_div(ga->samples, pl->g_ts);
+  }
   int splits = g->splits;
   if (splits <= 0) {  // auto: about one work item per SM, at least 256 elements of K per split
     splits = 148 / (tiles > 0 ? tiles : 1);
@@ -1326,12 +1384,27 @@ static int validate(const acx_gemm_t* g) {
   ACX_CHECK(g != nullptr, "null gemm");
   ACX_CHECK(g->m > 0 && g->n > 0 && g->k > 0, "empty problem");
   ACX_CHECK(g->num_pairs >= 1 && g->num_pairs <= 6, "num_pairs out of range");
-  ACX_CHECK(g->a.num_planes >= 1 && g->a.num_planes <= ACX_MAX_PLANES, "a.num_planes");
-  ACX_CHECK(g->b.num_planes >= 1 && g->b.num_planes <= ACX_MAX_PLANES, "b.num_planes");
+  const acx_gather_t* gb_eff = g->b_gather ? g->b_gather : ((g->a_gather && g->symmetric) ? g->a_gather : nullptr);
+  const int a_np = g->a_gather ? g->a_gather->num_planes : g->a.num_planes;
+  const int b_np = gb_eff ? gb_eff->num_planes : g->b.num_planes;
+  ACX_CHECK(a_np >= 1 && a_np <= ACX_MAX_PLANES, "a.num_planes");
+  ACX_CHECK(b_np >= 1 && b_np <= ACX_MAX_PLANES, "b.num_planes");
   for (int i = 0; i < g->num_pairs; ++i) {
-    ACX_CHECK(g->pair_a[i] >= 0 && g->pair_a[i] < g->a.num_planes, "pair_a index");
-    ACX_CHECK(g->pair_b[i] >= 0 && g->pair_b[i] < g->b.num_planes, "pair_b index");
+    ACX_CHECK(g->pair_a[i] >= 0 && g->pair_a[i] < a_np, "pair_a index");
+    ACX_CHECK(g->pair_b[i] >= 0 && g->pair_b[i] < b_np, "pair_b index");
   }
+  if (g->a_gather || g->b_gather) {
+    const acx_gather_t* ga = g->a_gather;
+    ACX_CHECK(ga != nullptr && gb_eff != nullptr, "gathered operands: both sides must be gathered (or the product symmetric with B = A)");
+    ACX_CHECK(g->trans_a == 1 && g->trans_b == 1, "gathered operands are MN-major (trans_a = trans_b = 1)");
+    ACX_CHECK(g->a_patch_u8 == nullptr, "a_gather and a_patch_u8 are exclusive");
+    ACX_CHECK(ga->gx >= 1 && ga->gy >= 1 && ga->samples >= 1 && (long long)ga->samples * ga->gx * ga->gy == (long long)g->k,
+              "gathered operands: k must be samples * gy * gx");
+    ACX_CHECK(gb_eff->gx == ga->gx && gb_eff->gy == ga->gy && gb_eff->samples == ga->samples, "gathered operands: A and B enumerate different locations");
+    ACX_CHECK(ga->num_chunks >= 1 && ga->num_chunks <= 16 && g->m <= 64 * ga->num_chunks, "a_gather: m exceeds 64 * num_chunks");
+    ACX_CHECK(gb_eff->num_chunks >= 1 && gb_eff->num_chunks <= 16 && g->n <= 64 * gb_eff->num_chunks, "b_gather: n exceeds 64 * num_chunks");
+  }
+  if (g->perm_m || g->perm_n) ACX_CHECK(g->bias == nullptr && g->mask_plane == nullptr, "perm_m / perm_n: no bias or mask");
   ACX_CHECK(g->trans_a == g->trans_b, "only (K-major,K-major) and (MN-major,MN-major) operand pairs are supported");
   if (g->a_patch_u8) {
     // A = the conv1 patch matrix of uint8 observations [samples, 84, 84, 4] (8x8 kernel, stride 4: 400 patch rows of 256
@@ -1359,7 +1432,16 @@ static int gemm_tc(const acx_gemm_t* g, cudaStream_t st) {
   const int major = g->trans_a ? 1 : 0;
   const bool patch = g->a_patch_u8 != nullptr;
   const bool b_patch = patch && pl.panel;   // SYRK panel mode: both operand sides are the patch tiles
-  for (int i = 0; i < 3; ++i) {
+  const acx_gather_t* ga = g->a_gather;
+  const acx_gather_t* gb = ga ? (g->b_gather ? g->b_gather : ga) : nullptr;
+  for (int i = 0; i < 3 && ga; ++i) {   // gathered operands: 5-D views, one box = the 64 locations of a k-block x one 64-column chunk
+    const int box[5] = {64, pl.g_bx, 1, pl.g_by, pl.g_ts};
+    int r = get_view_map(ga->planes[i < ga->num_planes ? i : 0], 5, ga->dim, ga->stride_bytes, box, 128, &ta[i]);
+    if (r) return r;
+    r = get_view_map(gb->planes[i < gb->num_planes ? i : 0], 5, gb->dim, gb->stride_bytes, box, 128, &tb[i]);
+    if (r) return r;
+  }
+  for (int i = 0; i < 3 && !ga; ++i) {
     const int ia = i < g->a.num_planes ? i : 0, ib = i < g->b.num_planes ? i : 0;
     int r;
     if (!b_patch) {
@@ -1379,9 +1461,23 @@ static int gemm_tc(const acx_gemm_t* g, cudaStream_t st) {
   }
   TcParams p;
   fill_out(g, &p.out);
-  p.k = g->k;
+  p.k = ga ? pl.kb_total * pl.bk : g->k;   // gathered: every k-block is whole (locations beyond the batch read as zero rows)
   p.kb_total = pl.kb_total;
   p.kb_per_split = pl.kb_per_split;
+  p.gather_a = p.gather_b = ga ? 1 : 0;
+  p.g_cells = pl.g_cells;
+  p.g_nx = pl.g_nx;
+  p.g_bx = pl.g_bx;
+  p.g_by = pl.g_by;
+  p.g_ts = pl.g_ts;
+  memset(p.ga, 0, sizeof(p.ga));
+  memset(p.gb, 0, sizeof(p.gb));
+  if (ga) {
+    for (int q = 0; q < 16; ++q) {
+      p.ga[0][q] = ga->c0[q]; p.ga[1][q] = ga->c1[q]; p.ga[2][q] = ga->c2[q]; p.ga[3][q] = ga->c3[q];
+      p.gb[0][q] = gb->c0[q]; p.gb[1][q] = gb->c1[q]; p.gb[2][q] = gb->c2[q]; p.gb[3][q] = gb->c3[q];
+    }
+  }
   p.num_pairs = g->num_pairs;
   for (int i = 0; i < 6; ++i) {
     p.pair_a[i] = g->pair_a[i];

@@ -39,6 +39,42 @@ __global__ void __launch_bounds__(256) im2col_conv1_kernel(const uint8_t* __rest
   *reinterpret_cast<uint4*>(out + (size_t)row * 256 + ky * 32 + q * 8) = make_uint4(t[0], t[1], t[2], t[3]);
 }
 
+// Row-pair interleaved bf16 copy of the observations: uint8 [R, 84, 84, 4] -> bf16 [R, 42, 84, 2, 4] with
+// out[r][p][x][q][c] = obs[r][2p + q][x][c] (raw byte values, exact).  In this layout the two kernel rows kh = 2j, 2j + 1 of
+// conv1's 8x8 / stride-4 patch at output location (oy, ox) are ONE contiguous run of 64 elements (128 bytes) starting at
+// pair-row 2 oy + j, pixel 4 ox - so the patch matrix P1 (envs/atari/model.py:173-179, 227-229) never has to exist: every
+// GEMM that consumed it reads 64-column chunks with TMA box loads from this copy, which is 2x the observations instead of
+// 7.2x and stays in L2.  The columns of a chunk arrive in the order (kw, q, c) instead of (kh, kw, c): see perm64 (gemm.cu).
+// One thread per (sample, pair-row, 4 pixels): two 16-byte loads, four 16-byte stores (64 contiguous bytes).
+__global__ void __launch_bounds__(256) obs_pairs_bf16_kernel(const uint8_t* __restrict__ obs, bf16* __restrict__ out, int samples) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)samples * 42 * 21) return;
+  const int xq = (int)(i % 21);
+  const long long rp = i / 21;   // sample * 42 + pair-row
+  const int pr = (int)(rp % 42);
+  const long long r = rp / 42;
+  const uint8_t* src = obs + ((size_t)(r * 84 + 2 * pr) * 84 + 4 * xq) * 4;
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(src));             // row 2p:     4 pixels x 4 channels
+  const uint4 b = __ldg(reinterpret_cast<const uint4*>(src + 84 * 4));    // row 2p + 1
+  const uint32_t wa[4] = {a.x, a.y, a.z, a.w}, wb[4] = {b.x, b.y, b.z, b.w};
+  uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)rp * 84 + 4 * xq) * 8);
+#pragma unroll
+  for (int px = 0; px < 4; ++px) {
+    uint32_t t[4];
+    const uint32_t w2[2] = {wa[px], wb[px]};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {   // byte -> bf16 as in im2col_conv1_kernel
+      const float f0 = __uint_as_float(__byte_perm(w2[q], 0x4B000000u, 0x7540)) - 8388608.0f;
+      const float f1 = __uint_as_float(__byte_perm(w2[q], 0x4B000000u, 0x7541)) - 8388608.0f;
+      const float f2 = __uint_as_float(__byte_perm(w2[q], 0x4B000000u, 0x7542)) - 8388608.0f;
+      const float f3 = __uint_as_float(__byte_perm(w2[q], 0x4B000000u, 0x7543)) - 8388608.0f;
+      t[2 * q] = __byte_perm(__float_as_uint(f0), __float_as_uint(f1), 0x7632);
+      t[2 * q + 1] = __byte_perm(__float_as_uint(f2), __float_as_uint(f3), 0x7632);
+    }
+    dst[px] = make_uint4(t[0], t[1], t[2], t[3]);
+  }
+}
+
 // generic NHWC bf16 im2col, patch order (ky, kx, c): each (row, ky) segment is k*C contiguous elements.
 // One warp per patch row (grid-stride): the row decode is warp-uniform, lanes own 16-byte vectors, every plane is
 // copied by the same thread (the index math is shared), reads are k*C*2-byte runs, writes are whole contiguous rows.
@@ -637,6 +673,7 @@ struct WeightPlanesJob {
   int ld_t;
   bf16* n[3];              // W planes [K, ld_n] or null
   int ld_n;
+  int perm_t;              // W^T columns in the (kw, row parity, c) order of the row-pair observation copy (conv1)
 };
 struct WeightPlanesArgs {
   WeightPlanesJob job[4];
@@ -665,7 +702,9 @@ __global__ void weight_planes_kernel(const WeightPlanesArgs a) {
     if (c < jb.c_cols && k < jb.ld_t) {
       bf16 x, y, z;
       split3(k < jb.k_rows ? tile[threadIdx.x][i] : 0.0f, x, y, z);
-      const size_t idx = (size_t)c * jb.ld_t + k;
+      // perm_t: weight row f = p*32 + kw*4 + ch of a 64-row chunk goes to column kw*8 + p*4 + ch (the inverse of perm64)
+      const int kd = jb.perm_t ? ((k & ~63) | (((k >> 2) & 7) << 3) | (((k >> 5) & 1) << 2) | (k & 3)) : k;
+      const size_t idx = (size_t)c * jb.ld_t + kd;
       jb.t[0][idx] = x;
       jb.t[1][idx] = y;
       jb.t[2][idx] = z;
@@ -726,6 +765,12 @@ __global__ void __launch_bounds__(1024) sample_actions_kernel(const float* __res
 int im2col_conv1(const uint8_t* obs, bf16* out, int rows_total, cudaStream_t st) {
   const long long total = (long long)rows_total * 32;
   im2col_conv1_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(obs, out, rows_total);
+  ACX_LAUNCH_CHECK();
+  return 0;
+}
+int obs_pairs_bf16(const uint8_t* obs, bf16* out, int samples, cudaStream_t st) {
+  const long long total = (long long)samples * 42 * 21;
+  obs_pairs_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(obs, out, samples);
   ACX_LAUNCH_CHECK();
   return 0;
 }
@@ -852,7 +897,7 @@ int transpose_split(const float* in, int k_rows, int c_cols, bf16* p0, bf16* p1,
   return 0;
 }
 int weight_planes(const float* const* w, const int* k_rows, const int* c_cols, bf16* const (*t)[3], const int* ld_t,
-                  bf16* const (*n)[3], const int* ld_n, int num_layers, cudaStream_t st) {
+                  bf16* const (*n)[3], const int* ld_n, int num_layers, cudaStream_t st, int perm_first) {
   ACX_CHECK(num_layers >= 1 && num_layers <= 4, "weight_planes: 1..4 layers");
   WeightPlanesArgs a;
   int max_k = 0, max_c = 0;
@@ -863,6 +908,7 @@ int weight_planes(const float* const* w, const int* k_rows, const int* c_cols, b
     a.job[i].c_cols = c_cols[s];
     a.job[i].ld_t = ld_t[s];
     a.job[i].ld_n = ld_n[s];
+    a.job[i].perm_t = (s == 0 && perm_first) ? 1 : 0;
     for (int q = 0; q < 3; ++q) {
       a.job[i].t[q] = t[s][q];
       a.job[i].n[q] = n[s][q];
@@ -893,4 +939,10 @@ extern "C" int acx_sample_actions(const float* d_logits, const float* d_uniform,
   ACX_CHECK(rows > 0 && num_actions >= 1 && num_actions <= 1024, "rows / num_actions out of range");
   return acx::sample_actions(d_logits, d_uniform, seed, step, rows, num_actions, greedy, d_actions,
                              reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int acx_obs_pairs_bf16(const uint8_t* d_obs, void* d_out, int samples, void* stream) {
+  ACX_CHECK(d_obs && d_out && samples > 0, "null argument");
+  ACX_CHECK((reinterpret_cast<uintptr_t>(d_obs) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0, "16-byte alignment");
+  return acx::obs_pairs_bf16(d_obs, reinterpret_cast<acx::bf16*>(d_out), samples, reinterpret_cast<cudaStream_t>(stream));
 }

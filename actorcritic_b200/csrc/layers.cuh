@@ -46,7 +46,10 @@ int conv_border(const uint8_t* obs_u8, const Planes* act, int n_rows, int hw_in,
 int transpose_split(const float* in, int k_rows, int c_cols, bf16* p0, bf16* p1, bf16* p2, int num_planes, int ld_out,
                     cudaStream_t st);
 int weight_planes(const float* const* w, const int* k_rows, const int* c_cols, bf16* const (*t)[3], const int* ld_t,
-                  bf16* const (*n)[3], const int* ld_n, int num_layers, cudaStream_t st);
+                  bf16* const (*n)[3], const int* ld_n, int num_layers, cudaStream_t st, int perm_first = 0);
+int obs_pairs_bf16(const uint8_t* obs, bf16* out, int samples, cudaStream_t st);
+int conv1_pairs_forward(const bf16* obs_pairs, const Planes& wT_perm, int samples, const float* bias, float alpha, const Planes& y,
+                        int num_pairs, const int* pair_a, const int* pair_b, cudaStream_t st);
 int sample_actions(const float* logits, const float* uniform, uint64_t seed, uint64_t step, int rows, int num_actions, int greedy,
                    int32_t* actions, cudaStream_t st, unsigned long long* step_counter = nullptr);
 int split_planes(const float* in, int ld_in, int rows, int cols, float scale, bf16* p0, bf16* p1, bf16* p2, int num_planes,

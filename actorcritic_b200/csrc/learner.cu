@@ -131,6 +131,11 @@ struct acx_learner {
   bool conv_tc[4];           // layer computes its input gradient with the gather-form tensor-core kernel (conv.cu)
   bool conv_fwd_tc[4];       // layer runs its forward on the implicit-GEMM kernel (patch matrix built on the aux lane)
   bool conv1_patch;          // conv1's patch matrix P1 is generated inside the GEMMs from the uint8 observations (never stored)
+  bool gather;               // no patch matrix is ever stored: the conv GEMMs read their patch operands in place (TMA box loads from
+                             // the activations; conv1 from the row-pair interleaved bf16 copy `obs_pairs` of the observations)
+  bf16* obs_pairs;           // [R, 42, 84, 2, 4] (layers.cu: obs_pairs_bf16)
+  acx_gather_t gat_x[3];     // patch operand of conv layer l over the N train samples (input factor, weight gradient)
+  acx_gather_t gat_g[3];     // pre-activation gradient of conv layer l as rows (sample, y, x) over the same locations
   Planes Vp, Wt;
   float* dot_partials;
   Scratch scr[kMaxLanes];
@@ -346,6 +351,7 @@ static size_t layout(acx_learner* l, uint8_t* base) {
 
   // ---- activations (forward rows R = N + E; backward rows 2N = true-loss rows then Fisher-sample rows)
   const int np = l->act_planes;
+  l->obs_pairs = reinterpret_cast<bf16*>(ar.take((size_t)R * 28224 * sizeof(bf16)));
   l->P1 = take_planes(ar, 1, (size_t)R * 400, 256);
   l->act1 = take_planes(ar, np, (size_t)R * 400, 32);
   l->P2 = take_planes(ar, np, (size_t)R * 81, 512);
@@ -389,6 +395,81 @@ static size_t layout(acx_learner* l, uint8_t* base) {
     sc.ws = reinterpret_cast<float*>(ar.take(sc.ws_bytes));
   }
   return align_up(ar.used, 256);
+}
+
+// The patch operands of the three conv layers as in-place views (acx_gather_t, include/acx.h): chunk q of location
+// (sample, y, x) = 64 contiguous bf16 of the layer's input tensor.
+//   conv1  8x8/4 on the row-pair copy [n][42][84][2][4]: chunk j = kernel rows 2j, 2j+1 -> pair-row 2 oy + j, pixel 4 ox
+//   conv2  4x4/2 on act1 [n][20][20][32]: chunk (kh, h) = kernel row kh, kernel columns 2h, 2h+1 -> row 2 oy + kh, pixel 2 (ox + h)
+//   conv3  3x3/1 on act2 [n][9][9][64]:   chunk (kh, kw) -> pixel (oy + kh, ox + kw)
+// and the pre-activation gradients [sample][y][x][C] as operands over the same locations.
+static void setup_gather(acx_learner* l) {
+  const int N = l->N;
+  auto fill = [](acx_gather_t& g, const Planes& pl, int nplanes) {
+    memset(&g, 0, sizeof(g));
+    for (int i = 0; i < nplanes; ++i) g.planes[i] = pl.p[i];
+    g.num_planes = nplanes;
+  };
+  {
+    acx_gather_t& g = l->gat_x[0];
+    Planes one;
+    one.p[0] = l->obs_pairs;
+    fill(g, one, 1);
+    const long long prow = 84 * 8 * 2;   // bytes of one pair-row
+    const long long dim[5] = {64, 20, 4, 20, N}, st[4] = {64, prow, 2 * prow, 42 * prow};
+    for (int i = 0; i < 5; ++i) g.dim[i] = dim[i];
+    for (int i = 0; i < 4; ++i) g.stride_bytes[i] = st[i];
+    g.gx = g.gy = 20;
+    g.samples = N;
+    g.num_chunks = 4;
+    for (int j = 0; j < 4; ++j) g.c2[j] = (signed char)j;
+  }
+  {
+    acx_gather_t& g = l->gat_x[1];
+    fill(g, l->act1, l->act1.n);
+    const long long px = 32 * 2;
+    const long long dim[5] = {64, 10, 4, 9, N}, st[4] = {2 * px, 20 * px, 40 * px, 400 * px};
+    for (int i = 0; i < 5; ++i) g.dim[i] = dim[i];
+    for (int i = 0; i < 4; ++i) g.stride_bytes[i] = st[i];
+    g.gx = g.gy = 9;
+    g.samples = N;
+    g.num_chunks = 8;
+    for (int kh = 0; kh < 4; ++kh)
+      for (int h = 0; h < 2; ++h) {
+        g.c1[kh * 2 + h] = (signed char)h;
+        g.c2[kh * 2 + h] = (signed char)kh;
+      }
+  }
+  {
+    acx_gather_t& g = l->gat_x[2];
+    fill(g, l->act2, l->act2.n);
+    const long long px = 64 * 2;
+    const long long dim[5] = {64, 9, 1, 9, N}, st[4] = {px, px, 9 * px, 81 * px};
+    for (int i = 0; i < 5; ++i) g.dim[i] = dim[i];
+    for (int i = 0; i < 4; ++i) g.stride_bytes[i] = st[i];
+    g.gx = g.gy = 7;
+    g.samples = N;
+    g.num_chunks = 9;
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw) {
+        g.c1[kh * 3 + kw] = (signed char)kw;
+        g.c3[kh * 3 + kw] = (signed char)kh;
+      }
+  }
+  const Planes* dp[3] = {&l->dpre1, &l->dpre2, &l->dpre3};
+  for (int li = 0; li < 3; ++li) {
+    acx_gather_t& g = l->gat_g[li];
+    const Layer& L = l->L[li];
+    fill(g, *dp[li], dp[li]->n);
+    const long long px = (long long)L.C * 2;
+    const long long dim[5] = {L.C, L.hw_out, 1, L.hw_out, N}, st[4] = {px, px, L.hw_out * px, (long long)L.hw_out * L.hw_out * px};
+    for (int i = 0; i < 5; ++i) g.dim[i] = dim[i];
+    for (int i = 0; i < 4; ++i) g.stride_bytes[i] = st[i];
+    g.gx = g.gy = L.hw_out;
+    g.samples = N;
+    g.num_chunks = (L.C + 63) / 64;
+    for (int j = 0; j < g.num_chunks; ++j) g.c0[j] = (signed char)(64 * j);
+  }
 }
 
 static void register_buffers(acx_learner* l) {
@@ -508,6 +589,9 @@ struct GemmOut {
   int mask_ld = 0, mask_rows = 0;
   const uint8_t* a_patch = nullptr;   // A = conv1 patch matrix generated in the kernel from these observations
   int a_patch_samples = 0;
+  const acx_gather_t* a_gather = nullptr;   // operands read in place from NHWC tensors (acx.h)
+  const acx_gather_t* b_gather = nullptr;
+  int perm_m = 0, perm_n = 0;
 };
 
 // plane pairs (i, j) with i + j <= level, low orders first
@@ -573,6 +657,10 @@ static int run_gemm(acx_learner* l, const Planes& a, const Planes& b, int trans,
   g.mask_rows = o.mask_rows;
   g.a_patch_u8 = o.a_patch;
   g.a_patch_samples = o.a_patch_samples;
+  g.a_gather = o.a_gather;
+  g.b_gather = o.b_gather;
+  g.perm_m = o.perm_m;
+  g.perm_n = o.perm_n;
   g.splits = 0;
   g.workspace = ln.sc->ws;
   g.workspace_bytes = ln.sc->ws_bytes;
@@ -612,7 +700,7 @@ static int refresh_weight_planes(acx_learner* l, cudaStream_t st) {
       n[i][q] = i > 0 ? l->wN[i].p[q] : nullptr;   // conv1 has no input gradient
     }
   }
-  ACX_TRY(weight_planes(w, kr, cc, t, ldt, n, ldn, 4, st));
+  ACX_TRY(weight_planes(w, kr, cc, t, ldt, n, ldn, 4, st, l->gather ? 1 : 0));   // gather: conv1's W^T columns in the row-pair copy's order
   for (int i = 1; i <= 2; ++i)
     if (l->conv_tc[i]) {
       const Layer& L = l->L[i];
@@ -648,11 +736,22 @@ static int conv_input_factor(acx_learner* l, int li, const Planes& patches, cons
   GemmOut o;
   o.c = dst;
   o.ldc = d;
-  if (li == 0 && l->conv1_patch) {   // P1^T P1 straight from the uint8 observations
+  if (l->gather) {                   // P^T P read in place from the layer's input (conv1: columns in the row-pair copy's order)
+    o.a_gather = &l->gat_x[li];
+    o.perm_m = o.perm_n = li == 0 ? 1 : 0;
+  } else if (li == 0 && l->conv1_patch) {   // P1^T P1 straight from the uint8 observations
     o.a_patch = obs_u8;
     o.a_patch_samples = l->N;
   }
-  ACX_TRY(run_gemm(l, first_planes(patches, o.a_patch ? 1 : patches.n), patches, 1, L.K, L.K, rows, l->lvl_factor, scale_sq, 1, o, ln));
+  if (l->gather) {
+    Planes x;   // only the plane count matters
+    x.n = l->gat_x[li].num_planes;
+    x.ld = 8;
+    for (int i = 0; i < x.n; ++i) x.p[i] = reinterpret_cast<bf16*>(const_cast<void*>(l->gat_x[li].planes[i]));
+    ACX_TRY(run_gemm(l, x, x, 1, L.K, L.K, rows, l->lvl_factor, scale_sq, 1, o, ln));
+  } else {
+    ACX_TRY(run_gemm(l, first_planes(patches, o.a_patch ? 1 : patches.n), patches, 1, L.K, L.K, rows, l->lvl_factor, scale_sq, 1, o, ln));
+  }
   ACX_TRY(conv_border(obs_u8, act_in, l->N, L.hw_in, L.cin, L.k, L.s, L.hw_out, border_scale, lb.sc->colsum_partial, kBorderChunks,
                       lb.sc->colsum_tmp + 4096, dst, d, lb.st));
   return 0;
@@ -720,7 +819,9 @@ static int forward(acx_learner* l, const uint8_t* obs, int rows, const Lane& ln,
       ACX_TRY(factor(li));
       return run_gemm(l, patches, l->wT[li], 0, rows * L.T, L.C, L.K, l->lvl_fwd, 1.0f, 0, o, ln);
     }
-    if (aux) {
+    if (aux && l->gather) {
+      ACX_TRY(factor(li));   // the input factor reads the layer's input in place: nothing to build
+    } else if (aux) {
       ACX_TRY(fork_lane(l, st, *aux));
       ACX_TRY(im2col_bf16(in, patches, rows * L.T, L.hw_in, L.cin, L.k, L.s, L.hw_out, aux->st));
       if (aux->st != st) ACX_TRY(record_tail(l, aux->st, &l->patches_ready[li]));
@@ -737,16 +838,29 @@ static int forward(acx_learner* l, const uint8_t* obs, int rows, const Lane& ln,
   o.relu = 1;
   // conv1: raw bytes are exact in bf16; the /255 of envs/atari/model.py:93 is the GEMM alpha
   // (with conv1_patch the GEMMs build the patch tiles themselves from `obs`: no im2col pass, no P1)
-  if (!l->conv1_patch) ACX_TRY(im2col_conv1(obs, l->P1.p[0], rows * 400, st));
-  ACX_TRY(factor(0));
   o.bias = l->params + l->L[0].off + (size_t)l->L[0].K * l->L[0].C;
   o.planes = &l->act1;
-  if (l->conv1_patch) {
-    o.a_patch = obs;
-    o.a_patch_samples = rows;
+  if (l->gather) {
+    // the row-pair interleaved bf16 copy of the observations replaces P1 (2x instead of 7.2x the observations, L2 resident);
+    // conv1 forward is an implicit GEMM on it (conv.cu), its input factor and weight gradient read it in place
+    ACX_TRY(obs_pairs_bf16(obs, l->obs_pairs, rows, st));
+    ACX_TRY(factor(0));
+    int pa[6], pb[6];
+    const int np = level_pairs(l->lvl_fwd, 1, l->wT[0].n, pa, pb);
+    set_cta_cap(lane_cta_cap(0));
+    const int rc = conv1_pairs_forward(l->obs_pairs, l->wT[0], rows, o.bias, 1.0f / 255.0f, l->act1, np, pa, pb, st);
+    set_cta_cap(0);
+    ACX_TRY(rc);
+  } else {
+    if (!l->conv1_patch) ACX_TRY(im2col_conv1(obs, l->P1.p[0], rows * 400, st));
+    ACX_TRY(factor(0));
+    if (l->conv1_patch) {
+      o.a_patch = obs;
+      o.a_patch_samples = rows;
+    }
+    ACX_TRY(run_gemm(l, l->P1, l->wT[0], 0, rows * 400, 32, 256, l->lvl_fwd, 1.0f / 255.0f, 0, o, ln));
+    o.a_patch = nullptr;
   }
-  ACX_TRY(run_gemm(l, l->P1, l->wT[0], 0, rows * 400, 32, 256, l->lvl_fwd, 1.0f / 255.0f, 0, o, ln));
-  o.a_patch = nullptr;
   ACX_TRY(conv_layer(1, l->act1, l->P2, l->act2));
   ACX_TRY(conv_layer(2, l->act2, l->P3, l->act3));
   ACX_TRY(factor(3));
@@ -770,6 +884,18 @@ static int weight_grad(acx_learner* l, int li, const Planes& x, const Planes& g,
   GemmOut o;
   o.c = l->grads + L.off;
   o.ldc = L.C;
+  if (l->gather && li < 3) {   // X^T g with both operands read in place over the same locations
+    o.a_gather = &l->gat_x[li];
+    o.b_gather = &l->gat_g[li];
+    o.perm_m = li == 0 ? 1 : 0;
+    Planes xa;   // only the plane counts matter
+    xa.n = l->gat_x[li].num_planes;
+    xa.ld = 8;
+    for (int i = 0; i < xa.n; ++i) xa.p[i] = reinterpret_cast<bf16*>(const_cast<void*>(l->gat_x[li].planes[i]));
+    ACX_TRY(run_gemm(l, xa, g, 1, L.K, L.C, rows, l->lvl_bwd, alpha, 0, o, ln));
+    if (with_bias) ACX_TRY(bias_grad(l, li, g, rows, ln));
+    return 0;
+  }
   if (li == 0 && l->conv1_patch) {
     o.a_patch = l->obs;
     o.a_patch_samples = l->N;
@@ -1146,6 +1272,11 @@ static int check_cfg(const acx_learner_config_t* c) {
 
 static void init_dims(acx_learner* l, const acx_learner_config_t* cfg) {
   l->cfg = *cfg;
+  {
+    // ACX_GATHER=0: round 1's materialised patch matrices P1 / P2 / P3 (im2col kernels)
+    const char* e = getenv("ACX_GATHER");
+    l->gather = cfg->gemm_impl == 0 && cfg->conv_impl == 0 && (e == nullptr || atoi(e) != 0);
+  }
   // precision: activations / gradients are kept as act_planes bf16 planes; a GEMM of level L accumulates the plane
   // pairs (i, j) with i + j <= L  (1 pair = bf16 inputs, 3 pairs ~ 2^-17, 6 pairs = fp32 class)
   switch (cfg->precision) {
@@ -1203,6 +1334,7 @@ acx_learner_t* acx_learner_create(const acx_learner_config_t* cfg, void* d_arena
     return nullptr;
   }
   layout(l, reinterpret_cast<uint8_t*>(d_arena));
+  setup_gather(l);
   register_buffers(l);
   l->gs = 0;
   l->ncov = 0;
@@ -1226,7 +1358,7 @@ acx_learner_t* acx_learner_create(const acx_learner_config_t* cfg, void* d_arena
   // implicit-GEMM forward of conv2 / conv3 only pays when its patch matrix can be built concurrently on another lane
   for (int i = 0; i < 4; ++i) {
     const ConvGeom g = {l->L[i].hw_in, l->L[i].cin, l->L[i].k, l->L[i].s, l->L[i].hw_out, l->L[i].C};
-    l->conv_fwd_tc[i] = (i == 1 || i == 2) && l->cfg.conv_impl == 0 && l->cfg.gemm_impl == 0 && l->lanes > 1 && fwd_tc_enabled() &&
+    l->conv_fwd_tc[i] = (i == 1 || i == 2) && l->cfg.conv_impl == 0 && l->cfg.gemm_impl == 0 && (l->lanes > 1 || l->gather) && fwd_tc_enabled() &&
                         conv_tc_supported(g, 0);
   }
   for (int i = 0; i + 1 < l->lanes; ++i)

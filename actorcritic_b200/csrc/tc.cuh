@@ -10,6 +10,11 @@ namespace acx {
 static __device__ int g_tc_error = 0;
 
 
+// conv.cu: cached tensor map of a bf16 tensor view of rank <= 5 (dim / box innermost first, stride_bytes[i] = byte stride of
+// dim i + 1); swizzle_bytes = 128 or 64
+int get_view_map(const void* ptr, int rank, const long long* dim, const long long* stride_bytes, const int* box, int swizzle_bytes,
+                 CUtensorMap* out);
+
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
 // ------------------------------------------------------------------------------------------------

@@ -106,6 +106,31 @@ def split_planes(x, num_planes, scale=1.0):
     return planes
 
 
+def gather_view(planes, dim, stride_bytes, gx, gy, samples, chunks):
+    """acx_gather_t (include/acx.h): a patch operand read in place.  `chunks` = per 64-column chunk the coordinates
+    (c0, c1, c2, c3) added to (0, x, 0, y, sample) of the 5-D view `dim` / `stride_bytes` (innermost first)."""
+    g = _lib.Gather()
+    for i, p in enumerate(planes):
+        g.planes[i] = p.data_ptr()
+    g.num_planes = len(planes)
+    for i in range(5):
+        g.dim[i] = dim[i]
+    for i in range(4):
+        g.stride_bytes[i] = stride_bytes[i]
+    g.gx, g.gy, g.samples, g.num_chunks = gx, gy, samples, len(chunks)
+    for q, (c0, c1, c2, c3) in enumerate(chunks):
+        g.c0[q], g.c1[q], g.c2[q], g.c3[q] = c0, c1, c2, c3
+    return g
+
+
+def obs_pairs(obs):
+    """uint8 [S, 84, 84, 4] -> the row-pair interleaved bf16 copy [S, 42, 84, 2, 4] (acx_obs_pairs_bf16)."""
+    assert obs.dtype == torch.uint8 and obs.is_contiguous() and tuple(obs.shape[1:]) == (84, 84, 4)
+    out = torch.empty((obs.shape[0], 42, 84, 2, 4), dtype=torch.bfloat16, device=obs.device)
+    _lib.check(_lib.load().acx_obs_pairs_bf16(obs.data_ptr(), out.data_ptr(), obs.shape[0], _stream()))
+    return out
+
+
 def _planes_struct(planes, rows, cols):
     s = _lib.Planes()
     for i, p in enumerate(planes):
@@ -119,10 +144,36 @@ PAIRS = {1: [(0, 0)], 3: [(0, 0), (0, 1), (1, 0)], 6: [(0, 0), (0, 1), (1, 0), (
 
 
 def gemm(a_planes, b_planes, m, n, k, trans=False, pairs=None, alpha=1.0, bias=None, relu=False, symmetric=False,
-         out_planes=0, want_f32=True, mask=None, mask_rows=0, splits=0, impl=0, a_patch_obs=None):
+         out_planes=0, want_f32=True, mask=None, mask_rows=0, splits=0, impl=0, a_patch_obs=None, a_gather=None, b_gather=None,
+         perm_m=0, perm_n=0):
     """C[m,n] = alpha * sum_pairs op(A_i) op(B_j) (+bias) via acx_gemm.
     trans=False: A planes stored [m,k], B planes stored [n,k];  trans=True: A stored [k,m], B stored [k,n]."""
     lib = _lib.load()
+    if a_gather is not None:
+        # operands read in place from NHWC tensors (acx_gather_t, include/acx.h); `a_planes` / `b_planes` only keep the tensors alive
+        assert trans and pairs is not None
+        dev = a_planes[0].device
+        g = _lib.Gemm()
+        g.a.num_planes, g.b.num_planes = a_gather.num_planes, (b_gather or a_gather).num_planes
+        g.a_gather = ctypes.pointer(a_gather)
+        if b_gather is not None:
+            g.b_gather = ctypes.pointer(b_gather)
+        g.perm_m, g.perm_n = perm_m, perm_n
+        g.trans_a = g.trans_b = 1
+        g.m, g.n, g.k = m, n, k
+        g.num_pairs = len(pairs)
+        for i, (pa, pb) in enumerate(pairs):
+            g.pair_a[i], g.pair_b[i] = pa, pb
+        g.alpha = alpha
+        g.symmetric = int(symmetric)
+        c = torch.empty((m, n), dtype=torch.float32, device=dev)
+        g.c, g.ldc = c.data_ptr(), n
+        g.splits = splits
+        ws_bytes = lib.acx_gemm_workspace_bytes(ctypes.byref(g))
+        ws = torch.zeros(max(ws_bytes, 4) // 4, dtype=torch.float32, device=dev)
+        g.workspace, g.workspace_bytes = ws.data_ptr(), ws_bytes
+        _lib.check(lib.acx_gemm(ctypes.byref(g), impl, _stream()))
+        return c, []
     dev = b_planes[0].device if a_patch_obs is None else a_patch_obs.device
     if a_patch_obs is not None:
         # A = the conv1 patch matrix of uint8 observations [samples, 84, 84, 4], generated inside the kernel (a_planes unused)

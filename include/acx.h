@@ -83,6 +83,21 @@ typedef struct {
   int ld;                              /* elements; multiple of 8 */
 } acx_planes_t;
 
+/* A GEMM operand that is never materialised: the patch matrix of an NHWC tensor - what the im2col of nn.conv2d
+ * (nn.py:88-110) or kfac's extract_image_patches (envs/atari/model.py:227-237) would build - read by TMA box loads straight
+ * from the tensor.  The rows of the operand are the locations (sample, y, x) of a gx x gy output grid (any order: the
+ * products that use it sum over rows); its columns come in chunks of 64 bf16 that are contiguous in memory.  `dim` /
+ * `stride_bytes` describe a 5-D view of each plane (innermost first, dim[0] elements contiguous, strides multiples of
+ * 16 bytes, overlapping allowed) in which chunk q of location (sample, y, x) starts at the coordinates
+ * (c0[q], x + c1[q], c2[q], y + c3[q], sample).  Out-of-range coordinates read as zero. */
+typedef struct {
+  const void* planes[ACX_MAX_PLANES]; int num_planes;
+  long long dim[5]; long long stride_bytes[4];
+  int gx, gy, samples;                 /* operand rows = samples * gy * gx */
+  int num_chunks;                      /* operand columns = 64 * num_chunks (<= 16 chunks) */
+  signed char c0[16], c1[16], c2[16], c3[16];
+} acx_gather_t;
+
 typedef struct {
   /* C[M,N] = alpha * sum_{(i,j) in pairs} opA(A_i) * opB(B_j)  (+ bias[n]) ; fp32 accumulate.
    * trans_a == 0: A stored [M,K] (K-major);  trans_a == 1: A stored [K,M] (MN-major).
@@ -115,8 +130,21 @@ typedef struct {
    * trans_a == 0: A = P1 [m = patch rows, k = 256];  trans_a == 1: A = P1 [k = patch rows, m = 256]; with `symmetric`
    * (n = 256) both sides are P1 and `b` is ignored.  Replaces extract_image_patches + the materialised patch matrix. */
   const uint8_t* a_patch_u8; int a_patch_samples;
+  /* optional (MN-major products only, trans_a == trans_b == 1): A and / or B are patch matrices read in place from NHWC
+   * tensors (see acx_gather_t; `a.planes` / `b.planes` are then ignored and k = samples * gy * gx).  Both operands must
+   * enumerate the same locations: either both are gathered over the same grid, or the product is `symmetric` and B = A.
+   * perm_m / perm_n != 0: row / column i of the result is stored at index (i & ~63) | perm(i & 63) with
+   * perm(kw*8 + p*4 + c) = p*32 + kw*4 + c - the column order of conv1's patches when they are read from the row-pair
+   * interleaved observation copy (acx_obs_pairs_bf16) back to the (kh, kw, c) order of the reference. */
+  const acx_gather_t* a_gather; const acx_gather_t* b_gather;
+  int perm_m, perm_n;
 } acx_gemm_t;
 
+/* Row-pair interleaved bf16 copy of uint8 observations [samples, 84, 84, 4] (envs/atari/model.py:92-93; raw byte values, exact):
+ * out[n][p][x][q][c] = obs[n][2p + q][x][c], bf16 [samples, 42, 84, 2, 4].  The two kernel rows 2j, 2j + 1 of conv1's 8x8 / stride-4
+ * patch at (oy, ox) are then 64 contiguous elements at pair-row 2 oy + j, pixel 4 ox, in the column order (kw, q, c): the patch
+ * matrix the reference's conv1 and kfac's conv1 input factor are built on never has to be stored (acx_gather_t, perm_m / perm_n). */
+int acx_obs_pairs_bf16(const uint8_t* d_obs, void* d_out, int samples, void* stream);
 /* impl: 0 = tcgen05 tensor-core kernel (the product path), 1 = SIMT fp32 reference kernel on the
  * same planes (debug/validation only, never selected automatically). */
 int acx_gemm(const acx_gemm_t* g, int impl, void* stream);
