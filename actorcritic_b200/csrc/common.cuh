@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <cstring>
 #include <string>
 
 #include "../../include/acx.h"
@@ -47,6 +48,46 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 typedef __nv_bfloat16 bf16;
+
+// Programmatic dependent launch: a kernel launched with `launch_pdl` may start (block scheduling, barrier / TMEM set-up)
+// while its predecessor in the stream is still running its tail; it must call pdl_wait() before it touches global memory
+// (waits until the predecessor grid has completed and its writes are visible).  pdl_trigger() in the predecessor allows the
+// successor's blocks to be scheduled from that point on (otherwise: when the predecessor has finished).  ACX_PDL=0 launches
+// everything with plain stream ordering.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// small kernels: let the successor be scheduled at once (it blocks in its own pdl_wait without holding much of an SM), then wait
+__device__ __forceinline__ void pdl_enter() {
+  pdl_trigger();
+  pdl_wait();
+}
+int pdl_level();   // ACX_PDL: 0 = off, 1 = tensor-core kernels and their finalize kernels, 2 = also the small kernels
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl_at(int level, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_level() >= level ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  return launch_pdl_at(1, kernel, grid, block, smem, st, static_cast<Args&&>(args)...);
+}
+// launch + error check + launch count, as ACX_LAUNCH_CHECK does for <<< >>> launches
+#define ACX_PDL_LAUNCH(kernel, grid, block, smem, st, ...)                                     \
+  do {                                                                                         \
+    ACX_CUDA(acx::launch_pdl_at(2, kernel, dim3(grid), dim3(block), (size_t)(smem), st, __VA_ARGS__)); \
+    acx::count_launch();                                                                       \
+  } while (0)
 
 // ---------------------------------------------------------------------------------------------
 // device helpers

@@ -111,6 +111,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int sub_tile_bytes = CV_A_TILE / p.nsub;
+  pdl_wait();   // the set-up above overlapped the predecessor's tail; its results are visible from here on
 
   if (warp == 0) {
     {
@@ -145,6 +146,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
           }
         }
       }
+      __syncwarp();
+      if (elect_one()) pdl_trigger();   // all loads of this CTA's last tile are issued: the successor's blocks may be scheduled
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one elected lane) =====
@@ -381,6 +384,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
 __global__ void __launch_bounds__(256) dgrad_weight_planes_kernel(const float* __restrict__ w, int c_in, int c_out, int k, int s,
                                                                   bf16* __restrict__ p0, bf16* __restrict__ p1, bf16* __restrict__ p2,
                                                                   int ld) {
+  pdl_enter();
   const int m = k / s;
   const int rows = s * s * c_in, cols = m * m * c_out;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < rows * ld; e += gridDim.x * blockDim.x) {
@@ -552,8 +556,7 @@ static int launch_conv(const CUtensorMap* ta, const CUtensorMap* tb, ConvTcParam
   int grid = std::min(p.num_tiles, conv_num_sms());
   if (g_cta_cap > 0 && grid > g_cta_cap) grid = g_cta_cap;
   const int smem = CV_SMEM_FIXED + p.stages * stage_bytes;
-  conv_tc_kernel<<<grid, CV_THREADS, smem, st>>>(ta[0], ta[1], ta[2], tb[0], tb[1], tb[2], p);
-  ACX_LAUNCH_CHECK();
+  ACX_CUDA(launch_pdl(conv_tc_kernel, dim3(grid), dim3(CV_THREADS), (size_t)smem, st, ta[0], ta[1], ta[2], tb[0], tb[1], tb[2], p));
   return 0;
 }
 
@@ -814,9 +817,7 @@ int conv_dgrad_weight_planes(const float* w, const ConvGeom& g, const Planes& ou
   const int m = g.k / g.s;
   ACX_CHECK(out.ld >= m * m * g.c_out, "dgrad weight planes: leading dimension too small");
   const int total = g.s * g.s * g.c_in * out.ld;
-  dgrad_weight_planes_kernel<<<std::min(ceil_div(total, 256), 296), 256, 0, st>>>(w, g.c_in, g.c_out, g.k, g.s, out.p[0], out.p[1],
-                                                                                 out.p[2], out.ld);
-  ACX_LAUNCH_CHECK();
+  ACX_PDL_LAUNCH(dgrad_weight_planes_kernel, std::min(ceil_div(total, 256), 296), 256, 0, st, w, g.c_in, g.c_out, g.k, g.s, out.p[0], out.p[1], out.p[2], out.ld);
   return 0;
 }
 

@@ -6,6 +6,7 @@
 //
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
 // warps 2..5 = epilogue (one TMEM lane quarter each).
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -68,6 +69,7 @@ struct TcParams {
   // which CTA arrives last.  Counters: per tile `groups` group counters + 1 tile counter, zero on entry, left zero.
   // gathered MN-major operands (acx_gather_t): k-block kb = the 64 locations of box (bx x by cells, ts samples) number
   // kb % g_cells of sample group kb / g_cells; chunk q of a location comes from coordinates (c0, x + c1, c2, y + c3, sample)
+  int same_operand;      // symmetric product of one operand with itself: diagonal tiles load their operand once (B = the A tiles)
   int gather_a, gather_b;
   int g_cells, g_nx, g_bx, g_by, g_ts;
   signed char ga[4][16], gb[4][16];
@@ -284,6 +286,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above overlapped the predecessor's tail; its results are visible from here on
 
   // work item -> (tile_m, tile_n, split)
   auto decode = [&](int w, int& tm, int& tn, int& split) {
@@ -325,9 +328,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
         const int nb = MAJOR == 0 ? 0 : min(BN / 64, (p.out.n - n0 + 63) / 64);
         const int nch = (p.out.n + 63) / 64;   // panel mode: 64-column chunks of X
         constexpr bool patch = PATCH;   // the A tiles (all tiles in panel mode) come from the patch warps
+        const bool diag = MAJOR == 1 && p.same_operand && tm == tn;   // B tile = A tile: loaded once
         const uint32_t tx = p.panel ? (patch ? 0u : (uint32_t)(p.npa * nch * bk * 128))
                                     : (MAJOR == 0 ? (uint32_t)(stage_bytes - (patch ? p.npa * a_tile_bytes : 0))
-                                                  : (uint32_t)(((patch ? 0 : p.npa * na) + p.npb * nb) * bk * 128));
+                                                  : (uint32_t)(((patch ? 0 : p.npa * na) + (diag ? 0 : p.npb * nb)) * bk * 128));
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
@@ -373,7 +377,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
               for (int j = 0; j < na; ++j) tma_load_2d(dst + j * (bk * 128), ma, &full_bar[s], m0 + 64 * j, kb * bk);
             }
           }
-          for (int i = 0; i < p.npb; ++i) {
+          for (int i = 0; i < p.npb && !diag; ++i) {
             const CUtensorMap* mb = i == 0 ? &tb0 : (i == 1 ? &tb1 : &tb2);
             uint8_t* dst = b_s + i * b_tile_bytes;
             if (MAJOR == 0) {
@@ -389,6 +393,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
           }
         }
       }
+      // every load of this CTA's last work item is issued: the successor's blocks may be scheduled onto SMs as they free up
+      __syncwarp();
+      if (elect_one()) pdl_trigger();
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one elected lane) =====
@@ -401,11 +408,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
     const uint32_t kstep = MAJOR == 0 ? 32u : p.mn_kstep;
     const uint64_t kstep16 = (uint64_t)(kstep >> 4);
     // descriptor offsets (16-byte units) of every plane pair's A / B tile inside a stage
-    uint32_t a_off[6], b_off[6];
+    uint32_t a_off[6], b_off[6], b_off_d[6];   // b_off_d: the B plane inside the A tiles (diagonal tiles of a one-operand SYRK)
 #pragma unroll
     for (int pr = 0; pr < 6; ++pr) {
       a_off[pr] = (uint32_t)(p.pair_a[pr] * a_tile_bytes) >> 4;
       b_off[pr] = (uint32_t)(p.pair_b[pr] * b_tile_bytes) >> 4;
+      b_off_d[pr] = (uint32_t)(p.pair_b[pr] * a_tile_bytes) >> 4;
     }
     const int npairs = p.num_pairs;
     const bool trace = p.trace != 0 && blockIdx.x == 0;   // ACX_GEMM_TRACE=1: where CTA 0's MMA warp spends its cycles
@@ -419,6 +427,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
       const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
       const int buf = p.panel ? 0 : (lt & 1);
       const uint32_t aph = p.panel ? ((uint32_t)lt & 1u) : ((uint32_t)(lt >> 1) & 1u);
+      const bool diag = MAJOR == 1 && p.same_operand && !p.panel && tm == tn;
       if (trace) tw = clock64();
       mbar_wait(&acc_empty[buf], aph ^ 1u, 4);
       if (trace) w_acc += clock64() - tw;
@@ -435,7 +444,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
           const int kvalid = min(bk, p.k - kb * bk);
           const int ksteps = (kvalid + 15) >> 4;
           const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-          const uint32_t b_addr = a_addr + (uint32_t)(p.npa * a_tile_bytes);
+          const uint32_t b_addr = diag ? a_addr : a_addr + (uint32_t)(p.npa * a_tile_bytes);
           // the descriptor of a tile advanced by `off` bytes is base + (off >> 4): only the 14-bit address field moves
           // (tiles are 1024-byte aligned inside the < 256 KB shared window, so the add never carries out of the field)
           const uint64_t a_desc0 = make_smem_desc_sw(a_addr, lbo, sbo, layout);
@@ -467,13 +476,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
                   umma_bf16(d_tmem, a_desc0 + (uint64_t)(a_off[pr] + (uint32_t)kk * (uint32_t)kstep16),
-                            b_desc0 + (uint64_t)(b_off[pr] + (uint32_t)kk * (uint32_t)kstep16), idesc, (pr | kk) ? 1u : acc_flag);
+                            b_desc0 + (uint64_t)((diag ? b_off_d[pr] : b_off[pr]) + (uint32_t)kk * (uint32_t)kstep16), idesc,
+                            (pr | kk) ? 1u : acc_flag);
               }
             }
           } else {
             for (int pr = 0; pr < p.num_pairs; ++pr) {
               uint64_t ad = a_desc0 + (uint64_t)((uint32_t)(p.pair_a[pr] * a_tile_bytes) >> 4);
-              uint64_t bd = b_desc0 + (uint64_t)((uint32_t)(p.pair_b[pr] * b_tile_bytes) >> 4);
+              uint64_t bd = b_desc0 + (uint64_t)((uint32_t)(p.pair_b[pr] * (diag ? a_tile_bytes : b_tile_bytes)) >> 4);
               for (int kk = 0; kk < ksteps; ++kk) {
                 umma_bf16(d_tmem, ad, bd, idesc, acc_flag);
                 acc_flag = 1u;
@@ -890,6 +900,7 @@ __global__ void __launch_bounds__(256) gemm_finalize_kernel(OutParams o, const f
                                                             long long ws_split_stride, int splits, int symmetric, int bm,
                                                             int bn) {
   __shared__ float red[256];
+  pdl_wait();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int m = blockIdx.y;
   float acc = 0.0f;
@@ -931,6 +942,7 @@ __global__ void __launch_bounds__(256) gemm_finalize_kernel(OutParams o, const f
 // 672 x 512 result; this one is bound by the launch and one L2 round trip).  Fixed association order: deterministic.
 __global__ void __launch_bounds__(256) gemm_finalize_vec4_kernel(OutParams o, const float* __restrict__ ws, int ws_ld,
                                                                  long long ws_split_stride, int splits) {
+  pdl_wait();
   const int nq = (o.n + 3) >> 2;   // a ragged last quad is allowed for plane-only outputs whose rows are padded (see below)
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i >= (long long)o.m * nq) return;
@@ -1018,6 +1030,7 @@ __global__ void __launch_bounds__(1024) gemm_finalize_sym_kernel(OutParams o, co
   // than one thread per element provides); lane z sums splits z, z + L, ... and the lanes are combined in lane order
   __shared__ float tile[8][33];
   __shared__ float red[3][256];
+  pdl_wait();
   int t = blockIdx.x, bi = 0, cnt = nblk;
   while (t >= cnt) {
     t -= cnt;
@@ -1132,6 +1145,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(SimtParams p) {
 
 __global__ void split_planes_kernel(const float* __restrict__ in, int ld_in, int rows, int cols, float scale, bf16* p0,
                                     bf16* p1, bf16* p2, int num_planes, int ld_out) {
+  pdl_enter();
   const size_t total = (size_t)rows * ld_out;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / ld_out), c = (int)(i % ld_out);
@@ -1305,11 +1319,18 @@ static void plan_tc(const acx_gemm_t* g, TcPlan* pl) {
     int bx = 1, by = 1;
     while (bx < 8 && ga->gx % (2 * bx) == 0) bx *= 2;
     while (bx * by < 64 && ga->gy % (2 * by) == 0) by *= 2;
+    if (const char* e = getenv("ACX_GATHER_CUT")) {   // triage: "bx,by" (powers of two; boxes that overhang the grid read zero rows)
+      int a = 0, b = 0;
+      if (sscanf(e, "%d,%d", &a, &b) == 2 && a >= 1 && b >= 1 && a * b <= 64 && (a & (a - 1)) == 0 && (b & (b - 1)) == 0) {
+        bx = a;
+        by = b;
+      }
+    }
     pl->g_bx = bx;
     pl->g_by = by;
     pl->g_ts = 64 / (bx * by);
-    pl->g_nx = ga->gx / bx;
-    pl->g_cells = pl->g_nx * (ga->gy / by);
+    pl->g_nx = ceil_div(ga->gx, bx);
+    pl->g_cells = pl->g_nx * ceil_div(ga->gy, by);
     pl->kb_total = pl->g_cells * ceil_div(ga->samples, pl->g_ts);
   }
   int splits = g->splits;
@@ -1359,14 +1380,23 @@ static int launch_tc(const CUtensorMap* ta, const CUtensorMap* tb, const TcParam
     configured = true;
   }
   if (g_probe_on) ACX_CUDA(cudaEventRecord(g_probe_ev[0], st));
-  gemm_tc_kernel<MAJOR, PATCH><<<grid, GEMM_THREADS + (PATCH ? PATCH_THREADS : 0), smem, st>>>(ta[0], ta[1], ta[2], tb[0], tb[1], tb[2], p);
-  ACX_LAUNCH_CHECK();
+  ACX_CUDA(launch_pdl(gemm_tc_kernel<MAJOR, PATCH>, dim3(grid), dim3(GEMM_THREADS + (PATCH ? PATCH_THREADS : 0)), (size_t)smem, st, ta[0], ta[1],
+                      ta[2], tb[0], tb[1], tb[2], p));
   if (g_probe_on) ACX_CUDA(cudaEventRecord(g_probe_ev[1], st));
   return 0;
 }
 
 // triage knob (ACX_MAIN_CTAS / ACX_SIDE_CTAS, learner.cu): cap on the persistent grid of the next tensor-core launches, so
 // that kernels of different lanes can share the SMs instead of queueing behind each other (0 = all SMs)
+int pdl_level() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ACX_PDL");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+
 int g_cta_cap = 0;
 void set_cta_cap(int cap) { g_cta_cap = cap; }
 
@@ -1464,6 +1494,15 @@ static int gemm_tc(const acx_gemm_t* g, cudaStream_t st) {
   p.k = ga ? pl.kb_total * pl.bk : g->k;   // gathered: every k-block is whole (locations beyond the batch read as zero rows)
   p.kb_total = pl.kb_total;
   p.kb_per_split = pl.kb_per_split;
+  {
+    const bool one = ga ? (g->b_gather == nullptr || g->b_gather == g->a_gather) : (g->a.planes[0] == g->b.planes[0] && g->a.ld == g->b.ld);
+    static int dg = -1;
+    if (dg < 0) {
+      const char* e = getenv("ACX_SYRK_DIAG");   // 0: diagonal tiles load both operand sides (round 1)
+      dg = e ? atoi(e) : 1;
+    }
+    p.same_operand = (dg && g->symmetric && major == 1 && !patch && one && pl.npa >= pl.npb) ? 1 : 0;
+  }
   p.gather_a = p.gather_b = ga ? 1 : 0;
   p.g_cells = pl.g_cells;
   p.g_nx = pl.g_nx;
@@ -1532,21 +1571,19 @@ static int gemm_tc(const acx_gemm_t* g, cudaStream_t st) {
   if (pl.to_ws && g->symmetric && g->n > 64) {
     const int nblk = ceil_div(g->n, 32);
     const int zl = pl.splits >= 64 ? 4 : (pl.splits >= 24 ? 2 : 1);   // split lanes per element
-    gemm_finalize_sym_kernel<<<dim3(nblk * (nblk + 1) / 2, 4), dim3(256, zl), 0, st>>>(p.out, p.ws, p.ws_ld, p.ws_split_stride, pl.splits, nblk);
-    ACX_LAUNCH_CHECK();
+    ACX_CUDA(launch_pdl(gemm_finalize_sym_kernel, dim3(nblk * (nblk + 1) / 2, 4), dim3(256, zl), 0, st, p.out, (const float*)p.ws, p.ws_ld,
+                        p.ws_split_stride, pl.splits, nblk));
   } else if (pl.to_ws && !g->symmetric && pl.splits <= 16 && finalize_vec4_ok(p.out, p.ws_ld, p.ws_split_stride)) {
     // (deep split-K of a small result - the conv wgrads - keeps the kernel whose thread lanes share the splits: measured
     // 5.4 vs 14.1 us at 146 splits of a 256 x 32 result)
     const long long quads = (long long)g->m * ((g->n + 3) >> 2);
-    gemm_finalize_vec4_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, st>>>(p.out, p.ws, p.ws_ld, p.ws_split_stride,
-                                                                              pl.splits);
-    ACX_LAUNCH_CHECK();
+    ACX_CUDA(launch_pdl(gemm_finalize_vec4_kernel, dim3((unsigned)((quads + 255) / 256)), dim3(256), 0, st, p.out, (const float*)p.ws, p.ws_ld,
+                        p.ws_split_stride, pl.splits));
   } else if (pl.to_ws) {
     const int lanes = pl.splits >= 8 ? 8 : (pl.splits >= 4 ? 4 : (pl.splits >= 2 ? 2 : 1));
     dim3 fg(ceil_div(g->n, 256 / lanes), g->m);
-    gemm_finalize_kernel<<<fg, dim3(256 / lanes, lanes), 0, st>>>(p.out, p.ws, p.ws_ld, p.ws_split_stride, pl.splits, g->symmetric, BM,
-                                            pl.bn);
-    ACX_LAUNCH_CHECK();
+    ACX_CUDA(launch_pdl(gemm_finalize_kernel, fg, dim3(256 / lanes, lanes), 0, st, p.out, (const float*)p.ws, p.ws_ld, p.ws_split_stride,
+                        pl.splits, g->symmetric, BM, pl.bn));
   }
   return 0;
 }
@@ -1587,8 +1624,7 @@ int split_planes(const float* in, int ld_in, int rows, int cols, float scale, bf
   const size_t total = (size_t)rows * ld_out;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  split_planes_kernel<<<blocks, 256, 0, st>>>(in, ld_in, rows, cols, scale, p0, p1, p2, num_planes, ld_out);
-  ACX_LAUNCH_CHECK();
+  ACX_PDL_LAUNCH(split_planes_kernel, blocks, 256, 0, st, in, ld_in, rows, cols, scale, p0, p1, p2, num_planes, ld_out);
   return 0;
 }
 

@@ -21,6 +21,7 @@ __global__ void homog_border_kernel(float* __restrict__ a, int d, const float* _
 
 // S <- decay * S + (1 - decay) * scale_c * C      (kfac MovingAverageVariable, cov_ema_decay)
 __global__ void ema_kernel(float* __restrict__ s, const float* __restrict__ c, size_t count, float decay, float wc) {
+  pdl_enter();
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t n4 = count / 4;
@@ -720,6 +721,7 @@ __global__ void __launch_bounds__(256, 1) inv_persistent_kernel(const InvPersist
 // partial[b] = sum over the b-th contiguous chunk of a[i] * b[i]   (deterministic two-stage reduction)
 __global__ void __launch_bounds__(256) dot_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t count,
                                                           float* __restrict__ partial) {
+  pdl_enter();
   __shared__ double red[8];
   const size_t per = (count + gridDim.x - 1) / gridDim.x;
   const size_t i0 = (size_t)blockIdx.x * per;
@@ -765,6 +767,7 @@ __global__ void __launch_bounds__(256) kfac_step_kernel(float* __restrict__ para
                                                         const float* __restrict__ partial, int num_partials,
                                                         const Sched* __restrict__ sched, float mu, float kappa,
                                                         float* __restrict__ out_scalars) {
+  pdl_enter();
   const float lr = sched->lr;
   const float s = sum_partials(partial, num_partials);
   float c = 1.0f;
@@ -811,6 +814,7 @@ __global__ void __launch_bounds__(256) momentum_clip_kernel(float* __restrict__ 
                                                             const float* __restrict__ grads, size_t count,
                                                             const float* __restrict__ partial, int num_partials, float lr,
                                                             float mu, float clip, float* __restrict__ out_scalars) {
+  pdl_enter();
   const float sq = sum_partials(partial, num_partials);
   const float norm = sqrtf(sq);
   const float scale = clip / fmaxf(norm, clip);
@@ -830,6 +834,7 @@ __global__ void __launch_bounds__(256) rmsprop_clip_kernel(float* __restrict__ p
                                                            const float* __restrict__ partial, int num_partials,
                                                            const Sched* __restrict__ sched, float decay, float eps, float clip,
                                                            float* __restrict__ out_scalars, float lr_value) {
+  pdl_enter();
   const float lr = sched ? sched->lr : lr_value;
   const float sq = sum_partials(partial, num_partials);
   const float norm = sqrtf(sq);
@@ -853,6 +858,7 @@ __global__ void __launch_bounds__(256) rmsprop_clip_kernel(float* __restrict__ p
 // ------------------------------------------------------------------------------------------------
 // W[r, c] = sum_k V[r, k] Ginv[k, c];  grid (ceil(d / 64), 1, jobs), 256 threads
 __global__ void __launch_bounds__(256) precon_vg_kernel(const PreconJob* __restrict__ jobs) {
+  pdl_enter();
   const PreconJob jb = jobs[blockIdx.z];
   const int d = jb.d, c = jb.c;
   const int r0 = blockIdx.x * 64;
@@ -904,6 +910,7 @@ __global__ void __launch_bounds__(256) precon_vg_kernel(const PreconJob* __restr
 // U[r, c] = scale * sum_k Ainv[r, k] W[k, c];  grid (ceil(d / 16), 1, jobs), 256 threads = 16 rows x 16 column lanes
 // (4 columns each), k in chunks of 64
 __global__ void __launch_bounds__(256) precon_aw_kernel(const PreconJob* __restrict__ jobs) {
+  pdl_enter();
   const PreconJob jb = jobs[blockIdx.z];
   const int d = jb.d, c = jb.c;
   const int r0 = blockIdx.x * 16;
@@ -956,6 +963,7 @@ __global__ void __launch_bounds__(256) precon_aw_kernel(const PreconJob* __restr
 
 // schedule state (one thread)
 __global__ void sched_begin_kernel(Sched* s, float lr_start, float lr_end, double decay_steps, float* out_lr) {
+  pdl_enter();
   // nn.py:154-156 linear_decay = polynomial_decay(power 1, cycle False), evaluated at the step the update starts with
   double g = (double)s->gs;
   if (g > decay_steps) g = decay_steps;
@@ -963,6 +971,7 @@ __global__ void sched_begin_kernel(Sched* s, float lr_start, float lr_end, doubl
   if (out_lr) *out_lr = s->lr;
 }
 __global__ void sched_advance_kernel(Sched* s, int gs_inc, int ncov_inc, float ema_decay, int zero_debias) {
+  pdl_enter();
   s->gs += (unsigned long long)gs_inc;
   s->ncov += (unsigned long long)ncov_inc;
   if (ncov_inc) {
@@ -976,6 +985,7 @@ __global__ void sched_advance_kernel(Sched* s, int gs_inc, int ncov_inc, float e
 // the counters (nothing later in the phase reads global_step; the inverse refresh reads the new debias factor)
 __global__ void sched_step_kernel(Sched* s, float lr_start, float lr_end, double decay_steps, float* out_lr, int gs_inc,
                                   int ncov_inc, float ema_decay, int zero_debias) {
+  pdl_enter();
   double g = (double)s->gs;
   if (g > decay_steps) g = decay_steps;
   s->lr = (float)(((double)lr_start - (double)lr_end) * (1.0 - g / decay_steps) + (double)lr_end);
@@ -994,18 +1004,15 @@ __global__ void sched_step_kernel(Sched* s, float lr_start, float lr_end, double
 // ------------------------------------------------------------------------------------------------
 int sched_step(Sched* s, float lr_start, float lr_end, double decay_steps, float* out_lr, int gs_inc, int ncov_inc,
                float ema_decay, int zero_debias, cudaStream_t st) {
-  sched_step_kernel<<<1, 1, 0, st>>>(s, lr_start, lr_end, decay_steps, out_lr, gs_inc, ncov_inc, ema_decay, zero_debias);
-  ACX_LAUNCH_CHECK();
+  ACX_PDL_LAUNCH(sched_step_kernel, 1, 1, 0, st, s, lr_start, lr_end, decay_steps, out_lr, gs_inc, ncov_inc, ema_decay, zero_debias);
   return 0;
 }
 int sched_begin(Sched* s, float lr_start, float lr_end, double decay_steps, float* out_lr, cudaStream_t st) {
-  sched_begin_kernel<<<1, 1, 0, st>>>(s, lr_start, lr_end, decay_steps, out_lr);
-  ACX_LAUNCH_CHECK();
+  ACX_PDL_LAUNCH(sched_begin_kernel, 1, 1, 0, st, s, lr_start, lr_end, decay_steps, out_lr);
   return 0;
 }
 int sched_advance(Sched* s, int gs_inc, int ncov_inc, float ema_decay, int zero_debias, cudaStream_t st) {
-  sched_advance_kernel<<<1, 1, 0, st>>>(s, gs_inc, ncov_inc, ema_decay, zero_debias);
-  ACX_LAUNCH_CHECK();
+  ACX_PDL_LAUNCH(sched_advance_kernel, 1, 1, 0, st, s, gs_inc, ncov_inc, ema_decay, zero_debias);
   return 0;
 }
 
@@ -1023,8 +1030,7 @@ int homog_border(float* a, int d, const float* colsum_scaled, cudaStream_t st) {
 }
 int ema_update(float* s, const float* c, size_t count, float decay, float scale_c, cudaStream_t st) {
   ACX_CHECK(((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(c)) & 15) == 0, "unaligned factor region");
-  ema_kernel<<<grid_for(count / 4 + 1, 256, 148 * 8), 256, 0, st>>>(s, c, count, decay, (1.0f - decay) * scale_c);
-  ACX_LAUNCH_CHECK();
+  ACX_PDL_LAUNCH(ema_kernel, grid_for(count / 4 + 1, 256, 148 * 8), 256, 0, st, s, c, count, decay, (1.0f - decay) * scale_c);
   return 0;
 }
 int fill_f32(float* p, size_t count, float v, cudaStream_t st) {
@@ -1169,38 +1175,29 @@ int spd_inverse_persistent(const InvJob* h_jobs, const InvJob* d_jobs, int num_j
 int precondition_small(const PreconJob* d_jobs, int num_jobs, int max_d, cudaStream_t st) {
   if (num_jobs == 0) return 0;
   dim3 grid(ceil_div(max_d, 64), 1, num_jobs);
-  precon_vg_kernel<<<grid, 256, 0, st>>>(d_jobs);
-  ACX_LAUNCH_CHECK();
-  precon_aw_kernel<<<dim3(ceil_div(max_d, 16), 1, num_jobs), 256, 0, st>>>(d_jobs);
-  ACX_LAUNCH_CHECK();
+  ACX_PDL_LAUNCH(precon_vg_kernel, grid, 256, 0, st, d_jobs);
+  ACX_PDL_LAUNCH(precon_aw_kernel, dim3(ceil_div(max_d, 16), 1, num_jobs), 256, 0, st, d_jobs);
   return 0;
 }
 
 int dot_partial(const float* a, const float* b, size_t count, float* partial, int num_partials, cudaStream_t st) {
-  dot_partial_kernel<<<num_partials, 256, 0, st>>>(a, b, count, partial);
-  ACX_LAUNCH_CHECK();
+  ACX_PDL_LAUNCH(dot_partial_kernel, num_partials, 256, 0, st, a, b, count, partial);
   return 0;
 }
 int kfac_step(float* params, float* velocity, const float* precon, size_t count, const float* dot_partials, int num_partials,
               const Sched* sched, float momentum, float norm_constraint, float* out_scalars, cudaStream_t st) {
-  kfac_step_kernel<<<grid_for(count, 256, 148 * 4), 256, 0, st>>>(params, velocity, precon, count, dot_partials, num_partials,
-                                                                 sched, momentum, norm_constraint, out_scalars);
-  ACX_LAUNCH_CHECK();
+  ACX_PDL_LAUNCH(kfac_step_kernel, grid_for(count, 256, 148 * 4), 256, 0, st, params, velocity, precon, count, dot_partials, num_partials, sched, momentum, norm_constraint, out_scalars);
   return 0;
 }
 int momentum_clip_step(float* params, float* accum, const float* grads, size_t count, const float* sq_partials, int num_partials,
                        float lr, float momentum, float clip_norm, float* out_scalars, cudaStream_t st) {
-  momentum_clip_kernel<<<grid_for(count, 256, 148 * 4), 256, 0, st>>>(params, accum, grads, count, sq_partials, num_partials, lr,
-                                                                     momentum, clip_norm, out_scalars);
-  ACX_LAUNCH_CHECK();
+  ACX_PDL_LAUNCH(momentum_clip_kernel, grid_for(count, 256, 148 * 4), 256, 0, st, params, accum, grads, count, sq_partials, num_partials, lr, momentum, clip_norm, out_scalars);
   return 0;
 }
 int rmsprop_clip_step(float* params, float* ms, const float* grads, size_t count, const float* sq_partials, int num_partials,
                       const Sched* sched, float decay, float epsilon, float clip_norm, float* out_scalars, cudaStream_t st,
                       float lr_value) {
-  rmsprop_clip_kernel<<<grid_for(count, 256, 148 * 4), 256, 0, st>>>(params, ms, grads, count, sq_partials, num_partials, sched,
-                                                                    decay, epsilon, clip_norm, out_scalars, lr_value);
-  ACX_LAUNCH_CHECK();
+  ACX_PDL_LAUNCH(rmsprop_clip_kernel, grid_for(count, 256, 148 * 4), 256, 0, st, params, ms, grads, count, sq_partials, num_partials, sched, decay, epsilon, clip_norm, out_scalars, lr_value);
   return 0;
 }
 

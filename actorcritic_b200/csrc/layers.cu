@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(256) im2col_conv1_kernel(const uint8_t* __rest
 // 7.2x and stays in L2.  The columns of a chunk arrive in the order (kw, q, c) instead of (kh, kw, c): see perm64 (gemm.cu).
 // One thread per (sample, pair-row, 4 pixels): two 16-byte loads, four 16-byte stores (64 contiguous bytes).
 __global__ void __launch_bounds__(256) obs_pairs_bf16_kernel(const uint8_t* __restrict__ obs, bf16* __restrict__ out, int samples) {
+  pdl_enter();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)samples * 42 * 21) return;
   const int xq = (int)(i % 21);
@@ -155,6 +156,7 @@ __global__ void __launch_bounds__(256) col2im_mask_split_kernel(const float* __r
 // ------------------------------------------------------------------------------------------------
 __global__ void heads_fwd_kernel(const Planes act4, const float* __restrict__ vpol, const float* __restrict__ vval, int rows,
                                  int num_actions, float* __restrict__ logits, float* __restrict__ values) {
+  pdl_enter();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -239,6 +241,7 @@ __global__ void __launch_bounds__(1024) loss_grad_kernel(const float* __restrict
                                                         const Sched* __restrict__ sched, int n_rows, int num_actions, float beta, float value_weight,
                                                         float policy_weight, float* __restrict__ dheads, float* __restrict__ scalars,
                                                         int want_fisher) {
+  pdl_enter();
   __shared__ float red[3][32];
   const uint64_t step = sched ? sched->gs : 0ull;
   float s_obj = 0.f, s_ent = 0.f, s_val = 0.f;
@@ -329,6 +332,7 @@ __global__ void __launch_bounds__(1024) loss_grad_kernel(const float* __restrict
 __global__ void heads_bwd_data_kernel(const float* __restrict__ dheads, const float* __restrict__ vpol,
                                       const float* __restrict__ vval, const bf16* __restrict__ act4_hi, int rows, int mask_rows,
                                       int num_actions, const Planes out) {
+  pdl_enter();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)rows * 512) return;
   const int j = (int)(i & 511), r = (int)(i >> 9);
@@ -348,6 +352,7 @@ __global__ void heads_bwd_data_kernel(const float* __restrict__ dheads, const fl
 // (j = 512 is the bias row: sum_n dH[n,a]); same for the value head.  One CTA per j, 128 threads over n.
 __global__ void __launch_bounds__(128) heads_wgrad_kernel(const float* __restrict__ dheads, const Planes act4, int n_rows,
                                                           int num_actions, float* __restrict__ gpol, float* __restrict__ gval) {
+  pdl_enter();
   __shared__ float red[4][32];
   const int j = blockIdx.x;  // 0..512
   const int ld = num_actions + 1;
@@ -389,6 +394,7 @@ __global__ void __launch_bounds__(128) heads_wgrad_kernel(const float* __restric
 // (c) output factors of the heads from the FISHER rows: G_pol = dz^T dz / N [A,A], G_val = dv^T dv / N [1,1]
 __global__ void __launch_bounds__(256) heads_gfactor_kernel(const float* __restrict__ dheads_fisher, int n_rows, int num_actions,
                                                             float* __restrict__ g_pol, float* __restrict__ g_val) {
+  pdl_enter();
   __shared__ float red[8];
   const int ld = num_actions + 1;
   const int pair = blockIdx.x;  // 0 .. A*A (last = value)
@@ -432,6 +438,7 @@ __device__ __forceinline__ void add8(float* acc, const uint4 q) {
 // grid (row chunks, column blocks of 2048)
 __global__ void __launch_bounds__(CS_THREADS) colsum_stage1_kernel(const Planes x, int rows, int cols, int rows_per_chunk,
                                                                    float* __restrict__ partial) {
+  pdl_enter();
   extern __shared__ float cs_smem[];   // [lanes_r][cb]
   const int col0 = blockIdx.y * CS_COLBLOCK;
   const int cb = min(CS_COLBLOCK, cols - col0);
@@ -486,6 +493,7 @@ __global__ void __launch_bounds__(CS_THREADS) colsum_stage1_kernel(const Planes 
 // per chunk); one 16-byte vector per thread.  grid (row chunks, ceil(cols / 4096))
 __global__ void __launch_bounds__(256) colsum_u8_kernel(const uint8_t* __restrict__ x, int rows, int cols, int rows_per_chunk,
                                                         float* __restrict__ partial) {
+  pdl_enter();
   const int c0 = (blockIdx.y * 256 + threadIdx.x) * 16;
   if (c0 >= cols) return;
   const int r0 = blockIdx.x * rows_per_chunk;
@@ -511,6 +519,7 @@ __global__ void __launch_bounds__(256) colsum_u8_kernel(const uint8_t* __restric
 // one warp per output element, lanes over the output locations
 __global__ void __launch_bounds__(256) window_sum_kernel(const float* __restrict__ sum_in, int hw_in, int c, int k, int s,
                                                          int hw_out, float scale, float* __restrict__ a, int d) {
+  pdl_enter();
   const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (i >= k * k * c) return;
@@ -536,6 +545,7 @@ template <int LANES>
 __global__ void __launch_bounds__(32 * LANES) colsum_stage2_kernel(const float* __restrict__ partial, int chunks, int cols, float scale,
                                                                    float* __restrict__ out, int out_stride, float* __restrict__ out2,
                                                                    int out2_stride, float* __restrict__ corner) {
+  pdl_enter();
   __shared__ float red[LANES][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -562,12 +572,16 @@ __global__ void __launch_bounds__(32 * LANES) colsum_stage2_kernel(const float* 
   }
 }
 
-static void launch_colsum_stage2(const float* partial, int chunks, int cols, float scale, float* out, int out_stride, float* out2,
-                                 int out2_stride, float* corner, cudaStream_t st) {
-  if (cols <= 128 && chunks >= 64)
-    colsum_stage2_kernel<32><<<ceil_div(cols, 32), dim3(32, 32), 0, st>>>(partial, chunks, cols, scale, out, out_stride, out2, out2_stride, corner);
-  else
-    colsum_stage2_kernel<8><<<ceil_div(cols, 32), dim3(32, 8), 0, st>>>(partial, chunks, cols, scale, out, out_stride, out2, out2_stride, corner);
+static int launch_colsum_stage2(const float* partial, int chunks, int cols, float scale, float* out, int out_stride, float* out2,
+                                int out2_stride, float* corner, cudaStream_t st) {
+  if (cols <= 128 && chunks >= 64) {
+    ACX_PDL_LAUNCH((colsum_stage2_kernel<32>), ceil_div(cols, 32), dim3(32, 32), 0, st, partial, chunks, cols, scale, out, out_stride, out2,
+                   out2_stride, corner);
+  } else {
+    ACX_PDL_LAUNCH((colsum_stage2_kernel<8>), ceil_div(cols, 32), dim3(32, 8), 0, st, partial, chunks, cols, scale, out, out_stride, out2,
+                   out2_stride, corner);
+  }
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -679,6 +693,7 @@ struct WeightPlanesArgs {
   WeightPlanesJob job[4];
 };
 __global__ void weight_planes_kernel(const WeightPlanesArgs a) {
+  pdl_enter();
   const WeightPlanesJob& jb = a.job[blockIdx.z];
   const int k0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   if (k0 >= jb.ld_t || c0 >= jb.c_cols) return;
@@ -717,6 +732,7 @@ __global__ void __launch_bounds__(1024) sample_actions_kernel(const float* __res
                                                              uint64_t seed, uint64_t step, unsigned long long* step_counter,
                                                              int rows, int num_actions, int greedy,
                                                              int32_t* __restrict__ actions) {
+  pdl_enter();
   // one CTA (rows are looped): with a device-resident call counter the Philox step is read from it and advanced here, so
   // a captured CUDA graph of an acting step stays valid from call to call
   if (step_counter) step = *step_counter;
@@ -770,8 +786,7 @@ int im2col_conv1(const uint8_t* obs, bf16* out, int rows_total, cudaStream_t st)
 }
 int obs_pairs_bf16(const uint8_t* obs, bf16* out, int samples, cudaStream_t st) {
   const long long total = (long long)samples * 42 * 21;
-  obs_pairs_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(obs, out, samples);
-  ACX_LAUNCH_CHECK();
+  ACX_PDL_LAUNCH(obs_pairs_bf16_kernel, (unsigned)((total + 255) / 256), 256, 0, st, obs, out, samples);
   return 0;
 }
 int im2col_bf16(const Planes& in, const Planes& out, int rows_total, int hw_in, int c, int k, int s, int hw_out, cudaStream_t st) {
@@ -791,8 +806,7 @@ int col2im_mask_split(const float* dp, const bf16* act_hi, const Planes& out, in
 }
 int heads_fwd(const Planes& act4, const float* vpol, const float* vval, int rows, int num_actions, float* logits, float* values,
               cudaStream_t st) {
-  heads_fwd_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(act4, vpol, vval, rows, num_actions, logits, values);
-  ACX_LAUNCH_CHECK();
+  ACX_PDL_LAUNCH(heads_fwd_kernel, ceil_div(rows, 8), 256, 0, st, act4, vpol, vval, rows, num_actions, logits, values);
   return 0;
 }
 int loss_grad(const float* logits, const float* values, const uint8_t* actions, const float* targets, const int32_t* fl,
@@ -800,24 +814,18 @@ int loss_grad(const float* logits, const float* values, const uint8_t* actions, 
               float* scalars, int want_fisher, cudaStream_t st, float pw) {
   // one row per thread up to 1024 rows (the serial exp / log chains of a row are the kernel's latency)
   const int threads = n_rows >= 1024 ? 1024 : (n_rows + 31) / 32 * 32;
-  loss_grad_kernel<<<1, threads, 0, st>>>(logits, values, actions, targets, fl, fe, seed, sched, n_rows, num_actions, beta, vw,
-                                          pw, dheads, scalars, want_fisher);
-  ACX_LAUNCH_CHECK();
+  ACX_PDL_LAUNCH(loss_grad_kernel, 1, threads, 0, st, logits, values, actions, targets, fl, fe, seed, sched, n_rows, num_actions, beta, vw, pw, dheads, scalars, want_fisher);
   return 0;
 }
 int heads_bwd(const float* dheads, const float* vpol, const float* vval, const Planes& act4, int n_rows, int rows_bwd,
               int num_actions, const Planes& dpre4, float* gpol, float* gval, cudaStream_t st) {
   const long long total = (long long)rows_bwd * 512;
-  heads_bwd_data_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dheads, vpol, vval, act4.p[0], rows_bwd, n_rows,
-                                                                        num_actions, dpre4);
-  ACX_LAUNCH_CHECK();
-  heads_wgrad_kernel<<<513, 128, 0, st>>>(dheads, act4, n_rows, num_actions, gpol, gval);
-  ACX_LAUNCH_CHECK();
+  ACX_PDL_LAUNCH(heads_bwd_data_kernel, (unsigned)((total + 255) / 256), 256, 0, st, dheads, vpol, vval, act4.p[0], rows_bwd, n_rows, num_actions, dpre4);
+  ACX_PDL_LAUNCH(heads_wgrad_kernel, 513, 128, 0, st, dheads, act4, n_rows, num_actions, gpol, gval);
   return 0;
 }
 int heads_gfactor(const float* dheads_fisher, int n_rows, int num_actions, float* g_pol, float* g_val, cudaStream_t st) {
-  heads_gfactor_kernel<<<num_actions * num_actions + 1, 256, 0, st>>>(dheads_fisher, n_rows, num_actions, g_pol, g_val);
-  ACX_LAUNCH_CHECK();
+  ACX_PDL_LAUNCH(heads_gfactor_kernel, num_actions * num_actions + 1, 256, 0, st, dheads_fisher, n_rows, num_actions, g_pol, g_val);
   return 0;
 }
 int colsum(const Planes& x, int rows, int cols, float scale, float* partial, int max_chunks, float* out, int out_stride,
@@ -837,10 +845,8 @@ int colsum(const Planes& x, int rows, int cols, float scale, float* partial, int
     ACX_CUDA(cudaFuncSetAttribute(colsum_stage1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     configured = true;
   }
-  colsum_stage1_kernel<<<dim3(chunks, ceil_div(cols, CS_COLBLOCK)), CS_THREADS, smem, st>>>(x, rows, cols, rpc, partial);
-  ACX_LAUNCH_CHECK();
-  launch_colsum_stage2(partial, chunks, cols, scale, out, out_stride, out2, out2_stride, corner, st);
-  ACX_LAUNCH_CHECK();
+  ACX_PDL_LAUNCH(colsum_stage1_kernel, dim3(chunks, ceil_div(cols, CS_COLBLOCK)), CS_THREADS, smem, st, x, rows, cols, rpc, partial);
+  if (int r2 = launch_colsum_stage2(partial, chunks, cols, scale, out, out_stride, out2, out2_stride, corner, st)) return r2;
   return 0;
 }
 
@@ -859,8 +865,7 @@ int gram_small(const Planes& x, int rows, int c, float scale, float* partial, in
     gram_stage1_kernel<64><<<chunks, 256, 0, st>>>(x, rows, rpc, partial);
   ACX_LAUNCH_CHECK();
   const int parts = chunks * (c == 32 ? 4 : 1);   // C = 32: four row groups per chunk
-  launch_colsum_stage2(partial, parts, c * c, scale, out, 1, nullptr, 0, nullptr, st);
-  ACX_LAUNCH_CHECK();
+  if (int r2 = launch_colsum_stage2(partial, parts, c * c, scale, out, 1, nullptr, 0, nullptr, st)) return r2;
   return 0;
 }
 
@@ -874,18 +879,15 @@ int conv_border(const uint8_t* obs_u8, const Planes* act, int n_rows, int hw_in,
     if (chunks > max_chunks) chunks = max_chunks;
     const int rpc = ceil_div(n_rows, chunks);
     chunks = ceil_div(n_rows, rpc);
-    colsum_u8_kernel<<<dim3(chunks, ceil_div(cols, 4096)), 256, 0, st>>>(obs_u8, n_rows, cols, rpc, partial);
-    ACX_LAUNCH_CHECK();
-    launch_colsum_stage2(partial, chunks, cols, 1.0f, sum_tmp, 1, nullptr, 0, nullptr, st);
-    ACX_LAUNCH_CHECK();
+    ACX_PDL_LAUNCH(colsum_u8_kernel, dim3(chunks, ceil_div(cols, 4096)), 256, 0, st, obs_u8, n_rows, cols, rpc, partial);
+    if (int r2 = launch_colsum_stage2(partial, chunks, cols, 1.0f, sum_tmp, 1, nullptr, 0, nullptr, st)) return r2;
   } else {
     Planes v = *act;
     v.ld = cols;
     int r = colsum(v, n_rows, cols, 1.0f, partial, max_chunks, sum_tmp, 1, st, nullptr, 0, nullptr);
     if (r) return r;
   }
-  window_sum_kernel<<<ceil_div(k * k * c, 8), 256, 0, st>>>(sum_tmp, hw_in, c, k, s, hw_out, scale, a, d);
-  ACX_LAUNCH_CHECK();
+  ACX_PDL_LAUNCH(window_sum_kernel, ceil_div(k * k * c, 8), 256, 0, st, sum_tmp, hw_in, c, k, s, hw_out, scale, a, d);
   return 0;
 }
 
@@ -919,15 +921,13 @@ int weight_planes(const float* const* w, const int* k_rows, const int* c_cols, b
     }
   }
   dim3 grid(ceil_div(max_k, 32), ceil_div(max_c, 32), num_layers);
-  weight_planes_kernel<<<grid, dim3(32, 8), 0, st>>>(a);
-  ACX_LAUNCH_CHECK();
+  ACX_PDL_LAUNCH(weight_planes_kernel, grid, dim3(32, 8), 0, st, a);
   return 0;
 }
 int sample_actions(const float* logits, const float* uniform, uint64_t seed, uint64_t step, int rows, int num_actions, int greedy,
                    int32_t* actions, cudaStream_t st, unsigned long long* step_counter) {
   const int threads = rows >= 1024 ? 1024 : (rows + 31) / 32 * 32;
-  sample_actions_kernel<<<1, threads, 0, st>>>(logits, uniform, seed, step, step_counter, rows, num_actions, greedy, actions);
-  ACX_LAUNCH_CHECK();
+  ACX_PDL_LAUNCH(sample_actions_kernel, 1, threads, 0, st, logits, uniform, seed, step, step_counter, rows, num_actions, greedy, actions);
   return 0;
 }
 

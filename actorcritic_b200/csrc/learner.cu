@@ -131,6 +131,7 @@ struct acx_learner {
   bool conv_tc[4];           // layer computes its input gradient with the gather-form tensor-core kernel (conv.cu)
   bool conv_fwd_tc[4];       // layer runs its forward on the implicit-GEMM kernel (patch matrix built on the aux lane)
   bool conv1_patch;          // conv1's patch matrix P1 is generated inside the GEMMs from the uint8 observations (never stored)
+  int gather_mask;           // bit l: conv layer l reads its patch operand in place (bit 0 = `gather`)
   bool gather;               // no patch matrix is ever stored: the conv GEMMs read their patch operands in place (TMA box loads from
                              // the activations; conv1 from the row-pair interleaved bf16 copy `obs_pairs` of the observations)
   bf16* obs_pairs;           // [R, 42, 84, 2, 4] (layers.cu: obs_pairs_bf16)
@@ -495,7 +496,8 @@ static void register_buffers(acx_learner* l) {
   reg(l, "values", l->values, (size_t)l->R * 4);
   reg(l, "targets", l->targets, (size_t)l->N * 4);
   reg(l, "advantages", l->adv, (size_t)l->N * 4);
-  reg(l, "patches/conv1", l->P1.p[0], (size_t)l->R * 400 * 256 * 2);   // bf16 [R*400, 256], raw byte values
+  reg(l, "patches/conv1", l->P1.p[0], (size_t)l->R * 400 * 256 * 2);   // bf16 [R*400, 256], raw byte values (ACX_GATHER=0 only)
+  reg(l, "obs_pairs", l->obs_pairs, (size_t)l->R * 28224 * 2);         // bf16 [R, 42, 84, 2, 4]: the row-pair copy of the observations
   // hi planes of the forward activations = the ReLU masks the backward pass applies (act > 0); exposed so that the parity
   // tests can tell arithmetic error from units whose pre-activation is within rounding of zero
   reg(l, "act_hi/conv1", l->act1.p[0], (size_t)l->R * 400 * 32 * 2);
@@ -736,14 +738,15 @@ static int conv_input_factor(acx_learner* l, int li, const Planes& patches, cons
   GemmOut o;
   o.c = dst;
   o.ldc = d;
-  if (l->gather) {                   // P^T P read in place from the layer's input (conv1: columns in the row-pair copy's order)
+  const bool gathered = ((l->gather_mask >> li) & 1) != 0;
+  if (gathered) {                    // P^T P read in place from the layer's input (conv1: columns in the row-pair copy's order)
     o.a_gather = &l->gat_x[li];
     o.perm_m = o.perm_n = li == 0 ? 1 : 0;
   } else if (li == 0 && l->conv1_patch) {   // P1^T P1 straight from the uint8 observations
     o.a_patch = obs_u8;
     o.a_patch_samples = l->N;
   }
-  if (l->gather) {
+  if (gathered) {
     Planes x;   // only the plane count matters
     x.n = l->gat_x[li].num_planes;
     x.ld = 8;
@@ -819,7 +822,7 @@ static int forward(acx_learner* l, const uint8_t* obs, int rows, const Lane& ln,
       ACX_TRY(factor(li));
       return run_gemm(l, patches, l->wT[li], 0, rows * L.T, L.C, L.K, l->lvl_fwd, 1.0f, 0, o, ln);
     }
-    if (aux && l->gather) {
+    if (aux && ((l->gather_mask >> li) & 1)) {
       ACX_TRY(factor(li));   // the input factor reads the layer's input in place: nothing to build
     } else if (aux) {
       ACX_TRY(fork_lane(l, st, *aux));
@@ -884,7 +887,7 @@ static int weight_grad(acx_learner* l, int li, const Planes& x, const Planes& g,
   GemmOut o;
   o.c = l->grads + L.off;
   o.ldc = L.C;
-  if (l->gather && li < 3) {   // X^T g with both operands read in place over the same locations
+  if (li < 3 && ((l->gather_mask >> li) & 1)) {   // X^T g with both operands read in place over the same locations
     o.a_gather = &l->gat_x[li];
     o.b_gather = &l->gat_g[li];
     o.perm_m = li == 0 ? 1 : 0;
@@ -1275,7 +1278,11 @@ static void init_dims(acx_learner* l, const acx_learner_config_t* cfg) {
   {
     // ACX_GATHER=0: round 1's materialised patch matrices P1 / P2 / P3 (im2col kernels)
     const char* e = getenv("ACX_GATHER");
-    l->gather = cfg->gemm_impl == 0 && cfg->conv_impl == 0 && (e == nullptr || atoi(e) != 0);
+    // ACX_GATHER = bit mask of the conv layers that read their patch operands in place (default 7 = all; 1 = conv1 only:
+    // conv2 / conv3 then build P2 / P3 with im2col_bf16 on a side lane as in round 1)
+    l->gather_mask = (cfg->gemm_impl == 0 && cfg->conv_impl == 0) ? (e == nullptr ? 7 : (atoi(e) & 7)) : 0;
+    if (l->gather_mask & 6) l->gather_mask |= 1;   // conv1 is the layer that pays most
+    l->gather = (l->gather_mask & 1) != 0;
   }
   // precision: activations / gradients are kept as act_planes bf16 planes; a GEMM of level L accumulates the plane
   // pairs (i, j) with i + j <= L  (1 pair = bf16 inputs, 3 pairs ~ 2^-17, 6 pairs = fp32 class)

@@ -9,6 +9,7 @@ namespace acx {
 __global__ void returns_kernel(const float* __restrict__ rewards, const uint8_t* __restrict__ terminals,
                                const float* __restrict__ values, const float* __restrict__ bootstrap, float gamma,
                                int num_envs, int num_steps, float* __restrict__ targets, float* __restrict__ adv) {
+  pdl_enter();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= num_envs) return;
   float run = bootstrap[e];
@@ -23,9 +24,7 @@ __global__ void returns_kernel(const float* __restrict__ rewards, const uint8_t*
 
 int returns_launch(const float* rewards, const uint8_t* terminals, const float* values, const float* bootstrap,
                    float gamma, int num_envs, int num_steps, float* targets, float* adv, cudaStream_t st) {
-  returns_kernel<<<ceil_div(num_envs, 64), 64, 0, st>>>(rewards, terminals, values, bootstrap, gamma, num_envs, num_steps,
-                                                     targets, adv);
-  ACX_LAUNCH_CHECK();
+  ACX_PDL_LAUNCH(returns_kernel, ceil_div(num_envs, 64), 64, 0, st, rewards, terminals, values, bootstrap, gamma, num_envs, num_steps, targets, adv);
   return 0;
 }
 

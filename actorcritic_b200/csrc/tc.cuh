@@ -1,6 +1,8 @@
 // tc.cuh - sm_100a PTX wrappers shared by the tensor-core kernels (gemm.cu, conv.cu): mbarrier, TMA tile loads,
 // TMEM allocation, tcgen05.mma / commit / ld, shared-memory matrix descriptors.
 #pragma once
+#include <cstring>
+
 #include "common.cuh"
 
 namespace acx {

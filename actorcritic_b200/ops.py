@@ -123,6 +123,22 @@ def gather_view(planes, dim, stride_bytes, gx, gy, samples, chunks):
     return g
 
 
+def nature_cnn_gather(planes, layer, samples):
+    """The in-place patch operand of a Nature-CNN conv layer (csrc/learner.cu:setup_gather): layer "conv1" on the row-pair
+    observation copy [S,42,84,2,4], "conv2" on act1 planes [S,20,20,32], "conv3" on act2 planes [S,9,9,64]."""
+    if layer == "conv2":
+        px = 32 * 2
+        return gather_view(planes, (64, 10, 4, 9, samples), (2 * px, 20 * px, 40 * px, 400 * px), 9, 9, samples,
+                           [(0, h, kh, 0) for kh in range(4) for h in range(2)])
+    if layer == "conv3":
+        px = 64 * 2
+        return gather_view(planes, (64, 9, 1, 9, samples), (px, px, 9 * px, 81 * px), 7, 7, samples,
+                           [(0, kw, 0, kh) for kh in range(3) for kw in range(3)])
+    prow = 84 * 8 * 2
+    return gather_view(planes, (64, 20, 4, 20, samples), (64, prow, 2 * prow, 42 * prow), 20, 20, samples,
+                       [(0, 0, j, 0) for j in range(4)])
+
+
 def obs_pairs(obs):
     """uint8 [S, 84, 84, 4] -> the row-pair interleaved bf16 copy [S, 42, 84, 2, 4] (acx_obs_pairs_bf16)."""
     assert obs.dtype == torch.uint8 and obs.is_contiguous() and tuple(obs.shape[1:]) == (84, 84, 4)

@@ -349,19 +349,21 @@ def run_native(args, rank, world, local_rank):
     stage_ms["inverse_per_refresh"] = float(np.sum(stage_sum["inverse"]) / max(1, sum(1 for x in stage_sum["inverse"] if x > 0.01)))
     flops = algorithmic_flops(n, envs, c3)
 
-    # dominant kernel, timed alone and live: the largest single launch of the update = the conv1 input-factor SYRK
-    # A1 = P1^T P1 (gemm_tc_kernel<1>, 256 x 256 output, K = N*400 patch rows, MN-major operands read once, symmetric
-    # tiles only, split-K over the SMs) on the engine's own patch matrix of the last update (131 MB > L2: every launch
-    # streams it from HBM).  Events are recorded by the library around the kernel itself on the launching stream.
+    # conv1 input factor A1 = P1^T P1 (gemm_tc_kernel<1>, SYRK panel mode, 256 x 256 output, K = N*400 patch rows), timed alone
+    # and live as the update runs it: the patch operand is read in place (acx_gather_t) from the engine's row-pair bf16 copy
+    # of the last update's observations (36 MB: L2 resident), results stored back in (kh, kw, c) order.  Events are recorded by
+    # the library around the kernel itself on the launching stream.
     from actorcritic_b200 import ops
     lib = _lib.load()
     k_rows = n * 400
-    p1 = e.buffer("patches/conv1", torch.bfloat16).view(-1, 256)[:k_rows]
+    pairs_copy = e.buffer("obs_pairs", torch.bfloat16)
+    ga1 = ops.nature_cnn_gather([pairs_copy], "conv1", n)
     lib.acx_gemm_enable_timing(1)
     durs = []
     with torch.cuda.stream(e.stream):
         for i in range(13):
-            ops.gemm([p1], [p1], 256, 256, k_rows, trans=True, symmetric=True, pairs=[(0, 0)], alpha=1.0 / (255.0 * 255.0 * k_rows))
+            ops.gemm([pairs_copy], [pairs_copy], 256, 256, k_rows, trans=True, symmetric=True, pairs=[(0, 0)],
+                     alpha=1.0 / (255.0 * 255.0 * k_rows), a_gather=ga1, perm_m=1, perm_n=1)
             ms = ctypes.c_float(0)
             _lib.check(lib.acx_gemm_last_ms(ctypes.byref(ms)))
             if i >= 3:
@@ -370,6 +372,24 @@ def run_native(args, rank, world, local_rank):
     syrk_ms = float(np.mean(durs))
     syrk_flops = float(k_rows) * 256 * 257          # rows * d * (d + 1), symmetric half
     syrk_tflops = syrk_flops / (syrk_ms * 1e-3) / 1e12
+    # the largest HBM-bound launch of the update: the row-pair copy itself (obs_pairs_bf16_kernel: uint8 observations read
+    # once, bf16 copy written once = 3 bytes per observation byte), timed with CUDA events over the 8 resident batches
+    # (152 MB > L2, so every launch reads its observations from HBM)
+    obs_all = [torch.cat([b["observations"].reshape(-1, 84, 84, 4), b["bootstrap_observations"].reshape(-1, 84, 84, 4)]) for b in resident]
+    pc_out = torch.empty((obs_all[0].shape[0], 42, 84, 2, 4), dtype=torch.bfloat16, device=dev)
+    with torch.cuda.stream(e.stream):
+        sp = ctypes.c_void_p(e.stream.cuda_stream)
+        for ob in obs_all[:3]:
+            _lib.check(lib.acx_obs_pairs_bf16(ob.data_ptr(), pc_out.data_ptr(), ob.shape[0], sp))
+        p0, p1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(e.stream)
+        for ob in obs_all:
+            _lib.check(lib.acx_obs_pairs_bf16(ob.data_ptr(), pc_out.data_ptr(), ob.shape[0], sp))
+        p1e.record(e.stream)
+    torch.cuda.synchronize()
+    pairs_ms = p0.elapsed_time(p1e) / len(obs_all)
+    pairs_bytes = 3 * obs_all[0].numel()
+    del obs_all, pc_out
 
     # dominant launch of the update since the gather-form input gradient replaced dgrad GEMM + col2im: conv_tc_kernel on
     # conv3 / conv2 (true + Fisher rows = 2N samples), each timed alone with CUDA events on the launching stream on
@@ -468,13 +488,14 @@ def run_native(args, rank, world, local_rank):
     try:
         rows2 = n * 81
         gen = torch.Generator(device=dev).manual_seed(11)
-        x2 = ops.split_planes(torch.rand((rows2, 512), device=dev, generator=gen), 2)
+        x2 = ops.split_planes(torch.rand((n * 400, 32), device=dev, generator=gen), 2)    # act1-shaped planes [N, 20, 20, 32]
+        ga2 = ops.nature_cnn_gather(x2, "conv2", n)
         torch.cuda.synchronize()
         lib.acx_gemm_enable_timing(1)
         d2 = []
         with torch.cuda.stream(e.stream):
             for i in range(9):
-                ops.gemm(x2, x2, 512, 512, rows2, trans=True, symmetric=True, pairs=ops.PAIRS[3], alpha=1.0 / rows2)
+                ops.gemm(x2, x2, 512, 512, rows2, trans=True, symmetric=True, pairs=ops.PAIRS[3], alpha=1.0 / rows2, a_gather=ga2)
                 ms = ctypes.c_float(0)
                 _lib.check(lib.acx_gemm_last_ms(ctypes.byref(ms)))
                 if i >= 3:
@@ -483,17 +504,20 @@ def run_native(args, rank, world, local_rank):
         ms2 = float(np.mean(d2))
         alg = float(rows2) * 512 * 513                       # rows * d * (d + 1): the symmetric half
         issued = 3.0 * 10 * 2.0 * rows2 * 128 * 128           # 3 plane pairs x 10 upper 128-tiles of the 4 x 4 tile grid
-        factor_syrk = {"kernel": "gemm_tc_kernel<1>: conv2 input factor A2 = P2^T P2 (512 x 512, K = %d patch rows, 3 plane pairs, "
-                                 "upper tiles, split-K; the split-K finalize is a separate launch)" % rows2,
+        factor_syrk = {"kernel": "gemm_tc_kernel<1>: conv2 input factor A2 = P2^T P2 (512 x 512, K = %d patch rows read in place from the "
+                                 "act1 planes by 5-D TMA box loads - no patch matrix -, 3 plane pairs, upper tiles, split-K; the split-K "
+                                 "finalize is a separate launch)" % rows2,
                        "bound": "tensor", "launch_ms": ms2, "algorithmic_gflop_per_launch": alg / 1e9,
                        "achieved": alg / (ms2 * 1e-3) / 1e12, "peak": peaks["tensor_burst"], "unit": "TFLOP/s",
                        "frac": alg / (ms2 * 1e-3) / 1e12 / peaks["tensor_burst"],
                        "issued_gflop_per_launch": issued / 1e9, "issued_frac": issued / (ms2 * 1e-3) / 1e12 / peaks["tensor_burst"],
-                       # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full, profiles/r2_prof_syrk_conv2_raw.txt;
-                       # algorithmic: 2 planes x rows x 512 x 2 B read once = 106 MB)
-                       "traffic": ncu_traffic("r2_prof_syrk_conv2_raw.txt"),
-                       "ncu": "profiles/r2_prof_syrk_conv2_details.txt: tensor pipe active 57.6 % of cycles, shared-memory "
-                              "operand wavefronts 45.6 % of peak, DRAM 27 %"}
+                       # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full, profiles/r2_prof_syrk_conv2_gather_raw.txt;
+                       # algorithmic: the two act1 planes read once = 2 x N x 20 x 20 x 32 x 2 B = 33 MB)
+                       "traffic": ncu_traffic("r2_prof_syrk_conv2_gather_raw.txt"),
+                       "algorithmic_bytes_per_launch": 2 * n * 400 * 32 * 2,
+                       "ncu": "profiles/r2_prof_syrk_conv2_gather_details.txt (this kernel); the same product on a materialised patch "
+                              "matrix: profiles/r2_prof_syrk_conv2_details.txt (tensor pipe active 57.6 % of cycles, shared-memory "
+                              "operand wavefronts 45.6 % of peak, DRAM 27 %)"}
         del x2
     except Exception as exc:  # noqa: BLE001
         factor_syrk = {"error": repr(exc)}
@@ -507,14 +531,16 @@ def run_native(args, rank, world, local_rank):
     # `roofline` = the dominant (longest) launch of the update; `hbm_kernel` inside it = the largest HBM-bound launch
     hbm_kernel = {
         "bound": "hbm",
-        "kernel": "gemm_tc_kernel<1> (SYRK panel mode): conv1 input factor A1 = P1^T P1, 256x256 output, "
-                  "K=%d patch rows - the largest HBM-bound launch" % k_rows,
-        "achieved": k_rows * 256 * 2 / (syrk_ms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
-        "frac": k_rows * 256 * 2 / (syrk_ms * 1e-3) / 1e9 / peaks["hbm"],
-        "traffic": 135727104,   # profiles/r1_prof_syrk_conv1_panel_details.txt
-        "algorithmic_bytes_per_launch": k_rows * 256 * 2, "launch_ms": syrk_ms,
-        "tensor": {"algorithmic_gflop_per_launch": syrk_flops / 1e9, "achieved_tflops": syrk_tflops,
-                   "frac_of_burst_bf16_peak": syrk_tflops / peaks["tensor_burst"]}}
+        "kernel": "obs_pairs_bf16_kernel: uint8 observations [%d, 84, 84, 4] -> row-pair interleaved bf16 copy (what replaced the "
+                  "conv1 patch matrix) - the largest HBM-bound launch of the update" % (n + envs),
+        "achieved": pairs_bytes / (pairs_ms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+        "frac": pairs_bytes / (pairs_ms * 1e-3) / 1e9 / peaks["hbm"],
+        "traffic": None, "algorithmic_bytes_per_launch": pairs_bytes, "launch_ms": pairs_ms,
+        "conv1_factor_syrk": {"kernel": "gemm_tc_kernel<1> (SYRK panel mode): conv1 input factor A1 = P1^T P1, 256 x 256 output, K = %d patch "
+                                        "rows read in place from the row-pair copy" % k_rows,
+                              "launch_ms": syrk_ms, "algorithmic_gflop_per_launch": syrk_flops / 1e9, "achieved_tflops": syrk_tflops,
+                              "frac_of_burst_bf16_peak": syrk_tflops / peaks["tensor_burst"],
+                              "round1": "on the materialised patch matrix (131 MB from HBM): 39 us"}}
     # the whole update against the tensor roofline: algorithmic GFLOP (symmetric-half counting) over the
     # device-timed step; inside a long loop the sustained peak is the relevant denominator
     per_gpu_gflop = update_gflop(c3) * n / 640.0 if update_gflop(c3) else None
@@ -524,8 +550,8 @@ def run_native(args, rank, world, local_rank):
         update_block = {"bound": "tensor", "algorithmic_gflop_per_update_per_gpu": per_gpu_gflop, "ms_per_step": ms_step,
                         "achieved": ach, "unit": "TFLOP/s", "peak": peaks["tensor_sustained"], "frac": ach / peaks["tensor_sustained"],
                         "frac_of_burst": ach / peaks["tensor_burst"],
-                        "note": "every launch of the update (78 at 32 x 20: 22 tensor-core kernels, HBM- and latency-bound helpers, "
-                                "the inverse refresh amortised over 10 updates) against the dense bf16 peak"}
+                        "note": "every launch of the update (%d per update at this size: 22 tensor-core kernels, HBM- and latency-bound "
+                                "helpers, the inverse refresh amortised over 10 updates) against the dense bf16 peak" % round(launches / max(1, args.steps))}
     if dom is None:   # im2col route / unsupported conv3 width: the largest launch is the HBM-bound conv1 factor SYRK
         roofline = dict(hbm_kernel, stage_ms=stage_ms, update=update_block)
     else:
@@ -582,10 +608,13 @@ def run_native(args, rank, world, local_rank):
         "env_frames_per_sec": total_envs * t_count * FRAMESKIP / ((ms_step + rollout_ms) * 1e-3),
         "env_frames_per_sec_learner_only": value * FRAMESKIP,
         "config": make_config(args, world),
-        "engine": {"precision": args.precision, "cuda_graphs": not args.no_graphs, "lanes": args.lanes if args.lanes > 0 else 3,
+        "engine": {"precision": args.precision, "cuda_graphs": not args.no_graphs, "lanes": args.lanes if args.lanes > 0 else 5,
+                   "patches": "never stored: conv input factors / weight gradients read their patch operands in place (5-D TMA box loads from "
+                              "the activations; conv1 from a row-pair interleaved bf16 copy of the observations)"
+                              if os.environ.get("ACX_GATHER", "1") != "0" else "materialised P1 / P2 / P3 (ACX_GATHER=0)",
                    "conv": "conv2/conv3 input gradient in gather form on the tensor cores (no patch-gradient matrix, no col2im)" if args.conv_impl == 0 else "dgrad GEMM + col2im",
                    "inverse": "fp32 blocked Gauss-Jordan, all factor tiles resident in shared memory, one persistent kernel (kfac_inv.cu)",
-                   "l2": "8 resident input batches rotated (152 MB > 126 MB L2); per-step intermediates ~0.9 GB, self-flushing"},
+                   "l2": "8 resident input batches rotated (152 MB > 126 MB L2); per-step intermediates ~0.4 GB"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 64,
                 "ms_per_step": ms_e2e / args.steps,
                 "note": "Engine.stage_batch + Engine.update(staged=True, fetch='async'): pinned host -> staging slot on a copy stream "
@@ -593,8 +622,6 @@ def run_native(args, rank, world, local_rank):
                         "step i's numbers after enqueuing step i+1; all reads complete inside the timed region"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        # the kernel's arithmetic intensity is 16.8 GFLOP / 131 MB = 128 FLOP/B, below the machine balance
-        # (1665 TFLOP/s / 6.56 TB/s = 254 FLOP/B): it is bound by streaming the patch matrix from HBM once
         "roofline": roofline,
         "preprocess": pre,
         "rollout": {"ms_per_%d_steps" % t_count: rollout_ms, "env_steps_per_sec": envs * t_count / (rollout_ms * 1e-3),

@@ -14,6 +14,22 @@ SHAPES = {  # name: (m, n, k, trans, sym, planes, out_planes)
     "fc4": (672, 512, 1568, False, False, 3, 3),
 }
 name = sys.argv[1]
+if name == "syrk_conv2_gather":   # the default path: A2 = P2^T P2 read in place from act1 planes [640, 20, 20, 32] (acx_gather_t)
+    import ctypes
+    from actorcritic_b200 import _lib
+    lib = _lib.load()
+    iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    xp = ops.split_planes(torch.rand((640 * 400, 32), device="cuda"), 2)
+    ga = ops.nature_cnn_gather(xp, "conv2", 640)
+    lib.acx_gemm_enable_timing(1)
+    durs = []
+    for _ in range(max(iters, 5)):
+        ops.gemm(xp, xp, 512, 512, 51840, trans=True, symmetric=True, pairs=ops.PAIRS[3], alpha=1.0 / 51840, a_gather=ga)
+        ms = ctypes.c_float(0)
+        _lib.check(lib.acx_gemm_last_ms(ctypes.byref(ms)))
+        durs.append(ms.value)
+    print(name, "kernel-only us (library events):", " ".join("%.1f" % (1e3 * d) for d in durs))
+    sys.exit(0)
 patch = name.endswith("_patch")
 if patch:
     name = name[:-6]
@@ -46,7 +62,7 @@ for _ in range(max(iters, 5)):
 lib.acx_gemm_enable_timing(0)
 print(name, "kernel-only us (library events):", " ".join("%.1f" % (1e3 * d) for d in durs))
 if os.environ.get("ACX_GEMM_TRACE"):
-    arr = (ctypes.c_longlong * 4)()
+    arr = (ctypes.c_longlong * 12)()
     lib.acx_debug_gemm_trace(arr)
     t = list(arr)
     print("  CTA 0 MMA warp: %d cycles, %d k-blocks (%.0f cycles each); waiting for operands %.0f%%, for an accumulator %.0f%%"
