@@ -332,30 +332,57 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
         const uint32_t tx = p.panel ? (patch ? 0u : (uint32_t)(p.npa * nch * bk * 128))
                                     : (MAJOR == 0 ? (uint32_t)(stage_bytes - (patch ? p.npa * a_tile_bytes : 0))
                                                   : (uint32_t)(((patch ? 0 : p.npa * na) + (diag ? 0 : p.npb * nb)) * bk * 128));
+        // gathered operands: the chunk coordinates of this work item's (up to 4) A and (up to 2) B chunks are fixed - read them
+        // from the parameters once, not per load (the issuing thread is alone: dependent parameter loads with run-time indices
+        // cost it hundreds of cycles per k-block)
+        int ac[4][4] = {}, bc[4][2] = {};
+        if (MAJOR == 1 && p.gather_a) {
+          const int qa = p.panel ? 0 : (m0 >> 6), qb = n0 >> 6;
+#pragma unroll
+          for (int d = 0; d < 4; ++d) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ac[d][j] = p.ga[d][min(qa + j, 15)];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) bc[d][j] = p.gb[d][min(qb + j, 15)];
+          }
+        }
+        // ... and the box position advances incrementally (cell inside the sample group, then the next group)
+        int g_cell = 0, g_grp = 0, g_cx = 0, g_cy = 0;
+        if (MAJOR == 1 && p.gather_a) {
+          g_grp = kb0 / p.g_cells;
+          g_cell = kb0 - g_grp * p.g_cells;
+          g_cy = g_cell / p.g_nx;
+          g_cx = g_cell - g_cy * p.g_nx;
+        }
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+          // gathered operands: where the 64 locations of this k-block sit in the (x, y, sample) space
+          const int gx0 = g_cx * p.g_bx, gy0 = g_cy * p.g_by, gn0 = g_grp * p.g_ts;
+          if (MAJOR == 1 && p.gather_a) {
+            if (++g_cx == p.g_nx) {
+              g_cx = 0;
+              ++g_cy;
+            }
+            if (++g_cell == p.g_cells) {
+              g_cell = g_cx = g_cy = 0;
+              ++g_grp;
+            }
+          }
           mbar_wait(&empty_bar[s], ph ^ 1u, 1);
           __syncwarp();
           if (!elect_one()) continue;
           mbar_expect_tx(&full_bar[s], tx);
           uint8_t* a_s = smem + s * stage_bytes;
-          // gathered operands: where the 64 locations of this k-block sit in the (x, y, sample) space
-          int gx0 = 0, gy0 = 0, gn0 = 0;
-          if (MAJOR == 1 && (p.gather_a | p.gather_b)) {
-            const int grp = kb / p.g_cells, cell = kb - grp * p.g_cells;
-            const int cy = cell / p.g_nx;
-            gx0 = (cell - cy * p.g_nx) * p.g_bx;
-            gy0 = cy * p.g_by;
-            gn0 = grp * p.g_ts;
-          }
           if (p.panel) {
             for (int i = 0; i < p.npa && !patch; ++i) {
               const CUtensorMap* ma = i == 0 ? &ta0 : (i == 1 ? &ta1 : &ta2);
-              for (int j = 0; j < nch; ++j) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {   // (a panel is at most 256 columns = 4 chunks)
+                if (j >= nch) break;
                 uint8_t* dst = a_s + i * panel_tile_bytes + j * (bk * 128);
                 if (MAJOR == 1 && p.gather_a)
-                  tma_load_5d(dst, ma, &full_bar[s], p.ga[0][j], gx0 + p.ga[1][j], p.ga[2][j], gy0 + p.ga[3][j], gn0);
+                  tma_load_5d(dst, ma, &full_bar[s], ac[0][j], gx0 + ac[1][j], ac[2][j], gy0 + ac[3][j], gn0);
                 else
                   tma_load_2d(dst, ma, &full_bar[s], 64 * j, kb * bk);
               }
@@ -369,10 +396,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
             if (MAJOR == 0) {
               tma_load_2d(dst, ma, &full_bar[s], kb * bk, m0);
             } else if (p.gather_a) {
-              for (int j = 0; j < na; ++j) {
-                const int q = (m0 >> 6) + j;
-                tma_load_5d(dst + j * (bk * 128), ma, &full_bar[s], p.ga[0][q], gx0 + p.ga[1][q], p.ga[2][q], gy0 + p.ga[3][q], gn0);
-              }
+#pragma unroll
+              for (int j = 0; j < 2; ++j)
+                if (j < na) tma_load_5d(dst + j * (bk * 128), ma, &full_bar[s], ac[0][j], gx0 + ac[1][j], ac[2][j], gy0 + ac[3][j], gn0);
             } else {
               for (int j = 0; j < na; ++j) tma_load_2d(dst + j * (bk * 128), ma, &full_bar[s], m0 + 64 * j, kb * bk);
             }
@@ -383,10 +409,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
             if (MAJOR == 0) {
               tma_load_2d(dst, mb, &full_bar[s], kb * bk, n0);
             } else if (p.gather_b) {
-              for (int j = 0; j < nb; ++j) {
-                const int q = (n0 >> 6) + j;
-                tma_load_5d(dst + j * (bk * 128), mb, &full_bar[s], p.gb[0][q], gx0 + p.gb[1][q], p.gb[2][q], gy0 + p.gb[3][q], gn0);
-              }
+#pragma unroll
+              for (int j = 0; j < 2; ++j)
+                if (j < nb) tma_load_5d(dst + j * (bk * 128), mb, &full_bar[s], bc[0][j], gx0 + bc[1][j], bc[2][j], gy0 + bc[3][j], gn0);
             } else {
               for (int j = 0; j < nb; ++j) tma_load_2d(dst + j * (bk * 128), mb, &full_bar[s], n0 + 64 * j, kb * bk);
             }

@@ -1,0 +1,4 @@
+cd /root/repo
+python -m pytest tests/test_gpu_gemm.py tests/test_gpu_gather_gemm.py tests/test_gpu_learner.py -x -q -m gpu 2>&1 | tail -3
+python tools/gather_probe.py 2>&1 | tail -6
+for i in 1 2; do python tools/update_time.py 300; done
