@@ -61,6 +61,7 @@ __device__ __forceinline__ void pdl_enter() {
   pdl_trigger();
   pdl_wait();
 }
+void set_pdl_override(int level);   // >= 0: the level of the following launches (the acting step: one serial chain); -1: back to ACX_PDL
 int pdl_level();   // ACX_PDL: 0 = off, 1 = tensor-core kernels and their finalize kernels, 2 = also the small kernels
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_pdl_at(int level, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

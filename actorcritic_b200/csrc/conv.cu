@@ -557,6 +557,7 @@ static int launch_conv(const CUtensorMap* ta, const CUtensorMap* tb, ConvTcParam
   if (g_cta_cap > 0 && grid > g_cta_cap) grid = g_cta_cap;
   const int smem = CV_SMEM_FIXED + p.stages * stage_bytes;
   ACX_CUDA(launch_pdl(conv_tc_kernel, dim3(grid), dim3(CV_THREADS), (size_t)smem, st, ta[0], ta[1], ta[2], tb[0], tb[1], tb[2], p));
+  acx::count_launch();
   return 0;
 }
 

@@ -1407,19 +1407,22 @@ static int launch_tc(const CUtensorMap* ta, const CUtensorMap* tb, const TcParam
   if (g_probe_on) ACX_CUDA(cudaEventRecord(g_probe_ev[0], st));
   ACX_CUDA(launch_pdl(gemm_tc_kernel<MAJOR, PATCH>, dim3(grid), dim3(GEMM_THREADS + (PATCH ? PATCH_THREADS : 0)), (size_t)smem, st, ta[0], ta[1],
                       ta[2], tb[0], tb[1], tb[2], p));
+    acx::count_launch();
   if (g_probe_on) ACX_CUDA(cudaEventRecord(g_probe_ev[1], st));
   return 0;
 }
 
 // triage knob (ACX_MAIN_CTAS / ACX_SIDE_CTAS, learner.cu): cap on the persistent grid of the next tensor-core launches, so
 // that kernels of different lanes can share the SMs instead of queueing behind each other (0 = all SMs)
+static int g_pdl_override = -1;
+void set_pdl_override(int level) { g_pdl_override = level; }
 int pdl_level() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("ACX_PDL");
     v = e ? atoi(e) : 1;
   }
-  return v;
+  return (v > 0 && g_pdl_override >= 0) ? g_pdl_override : v;
 }
 
 int g_cta_cap = 0;
@@ -1598,17 +1601,20 @@ static int gemm_tc(const acx_gemm_t* g, cudaStream_t st) {
     const int zl = pl.splits >= 64 ? 4 : (pl.splits >= 24 ? 2 : 1);   // split lanes per element
     ACX_CUDA(launch_pdl(gemm_finalize_sym_kernel, dim3(nblk * (nblk + 1) / 2, 4), dim3(256, zl), 0, st, p.out, (const float*)p.ws, p.ws_ld,
                         p.ws_split_stride, pl.splits, nblk));
+    acx::count_launch();
   } else if (pl.to_ws && !g->symmetric && pl.splits <= 16 && finalize_vec4_ok(p.out, p.ws_ld, p.ws_split_stride)) {
     // (deep split-K of a small result - the conv wgrads - keeps the kernel whose thread lanes share the splits: measured
     // 5.4 vs 14.1 us at 146 splits of a 256 x 32 result)
     const long long quads = (long long)g->m * ((g->n + 3) >> 2);
     ACX_CUDA(launch_pdl(gemm_finalize_vec4_kernel, dim3((unsigned)((quads + 255) / 256)), dim3(256), 0, st, p.out, (const float*)p.ws, p.ws_ld,
                         p.ws_split_stride, pl.splits));
+    acx::count_launch();
   } else if (pl.to_ws) {
     const int lanes = pl.splits >= 8 ? 8 : (pl.splits >= 4 ? 4 : (pl.splits >= 2 ? 2 : 1));
     dim3 fg(ceil_div(g->n, 256 / lanes), g->m);
     ACX_CUDA(launch_pdl(gemm_finalize_kernel, fg, dim3(256 / lanes, lanes), 0, st, p.out, (const float*)p.ws, p.ws_ld, p.ws_split_stride,
                         pl.splits, g->symmetric, BM, pl.bn));
+    acx::count_launch();
   }
   return 0;
 }

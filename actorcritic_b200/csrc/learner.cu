@@ -1636,6 +1636,15 @@ int acx_learner_get_state(const acx_learner_t* l, int64_t* global_step, int64_t*
   return 0;
 }
 
+static int act_pdl_level() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ACX_ACT_PDL");
+    v = e ? atoi(e) : 2;
+  }
+  return v;
+}
+
 int acx_learner_act(acx_learner_t* l, const uint8_t* d_obs, int rows, const float* d_uniform, int greedy, int32_t* d_actions,
                     float* d_logits, float* d_values, void* stream) {
   ACX_CHECK(l && d_obs && d_actions, "null argument");
@@ -1645,9 +1654,13 @@ int acx_learner_act(acx_learner_t* l, const uint8_t* d_obs, int rows, const floa
   // (the usual rollout loop: the environment's stack buffer in, the agent's action buffer out) the step is captured once
   // per pointer set and replayed as ONE graph launch; the call counter that seeds Philox lives on the device.
   auto issue = [&]() -> int {
+    // the acting step is ONE serial chain of small launches on one stream: every kernel lets its successor be scheduled at
+    // once (programmatic dependent launch, level 2) - inside an update the same setting gains nothing because the early
+    // blocks compete with the other lanes
+    set_pdl_override(act_pdl_level());
     int r = forward(l, d_obs, rows, lane_of(l, 0, st), nullptr, nullptr, false);
-    if (r) return r;
-    r = sample_actions(l->logits, d_uniform, l->cfg.seed, 0, rows, l->A, greedy, d_actions, st, l->act_counter);
+    if (r == 0) r = sample_actions(l->logits, d_uniform, l->cfg.seed, 0, rows, l->A, greedy, d_actions, st, l->act_counter);
+    set_pdl_override(-1);
     if (r) return r;
     if (d_logits)
       ACX_CUDA(cudaMemcpyAsync(d_logits, l->logits, (size_t)rows * l->A * sizeof(float), cudaMemcpyDeviceToDevice, st));

@@ -225,6 +225,7 @@ __global__ void __launch_bounds__(KPRE_THREADS, 4) preprocess_kernel(const uint8
                                                                      const uint8_t* __restrict__ reset_raw,
                                                                      const uint8_t* stack_in, uint8_t* stack_out,
                                                                      size_t out_env_stride, int num_envs) {
+  pdl_enter();   // in a rollout graph this kernel follows the previous step's sampling kernel on the same stream
   __shared__ __align__(16) uint8_t s_gray[BAND_SRC * RAW_W];   // 4800 B
 
   const int env = blockIdx.x / NUM_BANDS;
@@ -444,8 +445,8 @@ static int launch_kpre(const uint8_t* raw_a, const uint8_t* raw_b, const uint8_t
     preprocess_persistent_kernel<RESET><<<grid, KPRE_THREADS, KPRE_P_SMEM, st>>>(
         raw_a, raw_b, terminal, reset_mask, reset_raw, stack_in, stack_out, out_env_stride, items);
   } else {
-    preprocess_kernel<RESET><<<items, KPRE_THREADS, 0, st>>>(raw_a, raw_b, terminal, reset_mask, reset_raw, stack_in,
-                                                            stack_out, out_env_stride, num_envs);
+    ACX_CUDA(launch_pdl(preprocess_kernel<RESET>, dim3(items), dim3(KPRE_THREADS), 0, st, raw_a, raw_b, terminal, reset_mask, reset_raw,
+                        stack_in, stack_out, out_env_stride, num_envs));
   }
   ACX_LAUNCH_CHECK();
   return 0;
