@@ -111,6 +111,12 @@ SIGNATURES = {
     "acx_learner_wait_input_factors": (ctypes.c_int, [_P, _P]),
     "acx_learner_update_plan": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "acx_learner_set_external_ema": (ctypes.c_int, [_P, ctypes.c_int]),
+    "acx_peer_export": (ctypes.c_int, [_P, _P, ctypes.POINTER(ctypes.c_ulonglong)]),
+    "acx_peer_import": (ctypes.c_void_p, [_P, ctypes.c_ulonglong]),
+    "acx_learner_set_peers": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+    "acx_learner_wait_reduced": (ctypes.c_int, [_P, _P]),
+    "acx_learner_peer_reduce_prefix": (ctypes.c_int, [_P, _P]),
+    "acx_peer_error": (ctypes.c_int, []),
     "acx_learner_ema": (ctypes.c_int, [_P, _P]),
     "acx_learner_defer_input_factors": (ctypes.c_int, [_P, ctypes.c_int]),
     "acx_learner_set_profiling": (ctypes.c_int, [_P, ctypes.c_int]),

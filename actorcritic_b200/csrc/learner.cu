@@ -24,6 +24,16 @@
 
 namespace acx {
 
+// peer.cu: the data-parallel exchange as one kernel over NVLink peer memory
+struct PeerState {
+  int rank = 0, world = 0;
+  uint8_t* base[8] = {};   // arena base of every rank as mapped into this process
+};
+int peer_allreduce(const PeerState& ps, size_t region_offset_bytes, size_t flags_offset_bytes, size_t epochs_offset_bytes,
+                   long long count, long long scale_from, float scale, int channel, cudaStream_t st);
+size_t peer_flag_bytes();
+size_t peer_epoch_bytes();
+
 struct Layer {
   const char* name;
   int K, C;         // V_l = [K+1, C]
@@ -131,6 +141,11 @@ struct acx_learner {
   bool conv_tc[4];           // layer computes its input gradient with the gather-form tensor-core kernel (conv.cu)
   bool conv_fwd_tc[4];       // layer runs its forward on the implicit-GEMM kernel (patch matrix built on the aux lane)
   bool conv1_patch;          // conv1's patch matrix P1 is generated inside the GEMMs from the uint8 observations (never stored)
+  PeerState peer;            // world > 1: phase 2 sums the ranks' buckets itself (peer.cu) - the caller issues no collective for them
+  uint8_t* arena_base = nullptr;
+  unsigned int* peer_flags = nullptr;
+  unsigned int* peer_epochs = nullptr;
+  cudaEvent_t reduced = nullptr;   // [G | grads | scalars] of this update are summed over the ranks (external event, split exchange)
   int gather_mask;           // bit l: conv layer l reads its patch operand in place (bit 0 = `gather`)
   bool gather;               // no patch matrix is ever stored: the conv GEMMs read their patch operands in place (TMA box loads from
                              // the activations; conv1 from the row-pair interleaved bf16 copy `obs_pairs` of the observations)
@@ -277,6 +292,8 @@ static size_t layout(acx_learner* l, uint8_t* base) {
   l->lambdas = f32(8);
   l->scalars = f32(16);
   l->sched = reinterpret_cast<Sched*>(ar.take(sizeof(Sched)));
+  l->peer_flags = reinterpret_cast<unsigned int*>(ar.take(peer_flag_bytes()));
+  l->peer_epochs = reinterpret_cast<unsigned int*>(ar.take(peer_epoch_bytes()));
   l->d_a_ptrs = reinterpret_cast<const float**>(ar.take(6 * sizeof(float*)));
   l->d_g_ptrs = reinterpret_cast<const float**>(ar.take(6 * sizeof(float*)));
   l->d_a_dims = reinterpret_cast<int*>(ar.take(6 * sizeof(int)));
@@ -1123,7 +1140,25 @@ static int issue_phase2(acx_learner* l, const Plan2& p, cudaStream_t st) {
   Lane ema_ln = lane_of(l, 0, st);
   mark(l, 5, st);
   const bool ext_ema = l->external_ema && !p.a2c && !p.cold;   // the caller runs acx_learner_ema on its own stream
-  if (c.world_size > 1) {
+  if (c.world_size > 1 && l->peer.world > 1) {
+    // the exchange itself, over NVLink peer memory, fused with the 1 / world_size scaling (peer.cu): with an external EMA only
+    // what this phase reads travels here - [G | grads | scalars], G left unscaled for acx_learner_ema - and `reduced` tells
+    // the caller's EMA stream when it is complete; otherwise the whole bucket
+    const size_t flags_off = reinterpret_cast<uint8_t*>(l->peer_flags) - l->arena_base;
+    const size_t epochs_off = reinterpret_cast<uint8_t*>(l->peer_epochs) - l->arena_base;
+    const float inv_world = 1.0f / (float)c.world_size;
+    if (ext_ema) {
+      float* region = l->bucket + l->goff[0];
+      ACX_TRY(peer_allreduce(l->peer, reinterpret_cast<uint8_t*>(region) - l->arena_base, flags_off, epochs_off,
+                             (long long)(l->bucket_floats - l->goff[0]), (long long)(l->factor_floats - l->goff[0]), inv_world, 0, st));
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      ACX_CUDA(cudaStreamIsCapturing(st, &cs));
+      ACX_CUDA(cudaEventRecordWithFlags(l->reduced, st, cs == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault));
+    } else {
+      ACX_TRY(peer_allreduce(l->peer, reinterpret_cast<uint8_t*>(l->bucket) - l->arena_base, flags_off, epochs_off,
+                             (long long)l->bucket_floats, 0, inv_world, 0, st));
+    }
+  } else if (c.world_size > 1) {
     if (ext_ema)   // only what this phase reads: [grads | scalars]; the statistics are scaled by acx_learner_ema
       ACX_TRY(scale_f32(l->grads, l->bucket_floats - l->factor_floats, 1.0f / (float)c.world_size, st));
     else
@@ -1249,7 +1284,7 @@ static int run_cached(acx_learner* l, const GraphKey& key, cudaStream_t st, F&& 
 static int phase2(acx_learner* l, cudaStream_t st) {
   const Plan2 p = plan_phase2(l);
   if (p.a2c || p.cold) l->deferred = 0;   // no covariance update in this phase: nothing can have been left to it
-  GraphKey key = {2, p.key() | (l->deferred << 5) | (l->external_ema ? 1 << 10 : 0), nullptr, nullptr};
+  GraphKey key = {2, p.key() | (l->deferred << 5) | (l->external_ema ? 1 << 10 : 0) | (l->peer.world > 1 ? 1 << 11 : 0), nullptr, nullptr};
   const int r = run_cached(l, key, st, [&]() { return issue_phase2(l, p, st); });
   if (r) return r;
   l->deferred = 0;
@@ -1341,6 +1376,7 @@ acx_learner_t* acx_learner_create(const acx_learner_config_t* cfg, void* d_arena
     return nullptr;
   }
   layout(l, reinterpret_cast<uint8_t*>(d_arena));
+  l->arena_base = reinterpret_cast<uint8_t*>(d_arena);
   setup_gather(l);
   register_buffers(l);
   l->gs = 0;
@@ -1349,7 +1385,8 @@ acx_learner_t* acx_learner_create(const acx_learner_config_t* cfg, void* d_arena
   l->inverses_valid = false;
   l->act_calls = 0;
   l->lanes = cfg->num_lanes <= 0 ? kMaxLanes : std::min(cfg->num_lanes, kMaxLanes);
-  if (cudaEventCreateWithFlags(&l->a_ready, cudaEventDisableTiming) != cudaSuccess) {
+  if (cudaEventCreateWithFlags(&l->a_ready, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&l->reduced, cudaEventDisableTiming) != cudaSuccess) {
     acx::set_error("acx_learner_create: cudaEventCreateWithFlags failed");
     delete l;
     return nullptr;
@@ -1586,6 +1623,41 @@ int acx_learner_ema(acx_learner_t* l, void* stream) {
   const acx_learner_config_t& c = l->cfg;
   if (c.world_size > 1) ACX_TRY(scale_f32(l->stats, l->factor_floats, 1.0f / (float)c.world_size, st));
   ACX_TRY(ema_update(l->sums, l->stats, l->factor_floats, c.cov_ema_decay, 1.0f, st));
+  return 0;
+}
+
+int acx_learner_set_peers(acx_learner_t* l, int rank, int world, void* const* peer_arena_bases) {
+  ACX_CHECK(l, "null learner");
+  if (world <= 1 || peer_arena_bases == nullptr) {   // back to caller-side collectives
+    l->peer = acx::PeerState();
+    return 0;
+  }
+  ACX_CHECK(world == l->cfg.world_size && world <= 8 && rank >= 0 && rank < world, "acx_learner_set_peers: rank / world");
+  acx::PeerState ps;
+  ps.rank = rank;
+  ps.world = world;
+  for (int k = 0; k < world; ++k) {
+    ps.base[k] = k == rank ? l->arena_base : reinterpret_cast<uint8_t*>(peer_arena_bases[k]);
+    ACX_CHECK(ps.base[k] != nullptr, "acx_learner_set_peers: null peer arena");
+  }
+  l->peer = ps;
+  return 0;
+}
+
+int acx_learner_peer_reduce_prefix(acx_learner_t* l, void* stream) {
+  ACX_CHECK(l, "null learner");
+  ACX_CHECK(l->peer.world > 1, "acx_learner_peer_reduce_prefix: no peers (acx_learner_set_peers)");
+  // the input-factor statistics A (the prefix of the bucket), summed over the ranks on the caller's side stream while phase 2
+  // runs; unscaled (acx_learner_ema scales all statistics)
+  return acx::peer_allreduce(l->peer, reinterpret_cast<uint8_t*>(l->bucket) - l->arena_base,
+                             reinterpret_cast<uint8_t*>(l->peer_flags) - l->arena_base,
+                             reinterpret_cast<uint8_t*>(l->peer_epochs) - l->arena_base, (long long)l->goff[0],
+                             (long long)l->goff[0], 1.0f, 1, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int acx_learner_wait_reduced(acx_learner_t* l, void* stream) {
+  ACX_CHECK(l, "null learner");
+  ACX_CUDA(cudaStreamWaitEvent(reinterpret_cast<cudaStream_t>(stream), l->reduced, 0));
   return 0;
 }
 

@@ -418,6 +418,11 @@ class Engine:
         if self.config.world_size <= 1:
             return
         dist = torch.distributed
+        if self._peers_ready(group):
+            # the exchange runs inside phase 2 as one kernel over NVLink peer memory (csrc/peer.cu): nothing to issue here
+            # except, for updates with factor statistics and no inverse refresh, the input-factor prefix on the side stream
+            self._plan_peer_exchange(group)
+            return
         early = False
         if overlap is None:
             # Opt-in (ACX_DP_OVERLAP=1 or overlap=True).  Measured on one 8 x B200 box it does not pay: 2 ranks 1.097 ms/update
@@ -446,6 +451,87 @@ class Engine:
                 self.stream.wait_event(self._comm_done)
             else:
                 dist.all_reduce(self.bucket, op=dist.ReduceOp.SUM, group=group)
+
+    def _peers_ready(self, group):
+        """One-time set-up of the peer exchange (NCCL groups on one node, ACX_PEER != 0): every rank exports its arena with CUDA
+        IPC, maps the others' and hands the bases to the library.  All ranks agree on the outcome (a rank that cannot map a
+        peer sends everybody back to NCCL)."""
+        state = getattr(self, "_peer_state", None)
+        if state is not None:
+            return state
+        dist = torch.distributed
+        ok = os.environ.get("ACX_PEER", "1") != "0" and dist.get_backend(group) == "nccl" and self.config.world_size <= 8
+        bases = None
+        if ok:
+            handle = (ctypes.c_ubyte * 64)()
+            offset = ctypes.c_ulonglong(0)
+            base = self.arena.data_ptr() + self._arena_off
+            rc = self.lib.acx_peer_export(ctypes.c_void_p(base), handle, ctypes.byref(offset))
+            mine = (bytes(handle), int(offset.value), os.uname().nodename) if rc == 0 else None
+            everyone = [None] * self.config.world_size
+            dist.all_gather_object(everyone, mine, group=group)
+            rank = dist.get_rank(group)
+            ok = all(x is not None and x[2] == everyone[rank][2] for x in everyone)
+            if ok:
+                bases = (ctypes.c_void_p * self.config.world_size)()
+                with torch.cuda.device(self.device):
+                    for k, x in enumerate(everyone):
+                        if k == rank:
+                            bases[k] = base
+                            continue
+                        ptr = self.lib.acx_peer_import((ctypes.c_ubyte * 64).from_buffer_copy(x[0]), ctypes.c_ulonglong(x[1]))
+                        if not ptr:
+                            ok = False
+                            break
+                        bases[k] = ptr
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        ok = bool(flag.item())
+        if ok:
+            _lib.check(self.lib.acx_learner_set_peers(self._h, dist.get_rank(group), self.config.world_size, bases))
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=group)      # every rank's flags are zero and mapped before the first kernel signals
+        self._peer_state = ok
+        return ok
+
+    def _plan_peer_exchange(self, group):
+        """With peers: updates that carry factor statistics and do not refresh the inverses keep the split exchange - the
+        input-factor prefix A is summed by NCCL on a side stream UNDER phase 2, which itself sums [G | grads | scalars] over
+        peer memory; the side stream then waits for that (acx_learner_wait_reduced), scales the statistics and runs the EMA.
+        Everything else (cold / A2C updates, refresh updates) sums the whole bucket inside phase 2."""
+        dist = torch.distributed
+        self._after_phase2 = None
+        if not self.config.acktr or os.environ.get("ACX_DP_SPLIT", "1") == "0":
+            return
+        has_factors, will_invert = ctypes.c_int(0), ctypes.c_int(0)
+        _lib.check(self.lib.acx_learner_update_plan(self._h, ctypes.byref(has_factors), ctypes.byref(will_invert)))
+        if not has_factors.value or will_invert.value:
+            return
+        if getattr(self, "_split_stream", None) is None:
+            self._split_stream = torch.cuda.Stream(self.device)
+            self._split_group = dist.new_group(ranks=dist.get_process_group_ranks(group or dist.group.WORLD), backend="nccl")
+            self._p1_done, self._rest_done = torch.cuda.Event(), torch.cuda.Event()
+            self._ema_done = torch.cuda.Event()
+            self._split_a = self.buffer("input_factor_stats", torch.float32)
+            self._split_rest = self.bucket[self._split_a.numel():]
+        with self.on_stream():
+            self._p1_done.record(self.stream)
+
+        def after_phase2():     # enqueued behind the launch of phase 2, whose graph raises `reduced`
+            with torch.cuda.stream(self._split_stream):
+                self._split_stream.wait_event(self._p1_done)
+                # ACX_PEER_PREFIX=1: the prefix over peer memory too (its own flag channel) - measured slower at 2 ranks (0.816 vs
+                # 0.786 ms/update): the spinning CTAs of a second exchange kernel take more from phase 2 than NCCL's few do
+                if os.environ.get("ACX_PEER_PREFIX", "0") != "0":
+                    _lib.check(self.lib.acx_learner_peer_reduce_prefix(self._h, ctypes.c_void_p(self._split_stream.cuda_stream)))
+                else:
+                    dist.all_reduce(self._split_a, op=dist.ReduceOp.SUM, group=self._split_group)
+                _lib.check(self.lib.acx_learner_wait_reduced(self._h, ctypes.c_void_p(self._split_stream.cuda_stream)))
+                _lib.check(self.lib.acx_learner_ema(self._h, ctypes.c_void_p(self._split_stream.cuda_stream)))
+                self._ema_done.record(self._split_stream)
+        self._after_phase2 = after_phase2
+        self._ema_external = True
+        self._ema_pending = True
 
     def _split_exchange(self, group):
         """NCCL groups, K-FAC learners, covariance updates: phase 2 reads only [grads | scalars] of the bucket, so only
@@ -491,6 +577,9 @@ class Engine:
         self._ema_external = False
         with self.on_stream():
             _lib.check(self.lib.acx_learner_phase2(self._h, self._stream()))
+        after, self._after_phase2 = getattr(self, "_after_phase2", None), None
+        if after is not None:
+            after()
 
     def update(self, batch=None, fisher_labels=None, fisher_eps=None, fetch=True, group=None, staged=False):
         """The reference's `session.run([..., optimize_op], feed_dict)` (a2c_acktr.py:117-126)."""

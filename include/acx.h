@@ -302,6 +302,22 @@ int acx_learner_wait_input_factors(acx_learner_t* l, void* stream);
  * (actorcritic_b200.Engine.allreduce does this for NCCL groups; bit-identical to the single all-reduce.) */
 int acx_learner_update_plan(const acx_learner_t* l, int* has_factors, int* will_invert);
 int acx_learner_set_external_ema(acx_learner_t* l, int on);
+/* The exchange over NVLink peer memory instead of a caller-side collective (csrc/peer.cu): every rank maps every other rank's
+ * arena (acx_peer_export / acx_peer_import: CUDA IPC) and hands the mapped bases to acx_learner_set_peers (entry `rank` is ignored;
+ * world <= 8, one node).  From then on phase 2 starts with ONE kernel that sums the ranks' buckets in rank order - two-shot
+ * reduce-scatter + all-gather on peer pointers, flag barriers between equally numbered CTAs of the GPUs - fused with the
+ * 1 / world_size scaling: the whole `reduce_bucket`, or, with acx_learner_set_external_ema, only [G | grads | scalars] (the caller
+ * still sums the `input_factor_stats` prefix on its own stream, waits with acx_learner_wait_reduced for this update's kernel and
+ * runs acx_learner_ema).  The kernel is part of phase 2's CUDA graph, so a data-parallel update is two graph launches with no
+ * collective call in between.  Every rank must run the same sequence of updates.  acx_peer_error: non-zero after a barrier
+ * timed out (~2 s). */
+int acx_peer_export(const void* d_ptr, unsigned char* out_handle64, unsigned long long* out_offset);
+void* acx_peer_import(const unsigned char* handle64, unsigned long long offset);
+int acx_learner_set_peers(acx_learner_t* l, int rank, int world, void* const* peer_arena_bases);
+int acx_learner_wait_reduced(acx_learner_t* l, void* stream);
+/* the same kernel for the `input_factor_stats` prefix on the caller's side stream (its own flag channel; unscaled) */
+int acx_learner_peer_reduce_prefix(acx_learner_t* l, void* stream);
+int acx_peer_error(void);
 int acx_learner_ema(acx_learner_t* l, void* stream);
 /* Deferred input factors.  Only the next inverse refresh reads the K-FAC factor statistics, while the parameter update of
  * phase 2 needs nothing but the gradients.  With a non-zero `stage_mask` (bit s = input factor of conv1, conv2, conv3, fc4,

@@ -404,8 +404,13 @@ def _nccl_worker(rank, world, port, out_dir):
         kw = dict(num_steps=5, num_cold_updates=2, invert_every=2, lr_decay_steps=1000.0)
         params = onet.perturbed_params(4, 32, 7)
         results = {}
-        for split in ("1", "0"):      # split exchange (default) and the single all-reduce
+        # split exchange (default) and the single all-reduce, each with the exchange inside phase 2 over NVLink peer memory
+        # (csrc/peer.cu, default) and with NCCL between the phases
+        # ("2" = the general two-shot route of the peer kernel, which two ranks would not take by themselves)
+        for split, peer in (("1", "1"), ("0", "1"), ("1", "0"), ("0", "0"), ("1", "2")):
             os.environ["ACX_DP_SPLIT"] = split
+            os.environ["ACX_PEER"] = "0" if peer == "0" else "1"
+            os.environ["ACX_PEER_TWO_SHOT"] = "1" if peer == "2" else "0"
             e = eng.Engine(eng.EngineConfig(num_envs=8 // world, world_size=world, **kw))
             e.set_params(params)
             for u in range(7):
@@ -416,8 +421,11 @@ def _nccl_worker(rank, world, port, out_dir):
                 ee = torch.from_numpy(eps.reshape(8, 5)[lo:hi].reshape(-1).copy()).cuda()
                 e.update(batch, yy, ee, fetch=False)
             torch.cuda.synchronize()
-            results[split] = dict(params=e.get_params_flat().copy(), sums=e.buffer("factor_sums").cpu().numpy().copy(),
-                                  inv=e.buffer("inverses").cpu().numpy().copy(), gs=e.global_step)
+            assert bool(getattr(e, "_peer_state", False)) == (peer != "0"), "the peer exchange must be what ran"
+            from actorcritic_b200 import _lib
+            assert _lib.load().acx_peer_error() == 0
+            results[split + peer] = dict(params=e.get_params_flat().copy(), sums=e.buffer("factor_sums").cpu().numpy().copy(),
+                                         inv=e.buffer("inverses").cpu().numpy().copy(), gs=e.global_step)
         np.savez(os.path.join(out_dir, "rank%d.npz" % rank),
                  **{"%s_%s" % (k, s): v for s, r in results.items() for k, v in r.items()})
     finally:
@@ -438,8 +446,10 @@ def test_nccl_two_ranks_split_exchange_equals_single_device(tmp_path):
     mp.spawn(_nccl_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     r0, r1 = (np.load(str(tmp_path / ("rank%d.npz" % r))) for r in (0, 1))
     for key in ("params", "sums", "inv"):
-        assert np.array_equal(r0[key + "_1"], r1[key + "_1"]), key            # ranks never diverge
-        assert np.array_equal(r0[key + "_1"], r0[key + "_0"]), key            # split exchange == single all-reduce
+        for mode in ("11", "01", "10", "00", "12"):
+            assert np.array_equal(r0[key + "_" + mode], r1[key + "_" + mode]), (key, mode)     # ranks never diverge
+            # split exchange == single all-reduce, peer-memory exchange == NCCL (two ranks: one commutative addition)
+            assert np.array_equal(r0[key + "_11"], r0[key + "_" + mode]), (key, mode)
     eng = _engine_mod()
     full = eng.Engine(eng.EngineConfig(num_envs=8, num_steps=5, num_cold_updates=2, invert_every=2, lr_decay_steps=1000.0))
     full.set_params(onet.perturbed_params(4, 32, 7))
@@ -448,7 +458,7 @@ def test_nccl_two_ranks_split_exchange_equals_single_device(tmp_path):
         y, eps = synth.fisher_samples(70 + u, 40)
         full.update(batch, torch.from_numpy(y).cuda(), torch.from_numpy(eps).cuda(), fetch=False)
     torch.cuda.synchronize()
-    assert full.global_step == int(r0["gs_1"])
-    assert LC.rel_err(r0["sums_1"], full.buffer("factor_sums").cpu().numpy()) <= 1e-5
+    assert full.global_step == int(r0["gs_11"])
+    assert LC.rel_err(r0["sums_11"], full.buffer("factor_sums").cpu().numpy()) <= 1e-5
     # seven free-running K-FAC updates (lr 0.25): the 2-rank sum order differs from the single-device one by fp32 rounding
-    assert LC.rel_err(r0["params_1"], full.get_params_flat()) <= 1e-4
+    assert LC.rel_err(r0["params_11"], full.get_params_flat()) <= 1e-4
