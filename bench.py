@@ -250,7 +250,22 @@ def run_native(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = None
     if world > 1:
+        # keep this rank's host threads - and with them the pinned staging buffers they first touch - on the CPUs next to its
+        # GPU: eight ranks copying 19 MB per step from one NUMA node cost the end-to-end loop 0.15 ms per step in round 1
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pr = torch.cuda.get_device_properties(local_rank)
+            try:    # CUDA_VISIBLE_DEVICES may renumber the devices: find the NVML handle by PCI address
+                hnd = pynvml.nvmlDeviceGetHandleByPciBusId(b"%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id))
+            except Exception:  # noqa: BLE001
+                hnd = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+            pynvml.nvmlDeviceSetCpuAffinity(hnd)
+            numa = "rank pinned to the CPUs of GPU %d (nvmlDeviceSetCpuAffinity: %d CPUs)" % (local_rank, len(os.sched_getaffinity(0)))
+        except Exception as exc:  # noqa: BLE001
+            numa = "not pinned (%r)" % (exc,)
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
     envs, t_count, c3 = args.envs_per_gpu, args.num_steps, args.conv3
@@ -608,7 +623,10 @@ def run_native(args, rank, world, local_rank):
         "env_frames_per_sec": total_envs * t_count * FRAMESKIP / ((ms_step + rollout_ms) * 1e-3),
         "env_frames_per_sec_learner_only": value * FRAMESKIP,
         "config": make_config(args, world),
-        "engine": {"precision": args.precision, "cuda_graphs": not args.no_graphs, "lanes": args.lanes if args.lanes > 0 else 5,
+        "engine": {"host_affinity": numa, "exchange": None if world == 1 else (
+                       "one kernel over NVLink peer memory inside phase 2's graph (csrc/peer.cu) for [G | grads | scalars]; the input-factor "
+                       "prefix by NCCL on a side stream under phase 2" if getattr(e, "_peer_state", False) else "NCCL all-reduce between the phases"),
+                   "precision": args.precision, "cuda_graphs": not args.no_graphs, "lanes": args.lanes if args.lanes > 0 else 5,
                    "patches": "never stored: conv input factors / weight gradients read their patch operands in place (5-D TMA box loads from "
                               "the activations; conv1 from a row-pair interleaved bf16 copy of the observations)"
                               if os.environ.get("ACX_GATHER", "1") != "0" else "materialised P1 / P2 / P3 (ACX_GATHER=0)",
