@@ -88,6 +88,8 @@ SIGNATURES = {
     "acx_debug_set_mn_desc": (None, [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]),
     "acx_debug_set_fuse_reduce": (None, [ctypes.c_int]),
     "acx_obs_pairs_bf16": (ctypes.c_int, [_P, _P, ctypes.c_int, _P]),
+    "acx_conv1_pairs_forward": (ctypes.c_int, [_P, ctypes.POINTER(Planes), ctypes.c_int, _P, ctypes.c_float, ctypes.POINTER(Planes),
+                                               ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), _P]),
     "acx_debug_tc_error": (ctypes.c_int, []),
     "acx_gemm_enable_timing": (ctypes.c_int, [ctypes.c_int]),
     "acx_gemm_last_ms": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float)]),

@@ -64,6 +64,8 @@ struct ConvTcParams {
   int npl, ldcp;
   const bf16* mask;
   int mask_samples;
+  int b_resident;   // the whole weight operand (kb_total x npb tiles) is loaded once per CTA and stays in shared memory (conv1 forward: 32 KB;
+                    // the kernel is bound by L2 -> SM traffic and re-loading the weights for each of its 2100 tiles was a third of it)
   int debug;   // ACX_CONV_DEBUG bits (performance triage only): 1 skip activation loads, 2 skip weight loads, 4 skip MMAs, 8 skip stores
 };
 
@@ -83,13 +85,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
   }
   const int BN = p.bn;
   const int b_tile_bytes = BN * CV_BK * 2;
-  const int stage_bytes = p.npa * CV_A_TILE + p.npb * b_tile_bytes;
+  const int res_bytes = p.b_resident ? p.kb_total * p.npb * b_tile_bytes : 0;   // resident weight tiles come first
+  uint8_t* const res_b = smem;
+  smem += res_bytes;
+  const int stage_bytes = p.npa * CV_A_TILE + (p.b_resident ? 0 : p.npb * b_tile_bytes);
   float* epi = reinterpret_cast<float*>(smem + p.stages * stage_bytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(epi) + CV_EPI_BYTES);
   uint64_t* empty_bar = full_bar + CV_MAX_STAGES;
   uint64_t* acc_full = empty_bar + CV_MAX_STAGES;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* b_bar = reinterpret_cast<uint64_t*>(tmem_slot + 2);   // resident weights have landed
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tmem_cols = (uint32_t)(2 * BN);   // two accumulators: 64, 128 or 256 columns
@@ -103,6 +109,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
       mbar_init(&acc_full[b], 1);
       mbar_init(&acc_empty[b], BN > 32 ? 8 : 4);   // epilogue warps that drain an accumulator
     }
+    mbar_init(b_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
@@ -116,21 +123,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
   if (warp == 0) {
     {
       // ===== TMA producer: per k-block one box per (plane, sub-tile) of the activation + the weight tile =====
+      if (p.b_resident && elect_one()) {   // the whole weight operand, once
+        mbar_expect_tx(b_bar, (uint32_t)res_bytes);
+        for (int kb = 0; kb < p.kb_total; ++kb)
+          for (int i = 0; i < p.npb; ++i) {
+            const CUtensorMap* mb = i == 0 ? &tb0 : (i == 1 ? &tb1 : &tb2);
+            tma_load_2d(res_b + (kb * p.npb + i) * b_tile_bytes, mb, b_bar, kb * CV_BK, 0);
+          }
+      }
+      __syncwarp();
       int it = 0;
+      int ring_s = 0;
+      uint32_t ring_ph = 0u;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int grp = tile / p.cells, cell = tile - grp * p.cells;
         const int cy = cell / p.nx, cx = cell - cy * p.nx;
         const int sample0 = grp * p.ts, x0 = cx * p.bx, y0 = cy * p.by;
         const int y2 = p.ydim == 2 ? y0 : 0, y3 = p.ydim == 3 ? y0 : 0;
         for (int kb = 0; kb < p.kb_total; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+          const int s = ring_s;   // ring position and phase advance without a division (this thread is the bottleneck)
+          const uint32_t ph = ring_ph;
+          if (++ring_s == p.stages) {
+            ring_s = 0;
+            ring_ph ^= 1u;
+          }
           const int nload = min(p.nsub, p.num_sub - kb * p.nsub);
           mbar_wait(&empty_bar[s], ph ^ 1u, 1);
           __syncwarp();
           if (!elect_one()) continue;
           mbar_expect_tx(&full_bar[s], (uint32_t)(((p.debug & 1) ? 0 : p.npa * nload * p.sub_bytes) +
-                                                  ((p.debug & 2) ? 0 : p.npb * b_tile_bytes)));
+                                                  (((p.debug & 2) || p.b_resident) ? 0 : p.npb * b_tile_bytes)));
           uint8_t* a_s = smem + s * stage_bytes;
           uint8_t* b_s = a_s + p.npa * CV_A_TILE;
           for (int i = 0; i < p.npa && !(p.debug & 1); ++i) {
@@ -140,7 +162,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
               tma_load_5d(a_s + i * CV_A_TILE + j * sub_tile_bytes, ma, &full_bar[s], 0, p.tc1[t] + x0, p.tc2[t] + y2, p.tc3[t] + y3, sample0);
             }
           }
-          for (int i = 0; i < p.npb && !(p.debug & 2); ++i) {
+          for (int i = 0; i < p.npb && !(p.debug & 2) && !p.b_resident; ++i) {
             const CUtensorMap* mb = i == 0 ? &tb0 : (i == 1 ? &tb1 : &tb2);
             tma_load_2d(b_s + i * b_tile_bytes, mb, &full_bar[s], kb * CV_BK, 0);
           }
@@ -164,8 +186,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
 #pragma unroll
     for (int t = 0; t < 4; ++t) a_step[t] = (uint32_t)((t / ksteps) * sub_tile_bytes + (t % ksteps) * 32) >> 4;
     int it = 0, lt = 0;
+    int ring_s = 0;
+    uint32_t ring_ph = 0u;
+    // descriptors of stage 0 and their step from stage to stage: built once, advanced by an addition (the low 14-bit address
+    // field never carries out: every tile lies inside the 256 KB shared window)
+    const uint64_t a_desc_s0 = make_smem_desc_sw(smem_u32(smem), 16u, a_sbo, a_layout);
+    const uint64_t b_desc_s0 = p.b_resident ? make_smem_desc_sw(smem_u32(res_b), 16u, 1024u, 2u)
+                                            : make_smem_desc_sw(smem_u32(smem) + (uint32_t)(p.npa * CV_A_TILE), 16u, 1024u, 2u);
+    const uint64_t a_desc_step = (uint64_t)((uint32_t)stage_bytes >> 4);
+    uint64_t a_desc_cur = a_desc_s0, b_desc_cur = b_desc_s0;
     const bool trace = (p.debug & 32) && blockIdx.x == 0;
     long long w_full = 0, w_acc = 0, t_begin = trace ? clock64() : 0;
+    if (p.b_resident) {
+      mbar_wait(b_bar, 0u, 5);
+      tc_fence_after();
+    }
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
       const int buf = lt & 1;
       const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
@@ -178,33 +213,51 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
       for (int kb = 0; kb < p.kb_total; ++kb, ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        const int s = ring_s;   // ring position and phase advance without a division (this thread is the bottleneck)
+        const uint32_t ph = ring_ph;
+        const uint64_t a_desc0 = a_desc_cur;
+        const uint64_t b_desc0 = p.b_resident ? b_desc_s0 + (uint64_t)((uint32_t)(kb * p.npb * b_tile_bytes) >> 4) : b_desc_cur;
+        if (++ring_s == p.stages) {
+          ring_s = 0;
+          ring_ph ^= 1u;
+          a_desc_cur = a_desc_s0;
+          b_desc_cur = b_desc_s0;
+        } else {
+          a_desc_cur += a_desc_step;
+          b_desc_cur += a_desc_step;
+        }
         tw = trace ? clock64() : 0;
         mbar_wait(&full_bar[s], ph, 2);
         if (trace) w_full += clock64() - tw;
         tc_fence_after();
         if (elect_one()) {
           const int nload = min(p.nsub, p.num_sub - kb * p.nsub);
-          const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-          const uint32_t b_addr = a_addr + (uint32_t)(p.npa * CV_A_TILE);
           uint32_t acc_flag = kb > 0 ? 1u : 0u;
           // straight-line issue: a k-block is 4 MMA steps of K = 16 per plane pair (step t: A at a_step[t] inside the plane's
           // tile - the second 32-wide sub-tile starts sub_tile_bytes in -, B 32 bytes further along its 128-byte row); pair
           // offsets are hoisted out of the tile loop.  With run-time loop bounds and per-pair parameter loads the issue loop
           // itself cost 110-150 cycles per MMA (trace, ACX_CONV_DEBUG=32) against 48-64 in the tensor pipe.
-          const uint64_t a_desc0 = make_smem_desc_sw(a_addr, 16u, a_sbo, a_layout);
-          const uint64_t b_desc0 = make_smem_desc_sw(b_addr, 16u, 1024u, 2u);
           const int nsteps = nload * ksteps;
           if (!(p.debug & 4)) {
+            if (p.nsub == 1 && npairs == 3) {   // one 64-wide sub-tile: four steps of 32 bytes on both operands; the whole k-block as one block
+              umma_bf16_x4_pairs3(d_tmem, a_desc0, b_desc0, 2u, 2u, idesc, acc_flag, a_off[0], b_off[0], a_off[1], b_off[1], a_off[2], b_off[2]);
+            } else if (p.nsub == 1 && npairs == 2) {
+              umma_bf16_x4_pairs2(d_tmem, a_desc0, b_desc0, 2u, 2u, idesc, acc_flag, a_off[0], b_off[0], a_off[1], b_off[1]);
+            } else if (p.nsub == 1) {
 #pragma unroll
-            for (int pr = 0; pr < 6; ++pr) {
-              if (pr < npairs) {
+              for (int pr = 0; pr < 6; ++pr)
+                if (pr < npairs)
+                  umma_bf16_x4(d_tmem, a_desc0 + (uint64_t)a_off[pr], b_desc0 + (uint64_t)b_off[pr], 2u, 2u, idesc, pr ? 1u : acc_flag);
+            } else {
 #pragma unroll
-                for (int t = 0; t < 4; ++t)
-                  if (t < nsteps)
-                    umma_bf16(d_tmem, a_desc0 + (uint64_t)(a_off[pr] + a_step[t]), b_desc0 + (uint64_t)(b_off[pr] + 2u * (uint32_t)t), idesc,
-                              (pr | t) ? 1u : acc_flag);
+              for (int pr = 0; pr < 6; ++pr) {
+                if (pr < npairs) {
+#pragma unroll
+                  for (int t = 0; t < 4; ++t)
+                    if (t < nsteps)
+                      umma_bf16(d_tmem, a_desc0 + (uint64_t)(a_off[pr] + a_step[t]), b_desc0 + (uint64_t)(b_off[pr] + 2u * (uint32_t)t), idesc,
+                                (pr | t) ? 1u : acc_flag);
+                }
               }
             }
           }
@@ -307,8 +360,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
 #pragma unroll
         for (int t = 0; t < NIT; ++t) {
           row_ok[t] = row_off[t] != NO_ROW && row_smp[t] < smp_limit;
-          const int sm = sample0 + row_smp[t];
-          mrow[t] = base + row_off[t] - (size_t)(sm - sm % p.mask_samples) * img;
+          int sm = sample0 + row_smp[t], wrapped = 0;   // sample r uses the mask of sample r % mask_samples (r < 2 mask_samples as a rule)
+          while (mask != nullptr && sm >= p.mask_samples) {
+            sm -= p.mask_samples;
+            wrapped += p.mask_samples;
+          }
+          mrow[t] = base + row_off[t] - (size_t)wrapped * img;
         }
         for (int ch = grp, c = 0; ch < nchunks; ch += 2, ++c) {
           uint32_t raw[32];
@@ -536,8 +593,10 @@ static int fill_pairs(ConvTcParams* p, int num_pairs, const int* pair_a, const i
 }
 
 static int launch_conv(const CUtensorMap* ta, const CUtensorMap* tb, ConvTcParams& p, cudaStream_t st) {
-  const int stage_bytes = p.npa * CV_A_TILE + p.npb * p.bn * CV_BK * 2;
-  p.stages = (CV_SMEM_LIMIT - CV_SMEM_FIXED) / stage_bytes;
+  const int b_tile = p.bn * CV_BK * 2;
+  const int res_bytes = p.b_resident ? p.kb_total * p.npb * b_tile : 0;
+  const int stage_bytes = p.npa * CV_A_TILE + (p.b_resident ? 0 : p.npb * b_tile);
+  p.stages = (CV_SMEM_LIMIT - CV_SMEM_FIXED - res_bytes) / stage_bytes;
   if (p.stages > CV_MAX_STAGES) p.stages = CV_MAX_STAGES;
   ACX_CHECK(p.stages >= 2, "conv tile does not fit the shared-memory ring");
   static bool configured = false;
@@ -555,7 +614,7 @@ static int launch_conv(const CUtensorMap* ta, const CUtensorMap* tb, ConvTcParam
   }
   int grid = std::min(p.num_tiles, conv_num_sms());
   if (g_cta_cap > 0 && grid > g_cta_cap) grid = g_cta_cap;
-  const int smem = CV_SMEM_FIXED + p.stages * stage_bytes;
+  const int smem = CV_SMEM_FIXED + res_bytes + p.stages * stage_bytes;
   ACX_CUDA(launch_pdl(conv_tc_kernel, dim3(grid), dim3(CV_THREADS), (size_t)smem, st, ta[0], ta[1], ta[2], tb[0], tb[1], tb[2], p));
   acx::count_launch();
   return 0;
@@ -728,6 +787,14 @@ int conv1_pairs_forward(const bf16* obs_pairs, const Planes& wT_perm, int sample
   p.ldcp = y.ld;
   p.mask = nullptr;
   p.mask_samples = 1;
+  {
+    static int bres = -1;
+    if (bres < 0) {
+      const char* e = getenv("ACX_CONV1_BRES");   // 0: reload the weight tiles with every k-block (as the other layers do)
+      bres = e ? atoi(e) : 0;   // measured: no gain (0.7237 vs 0.7244 ms/update) - the kernel is not bound by these loads
+    }
+    p.b_resident = bres;   // 4 k-blocks x <= 3 planes x 4 KB
+  }
   for (int i = 0; i < y.n; ++i) ACX_CHECK((reinterpret_cast<uintptr_t>(y.p[i]) & 15) == 0, "output planes must be 16-byte aligned");
   CUtensorMap ta[3], tb[3];
   const long long prow = 84 * 8;   // elements of one pair-row
@@ -865,6 +932,13 @@ int acx_conv(const acx_conv_t* c, void* stream) {
 }
 
 int acx_debug_conv_trace(long long* h_out8) { return acx::conv_trace(h_out8); }
+
+int acx_conv1_pairs_forward(const void* d_obs_pairs, const acx_planes_t* w_perm, int samples, const float* d_bias, float alpha,
+                            const acx_planes_t* out, int num_pairs, const int* pair_a, const int* pair_b, void* stream) {
+  ACX_CHECK(d_obs_pairs && w_perm && out && pair_a && pair_b, "null argument");
+  return acx::conv1_pairs_forward(reinterpret_cast<const acx::bf16*>(d_obs_pairs), to_planes(*w_perm), samples, d_bias, alpha,
+                                  to_planes(*out), num_pairs, pair_a, pair_b, reinterpret_cast<cudaStream_t>(stream));
+}
 
 int acx_conv_dgrad_weights(const float* d_w, int hw_in, int c_in, int k, int stride, int hw_out, int c_out, void* const* d_planes,
                            int ld, void* stream) {

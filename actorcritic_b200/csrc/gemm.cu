@@ -316,6 +316,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
     {
       // ===== TMA producer (whole warp waits, one elected lane issues) =====
       int it = 0;
+      int ring_s = 0;
+      uint32_t ring_ph = 0u;
       for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
         int tm, tn, split;
         decode(w, tm, tn, split);
@@ -355,8 +357,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
           g_cx = g_cell - g_cy * p.g_nx;
         }
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+          const int s = ring_s;   // ring position and phase advance without a division (this thread is the bottleneck)
+          const uint32_t ph = ring_ph;
+          if (++ring_s == p.stages) {
+            ring_s = 0;
+            ring_ph ^= 1u;
+          }
           // gathered operands: where the 64 locations of this k-block sit in the (x, y, sample) space
           const int gx0 = g_cx * p.g_bx, gy0 = g_cy * p.g_by, gn0 = g_grp * p.g_ts;
           if (MAJOR == 1 && p.gather_a) {
@@ -445,11 +451,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
     long long w_full = 0, w_acc = 0, tw = 0;
     const long long t_begin = trace ? clock64() : 0;
     int it = 0, lt = 0;
+    int ring_s = 0;
+    uint32_t ring_ph = 0u;
+    // the descriptor of stage 0 and its step from stage to stage: built once, advanced by an addition (this thread is the
+    // bottleneck of the kernel: every instruction it does not execute per k-block is time the tensor pipe gets)
+    const uint64_t a_desc_s0 = make_smem_desc_sw(smem_u32(smem), lbo, sbo, layout);
+    const uint64_t desc_step = (uint64_t)((uint32_t)stage_bytes >> 4);
+    const uint64_t b_desc_off = (uint64_t)((uint32_t)(p.npa * a_tile_bytes) >> 4);
+    uint64_t a_desc_cur = a_desc_s0;
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++lt) {
       int tm, tn, split;
       decode(w, tm, tn, split);
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      int krem = p.k - kb0 * bk;   // K elements left from this k-block on
       const int buf = p.panel ? 0 : (lt & 1);
       const uint32_t aph = p.panel ? ((uint32_t)lt & 1u) : ((uint32_t)(lt >> 1) & 1u);
       const bool diag = MAJOR == 1 && p.same_operand && !p.panel && tm == tn;
@@ -459,21 +474,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(p.panel ? 0 : buf * BN);
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        const int s = ring_s;   // ring position and phase advance without a division (this thread is the bottleneck)
+        const uint32_t ph = ring_ph;
+        // the descriptor of a tile advanced by `off` bytes is base + (off >> 4): only the 14-bit address field moves
+        // (tiles are 1024-byte aligned inside the < 256 KB shared window, so the add never carries out of the field)
+        const uint64_t a_desc0 = a_desc_cur;
+        const uint64_t b_desc0 = diag ? a_desc_cur : a_desc_cur + b_desc_off;
+        if (++ring_s == p.stages) {
+          ring_s = 0;
+          ring_ph ^= 1u;
+          a_desc_cur = a_desc_s0;
+        } else {
+          a_desc_cur += desc_step;
+        }
+        const int kvalid = min(bk, krem);
+        krem -= bk;
         if (trace) tw = clock64();
         mbar_wait(&full_bar[s], ph, 2);
         if (trace) w_full += clock64() - tw;
         tc_fence_after();
         if (elect_one()) {
-          const int kvalid = min(bk, p.k - kb * bk);
           const int ksteps = (kvalid + 15) >> 4;
-          const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-          const uint32_t b_addr = diag ? a_addr : a_addr + (uint32_t)(p.npa * a_tile_bytes);
-          // the descriptor of a tile advanced by `off` bytes is base + (off >> 4): only the 14-bit address field moves
-          // (tiles are 1024-byte aligned inside the < 256 KB shared window, so the add never carries out of the field)
-          const uint64_t a_desc0 = make_smem_desc_sw(a_addr, lbo, sbo, layout);
-          const uint64_t b_desc0 = make_smem_desc_sw(b_addr, lbo, sbo, layout);
           uint32_t acc_flag = kb > kb0 ? 1u : 0u;
           if (p.panel) {
             // three upper sub-tiles (0,0) (0,1) (1,1): accumulators at TMEM columns 0, 128, 256
@@ -483,6 +504,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
                 uint64_t ad = a_desc0 + (uint64_t)((uint32_t)(p.pair_a[pr] * panel_tile_bytes + ti * a_tile_bytes) >> 4);
                 uint64_t bd = a_desc0 + (uint64_t)((uint32_t)(p.pair_b[pr] * panel_tile_bytes + tj * a_tile_bytes) >> 4);
                 uint32_t flag = (kb > kb0 || pr > 0) ? 1u : 0u;
+                if (ksteps == 4) {
+                  umma_bf16_x4(d_tmem + (uint32_t)(sub * 128), ad, bd, (uint32_t)kstep16, (uint32_t)kstep16, idesc, flag);
+                  continue;
+                }
                 for (int kk = 0; kk < ksteps; ++kk) {
                   umma_bf16(d_tmem + (uint32_t)(sub * 128), ad, bd, idesc, flag);
                   flag = 1u;
@@ -495,15 +520,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
             // full 64-deep k-block: straight-line code (pair offsets hoisted out of the tile loop, both loops unrolled).
             // The issuing thread is alone on its scheduler: with run-time loop bounds and per-pair parameter loads the
             // issue loop itself cost ~110 cycles per MMA (measured, conv.cu trace) against 48-64 in the tensor pipe.
+            if (npairs == 3) {
+              umma_bf16_x4_pairs3(d_tmem, a_desc0, b_desc0, (uint32_t)kstep16, (uint32_t)kstep16, idesc, acc_flag, a_off[0],
+                                  diag ? b_off_d[0] : b_off[0], a_off[1], diag ? b_off_d[1] : b_off[1], a_off[2], diag ? b_off_d[2] : b_off[2]);
+            } else if (npairs == 2) {
+              umma_bf16_x4_pairs2(d_tmem, a_desc0, b_desc0, (uint32_t)kstep16, (uint32_t)kstep16, idesc, acc_flag, a_off[0],
+                                  diag ? b_off_d[0] : b_off[0], a_off[1], diag ? b_off_d[1] : b_off[1]);
+            } else {
 #pragma unroll
-            for (int pr = 0; pr < 6; ++pr) {
-              if (pr < npairs) {
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                  umma_bf16(d_tmem, a_desc0 + (uint64_t)(a_off[pr] + (uint32_t)kk * (uint32_t)kstep16),
-                            b_desc0 + (uint64_t)((diag ? b_off_d[pr] : b_off[pr]) + (uint32_t)kk * (uint32_t)kstep16), idesc,
-                            (pr | kk) ? 1u : acc_flag);
-              }
+              for (int pr = 0; pr < 6; ++pr)
+                if (pr < npairs)
+                  umma_bf16_x4(d_tmem, a_desc0 + (uint64_t)a_off[pr], b_desc0 + (uint64_t)(diag ? b_off_d[pr] : b_off[pr]), (uint32_t)kstep16,
+                               (uint32_t)kstep16, idesc, pr ? 1u : acc_flag);
             }
           } else {
             for (int pr = 0; pr < p.num_pairs; ++pr) {
@@ -582,6 +610,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
     bool have = open_work();
     if (have) load_block(cur);
     int it = 0;
+    int ring_s = 0;
+    uint32_t ring_ph = 0u;
     while (have) {
       // remember where the current block goes, then advance and prefetch
       const int c_items = items, c_rpc = rows_per_chunk;
@@ -591,8 +621,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
         have = open_work();
       }
       if (have) load_block(nxt);
-      const int s = it % p.stages;
-      const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+      const int s = ring_s;   // ring position and phase advance without a division (this thread is the bottleneck)
+      const uint32_t ph = ring_ph;
+      if (++ring_s == p.stages) {
+        ring_s = 0;
+        ring_ph ^= 1u;
+      }
       mbar_wait(&empty_bar[s], ph ^ 1u, 6);
       uint8_t* a_s = smem + s * stage_bytes;
 #pragma unroll

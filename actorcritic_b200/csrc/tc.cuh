@@ -75,6 +75,127 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// The four K = 16 steps of one 64-deep k-block of one plane pair in ONE asm statement: the descriptors advance inside the block
+// (a/b step in 16-byte units), so ptxas moves the operands into uniform registers once and steps them there.  With one asm
+// statement per MMA it re-materialised every operand - descriptor halves, instruction descriptor, TMEM address - from vector
+// registers before each UTCHMMA: 16 instructions per MMA on the single issuing thread, which is what bounded the kernels
+// (ncu source view: the MMA warp never stalls, it executes; 105 - 144 cycles per MMA against 40 - 64 in the tensor pipe).
+__device__ __forceinline__ void umma_bf16_x4(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t astep16, uint32_t bstep16,
+                                             uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db, sa, sb;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.eq.b32 q, %5, %5;\n\t"
+      "cvt.u64.u32 sa, %3;\n\t"
+      "cvt.u64.u32 sb, %4;\n\t"
+      "mov.b64 da, %1;\n\t"
+      "mov.b64 db, %2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "add.u64 da, da, sa;\n\t"
+      "add.u64 db, db, sb;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, q;\n\t"
+      "add.u64 da, da, sa;\n\t"
+      "add.u64 db, db, sb;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, q;\n\t"
+      "add.u64 da, da, sa;\n\t"
+      "add.u64 db, db, sb;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, q;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(astep16), "r"(bstep16), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// ... and all plane pairs of a k-block in one statement (2 or 3 pairs: the shapes the learner runs)
+__device__ __forceinline__ void umma_bf16_x4_pairs2(uint32_t tmem_d, uint64_t a0, uint64_t b0, uint32_t astep16, uint32_t bstep16,
+                                                    uint32_t idesc, uint32_t acc, uint32_t oa0, uint32_t ob0, uint32_t oa1, uint32_t ob1) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db, sa, sb, t;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.eq.b32 q, %5, %5;\n\t"
+      "cvt.u64.u32 sa, %3;\n\t"
+      "cvt.u64.u32 sb, %4;\n\t"
+      "cvt.u64.u32 t, %7;\n\t"
+      "add.u64 da, %1, t;\n\t"
+      "cvt.u64.u32 t, %8;\n\t"
+      "add.u64 db, %2, t;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "add.u64 da, da, sa;\n\t"
+      "add.u64 db, db, sb;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, q;\n\t"
+      "add.u64 da, da, sa;\n\t"
+      "add.u64 db, db, sb;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, q;\n\t"
+      "add.u64 da, da, sa;\n\t"
+      "add.u64 db, db, sb;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, q;\n\t"
+      "cvt.u64.u32 t, %9;\n\t"
+      "add.u64 da, %1, t;\n\t"
+      "cvt.u64.u32 t, %10;\n\t"
+      "add.u64 db, %2, t;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, q;\n\t"
+      "add.u64 da, da, sa;\n\t"
+      "add.u64 db, db, sb;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, q;\n\t"
+      "add.u64 da, da, sa;\n\t"
+      "add.u64 db, db, sb;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, q;\n\t"
+      "add.u64 da, da, sa;\n\t"
+      "add.u64 db, db, sb;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, q;\n\t"
+      "}" ::"r"(tmem_d), "l"(a0), "l"(b0), "r"(astep16), "r"(bstep16), "r"(idesc), "r"(acc), "r"(oa0), "r"(ob0), "r"(oa1), "r"(ob1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_x4_pairs3(uint32_t tmem_d, uint64_t a0, uint64_t b0, uint32_t astep16, uint32_t bstep16,
+                                                    uint32_t idesc, uint32_t acc, uint32_t oa0, uint32_t ob0, uint32_t oa1, uint32_t ob1, uint32_t oa2, uint32_t ob2) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db, sa, sb, t;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.eq.b32 q, %5, %5;\n\t"
+      "cvt.u64.u32 sa, %3;\n\t"
+      "cvt.u64.u32 sb, %4;\n\t"
+      "cvt.u64.u32 t, %7;\n\t"
+      "add.u64 da, %1, t;\n\t"
+      "cvt.u64.u32 t, %8;\n\t"
+      "add.u64 db, %2, t;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "add.u64 da, da, sa;\n\t"
+      "add.u64 db, db, sb;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, q;\n\t"
+      "add.u64 da, da, sa;\n\t"
+      "add.u64 db, db, sb;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, q;\n\t"
+      "add.u64 da, da, sa;\n\t"
+      "add.u64 db, db, sb;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, q;\n\t"
+      "cvt.u64.u32 t, %9;\n\t"
+      "add.u64 da, %1, t;\n\t"
+      "cvt.u64.u32 t, %10;\n\t"
+      "add.u64 db, %2, t;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, q;\n\t"
+      "add.u64 da, da, sa;\n\t"
+      "add.u64 db, db, sb;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, q;\n\t"
+      "add.u64 da, da, sa;\n\t"
+      "add.u64 db, db, sb;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, q;\n\t"
+      "add.u64 da, da, sa;\n\t"
+      "add.u64 db, db, sb;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, q;\n\t"
+      "cvt.u64.u32 t, %11;\n\t"
+      "add.u64 da, %1, t;\n\t"
+      "cvt.u64.u32 t, %12;\n\t"
+      "add.u64 db, %2, t;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, q;\n\t"
+      "add.u64 da, da, sa;\n\t"
+      "add.u64 db, db, sb;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, q;\n\t"
+      "add.u64 da, da, sa;\n\t"
+      "add.u64 db, db, sb;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, q;\n\t"
+      "add.u64 da, da, sa;\n\t"
+      "add.u64 db, db, sb;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, q;\n\t"
+      "}" ::"r"(tmem_d), "l"(a0), "l"(b0), "r"(astep16), "r"(bstep16), "r"(idesc), "r"(acc), "r"(oa0), "r"(ob0), "r"(oa1), "r"(ob1), "r"(oa2), "r"(ob2)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");

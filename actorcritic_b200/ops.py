@@ -147,6 +147,28 @@ def obs_pairs(obs):
     return out
 
 
+def conv1_pairs_forward(pairs_copy, w, bias, pairs=None, out_planes=2, w_planes=3, alpha=1.0 / 255.0):
+    """relu(alpha * conv1(obs, w) + bias) from the row-pair copy (acx_conv1_pairs_forward); w fp32 [256, 32] with rows (kh, kw, c).
+    Returns bf16 planes [S * 400, 32]."""
+    lib = _lib.load()
+    samples = pairs_copy.shape[0]
+    f = torch.arange(256, device=w.device)
+    kh, kw, c = f // 32, (f // 4) % 8, f % 4
+    col = (kh // 2) * 64 + kw * 8 + (kh % 2) * 4 + c
+    wt = torch.empty((32, 256), dtype=torch.float32, device=w.device)
+    wt[:, col] = w.t().float()
+    wp = split_planes(wt, w_planes)
+    outs = [torch.zeros((samples * 400, 32), dtype=torch.bfloat16, device=w.device) for _ in range(out_planes)]
+    if pairs is None:
+        pairs = [(0, j) for j in range(min(w_planes, 2))]
+    pa = (ctypes.c_int * len(pairs))(*[p[0] for p in pairs])
+    pb = (ctypes.c_int * len(pairs))(*[p[1] for p in pairs])
+    ws, os_ = _planes_struct(wp, 32, 256), _planes_struct(outs, samples * 400, 32)
+    _lib.check(lib.acx_conv1_pairs_forward(pairs_copy.data_ptr(), ctypes.byref(ws), samples, bias.data_ptr(), ctypes.c_float(alpha),
+                                           ctypes.byref(os_), len(pairs), pa, pb, _stream()))
+    return outs
+
+
 def _planes_struct(planes, rows, cols):
     s = _lib.Planes()
     for i, p in enumerate(planes):

@@ -145,6 +145,11 @@ typedef struct {
  * patch at (oy, ox) are then 64 contiguous elements at pair-row 2 oy + j, pixel 4 ox, in the column order (kw, q, c): the patch
  * matrix the reference's conv1 and kfac's conv1 input factor are built on never has to be stored (acx_gather_t, perm_m / perm_n). */
 int acx_obs_pairs_bf16(const uint8_t* d_obs, void* d_out, int samples, void* stream);
+/* conv1 of the Nature-CNN (8x8 / stride 4, 32 filters, envs/atari/model.py:173-179) as an implicit GEMM on that copy:
+ * out = relu(alpha * conv(obs, W) + bias) as bf16 planes [samples * 400, 32].  w_perm: W^T planes [32, 256] whose columns are in
+ * the copy's order - column (kh / 2) * 64 + kw * 8 + (kh % 2) * 4 + c holds W[kh, kw, c, :]. */
+int acx_conv1_pairs_forward(const void* d_obs_pairs, const acx_planes_t* w_perm, int samples, const float* d_bias, float alpha,
+                            const acx_planes_t* out, int num_pairs, const int* pair_a, const int* pair_b, void* stream);
 /* impl: 0 = tcgen05 tensor-core kernel (the product path), 1 = SIMT fp32 reference kernel on the
  * same planes (debug/validation only, never selected automatically). */
 int acx_gemm(const acx_gemm_t* g, int impl, void* stream);

@@ -96,3 +96,19 @@ def test_conv1_from_the_row_pair_copy(samples):
     want = P.t() @ sum(p.double()[:, :32] for p in gp) / 255.0
     assert float((got.double() - want).abs().max()) <= 2e-6 * float(want.abs().max())
     assert _lib.load().acx_debug_tc_error() == 0
+
+
+@pytest.mark.parametrize("samples", [2, 33])
+def test_conv1_forward_on_the_row_pair_copy(samples):
+    """acx_conv1_pairs_forward (envs/atari/model.py:173-179: 8x8 / 4 convolution of obs / 255, bias, ReLU) against conv2d in fp64."""
+    from actorcritic_b200 import ops
+    gen = torch.Generator(device="cuda").manual_seed(samples)
+    obs = torch.randint(0, 256, (samples, 84, 84, 4), dtype=torch.uint8, device="cuda", generator=gen)
+    w = torch.randn((256, 32), device="cuda", generator=gen) * 0.05            # rows (kh, kw, c): the HWIO kernel flattened
+    bias = torch.randn(32, device="cuda", generator=gen) * 0.1
+    outs = ops.conv1_pairs_forward(ops.obs_pairs(obs), w, bias, w_planes=3, pairs=[(0, 0), (0, 1), (0, 2)])
+    got = sum(p.double() for p in outs)
+    wk = w.double().view(8, 8, 4, 32).permute(3, 2, 0, 1)                     # OIHW
+    want = torch.nn.functional.conv2d(obs.double().permute(0, 3, 1, 2) / 255.0, wk, bias.double(), stride=4).clamp_min(0)
+    want = want.permute(0, 2, 3, 1).reshape(samples * 400, 32)
+    assert float((got - want).abs().max()) <= 3e-5 * float(want.abs().max())   # two bf16 output planes: 2^-16
