@@ -248,6 +248,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
               for (int pr = 0; pr < 6; ++pr)
                 if (pr < npairs)
                   umma_bf16_x4(d_tmem, a_desc0 + (uint64_t)a_off[pr], b_desc0 + (uint64_t)b_off[pr], 2u, 2u, idesc, pr ? 1u : acc_flag);
+            } else if (nsteps == 4) {   // two 32-wide sub-tiles: the four steps of a pair as one block, A offsets per step
+#pragma unroll
+              for (int pr = 0; pr < 6; ++pr)
+                if (pr < npairs)
+                  umma_bf16_x4_steps(d_tmem, a_desc0 + (uint64_t)a_off[pr], b_desc0 + (uint64_t)b_off[pr], a_step[1], a_step[2], a_step[3], idesc,
+                                     pr ? 1u : acc_flag);
             } else {
 #pragma unroll
               for (int pr = 0; pr < 6; ++pr) {

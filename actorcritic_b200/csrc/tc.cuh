@@ -103,6 +103,31 @@ __device__ __forceinline__ void umma_bf16_x4(uint32_t tmem_d, uint64_t adesc, ui
       "l"(adesc), "l"(bdesc), "r"(astep16), "r"(bstep16), "r"(idesc), "r"(acc)
       : "memory");
 }
+// the same with explicit A offsets of steps 1..3 (16-byte units, relative to step 0): a k-block made of two 32-wide, 64-byte-swizzled
+// sub-tiles (conv3's input gradient at 32 channels) steps 0, +2 inside the first sub-tile and sub, sub + 2 inside the second
+__device__ __forceinline__ void umma_bf16_x4_steps(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                   uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db, t;\n\t"
+      "setp.ne.b32 p, %7, 0;\n\t"
+      "setp.eq.b32 q, %6, %6;\n\t"
+      "mov.b64 db, %2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, db, %6, p;\n\t"
+      "cvt.u64.u32 t, %3;\n\t"
+      "add.u64 da, %1, t;\n\t"
+      "add.u64 db, db, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %6, q;\n\t"
+      "cvt.u64.u32 t, %4;\n\t"
+      "add.u64 da, %1, t;\n\t"
+      "add.u64 db, db, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %6, q;\n\t"
+      "cvt.u64.u32 t, %5;\n\t"
+      "add.u64 da, %1, t;\n\t"
+      "add.u64 db, db, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %6, q;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(a1), "r"(a2), "r"(a3), "r"(idesc), "r"(acc)
+      : "memory");
+}
 // ... and all plane pairs of a k-block in one statement (2 or 3 pairs: the shapes the learner runs)
 __device__ __forceinline__ void umma_bf16_x4_pairs2(uint32_t tmem_d, uint64_t a0, uint64_t b0, uint32_t astep16, uint32_t bstep16,
                                                     uint32_t idesc, uint32_t acc, uint32_t oa0, uint32_t ob0, uint32_t oa1, uint32_t ob1) {
