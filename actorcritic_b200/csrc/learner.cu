@@ -702,7 +702,7 @@ static void mark(acx_learner* l, int k, cudaStream_t st) {
     if (_r) return _r;       \
   } while (0)
 
-static int refresh_weight_planes(acx_learner* l, cudaStream_t st) {
+static int refresh_weight_planes(acx_learner* l, cudaStream_t st, bool on_lanes = false) {
   const float* w[4];
   int kr[4], cc[4], ldt[4], ldn[4];
   bf16* t[4][3];
@@ -719,13 +719,25 @@ static int refresh_weight_planes(acx_learner* l, cudaStream_t st) {
       n[i][q] = i > 0 ? l->wN[i].p[q] : nullptr;   // conv1 has no input gradient
     }
   }
-  ACX_TRY(weight_planes(w, kr, cc, t, ldt, n, ldn, 4, st, l->gather ? 1 : 0));   // gather: conv1's W^T columns in the row-pair copy's order
+  // the three launches read the parameters and write disjoint planes: at the end of phase 2 (the tail of the update's critical
+  // path) the two input-gradient operands go to side lanes next to the main one
+  const Lane side[2] = {lane_of(l, 1, st), lane_of(l, 3, st)};
+  const bool fork = on_lanes && l->lanes > 1 && !l->profiling && st != nullptr;
   for (int i = 1; i <= 2; ++i)
     if (l->conv_tc[i]) {
       const Layer& L = l->L[i];
       const ConvGeom g = {L.hw_in, L.cin, L.k, L.s, L.hw_out, L.C};
-      ACX_TRY(conv_dgrad_weight_planes(l->params + L.off, g, l->wD[i], st));
+      const Lane& ln = side[i - 1];
+      if (fork && ln.index != 0) {
+        ACX_TRY(fork_lane(l, st, ln));
+        ACX_TRY(conv_dgrad_weight_planes(l->params + L.off, g, l->wD[i], ln.st));
+      } else {
+        ACX_TRY(conv_dgrad_weight_planes(l->params + L.off, g, l->wD[i], st));
+      }
     }
+  ACX_TRY(weight_planes(w, kr, cc, t, ldt, n, ldn, 4, st, l->gather ? 1 : 0));   // gather: conv1's W^T columns in the row-pair copy's order
+  if (fork)
+    for (int i = 0; i < 2; ++i) ACX_TRY(join_lane(l, side[i], st));
   return 0;
 }
 
@@ -1228,7 +1240,7 @@ static int issue_phase2(acx_learner* l, const Plan2& p, cudaStream_t st) {
     ACX_TRY(kfac_step(l->params, l->velocity, l->precon, P, l->dot_partials, kDotPartials, l->sched, c.momentum,
                       c.norm_constraint, l->scalars + 4, st));
   }
-  if (p.refresh) ACX_TRY(refresh_weight_planes(l, st));
+  if (p.refresh) ACX_TRY(refresh_weight_planes(l, st, true));
   ACX_TRY(join_lane(l, ema_ln, st));
   if (!p.kfac_apply) mark(l, 8, st);
   mark(l, 9, st);
