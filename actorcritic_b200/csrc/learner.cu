@@ -1176,11 +1176,15 @@ static int issue_phase2(acx_learner* l, const Plan2& p, cudaStream_t st) {
     else
       ACX_TRY(scale_f32(l->bucket, l->bucket_floats, 1.0f / (float)c.world_size, st));
   }
-  ACX_CUDA(cudaMemcpyAsync(l->scalars, l->bscalars, 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  // K-FAC updates: the loss scalars' copy and the schedule transition are needed only by the inverse refresh (debias factor) and
+  // by the parameter step (learning rate) - they run on a side lane next to the preconditioning instead of ahead of it
+  Lane sched_ln = lane_of(l, (p.a2c || p.cold) ? 0 : 3, st);
+  ACX_TRY(fork_lane(l, st, sched_ln));
+  ACX_CUDA(cudaMemcpyAsync(l->scalars, l->bscalars, 4 * sizeof(float), cudaMemcpyDeviceToDevice, sched_ln.st));
   // one launch for the whole schedule transition (kfac_utils.py:38-53): lr from the step the update starts with, then
   // global_step += (cold ? 2 : 1) [A2C: 1], covariance counter += (cold ? 0 : 1)
   ACX_TRY(sched_step(l->sched, c.lr_start, c.lr_end, c.lr_decay_steps, l->scalars + 7, p.a2c ? 1 : (p.cold ? 2 : 1),
-                     (p.a2c || p.cold) ? 0 : 1, c.cov_ema_decay, zero_debias_on(c) ? 1 : 0, st));
+                     (p.a2c || p.cold) ? 0 : 1, c.cov_ema_decay, zero_debias_on(c) ? 1 : 0, sched_ln.st));
   if (p.a2c) {   // ClipGlobalNorm(RMSProp)   a2c_acktr.py:250-251
     ACX_TRY(dot_partial(l->grads, l->grads, P, l->dot_partials, kDotPartials, st));
     ACX_TRY(rmsprop_clip_step(l->params, l->accum, l->grads, P, l->dot_partials, kDotPartials, l->sched, c.rms_decay,
@@ -1206,6 +1210,7 @@ static int issue_phase2(acx_learner* l, const Plan2& p, cudaStream_t st) {
     ACX_TRY(ema_update(l->sums, l->stats, l->factor_floats, c.cov_ema_decay, 1.0f, ema_ln.st));
   }
   mark(l, 6, st);
+  if (p.invert) ACX_TRY(join_lane(l, sched_ln, st));   // the refresh reads the zero-debias factor of the new covariance count
   if (p.invert) {
     // ACX_INV_IMPL: 2 (default) = fp32, all factor tiles resident in shared memory, one persistent kernel (kfac_inv.cu);
     // 1 = the fp64 Gauss-Jordan as one persistent kernel; 0 = the round-1 fp64 chain of ~150 launches (also the fallback when
@@ -1236,11 +1241,13 @@ static int issue_phase2(acx_learner* l, const Plan2& p, cudaStream_t st) {
   if (p.kfac_apply) {
     ACX_TRY(precondition(l, st));
     mark(l, 8, st);
+    ACX_TRY(join_lane(l, sched_ln, st));             // the step reads the learning rate
     ACX_TRY(dot_partial(l->grads, l->precon, P, l->dot_partials, kDotPartials, st));
     ACX_TRY(kfac_step(l->params, l->velocity, l->precon, P, l->dot_partials, kDotPartials, l->sched, c.momentum,
                       c.norm_constraint, l->scalars + 4, st));
   }
   if (p.refresh) ACX_TRY(refresh_weight_planes(l, st, true));
+  ACX_TRY(join_lane(l, sched_ln, st));
   ACX_TRY(join_lane(l, ema_ln, st));
   if (!p.kfac_apply) mark(l, 8, st);
   mark(l, 9, st);
