@@ -111,6 +111,7 @@ SIGNATURES = {
     "acx_learner_phase1": (ctypes.c_int, [_P, _P, _P, _P]),
     "acx_learner_phase2": (ctypes.c_int, [_P, _P]),
     "acx_learner_wait_input_factors": (ctypes.c_int, [_P, _P]),
+    "acx_learner_update": (ctypes.c_int, [_P, _P, _P, _P]),
     "acx_learner_update_plan": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "acx_learner_set_external_ema": (ctypes.c_int, [_P, ctypes.c_int]),
     "acx_peer_export": (ctypes.c_int, [_P, _P, ctypes.POINTER(ctypes.c_ulonglong)]),

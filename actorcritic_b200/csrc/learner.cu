@@ -1621,6 +1621,31 @@ int acx_learner_set_loss_weights(acx_learner_t* l, float policy_weight, float va
   return 0;
 }
 
+int acx_learner_update(acx_learner_t* l, const int32_t* d_fisher_labels, const float* d_fisher_eps, void* stream) {
+  ACX_CHECK(l, "null learner");
+  ACX_CHECK((d_fisher_labels == nullptr) == (d_fisher_eps == nullptr), "inject both Fisher labels and eps, or neither");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // both phases as ONE captured graph per schedule variant (nothing has to happen between them unless the caller runs a
+  // collective there): one graph launch per update
+  const bool fisher = l->cfg.acktr != 0 && l->gs >= l->cfg.num_cold_updates;
+  l->deferred = fisher ? resolve_deferred(l) : 0;
+  l->defer_request = 0;
+  const Plan2 p = plan_phase2(l);
+  if (p.a2c || p.cold) l->deferred = 0;
+  const int k1 = (fisher ? 1 : 0) | (l->deferred << 1) | (l->loss_variant << 8);
+  const int k2 = p.key() | (l->external_ema ? 1 << 10 : 0) | (l->peer.world > 1 ? 1 << 11 : 0);
+  GraphKey key = {4, k1 | (k2 << 16), d_fisher_labels, d_fisher_eps};
+  const int r = run_cached(l, key, st, [&]() {
+    const int r1 = issue_phase1(l, d_fisher_labels, d_fisher_eps, st);
+    return r1 ? r1 : issue_phase2(l, p, st);
+  });
+  l->a_ready_valid = false;
+  if (r) return r;
+  l->deferred = 0;
+  advance_phase2(l, p);
+  return 0;
+}
+
 int acx_learner_update_plan(const acx_learner_t* l, int* has_factors, int* will_invert) {
   ACX_CHECK(l, "null learner");
   const Plan2 p = plan_phase2(l);

@@ -590,9 +590,16 @@ class Engine:
                             batch["terminals"])
         # ACX_DEFER_FACTORS=<mask>: opt-in (measured slower: the deferred SYRKs are persistent CTAs that hold an SM's whole
         # shared memory, so phase 2's small kernels queue behind them instead of running beside them)
-        self.phase1(fisher_labels, fisher_eps, defer_factors="ACX_DEFER_FACTORS" in os.environ)
-        self.allreduce(group)
-        self.phase2()
+        if self.config.world_size == 1 and "ACX_DEFER_FACTORS" not in os.environ and os.environ.get("ACX_ONE_GRAPH", "1") != "0":
+            # nothing happens between the phases on a single GPU: both as one captured graph (acx_learner_update)
+            fl = ctypes.c_void_p(fisher_labels.data_ptr()) if fisher_labels is not None else None
+            fe = ctypes.c_void_p(fisher_eps.data_ptr()) if fisher_eps is not None else None
+            with self.on_stream():
+                _lib.check(self.lib.acx_learner_update(self._h, fl, fe, self._stream()))
+        else:
+            self.phase1(fisher_labels, fisher_eps, defer_factors="ACX_DEFER_FACTORS" in os.environ)
+            self.allreduce(group)
+            self.phase2()
         if not fetch:
             return None
         if fetch == "async":

@@ -295,6 +295,9 @@ int acx_learner_phase2(acx_learner_t* l, void* stream);
  * acx_learner_phase1 has been called (i.e. enqueued) this makes `stream` wait for that prefix only, so the caller can
  * all-reduce it on `stream` while the backward pass still runs; returns -1 (and makes nobody wait) when the last phase 1
  * computed no factor statistics or ran serially - then the prefix is complete when phase 1 is. */
+/* phase 1 + phase 2 back to back as ONE captured CUDA graph per schedule variant (one graph launch per update): for callers
+ * that run nothing between the phases - a single GPU, or peers set with acx_learner_set_peers and no external EMA. */
+int acx_learner_update(acx_learner_t* l, const int32_t* d_fisher_labels, const float* d_fisher_eps, void* stream);
 int acx_learner_wait_input_factors(acx_learner_t* l, void* stream);
 /* Split exchange for data-parallel learners.  Phase 2 reads only [grads | scalars] of the reduce bucket (and the stored
  * inverses); the factor statistics [A | G] are read by the EMA alone, whose result nothing needs before the next inverse
