@@ -240,9 +240,28 @@ __global__ void __launch_bounds__(1024) loss_grad_kernel(const float* __restrict
                                                         const float* __restrict__ fisher_eps, uint64_t seed,
                                                         const Sched* __restrict__ sched, int n_rows, int num_actions, float beta, float value_weight,
                                                         float policy_weight, float* __restrict__ dheads, float* __restrict__ scalars,
-                                                        int want_fisher) {
+                                                        int want_fisher, const float* __restrict__ rewards,
+                                                        const uint8_t* __restrict__ terminals, const float* __restrict__ bootstrap,
+                                                        float gamma, int num_envs, int num_steps, float* __restrict__ targets_out,
+                                                        float* __restrict__ adv_out) {
   pdl_enter();
   __shared__ float red[3][32];
+  if (rewards) {
+    // K-RET inside this (single-CTA) kernel: the n-step returns of objectives.py:178-214 - the same fp32 recursion as
+    // returns_kernel, one thread per environment - are written to `targets` before anybody reads them (one launch less on
+    // the critical path between the forward and the backward pass)
+    for (int e = threadIdx.x; e < num_envs; e += blockDim.x) {
+      float run = bootstrap[e];
+      const size_t base = (size_t)e * num_steps;
+      for (int t = num_steps - 1; t >= 0; --t) {
+        if (terminals[base + t]) run = 0.0f;
+        run = __fadd_rn(rewards[base + t], __fmul_rn(gamma, run));
+        targets_out[base + t] = run;
+        if (adv_out) adv_out[base + t] = run - values[base + t];
+      }
+    }
+    __syncthreads();
+  }
   const uint64_t step = sched ? sched->gs : 0ull;
   float s_obj = 0.f, s_ent = 0.f, s_val = 0.f;
   const float inv_n = 1.0f / (float)n_rows;
@@ -260,7 +279,7 @@ __global__ void __launch_bounds__(1024) loss_grad_kernel(const float* __restrict
       ent -= expf(lp) * lp;
     }
     const int act = actions[r];
-    const float v = values[r], tg = targets[r];
+    const float v = values[r], tg = rewards ? targets_out[r] : targets[r];
     const float adv = tg - v;
     const float logp_a = z[act] - lse;
     s_obj += adv * logp_a;
@@ -809,13 +828,48 @@ int heads_fwd(const Planes& act4, const float* vpol, const float* vval, int rows
   ACX_PDL_LAUNCH(heads_fwd_kernel, ceil_div(rows, 8), 256, 0, st, act4, vpol, vval, rows, num_actions, logits, values);
   return 0;
 }
+// K-RET + K-LOSS in one launch: returns / advantages of the rollout (rewards, terminals [E, T]; bootstrap [E]) into
+// targets_out / adv_out, then the A2C loss and its gradient with respect to the heads
+struct ReturnsIn {
+  const float* rewards = nullptr;
+  const uint8_t* terminals = nullptr;
+  const float* bootstrap = nullptr;
+  float gamma = 0.0f;
+  int num_envs = 0, num_steps = 0;
+  float* targets_out = nullptr;
+  float* adv_out = nullptr;
+};
+static int loss_grad_impl(const float* logits, const float* values, const uint8_t* actions, const float* targets, const int32_t* fl,
+                          const float* fe, uint64_t seed, const Sched* sched, int n_rows, int num_actions, float beta, float vw,
+                          float* dheads, float* scalars, int want_fisher, cudaStream_t st, float pw, const ReturnsIn& rt) {
+  // one row per thread up to 1024 rows (the serial exp / log chains of a row are the kernel's latency)
+  const int threads = n_rows >= 1024 ? 1024 : (n_rows + 31) / 32 * 32;
+  ACX_PDL_LAUNCH(loss_grad_kernel, 1, threads, 0, st, logits, values, actions, targets, fl, fe, seed, sched, n_rows, num_actions, beta, vw, pw,
+                 dheads, scalars, want_fisher, rt.rewards, rt.terminals, rt.bootstrap, rt.gamma, rt.num_envs, rt.num_steps, rt.targets_out,
+                 rt.adv_out);
+  return 0;
+}
 int loss_grad(const float* logits, const float* values, const uint8_t* actions, const float* targets, const int32_t* fl,
               const float* fe, uint64_t seed, const Sched* sched, int n_rows, int num_actions, float beta, float vw, float* dheads,
               float* scalars, int want_fisher, cudaStream_t st, float pw) {
-  // one row per thread up to 1024 rows (the serial exp / log chains of a row are the kernel's latency)
-  const int threads = n_rows >= 1024 ? 1024 : (n_rows + 31) / 32 * 32;
-  ACX_PDL_LAUNCH(loss_grad_kernel, 1, threads, 0, st, logits, values, actions, targets, fl, fe, seed, sched, n_rows, num_actions, beta, vw, pw, dheads, scalars, want_fisher);
-  return 0;
+  return loss_grad_impl(logits, values, actions, targets, fl, fe, seed, sched, n_rows, num_actions, beta, vw, dheads, scalars, want_fisher,
+                        st, pw, ReturnsIn());
+}
+int returns_loss_grad(const float* rewards, const uint8_t* terminals, const float* bootstrap, float gamma, int num_envs, int num_steps,
+                      float* targets, float* adv, const float* logits, const float* values, const uint8_t* actions, const int32_t* fl,
+                      const float* fe, uint64_t seed, const Sched* sched, int num_actions, float beta, float vw, float* dheads,
+                      float* scalars, int want_fisher, cudaStream_t st, float pw) {
+  ReturnsIn rt;
+  rt.rewards = rewards;
+  rt.terminals = terminals;
+  rt.bootstrap = bootstrap;
+  rt.gamma = gamma;
+  rt.num_envs = num_envs;
+  rt.num_steps = num_steps;
+  rt.targets_out = targets;
+  rt.adv_out = adv;
+  return loss_grad_impl(logits, values, actions, targets, fl, fe, seed, sched, num_envs * num_steps, num_actions, beta, vw, dheads, scalars,
+                        want_fisher, st, pw, rt);
 }
 int heads_bwd(const float* dheads, const float* vpol, const float* vval, const Planes& act4, int n_rows, int rows_bwd,
               int num_actions, const Planes& dpre4, float* gpol, float* gval, cudaStream_t st) {

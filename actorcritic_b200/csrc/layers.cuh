@@ -35,6 +35,10 @@ int heads_fwd(const Planes& act4, const float* vpol, const float* vval, int rows
 int loss_grad(const float* logits, const float* values, const uint8_t* actions, const float* targets, const int32_t* fl,
               const float* fe, uint64_t seed, const Sched* sched, int n_rows, int num_actions, float beta, float vw, float* dheads,
               float* scalars, int want_fisher, cudaStream_t st, float pw = 1.0f);
+int returns_loss_grad(const float* rewards, const uint8_t* terminals, const float* bootstrap, float gamma, int num_envs, int num_steps,
+                      float* targets, float* adv, const float* logits, const float* values, const uint8_t* actions, const int32_t* fl,
+                      const float* fe, uint64_t seed, const Sched* sched, int num_actions, float beta, float vw, float* dheads,
+                      float* scalars, int want_fisher, cudaStream_t st, float pw = 1.0f);
 int heads_bwd(const float* dheads, const float* vpol, const float* vval, const Planes& act4, int n_rows, int rows_bwd,
               int num_actions, const Planes& dpre4, float* gpol, float* gval, cudaStream_t st);
 int heads_gfactor(const float* dheads_fisher, int n_rows, int num_actions, float* g_pol, float* g_val, cudaStream_t st);

@@ -1017,9 +1017,10 @@ static int issue_phase1(acx_learner* l, const int32_t* fisher_labels, const floa
   }
   mark(l, 1, st);
   // targets use the bootstrap tower's values = rows [N, N+E) (envs/atari/model.py:116,126-127)
-  ACX_TRY(returns_launch(l->rewards, l->terminals, l->values, l->values + N, l->cfg.gamma, E, T, l->targets, l->adv, st));
-  ACX_TRY(loss_grad(l->logits, l->values, l->actions, l->targets, fisher_labels, fisher_eps, l->cfg.seed, l->sched, N, A,
-                    l->cfg.entropy_beta, l->value_weight, l->dheads, l->bscalars, fisher ? 1 : 0, st, l->policy_weight));
+  // (K-RET runs inside the loss kernel: one launch)
+  ACX_TRY(returns_loss_grad(l->rewards, l->terminals, l->values + N, l->cfg.gamma, E, T, l->targets, l->adv, l->logits, l->values,
+                            l->actions, fisher_labels, fisher_eps, l->cfg.seed, l->sched, A, l->cfg.entropy_beta, l->value_weight,
+                            l->dheads, l->bscalars, fisher ? 1 : 0, st, l->policy_weight));
   ACX_TRY(heads_bwd(l->dheads, l->params + l->L[4].off, l->params + l->L[5].off, l->act4, N, RB, A, l->dpre4,
                     l->grads + l->L[4].off, l->grads + l->L[5].off, st));
   const Planes flat3 = with_ld(l->act3, 49 * c3);
