@@ -292,12 +292,9 @@ def run_native(args, rank, world, local_rank):
             # enqueued, so the host never idles the GPU; every handle is resolved inside the timed region)
             e.stage_batch(host[(i + 1) % len(host)])
             return e.update(staged=True, fetch="async" if fetch else False)
-        b = src[i % len(src)]
-        e.load_batch(b["observations"], b["bootstrap_observations"], b["actions"], b["rewards"], b["terminals"])
-        e.phase1()
-        e.allreduce()
-        e.phase2()
-        return e.fetch_scalars() if fetch else None
+        # device-resident inputs: the same public call (on one GPU both phases replay as one CUDA graph; data parallel:
+        # phase 1, the exchange, phase 2)
+        return e.update(src[i % len(src)], fetch=bool(fetch))
 
     # prime: post-cold state, then enough updates to pass TWO inverse refreshes (not part of warm-up or timing): the
     # library captures the CUDA graph of a schedule variant on its second use, so after 23 updates (refreshes at
