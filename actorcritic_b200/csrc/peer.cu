@@ -209,8 +209,10 @@ int peer_allreduce(const PeerState& ps, size_t region_offset_bytes, size_t flags
   a.scale = scale;
   const char* e = getenv("ACX_PEER_TWO_SHOT");   // (read per launch: tests switch it between engines)
   a.one_shot = (ps.world == 2 && !(e && atoi(e))) ? 1 : 0;
-  int ctas = PEER_CTAS;
-  if (const char* c = getenv("ACX_PEER_CTAS")) {   // tuning knob (every rank must use the same value)
+  // the exchange phase 2 waits for takes every SM; the one that runs under phase 2 on a side stream (channel 1) only a few,
+  // so that its spinning CTAs leave the SMs to phase 2.  ACX_PEER_CTAS / ACX_PEER_SIDE_CTAS: tuning knobs (the same on every rank)
+  int ctas = channel == 0 ? PEER_CTAS : 24;
+  if (const char* c = getenv(channel == 0 ? "ACX_PEER_CTAS" : "ACX_PEER_SIDE_CTAS")) {
     const int v = atoi(c);
     if (v >= 1 && v <= PEER_CTAS) ctas = v;
   }
