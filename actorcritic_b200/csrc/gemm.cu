@@ -504,8 +504,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
                 uint64_t ad = a_desc0 + (uint64_t)((uint32_t)(p.pair_a[pr] * panel_tile_bytes + ti * a_tile_bytes) >> 4);
                 uint64_t bd = a_desc0 + (uint64_t)((uint32_t)(p.pair_b[pr] * panel_tile_bytes + tj * a_tile_bytes) >> 4);
                 uint32_t flag = (kb > kb0 || pr > 0) ? 1u : 0u;
-                if (ksteps == 4) {
+                if (ksteps == 4 || ksteps == 8) {
                   umma_bf16_x4(d_tmem + (uint32_t)(sub * 128), ad, bd, (uint32_t)kstep16, (uint32_t)kstep16, idesc, flag);
+                  if (ksteps == 8)
+                    umma_bf16_x4(d_tmem + (uint32_t)(sub * 128), ad + 4 * kstep16, bd + 4 * kstep16, (uint32_t)kstep16, (uint32_t)kstep16, idesc, 1u);
                   continue;
                 }
                 for (int kk = 0; kk < ksteps; ++kk) {
@@ -533,6 +535,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
                   umma_bf16_x4(d_tmem, a_desc0 + (uint64_t)a_off[pr], b_desc0 + (uint64_t)(diag ? b_off_d[pr] : b_off[pr]), (uint32_t)kstep16,
                                (uint32_t)kstep16, idesc, pr ? 1u : acc_flag);
             }
+          } else if (ksteps == 8) {
+            // 128-deep k-block: two groups of four steps per plane pair
+#pragma unroll
+            for (int pr = 0; pr < 6; ++pr)
+              if (pr < npairs) {
+                const uint64_t ad = a_desc0 + (uint64_t)a_off[pr], bd = b_desc0 + (uint64_t)(diag ? b_off_d[pr] : b_off[pr]);
+                umma_bf16_x4(d_tmem, ad, bd, (uint32_t)kstep16, (uint32_t)kstep16, idesc, pr ? 1u : acc_flag);
+                umma_bf16_x4(d_tmem, ad + 4 * kstep16, bd + 4 * kstep16, (uint32_t)kstep16, (uint32_t)kstep16, idesc, 1u);
+              }
           } else {
             for (int pr = 0; pr < p.num_pairs; ++pr) {
               uint64_t ad = a_desc0 + (uint64_t)((uint32_t)(p.pair_a[pr] * a_tile_bytes) >> 4);
@@ -1324,6 +1335,15 @@ static int fuse_reduce_enabled() {   // ACX_GEMM_FUSE_REDUCE / acx_debug_set_fus
 
 constexpr int SMEM_LIMIT = 232448;                       // 227 KB per CTA on sm_100
 constexpr int SMEM_FIXED = EPI_BYTES + 256;              // epilogue staging + barriers (the base is 1024-aligned)
+static int bk128_min_stages() {   // ACX_GEMM_BK128_STAGES: ring depth from which 128-deep k-blocks are chosen automatically (0 = never)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ACX_GEMM_BK128_STAGES");
+    v = e ? atoi(e) : 2;   // measured at 32 x 20: never 0.689, >= 3 stages 0.682, >= 2 stages 0.674 ms/update
+    if (v <= 0) v = 1000;
+  }
+  return v;
+}
 static int force_bk() {                                  // tuning knob: ACX_GEMM_BK=32 / 64 overrides the automatic k-block depth
   static int v = -1;
   if (v < 0) {
@@ -1368,6 +1388,13 @@ static void plan_tc(const acx_gemm_t* g, TcPlan* pl) {
   // Measured at 32 x 20 (ACX_GEMM_BK=32): halving the k-block to get 4-5 ring stages instead of 2 for the 3 + 3 plane GEMMs
   // is SLOWER (1.26 vs 1.16 ms/update): twice the stage hand-offs, and 64-byte swizzle rows; so 64 unless asked.
   pl->bk = (force_bk() == 32 && !g->a_gather) ? 32 : BK;
+  // 128-deep k-blocks for MN-major products whose stages are small (the deep-split conv weight gradients and output-factor
+  // SYRKs: 8 MMAs per 64-deep k-block): the hand-off between producer, issuing thread and tensor pipe costs ~250 cycles per
+  // k-block whatever its depth (tools/micro/mma_rate3.cu).  ACX_GEMM_BK=128 forces it wherever two stages fit, =64 forbids it.
+  if (g->trans_a && g->a_patch_u8 == nullptr && force_bk() != 64 && force_bk() != 32) {
+    const int st128 = stages_for(128);
+    if (force_bk() == 128 ? st128 >= 2 : st128 >= bk128_min_stages()) pl->bk = 128;
+  }
   pl->stages = stages_for(pl->bk);
   pl->kb_total = ceil_div(g->k, pl->bk);
   pl->g_bx = pl->g_by = pl->g_ts = pl->g_nx = pl->g_cells = 0;
@@ -1377,17 +1404,17 @@ static void plan_tc(const acx_gemm_t* g, TcPlan* pl) {
     const acx_gather_t* ga = g->a_gather;
     int bx = 1, by = 1;
     while (bx < 8 && ga->gx % (2 * bx) == 0) bx *= 2;
-    while (bx * by < 64 && ga->gy % (2 * by) == 0) by *= 2;
+    while (bx * by < pl->bk && ga->gy % (2 * by) == 0) by *= 2;
     if (const char* e = getenv("ACX_GATHER_CUT")) {   // triage: "bx,by" (powers of two; boxes that overhang the grid read zero rows)
       int a = 0, b = 0;
-      if (sscanf(e, "%d,%d", &a, &b) == 2 && a >= 1 && b >= 1 && a * b <= 64 && (a & (a - 1)) == 0 && (b & (b - 1)) == 0) {
+      if (sscanf(e, "%d,%d", &a, &b) == 2 && a >= 1 && b >= 1 && a * b <= pl->bk && (a & (a - 1)) == 0 && (b & (b - 1)) == 0) {
         bx = a;
         by = b;
       }
     }
     pl->g_bx = bx;
     pl->g_by = by;
-    pl->g_ts = 64 / (bx * by);
+    pl->g_ts = pl->bk / (bx * by);
     pl->g_nx = ceil_div(ga->gx, bx);
     pl->g_cells = pl->g_nx * ceil_div(ga->gy, by);
     pl->kb_total = pl->g_cells * ceil_div(ga->samples, pl->g_ts);
@@ -1395,7 +1422,7 @@ static void plan_tc(const acx_gemm_t* g, TcPlan* pl) {
   int splits = g->splits;
   if (splits <= 0) {  // auto: about one work item per SM, at least 256 elements of K per split
     splits = 148 / (tiles > 0 ? tiles : 1);
-    int cap = pl->kb_total / (4 * (BK / pl->bk));
+    int cap = (int)((long long)pl->kb_total * pl->bk / 256);   // at least 256 elements of K per split
     if (splits > cap) splits = cap;
     if (splits < 1) splits = 1;
   }

@@ -1,6 +1,7 @@
 """acx_gemm with the A operand generated in the kernel from uint8 observations (a_patch_u8: the conv1 patch matrix is never
 materialised) against the same GEMM on the materialised patch matrix: same bf16 operand values and the same accumulation
-order, so the results must be bit-identical."""
+order in the forward product, so that result must be bit-identical; the MN-major products (weight gradient, input factor)
+split K differently since the materialised operand runs 128-deep k-blocks, so they agree to fp32 summation order."""
 import numpy as np
 import pytest
 import torch
@@ -37,11 +38,11 @@ def test_patch_operand_forward_wgrad_syrk_bit_identical(samples):
     g = ops.split_planes(torch.randn((rows, 32), device="cuda", generator=gen) * 1e-3, 3)
     want, _ = ops.gemm([p1], g, 256, 32, rows, trans=True, pairs=pairs, alpha=1 / 255.0)
     got, _ = ops.gemm(None, g, 256, 32, rows, trans=True, pairs=pairs, alpha=1 / 255.0, a_patch_obs=obs)
-    assert torch.equal(got, want)
+    assert float((got - want).abs().max()) <= 2e-6 * float(want.abs().max())
     # input factor: P1^T P1 (symmetric, panel mode)
     want, _ = ops.gemm([p1], [p1], 256, 256, rows, trans=True, symmetric=True, pairs=[(0, 0)], alpha=1.0 / rows)
     got, _ = ops.gemm(None, None, 256, 256, rows, trans=True, symmetric=True, alpha=1.0 / rows, a_patch_obs=obs)
-    assert torch.equal(got, want)
+    assert float((got - want).abs().max()) <= 2e-6 * float(want.abs().max())
     assert _lib.load().acx_debug_tc_error() == 0
     # and against plain arithmetic (exact integers up to fp32 accumulation)
     ref = (p1.double().t() @ p1.double() / rows).cpu().numpy()
