@@ -620,6 +620,7 @@ static int launch_conv(const CUtensorMap* ta, const CUtensorMap* tb, ConvTcParam
   }
   int grid = std::min(p.num_tiles, conv_num_sms());
   if (g_cta_cap > 0 && grid > g_cta_cap) grid = g_cta_cap;
+  grid = ceil_div(p.num_tiles, ceil_div(p.num_tiles, grid));   // the smallest grid with the same number of rounds: idle SMs go to other lanes
   const int smem = CV_SMEM_FIXED + res_bytes + p.stages * stage_bytes;
   ACX_CUDA(launch_pdl(conv_tc_kernel, dim3(grid), dim3(CV_THREADS), (size_t)smem, st, ta[0], ta[1], ta[2], tb[0], tb[1], tb[2], p));
   acx::count_launch();

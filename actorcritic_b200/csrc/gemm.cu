@@ -1649,6 +1649,7 @@ static int gemm_tc(const acx_gemm_t* g, cudaStream_t st) {
   p.mn_kstep = g_mn_kstep ? g_mn_kstep : 2048u;
   int grid = p.total_work < num_sms() ? p.total_work : num_sms();
   if (g_cta_cap > 0 && grid > g_cta_cap) grid = g_cta_cap;
+  grid = ceil_div(p.total_work, ceil_div(p.total_work, grid));   // the smallest grid with the same number of rounds
   const int smem = SMEM_FIXED + p.stages * stage_bytes;
   int r;
   if (patch)

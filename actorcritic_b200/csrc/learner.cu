@@ -640,10 +640,10 @@ static int lane_cta_cap(const acx_learner* l, int lane_index) {
   if (lane_index != 0) return caps[1];
   if (caps[0] >= 0) return caps[0];
   // Default for K-FAC learners: the persistent grids of the caller's lane (forward, input gradients, conv1 weight gradient,
-  // preconditioning) leave 20 SMs to the factor / weight-gradient lanes, so that their kernels start beside the critical chain
+  // preconditioning) leave 16 SMs to the factor / weight-gradient lanes, so that their kernels start beside the critical chain
   // instead of queueing behind it: 0.674 -> 0.656 ms/update at 32 x 20 (measured 96 / 112 / 120 / 132 / 140 CTAs: 0.671 / 0.660 /
   // 0.656 / 0.656 / 0.657; capping the side lanes instead is slower).  Learners without K-FAC side work keep every SM.
-  return (l->cfg.acktr && l->lanes > 1 && !l->profiling) ? 128 : 0;
+  return (l->cfg.acktr && l->lanes > 1 && !l->profiling) ? 132 : 0;
 }
 
 static ConvGeom geom_of(const Layer& L) { return ConvGeom{L.hw_in, L.cin, L.k, L.s, L.hw_out, L.C}; }
@@ -1431,8 +1431,12 @@ acx_learner_t* acx_learner_create(const acx_learner_config_t* cfg, void* d_arena
     l->conv_fwd_tc[i] = (i == 1 || i == 2) && l->cfg.conv_impl == 0 && l->cfg.gemm_impl == 0 && (l->lanes > 1 || l->gather) && fwd_tc_enabled() &&
                         conv_tc_supported(g, 0);
   }
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);   // (numerically lowest = highest priority)
+  const char* pe = getenv("ACX_SIDE_PRIO");               // 1: side lanes at the lowest stream priority (triage)
+  const int side_prio = (pe && atoi(pe)) ? prio_lo : 0;
   for (int i = 0; i + 1 < l->lanes; ++i)
-    if (cudaStreamCreateWithFlags(&l->side[i], cudaStreamNonBlocking) != cudaSuccess) {
+    if (cudaStreamCreateWithPriority(&l->side[i], cudaStreamNonBlocking, side_prio) != cudaSuccess) {
       acx::set_error("acx_learner_create: cudaStreamCreateWithFlags failed");
       delete l;
       return nullptr;
