@@ -615,7 +615,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) inv_resident_kernel(const __gr
     if (!owner) {
       // look-ahead CTA of job `cta`: D_{p+1}^-1 from D_p^-1 (still in Ds) and the blocks published during step p - 1
       const ResJob& jb = s_jobs[cta];
-      const bool tr = a.trace && p < 128 && cta == 0 && threadIdx.x == 0;
+      const bool tr = a.trace == 1 && p < 128 && cta == 0 && threadIdx.x == 0;
       if (tr) g_res_trace[p * 8 + 5] = clock64();
       // barrier 1 of this step: nothing here depends on the panels, so arrive at once - but the counter is cumulative, so
       // this CTA must not arrive at barrier 2 before barrier 1 has completed (its arrival would be counted for barrier 1)
@@ -675,7 +675,8 @@ __global__ void __launch_bounds__(RES_THREADS, 1) inv_resident_kernel(const __gr
       if (tr) g_res_trace[p * 8 + 7] = clock64();
       continue;
     }
-    const bool tr = a.trace && p < 128 && cta == G - 1 && threadIdx.x == 0;
+    const bool tr = a.trace && p < 128 && cta == (a.trace == 2 ? ND : G - 1) && threadIdx.x == 0;
+    const bool tr2 = tr && a.trace == 2;   // first tile of the step: [5] operands staged [6] tile updated [7] published
     if (tr) g_res_trace[p * 8 + 0] = clock64();
     // panels
     for (int s = 0; s < a.slots; ++s) {
@@ -729,6 +730,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) inv_resident_kernel(const __gr
         return from;
       };
       s = next_active(0);
+      const int first = s;
       OpRegs regs;
       if (s < a.slots) fetch_ops(s_jobs[s_job[s]], p, s_ti[s], s_tj[s], regs);
       while (s < a.slots) {
@@ -738,12 +740,15 @@ __global__ void __launch_bounds__(RES_THREADS, 1) inv_resident_kernel(const __gr
         __syncthreads();                 // the previous tile is done with the staging buffers
         stage_ops(regs, As, Bs, Cs, tj == (p >> 1) && ti != tj);
         __syncthreads();
+        if (tr2 && s == first) g_res_trace[p * 8 + 5] = clock64();
         const int sn = next_active(s + 1);
         if (sn < a.slots && !(a.debug & 2)) fetch_ops(s_jobs[s_job[sn]], p, s_ti[sn], s_tj[sn], regs);
         update_tile(jb, p, ti, tj, T, As, Bs, Cs);
+        if (tr2 && s == first) g_res_trace[p * 8 + 6] = clock64();
         __syncthreads();
         if (sn < a.slots && (a.debug & 2)) fetch_ops(s_jobs[s_job[sn]], p, s_ti[sn], s_tj[sn], regs);
         publish_pair(jb, p + 1, ti, tj, T);    // for the look-ahead of step p + 1
+        if (tr2 && s == first) g_res_trace[p * 8 + 7] = clock64();
         s = sn;
       }
     }

@@ -86,7 +86,9 @@ if os.environ.get("ACX_INV_TRACE"):
         if r[4] == 0:
             break
         if p < 6 or p % 8 == 0 or p > 44:
-            print(p, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[4] - r[0], "||", r[6] - r[5])
+            print(p, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[4] - r[0], "||", r[6] - r[5],
+                  "| first tile: staged +%d, updated +%d, published +%d" % (r[5] - r[2], r[6] - r[5], r[7] - r[6])
+                  if os.environ.get("ACX_INV_TRACE") == "2" else "")
     valid = t[(t[:, 4] > 0)]
     tot = valid[:, 4] - valid[:, 0]
     print("sum cycles", int(tot.sum()), "panels", int((valid[:, 1] - valid[:, 0]).sum()), "bar1", int((valid[:, 2] - valid[:, 1]).sum()),
