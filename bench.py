@@ -311,12 +311,16 @@ def run_native(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(src, fetch, steps, warmup):
+    def timed(src, fetch, steps, warmup, window=False):
+        # window: cudaProfilerStart / Stop around the timed region (ACX_BENCH_NCU=1 with `ncu --profile-from-start off`: the
+        # launch list of exactly the steps `value` is measured on; a number printed by such a run is never a bench value)
         # everything is launched on the engine's stream (events are recorded on that stream too)
         with torch.cuda.stream(e.stream):
             for i in range(warmup):
                 step(i, src, fetch)
             barrier()
+            if window:
+                torch.cuda.profiler.start()
             launches0 = _lib.launch_count()
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
@@ -334,6 +338,8 @@ def run_native(args, rank, world, local_rank):
                 last = pending.result()
             ev1.record()
             barrier()
+            if window:
+                torch.cuda.profiler.stop()
         ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -342,7 +348,7 @@ def run_native(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_dev, launches, _ = timed(resident, False, args.steps, max(3, args.warmup))
+    ms_dev, launches, _ = timed(resident, False, args.steps, max(3, args.warmup), window=bool(os.environ.get("ACX_BENCH_NCU")))
     e.stage_batch(host[0])        # prologue of the double-buffered feed (the copy of step 0's batch)
     ms_e2e, _, scal = timed(host, True, args.steps, 3)
     clocks = sampler.stop() if rank == 0 else None
