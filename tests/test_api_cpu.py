@@ -180,6 +180,38 @@ def test_cabi_exports_every_declared_symbol():
     _lib.load()     # loads and binds every signature without a GPU; no compute call is made here
 
 
+def test_library_is_blackwell_native_and_links_no_vendor_math():
+    """The built library carries sm_100a code whose contraction kernels use tcgen05 (UTCHMMA) fed by TMA (UTMALDG) and read
+    their accumulators from tensor memory (LDTM), the large-batch K-PRE kernel stages frames with bulk copies (UBLKCP), and
+    nothing links cuBLAS / cuDNN / cuSOLVER.  Needs the CUDA binary tools only (no GPU)."""
+    import shutil
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    elf = subprocess.check_output(["cuobjdump", "-lelf", _lib.LIB_PATH], text=True)
+    assert "sm_100a" in elf, elf
+    sass = subprocess.check_output(["cuobjdump", "-sass", _lib.LIB_PATH], text=True)
+    per_kernel, name = {}, None
+    for line in sass.splitlines():
+        m = re.match(r"\s*Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            per_kernel[name] = set()
+        elif name is not None:
+            for op in ("UTCHMMA", "UTMALDG", "LDTM", "UBLKCP"):
+                if op in line:
+                    per_kernel[name].add(op)
+    def ops_of(fragment):
+        found = [v for k, v in per_kernel.items() if fragment in k]
+        assert found, fragment
+        return set().union(*found)
+    assert {"UTCHMMA", "UTMALDG", "LDTM"} <= ops_of("gemm_tc_kernel")
+    assert {"UTCHMMA", "UTMALDG", "LDTM"} <= ops_of("conv_tc_kernel")
+    assert "UBLKCP" in ops_of("preprocess_persistent_kernel")
+    needed = subprocess.check_output(["ldd", _lib.LIB_PATH], text=True)
+    for vendor in ("cublas", "cudnn", "cusolver", "nccl", "torch"):
+        assert vendor not in needed.lower(), needed
+
+
 def test_shard_range_and_batch():
     assert [parallel.shard_range(256, r, 8) for r in (0, 7)] == [(0, 32), (224, 256)]
     with pytest.raises(ValueError):
