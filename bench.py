@@ -66,7 +66,7 @@ def parse():
     ap.add_argument("--precision", type=int, default=0)
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--conv-impl", type=int, default=0, help="0 = gather-form conv dgrad (default), 1 = dgrad GEMM + col2im")
-    ap.add_argument("--lanes", type=int, default=0, help="concurrent lanes inside an update (0 = library default 3, 1 = serial)")
+    ap.add_argument("--lanes", type=int, default=0, help="concurrent lanes inside an update (0 = library default 5, 1 = serial)")
     ap.add_argument("--invert-every", type=int, default=10, help="diagnostic only: the reference uses 10 (a2c_acktr.py:245)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the conv3 = 64 and A2C 16 x 5 extra keys")
