@@ -180,6 +180,18 @@ def test_cabi_exports_every_declared_symbol():
     _lib.load()     # loads and binds every signature without a GPU; no compute call is made here
 
 
+def test_public_header_is_plain_c():
+    """include/acx.h is the drop-in boundary: it must compile as C99 and as C++ on its own (no torch / CUDA types)."""
+    import shutil
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not on PATH")
+    header = os.path.join(ROOT, "include", "acx.h")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", header])
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", header])
+    includes = re.findall(r"#\s*include\s*[<\"]([^>\"]+)", open(header).read())
+    assert set(includes) <= {"stddef.h", "stdint.h"}, includes
+
+
 def test_library_is_blackwell_native_and_links_no_vendor_math():
     """The built library carries sm_100a code whose contraction kernels use tcgen05 (UTCHMMA) fed by TMA (UTMALDG) and read
     their accumulators from tensor memory (LDTM), the large-batch K-PRE kernel stages frames with bulk copies (UBLKCP), and
